@@ -1,0 +1,210 @@
+/*
+ * fabber_cuda.h - thin host <-> device C ABI underneath Vb::DoCalculations
+ *
+ * This is the *inner* drop-in boundary of the B200-native VB path: everything the reference does
+ * between "voxel matrices are in RAM" and "resultMVNs / resultFs are filled"
+ * (reference: inference_vb.cc:360-767, Vb::DoCalculations / DoCalculationsVoxelwise /
+ * DoCalculationsSpatial) is one call into this ABI. Plain C structs, plain pointers and sizes;
+ * no STL, no torch types, no exceptions. Errors are int return codes plus a per-voxel status word.
+ *
+ * All numerics are FP64 (NEWMAT::Real is double in the reference). The time-series itself is FP32
+ * because every reference entry point stores FP32 (fabber_capi.h:128 `const float *data`,
+ * rundata_newimage.cc:100 volume4D<float>) - the FP32 device copy is lossless.
+ *
+ * Layouts (all structure-of-arrays, voxel index fastest => coalesced voxel-per-thread access):
+ *   data        float  [T][N]          row t = volume t (same as the C-API buffer restricted to mask;
+ *                                      reference rundata_array.cc:100-133, Matrix T x Nvox)
+ *   mean        double [P][N]          posterior means, Fabber space
+ *   cov         double [P(P+1)/2][N]   posterior covariance, packed lower triangle by rows
+ *                                      (1,1),(2,1),(2,2),(3,1).. = order of MVNDist::Save, dist_mvn.cc:419-432
+ *   noise       double [NN][N]         white: (b_i, c_i) Gamma scale/shape per phi  -> NN = 2*n_phis
+ *                                      ar1:   (b, c, a1_mean, a2_mean, a_prec11, a_prec21, a_prec22) -> NN = 7
+ *   free_energy double [N]
+ *   iterations  int    [N]             passes through the do{}while body (m_ctx->it, inference_vb.cc:499)
+ *   status      int    [N]             FABBER_VOX_* code of the first numerical failure, 0 if none
+ */
+#ifndef FABBER_CUDA_H
+#define FABBER_CUDA_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FABBER_CUDA_MAX_PARAMS 8
+#define FABBER_CUDA_MAX_PHIS 4
+#define FABBER_CUDA_AR_NOISE_FIELDS 7
+
+/* return codes */
+#define FABBER_CUDA_OK 0
+#define FABBER_CUDA_ERR_INVALID -1      /* bad argument / unsupported configuration */
+#define FABBER_CUDA_ERR_CUDA -2         /* CUDA runtime error (message via fabber_cuda_last_error) */
+#define FABBER_CUDA_ERR_BAD_VOXEL -3    /* numerical failure in a voxel and allow_bad_voxels == 0
+                                           (reference: rethrow at inference_vb.cc:534,542) */
+
+/* forward models with a __device__ Evaluate hook compiled in */
+#define FABBER_MODEL_LINEAR 1 /* fwdmodel_linear.cc:92-96  */
+#define FABBER_MODEL_POLY 2   /* fwdmodel_poly.cc:62-80    */
+#define FABBER_MODEL_EXP 3    /* examples/fwdmodel_exp.cc:65-82 */
+
+/* noise models */
+#define FABBER_NOISE_WHITE 0 /* noisemodel_white.cc */
+#define FABBER_NOISE_AR1 1   /* noisemodel_ar.cc, num-echoes=1, ar1-cross-terms=none */
+
+/* convergence detectors (registry names in setup.cc:49-57) */
+#define FABBER_CONV_MAXITS 0    /* "maxits"        convergence.cc:43  */
+#define FABBER_CONV_FCHANGE 1   /* "pointzeroone"  convergence.cc:86  */
+#define FABBER_CONV_FREDUCE 2   /* "freduce"       convergence.cc:117 */
+#define FABBER_CONV_TRIALMODE 3 /* "trialmode"     convergence.cc:162 */
+#define FABBER_CONV_LM 4        /* "lm"            convergence.cc:278 */
+
+/* per-voxel status codes (first failure wins) */
+#define FABBER_VOX_OK 0
+#define FABBER_VOX_NONFINITE_OFFSET 1   /* fwdmodel_linear.cc:134-140 */
+#define FABBER_VOX_NONFINITE_JACOBIAN 2 /* fwdmodel_linear.cc:174-181 */
+#define FABBER_VOX_NONFINITE_F 3        /* noisemodel_white.cc:445-451 */
+#define FABBER_VOX_SINGULAR 4           /* NEWMAT exception from a matrix inverse */
+#define FABBER_VOX_AR_NEG_VARIANCE 5    /* noisemodel_ar.cc:489-499 */
+#define FABBER_VOX_IGNORED 6            /* spatial mode: voxel dropped by IgnoreVoxel, inference_vb.cc:266 */
+/* OR-ed into the code when the failure happened in Vb::SetupPerVoxelDists (inference_vb.cc:235),
+ * which the reference never catches: always fatal, even with allow_bad_voxels. */
+#define FABBER_VOX_SETUP_FLAG 0x100
+
+typedef struct fabber_cuda_model
+{
+    int id;       /* FABBER_MODEL_* */
+    int n_params; /* P, 1..FABBER_CUDA_MAX_PARAMS */
+    /* LINEAR: design matrix, HOST pointer, row-major [T][P] doubles (copied by the library) */
+    const double *design;
+    /* POLY */
+    int poly_degree; /* P = degree + 1 */
+    /* EXP */
+    int exp_num;   /* number of exponentials, P = 2 * exp_num, params (amp_k, r_k) */
+    double exp_dt; /* sample spacing */
+} fabber_cuda_model;
+
+typedef struct fabber_cuda_param
+{
+    char transform;  /* 'I','L','S','F','A'  (transforms.h:20-24) */
+    char prior_type; /* 'N','I','A','M','m','P','p' (priors.h) */
+    char pad_[6];
+    double prior_mean; /* Fabber space, after Transform::ToFabber (fwdmodel.cc:277) */
+    double prior_prec; /* Fabber space precision = 1/ToFabberVar(var) */
+    double prior_var;  /* Fabber space variance (used by ARD on the first iteration, priors.cc:164) */
+    double post_mean;  /* MODEL space default initial posterior mean (fwdmodel.cc:302) */
+    double post_var;   /* MODEL space default initial posterior variance (fwdmodel.cc:304) */
+} fabber_cuda_param;
+
+typedef struct fabber_cuda_vb_problem
+{
+    int n_voxels; /* N */
+    int n_times;  /* T */
+    fabber_cuda_model model;
+    fabber_cuda_param params[FABBER_CUDA_MAX_PARAMS];
+
+    /* noise */
+    int noise_type; /* FABBER_NOISE_* */
+    int n_phis;     /* white: number of distinct phis in noise-pattern (<= FABBER_CUDA_MAX_PHIS) */
+    const unsigned char *phi_pattern; /* HOST [T]: 0-based phi index per time point, NULL = all 0 */
+    const unsigned char *time_masked; /* HOST [T]: 1 = masked time point (mt<n>), NULL = none */
+    double noise_prior_b[FABBER_CUDA_MAX_PHIS]; /* Gamma scale of prior      (noisemodel_white.cc:144) */
+    double noise_prior_c[FABBER_CUDA_MAX_PHIS]; /* Gamma shape of prior */
+    double noise_post_b[FABBER_CUDA_MAX_PHIS];  /* initial posterior         (noisemodel_white.cc:148) */
+    double noise_post_c[FABBER_CUDA_MAX_PHIS];
+    double locked_noise_stdev; /* <= 0: off (noisemodel_white.cc:265) */
+    double ar_alpha_prior_prec; /* AR1: prior/initial precision of alpha (1e-4, noisemodel_ar.cc:393) */
+
+    /* convergence */
+    int conv_type; /* FABBER_CONV_* */
+    int max_iterations;
+    double fchange; /* min-fchange (fchange/freduce/trialmode) or max-fchange (lm) */
+    int max_trials;
+    int need_f; /* compute free energy (m_needF, inference_vb.cc:242) */
+    int f_history_len; /* rows available in buffers.f_history (0 = not recorded) */
+    int allow_bad_voxels;
+
+    /* spatial mode only (inference_vb.cc:578, priors.cc:183-488) */
+    int spatial_dims;
+    double spatial_speed; /* -1 = unlimited */
+    double spatial_q1, spatial_q2;
+    int update_first_iter;
+    int nx, ny, nz; /* bounding grid of the coords, used for neighbour search */
+} fabber_cuda_vb_problem;
+
+typedef struct fabber_cuda_vb_buffers
+{
+    /* inputs (device pointers for fabber_cuda_*, host pointers for the test oracle) */
+    const float *data;                                  /* [T][N] */
+    const double *image_prior[FABBER_CUDA_MAX_PARAMS];  /* [N] for prior_type 'I', else NULL */
+    const double *init_mean;  /* optional [P][N] Fabber-space restart means (continue-from-mvn) */
+    const double *init_cov;   /* optional [P(P+1)/2][N] restart covariance, packed */
+    const double *init_noise; /* optional [NN][N] restart noise posterior */
+    const int *coords;        /* spatial: [3][N] integer voxel coordinates (x,y,z) */
+    /* outputs */
+    double *mean;        /* [P][N] */
+    double *cov;         /* [P(P+1)/2][N] */
+    double *noise;       /* [NN][N] */
+    double *free_energy; /* [N] or NULL */
+    double *f_history;   /* [f_history_len][N] or NULL */
+    int *iterations;     /* [N] or NULL */
+    int *status;         /* [N] */
+    double *spatial_ak;  /* spatial: HOST [max_iterations+1][P] aK history or NULL */
+} fabber_cuda_vb_buffers;
+
+/* --- device management helpers (so a C/C++ host needs no CUDA headers) -------------------- */
+int fabber_cuda_device_count(void);
+int fabber_cuda_set_device(int dev);
+const char *fabber_cuda_last_error(void);
+void *fabber_cuda_malloc(unsigned long long bytes);
+void fabber_cuda_free(void *dptr);
+void *fabber_cuda_host_alloc(unsigned long long bytes); /* pinned */
+void fabber_cuda_host_free(void *hptr);
+int fabber_cuda_memcpy_h2d(void *dst, const void *src, unsigned long long bytes, void *stream);
+int fabber_cuda_memcpy_d2h(void *dst, const void *src, unsigned long long bytes, void *stream);
+int fabber_cuda_memset(void *dst, int value, unsigned long long bytes, void *stream);
+int fabber_cuda_stream_sync(void *stream);
+
+/* Gather masked voxels: full[t][i] (i over nx*ny*nz, x fastest) -> out[t][v] for v in index list
+ * (reference rundata_array.cc:100-133 SetVoxelDataArray, done on the device). */
+int fabber_cuda_gather_voxels(const float *full, unsigned long long n_grid, int n_times,
+    const int *voxel_index, int n_voxels, float *out, void *stream);
+/* Scatter back: out_full[r][i] = (float) in[r][v], 0 outside mask (rundata_array.cc:68-98). */
+int fabber_cuda_scatter_voxels(const double *in, int n_rows, int n_voxels, const int *voxel_index,
+    unsigned long long n_grid, float *out_full, void *stream);
+
+/* --- the hot path --------------------------------------------------------------------------- */
+
+/* Non-spatial VB: all iterations of every voxel fused in one launch.
+ * Replaces Vb::SetupPerVoxelDists + Vb::DoCalculationsVoxelwise (inference_vb.cc:144-248,415-576).
+ * `stream` is a cudaStream_t (NULL = default stream). Asynchronous: returns after enqueueing.
+ * Returns FABBER_CUDA_OK / FABBER_CUDA_ERR_*. Per-voxel failures are reported in buffers.status;
+ * use fabber_cuda_check_status() after synchronising to apply the halt-on-bad-voxel policy. */
+int fabber_cuda_vb_voxelwise(
+    const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream);
+
+/* Spatial VB (iteration-major; replaces Vb::DoCalculationsSpatial, inference_vb.cc:578-767,
+ * SpatialPrior::CalculateaK / ApplyToMVN priors.cc:221-488, Vb::CalcNeighbours :830-964).
+ * Synchronous. Single-GPU entry; multi-GPU z-slab sharding is driven from the host layer. */
+int fabber_cuda_vb_spatial(
+    const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream);
+
+/* Scan status[] on the device; returns 0 if all OK, else the number of failed voxels and the
+ * index / code of the first one (synchronises the stream). */
+int fabber_cuda_check_status(
+    const int *status, int n_voxels, int *first_bad_voxel, int *first_bad_code, void *stream);
+
+/* Batched model evaluation at Fabber-space means: fit[t][v] = g(ToModel(mean[:,v]))
+ * (reference InferenceTechnique::SaveResults inference.cc:190-191 EvaluateFabber per voxel). */
+int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean /*[P][N]*/,
+    double *fit /*[T][N]*/, void *stream);
+
+/* Measured FP64 FMA throughput of the current device in GFLOP/s (dependent-free DFMA loop on all
+ * SMs; used as the roofline denominator because MEASURED_PEAKS.json carries no FP64 figure). */
+double fabber_cuda_measure_fp64_peak(int repeats);
+
+/* Number of kernels this library has launched so far in this process. */
+unsigned long long fabber_cuda_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
