@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py - voxel-iterations/second of the VB update loop on B200 (see BASELINE.json).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl reference]
+
+One "step" = one complete VB run (all iterations of every voxel, one fused kernel launch) over the
+synthetic volume that is already resident in HBM. `value` = voxel-iterations of all ranks / time.
+`e2e` = the same run driven with HOST buffers: pinned host -> device copy of the time-series, the
+launch, and the device -> host copy of every result array inside the timed region.
+
+Multi-GPU: one process per GPU (torchrun), voxels sharded, no data-path collective;
+each rank holds a full-size volume of its own (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # BASELINE.json configs[1]: poly degree 3, VB, white noise, synthetic 128^3 x 64, maxits 10
+    "c2": dict(name="C2 poly(degree 3) VB white noise, synthetic 128^3 x 64, maxits 10", side=128, T=64,
+               model="poly", spec=dict(degree=3), P=4, e=8, e0=0),
+    # BASELINE.json configs[2]: biexp VB, LM convergence, synthetic 256^3 x 96
+    "c3": dict(name="C3 exp(num-exps 2, dt 0.02) VB white noise, convergence=lm, synthetic 256^3 x 96", side=256,
+               T=96, model="exp", spec=dict(num_exps=2, dt=0.02, convergence="lm", need_f=True), P=4, e=46, e0=80),
+}
+
+
+def algorithmic_flops(w):
+    """FLOP per voxel-iteration of the minimal algorithm (FMA = 2, div = sqrt = 10,
+    exp = log = 20): (2P+1)(T e + e0) + 2TP + T[P(P+1) + 2P + 3] + (2P^3 + 10P^2 + 300)."""
+    P, T, e, e0 = w["P"], w["T"], w["e"], w["e0"]
+    return (2 * P + 1) * (T * e + e0) + 2 * T * P + T * (P * (P + 1) + 2 * P + 3) + (2 * P ** 3 + 10 * P ** 2 + 300)
+
+
+def algorithmic_bytes(w, n_iter):
+    """HBM bytes per voxel-iteration, all iterations fused (y read once, results written once)."""
+    P, T = w["P"], w["T"]
+    return (4 * T + 4 * ((P + 1) * (P + 2) // 2 + (P + 1) + 1) + 16) / max(n_iter, 1e-9)
+
+
+def make_volume(w, n_voxels, device, seed_offset=0):
+    from fabber_core_b200 import synth
+
+    if w["model"] == "poly":
+        return synth.poly_volume(n_voxels, w["T"], 3, seed=1002 + seed_offset, device=device)
+    return synth.biexp_volume(n_voxels, w["T"], 0.02, 0.02, seed=1003 + seed_offset, device=device)
+
+
+def make_spec(w):
+    from fabber_core_b200 import cuda_abi as abi
+
+    return abi.ProblemSpec(w["model"], w["T"], **w["spec"])
+
+
+class ClockSampler(object):
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = [l for (ts, l) in self.lines if t0 - 0.05 <= ts <= t1 + 0.15] or [l for (_, l) in self.lines]
+        for l in rows:
+            f = [x.strip() for x in l.split(",")]
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def oracle_throughput(w, threads, budget_s):
+    """Voxel-iterations/s of the CPU oracle (port of the reference's algorithm) on a bounded sample."""
+    import oracle
+    from concurrent.futures import ThreadPoolExecutor
+
+    oracle.lib()
+    probe_n = 256
+
+    def run_chunk(seed):
+        def f(n):
+            y = make_volume(w, n, "cpu", seed_offset=seed).numpy()
+            t0 = time.perf_counter()
+            out = oracle.run(make_spec(w), y)
+            return time.perf_counter() - t0, int(out["iterations"].sum())
+        return f
+
+    dt, its = run_chunk(0)(probe_n)
+    rate1 = its / dt
+    n_per_thread = int(max(probe_n, min(200000, rate1 * budget_s / max(its / probe_n, 1))))
+    datas = [make_volume(w, n_per_thread, "cpu", seed_offset=100 + i).numpy() for i in range(threads)]
+    specs = [make_spec(w) for _ in range(threads)]
+
+    def work(i):
+        out = oracle.run(specs[i], datas[i])  # ctypes releases the GIL: threads run in parallel
+        return int(out["iterations"].sum())
+
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(threads) as ex:
+        total = sum(ex.map(work, range(threads)))
+    dt = time.perf_counter() - t0
+    return total / dt, dt, n_per_thread * threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--voxels", type=int, default=0, help="override voxels per GPU (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n_vox = args.voxels or w["side"] ** 3
+    metric = "voxel-iterations/sec"
+    config = {"workload": w["name"], "voxels_per_gpu": n_vox, "timepoints": w["T"], "params": w["P"],
+              "sharding": "voxel ranges, no collective", "cache": "inputs larger than L2 (%.0f MB per step)"
+              % (n_vox * w["T"] * 4 / 1e6)}
+
+    if args.impl == "reference":
+        # the reference's own CPU algorithm (oracle port: the reference itself needs FSL's NEWMAT,
+        # which is not in the image) on all host cores, bounded sample per step
+        if rank != 0:
+            return 0
+        cores = os.cpu_count() or 1
+        rates = []
+        t_all0 = time.perf_counter()
+        for i in range(args.warmup + args.steps):
+            rate, dt, n = oracle_throughput(w, cores, budget_s=max(1.0, 60.0 / (args.warmup + args.steps)))
+            if i >= args.warmup:
+                rates.append((rate, dt, n))
+        value = float(np.mean([r[0] for r in rates]))
+        ms = float(np.mean([r[1] for r in rates]) * 1e3)
+        sample = "%d voxels of the same synthetic workload per step, %d threads" % (rates[0][2], cores)
+        print(json.dumps({
+            "impl": "reference", "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": value, "unit": "voxel-iterations/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "wall_s": time.perf_counter() - t_all0}))
+        return 0
+
+    import torch
+
+    from fabber_core_b200 import device
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: there is no CPU fallback for the product path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    L = device.lib()
+    device.check(L.fabber_cuda_set_device(local_rank), "set_device")
+    stream = torch.cuda.current_stream().cuda_stream
+
+    y = make_volume(w, n_vox, "cuda", seed_offset=rank)
+    spec = make_spec(w)
+    run = device.VbRun(spec, n_vox)
+    run.set_data_device(y.data_ptr())
+
+    def step():
+        rc = run.launch(stream)
+        if rc != 0:
+            raise RuntimeError("launch failed: %s" % device.last_error())
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    its_total = int(run.out["iterations"].to_host().astype(np.int64).sum())
+    n_bad = int(np.count_nonzero(run.out["status"].to_host()))
+    fp64_peak = L.fabber_cuda_measure_fp64_peak(3)  # GFLOP/s, measured live (no FP64 figure in MEASURED_PEAKS.json)
+
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.3)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+    launches0 = L.fabber_cuda_launch_count()
+    barrier()
+    t0 = time.time()
+    ev[0].record()
+    for i in range(args.steps):
+        step()
+        ev[i + 1].record()
+    barrier()
+    t1 = time.time()
+    launches = L.fabber_cuda_launch_count() - launches0
+    clocks = sampler.stop(t0, t1)
+    total_ms = ev[0].elapsed_time(ev[-1])
+    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
+    t_ms = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+    its = torch.tensor([its_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(its, op=dist.ReduceOp.SUM)
+    total_ms_max = float(t_ms.item())
+    its_all = float(its.item())
+    value = its_all * args.steps / (total_ms_max * 1e-3)
+
+    # ---- end-to-end: host buffers in, host buffers out, copies inside the timed region ------------
+    host_y = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
+    host_y.copy_(y)
+    outs = run.out
+    host_out = {k: torch.empty(v.nbytes, dtype=torch.uint8, pin_memory=True) for k, v in outs.items()}
+    h2d = host_y.numel() * 4
+    d2h = sum(v.nbytes for v in outs.values())
+
+    def e2e_step():
+        device.check(L.fabber_cuda_memcpy_h2d(y.data_ptr(), host_y.data_ptr(), h2d, stream), "h2d")
+        step()
+        for k, v in outs.items():
+            device.check(L.fabber_cuda_memcpy_d2h(host_out[k].data_ptr(), v.ptr, v.nbytes, stream), "d2h")
+
+    e2e_step()
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = its_all * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        W = algorithmic_flops(w)
+        per_launch_its = its_total  # this rank's launch
+        avg_kernel_s = float(np.mean(kernel_ms)) * 1e-3
+        achieved_tf = W * per_launch_its / avg_kernel_s / 1e12
+        peak_tf = fp64_peak / 1e3
+        n_iter = its_total / float(n_vox)
+        bytes_per_launch = algorithmic_bytes(w, n_iter) * per_launch_its
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except (OSError, ValueError):
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        line = {
+            "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                         "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+                         "peak_source": "measured live: dependent-free DFMA loop on all SMs "
+                                        "(MEASURED_PEAKS.json has no FP64 figure)",
+                         "flop_per_voxel_iteration": W, "kernel": "vb_voxelwise_white_kernel",
+                         "avg_launch_ms": avg_kernel_s * 1e3,
+                         "hbm": {"achieved": bytes_per_launch / avg_kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                 "frac": bytes_per_launch / avg_kernel_s / 1e9 / hbm_peak,
+                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
+            "iterations_per_voxel": n_iter, "bad_voxels": n_bad,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            rate, dt, n = oracle_throughput(w, 1, budget_s=12.0)
+            line["cpu_baseline"] = {"value": rate, "unit": "voxel-iterations/s", "cores": 1, "kind": "port",
+                                    "sample": "%d voxels of the same synthetic workload, %.1f s, single thread"
+                                    % (n, dt)}
+        print(json.dumps(line))
+    run.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

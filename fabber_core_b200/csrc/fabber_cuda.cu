@@ -1,0 +1,509 @@
+/*
+ * fabber_cuda.cu - implementation of the thin host <-> device C ABI declared in
+ * include/fabber_cuda.h: argument validation, staging of the small per-run constants (design
+ * matrix, noise pattern) and dispatch to the templated sm_100a kernels.
+ *
+ * There is deliberately no CPU path in here: if CUDA is unavailable every entry point fails with
+ * FABBER_CUDA_ERR_CUDA.
+ */
+#include <atomic>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "vb_launch.h"
+#include "vb_voxelwise.cuh"
+
+namespace fab
+{
+static std::atomic<unsigned long long> g_launches(0);
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+static thread_local std::string g_last_error;
+static int fail(int code, const std::string &msg)
+{
+    g_last_error = msg;
+    return code;
+}
+static int cuda_fail(cudaError_t e, const char *what)
+{
+    return fail(FABBER_CUDA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+/* getters exported by the per-model translation units (vb_inst.cu) */
+#define FAB_MODEL(id, p, name) const ModelLaunchers *name();
+#include "vb_models.inc"
+#undef FAB_MODEL
+
+const ModelLaunchers *find_model(int model_id, int n_params)
+{
+    struct Entry
+    {
+        int id, p;
+        const ModelLaunchers *(*get)();
+    };
+    static const Entry table[] = {
+#define FAB_MODEL(id, p, name) { id, p, name },
+#include "vb_models.inc"
+#undef FAB_MODEL
+    };
+    for (size_t i = 0; i < sizeof(table) / sizeof(table[0]); i++)
+        if (table[i].id == model_id && table[i].p == n_params)
+            return table[i].get();
+    return nullptr;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * small utility kernels
+ * ---------------------------------------------------------------------------------------------- */
+__global__ void gather_voxels_kernel(const float *__restrict__ full, size_t n_grid, int T,
+    const int *__restrict__ index, int N, float *__restrict__ out)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)T * N;
+    if (i >= total)
+        return;
+    const size_t t = i / N, v = i - t * N;
+    out[i] = full[t * n_grid + (size_t)index[v]];
+}
+
+__global__ void scatter_voxels_kernel(const double *__restrict__ in, int n_rows, int N,
+    const int *__restrict__ index, size_t n_grid, float *__restrict__ out_full)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)n_rows * N;
+    if (i >= total)
+        return;
+    const size_t r = i / N, v = i - r * N;
+    out_full[r * n_grid + (size_t)index[v]] = (float)in[i];
+}
+
+__global__ void status_scan_kernel(const int *__restrict__ status, int N, int *out /* [count, first, code] */)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const int s = status[i];
+    if (s != 0)
+    {
+        atomicAdd(&out[0], 1);
+        atomicMin(&out[1], i);
+    }
+}
+
+/* dependent-free DFMA loop: 8 independent accumulators per thread */
+__global__ void fp64_peak_kernel(double *out, int iters, double x)
+{
+    double a0 = threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double y = x * 0.5;
+#pragma unroll 1
+    for (int i = 0; i < iters; i++)
+    {
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+        {
+            a0 = fma(a0, x, y);
+            a1 = fma(a1, x, y);
+            a2 = fma(a2, x, y);
+            a3 = fma(a3, x, y);
+            a4 = fma(a4, x, y);
+            a5 = fma(a5, x, y);
+            a6 = fma(a6, x, y);
+            a7 = fma(a7, x, y);
+        }
+    }
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * problem -> kernel argument block
+ * ---------------------------------------------------------------------------------------------- */
+struct Staged
+{
+    double *design = nullptr;
+    unsigned char *pattern = nullptr;
+    void release(cudaStream_t s)
+    {
+        if (design)
+            cudaFreeAsync(design, s);
+        if (pattern)
+            cudaFreeAsync(pattern, s);
+        design = nullptr;
+        pattern = nullptr;
+    }
+};
+
+static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, cudaStream_t s,
+    VbArgs &a, Staged &st, bool &general)
+{
+    if (!prob || !buf)
+        return fail(FABBER_CUDA_ERR_INVALID, "null problem or buffers");
+    const int P = prob->model.n_params, T = prob->n_times, N = prob->n_voxels;
+    if (P < 1 || P > FABBER_CUDA_MAX_PARAMS)
+        return fail(FABBER_CUDA_ERR_INVALID, "n_params out of range");
+    if (T < 1 || N < 0)
+        return fail(FABBER_CUDA_ERR_INVALID, "bad n_times / n_voxels");
+    if (prob->max_iterations <= 0)
+        return fail(FABBER_CUDA_ERR_INVALID, "max_iterations must be positive"); /* convergence.cc:38 */
+    if (prob->conv_type != FABBER_CONV_MAXITS && !(prob->fchange > 0))
+        return fail(FABBER_CUDA_ERR_INVALID, "fchange must be positive"); /* convergence.cc:73,261 */
+    if (prob->conv_type == FABBER_CONV_TRIALMODE && prob->max_trials <= 0)
+        return fail(FABBER_CUDA_ERR_INVALID, "max_trials must be positive"); /* convergence.cc:148 */
+    if (N > 0 && (!buf->data || !buf->mean || !buf->cov || !buf->noise || !buf->status))
+        return fail(FABBER_CUDA_ERR_INVALID, "missing data / mean / cov / noise / status buffer");
+    if ((buf->init_mean == nullptr) != (buf->init_cov == nullptr))
+        return fail(FABBER_CUDA_ERR_INVALID, "init_mean and init_cov must be given together");
+
+    memset(&a, 0, sizeof(a));
+    a.N = N;
+    a.T = T;
+    a.data = buf->data;
+    for (int i = 0; i < P; i++)
+    {
+        a.params[i] = prob->params[i];
+        if (a.params[i].prior_type == '-')
+            a.params[i].prior_type = 'N';
+        const char tr = a.params[i].transform;
+        if (tr != 'I' && tr != 'L' && tr != 'S' && tr != 'F' && tr != 'A')
+            return fail(FABBER_CUDA_ERR_INVALID, "unknown transform code");
+        a.image_prior[i] = buf->image_prior[i];
+        if (a.params[i].prior_type == 'I' && N > 0 && !buf->image_prior[i])
+            return fail(FABBER_CUDA_ERR_INVALID, "image prior without image");
+    }
+    a.exp_dt = prob->model.exp_dt;
+    if (prob->model.id == FABBER_MODEL_POLY && prob->model.poly_degree + 1 != P)
+        return fail(FABBER_CUDA_ERR_INVALID, "poly: n_params != degree + 1");
+    if (prob->model.id == FABBER_MODEL_EXP && 2 * prob->model.exp_num != P)
+        return fail(FABBER_CUDA_ERR_INVALID, "exp: n_params != 2 * num_exps");
+
+    /* noise */
+    const bool ar = prob->noise_type == FABBER_NOISE_AR1;
+    a.n_phis = ar ? 1 : prob->n_phis;
+    if (a.n_phis < 1 || a.n_phis > FABBER_CUDA_MAX_PHIS)
+        return fail(FABBER_CUDA_ERR_INVALID, "n_phis out of range");
+    if (ar && prob->time_masked)
+        for (int t = 0; t < T; t++)
+            if (prob->time_masked[t]) /* noisemodel_ar.cc: masked time points not supported */
+                return fail(FABBER_CUDA_ERR_INVALID, "AR noise model does not support masked time points");
+    std::vector<unsigned char> pat(T, 0);
+    general = false;
+    int n_masked = 0;
+    for (int i = 0; i < FABBER_CUDA_MAX_PHIS; i++)
+        a.n_per_phi[i] = 0;
+    for (int t = 0; t < T; t++)
+    {
+        int ph = (!ar && prob->phi_pattern) ? prob->phi_pattern[t] : 0;
+        if (ph >= a.n_phis)
+            return fail(FABBER_CUDA_ERR_INVALID, "phi_pattern entry >= n_phis");
+        if (prob->time_masked && prob->time_masked[t])
+        {
+            pat[t] = FAB_PAT_MASKED;
+            n_masked++;
+            general = true;
+        }
+        else
+        {
+            pat[t] = (unsigned char)ph;
+            a.n_per_phi[ph]++;
+        }
+    }
+    if (a.n_phis > 1)
+        general = true;
+    a.n_unmasked = T - n_masked;
+    for (int i = 0; i < FABBER_CUDA_MAX_PHIS; i++)
+    {
+        a.noise_prior_b[i] = prob->noise_prior_b[i];
+        a.noise_prior_c[i] = prob->noise_prior_c[i];
+        a.noise_post_b[i] = prob->noise_post_b[i];
+        a.noise_post_c[i] = prob->noise_post_c[i];
+    }
+    a.locked_noise_stdev = prob->locked_noise_stdev;
+    a.ar_alpha_prior_prec = prob->ar_alpha_prior_prec;
+    a.conv_type = prob->conv_type;
+    a.max_iterations = prob->max_iterations;
+    a.max_trials = prob->max_trials;
+    a.fchange = prob->fchange;
+    a.need_f = (prob->need_f || prob->conv_type != FABBER_CONV_MAXITS) ? 1 : 0;
+    a.f_history_len = buf->f_history ? prob->f_history_len : 0;
+    a.init_mean = buf->init_mean;
+    a.init_cov = buf->init_cov;
+    a.init_noise = buf->init_noise;
+    a.mean = buf->mean;
+    a.cov = buf->cov;
+    a.noise = buf->noise;
+    a.free_energy = buf->free_energy;
+    a.f_history = a.f_history_len > 0 ? buf->f_history : nullptr;
+    a.iterations = buf->iterations;
+    a.status = buf->status;
+
+    /* stage the per-run constants */
+    cudaError_t e;
+    if (prob->model.id == FABBER_MODEL_LINEAR)
+    {
+        if (!prob->model.design)
+            return fail(FABBER_CUDA_ERR_INVALID, "linear model without design matrix");
+        const size_t bytes = (size_t)T * P * sizeof(double);
+        if ((e = cudaMallocAsync((void **)&st.design, bytes, s)) != cudaSuccess)
+            return cuda_fail(e, "cudaMallocAsync(design)");
+        if ((e = cudaMemcpyAsync(st.design, prob->model.design, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpyAsync(design)");
+        a.design = st.design;
+    }
+    if (general)
+    {
+        if ((e = cudaMallocAsync((void **)&st.pattern, (size_t)T, s)) != cudaSuccess)
+            return cuda_fail(e, "cudaMallocAsync(pattern)");
+        if ((e = cudaMemcpyAsync(st.pattern, pat.data(), (size_t)T, cudaMemcpyHostToDevice, s)) != cudaSuccess)
+            return cuda_fail(e, "cudaMemcpyAsync(pattern)");
+        /* pat is pageable host memory: the copy is staged before the call returns */
+        a.pattern = st.pattern;
+    }
+    return FABBER_CUDA_OK;
+}
+
+} // namespace fab
+
+using namespace fab;
+
+extern "C" {
+
+int fabber_cuda_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess)
+        return 0;
+    return n;
+}
+
+int fabber_cuda_set_device(int dev)
+{
+    cudaError_t e = cudaSetDevice(dev);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaSetDevice");
+}
+
+const char *fabber_cuda_last_error(void) { return g_last_error.c_str(); }
+
+void *fabber_cuda_malloc(unsigned long long bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMalloc(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+    {
+        cuda_fail(e, "cudaMalloc");
+        return nullptr;
+    }
+    return p;
+}
+void fabber_cuda_free(void *dptr)
+{
+    if (dptr)
+        cudaFree(dptr);
+}
+void *fabber_cuda_host_alloc(unsigned long long bytes)
+{
+    void *p = nullptr;
+    cudaError_t e = cudaMallocHost(&p, bytes ? bytes : 1);
+    if (e != cudaSuccess)
+    {
+        cuda_fail(e, "cudaMallocHost");
+        return nullptr;
+    }
+    return p;
+}
+void fabber_cuda_host_free(void *hptr)
+{
+    if (hptr)
+        cudaFreeHost(hptr);
+}
+int fabber_cuda_memcpy_h2d(void *dst, const void *src, unsigned long long bytes, void *stream)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, (cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaMemcpyAsync(h2d)");
+}
+int fabber_cuda_memcpy_d2h(void *dst, const void *src, unsigned long long bytes, void *stream)
+{
+    cudaError_t e = cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaMemcpyAsync(d2h)");
+}
+int fabber_cuda_memset(void *dst, int value, unsigned long long bytes, void *stream)
+{
+    cudaError_t e = cudaMemsetAsync(dst, value, bytes, (cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaMemsetAsync");
+}
+int fabber_cuda_stream_sync(void *stream)
+{
+    cudaError_t e = cudaStreamSynchronize((cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaStreamSynchronize");
+}
+
+int fabber_cuda_gather_voxels(const float *full, unsigned long long n_grid, int n_times, const int *voxel_index,
+    int n_voxels, float *out, void *stream)
+{
+    if (n_voxels <= 0 || n_times <= 0)
+        return FABBER_CUDA_OK;
+    const size_t total = (size_t)n_times * n_voxels;
+    gather_voxels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        full, (size_t)n_grid, n_times, voxel_index, n_voxels, out);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "gather_voxels");
+}
+
+int fabber_cuda_scatter_voxels(const double *in, int n_rows, int n_voxels, const int *voxel_index,
+    unsigned long long n_grid, float *out_full, void *stream)
+{
+    cudaError_t e = cudaMemsetAsync(out_full, 0, (size_t)n_rows * n_grid * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaMemsetAsync(scatter)");
+    if (n_voxels <= 0 || n_rows <= 0)
+        return FABBER_CUDA_OK;
+    const size_t total = (size_t)n_rows * n_voxels;
+    scatter_voxels_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        in, n_rows, n_voxels, voxel_index, (size_t)n_grid, out_full);
+    count_launch();
+    e = cudaGetLastError();
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "scatter_voxels");
+}
+
+int fabber_cuda_vb_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    VbArgs a;
+    Staged st;
+    bool general = false;
+    int rc = build_args(prob, buf, s, a, st, general);
+    if (rc != FABBER_CUDA_OK)
+    {
+        st.release(s);
+        return rc;
+    }
+    const int P = prob->model.n_params;
+    for (int i = 0; i < P; i++)
+    {
+        const char ty = a.params[i].prior_type;
+        if (ty != 'N' && ty != 'I' && ty != 'A')
+        {
+            st.release(s);
+            return fail(FABBER_CUDA_ERR_INVALID,
+                "prior type is spatial or unknown: use fabber_cuda_vb_spatial (inference_vb.cc:334-358)");
+        }
+    }
+    const ModelLaunchers *ml = find_model(prob->model.id, P);
+    if (!ml)
+    {
+        st.release(s);
+        return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
+    }
+    VbLaunchFn fn = nullptr;
+    if (prob->noise_type == FABBER_NOISE_AR1)
+        fn = ml->ar1;
+    else if (prob->noise_type == FABBER_NOISE_WHITE)
+    {
+        const bool snap = prob->conv_type == FABBER_CONV_TRIALMODE || prob->conv_type == FABBER_CONV_FREDUCE;
+        fn = general ? ml->white_general : (snap ? ml->white_fast_snap : ml->white_fast);
+    }
+    if (!fn)
+    {
+        st.release(s);
+        return fail(FABBER_CUDA_ERR_INVALID, "noise model not available for this model");
+    }
+    cudaError_t e = fn(a, s);
+    st.release(s);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "vb_voxelwise launch");
+    return FABBER_CUDA_OK;
+}
+
+int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *, const fabber_cuda_vb_buffers *, void *)
+{
+    return fail(FABBER_CUDA_ERR_INVALID, "spatial VB kernels not built yet");
+}
+
+int fabber_cuda_check_status(const int *status, int n_voxels, int *first_bad_voxel, int *first_bad_code, void *stream)
+{
+    cudaStream_t s = (cudaStream_t)stream;
+    if (first_bad_voxel)
+        *first_bad_voxel = -1;
+    if (first_bad_code)
+        *first_bad_code = 0;
+    if (n_voxels <= 0)
+        return 0;
+    int *d = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d, 3 * sizeof(int), s);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaMallocAsync(status)");
+    int h[3] = { 0, 0x7fffffff, 0 };
+    cudaMemcpyAsync(d, h, sizeof(h), cudaMemcpyHostToDevice, s);
+    status_scan_kernel<<<(unsigned)((n_voxels + 255) / 256), 256, 0, s>>>(status, n_voxels, d);
+    count_launch();
+    cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, s);
+    e = cudaStreamSynchronize(s);
+    if (e == cudaSuccess && h[0] > 0)
+    {
+        int code = 0;
+        e = cudaMemcpy(&code, status + h[1], sizeof(int), cudaMemcpyDeviceToHost);
+        if (first_bad_voxel)
+            *first_bad_voxel = h[1];
+        if (first_bad_code)
+            *first_bad_code = code;
+    }
+    cudaFreeAsync(d, s);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "check_status");
+    return h[0];
+}
+
+int fabber_cuda_model_fit(const fabber_cuda_vb_problem *, const double *, double *, void *)
+{
+    return fail(FABBER_CUDA_ERR_INVALID, "model_fit kernel not built yet");
+}
+
+double fabber_cuda_measure_fp64_peak(int repeats)
+{
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return -1.0;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int threads = 256, blocks = sms * 8, iters = 4096;
+    double *out = nullptr;
+    if (cudaMalloc((void **)&out, (size_t)threads * blocks * sizeof(double)) != cudaSuccess)
+        return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    double best = 0.0;
+    if (repeats < 1)
+        repeats = 1;
+    for (int r = 0; r < repeats + 1; r++)
+    {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(out, iters, 1.0000001);
+        count_launch();
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess)
+        {
+            best = -1.0;
+            break;
+        }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 64.0 * (double)iters * threads * blocks;
+        const double gf = flops / (ms * 1e-3) * 1e-9;
+        if (r > 0 && gf > best) /* first repeat is warm-up */
+            best = gf;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}
+
+unsigned long long fabber_cuda_launch_count(void) { return g_launches.load(); }
+
+/* struct sizes, so that language bindings can verify their mirror of the header */
+int fabber_cuda_sizeof_problem(void) { return (int)sizeof(fabber_cuda_vb_problem); }
+int fabber_cuda_sizeof_buffers(void) { return (int)sizeof(fabber_cuda_vb_buffers); }
+
+} // extern "C"

@@ -1,0 +1,32 @@
+/*
+ * vb_launch.h - host-side launcher table for the templated VB kernels.
+ *
+ * Every (model family, parameter count) pair is compiled in its own translation unit
+ * (vb_inst.cu with -DFAB_FAMILY/-DFAB_K, see Makefile) so the build parallelises; each unit exports
+ * one getter returning the launchers for that model.
+ */
+#pragma once
+#include <cuda_runtime.h>
+
+namespace fab
+{
+struct VbArgs;
+
+typedef cudaError_t (*VbLaunchFn)(const VbArgs &, cudaStream_t);
+
+struct ModelLaunchers
+{
+    VbLaunchFn white_fast;      /* one phi, no masked samples, detectors without a real snapshot */
+    VbLaunchFn white_fast_snap; /* same, trialmode / freduce (snapshot + revert) */
+    VbLaunchFn white_general;   /* noise patterns (<= FABBER_CUDA_MAX_PHIS) and masked samples */
+    VbLaunchFn ar1;             /* AR(1) noise */
+    VbLaunchFn model_fit;       /* batched model evaluation */
+    VbLaunchFn spatial_setup;   /* spatial mode kernels */
+    VbLaunchFn spatial_theta;
+    VbLaunchFn spatial_noise;
+};
+
+/* returns NULL when no device Evaluate hook is compiled for that size */
+const ModelLaunchers *find_model(int model_id, int n_params);
+
+} // namespace fab

@@ -1,0 +1,249 @@
+/*
+ * vb_models.cuh - forward models as __device__ Evaluate hooks.
+ *
+ * Each model is a struct with
+ *   P                      number of parameters (compile time)
+ *   Ctx                    per-thread constants (pointers into shared memory, scalars)
+ *   smem_bytes(args)       dynamic shared memory the model wants (design / timing vectors)
+ *   stage(args, smem)      block-cooperative staging into shared memory
+ *   make_ctx(args, smem)   builds Ctx
+ *   eval(ctx, t, p)        one sample of EvaluateModel at model-space parameters p
+ *   eval_fd(ctx, t, p0, pp, pn, g, gp, gn)
+ *                          the 2P+1 evaluations LinearizedFwdModel::ReCentre needs at sample t:
+ *                          g = f(p0), gp[i] = f(p0 with p0[i] -> pp[i]), gn[i] likewise with pn[i].
+ *                          Every value is bit-identical to calling eval() on the perturbed vector;
+ *                          models override it only to share sub-expressions that provably do not
+ *                          depend on the perturbed element (e.g. exp(-r t) when an amplitude moves).
+ *   init_voxel(...)        FwdModel::InitVoxelPosterior hook (model-space means)
+ *
+ * The arithmetic inside eval() follows the reference's EvaluateModel operation by operation, with
+ * explicit round-to-nearest intrinsics so that nvcc does not contract mul+add into FMA: the
+ * finite-difference Jacobian amplifies last-bit differences of g by ~1e5 (SURVEY.md hard part 1).
+ *
+ * Reference: fwdmodel_linear.cc:92-96, fwdmodel_poly.cc:62-80, examples/fwdmodel_exp.cc:65-91.
+ */
+#pragma once
+#include "vb_device.cuh"
+
+namespace fab
+{
+struct VbArgs;
+
+/* ---------------------------------------------------------------------------------------------
+ * linear:  result = design * (params - 0) + 0          (fwdmodel_linear.cc:95)
+ * design is staged in shared memory, row-major [T][P]; all threads of a warp read the same row
+ * (broadcast, conflict free).
+ * ------------------------------------------------------------------------------------------- */
+template <int P_> struct LinearModel
+{
+    static constexpr int P = P_;
+    static constexpr int ID = FABBER_MODEL_LINEAR;
+    struct Ctx
+    {
+        const double *design;
+    };
+    static __host__ __device__ size_t smem_bytes(int T) { return (size_t)T * P * sizeof(double); }
+    template <class Args> static FAB_DEV void stage(const Args &a, double *smem)
+    {
+        for (int i = threadIdx.x; i < a.T * P; i += blockDim.x)
+            smem[i] = a.design[i];
+    }
+    template <class Args> static FAB_DEV Ctx make_ctx(const Args &, double *smem)
+    {
+        Ctx c;
+        c.design = smem;
+        return c;
+    }
+    static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])
+    {
+        const double *row = c.design + t * P;
+        double s = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++)
+            s = __dadd_rn(s, __dmul_rn(row[j], p[j]));
+        return s;
+    }
+    static FAB_DEV void eval_fd(const Ctx &c, int t, const double (&p0)[P], const double (&pp)[P],
+        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
+    {
+        const double *row = c.design + t * P;
+        double d[P], prod[P];
+#pragma unroll
+        for (int j = 0; j < P; j++)
+        {
+            d[j] = row[j];
+            prod[j] = __dmul_rn(d[j], p0[j]);
+        }
+        /* prefix[j] = sum of the first j products, in the reference's left-to-right order */
+        double prefix[P + 1];
+        prefix[0] = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++)
+            prefix[j + 1] = __dadd_rn(prefix[j], prod[j]);
+        g = prefix[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            double sp = __dadd_rn(prefix[i], __dmul_rn(d[i], pp[i]));
+            double sn = __dadd_rn(prefix[i], __dmul_rn(d[i], pn[i]));
+#pragma unroll
+            for (int j = i + 1; j < P; j++)
+            {
+                sp = __dadd_rn(sp, prod[j]);
+                sn = __dadd_rn(sn, prod[j]);
+            }
+            gp[i] = sp;
+            gn[i] = sn;
+        }
+    }
+    template <class Args> static FAB_DEV void init_voxel(const Args &, int, double (&)[P]) {}
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * poly:  result(i) = sum_n c_n * i^n, i = 1..T, with the power kept in an `int`
+ * (fwdmodel_poly.cc:68-79; wraps like the reference for i^(n) >= 2^31).
+ * ------------------------------------------------------------------------------------------- */
+template <int P_> struct PolyModel
+{
+    static constexpr int P = P_; /* degree + 1 */
+    static constexpr int ID = FABBER_MODEL_POLY;
+    struct Ctx
+    {
+    };
+    static __host__ __device__ size_t smem_bytes(int) { return 0; }
+    template <class Args> static FAB_DEV void stage(const Args &, double *) {}
+    template <class Args> static FAB_DEV Ctx make_ctx(const Args &, double *) { return Ctx(); }
+    static FAB_DEV void powers(int t, double (&pw)[P])
+    {
+        unsigned int x = 1u, i = (unsigned int)(t + 1);
+#pragma unroll
+        for (int n = 0; n < P; n++)
+        {
+            pw[n] = (double)(int)x;
+            x *= i;
+        }
+    }
+    static FAB_DEV double eval(const Ctx &, int t, const double (&p)[P])
+    {
+        double pw[P];
+        powers(t, pw);
+        double s = 0.0;
+#pragma unroll
+        for (int n = 0; n < P; n++)
+            s = __dadd_rn(s, __dmul_rn(p[n], pw[n]));
+        return s;
+    }
+    static FAB_DEV void eval_fd(const Ctx &, int t, const double (&p0)[P], const double (&pp)[P],
+        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
+    {
+        double pw[P], prod[P], prefix[P + 1];
+        powers(t, pw);
+        prefix[0] = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++)
+        {
+            prod[j] = __dmul_rn(p0[j], pw[j]);
+            prefix[j + 1] = __dadd_rn(prefix[j], prod[j]);
+        }
+        g = prefix[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            double sp = __dadd_rn(prefix[i], __dmul_rn(pp[i], pw[i]));
+            double sn = __dadd_rn(prefix[i], __dmul_rn(pn[i], pw[i]));
+#pragma unroll
+            for (int j = i + 1; j < P; j++)
+            {
+                sp = __dadd_rn(sp, prod[j]);
+                sn = __dadd_rn(sn, prod[j]);
+            }
+            gp[i] = sp;
+            gn[i] = sn;
+        }
+    }
+    template <class Args> static FAB_DEV void init_voxel(const Args &, int, double (&)[P]) {}
+};
+
+/* ---------------------------------------------------------------------------------------------
+ * exp:  result(i) = sum_k amp_k * exp(-r_k * (double(i) * dt)), i = 0..T-1
+ * (examples/fwdmodel_exp.cc:71-81), parameters (amp_1, r_1, amp_2, r_2, ...).
+ * InitVoxelPosterior: amp_k = max(data) / (n + k)  (:84-91).
+ * ------------------------------------------------------------------------------------------- */
+template <int NE> struct ExpModel
+{
+    static constexpr int P = 2 * NE;
+    static constexpr int ID = FABBER_MODEL_EXP;
+    struct Ctx
+    {
+        double dt;
+    };
+    static __host__ __device__ size_t smem_bytes(int) { return 0; }
+    template <class Args> static FAB_DEV void stage(const Args &, double *) {}
+    template <class Args> static FAB_DEV Ctx make_ctx(const Args &a, double *)
+    {
+        Ctx c;
+        c.dt = a.exp_dt;
+        return c;
+    }
+    static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])
+    {
+        double tt = __dmul_rn((double)t, c.dt);
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+            s = __dadd_rn(s, __dmul_rn(p[2 * k], exp(__dmul_rn(-p[2 * k + 1], tt))));
+        return s;
+    }
+    static FAB_DEV void eval_fd(const Ctx &c, int t, const double (&p0)[P], const double (&pp)[P],
+        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
+    {
+        double tt = __dmul_rn((double)t, c.dt);
+        double e0[NE], term[NE];
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+        {
+            e0[k] = exp(__dmul_rn(-p0[2 * k + 1], tt));
+            term[k] = __dmul_rn(p0[2 * k], e0[k]);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+            s = __dadd_rn(s, term[k]);
+        g = s;
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+        {
+            /* amplitude k moves: exp(-r_k t) is unchanged; rate k moves: two new exponentials */
+            double ta[4];
+            ta[0] = __dmul_rn(pp[2 * k], e0[k]);
+            ta[1] = __dmul_rn(pn[2 * k], e0[k]);
+            ta[2] = __dmul_rn(p0[2 * k], exp(__dmul_rn(-pp[2 * k + 1], tt)));
+            ta[3] = __dmul_rn(p0[2 * k], exp(__dmul_rn(-pn[2 * k + 1], tt)));
+            double out[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++)
+            {
+                double acc = 0.0;
+#pragma unroll
+                for (int j = 0; j < NE; j++)
+                    acc = __dadd_rn(acc, j == k ? ta[q] : term[j]);
+                out[q] = acc;
+            }
+            gp[2 * k] = out[0];
+            gn[2 * k] = out[1];
+            gp[2 * k + 1] = out[2];
+            gn[2 * k + 1] = out[3];
+        }
+    }
+    template <class Args> static FAB_DEV void init_voxel(const Args &a, int v, double (&m)[P])
+    {
+        double mx = (double)a.data[v];
+        for (int t = 1; t < a.T; t++)
+            mx = fmax(mx, (double)a.data[(size_t)t * a.N + v]);
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+            m[2 * k] = mx / (double)(NE + k);
+    }
+};
+
+} // namespace fab

@@ -1,0 +1,550 @@
+/*
+ * vb_voxelwise.cuh - non-spatial VB with white noise: all iterations of a voxel in one thread.
+ *
+ * Replaces, per voxel, Vb::SetupPerVoxelDists + the body of Vb::DoCalculationsVoxelwise
+ * (inference_vb.cc:144-248, 415-576) with the operators it calls:
+ *   LinearizedFwdModel::ReCentre        fwdmodel_linear.cc:126-181
+ *   Default/Image/ARD Prior::ApplyToMVN priors.cc:108-181
+ *   WhiteNoiseModel::UpdateTheta        noisemodel_white.cc:275-363 (incl. the LM branch)
+ *   WhiteNoiseModel::UpdateNoise        noisemodel_white.cc:228-273
+ *   WhiteNoiseModel::CalcFreeEnergy     noisemodel_white.cc:365-454
+ *   ConvergenceDetector::Test etc.      convergence.cc
+ *
+ * Re-design (not a translation): the reference keeps a T x P Jacobian, T-vectors and T x T diagonal
+ * matrices per voxel and walks them ~10 times per iteration. Here one pass over the time-series per
+ * iteration evaluates the model at the 2P+1 finite-difference points and folds each sample straight
+ * into the sufficient statistics
+ *      A = J^T Q J (packed),  b = J^T Q r,  rr = r^T Q r,   r = y - g(c)
+ * per noise precision phi. Everything UpdateTheta / UpdateNoise / CalcFreeEnergy need is a function
+ * of (A, b, rr) and P-sized state, because k = y - g + J (c - m) = r + J d:
+ *      k^T Q k = rr + 2 b.d + d^T A d,   J^T Q (y - g + J c) = b + A c,   tr(Sigma J^T Q J) = tr(Sigma A).
+ * J and g are never stored. The y read is coalesced ([T][N], voxel fastest); the design matrix and
+ * noise pattern are staged in shared memory; P x P algebra is fully unrolled in registers.
+ */
+#pragma once
+#include "vb_models.cuh"
+
+namespace fab
+{
+#define FAB_MAX_PHIS FABBER_CUDA_MAX_PHIS
+#define FAB_PAT_MASKED 255
+
+/* Kernel argument block (passed by value as a __grid_constant__ parameter; < 4 KB). */
+struct VbArgs
+{
+    int N, T;
+    const float *data;          /* [T][N] */
+    const double *design;       /* device [T][P], linear model */
+    const unsigned char *pattern; /* device [T]: phi index per sample, 255 = masked; NULL = all phi 0 */
+    fabber_cuda_param params[FABBER_CUDA_MAX_PARAMS];
+    double exp_dt;
+    int n_phis;
+    int n_per_phi[FAB_MAX_PHIS]; /* unmasked samples using each phi (Qi.Trace()) */
+    int n_unmasked;              /* T - #masked */
+    double noise_prior_b[FAB_MAX_PHIS], noise_prior_c[FAB_MAX_PHIS];
+    double noise_post_b[FAB_MAX_PHIS], noise_post_c[FAB_MAX_PHIS];
+    double locked_noise_stdev;
+    double ar_alpha_prior_prec;
+    int conv_type, max_iterations, max_trials, need_f, f_history_len;
+    double fchange;
+    const double *image_prior[FABBER_CUDA_MAX_PARAMS];
+    const double *init_mean, *init_cov, *init_noise;
+    double *mean, *cov, *noise, *free_energy, *f_history;
+    int *iterations, *status;
+};
+
+template <int P> struct Stats
+{
+    double A[NTri<P>::value];
+    double b[P];
+    double rr;
+    FAB_DEV void zero()
+    {
+#pragma unroll
+        for (int i = 0; i < NTri<P>::value; i++)
+            A[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            b[i] = 0.0;
+        rr = 0.0;
+    }
+    FAB_DEV void add(double r, const double (&J)[P])
+    {
+        rr = fma(r, r, rr);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            b[i] = fma(J[i], r, b[i]);
+#pragma unroll
+            for (int j = 0; j <= i; j++)
+                A[tri(i, j)] = fma(J[i], J[j], A[tri(i, j)]);
+        }
+    }
+};
+
+/*
+ * LinearizedFwdModel::ReCentre fused with the statistics pass. Returns 0, or FABBER_VOX_NONFINITE_*
+ * exactly where the reference throws (offset checked before the Jacobian, fwdmodel_linear.cc:134,174).
+ * NPHI == 1: single phi, no masked samples (fast path). NPHI > 1: `pat` gives the phi per sample.
+ */
+template <class Model, int NPHI>
+FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
+    const double (&c)[Model::P], Stats<Model::P> (&S)[NPHI])
+{
+    constexpr int P = Model::P;
+    double p0[P], pp[P], pn[P], rden[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        const char code = a.params[i].transform;
+        double delta = c[i] * 1e-5;
+        if (delta < 0)
+            delta = -delta;
+        if (delta < 1e-10)
+            delta = 1e-10;
+        const double c2 = c[i] + delta, c3 = c[i] - delta;
+        p0[i] = to_model(code, c[i]);
+        pp[i] = to_model(code, c2);
+        pn[i] = to_model(code, c3);
+        rden[i] = 1.0 / (c2 - c3);
+    }
+#pragma unroll
+    for (int i = 0; i < NPHI; i++)
+        S[i].zero();
+    bool bad_g = false, bad_j = false;
+    const float *yp = a.data + v;
+    const size_t stride = (size_t)a.N;
+#pragma unroll 1
+    for (int t = 0; t < a.T; t++)
+    {
+        const double y = (double)__ldg(yp + t * stride);
+        double g, gp[P], gn[P], J[P];
+        Model::eval_fd(mc, t, p0, pp, pn, g, gp, gn);
+        bad_g = bad_g || !finite_d(g);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            J[i] = (gp[i] - gn[i]) * rden[i];
+            bad_j = bad_j || !finite_d(J[i]);
+        }
+        const double r = y - g;
+        if (NPHI == 1)
+            S[0].add(r, J);
+        else
+        {
+            const int ph = pat[t];
+#pragma unroll
+            for (int i = 0; i < NPHI; i++)
+                if (ph == i)
+                    S[i].add(r, J);
+        }
+    }
+    return bad_g ? FABBER_VOX_NONFINITE_OFFSET : (bad_j ? FABBER_VOX_NONFINITE_JACOBIAN : 0);
+}
+
+/* WhiteNoiseModel::CalcFreeEnergy with c == m (always true where Vb reads F: after ReCentre). */
+template <int P, int NPHI>
+FAB_DEV double white_free_energy(const VbArgs &a, const Stats<P> (&S)[NPHI], const double (&m)[P],
+    const double (&Sig)[NTri<P>::value], double logdetLam, const double (&m0)[P], const double (&L0)[P],
+    const double (&nb)[NPHI], const double (&nc)[NPHI])
+{
+    const double log2pi = log(2 * 3.14159265358979323846);
+    const double elTheta = 0.5 * logdetLam - 0.5 * P * (log2pi + 1);
+    double elPhi = 0.0, p0 = 0.0, p2 = 0.0, p9 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NPHI; i++)
+    {
+        if (i < a.n_phis)
+        {
+            const double si = nb[i], ci = nc[i];
+            const double siP = a.noise_prior_b[i], ciP = a.noise_prior_c[i];
+            const double dg = digamma_fsl(ci), lsi = log(si);
+            elPhi += -gammaln(ci) - ci * lsi - ci + (ci - 1) * (dg + lsi);
+            p0 += (dg + lsi) * ((double)a.n_per_phi[i] * 0.5 + ciP - 1);
+            p9 += -gammaln(ciP) - ciP * log(siP) - si * ci / siP;
+            p2 += -0.5 * si * ci * S[i].rr - 0.5 * trace_prod<P>(S[i].A, Sig);
+        }
+    }
+    double ld0 = 0.0, q = 0.0, tr0 = 0.0;
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        ld0 += log(fabs(L0[i]));
+        const double dm = m[i] - m0[i];
+        q += dm * L0[i] * dm;
+        tr0 += Sig[tri(i, i)] * L0[i];
+    }
+    const double p3 = 0.5 * ld0 - 0.5 * a.n_unmasked * log2pi - 0.5 * P * log2pi;
+    const double p4 = -0.5 * q;
+    const double p5 = -0.5 * tr0;
+    double F = -elTheta - elPhi;
+    F += p0;
+    F += p2;
+    F += p3;
+    F += p4;
+    F += p5;
+    F += p9;
+    return F;
+}
+
+template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
+{
+    static constexpr int P = Model::P;
+    static constexpr int NT = NTri<P>::value;
+
+    double m[P], Lam[NT], Sig[NT], m0[P], L0[P], nb[NPHI], nc[NPHI];
+    double logdetLam;
+
+    struct Snapshot
+    {
+        double m[P], Lam[NT], m0[P], L0[P], nb[NPHI], nc[NPHI];
+    };
+    FAB_DEV void save(Snapshot &s) const
+    {
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            s.m[i] = m[i];
+            s.m0[i] = m0[i];
+            s.L0[i] = L0[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            s.Lam[i] = Lam[i];
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            s.nb[i] = nb[i];
+            s.nc[i] = nc[i];
+        }
+    }
+    FAB_DEV void restore(const Snapshot &s)
+    {
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            m[i] = s.m[i];
+            m0[i] = s.m0[i];
+            L0[i] = s.L0[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Lam[i] = s.Lam[i];
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            nb[i] = s.nb[i];
+            nc[i] = s.nc[i];
+        }
+    }
+
+    /* priors.cc:108-181. Returns the free-energy contribution of parameter k. */
+    FAB_DEV double apply_prior(const VbArgs &a, int k, int v, int it)
+    {
+        const fabber_cuda_param &p = a.params[k];
+        if (p.prior_type == 'A')
+        {
+            const double new_cov = m[k] * m[k] + Sig[tri(k, k)];
+            if (it == 0)
+            {
+                L0[k] = 1.0 / p.prior_var;
+                m0[k] = p.prior_mean;
+            }
+            else
+                L0[k] = 1.0 / new_cov;
+            const double b = 2 / new_cov;
+            return -1.5 * (log(b) + digamma_fsl(0.5)) - 0.5 - gammaln(0.5) - 0.5 * log(b);
+        }
+        m0[k] = (p.prior_type == 'I') ? a.image_prior[k][v] : p.prior_mean;
+        L0[k] = p.prior_prec;
+        return 0.0;
+    }
+
+    /* noisemodel_white.cc:275-363. Returns false if the posterior precision is singular. */
+    FAB_DEV bool update_theta(const VbArgs &a, const Stats<P> (&S)[NPHI], const double (&c)[P], double alpha)
+    {
+        double Aw[NT], bw[P];
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Aw[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            bw[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+            if (i < a.n_phis)
+            {
+                const double x = nb[i] * nc[i]; /* GammaDist::CalcMean */
+#pragma unroll
+                for (int j = 0; j < NT; j++)
+                    Aw[j] = fma(x, S[i].A[j], Aw[j]);
+#pragma unroll
+                for (int j = 0; j < P; j++)
+                    bw[j] = fma(x, S[i].b[j], bw[j]);
+            }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Lam[i] = Aw[i];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            Lam[tri(i, i)] = L0[i] + Aw[tri(i, i)];
+        double P0m0[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            P0m0[i] = L0[i] * m0[i];
+        if (alpha <= 0.0)
+        {
+            if (!mvn_inverse<P>(Lam, Sig, logdetLam))
+                return false;
+            double Ac[P], rhs[P];
+            symv<P>(Aw, c, Ac);
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                rhs[i] = (bw[i] + Ac[i]) + P0m0[i];
+            symv<P>(Sig, rhs, m);
+        }
+        else
+        {
+            double D[NT], Dinv[NT], Delta[P], step[P], ld;
+#pragma unroll
+            for (int i = 0; i < NT; i++)
+                D[i] = Lam[i];
+#pragma unroll
+            for (int i = 0; i < P; i++)
+            {
+                D[tri(i, i)] = Lam[tri(i, i)] + alpha * Lam[tri(i, i)];
+                Delta[i] = bw[i] + P0m0[i] - L0[i] * c[i];
+            }
+            if (ldl_inverse<P>(D, Dinv, ld))
+            {
+                symv<P>(Dinv, Delta, step);
+#pragma unroll
+                for (int i = 0; i < P; i++)
+                    m[i] = c[i] + step[i];
+            }
+            /* Sigma is first needed by UpdateNoise (theta.GetCovariance(), noisemodel_white.cc:252) */
+            if (!mvn_inverse<P>(Lam, Sig, logdetLam))
+                return false;
+        }
+        return true;
+    }
+
+    /* noisemodel_white.cc:228-273 */
+    FAB_DEV void update_noise(const VbArgs &a, const Stats<P> (&S)[NPHI], const double (&c)[P])
+    {
+        double d[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            d[i] = c[i] - m[i];
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+            if (i < a.n_phis)
+            {
+                double bd = 0.0;
+#pragma unroll
+                for (int j = 0; j < P; j++)
+                    bd += S[i].b[j] * d[j];
+                const double kk = S[i].rr + 2.0 * bd + quadform<P>(S[i].A, d);
+                const double tmp = kk + trace_prod<P>(Sig, S[i].A);
+                nb[i] = 1 / (tmp * 0.5 + 1 / a.noise_prior_b[i]);
+                nc[i] = ((double)a.n_per_phi[i] - 1) * 0.5 + a.noise_prior_c[i];
+                if (a.locked_noise_stdev > 0)
+                    nb[i] = 1 / nc[i] / a.locked_noise_stdev / a.locked_noise_stdev;
+            }
+    }
+};
+
+constexpr int VB_BLOCK = 128;
+
+template <class Model, int NPHI, bool SNAP>
+__global__ void __launch_bounds__(VB_BLOCK) vb_voxelwise_white_kernel(const __grid_constant__ VbArgs a)
+{
+    constexpr int P = Model::P;
+    constexpr int NT = NTri<P>::value;
+    extern __shared__ double smem[];
+    Model::stage(a, smem);
+    unsigned char *pat = reinterpret_cast<unsigned char *>(smem) + Model::smem_bytes(a.T);
+    if (NPHI > 1)
+        for (int i = threadIdx.x; i < a.T; i += blockDim.x)
+            pat[i] = a.pattern ? a.pattern[i] : 0;
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N)
+        return;
+    const typename Model::Ctx mc = Model::make_ctx(a, smem);
+    const size_t N = (size_t)a.N;
+
+    WhiteVoxel<Model, NPHI, SNAP> X;
+    int status = 0;
+    double F = 1234.5678; /* inference_vb.cc:438 */
+    int it = 0;
+
+    /* ---- SetupPerVoxelDists (inference_vb.cc:207-247, fwdmodel.cc:284-324) ------------------- */
+    if (a.init_mean)
+    {
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            X.m[i] = a.init_mean[i * N + v];
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            X.Sig[i] = a.init_cov[i * N + v];
+        double ld;
+        if (!mvn_inverse<P>(X.Sig, X.Lam, ld))
+            status = FABBER_VOX_SINGULAR | FABBER_VOX_SETUP_FLAG;
+        X.logdetLam = -ld;
+    }
+    else
+    {
+        double var[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            X.m[i] = (a.params[i].prior_type == 'I') ? a.image_prior[i][v] : a.params[i].post_mean;
+            var[i] = a.params[i].post_var;
+        }
+        Model::init_voxel(a, v, X.m);
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+        {
+            X.Sig[i] = 0.0;
+            X.Lam[i] = 0.0;
+        }
+        X.logdetLam = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            const char code = a.params[i].transform;
+            X.m[i] = to_fabber(code, X.m[i]);
+            const double fv = to_fabber_var(code, var[i]);
+            X.Sig[tri(i, i)] = fv;
+            X.Lam[tri(i, i)] = 1.0 / fv;
+            X.logdetLam += log(fabs(X.Lam[tri(i, i)]));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NPHI; i++)
+    {
+        X.nb[i] = a.init_noise ? a.init_noise[(2 * i) * N + v] : a.noise_post_b[i];
+        X.nc[i] = a.init_noise ? a.init_noise[(2 * i + 1) * N + v] : a.noise_post_c[i];
+        if (i >= a.n_phis)
+            X.nb[i] = X.nc[i] = 1.0;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        X.m0[i] = 0.0; /* fwd_prior starts as N(0, I), inference_vb.cc:159 */
+        X.L0[i] = 1.0;
+    }
+
+    Stats<P> S[NPHI];
+    double c[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        c[i] = X.m[i];
+    if (status == 0)
+    {
+        /* ReCentre at :235 (set-up: a failure here is never caught by the reference). The second
+         * ReCentre at :443 recomputes the same values from the same centre. */
+        const int err = recentre_stats<Model, NPHI>(a, mc, pat, v, c, S);
+        if (err)
+            status = err | FABBER_VOX_SETUP_FLAG;
+    }
+
+    if (status == 0)
+    {
+        Conv conv;
+        conv.init(a.conv_type, a.max_iterations, a.fchange, a.max_trials);
+        typename WhiteVoxel<Model, NPHI, SNAP>::Snapshot snap;
+        if (SNAP)
+            X.save(snap); /* pre-loop copies, inference_vb.cc:432-434 */
+        double Fprior = 0.0;
+        do
+        {
+            if (SNAP && conv.need_save())
+                X.save(snap);
+#pragma unroll
+            for (int k = 0; k < P; k++)
+                Fprior = X.apply_prior(a, k, v, it); /* '=' not '+=': inference_vb.cc:462 */
+            if (!X.update_theta(a, S, c, conv.lm_alpha()))
+            {
+                status = FABBER_VOX_SINGULAR;
+                break;
+            }
+            X.update_noise(a, S, c);
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                c[i] = X.m[i];
+            const int err = recentre_stats<Model, NPHI>(a, mc, pat, v, c, S);
+            if (err)
+            {
+                status = err;
+                break;
+            }
+            if (a.need_f)
+            {
+                F = white_free_energy<P, NPHI>(a, S, X.m, X.Sig, X.logdetLam, X.m0, X.L0, X.nb, X.nc) + Fprior;
+                if (!finite_d(F))
+                {
+                    status = FABBER_VOX_NONFINITE_F;
+                    break;
+                }
+            }
+            if (a.f_history && it < a.f_history_len)
+                a.f_history[it * N + v] = F;
+            ++it;
+        } while (!conv.test(F));
+
+        if (status == 0 && SNAP)
+        {
+            if (conv.need_save())
+                X.save(snap);
+            if (conv.need_revert())
+            {
+                X.restore(snap);
+                if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam))
+                    status = FABBER_VOX_SINGULAR;
+#pragma unroll
+                for (int i = 0; i < P; i++)
+                    c[i] = X.m[i];
+                const int err = status ? 0 : recentre_stats<Model, NPHI>(a, mc, pat, v, c, S);
+                if (err)
+                    status = err;
+                else if (status == 0 && a.need_f)
+                {
+                    F = white_free_energy<P, NPHI>(a, S, X.m, X.Sig, X.logdetLam, X.m0, X.L0, X.nb, X.nc) + Fprior;
+                    if (!finite_d(F))
+                        status = FABBER_VOX_NONFINITE_F;
+                }
+            }
+        }
+        /* LM: m_save is always true (convergence.cc:270), so the snapshot taken after the loop
+         * (:506-513) is the current state and the revert at :516-525 restores exactly that,
+         * re-centres on the same means and recomputes the same F - a no-op on every output. */
+    }
+
+    /* ---- results (inference_vb.cc:546-570; padded F history :1041-1044) ----------------------- */
+    if (a.f_history)
+        for (int h = it; h < a.f_history_len; h++)
+            a.f_history[h * N + v] = F;
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        a.mean[i * N + v] = X.m[i];
+    const bool zero_cov = (status & 0xff) == FABBER_VOX_SINGULAR;
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        a.cov[i * N + v] = zero_cov ? 0.0 : X.Sig[i];
+#pragma unroll
+    for (int i = 0; i < NPHI; i++)
+        if (i < a.n_phis)
+        {
+            a.noise[(2 * i) * N + v] = X.nb[i];
+            a.noise[(2 * i + 1) * N + v] = X.nc[i];
+        }
+    if (a.free_energy)
+        a.free_energy[v] = F;
+    if (a.iterations)
+        a.iterations[v] = it;
+    a.status[v] = status;
+}
+
+} // namespace fab

@@ -255,4 +255,4 @@ class ProblemSpec(object):
 
 def library_path():
     here = os.path.dirname(os.path.abspath(__file__))
-    return os.path.join(here, "csrc", "libfabbercore_b200.so")
+    return os.path.join(here, "csrc", "libfabber_cuda.so")

@@ -1,0 +1,210 @@
+"""Host-side driver of the inner C ABI (include/fabber_cuda.h) through ctypes.
+
+This is plumbing only: it owns device buffers, copies inputs/outputs and calls the hand-written
+CUDA library. There is no CPU fallback - if the library cannot be loaded or no GPU is present the
+calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import cuda_abi as abi
+
+_LIB = None
+
+
+class CudaError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libfabber_cuda.so (built in-tree by fabber_core_b200/csrc/Makefile). Fails loudly."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = abi.library_path()
+    if not os.path.exists(path):
+        raise CudaError("CUDA extension %s is missing: run `python -c 'import __graft_entry__ as g; g.build()'`"
+                        % path)
+    L = C.CDLL(path)
+    L.fabber_cuda_last_error.restype = C.c_char_p
+    L.fabber_cuda_malloc.restype = C.c_void_p
+    L.fabber_cuda_malloc.argtypes = [C.c_ulonglong]
+    L.fabber_cuda_free.argtypes = [C.c_void_p]
+    L.fabber_cuda_host_alloc.restype = C.c_void_p
+    L.fabber_cuda_host_alloc.argtypes = [C.c_ulonglong]
+    L.fabber_cuda_host_free.argtypes = [C.c_void_p]
+    for fn in (L.fabber_cuda_memcpy_h2d, L.fabber_cuda_memcpy_d2h):
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_ulonglong, C.c_void_p]
+        fn.restype = C.c_int
+    L.fabber_cuda_memset.argtypes = [C.c_void_p, C.c_int, C.c_ulonglong, C.c_void_p]
+    L.fabber_cuda_stream_sync.argtypes = [C.c_void_p]
+    L.fabber_cuda_vb_voxelwise.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fabber_cuda_vb_voxelwise.restype = C.c_int
+    L.fabber_cuda_vb_spatial.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fabber_cuda_vb_spatial.restype = C.c_int
+    L.fabber_cuda_check_status.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fabber_cuda_check_status.restype = C.c_int
+    L.fabber_cuda_model_fit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    L.fabber_cuda_model_fit.restype = C.c_int
+    L.fabber_cuda_measure_fp64_peak.restype = C.c_double
+    L.fabber_cuda_measure_fp64_peak.argtypes = [C.c_int]
+    L.fabber_cuda_launch_count.restype = C.c_ulonglong
+    L.fabber_cuda_gather_voxels.argtypes = [C.c_void_p, C.c_ulonglong, C.c_int, C.c_void_p, C.c_int,
+                                            C.c_void_p, C.c_void_p]
+    L.fabber_cuda_scatter_voxels.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_ulonglong,
+                                             C.c_void_p, C.c_void_p]
+    if L.fabber_cuda_sizeof_problem() != C.sizeof(abi.VbProblem):
+        raise CudaError("ctypes mirror of fabber_cuda_vb_problem is out of date")
+    if L.fabber_cuda_sizeof_buffers() != C.sizeof(abi.VbBuffers):
+        raise CudaError("ctypes mirror of fabber_cuda_vb_buffers is out of date")
+    _LIB = L
+    return L
+
+
+def last_error():
+    return lib().fabber_cuda_last_error().decode(errors="replace")
+
+
+def check(rc, what):
+    if rc != abi.OK:
+        raise CudaError("%s failed (%d): %s" % (what, rc, last_error()))
+
+
+class DeviceArray(object):
+    """A device allocation with a numpy-like shape/dtype; freed on close() or garbage collection."""
+
+    def __init__(self, shape, dtype):
+        self.shape = tuple(int(s) for s in np.atleast_1d(shape))
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.ptr = lib().fabber_cuda_malloc(self.nbytes)
+        if not self.ptr:
+            raise CudaError("device allocation of %d bytes failed: %s" % (self.nbytes, last_error()))
+
+    @classmethod
+    def from_host(cls, arr, dtype=None, stream=None):
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        d = cls(arr.shape, arr.dtype)
+        check(lib().fabber_cuda_memcpy_h2d(d.ptr, arr.ctypes.data, d.nbytes, stream), "h2d copy")
+        check(lib().fabber_cuda_stream_sync(stream), "sync")
+        return d
+
+    def to_host(self, stream=None):
+        out = np.empty(self.shape, dtype=self.dtype)
+        check(lib().fabber_cuda_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes, stream), "d2h copy")
+        check(lib().fabber_cuda_stream_sync(stream), "sync")
+        return out
+
+    def close(self):
+        if self.ptr:
+            lib().fabber_cuda_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class VbRun(object):
+    """Device-resident buffers of one VB run (inputs + outputs) and the launch call."""
+
+    def __init__(self, spec, n_voxels, spatial=False):
+        self.spec = spec
+        self.N = int(n_voxels)
+        self.spatial = spatial
+        P, NN, N = spec.P, spec.NN, self.N
+        self.buf = abi.VbBuffers()
+        self.out = {
+            "mean": DeviceArray((P, N), np.float64),
+            "cov": DeviceArray((spec.ncov, N), np.float64),
+            "noise": DeviceArray((NN, N), np.float64),
+            "free_energy": DeviceArray((N,), np.float64),
+            "iterations": DeviceArray((N,), np.int32),
+            "status": DeviceArray((N,), np.int32),
+        }
+        if spec.prob.f_history_len > 0:
+            self.out["f_history"] = DeviceArray((spec.prob.f_history_len, N), np.float64)
+            self.buf.f_history = self.out["f_history"].ptr
+        for k in ("mean", "cov", "noise", "free_energy", "iterations", "status"):
+            setattr(self.buf, k, self.out[k].ptr)
+        self.inputs = {}
+        self.ak = None
+        if spatial:
+            self.ak = np.zeros((spec.prob.max_iterations + 1, P))
+            self.buf.spatial_ak = self.ak.ctypes.data
+
+    def set_data(self, data, stream=None):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        assert data.shape == (self.spec.n_times, self.N)
+        self.inputs["data"] = DeviceArray.from_host(data, stream=stream)
+        self.buf.data = self.inputs["data"].ptr
+
+    def set_data_device(self, ptr):
+        self.buf.data = ptr
+
+    def set_image_prior(self, k, img):
+        d = DeviceArray.from_host(img, dtype=np.float64)
+        self.inputs["image%d" % k] = d
+        self.buf.image_prior[k] = d.ptr
+
+    def set_initial(self, mean=None, cov=None, noise=None):
+        for name, arr in (("init_mean", mean), ("init_cov", cov), ("init_noise", noise)):
+            if arr is not None:
+                d = DeviceArray.from_host(arr, dtype=np.float64)
+                self.inputs[name] = d
+                setattr(self.buf, name, d.ptr)
+
+    def set_coords(self, coords):
+        d = DeviceArray.from_host(coords, dtype=np.int32)
+        self.inputs["coords"] = d
+        self.buf.coords = d.ptr
+
+    def launch(self, stream=None):
+        prob = self.spec.prob
+        prob.n_voxels = self.N
+        fn = lib().fabber_cuda_vb_spatial if self.spatial else lib().fabber_cuda_vb_voxelwise
+        return fn(C.byref(prob), C.byref(self.buf), stream)
+
+    def sync(self, stream=None):
+        check(lib().fabber_cuda_stream_sync(stream), "stream sync")
+
+    def results(self, stream=None):
+        out = {k: v.to_host(stream) for k, v in self.out.items()}
+        if self.ak is not None:
+            out["spatial_ak"] = self.ak.copy()
+        return out
+
+    def close(self):
+        for d in list(self.out.values()) + list(self.inputs.values()):
+            d.close()
+
+
+def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=None, init_cov=None,
+        init_noise=None):
+    """Convenience: host arrays in, host arrays out (same signature as the test oracle's run())."""
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    r = VbRun(spec, data.shape[1], spatial=spatial)
+    try:
+        r.set_data(data)
+        for k, img in (image_priors or {}).items():
+            r.set_image_prior(k, img)
+        r.set_initial(init_mean, init_cov, init_noise)
+        if coords is not None:
+            r.set_coords(coords)
+        rc = r.launch()
+        if rc not in (abi.OK, abi.ERR_BAD_VOXEL):
+            raise CudaError("VB launch failed (%d): %s" % (rc, last_error()))
+        r.sync()
+        out = r.results()
+        if rc == abi.OK and not spec.prob.allow_bad_voxels:
+            nbad = int(np.count_nonzero(out["status"]))
+            if nbad:
+                rc = abi.ERR_BAD_VOXEL
+        out["rc"] = rc
+        return out
+    finally:
+        r.close()

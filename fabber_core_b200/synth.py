@@ -1,0 +1,80 @@
+"""Synthetic volumes for the configurations in BASELINE.json.
+
+All generators return a float32 tensor in the C-API voxel layout [T][N] (row t = volume t, voxel
+index x fastest) on the requested torch device, filled row by row so that a 256^3 x 96 volume never
+needs more than one extra [N] temporary. The seeds are the ones SURVEY.md names.
+"""
+import math
+
+import numpy as np
+import torch
+
+
+def _gen(device, seed):
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    return g
+
+
+def poly_volume(n_voxels, n_times=64, degree=3, seed=1002, device="cpu"):
+    """C2: y = sum_n c_n i^n (i = 1..T) + N(0, 1); c0~U(50,150), c1~U(-2,2), c2~U(-.05,.05), c3~U(-5e-4,5e-4)."""
+    g = _gen(device, seed)
+    lo = [50.0, -2.0, -0.05, -5e-4] + [0.0] * 8
+    hi = [150.0, 2.0, 0.05, 5e-4] + [0.0] * 8
+    coef = [lo[n] + (hi[n] - lo[n]) * torch.rand(n_voxels, generator=g, device=device, dtype=torch.float64)
+            for n in range(degree + 1)]
+    y = torch.empty((n_times, n_voxels), dtype=torch.float32, device=device)
+    for t in range(n_times):
+        i = float(t + 1)
+        acc = torch.zeros(n_voxels, dtype=torch.float64, device=device)
+        for n in range(degree + 1):
+            acc += coef[n] * (i ** n)
+        acc += torch.randn(n_voxels, generator=g, device=device, dtype=torch.float64)
+        y[t] = acc.to(torch.float32)
+    return y
+
+
+def biexp_volume(n_voxels, n_times=96, dt=0.02, noise=0.02, seed=1003, device="cpu", smooth_shape=None):
+    """C3 (and C5 with smooth_shape=(nx,ny,nz)): y = amp1 exp(-r1 t) + 0.5 exp(-6 t) + N(0, noise^2).
+
+    Truth as in the reference's examples/test_biexp.py:17-22: amp1~U(0.5,1), r1~U(0.8,1), amp2=0.5, r2=6.
+    With smooth_shape the truth fields are the smooth ones of SURVEY.md 8d (C5)."""
+    g = _gen(device, seed)
+    if smooth_shape is None:
+        amp1 = 0.5 + 0.5 * torch.rand(n_voxels, generator=g, device=device, dtype=torch.float64)
+        r1 = 0.8 + 0.2 * torch.rand(n_voxels, generator=g, device=device, dtype=torch.float64)
+    else:
+        nx, ny, nz = smooth_shape
+        assert nx * ny * nz == n_voxels
+        idx = torch.arange(n_voxels, device=device)
+        x = (idx % nx).to(torch.float64)
+        yy = ((idx // nx) % ny).to(torch.float64)
+        z = (idx // (nx * ny)).to(torch.float64)
+        amp1 = 0.75 + 0.25 * torch.cos(2 * math.pi * x / 64) * torch.cos(2 * math.pi * yy / 64)
+        r1 = 0.9 + 0.1 * torch.sin(2 * math.pi * z / 64)
+    y = torch.empty((n_times, n_voxels), dtype=torch.float32, device=device)
+    for t in range(n_times):
+        tt = t * dt
+        acc = amp1 * torch.exp(-r1 * tt) + 0.5 * math.exp(-6.0 * tt)
+        acc += noise * torch.randn(n_voxels, generator=g, device=device, dtype=torch.float64)
+        y[t] = acc.to(torch.float32)
+    return y
+
+
+def ar_design(n_times=200):
+    """C4 design: columns 1, t/T, sin(2 pi t/50), cos(2 pi t/50)."""
+    t = np.arange(n_times, dtype=np.float64)
+    return np.stack([np.ones(n_times), t / n_times, np.sin(2 * np.pi * t / 50), np.cos(2 * np.pi * t / 50)], axis=1)
+
+
+def linear_ar_volume(n_voxels, n_times=200, rho=0.3, seed=1004, device="cpu"):
+    """C4: y = design beta + AR(1) noise (rho, unit innovations); beta ~ N(0, 100^2)^4."""
+    g = _gen(device, seed)
+    design = torch.as_tensor(ar_design(n_times), device=device)
+    beta = 100.0 * torch.randn((4, n_voxels), generator=g, device=device, dtype=torch.float64)
+    y = torch.empty((n_times, n_voxels), dtype=torch.float32, device=device)
+    e = torch.zeros(n_voxels, dtype=torch.float64, device=device)
+    for t in range(n_times):
+        e = rho * e + torch.randn(n_voxels, generator=g, device=device, dtype=torch.float64)
+        y[t] = (design[t] @ beta + e).to(torch.float32)
+    return y

@@ -204,6 +204,10 @@ double fabber_cuda_measure_fp64_peak(int repeats);
 /* Number of kernels this library has launched so far in this process. */
 unsigned long long fabber_cuda_launch_count(void);
 
+/* sizeof() of the two structs above as compiled, so language bindings can verify their mirror. */
+int fabber_cuda_sizeof_problem(void);
+int fabber_cuda_sizeof_buffers(void);
+
 #ifdef __cplusplus
 }
 #endif

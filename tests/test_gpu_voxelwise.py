@@ -1,0 +1,173 @@
+"""GPU parity: the CUDA voxelwise VB path (through the C ABI) against the CPU oracle and the
+reference's golden outputs. Run on the B200 box with `pytest -m gpu`."""
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from fabber_core_b200 import cuda_abi as abi
+from fabber_core_b200 import device, synth
+from parity import compare, tri
+
+pytestmark = pytest.mark.gpu
+
+
+def both(spec_kwargs, data, **run_kwargs):
+    model = spec_kwargs.pop("model")
+    n_times = data.shape[0]
+    ref = oracle.run(abi.ProblemSpec(model, n_times, **spec_kwargs), data, **run_kwargs)
+    gpu = device.run(abi.ProblemSpec(model, n_times, **spec_kwargs), data, **run_kwargs)
+    return gpu, ref
+
+
+def test_library_reports_device():
+    assert device.lib().fabber_cuda_device_count() >= 1
+
+
+def test_c1_linear_golden(golden):
+    gpu, ref = both(dict(model="linear", design=golden["design"]), golden["data"])
+    compare(gpu, ref, 4, check_f=False, label="C1 linear")
+    for i in range(4):
+        g = golden["linear_vb/mean_Parameter_%d" % (i + 1)][0]
+        assert np.max(np.abs(gpu["mean"][i] - g)) < 1e-3  # test/test_commandline.cc:10 ALLOWED_DELTA
+        assert np.max(np.abs(gpu["mean"][i] - g) / np.abs(g)) < 5e-6
+        z = gpu["mean"][i] / np.sqrt(gpu["cov"][tri(i, i)])
+        gz = golden["linear_vb/zstat_Parameter_%d" % (i + 1)][0]
+        assert np.max(np.abs(z - gz) / np.abs(gz)) < 5e-6
+
+
+def test_c1_poly_golden(golden):
+    gpu, ref = both(dict(model="poly", degree=2), golden["data"])
+    compare(gpu, ref, 3, check_f=False, label="C1 poly")
+    for i in range(3):
+        g = golden["poly/mean_c%d" % i][0]
+        assert np.max(np.abs(gpu["mean"][i] - g) / np.abs(g)) < 5e-6
+        gs = golden["poly/std_c%d" % i][0]
+        assert np.max(np.abs(np.sqrt(gpu["cov"][tri(i, i)]) - gs) / gs) < 5e-6
+
+
+@pytest.mark.parametrize("conv", ["maxits", "pointzeroone", "freduce", "trialmode", "lm"])
+def test_c2_poly_synthetic(conv):
+    y = synth.poly_volume(3000, 64, 3, seed=1002).numpy()
+    gpu, ref = both(dict(model="poly", degree=3, convergence=conv, need_f=True), y)
+    compare(gpu, ref, 4, label="C2 poly %s" % conv)
+
+
+@pytest.mark.parametrize("conv", ["maxits", "pointzeroone", "freduce", "trialmode", "lm"])
+def test_c3_biexp_synthetic(conv):
+    y = synth.biexp_volume(3000, 96, 0.02, 0.02, seed=1003).numpy()
+    gpu, ref = both(dict(model="exp", num_exps=2, dt=0.02, convergence=conv, need_f=True), y)
+    compare(gpu, ref, 4, label="C3 biexp %s" % conv)
+
+
+def test_c3_biexp_noisy_stress_allow_bad_voxels():
+    """noise 0.1 produces divergent voxels (doc/models.rst:473-489): masks and counts must still agree."""
+    y = synth.biexp_volume(2000, 96, 0.02, 0.1, seed=7).numpy()
+    gpu, ref = both(dict(model="exp", num_exps=2, dt=0.02, convergence="lm", need_f=True,
+                         allow_bad_voxels=True), y)
+    compare(gpu, ref, 4, label="C3 stress")
+
+
+@pytest.mark.parametrize("degree", [0, 1, 5, 7])
+def test_poly_other_sizes(degree):
+    y = synth.poly_volume(500, 40, min(degree, 3), seed=11).numpy()
+    gpu, ref = both(dict(model="poly", degree=degree, need_f=True), y)
+    compare(gpu, ref, degree + 1, label="poly degree %d" % degree, rtol=1e-5 if degree >= 5 else 1e-6)
+
+
+def test_constant_data_recovers_value():
+    """test/test_inference.cc:108-160: constant data -> mean == VAL to float precision."""
+    y = np.full((10, 7), 7.32, dtype=np.float32)
+    gpu, ref = both(dict(model="poly", degree=0), y)
+    assert np.allclose(gpu["mean"][0], np.float32(7.32), rtol=1e-6)
+    compare(gpu, ref, 1, check_f=False, label="constant")
+
+
+def test_noise_pattern_and_masked_timepoints():
+    y = synth.poly_volume(800, 64, 2, seed=5).numpy()
+    gpu, ref = both(dict(model="poly", degree=2, noise_pattern="12", masked_timepoints=(3, 10, 64),
+                         need_f=True, convergence="pointzeroone"), y)
+    compare(gpu, ref, 3, label="pattern+mask")
+
+
+def test_masked_timepoints_single_phi():
+    y = synth.poly_volume(800, 64, 2, seed=6).numpy()
+    y[4] = 1e4  # corrupt a sample, then mask it (test/test_inference.cc:485-560)
+    gpu, ref = both(dict(model="poly", degree=2, masked_timepoints=(5,), need_f=True), y)
+    compare(gpu, ref, 3, label="mask")
+
+
+def test_ard_and_image_priors():
+    rng = np.random.default_rng(3)
+    design = rng.standard_normal((50, 3))
+    beta = rng.standard_normal((3, 600)) * np.array([[10.0], [0.0], [5.0]])
+    y = (design @ beta + rng.standard_normal((50, 600))).astype(np.float32)
+    img = beta[2] + 0.1 * rng.standard_normal(600)
+    kw = dict(model="linear", design=design, prior_types=["N", "A", "I"], need_f=True,
+              param_overrides={"Parameter_3": {"prec": 4.0}}, convergence="trialmode")
+    gpu, ref = both(kw, y, image_priors={2: img})
+    compare(gpu, ref, 3, label="ARD+image")
+
+
+def test_noise_options():
+    y = synth.poly_volume(500, 64, 1, seed=8).numpy()
+    gpu, ref = both(dict(model="poly", degree=1, prior_noise_stddev=2.0, need_f=True), y)
+    compare(gpu, ref, 2, label="prior-noise-stddev")
+    gpu, ref = both(dict(model="poly", degree=1, locked_noise_stdev=1.5, need_f=True), y)
+    compare(gpu, ref, 2, label="locked-noise-stdev")
+
+
+def test_restart_from_mvn():
+    """continue-from-mvn (inference_vb.cc:181-216): second run starts from the first run's posterior."""
+    y = synth.biexp_volume(500, 96, 0.02, 0.02, seed=9).numpy()
+    kw = dict(model="exp", num_exps=2, dt=0.02, max_iterations=3, need_f=True)
+    first = oracle.run(abi.ProblemSpec("exp", 96, **{k: v for k, v in kw.items() if k != "model"}), y)
+    gpu, ref = both(dict(kw), y, init_mean=first["mean"], init_cov=first["cov"], init_noise=first["noise"])
+    compare(gpu, ref, 4, label="restart")
+
+
+def test_empty_volume_ok():
+    """test/test_inference.cc:57-73: zero voxels is not an error."""
+    spec = abi.ProblemSpec("poly", 10, degree=1)
+    out = device.run(spec, np.zeros((10, 0), dtype=np.float32))
+    assert out["rc"] == 0 and out["mean"].shape == (2, 0)
+
+
+def test_bad_voxel_halts_by_default():
+    y = synth.biexp_volume(64, 96, 0.02, 0.02, seed=10).numpy()
+    y[:, 5] = np.inf
+    gpu, ref = both(dict(model="exp", num_exps=2, dt=0.02), y)
+    assert ref["rc"] == abi.ERR_BAD_VOXEL and gpu["rc"] == abi.ERR_BAD_VOXEL
+    assert gpu["status"][5] == ref["status"][5] != 0
+
+
+def test_invalid_arguments_are_rejected():
+    spec = abi.ProblemSpec("poly", 10, degree=1, prior_types=["M", "N"])
+    with pytest.raises(device.CudaError):
+        device.run(spec, np.zeros((10, 4), dtype=np.float32))
+    spec = abi.ProblemSpec("poly", 10, degree=1, max_iterations=0)
+    with pytest.raises(device.CudaError):
+        device.run(spec, np.zeros((10, 4), dtype=np.float32))
+
+
+def test_full_size_properties_c2():
+    """Size-independent properties at BASELINE's C2 size (128^3 x 64): the fit of voxel i depends on
+    voxel i only, so a strided sample re-run as its own small volume must reproduce the big run bit for
+    bit, and that sample must match the oracle."""
+    n = 128 ** 3
+    y = synth.poly_volume(n, 64, 3, seed=1002, device="cuda")
+    spec = abi.ProblemSpec("poly", 64, degree=3)
+    run = device.VbRun(spec, n)
+    run.set_data_device(y.data_ptr())
+    assert run.launch(torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    big = run.results()
+    run.close()
+    assert np.all(big["status"] == 0) and np.all(big["iterations"] == 10)
+    pick = np.arange(0, n, 4099)
+    ys = y[:, torch.as_tensor(pick, device="cuda")].cpu().numpy()
+    small = device.run(abi.ProblemSpec("poly", 64, degree=3), ys)
+    for k in ("mean", "cov", "noise"):
+        assert np.array_equal(small[k], big[k][:, pick]), k
+    ref = oracle.run(abi.ProblemSpec("poly", 64, degree=3), ys)
+    compare(small, ref, 4, check_f=False, label="C2 full-size sample")
