@@ -20,7 +20,9 @@ template <int NPHI, bool SNAP> static cudaError_t launch_white(const VbArgs &a, 
 {
     if (a.N <= 0)
         return cudaSuccess;
-    const size_t smem = M::smem_bytes(a.T) + (NPHI > 1 ? (size_t)a.T : 0);
+    typedef WhiteVoxel<M, NPHI, SNAP> Vox;
+    const size_t smem = M::smem_bytes(a.T) + (size_t)(Vox::STASH_DOUBLES + Vox::SNAP_DOUBLES) * VB_BLOCK * sizeof(double)
+        + (NPHI > 1 ? (size_t)a.T : 0);
     auto kern = vb_voxelwise_white_kernel<M, NPHI, SNAP>;
     if (smem > 48 * 1024)
     {

@@ -56,10 +56,11 @@ template <int P_> struct LinearModel
     }
     static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])
     {
+        /* (0.0 + x) is x: the first add of the reference's zero-initialised accumulator is skipped */
         const double *row = c.design + t * P;
-        double s = 0.0;
+        double s = __dmul_rn(row[0], p[0]);
 #pragma unroll
-        for (int j = 0; j < P; j++)
+        for (int j = 1; j < P; j++)
             s = __dadd_rn(s, __dmul_rn(row[j], p[j]));
         return s;
     }
@@ -74,18 +75,25 @@ template <int P_> struct LinearModel
             d[j] = row[j];
             prod[j] = __dmul_rn(d[j], p0[j]);
         }
-        /* prefix[j] = sum of the first j products, in the reference's left-to-right order */
+        /* prefix[j] = sum of the first j products, in the reference's left-to-right order
+         * (prefix[1] = 0.0 + prod[0] = prod[0]: the add to the zero-initialised accumulator is skipped) */
         double prefix[P + 1];
         prefix[0] = 0.0;
+        prefix[1] = prod[0];
 #pragma unroll
-        for (int j = 0; j < P; j++)
+        for (int j = 1; j < P; j++)
             prefix[j + 1] = __dadd_rn(prefix[j], prod[j]);
         g = prefix[P];
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
-            double sp = __dadd_rn(prefix[i], __dmul_rn(d[i], pp[i]));
-            double sn = __dadd_rn(prefix[i], __dmul_rn(d[i], pn[i]));
+            double sp = __dmul_rn(d[i], pp[i]);
+            double sn = __dmul_rn(d[i], pn[i]);
+            if (i > 0)
+            {
+                sp = __dadd_rn(prefix[i], sp);
+                sn = __dadd_rn(prefix[i], sn);
+            }
 #pragma unroll
             for (int j = i + 1; j < P; j++)
             {
@@ -127,9 +135,9 @@ template <int P_> struct PolyModel
     {
         double pw[P];
         powers(t, pw);
-        double s = 0.0;
+        double s = __dmul_rn(p[0], pw[0]);
 #pragma unroll
-        for (int n = 0; n < P; n++)
+        for (int n = 1; n < P; n++)
             s = __dadd_rn(s, __dmul_rn(p[n], pw[n]));
         return s;
     }
@@ -143,14 +151,19 @@ template <int P_> struct PolyModel
         for (int j = 0; j < P; j++)
         {
             prod[j] = __dmul_rn(p0[j], pw[j]);
-            prefix[j + 1] = __dadd_rn(prefix[j], prod[j]);
+            prefix[j + 1] = j == 0 ? prod[0] : __dadd_rn(prefix[j], prod[j]);
         }
         g = prefix[P];
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
-            double sp = __dadd_rn(prefix[i], __dmul_rn(pp[i], pw[i]));
-            double sn = __dadd_rn(prefix[i], __dmul_rn(pn[i], pw[i]));
+            double sp = __dmul_rn(pp[i], pw[i]);
+            double sn = __dmul_rn(pn[i], pw[i]);
+            if (i > 0)
+            {
+                sp = __dadd_rn(prefix[i], sp);
+                sn = __dadd_rn(prefix[i], sn);
+            }
 #pragma unroll
             for (int j = i + 1; j < P; j++)
             {
@@ -188,9 +201,9 @@ template <int NE> struct ExpModel
     static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])
     {
         double tt = __dmul_rn((double)t, c.dt);
-        double s = 0.0;
+        double s = __dmul_rn(p[0], exp(__dmul_rn(-p[1], tt)));
 #pragma unroll
-        for (int k = 0; k < NE; k++)
+        for (int k = 1; k < NE; k++)
             s = __dadd_rn(s, __dmul_rn(p[2 * k], exp(__dmul_rn(-p[2 * k + 1], tt))));
         return s;
     }
@@ -205,9 +218,9 @@ template <int NE> struct ExpModel
             e0[k] = exp(__dmul_rn(-p0[2 * k + 1], tt));
             term[k] = __dmul_rn(p0[2 * k], e0[k]);
         }
-        double s = 0.0;
+        double s = term[0];
 #pragma unroll
-        for (int k = 0; k < NE; k++)
+        for (int k = 1; k < NE; k++)
             s = __dadd_rn(s, term[k]);
         g = s;
 #pragma unroll
@@ -223,9 +236,9 @@ template <int NE> struct ExpModel
 #pragma unroll
             for (int q = 0; q < 4; q++)
             {
-                double acc = 0.0;
+                double acc = (k == 0) ? ta[q] : term[0];
 #pragma unroll
-                for (int j = 0; j < NE; j++)
+                for (int j = 1; j < NE; j++)
                     acc = __dadd_rn(acc, j == k ? ta[q] : term[j]);
                 out[q] = acc;
             }

@@ -28,6 +28,7 @@ namespace fab
 {
 #define FAB_MAX_PHIS FABBER_CUDA_MAX_PHIS
 #define FAB_PAT_MASKED 255
+constexpr int VB_BLOCK = 128;
 
 /* Kernel argument block (passed by value as a __grid_constant__ parameter; < 4 KB). */
 struct VbArgs
@@ -114,10 +115,13 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
     bool bad_g = false, bad_j = false;
     const float *yp = a.data + v;
     const size_t stride = (size_t)a.N;
+    float ynext = __ldg(yp);
 #pragma unroll 1
     for (int t = 0; t < a.T; t++)
     {
-        const double y = (double)__ldg(yp + t * stride);
+        const double y = (double)ynext;
+        if (t + 1 < a.T) /* software prefetch: the load of sample t+1 overlaps the arithmetic of sample t */
+            ynext = __ldg(yp + (size_t)(t + 1) * stride);
         double g, gp[P], gn[P], J[P];
         Model::eval_fd(mc, t, p0, pp, pn, g, gp, gn);
         bad_g = bad_g || !finite_d(g);
@@ -195,46 +199,99 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
     double m[P], Lam[NT], Sig[NT], m0[P], L0[P], nb[NPHI], nc[NPHI];
     double logdetLam;
 
-    struct Snapshot
+    /* Shared-memory parking. The state above (~40 doubles at P = 4) is dead during the pass over the
+     * time-series; left in registers it would cost ~80 registers of occupancy in the hot loop. It is
+     * parked in shared memory around the pass instead ([slot][thread] layout: conflict-free 64-bit
+     * accesses; volatile so the compiler cannot forward the values through registers).
+     * The trialmode / freduce snapshot (inference_vb.cc:432-434,451-458) lives there permanently. */
+    static constexpr int STASH_DOUBLES = 3 * P + 2 * NT + 2 * NPHI + 1;
+    static constexpr int SNAP_DOUBLES = SNAP ? 3 * P + NT + 2 * NPHI : 0;
+    FAB_DEV void stash(volatile double *s) const
     {
-        double m[P], Lam[NT], m0[P], L0[P], nb[NPHI], nc[NPHI];
-    };
-    FAB_DEV void save(Snapshot &s) const
-    {
+        int k = 0;
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
-            s.m[i] = m[i];
-            s.m0[i] = m0[i];
-            s.L0[i] = L0[i];
+            s[(k++) * VB_BLOCK] = m[i];
+            s[(k++) * VB_BLOCK] = m0[i];
+            s[(k++) * VB_BLOCK] = L0[i];
         }
 #pragma unroll
         for (int i = 0; i < NT; i++)
-            s.Lam[i] = Lam[i];
+        {
+            s[(k++) * VB_BLOCK] = Lam[i];
+            s[(k++) * VB_BLOCK] = Sig[i];
+        }
 #pragma unroll
         for (int i = 0; i < NPHI; i++)
         {
-            s.nb[i] = nb[i];
-            s.nc[i] = nc[i];
+            s[(k++) * VB_BLOCK] = nb[i];
+            s[(k++) * VB_BLOCK] = nc[i];
+        }
+        s[(k++) * VB_BLOCK] = logdetLam;
+    }
+    FAB_DEV void unstash(const volatile double *s)
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            m[i] = s[(k++) * VB_BLOCK];
+            m0[i] = s[(k++) * VB_BLOCK];
+            L0[i] = s[(k++) * VB_BLOCK];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+        {
+            Lam[i] = s[(k++) * VB_BLOCK];
+            Sig[i] = s[(k++) * VB_BLOCK];
+        }
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            nb[i] = s[(k++) * VB_BLOCK];
+            nc[i] = s[(k++) * VB_BLOCK];
+        }
+        logdetLam = s[(k++) * VB_BLOCK];
+    }
+    FAB_DEV void save(volatile double *s) const
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            s[(k++) * VB_BLOCK] = m[i];
+            s[(k++) * VB_BLOCK] = m0[i];
+            s[(k++) * VB_BLOCK] = L0[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            s[(k++) * VB_BLOCK] = Lam[i];
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            s[(k++) * VB_BLOCK] = nb[i];
+            s[(k++) * VB_BLOCK] = nc[i];
         }
     }
-    FAB_DEV void restore(const Snapshot &s)
+    FAB_DEV void restore(const volatile double *s)
     {
+        int k = 0;
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
-            m[i] = s.m[i];
-            m0[i] = s.m0[i];
-            L0[i] = s.L0[i];
+            m[i] = s[(k++) * VB_BLOCK];
+            m0[i] = s[(k++) * VB_BLOCK];
+            L0[i] = s[(k++) * VB_BLOCK];
         }
 #pragma unroll
         for (int i = 0; i < NT; i++)
-            Lam[i] = s.Lam[i];
+            Lam[i] = s[(k++) * VB_BLOCK];
 #pragma unroll
         for (int i = 0; i < NPHI; i++)
         {
-            nb[i] = s.nb[i];
-            nc[i] = s.nc[i];
+            nb[i] = s[(k++) * VB_BLOCK];
+            nc[i] = s[(k++) * VB_BLOCK];
         }
     }
 
@@ -354,16 +411,22 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
     }
 };
 
-constexpr int VB_BLOCK = 128;
-
+#ifndef FAB_MIN_BLOCKS
+#define FAB_MIN_BLOCKS 3 /* measured on B200: 3 x 128 threads/SM (<=168 regs, no spills) beats 2 and 4, profiles/ */
+#endif
 template <class Model, int NPHI, bool SNAP>
-__global__ void __launch_bounds__(VB_BLOCK) vb_voxelwise_white_kernel(const __grid_constant__ VbArgs a)
+__global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_white_kernel(const __grid_constant__ VbArgs a)
 {
     constexpr int P = Model::P;
     constexpr int NT = NTri<P>::value;
     extern __shared__ double smem[];
     Model::stage(a, smem);
-    unsigned char *pat = reinterpret_cast<unsigned char *>(smem) + Model::smem_bytes(a.T);
+    typedef WhiteVoxel<Model, NPHI, SNAP> Vox;
+    /* dynamic shared memory: [model constants][state parking][snapshot][noise pattern] */
+    volatile double *park = smem + Model::smem_bytes(a.T) / sizeof(double) + threadIdx.x;
+    volatile double *snap = park + Vox::STASH_DOUBLES * VB_BLOCK;
+    unsigned char *pat = reinterpret_cast<unsigned char *>(
+        smem + Model::smem_bytes(a.T) / sizeof(double) + (Vox::STASH_DOUBLES + Vox::SNAP_DOUBLES) * VB_BLOCK);
     if (NPHI > 1)
         for (int i = threadIdx.x; i < a.T; i += blockDim.x)
             pat[i] = a.pattern ? a.pattern[i] : 0;
@@ -374,7 +437,7 @@ __global__ void __launch_bounds__(VB_BLOCK) vb_voxelwise_white_kernel(const __gr
     const typename Model::Ctx mc = Model::make_ctx(a, smem);
     const size_t N = (size_t)a.N;
 
-    WhiteVoxel<Model, NPHI, SNAP> X;
+    Vox X;
     int status = 0;
     double F = 1234.5678; /* inference_vb.cc:438 */
     int it = 0;
@@ -436,45 +499,45 @@ __global__ void __launch_bounds__(VB_BLOCK) vb_voxelwise_white_kernel(const __gr
         X.L0[i] = 1.0;
     }
 
+    /* One call site for the pass over the time-series (keeps the hot loop a single copy in the
+     * instruction cache): a small state machine walks set-up -> iterations -> optional revert.
+     *   SETUP  : ReCentre of SetupPerVoxelDists (:235). A failure here is never caught by the reference.
+     *            The second ReCentre at :443 recomputes the same values from the same centre.
+     *   ITER   : ReCentre at the end of an iteration (:490), then F, ++it and Test() (:495-500).
+     *   REVERT : ReCentre + F after restoring the snapshot (:516-525).                              */
+    enum
+    {
+        PH_SETUP,
+        PH_ITER,
+        PH_REVERT
+    };
     Stats<P> S[NPHI];
     double c[P];
-#pragma unroll
-    for (int i = 0; i < P; i++)
-        c[i] = X.m[i];
-    if (status == 0)
+    Conv conv;
+    conv.init(a.conv_type, a.max_iterations, a.fchange, a.max_trials);
+    double Fprior = 0.0;
+    int phase = PH_SETUP;
+    while (status == 0)
     {
-        /* ReCentre at :235 (set-up: a failure here is never caught by the reference). The second
-         * ReCentre at :443 recomputes the same values from the same centre. */
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            c[i] = X.m[i];
+        X.stash(park);
         const int err = recentre_stats<Model, NPHI>(a, mc, pat, v, c, S);
-        if (err)
-            status = err | FABBER_VOX_SETUP_FLAG;
-    }
-
-    if (status == 0)
-    {
-        Conv conv;
-        conv.init(a.conv_type, a.max_iterations, a.fchange, a.max_trials);
-        typename WhiteVoxel<Model, NPHI, SNAP>::Snapshot snap;
-        if (SNAP)
-            X.save(snap); /* pre-loop copies, inference_vb.cc:432-434 */
-        double Fprior = 0.0;
-        do
+        X.unstash(park);
+        if (phase == PH_SETUP)
         {
-            if (SNAP && conv.need_save())
-                X.save(snap);
-#pragma unroll
-            for (int k = 0; k < P; k++)
-                Fprior = X.apply_prior(a, k, v, it); /* '=' not '+=': inference_vb.cc:462 */
-            if (!X.update_theta(a, S, c, conv.lm_alpha()))
+            if (err)
             {
-                status = FABBER_VOX_SINGULAR;
+                status = err | FABBER_VOX_SETUP_FLAG;
                 break;
             }
-            X.update_noise(a, S, c);
-#pragma unroll
-            for (int i = 0; i < P; i++)
-                c[i] = X.m[i];
-            const int err = recentre_stats<Model, NPHI>(a, mc, pat, v, c, S);
+            if (SNAP)
+                X.save(snap); /* pre-loop copies, inference_vb.cc:432-434 */
+            phase = PH_ITER;
+        }
+        else
+        {
             if (err)
             {
                 status = err;
@@ -489,37 +552,48 @@ __global__ void __launch_bounds__(VB_BLOCK) vb_voxelwise_white_kernel(const __gr
                     break;
                 }
             }
+            if (phase == PH_REVERT)
+                break;
             if (a.f_history && it < a.f_history_len)
                 a.f_history[it * N + v] = F;
             ++it;
-        } while (!conv.test(F));
-
-        if (status == 0 && SNAP)
-        {
-            if (conv.need_save())
-                X.save(snap);
-            if (conv.need_revert())
+            if (conv.test(F))
             {
-                X.restore(snap);
-                if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam))
-                    status = FABBER_VOX_SINGULAR;
-#pragma unroll
-                for (int i = 0; i < P; i++)
-                    c[i] = X.m[i];
-                const int err = status ? 0 : recentre_stats<Model, NPHI>(a, mc, pat, v, c, S);
-                if (err)
-                    status = err;
-                else if (status == 0 && a.need_f)
+                /* LM: m_save is always true (convergence.cc:270), so the snapshot taken after the
+                 * loop (:506-513) is the current state and the revert at :516-525 restores exactly
+                 * that, re-centres on the same means and recomputes the same F: a no-op on every
+                 * output, so only detectors with a real snapshot (SNAP) take the revert path. */
+                if (SNAP)
                 {
-                    F = white_free_energy<P, NPHI>(a, S, X.m, X.Sig, X.logdetLam, X.m0, X.L0, X.nb, X.nc) + Fprior;
-                    if (!finite_d(F))
-                        status = FABBER_VOX_NONFINITE_F;
+                    if (conv.need_save())
+                        X.save(snap);
+                    if (conv.need_revert())
+                    {
+                        X.restore(snap);
+                        if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam))
+                        {
+                            status = FABBER_VOX_SINGULAR;
+                            break;
+                        }
+                        phase = PH_REVERT;
+                        continue;
+                    }
                 }
+                break;
             }
         }
-        /* LM: m_save is always true (convergence.cc:270), so the snapshot taken after the loop
-         * (:506-513) is the current state and the revert at :516-525 restores exactly that,
-         * re-centres on the same means and recomputes the same F - a no-op on every output. */
+        /* ---- one VB iteration: priors, theta, noise (inference_vb.cc:451-480) ---- */
+        if (SNAP && conv.need_save())
+            X.save(snap);
+#pragma unroll
+        for (int k = 0; k < P; k++)
+            Fprior = X.apply_prior(a, k, v, it); /* '=' not '+=': inference_vb.cc:462 */
+        if (!X.update_theta(a, S, c, conv.lm_alpha()))
+        {
+            status = FABBER_VOX_SINGULAR;
+            break;
+        }
+        X.update_noise(a, S, c);
     }
 
     /* ---- results (inference_vb.cc:546-570; padded F history :1041-1044) ----------------------- */

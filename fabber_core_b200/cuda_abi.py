@@ -254,5 +254,7 @@ class ProblemSpec(object):
 
 
 def library_path():
+    if os.environ.get("FABBER_CUDA_LIB"):  # developer knob: kernel-tuning builds (csrc/Makefile SUBSET=1)
+        return os.environ["FABBER_CUDA_LIB"]
     here = os.path.dirname(os.path.abspath(__file__))
     return os.path.join(here, "csrc", "libfabber_cuda.so")

@@ -12,25 +12,28 @@ import numpy as np
 from fabber_core_b200 import cuda_abi as abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = None
+_LIBS = {}
 
 
 def build():
     subprocess.check_call(["make", "-s", "-C", _HERE])
 
 
-def lib():
-    global _LIB
-    if _LIB is None:
-        path = os.path.join(_HERE, "_build", "libvb_oracle.so")
+def lib(variant=""):
+    """variant "" = the oracle proper; "fma" / "ulp" = noise-floor probes (same source with FMA
+    contraction / with the model's exp() perturbed by <= 1 ULP, see oracle/Makefile)."""
+    if variant not in _LIBS:
+        name = {"fma": "libvb_oracle_fma.so", "ulp": "libvb_oracle_ulp.so"}.get(variant, "libvb_oracle.so")
+        path = os.path.join(_HERE, "_build", name)
         if not os.path.exists(path):
             build()
-        _LIB = C.CDLL(path)
-        _LIB.vb_oracle_gammaln.restype = C.c_double
-        _LIB.vb_oracle_gammaln.argtypes = [C.c_double]
-        _LIB.vb_oracle_digamma.restype = C.c_double
-        _LIB.vb_oracle_digamma.argtypes = [C.c_double]
-    return _LIB
+        L = C.CDLL(path)
+        L.vb_oracle_gammaln.restype = C.c_double
+        L.vb_oracle_gammaln.argtypes = [C.c_double]
+        L.vb_oracle_digamma.restype = C.c_double
+        L.vb_oracle_digamma.argtypes = [C.c_double]
+        _LIBS[variant] = L
+    return _LIBS[variant]
 
 
 def _ptr(a):
@@ -38,7 +41,7 @@ def _ptr(a):
 
 
 def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=None, init_cov=None,
-        init_noise=None):
+        init_noise=None, variant=""):
     """Run the oracle. data: float32 [T][N]. Returns dict of numpy arrays (see fabber_cuda.h layouts)."""
     data = np.ascontiguousarray(data, dtype=np.float32)
     T, N = data.shape
@@ -83,7 +86,7 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
     buf.free_energy = out["free_energy"].ctypes.data
     buf.iterations = out["iterations"].ctypes.data
     buf.status = out["status"].ctypes.data
-    fn = lib().vb_oracle_spatial if spatial else lib().vb_oracle_voxelwise
+    fn = lib(variant).vb_oracle_spatial if spatial else lib(variant).vb_oracle_voxelwise
     fn.restype = C.c_int
     rc = fn(C.byref(prob), C.byref(buf))
     out["rc"] = rc

@@ -430,6 +430,29 @@ struct ModelCtx
     int T, P;
 };
 
+// Noise-floor probe only (oracle/Makefile target libvb_oracle_ulp.so, -DORACLE_EXP_ULP_PROBE): model
+// the forward model being linked against a different, equally valid libm whose exp() is accurate to
+// <= 1 ULP instead of glibc's: half of the results are moved to an adjacent double, chosen by a hash of
+// the bits. Never defined for the oracle proper.
+inline double model_exp(double x)
+{
+    double e = std::exp(x);
+#ifdef ORACLE_EXP_ULP_PROBE
+    unsigned long long u;
+    std::memcpy(&u, &e, sizeof(u));
+    unsigned long long h = u * 0x9E3779B97F4A7C15ull;
+    h ^= h >> 29;
+    if (std::isfinite(e) && e != 0.0)
+    {
+        if ((h & 3ull) == 1ull)
+            e = std::nextafter(e, INFINITY);
+        else if ((h & 3ull) == 2ull)
+            e = std::nextafter(e, -INFINITY);
+    }
+#endif
+    return e;
+}
+
 void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
 {
     const fabber_cuda_model &m = mc.prob->model;
@@ -471,7 +494,7 @@ void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
             for (int i = 0; i < T; i++)
             {
                 double t = double(i) * m.exp_dt;
-                double val = amp * std::exp(-r * t);
+                double val = amp * model_exp(-r * t);
                 result[i] += val;
             }
         }

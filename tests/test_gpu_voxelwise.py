@@ -12,12 +12,26 @@ from parity import compare, tri
 pytestmark = pytest.mark.gpu
 
 
-def both(spec_kwargs, data, **run_kwargs):
+# biexp with the reference's default priors starts both exponentials at the same rate: the fit then
+# relies on rounding noise to break the symmetry and is chaotic in the reference itself (two CPU builds
+# of the oracle disagree by O(1)). A prior mean on r2 (--PSP_byname1=r2
+# --PSP_byname1_mean=6) makes the problem well posed; that is the C3 configuration used throughout.
+C3 = dict(model="exp", num_exps=2, dt=0.02, param_overrides={"r2": {"mean": 6.0}})
+
+
+def both(spec_kwargs, data, floor=True, **run_kwargs):
+    """-> (gpu, oracle, [oracle noise-floor probes]) on the same inputs"""
+    spec_kwargs = dict(spec_kwargs)
     model = spec_kwargs.pop("model")
     n_times = data.shape[0]
     ref = oracle.run(abi.ProblemSpec(model, n_times, **spec_kwargs), data, **run_kwargs)
+    probes = None
+    if floor:
+        variants = ("fma", "ulp") if model == "exp" else ("fma",)
+        probes = [oracle.run(abi.ProblemSpec(model, n_times, **spec_kwargs), data, variant=vr, **run_kwargs)
+                  for vr in variants]
     gpu = device.run(abi.ProblemSpec(model, n_times, **spec_kwargs), data, **run_kwargs)
-    return gpu, ref
+    return gpu, ref, probes
 
 
 def test_library_reports_device():
@@ -25,8 +39,8 @@ def test_library_reports_device():
 
 
 def test_c1_linear_golden(golden):
-    gpu, ref = both(dict(model="linear", design=golden["design"]), golden["data"])
-    compare(gpu, ref, 4, check_f=False, label="C1 linear")
+    gpu, ref, fma = both(dict(model="linear", design=golden["design"]), golden["data"])
+    compare(gpu, ref, 4, fma, check_f=False, label="C1 linear")
     for i in range(4):
         g = golden["linear_vb/mean_Parameter_%d" % (i + 1)][0]
         assert np.max(np.abs(gpu["mean"][i] - g)) < 1e-3  # test/test_commandline.cc:10 ALLOWED_DELTA
@@ -37,8 +51,8 @@ def test_c1_linear_golden(golden):
 
 
 def test_c1_poly_golden(golden):
-    gpu, ref = both(dict(model="poly", degree=2), golden["data"])
-    compare(gpu, ref, 3, check_f=False, label="C1 poly")
+    gpu, ref, fma = both(dict(model="poly", degree=2), golden["data"])
+    compare(gpu, ref, 3, fma, check_f=False, label="C1 poly")
     for i in range(3):
         g = golden["poly/mean_c%d" % i][0]
         assert np.max(np.abs(gpu["mean"][i] - g) / np.abs(g)) < 5e-6
@@ -49,52 +63,60 @@ def test_c1_poly_golden(golden):
 @pytest.mark.parametrize("conv", ["maxits", "pointzeroone", "freduce", "trialmode", "lm"])
 def test_c2_poly_synthetic(conv):
     y = synth.poly_volume(3000, 64, 3, seed=1002).numpy()
-    gpu, ref = both(dict(model="poly", degree=3, convergence=conv, need_f=True), y)
-    compare(gpu, ref, 4, label="C2 poly %s" % conv)
+    gpu, ref, fma = both(dict(model="poly", degree=3, convergence=conv, need_f=True), y)
+    compare(gpu, ref, 4, fma, label="C2 poly %s" % conv)
 
 
 @pytest.mark.parametrize("conv", ["maxits", "pointzeroone", "freduce", "trialmode", "lm"])
 def test_c3_biexp_synthetic(conv):
     y = synth.biexp_volume(3000, 96, 0.02, 0.02, seed=1003).numpy()
-    gpu, ref = both(dict(model="exp", num_exps=2, dt=0.02, convergence=conv, need_f=True), y)
-    compare(gpu, ref, 4, label="C3 biexp %s" % conv)
+    gpu, ref, fma = both(dict(C3, convergence=conv, need_f=True, allow_bad_voxels=True), y)
+    compare(gpu, ref, 4, fma, label="C3 biexp %s" % conv)
 
 
 def test_c3_biexp_noisy_stress_allow_bad_voxels():
-    """noise 0.1 produces divergent voxels (doc/models.rst:473-489): masks and counts must still agree."""
+    """noise 0.1 (the reference example's level, examples/test_biexp.py): masks and counts must agree
+    wherever the two CPU builds agree with each other."""
     y = synth.biexp_volume(2000, 96, 0.02, 0.1, seed=7).numpy()
-    gpu, ref = both(dict(model="exp", num_exps=2, dt=0.02, convergence="lm", need_f=True,
-                         allow_bad_voxels=True), y)
-    compare(gpu, ref, 4, label="C3 stress")
+    gpu, ref, fma = both(dict(C3, convergence="lm", need_f=True, allow_bad_voxels=True), y)
+    compare(gpu, ref, 4, fma, label="C3 stress noise 0.1", max_ambiguous=0.05)
+
+
+def test_biexp_default_priors_first_iterations():
+    """With the reference's default (symmetric) priors only the first iterations are reproducible by
+    any implementation; pin those: centre == 0 makes the FD step 1e-10, i.e. ~1e-6 Jacobian noise."""
+    y = synth.biexp_volume(1000, 96, 0.02, 0.02, seed=1003).numpy()
+    gpu, ref, fma = both(dict(model="exp", num_exps=2, dt=0.02, max_iterations=2, need_f=True), y)
+    compare(gpu, ref, 4, fma, label="biexp default priors, 2 iterations")
 
 
 @pytest.mark.parametrize("degree", [0, 1, 5, 7])
 def test_poly_other_sizes(degree):
     y = synth.poly_volume(500, 40, min(degree, 3), seed=11).numpy()
-    gpu, ref = both(dict(model="poly", degree=degree, need_f=True), y)
-    compare(gpu, ref, degree + 1, label="poly degree %d" % degree, rtol=1e-5 if degree >= 5 else 1e-6)
+    gpu, ref, fma = both(dict(model="poly", degree=degree, need_f=True), y)
+    compare(gpu, ref, degree + 1, fma, label="poly degree %d" % degree)
 
 
 def test_constant_data_recovers_value():
     """test/test_inference.cc:108-160: constant data -> mean == VAL to float precision."""
     y = np.full((10, 7), 7.32, dtype=np.float32)
-    gpu, ref = both(dict(model="poly", degree=0), y)
+    gpu, ref, fma = both(dict(model="poly", degree=0), y)
     assert np.allclose(gpu["mean"][0], np.float32(7.32), rtol=1e-6)
-    compare(gpu, ref, 1, check_f=False, label="constant")
+    compare(gpu, ref, 1, fma, check_f=False, label="constant")
 
 
 def test_noise_pattern_and_masked_timepoints():
     y = synth.poly_volume(800, 64, 2, seed=5).numpy()
-    gpu, ref = both(dict(model="poly", degree=2, noise_pattern="12", masked_timepoints=(3, 10, 64),
-                         need_f=True, convergence="pointzeroone"), y)
-    compare(gpu, ref, 3, label="pattern+mask")
+    gpu, ref, fma = both(dict(model="poly", degree=2, noise_pattern="12", masked_timepoints=(3, 10, 64),
+                              need_f=True, convergence="pointzeroone"), y)
+    compare(gpu, ref, 3, fma, label="pattern+mask")
 
 
 def test_masked_timepoints_single_phi():
     y = synth.poly_volume(800, 64, 2, seed=6).numpy()
     y[4] = 1e4  # corrupt a sample, then mask it (test/test_inference.cc:485-560)
-    gpu, ref = both(dict(model="poly", degree=2, masked_timepoints=(5,), need_f=True), y)
-    compare(gpu, ref, 3, label="mask")
+    gpu, ref, fma = both(dict(model="poly", degree=2, masked_timepoints=(5,), need_f=True), y)
+    compare(gpu, ref, 3, fma, label="mask")
 
 
 def test_ard_and_image_priors():
@@ -105,25 +127,25 @@ def test_ard_and_image_priors():
     img = beta[2] + 0.1 * rng.standard_normal(600)
     kw = dict(model="linear", design=design, prior_types=["N", "A", "I"], need_f=True,
               param_overrides={"Parameter_3": {"prec": 4.0}}, convergence="trialmode")
-    gpu, ref = both(kw, y, image_priors={2: img})
-    compare(gpu, ref, 3, label="ARD+image")
+    gpu, ref, fma = both(kw, y, image_priors={2: img})
+    compare(gpu, ref, 3, fma, label="ARD+image")
 
 
 def test_noise_options():
     y = synth.poly_volume(500, 64, 1, seed=8).numpy()
-    gpu, ref = both(dict(model="poly", degree=1, prior_noise_stddev=2.0, need_f=True), y)
-    compare(gpu, ref, 2, label="prior-noise-stddev")
-    gpu, ref = both(dict(model="poly", degree=1, locked_noise_stdev=1.5, need_f=True), y)
-    compare(gpu, ref, 2, label="locked-noise-stdev")
+    gpu, ref, fma = both(dict(model="poly", degree=1, prior_noise_stddev=2.0, need_f=True), y)
+    compare(gpu, ref, 2, fma, label="prior-noise-stddev")
+    gpu, ref, fma = both(dict(model="poly", degree=1, locked_noise_stdev=1.5, need_f=True), y)
+    compare(gpu, ref, 2, fma, label="locked-noise-stdev")
 
 
 def test_restart_from_mvn():
     """continue-from-mvn (inference_vb.cc:181-216): second run starts from the first run's posterior."""
     y = synth.biexp_volume(500, 96, 0.02, 0.02, seed=9).numpy()
-    kw = dict(model="exp", num_exps=2, dt=0.02, max_iterations=3, need_f=True)
+    kw = dict(C3, max_iterations=3, need_f=True)
     first = oracle.run(abi.ProblemSpec("exp", 96, **{k: v for k, v in kw.items() if k != "model"}), y)
-    gpu, ref = both(dict(kw), y, init_mean=first["mean"], init_cov=first["cov"], init_noise=first["noise"])
-    compare(gpu, ref, 4, label="restart")
+    gpu, ref, fma = both(kw, y, init_mean=first["mean"], init_cov=first["cov"], init_noise=first["noise"])
+    compare(gpu, ref, 4, fma, label="restart")
 
 
 def test_empty_volume_ok():
@@ -136,7 +158,7 @@ def test_empty_volume_ok():
 def test_bad_voxel_halts_by_default():
     y = synth.biexp_volume(64, 96, 0.02, 0.02, seed=10).numpy()
     y[:, 5] = np.inf
-    gpu, ref = both(dict(model="exp", num_exps=2, dt=0.02), y)
+    gpu, ref, _ = both(dict(C3), y, floor=False)
     assert ref["rc"] == abi.ERR_BAD_VOXEL and gpu["rc"] == abi.ERR_BAD_VOXEL
     assert gpu["status"][5] == ref["status"][5] != 0
 
@@ -170,4 +192,5 @@ def test_full_size_properties_c2():
     for k in ("mean", "cov", "noise"):
         assert np.array_equal(small[k], big[k][:, pick]), k
     ref = oracle.run(abi.ProblemSpec("poly", 64, degree=3), ys)
-    compare(small, ref, 4, check_f=False, label="C2 full-size sample")
+    fma = oracle.run(abi.ProblemSpec("poly", 64, degree=3), ys, variant="fma")
+    compare(small, ref, 4, fma, check_f=False, label="C2 full-size sample")
