@@ -35,12 +35,26 @@ WORKLOADS = {
                     "synthetic 256^3 x 96", side=256, T=96, model="exp",
                spec=dict(num_exps=2, dt=0.02, convergence="lm", need_f=True,
                          param_overrides={"r2": {"mean": 6.0}}), P=4, e=46, e0=80),
+    # BASELINE.json configs[3]: linear model (synthetic 200 x 4 design), AR(1) noise, synthetic 256^3 x 200
+    # (the reference has no AR(2): Ar1cNoiseModel only, setup.cc:39)
+    "c4": dict(name="C4 linear(200x4 design) VB AR(1) noise (num-echoes 1, cross-terms none), synthetic "
+                    "256^3 x 200, maxits 10", side=256, T=200, model="linear", spec=dict(noise="ar"), P=4, e=8, e0=0,
+               flops=35900),
+    # BASELINE.json configs[4]: spatialvb (MRF spatial prior 'M' on every parameter), biexp, smooth synthetic
+    # 256^3 x 96. NB the reference's CovarianceCache is dead code; the MRF prior is
+    # SpatialPrior in priors.cc.
+    "c5": dict(name="C5 exp(num-exps 2, dt 0.02, PSP_byname r2 mean 6) spatialvb, param-spatial-priors=M+, "
+                    "smooth synthetic 256^3 x 96, maxits 10", side=256, T=96, model="exp", spatial=True,
+               spec=dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), param_overrides={"r2": {"mean": 6.0}}),
+               P=4, e=46, e0=80),
 }
 
 
 def algorithmic_flops(w):
     """FLOP per voxel-iteration of the minimal algorithm (FMA = 2, div = sqrt = 10,
     exp = log = 20): (2P+1)(T e + e0) + 2TP + T[P(P+1) + 2P + 3] + (2P^3 + 10P^2 + 300)."""
+    if "flops" in w:  # AR(1): statistics tripled + 2x2 alpha algebra, SURVEY.md 8(d): 35.9 kFLOP
+        return w["flops"]
     P, T, e, e0 = w["P"], w["T"], w["e"], w["e0"]
     return (2 * P + 1) * (T * e + e0) + 2 * T * P + T * (P * (P + 1) + 2 * P + 3) + (2 * P ** 3 + 10 * P ** 2 + 300)
 
@@ -48,6 +62,8 @@ def algorithmic_flops(w):
 def algorithmic_bytes(w, n_iter):
     """HBM bytes per voxel-iteration, all iterations fused (y read once, results written once)."""
     P, T = w["P"], w["T"]
+    if w.get("spatial"):  # iteration-at-a-time: y + the per-voxel state round trip each iteration
+        return 4 * T + 16 * (P + P * (P + 1) // 2 + 2) + 8
     return (4 * T + 4 * ((P + 1) * (P + 2) // 2 + (P + 1) + 1) + 16) / max(n_iter, 1e-9)
 
 
@@ -56,13 +72,29 @@ def make_volume(w, n_voxels, device, seed_offset=0):
 
     if w["model"] == "poly":
         return synth.poly_volume(n_voxels, w["T"], 3, seed=1002 + seed_offset, device=device)
+    if w["model"] == "linear":
+        return synth.linear_ar_volume(n_voxels, w["T"], 0.3, seed=1004 + seed_offset, device=device)
+    if w.get("spatial"):
+        side = round(n_voxels ** (1.0 / 3))
+        assert side ** 3 == n_voxels, "spatial workloads need a cubic voxel count"
+        return synth.biexp_volume(n_voxels, w["T"], 0.02, 0.02, seed=1005 + seed_offset, device=device,
+                                  smooth_shape=(side, side, side))
     return synth.biexp_volume(n_voxels, w["T"], 0.02, 0.02, seed=1003 + seed_offset, device=device)
 
 
-def make_spec(w):
+def make_spec(w, n_voxels=0):
     from fabber_core_b200 import cuda_abi as abi
 
-    return abi.ProblemSpec(w["model"], w["T"], **w["spec"])
+    from fabber_core_b200 import synth
+
+    spec = dict(w["spec"])
+    if w["model"] == "linear":
+        spec["design"] = synth.ar_design(w["T"])
+    ps = abi.ProblemSpec(w["model"], w["T"], **spec)
+    if w.get("spatial") and n_voxels:
+        side = round(n_voxels ** (1.0 / 3))
+        ps.prob.nx = ps.prob.ny = ps.prob.nz = side
+    return ps
 
 
 class ClockSampler(object):
@@ -108,30 +140,44 @@ class ClockSampler(object):
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def oracle_run(w, y):
+    import oracle
+
+    n = y.shape[1]
+    if not w.get("spatial"):
+        return oracle.run(make_spec(w), y)
+    side = round(n ** (1.0 / 3))
+    idx = np.arange(n)
+    coords = np.stack([idx % side, (idx // side) % side, idx // (side * side)]).astype(np.int32)
+    return oracle.run(make_spec(w, n), y, spatial=True, coords=coords)
+
+
 def oracle_throughput(w, threads, budget_s):
     """Voxel-iterations/s of the CPU oracle (port of the reference's algorithm) on a bounded sample."""
     import oracle
     from concurrent.futures import ThreadPoolExecutor
 
     oracle.lib()
-    probe_n = 256
+    probe_n = 343 if w.get("spatial") else 256
 
     def run_chunk(seed):
         def f(n):
             y = make_volume(w, n, "cpu", seed_offset=seed).numpy()
             t0 = time.perf_counter()
-            out = oracle.run(make_spec(w), y)
+            out = oracle_run(w, y)
             return time.perf_counter() - t0, int(out["iterations"].sum())
         return f
 
     dt, its = run_chunk(0)(probe_n)
     rate1 = its / dt
     n_per_thread = int(max(probe_n, min(200000, rate1 * budget_s / max(its / probe_n, 1))))
+    if w.get("spatial"):
+        side = max(4, int(round(n_per_thread ** (1.0 / 3))))
+        n_per_thread = side ** 3
     datas = [make_volume(w, n_per_thread, "cpu", seed_offset=100 + i).numpy() for i in range(threads)]
-    specs = [make_spec(w) for _ in range(threads)]
 
     def work(i):
-        out = oracle.run(specs[i], datas[i])  # ctypes releases the GIL: threads run in parallel
+        out = oracle_run(w, datas[i])  # ctypes releases the GIL: threads run in parallel
         return int(out["iterations"].sum())
 
     t0 = time.perf_counter()
@@ -202,9 +248,15 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream
 
     y = make_volume(w, n_vox, "cuda", seed_offset=rank)
-    spec = make_spec(w)
-    run = device.VbRun(spec, n_vox)
+    spec = make_spec(w, n_vox)
+    spatial = bool(w.get("spatial"))
+    run = device.VbRun(spec, n_vox, spatial=spatial)
     run.set_data_device(y.data_ptr())
+    if spatial:
+        idx = torch.arange(n_vox, device="cuda")
+        side = spec.prob.nx
+        coords = torch.stack([idx % side, (idx // side) % side, idx // (side * side)]).to(torch.int32).contiguous()
+        run.buf.coords = coords.data_ptr()
 
     def step():
         rc = run.launch(stream)
@@ -304,7 +356,8 @@ def main():
                          "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
                          "peak_source": "measured live: dependent-free DFMA loop on all SMs "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
-                         "flop_per_voxel_iteration": W, "kernel": "vb_voxelwise_white_kernel",
+                         "flop_per_voxel_iteration": W, "kernel": ("sp_noise_kernel (+ sp_theta / sp_sweep / sp_ak)" if spatial else "vb_voxelwise_ar_kernel"
+                                    if w["spec"].get("noise") == "ar" else "vb_voxelwise_white_kernel"),
                          "avg_launch_ms": avg_kernel_s * 1e3,
                          "hbm": {"achieved": bytes_per_launch / avg_kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
                                  "frac": bytes_per_launch / avg_kernel_s / 1e9 / hbm_peak,

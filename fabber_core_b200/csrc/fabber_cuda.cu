@@ -13,6 +13,8 @@
 #include <vector>
 
 #include "vb_launch.h"
+#define FAB_SPATIAL_HOST_KERNELS
+#include "vb_spatial.cuh"
 #include "vb_voxelwise.cuh"
 
 namespace fab
@@ -263,6 +265,31 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
     return FABBER_CUDA_OK;
 }
 
+/* device scratch of one spatial run; freed in reverse on any exit path */
+struct Scratch
+{
+    cudaStream_t s;
+    std::vector<void *> ptrs;
+    explicit Scratch(cudaStream_t st)
+        : s(st)
+    {
+    }
+    template <class T> T *get(size_t n)
+    {
+        void *p = nullptr;
+        if (cudaMallocAsync(&p, (n ? n : 1) * sizeof(T), s) != cudaSuccess)
+            return nullptr;
+        ptrs.push_back(p);
+        return (T *)p;
+    }
+    ~Scratch()
+    {
+        for (size_t i = ptrs.size(); i-- > 0;)
+            cudaFreeAsync(ptrs[i], s);
+    }
+};
+
+
 } // namespace fab
 
 using namespace fab;
@@ -416,9 +443,160 @@ int fabber_cuda_vb_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cu
     return FABBER_CUDA_OK;
 }
 
-int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *, const fabber_cuda_vb_buffers *, void *)
+int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream)
 {
-    return fail(FABBER_CUDA_ERR_INVALID, "spatial VB kernels not built yet");
+    cudaStream_t st = (cudaStream_t)stream;
+    SpArgs sp;
+    memset(&sp, 0, sizeof(sp));
+    Staged staged;
+    bool general = false;
+    int rc = build_args(prob, buf, st, sp.v, staged, general);
+    struct ReleaseStaged
+    {
+        Staged &s;
+        cudaStream_t st;
+        ~ReleaseStaged() { s.release(st); }
+    } rel = { staged, st };
+    if (rc != FABBER_CUDA_OK)
+        return rc;
+    if (prob->noise_type != FABBER_NOISE_WHITE || general)
+        return fail(FABBER_CUDA_ERR_INVALID,
+            "spatial VB kernels support white noise with one phi and no masked time points");
+    const int P = prob->model.n_params, N = prob->n_voxels, NT = P * (P + 1) / 2;
+    bool any_spatial = false, any_coupled = false;
+    for (int i = 0; i < P; i++)
+    {
+        const char ty = sp.v.params[i].prior_type;
+        if (ty == 'M' || ty == 'm')
+            any_coupled = true;
+        if (ty == 'M' || ty == 'm' || ty == 'P' || ty == 'p')
+            any_spatial = true;
+        else if (ty != 'N' && ty != 'I' && ty != 'A')
+            return fail(FABBER_CUDA_ERR_INVALID, "unknown prior type");
+    }
+    if (prob->spatial_dims < 0 || prob->spatial_dims > 3)
+        return fail(FABBER_CUDA_ERR_INVALID, "spatial-dims must be 0, 1, 2 or 3"); /* priors.cc:191-194 */
+    const ModelLaunchers *ml = find_model(prob->model.id, P);
+    if (!ml)
+        return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
+    if (N == 0)
+        return FABBER_CUDA_OK;
+    if (!buf->coords)
+        return fail(FABBER_CUDA_ERR_INVALID, "spatial VB needs voxel coordinates");
+    const int nx = prob->nx, ny = prob->ny, nz = prob->nz;
+    if (nx <= 0 || ny <= 0 || nz <= 0)
+        return fail(FABBER_CUDA_ERR_INVALID, "spatial VB needs the bounding grid nx, ny, nz");
+    const size_t n_grid = (size_t)nx * ny * nz;
+    const int n_planes = nx + ny + nz;
+    const int max_it = prob->max_iterations;
+
+    Scratch sc(st);
+    int *grid2vox = sc.get<int>(n_grid), *nn_idx = sc.get<int>((size_t)6 * N), *plane_of = sc.get<int>(N);
+    int *order = sc.get<int>(N), *hist = sc.get<int>(n_planes + 1), *cursor = sc.get<int>(n_planes + 1);
+    int *bad = sc.get<int>(1);
+    sp.centre = sc.get<double>((size_t)P * N);
+    sp.stats = sc.get<double>((size_t)(NT + P + 1) * N);
+    sp.m0 = sc.get<double>((size_t)P * N);
+    sp.L0 = sc.get<double>((size_t)P * N);
+    sp.rhs = sc.get<double>((size_t)P * N);
+    sp.logdet = sc.get<double>(N);
+    sp.aK = sc.get<double>(P);
+    sp.ak_hist = sc.get<double>((size_t)(max_it + 1) * P);
+    sp.ak_partial = sc.get<double>((size_t)SP_AK_BLOCKS * 2 * P);
+    sp.fprior_last = sc.get<double>(1);
+    if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !cursor || !bad || !sp.centre || !sp.stats || !sp.m0
+        || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last)
+        return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+    sp.nn_idx = nn_idx;
+    sp.order = order;
+    sp.ak_blocks = SP_AK_BLOCKS;
+    sp.spatial_dims = prob->spatial_dims;
+    sp.update_first_iter = prob->update_first_iter;
+    sp.any_coupled = any_coupled ? 1 : 0;
+    sp.q1 = prob->spatial_q1;
+    sp.q2 = prob->spatial_q2;
+    sp.speed = prob->spatial_speed;
+
+    /* ---- neighbours + hyper-plane order (Vb::CalcNeighbours) ---------------------------------- */
+    cudaMemsetAsync(grid2vox, 0xff, n_grid * sizeof(int), st);
+    cudaMemsetAsync(hist, 0, (n_planes + 1) * sizeof(int), st);
+    cudaMemsetAsync(bad, 0, sizeof(int), st);
+    cudaMemsetAsync(sp.fprior_last, 0, sizeof(double), st);
+    {
+        std::vector<double> ak0(P, 1e-8); /* SpatialPrior::m_aK initial value, priors.cc:185 */
+        cudaMemcpyAsync(sp.aK, ak0.data(), P * sizeof(double), cudaMemcpyHostToDevice, st);
+        cudaStreamSynchronize(st);
+    }
+    const unsigned gridN = (unsigned)((N + 255) / 256);
+    sp_grid_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, bad);
+    count_launch();
+    sp_neighbour_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, prob->spatial_dims, nn_idx,
+        plane_of, hist);
+    count_launch();
+    std::vector<int> h_hist(n_planes + 1), h_begin(n_planes + 1);
+    int h_bad = 0;
+    cudaMemcpyAsync(h_hist.data(), hist, (n_planes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "spatial neighbour set-up");
+    if (h_bad == 1)
+        return fail(FABBER_CUDA_ERR_INVALID, "voxel coordinates outside the nx, ny, nz grid");
+    if (h_bad == 2)
+        return fail(FABBER_CUDA_ERR_INVALID,
+            "coordinates must be in increasing order (x fastest, then y, then z), inference_vb.cc:769-793");
+    int acc = 0;
+    for (int h = 0; h <= n_planes; h++)
+    {
+        h_begin[h] = acc;
+        acc += h_hist[h];
+    }
+    cudaMemcpyAsync(cursor, h_begin.data(), (n_planes + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
+    sp_order_kernel<<<gridN, 256, 0, st>>>(plane_of, N, cursor, order);
+    count_launch();
+    cudaStreamSynchronize(st); /* h_begin is pageable host memory */
+
+    /* ---- set-up, then the iteration-major loop ------------------------------------------------- */
+#define FAB_SP_LAUNCH(fn)                                \
+    do                                                   \
+    {                                                    \
+        cudaError_t le = ml->fn(sp, st);                 \
+        if (le != cudaSuccess)                           \
+            return cuda_fail(le, "spatial VB " #fn);     \
+    } while (0)
+    sp.it = 0;
+    FAB_SP_LAUNCH(sp_setup);
+    for (int it = 0; it < max_it; it++)
+    {
+        sp.it = it;
+        /* SpatialPrior::ApplyToMVN at v == 1: aK is refreshed from the current posteriors unless this is
+         * the first iteration (priors.cc:350-358) */
+        sp.ak_update = (any_spatial && (it > 0 || prob->update_first_iter)) ? 1 : 0;
+        if (sp.ak_update)
+            FAB_SP_LAUNCH(sp_ak_partial);
+        FAB_SP_LAUNCH(sp_ak_final);
+        FAB_SP_LAUNCH(sp_theta);
+        if (any_coupled)
+            for (int h = 0; h < n_planes; h++)
+                if (h_hist[h] > 0)
+                {
+                    sp.plane_begin = h_begin[h];
+                    sp.plane_count = h_hist[h];
+                    FAB_SP_LAUNCH(sp_sweep);
+                }
+        FAB_SP_LAUNCH(sp_noise);
+    }
+    sp.it = max_it;
+    sp.ak_update = 0;
+    FAB_SP_LAUNCH(sp_ak_final);
+#undef FAB_SP_LAUNCH
+    if (buf->spatial_ak)
+        cudaMemcpyAsync(buf->spatial_ak, sp.ak_hist, (size_t)(max_it + 1) * P * sizeof(double),
+            cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "spatial VB");
+    return FABBER_CUDA_OK;
 }
 
 int fabber_cuda_check_status(const int *status, int n_voxels, int *first_bad_voxel, int *first_bad_code, void *stream)

@@ -5,6 +5,8 @@
  */
 #include "vb_launch.h"
 #include "vb_voxelwise.cuh"
+#include "vb_voxelwise_ar.cuh"
+#include "vb_spatial.cuh"
 
 #if !defined(FAB_FAMILY) || !defined(FAB_K) || !defined(FAB_GETTER)
 #error "compile with -DFAB_FAMILY=.. -DFAB_K=.. -DFAB_GETTER=.."
@@ -36,15 +38,86 @@ template <int NPHI, bool SNAP> static cudaError_t launch_white(const VbArgs &a, 
     return cudaGetLastError();
 }
 
+static cudaError_t launch_ar(const VbArgs &a, cudaStream_t s)
+{
+    if (a.N <= 0)
+        return cudaSuccess;
+    typedef ArVoxel<M> Vox;
+    const bool use_snap = a.conv_type == FABBER_CONV_TRIALMODE || a.conv_type == FABBER_CONV_FREDUCE;
+    const size_t smem = M::smem_bytes(a.T)
+        + (size_t)(Vox::STASH_DOUBLES + (use_snap ? Vox::SNAP_DOUBLES : 0)) * VB_BLOCK * sizeof(double);
+    auto kern = vb_voxelwise_ar_kernel<M>;
+    if (smem > 48 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
+    const unsigned grid = (unsigned)((a.N + VB_BLOCK - 1) / VB_BLOCK);
+    kern<<<grid, VB_BLOCK, smem, s>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_sp_setup(const SpArgs &s, cudaStream_t st)
+{
+    const size_t smem = M::smem_bytes(s.v.T);
+    auto kern = sp_setup_kernel<M>;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)((s.v.N + VB_BLOCK - 1) / VB_BLOCK), VB_BLOCK, smem, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+static cudaError_t launch_sp_noise(const SpArgs &s, cudaStream_t st)
+{
+    const size_t smem = M::smem_bytes(s.v.T) + (size_t)NTri<M::P>::value * VB_BLOCK * sizeof(double);
+    auto kern = sp_noise_kernel<M>;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)((s.v.N + VB_BLOCK - 1) / VB_BLOCK), VB_BLOCK, smem, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+static cudaError_t launch_sp_ak_partial(const SpArgs &s, cudaStream_t st)
+{
+    sp_ak_partial_kernel<M::P><<<SP_AK_BLOCKS, 256, 0, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+static cudaError_t launch_sp_ak_final(const SpArgs &s, cudaStream_t st)
+{
+    sp_ak_final_kernel<M::P><<<1, 32, 0, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+static cudaError_t launch_sp_theta(const SpArgs &s, cudaStream_t st)
+{
+    sp_theta_kernel<M::P><<<(unsigned)((s.v.N + VB_BLOCK - 1) / VB_BLOCK), VB_BLOCK, 0, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
+{
+    if (s.plane_count <= 0)
+        return cudaSuccess;
+    sp_sweep_kernel<M::P><<<(unsigned)((s.plane_count + 127) / 128), 128, 0, st>>>(s);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static const ModelLaunchers g_launchers = {
     launch_white<1, false>,
     launch_white<1, true>,
     launch_white<FABBER_CUDA_MAX_PHIS, true>,
+    launch_ar,
     nullptr,
-    nullptr,
-    nullptr,
-    nullptr,
-    nullptr,
+    launch_sp_setup,
+    launch_sp_ak_partial,
+    launch_sp_ak_final,
+    launch_sp_theta,
+    launch_sp_sweep,
+    launch_sp_noise,
 };
 
 const ModelLaunchers *FAB_GETTER() { return &g_launchers; }

@@ -11,8 +11,10 @@
 namespace fab
 {
 struct VbArgs;
+struct SpArgs;
 
 typedef cudaError_t (*VbLaunchFn)(const VbArgs &, cudaStream_t);
+typedef cudaError_t (*SpLaunchFn)(const SpArgs &, cudaStream_t);
 
 struct ModelLaunchers
 {
@@ -21,10 +23,12 @@ struct ModelLaunchers
     VbLaunchFn white_general;   /* noise patterns (<= FABBER_CUDA_MAX_PHIS) and masked samples */
     VbLaunchFn ar1;             /* AR(1) noise */
     VbLaunchFn model_fit;       /* batched model evaluation */
-    VbLaunchFn spatial_setup;   /* spatial mode kernels */
-    VbLaunchFn spatial_theta;
-    VbLaunchFn spatial_noise;
+    /* spatial mode (vb_spatial.cuh) */
+    SpLaunchFn sp_setup, sp_ak_partial, sp_ak_final, sp_theta, sp_sweep, sp_noise;
 };
+
+/* number of blocks the aK partial reduction is launched with (size of SpArgs::ak_partial) */
+constexpr int SP_AK_BLOCKS = 1184; /* 148 SMs x 8 */
 
 /* returns NULL when no device Evaluate hook is compiled for that size */
 const ModelLaunchers *find_model(int model_id, int n_params);

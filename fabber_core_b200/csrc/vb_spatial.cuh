@@ -1,0 +1,596 @@
+/*
+ * vb_spatial.cuh - spatial VB (iteration-major), white noise.
+ *
+ * Replaces Vb::DoCalculationsSpatial (inference_vb.cc:578-767) with SpatialPrior::CalculateaK /
+ * ApplyToMVN (priors.cc:221-488) and Vb::CalcNeighbours (inference_vb.cc:830-964).
+ *
+ * The reference sweeps the voxels sequentially: voxel v's MRF prior mean uses the posterior means of
+ * its neighbours, those with a smaller index already updated in the same sweep (Gauss-Seidel). To
+ * keep that exactly while running in parallel the sweep is split:
+ *
+ *   sp_theta_kernel   (parallel)  priors' precisions, Lambda = Lambda0 + phi A, Sigma = Lambda^-1 and the
+ *                                 neighbour-independent part of the right-hand side. The spatial prior
+ *                                 *precision* depends only on aK and the neighbour count (priors.cc:406-429).
+ *   sp_sweep_kernel   (wavefront) m_v = Sigma_v (rhs_v + sum_k spatial_prec_k * mean_nn,k e_k), launched once
+ *                                 per hyper-plane x+y+z = h in increasing h: in lexicographic voxel order
+ *                                 (x fastest) the already-updated neighbours -x,-y,-z lie on plane h-1 and
+ *                                 the not-yet-updated ones +x,+y,+z on plane h+1, so all voxels of a plane
+ *                                 are independent and see exactly the values the sequential sweep sees.
+ *   sp_noise_kernel   (parallel)  UpdateNoise, ReCentre (the pass over the time-series -> new sufficient
+ *                                 statistics) and the free energy, second loop of the reference (:675-722).
+ *   sp_ak_*           (reduction) the two global sums of CalculateaK per spatial parameter, deterministic
+ *                                 two-stage reduction; aK itself is computed on the device.
+ *
+ * P/p (Penny) priors: `double rec = 1 / (8*nn - nn2)` is an INTEGER division in the reference
+ * (priors.cc:455) and |8 nn - nn2| >= 3 for every reachable neighbour count, so rec == 0 and the
+ * neighbour mean drops out of the prior mean; only the precision and aK see the neighbours. Those types
+ * therefore need no ordered sweep (and no second-neighbour lists) - reproduced, not "fixed".
+ *
+ * Between kernels the per-voxel state lives in HBM as structure-of-arrays [field][N] doubles.
+ */
+#pragma once
+#include "vb_voxelwise.cuh"
+
+namespace fab
+{
+struct SpArgs
+{
+    VbArgs v;
+    const int *nn_idx;   /* [6][N]: +x,-x,+y,-y,+z,-z neighbour voxel or -1 (restricted by spatial_dims) */
+    double *centre;      /* [P][N] */
+    double *stats;       /* [NT + P + 1][N] : A, b, rr */
+    double *m0, *L0;     /* [P][N] prior mean / diagonal prior precision */
+    double *rhs;         /* [P][N] neighbour-independent right-hand side */
+    double *logdet;      /* [N] log|det Lambda| */
+    double *aK;          /* [P] current spatial precisions (device) */
+    double *ak_hist;     /* [max_it + 1][P] (device) */
+    double *ak_partial;  /* [ak_blocks][2][P] */
+    double *fprior_last; /* [1] stale Fprior of the last voxel (inference_vb.cc:700) */
+    const int *order;    /* voxels sorted by hyper-plane */
+    int plane_begin, plane_count;
+    int ak_blocks;
+    int it;
+    int spatial_dims;
+    int update_first_iter;
+    int any_coupled; /* any 'M' / 'm' parameter */
+    int ak_update;   /* sp_ak_final_kernel: recompute aK (else only record the history row) */
+    double q1, q2, speed;
+};
+
+FAB_DEV bool is_spatial_type(char t) { return t == 'M' || t == 'm' || t == 'P' || t == 'p'; }
+
+/* ---- set-up: initial posterior, noise, first ReCentre (Vb::SetupPerVoxelDists) ------------------- */
+template <class Model> __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_setup_kernel(const __grid_constant__ SpArgs s)
+{
+    constexpr int P = Model::P;
+    constexpr int NT = NTri<P>::value;
+    const VbArgs &a = s.v;
+    extern __shared__ double smem[];
+    Model::stage(a, smem);
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N)
+        return;
+    const typename Model::Ctx mc = Model::make_ctx(a, smem);
+    const size_t N = (size_t)a.N;
+    double m[P], Sig[NT];
+    int status = 0;
+    if (a.init_mean)
+    {
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            m[i] = a.init_mean[i * N + v];
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Sig[i] = a.init_cov[i * N + v];
+    }
+    else
+    {
+        double var[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            m[i] = (a.params[i].prior_type == 'I') ? a.image_prior[i][v] : a.params[i].post_mean;
+            var[i] = a.params[i].post_var;
+        }
+        Model::init_voxel(a, v, m);
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Sig[i] = 0.0;
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            const char code = a.params[i].transform;
+            m[i] = to_fabber(code, m[i]);
+            Sig[tri(i, i)] = to_fabber_var(code, var[i]);
+        }
+    }
+    Stats<P> S[1];
+    const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, m, S);
+    if (err)
+        status = err | FABBER_VOX_SETUP_FLAG;
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        a.mean[i * N + v] = m[i];
+        s.centre[i * N + v] = m[i];
+        s.m0[i * N + v] = 0.0;
+        s.L0[i * N + v] = 1.0;
+        s.stats[(NT + i) * N + v] = S[0].b[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+    {
+        a.cov[i * N + v] = Sig[i];
+        s.stats[i * N + v] = S[0].A[i];
+    }
+    s.stats[(NT + P) * N + v] = S[0].rr;
+    a.noise[0 * N + v] = a.init_noise ? a.init_noise[0 * N + v] : a.noise_post_b[0];
+    a.noise[1 * N + v] = a.init_noise ? a.init_noise[1 * N + v] : a.noise_post_c[0];
+    s.logdet[v] = 0.0;
+    if (a.free_energy)
+        a.free_energy[v] = 9999.0; /* resultFs default, inference_vb.cc:165 */
+    if (a.iterations)
+        a.iterations[v] = 0;
+    a.status[v] = status;
+}
+
+/* ---- aK: per-block partial sums of trace_term and term2 (priors.cc:233-294) ------------------------ */
+template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(const __grid_constant__ SpArgs s)
+{
+    const VbArgs &a = s.v;
+    const size_t N = (size_t)a.N;
+    double tr[P], t2[P];
+#pragma unroll
+    for (int k = 0; k < P; k++)
+        tr[k] = t2[k] = 0.0;
+    const int dims = s.spatial_dims;
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < a.N; v += gridDim.x * blockDim.x)
+    {
+        if (a.status[v] != 0)
+            continue; /* ignore_voxels */
+        int nbr[6], nn = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+        {
+            nbr[j] = s.nn_idx[j * N + v];
+            nn += nbr[j] >= 0;
+        }
+#pragma unroll
+        for (int k = 0; k < P; k++)
+        {
+            const char ty = a.params[k].prior_type;
+            if (!is_spatial_type(ty))
+                continue;
+            const double sigmaK = a.cov[tri(k, k) * N + v];
+            const double wK = a.mean[k * N + v];
+            if (ty == 'm')
+                tr[k] += sigmaK * dims * 2;
+            else if (ty == 'M')
+                tr[k] += sigmaK * (nn + 1e-8);
+            else if (ty == 'p')
+                tr[k] += sigmaK * (4 * dims * dims + 2 * dims);
+            else
+                tr[k] += sigmaK * (nn * nn + nn);
+            double SwK = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+                if (nbr[j] >= 0)
+                    SwK += wK - a.mean[k * N + nbr[j]];
+            if (ty == 'p' || ty == 'm')
+                SwK += wK * (dims * 2 - (double)nn);
+            if (ty == 'm' || ty == 'M')
+                t2[k] += SwK * wK;
+            else
+                t2[k] += SwK * SwK;
+        }
+    }
+    __shared__ double red[2 * P][256 / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < P; k++)
+    {
+        double x = tr[k], y = t2[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+        {
+            x += __shfl_down_sync(0xffffffffu, x, o);
+            y += __shfl_down_sync(0xffffffffu, y, o);
+        }
+        if (lane == 0)
+        {
+            red[k][warp] = x;
+            red[P + k][warp] = y;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 2 * P)
+    {
+        double x = 0.0;
+        for (int w = 0; w < 256 / 32; w++)
+            x += red[threadIdx.x][w];
+        s.ak_partial[(size_t)blockIdx.x * 2 * P + threadIdx.x] = x;
+    }
+}
+
+/* one block: fixed-order final sum, then the Penny update for aK (priors.cc:296-343) */
+template <int P> __global__ void sp_ak_final_kernel(const __grid_constant__ SpArgs s)
+{
+    const VbArgs &a = s.v;
+    const int k = threadIdx.x;
+    if (k >= P)
+        return;
+    const char ty = a.params[k].prior_type;
+    if (s.ak_update && is_spatial_type(ty))
+    {
+        double trace_term = 0.0, term2 = 0.0;
+        for (int b = 0; b < s.ak_blocks; b++)
+        {
+            trace_term += s.ak_partial[(size_t)b * 2 * P + k];
+            term2 += s.ak_partial[(size_t)b * 2 * P + P + k];
+        }
+        const double gk = 1 / (0.5 * trace_term + 0.5 * term2 + 1 / s.q1);
+        const double hK = (a.N * 0.5 + s.q2);
+        double aK = gk * hK;
+        if (aK < 1e-50)
+            aK = 1e-50;
+        double aKMax = aK * s.speed;
+        if (aKMax < 0.5)
+            aKMax = 0.5;
+        if ((s.speed > 0) && (aK > aKMax))
+            aK = aKMax;
+        s.aK[k] = aK;
+    }
+    s.ak_hist[(size_t)s.it * P + k] = is_spatial_type(ty) ? s.aK[k] : 0.0;
+}
+
+/* ---- theta, neighbour-independent part (first loop of the reference, :614-650) --------------------- */
+template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(const __grid_constant__ SpArgs s)
+{
+    constexpr int NT = NTri<P>::value;
+    const VbArgs &a = s.v;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N)
+        return;
+    const size_t N = (size_t)a.N;
+    if (a.status[v] != 0)
+        return;
+    double m[P], c[P], A[NT], b[P], L0[P], m0[P], sigd[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        m[i] = a.mean[i * N + v];
+        c[i] = s.centre[i * N + v];
+        b[i] = s.stats[(NT + i) * N + v];
+        sigd[i] = a.cov[tri(i, i) * N + v];
+        m0[i] = s.m0[i * N + v];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        A[i] = s.stats[i * N + v];
+    int nn = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+        nn += s.nn_idx[j * N + v] >= 0;
+    const int dims = s.spatial_dims;
+    double Fprior = 0.0;
+    bool coupled[P];
+#pragma unroll
+    for (int k = 0; k < P; k++)
+    {
+        const fabber_cuda_param &p = a.params[k];
+        const char ty = p.prior_type;
+        coupled[k] = false;
+        if (ty == 'A')
+        {
+            const double new_cov = m[k] * m[k] + sigd[k];
+            if (s.it == 0)
+            {
+                L0[k] = 1.0 / p.prior_var;
+                m0[k] = p.prior_mean;
+            }
+            else
+                L0[k] = 1.0 / new_cov;
+            const double bb = 2 / new_cov;
+            Fprior += -1.5 * (log(bb) + digamma_fsl(0.5)) - 0.5 - gammaln(0.5) - 0.5 * log(bb);
+        }
+        else if (is_spatial_type(ty))
+        {
+            const double aK = s.aK[k];
+            int n1 = nn;
+            if (ty == 'p' || ty == 'm')
+                n1 = 2 * dims;
+            double sp;
+            if (ty == 'M')
+                sp = aK * (n1 + 1e-8);
+            else if (ty == 'm')
+                sp = aK * n1;
+            else
+                sp = aK * (n1 * n1 + n1);
+            L0[k] = (ty == 'p' || ty == 'm') ? sp : p.prior_prec + sp;
+            if (ty == 'M' || ty == 'm')
+                coupled[k] = true; /* prior mean needs the neighbours: sp_sweep_kernel */
+            else
+            {
+                /* rec == 0 (integer division, priors.cc:455): spatial_mean == 0 */
+                const double spatial_mean = 0.0;
+                m0[k] = (1.0 / L0[k]) * (sp * spatial_mean + p.prior_prec * p.prior_mean);
+            }
+        }
+        else
+        {
+            m0[k] = (ty == 'I') ? a.image_prior[k][v] : p.prior_mean;
+            L0[k] = p.prior_prec;
+        }
+    }
+    if (v == a.N - 1)
+        *s.fprior_last = Fprior;
+    const double phi = a.noise[0 * N + v] * a.noise[1 * N + v];
+    double Lam[NT], Sig[NT], ld;
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        Lam[i] = phi * A[i];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        Lam[tri(i, i)] = L0[i] + phi * A[tri(i, i)];
+    if (!mvn_inverse<P>(Lam, Sig, ld))
+    {
+        a.status[v] = FABBER_VOX_SINGULAR;
+        return;
+    }
+    double Aw[NT], Ac[P], rhs[P];
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        Aw[i] = phi * A[i];
+    symv<P>(Aw, c, Ac);
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        rhs[i] = (phi * b[i] + Ac[i]) + (coupled[i] ? 0.0 : L0[i] * m0[i]);
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        a.cov[i * N + v] = Sig[i];
+    s.logdet[v] = ld;
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        s.L0[i * N + v] = L0[i];
+        if (!coupled[i])
+            s.m0[i * N + v] = m0[i];
+    }
+    if (s.any_coupled)
+    {
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            s.rhs[i * N + v] = rhs[i];
+    }
+    else
+    {
+        double mn[P];
+        symv<P>(Sig, rhs, mn);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            a.mean[i * N + v] = mn[i];
+    }
+}
+
+/* ---- ordered sweep over one hyper-plane: MRF prior means + posterior means, in place --------------- */
+template <int P> __global__ void __launch_bounds__(128) sp_sweep_kernel(const __grid_constant__ SpArgs s)
+{
+    constexpr int NT = NTri<P>::value;
+    const VbArgs &a = s.v;
+    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i0 >= s.plane_count)
+        return;
+    const int v = s.order[s.plane_begin + i0];
+    const size_t N = (size_t)a.N;
+    if (a.status[v] != 0)
+        return;
+    int nbr[6], nn = 0;
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+    {
+        nbr[j] = s.nn_idx[j * N + v];
+        nn += nbr[j] >= 0;
+    }
+    double rhs[P], Sig[NT];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        rhs[i] = s.rhs[i * N + v];
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        Sig[i] = a.cov[i * N + v];
+    const int dims = s.spatial_dims;
+#pragma unroll
+    for (int k = 0; k < P; k++)
+    {
+        const char ty = a.params[k].prior_type;
+        if (ty != 'M' && ty != 'm')
+            continue;
+        double contrib = 0.0;
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+            if (nbr[j] >= 0)
+                contrib += a.mean[k * N + nbr[j]];
+        const int n1 = (ty == 'm') ? 2 * dims : nn;
+        const double aK = s.aK[k];
+        const double sp = (ty == 'M') ? aK * (n1 + 1e-8) : aK * n1;
+        const double rec = 1 / double(n1);
+        const double spatial_mean = contrib * rec;
+        const double L0k = s.L0[k * N + v];
+        const double m0k = (1.0 / L0k) * sp * spatial_mean; /* priors.cc:469-470 */
+        s.m0[k * N + v] = m0k;
+        rhs[k] += L0k * m0k;
+    }
+    double mn[P];
+    symv<P>(Sig, rhs, mn);
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        a.mean[i * N + v] = mn[i];
+}
+
+/* ---- noise update, ReCentre and free energy (second loop of the reference, :675-722) --------------- */
+template <class Model>
+__global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_noise_kernel(const __grid_constant__ SpArgs s)
+{
+    constexpr int P = Model::P;
+    constexpr int NT = NTri<P>::value;
+    const VbArgs &a = s.v;
+    extern __shared__ double smem[];
+    Model::stage(a, smem);
+    volatile double *park = smem + Model::smem_bytes(a.T) / sizeof(double) + threadIdx.x;
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N)
+        return;
+    const size_t N = (size_t)a.N;
+    if (a.status[v] != 0)
+        return;
+    const typename Model::Ctx mc = Model::make_ctx(a, smem);
+    double m[P], Sig[NT];
+    Stats<P> S[1];
+    double nb, nc;
+    {
+        double d[P];
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            m[i] = a.mean[i * N + v];
+            d[i] = s.centre[i * N + v] - m[i];
+            S[0].b[i] = s.stats[(NT + i) * N + v];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+        {
+            Sig[i] = a.cov[i * N + v];
+            S[0].A[i] = s.stats[i * N + v];
+        }
+        S[0].rr = s.stats[(NT + P) * N + v];
+        /* WhiteNoiseModel::UpdateNoise, noisemodel_white.cc:228-273 */
+        double bd = 0.0;
+#pragma unroll
+        for (int j = 0; j < P; j++)
+            bd += S[0].b[j] * d[j];
+        const double kk = S[0].rr + 2.0 * bd + quadform<P>(S[0].A, d);
+        const double tmp = kk + trace_prod<P>(Sig, S[0].A);
+        nb = 1 / (tmp * 0.5 + 1 / a.noise_prior_b[0]);
+        nc = ((double)a.n_per_phi[0] - 1) * 0.5 + a.noise_prior_c[0];
+        if (a.locked_noise_stdev > 0)
+            nb = 1 / nc / a.locked_noise_stdev / a.locked_noise_stdev;
+    }
+    /* park what F needs; the pass over the time-series only needs the new centre */
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            park[(k++) * VB_BLOCK] = Sig[i];
+    }
+    const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, m, S);
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Sig[i] = park[(k++) * VB_BLOCK];
+    }
+    a.noise[0 * N + v] = nb;
+    a.noise[1 * N + v] = nc;
+    if (err)
+    {
+        a.status[v] = err;
+        return;
+    }
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        s.centre[i * N + v] = m[i];
+        s.stats[(NT + i) * N + v] = S[0].b[i];
+    }
+#pragma unroll
+    for (int i = 0; i < NT; i++)
+        s.stats[i * N + v] = S[0].A[i];
+    s.stats[(NT + P) * N + v] = S[0].rr;
+    if (a.iterations)
+        a.iterations[v] = s.it + 1;
+    if (a.need_f)
+    {
+        double m0[P], L0[P], nbv[1] = { nb }, ncv[1] = { nc };
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            m0[i] = s.m0[i * N + v];
+            L0[i] = s.L0[i * N + v];
+        }
+        const double F = white_free_energy<P, 1>(a, S, m, Sig, s.logdet[v], m0, L0, nbv, ncv) + *s.fprior_last;
+        if (!finite_d(F))
+        {
+            a.status[v] = FABBER_VOX_NONFINITE_F;
+            return;
+        }
+        if (a.free_energy)
+            a.free_energy[v] = F;
+        if (a.f_history && s.it < a.f_history_len)
+            a.f_history[s.it * N + v] = F;
+    }
+}
+
+/* ---- neighbour table and hyper-plane ordering (Vb::CalcNeighbours, inference_vb.cc:830-934) ---------
+ * model independent: compiled once, in fabber_cuda.cu */
+#ifdef FAB_SPATIAL_HOST_KERNELS
+__global__ void sp_grid_kernel(const int *coords, int N, int nx, int ny, int nz, int *grid2vox, int *bad)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N)
+        return;
+    const int x = coords[v], y = coords[(size_t)N + v], z = coords[2 * (size_t)N + v];
+    if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz)
+    {
+        atomicExch(bad, 1);
+        return;
+    }
+    grid2vox[((size_t)z * ny + y) * nx + x] = v;
+    /* CheckCoordMatrixCorrectlyOrdered (:769-793): x fastest, then y, then z, strictly increasing */
+    if (v + 1 < N)
+    {
+        const int x2 = coords[v + 1], y2 = coords[(size_t)N + v + 1], z2 = coords[2 * (size_t)N + v + 1];
+        const int sx = (x2 > x) - (x2 < x), sy = (y2 > y) - (y2 < y), sz = (z2 > z) - (z2 < z);
+        if (sx + 10 * sy + 100 * sz <= 0)
+            atomicExch(bad, 2);
+    }
+}
+
+__global__ void sp_neighbour_kernel(const int *coords, int N, int nx, int ny, int nz, const int *grid2vox, int dims,
+    int *nn_idx, int *plane_of, int *plane_hist)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N)
+        return;
+    const int x = coords[v], y = coords[(size_t)N + v], z = coords[2 * (size_t)N + v];
+    const int dx[6] = { 1, -1, 0, 0, 0, 0 }, dy[6] = { 0, 0, 1, -1, 0, 0 }, dz[6] = { 0, 0, 0, 0, 1, -1 };
+#pragma unroll
+    for (int j = 0; j < 6; j++)
+    {
+        int id = -1;
+        if (j < 2 * dims)
+        {
+            const int xx = x + dx[j], yy = y + dy[j], zz = z + dz[j];
+            if (xx >= 0 && yy >= 0 && zz >= 0 && xx < nx && yy < ny && zz < nz)
+                id = grid2vox[((size_t)zz * ny + yy) * nx + xx];
+        }
+        nn_idx[(size_t)j * N + v] = id;
+    }
+    const int h = x + y + z;
+    plane_of[v] = h;
+    atomicAdd(&plane_hist[h], 1);
+}
+
+__global__ void sp_order_kernel(const int *plane_of, int N, int *cursor, int *order)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= N)
+        return;
+    const int pos = atomicAdd(&cursor[plane_of[v]], 1);
+    order[pos] = v;
+}
+
+#endif /* FAB_SPATIAL_HOST_KERNELS */
+
+} // namespace fab

@@ -1,0 +1,327 @@
+/*
+ * fabber_host.h - C++ host side above the device C ABI (include/fabber_cuda.h).
+ *
+ * Mirrors the reference's plugin / operator interface for the VB path - same class names, option names,
+ * argument meaning and error behaviour - so that code written against fabber_core reads the same here:
+ *   FabberRunData / FabberRunDataArray   rundata.h:215-672, rundata_array.h  (options map, voxel data
+ *                                        T x Nvox, extent + mask, Run())
+ *   Parameter / DistParams / Transform   fwdmodel.h:24-57, transforms.h
+ *   FwdModel                             fwdmodel.h:59-371 (Initialize, GetParameterDefaults,
+ *                                        EvaluateModel, InitVoxelPosterior, GetOutputs, GetOptions ...)
+ *                                        + one addition: GetDeviceModel(), the __device__ Evaluate hook id
+ *   LinearFwdModel / PolynomialFwdModel / ExpFwdModel   fwdmodel_linear.*, fwdmodel_poly.*, examples/fwdmodel_exp.*
+ *   Vb                                   inference_vb.h (Initialize / DoCalculations / SaveResults); its
+ *                                        DoCalculations marshals SoA buffers and calls fabber_cuda_vb_*.
+ * No NEWMAT: matrices are plain row-major arrays. No CPU inference path exists in here.
+ */
+#pragma once
+#include <map>
+#include <memory>
+#include <set>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/fabber_cuda.h"
+
+namespace fabber_b200
+{
+/* ---- exceptions (rundata.h:676-757) ----------------------------------------------------------- */
+struct FabberError : std::runtime_error
+{
+    explicit FabberError(const std::string &m)
+        : std::runtime_error(m)
+    {
+    }
+};
+struct FabberInternalError : FabberError
+{
+    explicit FabberInternalError(const std::string &m)
+        : FabberError(m)
+    {
+    }
+};
+struct FabberRunDataError : FabberError
+{
+    explicit FabberRunDataError(const std::string &m)
+        : FabberError(m)
+    {
+    }
+};
+struct InvalidOptionValue : FabberRunDataError
+{
+    InvalidOptionValue(const std::string &key, const std::string &value, const std::string &reason)
+        : FabberRunDataError("Invalid value for option " + key + ": " + value + " (" + reason + ")")
+    {
+    }
+};
+struct MandatoryOptionMissing : FabberRunDataError
+{
+    explicit MandatoryOptionMissing(const std::string &key)
+        : FabberRunDataError("No value given for mandatory option: " + key)
+    {
+    }
+};
+struct DataNotFound : FabberRunDataError
+{
+    explicit DataNotFound(const std::string &key)
+        : FabberRunDataError("Data not found: " + key)
+    {
+    }
+};
+
+/* ---- option description (rundata.h:45-99) ------------------------------------------------------- */
+enum OptionType
+{
+    OPT_BOOL,
+    OPT_STR,
+    OPT_INT,
+    OPT_FLOAT,
+    OPT_FILE,
+    OPT_IMAGE,
+    OPT_TIMESERIES,
+    OPT_MVN,
+    OPT_MATRIX
+};
+struct OptionSpec
+{
+    std::string name;
+    OptionType type;
+    std::string description;
+    bool optional;
+    std::string def;
+};
+const char *option_type_name(OptionType t);
+
+template <class T> std::string stringify(const T &v)
+{
+    std::ostringstream s;
+    s << v;
+    return s.str();
+}
+
+/* ---- voxel data: rows x nvoxels, row t = volume t (rundata.h:628) -------------------------------- */
+struct VoxelData
+{
+    int rows;
+    size_t cols;
+    bool is_float;         /* input series keep the caller's float32 (lossless); outputs are double */
+    float *f;              /* pinned host memory when is_float */
+    std::vector<double> d; /* otherwise */
+    VoxelData();
+    ~VoxelData();
+    VoxelData(const VoxelData &) = delete;
+    VoxelData &operator=(const VoxelData &) = delete;
+    void alloc_float(int r, size_t c);
+    void alloc_double(int r, size_t c);
+    double at(int r, size_t c) const { return is_float ? (double)f[(size_t)r * cols + c] : d[(size_t)r * cols + c]; }
+};
+
+/* ---- run data (rundata.h:215-672 + rundata_array.cc) -------------------------------------------- */
+class FabberRunData
+{
+public:
+    FabberRunData();
+    virtual ~FabberRunData();
+
+    /* options (rundata.cc:427-600): booleans are "key present with empty value" */
+    void Set(const std::string &key, const std::string &value);
+    void SetBool(const std::string &key, bool value = true);
+    void Unset(const std::string &key);
+    bool HaveKey(const std::string &key) const;
+    std::string GetString(const std::string &key);
+    std::string GetStringDefault(const std::string &key, const std::string &def);
+    bool GetBool(const std::string &key);
+    int GetInt(const std::string &key, int min = INT32_MIN, int max = INT32_MAX);
+    int GetIntDefault(const std::string &key, int def, int min = INT32_MIN, int max = INT32_MAX);
+    double GetDouble(const std::string &key);
+    double GetDoubleDefault(const std::string &key, double def);
+    std::vector<std::string> GetStringList(const std::string &key); /* key1, key2, ... (rundata.cc:557-574) */
+    std::vector<int> GetIntList(const std::string &key, int min = INT32_MIN, int max = INT32_MAX);
+
+    /* extent, mask and coordinates (rundata_array.cc:23-66): voxel order x fastest, then y, then z */
+    void SetExtent(int nx, int ny, int nz, const int *mask);
+    const int *Extent() const { return m_extent; }
+    size_t NumVoxels() const { return m_voxel_index.size(); }
+    const std::vector<int> &VoxelIndex() const { return m_voxel_index; } /* grid offset of each masked voxel */
+    const std::vector<int> &Coords() const { return m_coords; }         /* [3][N] */
+
+    /* voxel data (rundata.cc:753-938, rundata_array.cc:68-133) */
+    void SetVoxelDataArray(const std::string &key, int data_size, const float *data);
+    void GetVoxelDataArray(const std::string &key, float *data);
+    int GetVoxelDataSize(const std::string &key);
+    const VoxelData &GetVoxelData(const std::string &key);
+    const VoxelData &GetMainVoxelData();
+    VoxelData &NewVoxelData(const std::string &key, int rows); /* SaveVoxelData target (rundata.cc:932-938) */
+    void ClearVoxelData(const std::string &key);
+
+    /* Run: model + technique from their registries, Initialize -> DoCalculations -> SaveResults
+     * (rundata.cc:248-311) */
+    void Run(void (*progress_cb)(int, int) = nullptr);
+
+    std::ostream &Log() { return m_log; }
+    std::string LogText() const { return m_log.str(); }
+    void ClearLog() { m_log.str(""); }
+    void Progress(int v, int n)
+    {
+        if (m_progress)
+            m_progress(v, n);
+    }
+    static void GetOptions(std::vector<OptionSpec> &opts);
+
+private:
+    std::map<std::string, std::string> m_params;
+    std::map<std::string, std::unique_ptr<VoxelData>> m_voxel_data;
+    int m_extent[3];
+    bool m_have_extent;
+    std::vector<int> m_mask, m_voxel_index, m_coords;
+    std::ostringstream m_log;
+    void (*m_progress)(int, int);
+};
+typedef FabberRunData FabberRunDataArray;
+
+/* ---- parameters and transforms (fwdmodel.h:24-57, transforms.h) ---------------------------------- */
+struct DistParams
+{
+    double m_mean, m_var;
+    DistParams(double mean = 0, double var = 1)
+        : m_mean(mean)
+        , m_var(var)
+    {
+    }
+    double mean() const { return m_mean; }
+    double var() const { return m_var; }
+    double prec() const { return 1 / m_var; }
+};
+double transform_to_model(char code, double v);
+double transform_to_fabber(char code, double v);
+double transform_to_model_var(char code, double v);
+double transform_to_fabber_var(char code, double v);
+
+struct Parameter
+{
+    unsigned idx;
+    std::string name;
+    DistParams prior, post;
+    char prior_type; /* 'N','I','A','M','m','P','p', '-' = model default */
+    char transform;  /* 'I','L','S','F','A' */
+    std::map<std::string, std::string> options;
+    Parameter(unsigned i = 0, const std::string &n = "", DistParams pr = DistParams(), DistParams po = DistParams(),
+        char ptype = 'N', char tr = 'I')
+        : idx(i)
+        , name(n)
+        , prior(pr)
+        , post(po)
+        , prior_type(ptype)
+        , transform(tr)
+    {
+    }
+};
+std::string ExpandPriorTypesString(std::string priors_str, unsigned num_params); /* priors.cc:35-106 */
+
+/* ---- forward models ----------------------------------------------------------------------------- */
+class FwdModel
+{
+public:
+    static FwdModel *NewFromName(const std::string &name); /* registry names: setup.cc:44-47 + "exp" */
+    static std::vector<std::string> GetKnown();
+    virtual ~FwdModel() {}
+    virtual std::string ModelVersion() const { return "b200"; }
+    virtual std::string GetDescription() const { return ""; }
+    virtual void GetOptions(std::vector<OptionSpec> &) const {}
+    virtual void Initialize(FabberRunData &rundata) = 0;
+    virtual void GetParameterDefaults(std::vector<Parameter> &params) const = 0;
+    /* one voxel's model prediction from model-space parameters (fwdmodel.h:149) */
+    virtual void EvaluateModel(const std::vector<double> &params, std::vector<double> &result, int n_times,
+        const std::string &key = "") const = 0;
+    virtual void GetOutputs(std::vector<std::string> &) const {}
+    /* B200 addition: describe the compiled __device__ Evaluate hook for this model instance */
+    virtual void GetDeviceModel(fabber_cuda_model &m) const = 0;
+
+    /* fwdmodel.cc:210-282: defaults + param-spatial-priors + PSP_byname overrides, prior -> Fabber space */
+    void GetParameters(FabberRunData &rundata, std::vector<Parameter> &params);
+    /* fwdmodel.cc:365-382 */
+    void EvaluateFabber(const std::vector<double> &theta, std::vector<double> &result, int n_times,
+        const std::string &key = "") const;
+    const std::vector<Parameter> &Params() const { return m_params; }
+
+protected:
+    std::vector<Parameter> m_params;
+};
+
+class LinearFwdModel : public FwdModel
+{
+public:
+    std::string GetDescription() const override;
+    void GetOptions(std::vector<OptionSpec> &opts) const override;
+    void Initialize(FabberRunData &rundata) override;
+    void GetParameterDefaults(std::vector<Parameter> &params) const override;
+    void EvaluateModel(const std::vector<double> &p, std::vector<double> &result, int n_times,
+        const std::string &key) const override;
+    void GetDeviceModel(fabber_cuda_model &m) const override;
+
+private:
+    std::vector<double> m_design; /* [T][P] row-major */
+    int m_ntimes = 0, m_nbasis = 0;
+};
+class PolynomialFwdModel : public FwdModel
+{
+public:
+    std::string GetDescription() const override;
+    void GetOptions(std::vector<OptionSpec> &opts) const override;
+    void Initialize(FabberRunData &rundata) override;
+    void GetParameterDefaults(std::vector<Parameter> &params) const override;
+    void EvaluateModel(const std::vector<double> &p, std::vector<double> &result, int n_times,
+        const std::string &key) const override;
+    void GetDeviceModel(fabber_cuda_model &m) const override;
+
+private:
+    int m_degree = 0;
+};
+class ExpFwdModel : public FwdModel
+{
+public:
+    std::string GetDescription() const override;
+    void GetOptions(std::vector<OptionSpec> &opts) const override;
+    void Initialize(FabberRunData &rundata) override;
+    void GetParameterDefaults(std::vector<Parameter> &params) const override;
+    void EvaluateModel(const std::vector<double> &p, std::vector<double> &result, int n_times,
+        const std::string &key) const override;
+    void GetDeviceModel(fabber_cuda_model &m) const override;
+
+private:
+    double m_dt = 1.0;
+    int m_num = 1;
+};
+
+/* tools.cc:27-40: VEST or plain ASCII matrix file -> row-major values */
+void read_matrix_file(const std::string &filename, std::vector<double> &values, int &rows, int &cols);
+
+/* ---- inference technique ---------------------------------------------------------------------------- */
+class Vb
+{
+public:
+    static std::vector<std::string> GetKnownMethods(); /* vb, spatialvb (setup.cc:29-30) */
+    static void GetOptions(std::vector<OptionSpec> &opts);
+    static std::string GetDescription();
+    void Initialize(FwdModel *model, FabberRunData &rundata); /* inference_vb.cc:100, inference.cc:62 */
+    void DoCalculations(FabberRunData &rundata);              /* inference_vb.cc:360 - runs on the GPU */
+    void SaveResults(FabberRunData &rundata);                 /* inference_vb.cc:966, inference.cc:112 */
+
+private:
+    bool IsSpatial(FabberRunData &rundata, const std::vector<Parameter> &params) const; /* :334-358 */
+    FwdModel *m_model = nullptr;
+    int m_num_params = 0, m_noise_params = 0;
+    bool m_ar = false, m_saveF = false, m_saveFsHistory = false, m_printF = false, m_needF = false;
+    bool m_halt_bad_voxel = true;
+    int m_nphis = 1;
+    /* results, structure of arrays over voxels (the layout of include/fabber_cuda.h) */
+    size_t m_nvoxels = 0;
+    int m_ntimes = 0;
+    std::vector<double> m_mean, m_cov, m_noise, m_F, m_Fhist;
+    std::vector<int> m_status, m_iterations;
+    int m_fhist_len = 0;
+};
+
+} // namespace fabber_b200

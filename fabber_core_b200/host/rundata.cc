@@ -1,0 +1,335 @@
+/*
+ * rundata.cc - FabberRunData / FabberRunDataArray: option map, extent + mask, voxel data T x Nvox.
+ * Behaviour follows rundata.cc:427-600 (options), rundata_array.cc:23-133 (array I/O) and
+ * rundata.cc:248-311 (Run). The main data keeps the caller's float32 samples in pinned host memory so
+ * that the copy to the GPU runs at full PCIe speed; outputs are double and converted to float on read,
+ * as in the reference.
+ */
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <ctime>
+
+#include "fabber_host.h"
+
+namespace fabber_b200
+{
+const char *option_type_name(OptionType t)
+{
+    switch (t)
+    {
+    case OPT_BOOL:
+        return "BOOL";
+    case OPT_STR:
+        return "STR";
+    case OPT_INT:
+        return "INT";
+    case OPT_FLOAT:
+        return "FLOAT";
+    case OPT_FILE:
+        return "FILE";
+    case OPT_IMAGE:
+        return "IMAGE";
+    case OPT_TIMESERIES:
+        return "TIMESERIES";
+    case OPT_MVN:
+        return "MVN";
+    case OPT_MATRIX:
+        return "MATRIX";
+    }
+    return "UNKNOWN";
+}
+
+VoxelData::VoxelData()
+    : rows(0)
+    , cols(0)
+    , is_float(false)
+    , f(nullptr)
+{
+}
+VoxelData::~VoxelData()
+{
+    if (f)
+        fabber_cuda_host_free(f);
+}
+void VoxelData::alloc_float(int r, size_t c)
+{
+    rows = r;
+    cols = c;
+    is_float = true;
+    if (f)
+        fabber_cuda_host_free(f);
+    f = (float *)fabber_cuda_host_alloc((unsigned long long)r * c * sizeof(float));
+    if (!f)
+        throw FabberInternalError(std::string("Could not allocate pinned host memory: ") + fabber_cuda_last_error());
+}
+void VoxelData::alloc_double(int r, size_t c)
+{
+    rows = r;
+    cols = c;
+    is_float = false;
+    d.assign((size_t)r * c, 0.0);
+}
+
+FabberRunData::FabberRunData()
+    : m_have_extent(false)
+    , m_progress(nullptr)
+{
+    m_extent[0] = m_extent[1] = m_extent[2] = 0;
+}
+FabberRunData::~FabberRunData() {}
+
+void FabberRunData::Set(const std::string &key, const std::string &value) { m_params[key] = value; }
+void FabberRunData::SetBool(const std::string &key, bool value)
+{
+    if (value)
+        m_params[key] = "";
+    else
+        m_params.erase(key);
+}
+void FabberRunData::Unset(const std::string &key) { m_params.erase(key); }
+bool FabberRunData::HaveKey(const std::string &key) const { return m_params.count(key) > 0; }
+
+std::string FabberRunData::GetString(const std::string &key)
+{
+    if (m_params.count(key) == 0)
+        throw MandatoryOptionMissing(key);
+    return m_params[key];
+}
+std::string FabberRunData::GetStringDefault(const std::string &key, const std::string &def)
+{
+    if (m_params.count(key) == 0)
+        return def;
+    if (m_params[key] == "")
+        throw InvalidOptionValue(key, "<no value>", "Value must be given");
+    return m_params[key];
+}
+bool FabberRunData::GetBool(const std::string &key)
+{
+    if (m_params.count(key) == 0)
+        return false;
+    if (m_params[key] == "")
+        return true;
+    throw InvalidOptionValue(key, m_params[key], "Value should not be given for boolean option");
+}
+static bool parse_int(const std::string &s, int &out)
+{
+    std::istringstream i(s);
+    char c;
+    if (!(i >> out) || (i >> c))
+        return false;
+    return true;
+}
+static bool parse_double(const std::string &s, double &out)
+{
+    std::istringstream i(s);
+    char c;
+    if (!(i >> out) || (i >> c))
+        return false;
+    return true;
+}
+int FabberRunData::GetInt(const std::string &key, int min, int max)
+{
+    std::string val = GetString(key);
+    int i;
+    if (!parse_int(val, i))
+        throw InvalidOptionValue(key, val, "Must be an integer");
+    if (i < min)
+        throw InvalidOptionValue(key, val, "Minimum " + stringify(min));
+    if (i > max)
+        throw InvalidOptionValue(key, val, "Maximum " + stringify(max));
+    return i;
+}
+int FabberRunData::GetIntDefault(const std::string &key, int def, int min, int max)
+{
+    return m_params.count(key) == 0 ? def : GetInt(key, min, max);
+}
+double FabberRunData::GetDouble(const std::string &key)
+{
+    std::string val = GetString(key);
+    double d;
+    if (!parse_double(val, d))
+        throw InvalidOptionValue(key, val, "Must be an number");
+    return d;
+}
+double FabberRunData::GetDoubleDefault(const std::string &key, double def)
+{
+    return m_params.count(key) == 0 ? def : GetDouble(key);
+}
+std::vector<std::string> FabberRunData::GetStringList(const std::string &prefix)
+{
+    std::vector<std::string> ret;
+    if (HaveKey(prefix))
+        ret.push_back(GetString(prefix));
+    else
+        for (int n = 1; HaveKey(prefix + stringify(n)); n++)
+            ret.push_back(GetString(prefix + stringify(n)));
+    return ret;
+}
+std::vector<int> FabberRunData::GetIntList(const std::string &prefix, int min, int max)
+{
+    std::vector<int> ret;
+    if (HaveKey(prefix))
+        ret.push_back(GetInt(prefix, min, max));
+    else
+        for (int n = 1; HaveKey(prefix + stringify(n)); n++)
+            ret.push_back(GetInt(prefix + stringify(n), min, max));
+    return ret;
+}
+
+/* rundata_array.cc:23-66 */
+void FabberRunData::SetExtent(int nx, int ny, int nz, const int *mask)
+{
+    if (nx <= 0 || ny <= 0 || nz <= 0)
+        throw FabberRunDataError("Dimensions must be >0");
+    m_extent[0] = nx;
+    m_extent[1] = ny;
+    m_extent[2] = nz;
+    m_have_extent = true;
+    const size_t nv = (size_t)nx * ny * nz;
+    if (mask)
+        m_mask.assign(mask, mask + nv);
+    else
+        m_mask.assign(nv, 1);
+    m_voxel_index.clear();
+    std::vector<int> cx, cy, cz;
+    size_t i = 0;
+    for (int z = 0; z < nz; z++)
+        for (int y = 0; y < ny; y++)
+            for (int x = 0; x < nx; x++, i++)
+                if (m_mask[i] != 0)
+                {
+                    m_voxel_index.push_back((int)i);
+                    cx.push_back(x);
+                    cy.push_back(y);
+                    cz.push_back(z);
+                }
+    m_coords.clear();
+    m_coords.insert(m_coords.end(), cx.begin(), cx.end());
+    m_coords.insert(m_coords.end(), cy.begin(), cy.end());
+    m_coords.insert(m_coords.end(), cz.begin(), cz.end());
+}
+
+/* rundata_array.cc:100-133: float[t][z][y][x] -> T x Nvox */
+void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, const float *data)
+{
+    if (!m_have_extent)
+        throw FabberRunDataError("Extent must be set before voxel data");
+    const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
+    const size_t N = m_voxel_index.size();
+    std::unique_ptr<VoxelData> vd(new VoxelData());
+    vd->alloc_float(data_size, N);
+    for (int t = 0; t < data_size; t++)
+    {
+        const float *src = data + (size_t)t * n_grid;
+        float *dst = vd->f + (size_t)t * N;
+        if (N == n_grid)
+            memcpy(dst, src, N * sizeof(float));
+        else
+            for (size_t v = 0; v < N; v++)
+                dst[v] = src[m_voxel_index[v]];
+    }
+    m_voxel_data[key] = std::move(vd);
+}
+
+const VoxelData &FabberRunData::GetVoxelData(const std::string &key_in)
+{
+    /* indirection: an option may name the data key (rundata.cc:802-823) */
+    std::string key = key_in;
+    std::set<std::string> seen;
+    while (m_voxel_data.count(key) == 0)
+    {
+        if (m_params.count(key) == 0 || m_params[key] == "" || seen.count(key))
+            throw DataNotFound(key_in);
+        seen.insert(key);
+        key = m_params[key];
+    }
+    return *m_voxel_data[key];
+}
+const VoxelData &FabberRunData::GetMainVoxelData() { return GetVoxelData("data"); }
+int FabberRunData::GetVoxelDataSize(const std::string &key) { return GetVoxelData(key).rows; }
+VoxelData &FabberRunData::NewVoxelData(const std::string &key, int rows)
+{
+    std::unique_ptr<VoxelData> vd(new VoxelData());
+    vd->alloc_double(rows, m_voxel_index.size());
+    m_voxel_data[key] = std::move(vd);
+    return *m_voxel_data[key];
+}
+void FabberRunData::ClearVoxelData(const std::string &key) { m_voxel_data.erase(key); }
+
+/* rundata_array.cc:68-98: T x Nvox -> float[t][z][y][x], zeros outside the mask */
+void FabberRunData::GetVoxelDataArray(const std::string &key, float *data)
+{
+    const VoxelData &vd = GetVoxelData(key);
+    const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
+    const size_t N = m_voxel_index.size();
+    for (int t = 0; t < vd.rows; t++)
+    {
+        float *dst = data + (size_t)t * n_grid;
+        if (N != n_grid)
+            memset(dst, 0, n_grid * sizeof(float));
+        if (vd.is_float)
+            for (size_t v = 0; v < N; v++)
+                dst[m_voxel_index[v]] = vd.f[(size_t)t * N + v];
+        else
+            for (size_t v = 0; v < N; v++)
+                dst[m_voxel_index[v]] = (float)vd.d[(size_t)t * N + v];
+    }
+}
+
+void FabberRunData::GetOptions(std::vector<OptionSpec> &opts)
+{
+    /* the VB-relevant subset of rundata.cc:139-201 */
+    static const OptionSpec O[] = {
+        { "method", OPT_STR, "Use this inference method", false, "" },
+        { "model", OPT_STR, "Use this forward model", false, "" },
+        { "data", OPT_TIMESERIES, "Main voxel data", false, "" },
+        { "mask", OPT_IMAGE, "Mask: inference will only be performed where mask value > 0", true, "" },
+        { "mt<n>", OPT_INT, "List of masked time points, indexed from 1", true, "" },
+        { "suppdata", OPT_TIMESERIES, "'Supplemental' timeseries data, required for some models", true, "" },
+        { "save-mean", OPT_BOOL, "Output the parameter means", true, "" },
+        { "save-std", OPT_BOOL, "Output the parameter standard deviations", true, "" },
+        { "save-var", OPT_BOOL, "Output the parameter variances", true, "" },
+        { "save-zstat", OPT_BOOL, "Output the parameter Zstats", true, "" },
+        { "save-noise-mean", OPT_BOOL, "Output the noise means", true, "" },
+        { "save-noise-std", OPT_BOOL, "Output the noise standard deviations", true, "" },
+        { "save-free-energy", OPT_BOOL, "Output the free energy, if calculated", true, "" },
+        { "save-model-fit", OPT_BOOL, "Output the model prediction as a 4d volume", true, "" },
+        { "save-residuals", OPT_BOOL, "Output the difference between the data and the model prediction", true, "" },
+        { "save-mvn", OPT_BOOL, "Output the final MVN distributions", true, "" },
+        { "allow-bad-voxels", OPT_BOOL, "Continue if numerical error found in a voxel, rather than stopping", true, "" },
+    };
+    for (size_t i = 0; i < sizeof(O) / sizeof(O[0]); i++)
+        opts.push_back(O[i]);
+}
+
+/* rundata.cc:248-311 */
+void FabberRunData::Run(void (*progress_cb)(int, int))
+{
+    m_progress = progress_cb;
+    time_t start;
+    time(&start);
+    m_log << "FabberRunData::Start time: " << ctime(&start);
+    std::unique_ptr<FwdModel> fwd_model(FwdModel::NewFromName(GetString("model")));
+    fwd_model->Initialize(*this);
+    std::vector<Parameter> params;
+    fwd_model->GetParameters(*this, params);
+    m_log << "FabberRunData::Forward Model version " << fwd_model->ModelVersion() << std::endl;
+
+    const std::string method = GetString("method");
+    if (method != "vb" && method != "spatialvb")
+        throw InvalidOptionValue("method", method,
+            "only vb and spatialvb run on the GPU path (nlls and other methods are outside this library)");
+    Vb vb;
+    vb.Initialize(fwd_model.get(), *this);
+    vb.DoCalculations(*this);
+    vb.SaveResults(*this);
+    time_t end;
+    time(&end);
+    m_log << "FabberRunData::All done." << std::endl;
+    m_log << "FabberRunData::End time: " << ctime(&end);
+    m_log << "FabberRunData::Duration: " << (long)difftime(end, start) << " seconds." << std::endl;
+    m_progress = nullptr;
+}
+
+} // namespace fabber_b200

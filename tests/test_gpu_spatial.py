@@ -1,0 +1,138 @@
+"""GPU parity: spatial VB (MRF / Penny spatial priors, ordered Gauss-Seidel sweep) through the C ABI
+against the CPU oracle. The reference pins spatial mode only without coupling (outdata_linear_spatialvb
+used 'N' priors); everything with an M/m/P/p prior is checked against the oracle alone ("parity
+unpinned" upstream)."""
+import numpy as np
+import pytest
+
+import oracle
+from fabber_core_b200 import cuda_abi as abi
+from fabber_core_b200 import device, synth
+from parity import compare, tri
+
+pytestmark = pytest.mark.gpu
+
+C5 = dict(model="exp", num_exps=2, dt=0.02, param_overrides={"r2": {"mean": 6.0}})
+
+
+def grid_coords(nx, ny, nz, mask=None):
+    idx = np.arange(nx * ny * nz)
+    coords = np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.int32)
+    if mask is not None:
+        coords = coords[:, mask.reshape(-1)]
+    return np.ascontiguousarray(coords)
+
+
+def both_spatial(spec_kwargs, data, coords, shape, **run_kwargs):
+    spec_kwargs = dict(spec_kwargs)
+    model = spec_kwargs.pop("model")
+    T = data.shape[0]
+
+    def mk():
+        sp = abi.ProblemSpec(model, T, **spec_kwargs)
+        sp.prob.nx, sp.prob.ny, sp.prob.nz = shape
+        return sp
+
+    ref = oracle.run(mk(), data, spatial=True, coords=coords, **run_kwargs)
+    variants = ("fma", "ulp") if model == "exp" else ("fma",)
+    probes = [oracle.run(mk(), data, spatial=True, coords=coords, variant=vr, **run_kwargs) for vr in variants]
+    gpu = device.run(mk(), data, spatial=True, coords=coords, **run_kwargs)
+    return gpu, ref, probes
+
+
+def check_ak(gpu, ref, probes, rtol=1e-6):
+    floor = max(np.max(np.abs(p["spatial_ak"] - ref["spatial_ak"]) / np.maximum(np.abs(ref["spatial_ak"]), 1e-300))
+                for p in probes)
+    err = np.max(np.abs(gpu["spatial_ak"] - ref["spatial_ak"]) / np.maximum(np.abs(ref["spatial_ak"]), 1e-300))
+    assert err <= max(rtol, 8 * floor), (err, floor)
+
+
+def test_linear_spatialvb_golden_no_coupling(golden):
+    coords = grid_coords(3, 3, 2)
+    gpu, ref, probes = both_spatial(dict(model="linear", design=golden["design"]), golden["data"], coords, (3, 3, 2))
+    compare(gpu, ref, 4, probes, check_f=False, label="spatialvb linear N priors")
+    for i in range(4):
+        g = golden["linear_spatialvb/mean_Parameter_%d" % (i + 1)][0]
+        assert np.max(np.abs(gpu["mean"][i] - g) / np.abs(g)) < 5e-6
+
+
+@pytest.mark.parametrize("types", ["MMMM", "PPPP", "MNMN", "MAMN"])
+def test_c5_biexp_spatial_priors(types):
+    nx, ny, nz = 12, 10, 6
+    y = synth.biexp_volume(nx * ny * nz, 96, 0.02, 0.02, seed=1005, smooth_shape=(nx, ny, nz)).numpy()
+    coords = grid_coords(nx, ny, nz)
+    gpu, ref, probes = both_spatial(dict(C5, prior_types=list(types), need_f=True, max_iterations=6,
+                                         allow_bad_voxels=True), y, coords, (nx, ny, nz))
+    compare(gpu, ref, 4, probes, label="C5 spatial %s" % types)
+    check_ak(gpu, ref, probes)
+
+
+@pytest.mark.parametrize("types", ["mmm", "ppp", "pMm", "PmN"])
+def test_poly_spatial_dirichlet_priors(types):
+    """'m' / 'p' ignore the model's own prior precision (priors.cc:421-425); on the log-transformed biexp
+    they make the reference itself overflow in the first iteration, so they are exercised on poly."""
+    nx, ny, nz = 10, 9, 5
+    y = synth.poly_volume(nx * ny * nz, 40, 2, seed=35).numpy()
+    coords = grid_coords(nx, ny, nz)
+    gpu, ref, probes = both_spatial(dict(model="poly", degree=2, prior_types=list(types), need_f=True,
+                                         max_iterations=5, allow_bad_voxels=True), y, coords, (nx, ny, nz))
+    compare(gpu, ref, 3, probes, label="poly spatial %s" % types)
+    check_ak(gpu, ref, probes)
+
+
+def test_spatial_blow_up_is_reported_like_the_reference():
+    """biexp with 'p' priors: every voxel overflows in iteration 1 in the reference too; by default the
+    run halts (inference_vb.cc:652-671) - same return code, and with allow-bad-voxels the same masks."""
+    nx, ny, nz = 6, 5, 4
+    y = synth.biexp_volume(nx * ny * nz, 96, 0.02, 0.02, seed=1005, smooth_shape=(nx, ny, nz)).numpy()
+    coords = grid_coords(nx, ny, nz)
+    kw = dict(C5, prior_types=list("pppp"), max_iterations=3)
+    gpu, ref, _ = both_spatial(kw, y, coords, (nx, ny, nz))
+    assert ref["rc"] == abi.ERR_BAD_VOXEL and gpu["rc"] == abi.ERR_BAD_VOXEL
+    gpu, ref, _ = both_spatial(dict(kw, allow_bad_voxels=True), y, coords, (nx, ny, nz))
+    assert np.array_equal(gpu["status"] != 0, ref["status"] != 0)
+
+
+def test_spatial_irregular_mask_and_update_first_iter():
+    nx, ny, nz = 11, 11, 7
+    zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    mask = ((xx - 5) ** 2 + (yy - 5) ** 2 + (2 * (zz - 3)) ** 2) < 0.45 * 11 * 0.45 * 11
+    full = synth.poly_volume(nx * ny * nz, 40, 2, seed=31).numpy()
+    y = np.ascontiguousarray(full[:, mask.reshape(-1)])
+    coords = grid_coords(nx, ny, nz, mask)
+    gpu, ref, probes = both_spatial(dict(model="poly", degree=2, prior_types=list("MMM"), need_f=True,
+                                         update_first_iter=True, max_iterations=5, allow_bad_voxels=True), y, coords,
+                                    (nx, ny, nz))
+    compare(gpu, ref, 3, probes, label="spatial irregular mask")
+    check_ak(gpu, ref, probes)
+
+
+@pytest.mark.parametrize("dims", [1, 2])
+def test_spatial_dims(dims):
+    nx, ny, nz = 9, 8, 3
+    y = synth.poly_volume(nx * ny * nz, 30, 1, seed=32).numpy()
+    coords = grid_coords(nx, ny, nz)
+    gpu, ref, probes = both_spatial(dict(model="poly", degree=1, prior_types=list("Mm"), spatial_dims=dims,
+                                         need_f=True, max_iterations=4, allow_bad_voxels=True), y, coords, (nx, ny, nz))
+    compare(gpu, ref, 2, probes, label="spatial dims %d" % dims)
+    check_ak(gpu, ref, probes)
+
+
+def test_spatial_speed_limit():
+    nx, ny, nz = 8, 8, 4
+    y = synth.poly_volume(nx * ny * nz, 30, 1, seed=33).numpy()
+    coords = grid_coords(nx, ny, nz)
+    gpu, ref, probes = both_spatial(dict(model="poly", degree=1, prior_types=list("MM"), spatial_speed=2.0,
+                                         spatial_q1=5.0, spatial_q2=2.0, max_iterations=4), y, coords, (nx, ny, nz))
+    compare(gpu, ref, 2, probes, check_f=False, label="spatial speed")
+    check_ak(gpu, ref, probes)
+
+
+def test_spatial_rejects_unordered_coords():
+    nx, ny, nz = 4, 4, 2
+    y = synth.poly_volume(nx * ny * nz, 20, 1, seed=34).numpy()
+    coords = grid_coords(nx, ny, nz)[:, ::-1].copy()
+    spec = abi.ProblemSpec("poly", 20, degree=1, prior_types=list("MM"))
+    spec.prob.nx, spec.prob.ny, spec.prob.nz = nx, ny, nz
+    with pytest.raises(device.CudaError):
+        device.run(spec, y, spatial=True, coords=coords)

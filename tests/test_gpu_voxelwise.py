@@ -194,3 +194,38 @@ def test_full_size_properties_c2():
     ref = oracle.run(abi.ProblemSpec("poly", 64, degree=3), ys)
     fma = oracle.run(abi.ProblemSpec("poly", 64, degree=3), ys, variant="fma")
     compare(small, ref, 4, fma, check_f=False, label="C2 full-size sample")
+
+
+# ---- AR(1) noise (noisemodel_ar.cc, num-echoes=1, ar1-cross-terms=none) ---------------------------
+@pytest.mark.parametrize("conv", ["maxits", "pointzeroone", "trialmode", "lm"])
+def test_c4_linear_ar1(conv):
+    y = synth.linear_ar_volume(1500, 200, 0.3, seed=1004).numpy()
+    gpu, ref, probes = both(dict(model="linear", design=synth.ar_design(200), noise="ar", convergence=conv,
+                                 need_f=True), y)
+    compare(gpu, ref, 4, probes, label="C4 linear AR1 %s" % conv)
+    # the AR coefficient is recovered (truth 0.3)
+    assert abs(np.median(gpu["noise"][2]) - 0.3) < 0.05
+
+
+def test_poly_ar1_fit():
+    """test/test_vb.cc:617-694: polynomial data + noise, AR noise model, coefficients within 0.2."""
+    rng = np.random.default_rng(12)
+    T, N = 50, 64
+    i = np.arange(1, T + 1, dtype=np.float64)[:, None]
+    y = (2.0 + 0.5 * i + 0.01 * i * i + 0.05 * rng.standard_normal((T, N))).astype(np.float32)
+    gpu, ref, probes = both(dict(model="poly", degree=2, noise="ar", need_f=True), y)
+    compare(gpu, ref, 3, probes, label="poly AR1")
+    assert np.all(np.abs(gpu["mean"][0] - 2.0) < 0.2) and np.all(np.abs(gpu["mean"][1] - 0.5) < 0.2)
+
+
+def test_ar1_with_masked_timepoints_is_rejected():
+    """test/test_inference.cc:564-633: AR + masked time points must fail."""
+    spec = abi.ProblemSpec("poly", 20, degree=1, noise="ar", masked_timepoints=(3,))
+    with pytest.raises(device.CudaError):
+        device.run(spec, np.ones((20, 4), dtype=np.float32))
+
+
+def test_biexp_ar1():
+    y = synth.biexp_volume(600, 96, 0.02, 0.02, seed=21).numpy()
+    gpu, ref, probes = both(dict(C3, noise="ar", need_f=True, convergence="pointzeroone"), y)
+    compare(gpu, ref, 4, probes, label="biexp AR1")
