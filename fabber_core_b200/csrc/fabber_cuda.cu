@@ -6,6 +6,8 @@
  * There is deliberately no CPU path in here: if CUDA is unavailable every entry point fails with
  * FABBER_CUDA_ERR_CUDA.
  */
+#include <cub/cub.cuh>
+
 #include <atomic>
 #include <cstdio>
 #include <cstring>
@@ -31,6 +33,24 @@ static int fail(int code, const std::string &msg)
 static int cuda_fail(cudaError_t e, const char *what)
 {
     return fail(FABBER_CUDA_ERR_CUDA, std::string(what) + ": " + cudaGetErrorString(e));
+}
+
+/* Scratch comes from the stream-ordered allocator. By default the pool hands freed memory back to the
+ * driver at the next synchronisation, so a spatial run would re-acquire ~14 GB from the OS on every call
+ * (seconds, and erratic - measured). Keep it cached in the pool instead. */
+static void keep_pool_memory()
+{
+    static int done_for_device = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for_device)
+        return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+    {
+        unsigned long long threshold = ~0ull;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+    done_for_device = dev;
 }
 
 /* getters exported by the per-model translation units (vb_inst.cu) */
@@ -94,6 +114,56 @@ __global__ void status_scan_kernel(const int *__restrict__ status, int N, int *o
     }
 }
 
+/* row-wise voxel permutation of a [rows][N] array: gather out[r][i] = in[r][perm[i]], or its inverse
+ * scatter out[r][perm[i]] = in[r][i] (spatial VB keeps its state in hyper-plane-major voxel order) */
+template <class T, bool GATHER>
+__global__ void permute_rows_kernel(const T *__restrict__ in, T *__restrict__ out, const int *__restrict__ perm,
+    int rows, int N)
+{
+    const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (size_t)rows * N)
+        return;
+    const size_t r = idx / N, i = idx - r * N;
+    if (GATHER)
+        out[idx] = in[r * N + (size_t)perm[i]];
+    else
+        out[r * N + (size_t)perm[i]] = in[idx];
+}
+template <class T, bool GATHER>
+static void permute_rows(const T *in, T *out, const int *perm, int rows, int N, cudaStream_t st)
+{
+    const size_t total = (size_t)rows * N;
+    if (total == 0)
+        return;
+    permute_rows_kernel<T, GATHER><<<(unsigned)((total + 255) / 256), 256, 0, st>>>(in, out, perm, rows, N);
+    count_launch();
+}
+__global__ void iota_kernel(int *out, int N)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N)
+        out[i] = i;
+}
+__global__ void rank_kernel(const int *order, int N, int *rank)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N)
+        rank[order[i]] = i;
+}
+/* neighbour table in permuted numbering: nnp[j][pos] = rank[nn[j][order[pos]]] */
+__global__ void renumber_neighbours_kernel(const int *nn, const int *order, const int *rank, int N, int *nnp)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N)
+        return;
+    const int v = order[i];
+    for (int j = 0; j < 6; j++)
+    {
+        const int n = nn[(size_t)j * N + v];
+        nnp[(size_t)j * N + i] = n >= 0 ? rank[n] : -1;
+    }
+}
+
 /* dependent-free DFMA loop: 8 independent accumulators per thread */
 __global__ void fp64_peak_kernel(double *out, int iters, double x)
 {
@@ -142,6 +212,7 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
 {
     if (!prob || !buf)
         return fail(FABBER_CUDA_ERR_INVALID, "null problem or buffers");
+    keep_pool_memory();
     const int P = prob->model.n_params, T = prob->n_times, N = prob->n_voxels;
     if (P < 1 || P > FABBER_CUDA_MAX_PARAMS)
         return fail(FABBER_CUDA_ERR_INVALID, "n_params out of range");
@@ -492,8 +563,9 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
 
     Scratch sc(st);
     int *grid2vox = sc.get<int>(n_grid), *nn_idx = sc.get<int>((size_t)6 * N), *plane_of = sc.get<int>(N);
-    int *order = sc.get<int>(N), *hist = sc.get<int>(n_planes + 1), *cursor = sc.get<int>(n_planes + 1);
-    int *bad = sc.get<int>(1);
+    int *order = sc.get<int>(N), *hist = sc.get<int>(n_planes + 1), *rank = sc.get<int>(N);
+    int *bad = sc.get<int>(1), *iota = sc.get<int>(N), *plane_sorted = sc.get<int>(N), *nnp = sc.get<int>((size_t)6 * N);
+    int *plane_starts = sc.get<int>(n_planes + 2);
     sp.centre = sc.get<double>((size_t)P * N);
     sp.stats = sc.get<double>((size_t)(NT + P + 1) * N);
     sp.m0 = sc.get<double>((size_t)P * N);
@@ -504,11 +576,17 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
     sp.ak_hist = sc.get<double>((size_t)(max_it + 1) * P);
     sp.ak_partial = sc.get<double>((size_t)SP_AK_BLOCKS * 2 * P);
     sp.fprior_last = sc.get<double>(1);
-    if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !cursor || !bad || !sp.centre || !sp.stats || !sp.m0
-        || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last)
+    /* the run's inputs and outputs in hyper-plane-major voxel order (see below) */
+    const int H = sp.v.f_history_len;
+    float *y_p = sc.get<float>((size_t)prob->n_times * N);
+    double *mean_p = sc.get<double>((size_t)P * N), *cov_p = sc.get<double>((size_t)NT * N);
+    double *noise_p = sc.get<double>((size_t)2 * N), *F_p = sc.get<double>(N), *hist_p = sc.get<double>((size_t)H * N);
+    int *its_p = sc.get<int>(N), *status_p = sc.get<int>(N);
+    if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !rank || !bad || !iota || !plane_sorted || !nnp
+        || !plane_starts || !sp.centre || !sp.stats || !sp.m0 || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK
+        || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last || !y_p || !mean_p || !cov_p || !noise_p || !F_p || !hist_p
+        || !its_p || !status_p)
         return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-    sp.nn_idx = nn_idx;
-    sp.order = order;
     sp.ak_blocks = SP_AK_BLOCKS;
     sp.spatial_dims = prob->spatial_dims;
     sp.update_first_iter = prob->update_first_iter;
@@ -517,7 +595,13 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
     sp.q2 = prob->spatial_q2;
     sp.speed = prob->spatial_speed;
 
-    /* ---- neighbours + hyper-plane order (Vb::CalcNeighbours) ---------------------------------- */
+    /* ---- neighbours (Vb::CalcNeighbours) and the hyper-plane-major renumbering ----------------------
+     * The ordered sweep walks planes x+y+z = h. In the caller's x-fastest order the voxels of a plane are
+     * strided through memory and every access of the sweep is an uncoalesced 8-byte gather (measured:
+     * 64 % of the step). So the whole spatial run works on a renumbered volume: voxels sorted by plane,
+     * original order kept inside a plane (stable radix sort), which makes every per-voxel array access of
+     * every kernel coalesced and keeps the -x/-y/-z neighbours of consecutive voxels consecutive too. The
+     * time-series is permuted once on the way in, the results once on the way out. */
     cudaMemsetAsync(grid2vox, 0xff, n_grid * sizeof(int), st);
     cudaMemsetAsync(hist, 0, (n_planes + 1) * sizeof(int), st);
     cudaMemsetAsync(bad, 0, sizeof(int), st);
@@ -533,7 +617,27 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
     sp_neighbour_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, prob->spatial_dims, nn_idx,
         plane_of, hist);
     count_launch();
-    std::vector<int> h_hist(n_planes + 1), h_begin(n_planes + 1);
+    iota_kernel<<<gridN, 256, 0, st>>>(iota, N);
+    count_launch();
+    {
+        int bits = 1;
+        while ((1 << bits) <= n_planes)
+            bits++;
+        size_t tmp_bytes = 0;
+        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plane_of, plane_sorted, iota, order, N, 0, bits, st);
+        void *tmp = sc.get<char>(tmp_bytes);
+        if (!tmp)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        cudaError_t se = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plane_of, plane_sorted, iota, order, N, 0, bits, st);
+        if (se != cudaSuccess)
+            return cuda_fail(se, "hyper-plane sort");
+        count_launch();
+    }
+    rank_kernel<<<gridN, 256, 0, st>>>(order, N, rank);
+    count_launch();
+    renumber_neighbours_kernel<<<gridN, 256, 0, st>>>(nn_idx, order, rank, N, nnp);
+    count_launch();
+    std::vector<int> h_hist(n_planes + 1), h_begin(n_planes + 2);
     int h_bad = 0;
     cudaMemcpyAsync(h_hist.data(), hist, (n_planes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st);
     cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
@@ -551,9 +655,50 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
         h_begin[h] = acc;
         acc += h_hist[h];
     }
-    cudaMemcpyAsync(cursor, h_begin.data(), (n_planes + 1) * sizeof(int), cudaMemcpyHostToDevice, st);
-    sp_order_kernel<<<gridN, 256, 0, st>>>(plane_of, N, cursor, order);
-    count_launch();
+    h_begin[n_planes + 1] = acc;
+    cudaMemcpyAsync(plane_starts, h_begin.data(), (n_planes + 2) * sizeof(int), cudaMemcpyHostToDevice, st);
+    sp.plane_starts = plane_starts;
+    sp.n_planes = n_planes + 1;
+    sp.nn_idx = nnp;
+    sp.order = order;
+
+    /* inputs into plane-major order */
+    permute_rows<float, true>(buf->data, y_p, order, prob->n_times, N, st);
+    sp.v.data = y_p;
+    for (int i = 0; i < P; i++)
+        if (sp.v.image_prior[i])
+        {
+            double *img = sc.get<double>(N);
+            if (!img)
+                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+            permute_rows<double, true>(sp.v.image_prior[i], img, order, 1, N, st);
+            sp.v.image_prior[i] = img;
+        }
+    if (sp.v.init_mean)
+    {
+        double *im = sc.get<double>((size_t)P * N), *ic = sc.get<double>((size_t)NT * N);
+        if (!im || !ic)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        permute_rows<double, true>(sp.v.init_mean, im, order, P, N, st);
+        permute_rows<double, true>(sp.v.init_cov, ic, order, NT, N, st);
+        sp.v.init_mean = im;
+        sp.v.init_cov = ic;
+    }
+    if (sp.v.init_noise)
+    {
+        double *in = sc.get<double>((size_t)2 * N);
+        if (!in)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        permute_rows<double, true>(sp.v.init_noise, in, order, 2, N, st);
+        sp.v.init_noise = in;
+    }
+    sp.v.mean = mean_p;
+    sp.v.cov = cov_p;
+    sp.v.noise = noise_p;
+    sp.v.free_energy = F_p;
+    sp.v.f_history = H > 0 ? hist_p : nullptr;
+    sp.v.iterations = its_p;
+    sp.v.status = status_p;
     cudaStreamSynchronize(st); /* h_begin is pageable host memory */
 
     /* ---- set-up, then the iteration-major loop ------------------------------------------------- */
@@ -577,19 +722,24 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
         FAB_SP_LAUNCH(sp_ak_final);
         FAB_SP_LAUNCH(sp_theta);
         if (any_coupled)
-            for (int h = 0; h < n_planes; h++)
-                if (h_hist[h] > 0)
-                {
-                    sp.plane_begin = h_begin[h];
-                    sp.plane_count = h_hist[h];
-                    FAB_SP_LAUNCH(sp_sweep);
-                }
+            FAB_SP_LAUNCH(sp_sweep);
         FAB_SP_LAUNCH(sp_noise);
     }
     sp.it = max_it;
     sp.ak_update = 0;
     FAB_SP_LAUNCH(sp_ak_final);
 #undef FAB_SP_LAUNCH
+    /* results back into the caller's voxel order */
+    permute_rows<double, false>(mean_p, buf->mean, order, P, N, st);
+    permute_rows<double, false>(cov_p, buf->cov, order, NT, N, st);
+    permute_rows<double, false>(noise_p, buf->noise, order, 2, N, st);
+    permute_rows<int, false>(status_p, buf->status, order, 1, N, st);
+    if (buf->free_energy)
+        permute_rows<double, false>(F_p, buf->free_energy, order, 1, N, st);
+    if (buf->iterations)
+        permute_rows<int, false>(its_p, buf->iterations, order, 1, N, st);
+    if (H > 0)
+        permute_rows<double, false>(hist_p, buf->f_history, order, H, N, st);
     if (buf->spatial_ak)
         cudaMemcpyAsync(buf->spatial_ak, sp.ak_hist, (size_t)(max_it + 1) * P * sizeof(double),
             cudaMemcpyDeviceToHost, st);
@@ -633,9 +783,43 @@ int fabber_cuda_check_status(const int *status, int n_voxels, int *first_bad_vox
     return h[0];
 }
 
-int fabber_cuda_model_fit(const fabber_cuda_vb_problem *, const double *, double *, void *)
+int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean, double *fit, void *stream)
 {
-    return fail(FABBER_CUDA_ERR_INVALID, "model_fit kernel not built yet");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!prob || !mean || !fit)
+        return fail(FABBER_CUDA_ERR_INVALID, "null argument");
+    const int P = prob->model.n_params, T = prob->n_times, N = prob->n_voxels;
+    if (P < 1 || P > FABBER_CUDA_MAX_PARAMS || T < 1 || N < 0)
+        return fail(FABBER_CUDA_ERR_INVALID, "bad sizes");
+    const ModelLaunchers *ml = find_model(prob->model.id, P);
+    if (!ml || !ml->model_fit)
+        return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
+    VbArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N;
+    a.T = T;
+    for (int i = 0; i < P; i++)
+        a.params[i] = prob->params[i];
+    a.exp_dt = prob->model.exp_dt;
+    a.fit_mean = mean;
+    a.fit_out = fit;
+    Staged staged;
+    if (prob->model.id == FABBER_MODEL_LINEAR)
+    {
+        if (!prob->model.design)
+            return fail(FABBER_CUDA_ERR_INVALID, "linear model without design matrix");
+        const size_t bytes = (size_t)T * P * sizeof(double);
+        cudaError_t e = cudaMallocAsync((void **)&staged.design, bytes, st);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "cudaMallocAsync(design)");
+        cudaMemcpyAsync(staged.design, prob->model.design, bytes, cudaMemcpyHostToDevice, st);
+        a.design = staged.design;
+    }
+    cudaError_t e = ml->model_fit(a, st);
+    staged.release(st);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "model_fit launch");
+    return FABBER_CUDA_OK;
 }
 
 double fabber_cuda_measure_fp64_peak(int repeats)

@@ -3,6 +3,8 @@
  *   -DFAB_FAMILY=<LinearModel|PolyModel|ExpModel> -DFAB_K=<template argument> -DFAB_GETTER=<symbol>
  * Instantiates every kernel that model needs and exports its launcher table.
  */
+#include <cstdlib>
+
 #include "vb_launch.h"
 #include "vb_voxelwise.cuh"
 #include "vb_voxelwise_ar.cuh"
@@ -59,6 +61,19 @@ static cudaError_t launch_ar(const VbArgs &a, cudaStream_t s)
     return cudaGetLastError();
 }
 
+static cudaError_t launch_model_fit(const VbArgs &a, cudaStream_t s)
+{
+    if (a.N <= 0)
+        return cudaSuccess;
+    const size_t smem = M::smem_bytes(a.T);
+    auto kern = model_fit_kernel<M>;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<(unsigned)((a.N + 255) / 256), 256, smem, s>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
 static cudaError_t launch_sp_setup(const SpArgs &s, cudaStream_t st)
 {
     const size_t smem = M::smem_bytes(s.v.T);
@@ -87,7 +102,7 @@ static cudaError_t launch_sp_ak_partial(const SpArgs &s, cudaStream_t st)
 }
 static cudaError_t launch_sp_ak_final(const SpArgs &s, cudaStream_t st)
 {
-    sp_ak_final_kernel<M::P><<<1, 32, 0, st>>>(s);
+    sp_ak_final_kernel<M::P><<<1, 256, 0, st>>>(s);
     count_launch();
     return cudaGetLastError();
 }
@@ -99,11 +114,30 @@ static cudaError_t launch_sp_theta(const SpArgs &s, cudaStream_t st)
 }
 static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
 {
-    if (s.plane_count <= 0)
-        return cudaSuccess;
-    sp_sweep_kernel<M::P><<<(unsigned)((s.plane_count + 127) / 128), 128, 0, st>>>(s);
+    /* persistent cooperative kernel: as many CTAs as can be co-resident (grid-wide barrier inside) */
+    static int grid = 0;
+    auto kern = sp_sweep_kernel<M::P>;
+    if (grid == 0)
+    {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, SP_SWEEP_BLOCK, 0);
+        if (e != cudaSuccess)
+            return e;
+        if (per_sm < 1)
+            return cudaErrorLaunchOutOfResources;
+        int want = 2; /* CTAs per SM: the grid-wide barrier gets dearer with every CTA (measured, profiles/) */
+        if (const char *env = getenv("FABBER_SWEEP_CTAS_PER_SM"))
+            want = atoi(env);
+        if (want < 1)
+            want = 1;
+        grid = sms * (per_sm > want ? want : per_sm);
+    }
+    void *args[] = { (void *)&s };
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(SP_SWEEP_BLOCK), args, 0, st);
     count_launch();
-    return cudaGetLastError();
+    return e;
 }
 
 static const ModelLaunchers g_launchers = {
@@ -111,7 +145,7 @@ static const ModelLaunchers g_launchers = {
     launch_white<1, true>,
     launch_white<FABBER_CUDA_MAX_PHIS, true>,
     launch_ar,
-    nullptr,
+    launch_model_fit,
     launch_sp_setup,
     launch_sp_ak_partial,
     launch_sp_ak_final,

@@ -26,9 +26,13 @@
  * neighbour mean drops out of the prior mean; only the precision and aK see the neighbours. Those types
  * therefore need no ordered sweep (and no second-neighbour lists) - reproduced, not "fixed".
  *
- * Between kernels the per-voxel state lives in HBM as structure-of-arrays [field][N] doubles.
+ * Between kernels the per-voxel state lives in HBM as structure-of-arrays [field][N] doubles. All kernels
+ * of a spatial run index voxels in HYPER-PLANE-MAJOR order (fabber_cuda.cu renumbers inputs on the way in
+ * and results on the way out), so that a plane of the sweep is a contiguous, coalesced range.
  */
 #pragma once
+#include <cooperative_groups.h>
+
 #include "vb_voxelwise.cuh"
 
 namespace fab
@@ -46,8 +50,9 @@ struct SpArgs
     double *ak_hist;     /* [max_it + 1][P] (device) */
     double *ak_partial;  /* [ak_blocks][2][P] */
     double *fprior_last; /* [1] stale Fprior of the last voxel (inference_vb.cc:700) */
-    const int *order;    /* voxels sorted by hyper-plane */
-    int plane_begin, plane_count;
+    const int *order;    /* original voxel index of each (plane-major) position */
+    const int *plane_starts; /* [n_planes + 1] offsets into order (device) */
+    int n_planes;
     int ak_blocks;
     int it;
     int spatial_dims;
@@ -213,22 +218,37 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
     }
 }
 
-/* one block: fixed-order final sum, then the Penny update for aK (priors.cc:296-343) */
-template <int P> __global__ void sp_ak_final_kernel(const __grid_constant__ SpArgs s)
+/* one block: fixed-order (hence deterministic) final sum, then the Penny update for aK (priors.cc:296-343) */
+template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const __grid_constant__ SpArgs s)
 {
     const VbArgs &a = s.v;
+    __shared__ double red[256];
+    __shared__ double sums[2 * P];
+    if (s.ak_update)
+        for (int q = 0; q < 2 * P; q++)
+        {
+            double x = 0.0;
+            for (int b = threadIdx.x; b < s.ak_blocks; b += 256)
+                x += s.ak_partial[(size_t)b * 2 * P + q];
+            red[threadIdx.x] = x;
+            __syncthreads();
+            for (int o = 128; o > 0; o >>= 1)
+            {
+                if (threadIdx.x < o)
+                    red[threadIdx.x] += red[threadIdx.x + o];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0)
+                sums[q] = red[0];
+            __syncthreads();
+        }
     const int k = threadIdx.x;
     if (k >= P)
         return;
     const char ty = a.params[k].prior_type;
     if (s.ak_update && is_spatial_type(ty))
     {
-        double trace_term = 0.0, term2 = 0.0;
-        for (int b = 0; b < s.ak_blocks; b++)
-        {
-            trace_term += s.ak_partial[(size_t)b * 2 * P + k];
-            term2 += s.ak_partial[(size_t)b * 2 * P + P + k];
-        }
+        const double trace_term = sums[k], term2 = sums[P + k];
         const double gk = 1 / (0.5 * trace_term + 0.5 * term2 + 1 / s.q1);
         const double hK = (a.N * 0.5 + s.q2);
         double aK = gk * hK;
@@ -323,7 +343,7 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
             L0[k] = p.prior_prec;
         }
     }
-    if (v == a.N - 1)
+    if (s.order[v] == a.N - 1) /* the reference's last voxel: its Fprior goes stale into the second loop */
         *s.fprior_last = Fprior;
     const double phi = a.noise[0 * N + v] * a.noise[1 * N + v];
     double Lam[NT], Sig[NT], ld;
@@ -373,59 +393,119 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
     }
 }
 
-/* ---- ordered sweep over one hyper-plane: MRF prior means + posterior means, in place --------------- */
-template <int P> __global__ void __launch_bounds__(128) sp_sweep_kernel(const __grid_constant__ SpArgs s)
+/* ---- ordered sweep: MRF prior means + posterior means, in place, plane by plane ------------------------
+ * One persistent cooperative kernel walks the hyper-planes with a grid-wide barrier between them (a
+ * launch per plane costs ~13 us each, 64 % of the spatial step in the round-1 launch list). Neighbour
+ * means are read with ld.global.cg: they were written by other SMs one barrier ago and must not be
+ * served from a stale L1 line. */
+constexpr int SP_SWEEP_BLOCK = 256;
+
+template <int P> struct SweepVoxel
 {
-    constexpr int NT = NTri<P>::value;
-    const VbArgs &a = s.v;
-    const int i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i0 >= s.plane_count)
-        return;
-    const int v = s.order[s.plane_begin + i0];
-    const size_t N = (size_t)a.N;
-    if (a.status[v] != 0)
-        return;
-    int nbr[6], nn = 0;
-#pragma unroll
-    for (int j = 0; j < 6; j++)
+    static constexpr int NT = NTri<P>::value;
+    int v, nbr[6];
+    double rhs[P], Sig[NT], L0[P];
+    bool live;
+    /* everything that does not depend on this sweep's updates: issued one barrier early */
+    FAB_DEV void load_static(const SpArgs &s, int pos)
     {
-        nbr[j] = s.nn_idx[j * N + v];
-        nn += nbr[j] >= 0;
-    }
-    double rhs[P], Sig[NT];
-#pragma unroll
-    for (int i = 0; i < P; i++)
-        rhs[i] = s.rhs[i * N + v];
-#pragma unroll
-    for (int i = 0; i < NT; i++)
-        Sig[i] = a.cov[i * N + v];
-    const int dims = s.spatial_dims;
-#pragma unroll
-    for (int k = 0; k < P; k++)
-    {
-        const char ty = a.params[k].prior_type;
-        if (ty != 'M' && ty != 'm')
-            continue;
-        double contrib = 0.0;
+        const VbArgs &a = s.v;
+        const size_t N = (size_t)a.N;
+        v = pos;
+        live = a.status[pos] == 0;
 #pragma unroll
         for (int j = 0; j < 6; j++)
-            if (nbr[j] >= 0)
-                contrib += a.mean[k * N + nbr[j]];
-        const int n1 = (ty == 'm') ? 2 * dims : nn;
-        const double aK = s.aK[k];
-        const double sp = (ty == 'M') ? aK * (n1 + 1e-8) : aK * n1;
-        const double rec = 1 / double(n1);
-        const double spatial_mean = contrib * rec;
-        const double L0k = s.L0[k * N + v];
-        const double m0k = (1.0 / L0k) * sp * spatial_mean; /* priors.cc:469-470 */
-        s.m0[k * N + v] = m0k;
-        rhs[k] += L0k * m0k;
-    }
-    double mn[P];
-    symv<P>(Sig, rhs, mn);
+            nbr[j] = s.nn_idx[j * N + pos];
 #pragma unroll
-    for (int i = 0; i < P; i++)
-        a.mean[i * N + v] = mn[i];
+        for (int i = 0; i < P; i++)
+        {
+            rhs[i] = s.rhs[i * N + pos];
+            L0[i] = s.L0[i * N + pos];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            Sig[i] = a.cov[i * N + pos];
+    }
+    /* the part on the critical path: neighbour means (ld.global.cg - written by other SMs one barrier
+     * ago, must not come from a stale L1 line), prior mean, posterior mean */
+    FAB_DEV void finish(const SpArgs &s)
+    {
+        if (!live)
+            return;
+        const VbArgs &a = s.v;
+        const size_t N = (size_t)a.N;
+        int nn = 0;
+#pragma unroll
+        for (int j = 0; j < 6; j++)
+            nn += nbr[j] >= 0;
+        const int dims = s.spatial_dims;
+#pragma unroll
+        for (int k = 0; k < P; k++)
+        {
+            const char ty = a.params[k].prior_type;
+            if (ty != 'M' && ty != 'm')
+                continue;
+            double contrib = 0.0;
+#pragma unroll
+            for (int j = 0; j < 6; j++)
+                if (nbr[j] >= 0)
+                    contrib += __ldcg(a.mean + k * N + nbr[j]);
+            const int n1 = (ty == 'm') ? 2 * dims : nn;
+            const double aK = s.aK[k];
+            const double sp = (ty == 'M') ? aK * (n1 + 1e-8) : aK * n1;
+            const double rec = 1 / double(n1);
+            const double spatial_mean = contrib * rec;
+            const double m0k = (1.0 / L0[k]) * sp * spatial_mean; /* priors.cc:469-470 */
+            s.m0[k * N + v] = m0k;
+            rhs[k] += L0[k] * m0k;
+        }
+        double mn[P];
+        symv<P>(Sig, rhs, mn);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            __stcg(a.mean + i * N + v, mn[i]);
+    }
+};
+
+template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kernel(const __grid_constant__ SpArgs s)
+{
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    SweepVoxel<P> cur;
+    bool have = false;
+    {
+        const int b = s.plane_starts[0], e = s.plane_starts[1];
+        if (b + tid < e)
+        {
+            cur.load_static(s, b + tid);
+            have = true;
+        }
+    }
+    for (int h = 0; h < s.n_planes; h++)
+    {
+        const int b = s.plane_starts[h], e = s.plane_starts[h + 1];
+        if (have)
+            cur.finish(s);
+        for (int i = b + tid + stride; i < e; i += stride) /* planes wider than the grid */
+        {
+            SweepVoxel<P> extra;
+            extra.load_static(s, i);
+            extra.finish(s);
+        }
+        have = false;
+        if (h + 1 < s.n_planes)
+        {
+            const int b2 = e, e2 = s.plane_starts[h + 2];
+            if (b2 + tid < e2)
+            {
+                cur.load_static(s, b2 + tid); /* prefetch: overlaps the barrier */
+                have = true;
+            }
+        }
+        if (e > b) /* uniform across the grid: every thread skips the same empty planes */
+            grid.sync();
+    }
 }
 
 /* ---- noise update, ReCentre and free energy (second loop of the reference, :675-722) --------------- */
@@ -580,15 +660,6 @@ __global__ void sp_neighbour_kernel(const int *coords, int N, int nx, int ny, in
     const int h = x + y + z;
     plane_of[v] = h;
     atomicAdd(&plane_hist[h], 1);
-}
-
-__global__ void sp_order_kernel(const int *plane_of, int N, int *cursor, int *order)
-{
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= N)
-        return;
-    const int pos = atomicAdd(&cursor[plane_of[v]], 1);
-    order[pos] = v;
 }
 
 #endif /* FAB_SPATIAL_HOST_KERNELS */

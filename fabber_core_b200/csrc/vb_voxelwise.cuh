@@ -52,7 +52,29 @@ struct VbArgs
     const double *init_mean, *init_cov, *init_noise;
     double *mean, *cov, *noise, *free_energy, *f_history;
     int *iterations, *status;
+    const double *fit_mean; /* model_fit_kernel: [P][N] Fabber-space means in, */
+    double *fit_out;        /*                   [T][N] model prediction out  */
 };
+
+/* fit[t][v] = g(ToModel(mean[:, v])): the modelfit / residuals output (inference.cc:190-191) */
+template <class Model> __global__ void __launch_bounds__(256) model_fit_kernel(const __grid_constant__ VbArgs a)
+{
+    constexpr int P = Model::P;
+    extern __shared__ double smem[];
+    Model::stage(a, smem);
+    __syncthreads();
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N)
+        return;
+    const typename Model::Ctx mc = Model::make_ctx(a, smem);
+    const size_t N = (size_t)a.N;
+    double p[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        p[i] = to_model(a.params[i].transform, a.fit_mean[i * N + v]);
+    for (int t = 0; t < a.T; t++)
+        a.fit_out[t * N + v] = Model::eval(mc, t, p);
+}
 
 template <int P> struct Stats
 {

@@ -349,7 +349,7 @@ void ExpFwdModel::Initialize(FabberRunData &rundata)
     m_dt = rundata.GetDouble("dt");
     m_num = rundata.GetIntDefault("num-exps", 1);
     if (m_num < 1 || 2 * m_num > FABBER_CUDA_MAX_PARAMS)
-        throw InvalidOptionValue("num-exps", stringify(m_num), "Must be between 1 and 4");
+        throw InvalidOptionValue("num-exps", stringify(m_num), "Must be between 1 and 3");
 }
 void ExpFwdModel::GetParameterDefaults(std::vector<Parameter> &params) const
 {

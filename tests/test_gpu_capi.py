@@ -1,0 +1,180 @@
+"""GPU: end-to-end through the reference's public C API (libfabbercore_b200.so, include/fabber_capi.h),
+driven exactly as py/fabber.py drives the reference: options -> extent -> data -> dorun -> get_data."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle
+from fabber_core_b200 import cuda_abi as abi
+from fabber_core_b200 import fabber as fab
+from fabber_core_b200 import synth
+from parity import tri
+
+pytestmark = pytest.mark.gpu
+
+
+def volume(series, shape):
+    """[T][N] (x fastest) -> [x, y, z, t]"""
+    nx, ny, nz = shape
+    return np.ascontiguousarray(series.T.reshape(nz, ny, nx, -1).transpose(2, 1, 0, 3))
+
+
+def flat(img):
+    """[x, y, z(, k)] -> [k][N] in voxel order"""
+    if img.ndim == 3:
+        img = img[..., None]
+    return np.stack([img[..., k].reshape(-1, order="F") for k in range(img.shape[3])])
+
+
+def design_file(tmp_path, design):
+    p = tmp_path / "design.mat"
+    p.write_text("\n".join(" ".join("%.17g" % x for x in row) for row in design) + "\n")
+    return str(p)
+
+
+def test_c1_regression_case_through_capi(golden, tmp_path):
+    """BASELINE configs[0]: --model=linear --basis=... --noise=white --method=vb on test_data_small,
+    compared with test/outdata_linear_vb exactly as test/test_commandline.cc:108-139 does (1e-3 absolute)
+    and at float32 precision."""
+    f = fab.Fabber()
+    opts = {"model": "linear", "basis": design_file(tmp_path, golden["design"]), "noise": "white", "method": "vb",
+            "save-mean": True, "save-zstat": True, "save-std": True, "save-mvn": True, "save-noise-mean": True,
+            "save-noise-std": True, "save-model-fit": True, "save-residuals": True}
+    run = f.run_with_data(opts, {"data": volume(golden["data"], (3, 3, 2))})
+    assert "Parameter_1" in " ".join(run.data.keys())
+    for i in range(1, 5):
+        m = flat(run.data["mean_Parameter_%d" % i])[0]
+        g = golden["linear_vb/mean_Parameter_%d" % i][0]
+        assert np.max(np.abs(m - g)) < 1e-3
+        assert np.max(np.abs(m - g) / np.abs(g)) < 5e-6
+        z = flat(run.data["zstat_Parameter_%d" % i])[0]
+        gz = golden["linear_vb/zstat_Parameter_%d" % i][0]
+        assert np.max(np.abs(z - gz) / np.abs(gz)) < 5e-6
+    mvn = flat(run.data["finalMVN"])
+    g = golden["linear_vb/finalMVN"]
+    assert mvn.shape == g.shape == (21, 18)
+    scale = np.maximum(np.abs(g), np.abs(g).max(axis=0, keepdims=True) * 1e-7)
+    assert np.max(np.abs(mvn - g) / np.maximum(scale, 1e-30)) < 2e-5
+    assert np.all(mvn[20] == 1.0)
+    nm = flat(run.data["noise_means"])[0]
+    assert np.max(np.abs(nm - g[19]) / g[19]) < 5e-6
+    # modelfit + residuals = data
+    fit, res = flat(run.data["modelfit"]), flat(run.data["residuals"])
+    assert np.max(np.abs(fit + res - golden["data"])) < 1e-2
+    assert "Vb::" in run.log and "Duration" in run.log
+
+
+def test_poly_golden_through_capi(golden):
+    f = fab.Fabber()
+    run = f.run_with_data({"model": "poly", "degree": 2, "noise": "white", "method": "vb", "save-mean": True,
+                           "save-std": True, "save-noise-mean": True, "save-noise-std": True},
+                          {"data": volume(golden["data"], (3, 3, 2))})
+    for i in range(3):
+        for kind in ("mean", "std"):
+            v = flat(run.data["%s_c%d" % (kind, i)])[0]
+            g = golden["poly/%s_c%d" % (kind, i)][0]
+            assert np.max(np.abs(v - g) / np.abs(g)) < 5e-6
+    assert np.max(np.abs(flat(run.data["noise_means"])[0] / golden["poly/noise_means"][0] - 1)) < 5e-6
+    assert np.max(np.abs(flat(run.data["noise_stdevs"])[0] / golden["poly/noise_stdevs"][0] - 1)) < 5e-6
+
+
+@pytest.mark.parametrize("method", ["vb", "spatialvb"])
+def test_constant_data_and_mask(method):
+    """test/test_inference.cc:108-160 (param. over vb, spatialvb): constant data -> mean_c0 == VAL;
+    voxels outside the mask come back as zeros (rundata_array.cc:68-98)."""
+    nx, ny, nz, nt, val = 5, 4, 3, 10, 7.32
+    data = np.full((nx, ny, nz, nt), val, dtype=np.float32)
+    mask = np.ones((nx, ny, nz), dtype=np.int32)
+    mask[0, :, :] = 0
+    mask[2, 1, 1] = 0
+    f = fab.Fabber()
+    seen = []
+    run = f.run_with_data({"model": "poly", "degree": 0, "noise": "white", "method": method, "save-mean": True},
+                          {"data": data}, mask=mask, progress_cb=lambda v, n: seen.append((v, n)))
+    mean = run.data["mean_c0"]
+    assert mean.shape == (nx, ny, nz)
+    assert np.all(mean[mask == 0] == 0)
+    assert np.allclose(mean[mask != 0], np.float32(val), rtol=1e-6)
+    assert seen and seen[-1][0] == seen[-1][1] == int(mask.sum())
+
+
+def test_capi_matches_inner_abi_on_biexp_lm():
+    """Same problem through the option strings and through the inner ABI: identical numbers."""
+    nx, ny, nz = 8, 6, 5
+    n = nx * ny * nz
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=41).numpy()
+    f = fab.Fabber()
+    opts = {"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "vb", "convergence": "lm",
+            "PSP_byname1": "r2", "PSP_byname1_mean": 6.0, "save-mvn": True, "save-free-energy": True,
+            "save-mean": True, "save-var": True}
+    run = f.run_with_data(opts, {"data": volume(y, (nx, ny, nz))})
+    ref = oracle.run(abi.ProblemSpec("exp", 96, num_exps=2, dt=0.02, convergence="lm", need_f=True,
+                                     param_overrides={"r2": {"mean": 6.0}}), y)
+    mvn = flat(run.data["finalMVN"]).astype(np.float64)
+    # float32 outputs of a float64 computation: compare at float32 precision
+    for i in range(4):
+        assert np.allclose(mvn[15 + i], ref["mean"][i], rtol=2e-5, atol=1e-6)
+        assert np.allclose(mvn[tri(i, i)], ref["cov"][tri(i, i)], rtol=2e-5)
+        # model-space outputs: log transform (transforms.h:135-156)
+        assert np.allclose(flat(run.data["mean_" + ["amp1", "r1", "amp2", "r2"][i]])[0], np.exp(ref["mean"][i]), rtol=2e-5)
+        assert np.allclose(flat(run.data["var_" + ["amp1", "r1", "amp2", "r2"][i]])[0], np.exp(ref["cov"][tri(i, i)]), rtol=2e-5)
+    assert np.allclose(flat(run.data["freeEnergy"])[0], ref["free_energy"], rtol=2e-5)
+
+
+def test_restart_from_mvn_and_output_only():
+    """test/test_vb.cc:305-498: continue-from-mvn restarts from a saved finalMVN; output-only re-emits it."""
+    nx, ny, nz = 6, 5, 4
+    y = synth.poly_volume(nx * ny * nz, 30, 2, seed=42).numpy()
+    data = volume(y, (nx, ny, nz))
+    f = fab.Fabber()
+    base = {"model": "poly", "degree": 2, "noise": "white", "method": "vb", "save-mvn": True, "save-mean": True}
+    first = f.run_with_data(dict(base, **{"max-iterations": 3}), {"data": data})
+    second = f.run_with_data(dict(base, **{"max-iterations": 7, "continue-from-mvn": "mvn_in"}),
+                             {"data": data, "mvn_in": first.data["finalMVN"]})
+    full = f.run_with_data(dict(base, **{"max-iterations": 10}), {"data": data})
+    # 3 + 7 iterations from the float32 checkpoint land where 10 iterations do (to checkpoint precision)
+    assert np.allclose(second.data["mean_c0"], full.data["mean_c0"], rtol=1e-4, atol=1e-4)
+    echo = f.run_with_data(dict(base, **{"output-only": True, "continue-from-mvn": "mvn_in"}),
+                           {"data": data, "mvn_in": first.data["finalMVN"]})
+    assert np.allclose(echo.data["finalMVN"][..., :6], first.data["finalMVN"][..., :6], rtol=1e-6)
+    assert np.array_equal(echo.data["mean_c0"], first.data["mean_c0"])
+
+
+def test_ar_noise_and_error_paths():
+    nx, ny, nz = 6, 5, 3
+    y = synth.linear_ar_volume(nx * ny * nz, 200, 0.3, seed=43).numpy()
+    import tempfile
+
+    with tempfile.TemporaryDirectory() as d:
+        basis = os.path.join(d, "ar.mat")
+        np.savetxt(basis, synth.ar_design(200), fmt="%.17g")
+        f = fab.Fabber()
+        run = f.run_with_data({"model": "linear", "basis": basis, "noise": "ar", "method": "vb", "save-mvn": True,
+                               "save-noise-mean": True}, {"data": volume(y, (nx, ny, nz))})
+        nm = flat(run.data["noise_means"])
+        assert nm.shape[0] == 3 and abs(np.median(nm[0]) - 0.3) < 0.1   # alpha1, alpha2, phi
+        assert flat(run.data["finalMVN"]).shape[0] == 7 * 8 // 2 + 7 + 1
+        # AR + masked time points must fail (test/test_inference.cc:564-633)
+        with pytest.raises(fab.FabberException):
+            f.run_with_data({"model": "linear", "basis": basis, "noise": "ar", "method": "vb", "mt1": 3},
+                            {"data": volume(y, (nx, ny, nz))})
+        # unknown method / missing noise option
+        with pytest.raises(fab.FabberException):
+            f.run_with_data({"model": "linear", "basis": basis, "noise": "white", "method": "nlls"},
+                            {"data": volume(y, (nx, ny, nz))})
+        with pytest.raises(fab.FabberException) as e:
+            f.run_with_data({"model": "linear", "basis": basis, "method": "vb"}, {"data": volume(y, (nx, ny, nz))})
+        assert "noise" in str(e.value)
+
+
+def test_bad_voxel_policy_through_capi():
+    nx, ny, nz = 4, 4, 2
+    y = synth.biexp_volume(nx * ny * nz, 96, 0.02, 0.02, seed=44).numpy()
+    y[:, 5] = np.inf
+    f = fab.Fabber()
+    opts = {"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "vb", "PSP_byname1": "r2",
+            "PSP_byname1_mean": 6.0, "save-mean": True}
+    with pytest.raises(fab.FabberException) as e:
+        f.run_with_data(opts, {"data": volume(y, (nx, ny, nz))})
+    assert e.value.errcode == fab.FABBER_ERR_FATAL and "Non-finite" in str(e.value)

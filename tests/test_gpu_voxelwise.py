@@ -90,7 +90,7 @@ def test_biexp_default_priors_first_iterations():
     compare(gpu, ref, 4, fma, label="biexp default priors, 2 iterations")
 
 
-@pytest.mark.parametrize("degree", [0, 1, 5, 7])
+@pytest.mark.parametrize("degree", [0, 1, 4, 5])
 def test_poly_other_sizes(degree):
     y = synth.poly_volume(500, 40, min(degree, 3), seed=11).numpy()
     gpu, ref, fma = both(dict(model="poly", degree=degree, need_f=True), y)
