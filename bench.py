@@ -27,26 +27,33 @@ sys.path.insert(0, ROOT)
 WORKLOADS = {
     # BASELINE.json configs[1]: poly degree 3, VB, white noise, synthetic 128^3 x 64, maxits 10
     "c2": dict(name="C2 poly(degree 3) VB white noise, synthetic 128^3 x 64, maxits 10", side=128, T=64,
-               model="poly", spec=dict(degree=3), P=4, e=8, e0=0),
+               model="poly", spec=dict(degree=3), P=4, e=8, e0=0,
+               capi={"model": "poly", "degree": 3, "noise": "white", "method": "vb", "max-iterations": 10}),
     # BASELINE.json configs[2]: biexp VB, LM convergence, synthetic 256^3 x 96
     # (prior mean 6 on r2 via PSP_byname: with the default symmetric priors the reference's own fit is
     #  chaotic - see DESIGN.md "C3")
     "c3": dict(name="C3 exp(num-exps 2, dt 0.02, PSP_byname r2 mean 6) VB white noise, convergence=lm, "
                     "synthetic 256^3 x 96", side=256, T=96, model="exp",
                spec=dict(num_exps=2, dt=0.02, convergence="lm", need_f=True,
-                         param_overrides={"r2": {"mean": 6.0}}), P=4, e=46, e0=80),
+                         param_overrides={"r2": {"mean": 6.0}}), P=4, e=46, e0=80,
+               capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "vb", "convergence": "lm",
+                     "max-iterations": 10, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0}),
     # BASELINE.json configs[3]: linear model (synthetic 200 x 4 design), AR(1) noise, synthetic 256^3 x 200
     # (the reference has no AR(2): Ar1cNoiseModel only, setup.cc:39)
     "c4": dict(name="C4 linear(200x4 design) VB AR(1) noise (num-echoes 1, cross-terms none), synthetic "
                     "256^3 x 200, maxits 10", side=256, T=200, model="linear", spec=dict(noise="ar"), P=4, e=8, e0=0,
-               flops=35900),
+               flops=35900,
+               capi={"model": "linear", "basis": "@design", "noise": "ar", "method": "vb", "max-iterations": 10}),
     # BASELINE.json configs[4]: spatialvb (MRF spatial prior 'M' on every parameter), biexp, smooth synthetic
     # 256^3 x 96. NB the reference's CovarianceCache is dead code; the MRF prior is
     # SpatialPrior in priors.cc.
     "c5": dict(name="C5 exp(num-exps 2, dt 0.02, PSP_byname r2 mean 6) spatialvb, param-spatial-priors=M+, "
                     "smooth synthetic 256^3 x 96, maxits 10", side=256, T=96, model="exp", spatial=True,
                spec=dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), param_overrides={"r2": {"mean": 6.0}}),
-               P=4, e=46, e0=80),
+               P=4, e=46, e0=80,
+               capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "spatialvb",
+                     "param-spatial-priors": "M+", "max-iterations": 10, "PSP_byname1": "r2",
+                     "PSP_byname1_mean": 6.0}),
 }
 
 
@@ -138,6 +145,61 @@ class ClockSampler(object):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def capi_e2e(w, host_y, extent, steps):
+    """End to end through the reference-facing C API (include/fabber_capi.h) with HOST buffers, exactly the
+    calls py/fabber.py makes: fabber_set_data (host float32 volume in) -> fabber_dorun -> fabber_get_data of
+    every requested output (host float32 volumes out). Wall clock around the synchronous calls; the copies
+    host -> pinned -> device and device -> host -> caller are all inside. Returns (seconds per step, h2d
+    bytes, d2h bytes)."""
+    import ctypes as C
+    import tempfile
+
+    from fabber_core_b200 import fabber as fab
+    from fabber_core_b200 import synth
+
+    f = fab.Fabber()
+    opts = dict(w["capi"])
+    tmp = None
+    if opts.get("basis") == "@design":
+        tmp = tempfile.NamedTemporaryFile("w", suffix=".mat", delete=False)
+        np.savetxt(tmp, synth.ar_design(w["T"]), fmt="%.17g")
+        tmp.close()
+        opts["basis"] = tmp.name
+    opts.update({"save-mean": True, "save-std": True, "save-noise-mean": True})
+    f._set_options(opts)
+    f._trycall(f.clib.fabber_get_model_params, f.handle, len(f.outbuf), f.outbuf, f.errbuf)
+    params = f.outbuf.value.decode().splitlines()
+    outputs = ["mean_" + p for p in params] + ["std_" + p for p in params] + ["noise_means"]
+    n = extent[0] * extent[1] * extent[2]
+    mask = np.ones(n, dtype=np.int32)
+    f._trycall(f.clib.fabber_set_extent, f.handle, extent[0], extent[1], extent[2], mask, f.errbuf)
+    flat = host_y.reshape(-1)  # [t][z][y][x] == [T][N] for a full mask
+    bufs = {}
+    noop = f.progress_cb_type(0)
+
+    def one():
+        f._trycall(f.clib.fabber_set_data, f.handle, b"data", w["T"], flat, f.errbuf)
+        f._trycall(f.clib.fabber_dorun, f.handle, len(f.outbuf), f.outbuf, f.errbuf, noop)
+        nbytes = 0
+        for key in outputs:
+            size = f._trycall(f.clib.fabber_get_data_size, f.handle, key.encode(), f.errbuf)
+            if key not in bufs:
+                bufs[key] = np.empty(n * size, dtype=np.float32)
+            f._trycall(f.clib.fabber_get_data, f.handle, key.encode(), bufs[key], f.errbuf)
+            nbytes += bufs[key].nbytes
+        return nbytes
+
+    one()  # warm-up
+    t0 = time.perf_counter()
+    d2h = 0
+    for _ in range(steps):
+        d2h = one()
+    dt = (time.perf_counter() - t0) / steps
+    if tmp is not None:
+        os.unlink(tmp.name)
+    return dt, flat.nbytes, d2h
 
 
 def oracle_run(w, y):
@@ -327,8 +389,23 @@ def main():
     e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_value = its_all * e2e_steps / (float(e2e_ms.item()) * 1e-3)
+    e2e_inner = its_all * e2e_steps / (float(e2e_ms.item()) * 1e-3)
     torch.cuda.profiler.stop()
+
+    # ---- the headline end-to-end number: the reference's public C API with host buffers --------------
+    run.close()
+    del host_out
+    host_np = host_y.numpy()
+    del y
+    torch.cuda.empty_cache()
+    capi_steps = max(1, min(args.steps, 3))
+    side = round(n_vox ** (1.0 / 3))
+    extent = (side, side, side) if side ** 3 == n_vox else (n_vox, 1, 1)
+    capi_s, capi_h2d, capi_d2h = capi_e2e(w, host_np, extent, capi_steps)
+    t_capi = torch.tensor([capi_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t_capi, op=dist.ReduceOp.MAX)
+    e2e_value = its_all / float(t_capi.item())
 
     if rank == 0:
         W = algorithmic_flops(w)
@@ -348,8 +425,13 @@ def main():
             "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": h2d,
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps},
+            "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": capi_h2d,
+                    "d2h_bytes_per_step": capi_d2h, "steps": capi_steps,
+                    "path": "fabber_capi (libfabbercore_b200.so): fabber_set_data -> fabber_dorun -> fabber_get_data "
+                            "of mean_*, std_*, noise_means; host float32 buffers in and out; wall clock",
+                    "inner_abi": {"value": e2e_inner, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                  "steps": e2e_steps,
+                                  "path": "fabber_cuda_vb_* with pinned host buffers, raw result arrays, CUDA events"}},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
@@ -370,7 +452,6 @@ def main():
                                     "sample": "%d voxels of the same synthetic workload, %.1f s, single thread"
                                     % (n, dt)}
         print(json.dumps(line))
-    run.close()
     if world > 1:
         dist.destroy_process_group()
     return 0

@@ -9,6 +9,7 @@
 #include <cub/cub.cuh>
 
 #include <atomic>
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -162,6 +163,129 @@ __global__ void renumber_neighbours_kernel(const int *nn, const int *order, cons
         const int n = nn[(size_t)j * N + v];
         nnp[(size_t)j * N + i] = n >= 0 ? rank[n] : -1;
     }
+}
+
+/* SaveResults on the device: model-space mean / std / zstat / var per parameter, noise means and
+ * standard deviations, the packed finalMVN rows, F and its history - all float32 (memory-bound map). */
+struct SaveArgs
+{
+    int N, P, n_noise, ar, n_phis, f_len;
+    char transform[FABBER_CUDA_MAX_PARAMS];
+    const double *mean, *cov, *noise, *free_energy, *f_history;
+    const int *iterations;
+    fabber_cuda_vb_outputs out;
+};
+__device__ inline int save_tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+__device__ inline double save_to_model_var(char code, double v)
+{
+    switch (code)
+    {
+    case 'L':
+        return exp(v);
+    case 'I':
+    case 'F':
+        return v;
+    default: /* transforms.cc:17-20 */
+    {
+        const double d = fab::to_model(code, sqrt(v)) - fab::to_model(code, 0.0);
+        return d * d;
+    }
+    }
+}
+__global__ void __launch_bounds__(256) save_results_kernel(const __grid_constant__ SaveArgs a)
+{
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.N)
+        return;
+    const size_t N = (size_t)a.N;
+    const int P = a.P, Nn = a.n_noise, NA = P + Nn;
+    for (int i = 0; i < P; i++)
+    {
+        const double mean = fab::to_model(a.transform[i], a.mean[i * N + v]);
+        const double var = save_to_model_var(a.transform[i], a.cov[save_tri(i, i) * N + v]);
+        const double sd = sqrt(var);
+        if (a.out.mean)
+            a.out.mean[i * N + v] = (float)mean;
+        if (a.out.std)
+            a.out.std[i * N + v] = (float)sd;
+        if (a.out.zstat)
+            a.out.zstat[i * N + v] = (float)(mean / sd);
+        if (a.out.var)
+            a.out.var[i * N + v] = (float)var;
+    }
+    /* noise block of the result MVN (WhiteParams / Ar1cParams::OutputAsMVN) */
+    double nmean[4], ncov[4][4];
+    for (int i = 0; i < 4; i++)
+    {
+        nmean[i] = 0.0;
+        for (int j = 0; j < 4; j++)
+            ncov[i][j] = 0.0;
+    }
+    if (a.ar)
+    {
+        const double b = a.noise[0 * N + v], c = a.noise[1 * N + v];
+        const double p11 = a.noise[4 * N + v], p21 = a.noise[5 * N + v], p22 = a.noise[6 * N + v];
+        const double det = p11 * p22 - p21 * p21;
+        nmean[0] = a.noise[2 * N + v];
+        nmean[1] = a.noise[3 * N + v];
+        nmean[2] = b * c;
+        ncov[0][0] = p22 / det;
+        ncov[1][1] = p11 / det;
+        ncov[0][1] = ncov[1][0] = -p21 / det;
+        ncov[2][2] = b * b * c;
+    }
+    else
+        for (int i = 0; i < a.n_phis; i++)
+        {
+            const double b = a.noise[(2 * i) * N + v], c = a.noise[(2 * i + 1) * N + v];
+            nmean[i] = b * c;         /* GammaDist::CalcMean, dist_gamma.cc:21 */
+            ncov[i][i] = b * b * c;   /* CalcVariance :25 */
+        }
+    for (int i = 0; i < Nn; i++)
+    {
+        if (a.out.noise_mean)
+            a.out.noise_mean[i * N + v] = (float)nmean[i];
+        if (a.out.noise_std)
+            a.out.noise_std[i * N + v] = (float)sqrt(ncov[i][i]);
+    }
+    if (a.out.final_mvn)
+    {
+        int idx = 0;
+        for (int r = 0; r < NA; r++)
+            for (int c = 0; c <= r; c++, idx++)
+            {
+                double val = 0.0;
+                if (r < P)
+                    val = a.cov[save_tri(r, c) * N + v];
+                else if (c >= P)
+                    val = ncov[r - P][c - P];
+                a.out.final_mvn[idx * N + v] = (float)val;
+            }
+        for (int i = 0; i < P; i++)
+            a.out.final_mvn[(idx + i) * N + v] = (float)a.mean[i * N + v];
+        for (int i = 0; i < Nn; i++)
+            a.out.final_mvn[(idx + P + i) * N + v] = (float)nmean[i];
+        a.out.final_mvn[(idx + NA) * N + v] = 1.0f;
+    }
+    if (a.out.free_energy && a.free_energy)
+        a.out.free_energy[v] = (float)a.free_energy[v];
+    if (a.out.f_history && a.f_history)
+    {
+        const int its = a.iterations ? a.iterations[v] : a.f_len;
+        for (int r = 0; r < a.out.f_history_rows; r++)
+            a.out.f_history[r * N + v]
+                = (float)((r < its && r < a.f_len) ? a.f_history[r * N + v] : (a.free_energy ? a.free_energy[v] : 0.0));
+    }
+}
+__global__ void max_int_kernel(const int *values, int n, int *result)
+{
+    int m = INT_MIN;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        m = max(m, values[i]);
+    for (int o = 16; o > 0; o >>= 1)
+        m = max(m, __shfl_down_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0)
+        atomicMax(result, m);
 }
 
 /* dependent-free DFMA loop: 8 independent accumulators per thread */
@@ -783,10 +907,92 @@ int fabber_cuda_check_status(const int *status, int n_voxels, int *first_bad_vox
     return h[0];
 }
 
-int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean, double *fit, void *stream)
+int fabber_cuda_max_int(const int *values, int n, int *result, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    if (!prob || !mean || !fit)
+    if (!result)
+        return fail(FABBER_CUDA_ERR_INVALID, "null result");
+    *result = 0;
+    if (n <= 0)
+        return FABBER_CUDA_OK;
+    int *d = nullptr;
+    cudaError_t e = cudaMallocAsync((void **)&d, sizeof(int), st);
+    if (e != cudaSuccess)
+        return cuda_fail(e, "cudaMallocAsync(max)");
+    int init = INT_MIN;
+    cudaMemcpyAsync(d, &init, sizeof(int), cudaMemcpyHostToDevice, st);
+    max_int_kernel<<<592, 256, 0, st>>>(values, n, d);
+    count_launch();
+    cudaMemcpyAsync(result, d, sizeof(int), cudaMemcpyDeviceToHost, st);
+    e = cudaStreamSynchronize(st);
+    cudaFreeAsync(d, st);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "max_int");
+}
+
+static int model_fit_impl(const fabber_cuda_vb_problem *prob, const double *mean, double *fit, const float *data,
+    float *fit_f32, float *resid_f32, cudaStream_t st);
+
+int fabber_cuda_vb_save_results(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
+    const fabber_cuda_vb_outputs *out, void *stream)
+{
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!prob || !buf || !out)
+        return fail(FABBER_CUDA_ERR_INVALID, "null argument");
+    const int P = prob->model.n_params, N = prob->n_voxels;
+    if (P < 1 || P > FABBER_CUDA_MAX_PARAMS || N < 0)
+        return fail(FABBER_CUDA_ERR_INVALID, "bad sizes");
+    if (N == 0)
+        return FABBER_CUDA_OK;
+    if (!buf->mean || !buf->cov || !buf->noise)
+        return fail(FABBER_CUDA_ERR_INVALID, "missing mean / cov / noise result arrays");
+    SaveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.N = N;
+    a.P = P;
+    a.ar = prob->noise_type == FABBER_NOISE_AR1;
+    a.n_phis = a.ar ? 1 : prob->n_phis;
+    a.n_noise = a.ar ? 3 : prob->n_phis;
+    if (a.n_noise < 1 || a.n_noise > 4)
+        return fail(FABBER_CUDA_ERR_INVALID, "n_phis out of range");
+    a.f_len = buf->f_history ? prob->f_history_len : 0;
+    for (int i = 0; i < P; i++)
+        a.transform[i] = prob->params[i].transform;
+    a.mean = buf->mean;
+    a.cov = buf->cov;
+    a.noise = buf->noise;
+    a.free_energy = buf->free_energy;
+    a.f_history = buf->f_history;
+    a.iterations = buf->iterations;
+    a.out = *out;
+    if (out->mean || out->std || out->zstat || out->var || out->noise_mean || out->noise_std || out->final_mvn
+        || out->free_energy || out->f_history)
+    {
+        save_results_kernel<<<(unsigned)((N + 255) / 256), 256, 0, st>>>(a);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess)
+            return cuda_fail(e, "save_results launch");
+    }
+    if (out->model_fit || out->residuals)
+    {
+        if (out->residuals && !out->data)
+            return fail(FABBER_CUDA_ERR_INVALID, "residuals need the input series");
+        return model_fit_impl(prob, buf->mean, nullptr, out->data, out->model_fit, out->residuals, st);
+    }
+    return FABBER_CUDA_OK;
+}
+
+int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean, double *fit, void *stream)
+{
+    if (!fit)
+        return fail(FABBER_CUDA_ERR_INVALID, "null argument");
+    return model_fit_impl(prob, mean, fit, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+static int model_fit_impl(const fabber_cuda_vb_problem *prob, const double *mean, double *fit, const float *data,
+    float *fit_f32, float *resid_f32, cudaStream_t st)
+{
+    if (!prob || !mean)
         return fail(FABBER_CUDA_ERR_INVALID, "null argument");
     const int P = prob->model.n_params, T = prob->n_times, N = prob->n_voxels;
     if (P < 1 || P > FABBER_CUDA_MAX_PARAMS || T < 1 || N < 0)
@@ -803,6 +1009,9 @@ int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean
     a.exp_dt = prob->model.exp_dt;
     a.fit_mean = mean;
     a.fit_out = fit;
+    a.fit_out_f32 = fit_f32;
+    a.resid_out_f32 = resid_f32;
+    a.data = data;
     Staged staged;
     if (prob->model.id == FABBER_MODEL_LINEAR)
     {

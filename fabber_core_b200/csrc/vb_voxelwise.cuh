@@ -53,7 +53,9 @@ struct VbArgs
     double *mean, *cov, *noise, *free_energy, *f_history;
     int *iterations, *status;
     const double *fit_mean; /* model_fit_kernel: [P][N] Fabber-space means in, */
-    double *fit_out;        /*                   [T][N] model prediction out  */
+    double *fit_out;        /*                   [T][N] model prediction out (double), or */
+    float *fit_out_f32;     /*                   [T][N] model prediction, float32, and/or */
+    float *resid_out_f32;   /*                   [T][N] data - prediction, float32 */
 };
 
 /* fit[t][v] = g(ToModel(mean[:, v])): the modelfit / residuals output (inference.cc:190-191) */
@@ -73,7 +75,15 @@ template <class Model> __global__ void __launch_bounds__(256) model_fit_kernel(c
     for (int i = 0; i < P; i++)
         p[i] = to_model(a.params[i].transform, a.fit_mean[i * N + v]);
     for (int t = 0; t < a.T; t++)
-        a.fit_out[t * N + v] = Model::eval(mc, t, p);
+    {
+        const double g = Model::eval(mc, t, p);
+        if (a.fit_out)
+            a.fit_out[t * N + v] = g;
+        if (a.fit_out_f32)
+            a.fit_out_f32[t * N + v] = (float)g;
+        if (a.resid_out_f32)
+            a.resid_out_f32[t * N + v] = (float)((double)a.data[t * N + v] - g);
+    }
 }
 
 template <int P> struct Stats

@@ -15,6 +15,7 @@
  * No NEWMAT: matrices are plain row-major arrays. No CPU inference path exists in here.
  */
 #pragma once
+#include <functional>
 #include <map>
 #include <memory>
 #include <set>
@@ -94,6 +95,10 @@ struct OptionSpec
 };
 const char *option_type_name(OptionType t);
 
+/* Host-side copies and output maps are memory-bound loops over 10^7..10^9 elements: split them over the
+ * host cores (the reference does them single-threaded). fn(begin, end) must be independent per range. */
+void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_chunk = 1 << 16);
+
 template <class T> std::string stringify(const T &v)
 {
     std::ostringstream s;
@@ -101,21 +106,31 @@ template <class T> std::string stringify(const T &v)
     return s.str();
 }
 
-/* ---- voxel data: rows x nvoxels, row t = volume t (rundata.h:628) -------------------------------- */
+/* ---- memory cache ---------------------------------------------------------------------------------
+ * cudaMallocHost / cudaMalloc / cudaFree cost 0.1-1 s per GB and synchronise the device; a client that
+ * calls set_data -> dorun -> get_data repeatedly would spend most of its time there (measured). Freed
+ * blocks are parked by size and handed out again. */
+void *cached_pinned_alloc(size_t bytes);
+void cached_pinned_free(void *p, size_t bytes);
+void *cached_device_alloc(size_t bytes);
+void cached_device_free(void *p, size_t bytes);
+
+/* ---- voxel data: rows x nvoxels, row t = volume t (rundata.h:628) --------------------------------
+ * float32 throughout: every value enters (fabber_set_data) and leaves (fabber_get_data) the reference's
+ * C API as float32, so nothing is lost; the buffers are pinned so device copies run at PCIe speed. */
 struct VoxelData
 {
     int rows;
     size_t cols;
-    bool is_float;         /* input series keep the caller's float32 (lossless); outputs are double */
-    float *f;              /* pinned host memory when is_float */
-    std::vector<double> d; /* otherwise */
+    float *f;   /* pinned host memory [rows][cols] */
+    float *dev; /* optional device-resident copy (main data: uploaded while it is being set) */
     VoxelData();
     ~VoxelData();
     VoxelData(const VoxelData &) = delete;
     VoxelData &operator=(const VoxelData &) = delete;
-    void alloc_float(int r, size_t c);
-    void alloc_double(int r, size_t c);
-    double at(int r, size_t c) const { return is_float ? (double)f[(size_t)r * cols + c] : d[(size_t)r * cols + c]; }
+    void alloc(int r, size_t c);
+    size_t bytes() const { return (size_t)rows * cols * sizeof(float); }
+    double at(int r, size_t c) const { return (double)f[(size_t)r * cols + c]; }
 };
 
 /* ---- run data (rundata.h:215-672 + rundata_array.cc) -------------------------------------------- */
@@ -154,6 +169,7 @@ public:
     const VoxelData &GetVoxelData(const std::string &key);
     const VoxelData &GetMainVoxelData();
     VoxelData &NewVoxelData(const std::string &key, int rows); /* SaveVoxelData target (rundata.cc:932-938) */
+    VoxelData &MutableVoxelData(const std::string &key);
     void ClearVoxelData(const std::string &key);
 
     /* Run: model + technique from their registries, Initialize -> DoCalculations -> SaveResults
@@ -316,12 +332,22 @@ private:
     bool m_ar = false, m_saveF = false, m_saveFsHistory = false, m_printF = false, m_needF = false;
     bool m_halt_bad_voxel = true;
     int m_nphis = 1;
-    /* results, structure of arrays over voxels (the layout of include/fabber_cuda.h) */
+    /* results stay on the device, structure of arrays over voxels (the layout of include/fabber_cuda.h);
+     * SaveResults turns them into float32 output maps there and downloads only what was asked for */
     size_t m_nvoxels = 0;
-    int m_ntimes = 0;
-    std::vector<double> m_mean, m_cov, m_noise, m_F, m_Fhist;
-    std::vector<int> m_status, m_iterations;
-    int m_fhist_len = 0;
+    int m_ntimes = 0, m_nn = 0, m_fhist_len = 0;
+    fabber_cuda_vb_problem m_prob;
+    std::vector<unsigned char> m_pattern, m_masked;
+    struct DevArray
+    {
+        void *p = nullptr;
+        size_t bytes = 0;
+    };
+    DevArray m_d_mean, m_d_cov, m_d_noise, m_d_F, m_d_hist, m_d_its, m_d_status;
+    void ReleaseDevice();
+
+public:
+    ~Vb() { ReleaseDevice(); }
 };
 
 } // namespace fabber_b200

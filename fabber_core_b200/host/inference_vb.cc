@@ -14,12 +14,25 @@
 #include <cmath>
 #include <cstring>
 
+#include <chrono>
+
 #include "fabber_host.h"
 
 namespace fabber_b200
 {
 namespace
 {
+struct StopWatch
+{
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    double lap_ms()
+    {
+        std::chrono::steady_clock::time_point t1 = std::chrono::steady_clock::now();
+        double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
+        t0 = t1;
+        return ms;
+    }
+};
 /* RAII for device allocations */
 struct DeviceBuf
 {
@@ -127,11 +140,26 @@ bool Vb::IsSpatial(FabberRunData &rundata, const std::vector<Parameter> &params)
     return false;
 }
 
+void Vb::ReleaseDevice()
+{
+    DevArray *all[] = { &m_d_mean, &m_d_cov, &m_d_noise, &m_d_F, &m_d_hist, &m_d_its, &m_d_status };
+    bool any = false;
+    for (DevArray *d : all)
+        any = any || d->p;
+    if (any)
+        fabber_cuda_stream_sync(nullptr);
+    for (DevArray *d : all)
+    {
+        cached_device_free(d->p, d->bytes);
+        d->p = nullptr;
+        d->bytes = 0;
+    }
+}
+
 void Vb::DoCalculations(FabberRunData &rundata)
 {
-    const VoxelData &data = rundata.GetMainVoxelData();
-    if (!data.is_float)
-        throw FabberInternalError("main voxel data must be the float32 series set with fabber_set_data");
+    StopWatch sw;
+    VoxelData &data = rundata.MutableVoxelData("data");
     const size_t N = data.cols;
     const int T = data.rows;
     m_nvoxels = N;
@@ -140,7 +168,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
     m_model->GetParameters(rundata, params);
     const int P = m_num_params, NT = P * (P + 1) / 2;
 
-    fabber_cuda_vb_problem prob;
+    fabber_cuda_vb_problem &prob = m_prob;
     memset(&prob, 0, sizeof(prob));
     prob.n_voxels = (int)N;
     prob.n_times = T;
@@ -160,13 +188,14 @@ void Vb::DoCalculations(FabberRunData &rundata)
     }
 
     /* ---- noise model options ---------------------------------------------------------------------- */
-    std::vector<unsigned char> pattern(T, 0), masked(T, 0);
+    m_pattern.assign(T, 0);
+    m_masked.assign(T, 0);
     const std::vector<int> mt = rundata.GetIntList("mt", 1); /* inference.cc:96-103 */
     for (size_t i = 0; i < mt.size(); i++)
     {
         if (mt[i] > T)
             throw InvalidOptionValue("mt", stringify(mt[i]), "Masked time point beyond the end of the data");
-        masked[mt[i] - 1] = 1;
+        m_masked[mt[i] - 1] = 1;
     }
     if (m_ar)
     {
@@ -208,7 +237,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
         if (nphis > FABBER_CUDA_MAX_PHIS)
             throw InvalidOptionValue("noise-pattern", pat, "more noise precisions than the device kernels carry");
         for (int t = 0; t < T; t++)
-            pattern[t] = (unsigned char)(digits[t % digits.size()] - 1);
+            m_pattern[t] = (unsigned char)(digits[t % digits.size()] - 1);
         prob.n_phis = nphis;
         m_nphis = nphis;
         m_noise_params = nphis;
@@ -232,8 +261,8 @@ void Vb::DoCalculations(FabberRunData &rundata)
         }
         prob.locked_noise_stdev = rundata.GetDoubleDefault("locked-noise-stdev", -1);
     }
-    prob.phi_pattern = pattern.data();
-    prob.time_masked = mt.empty() ? nullptr : masked.data();
+    prob.phi_pattern = m_pattern.data();
+    prob.time_masked = mt.empty() ? nullptr : m_masked.data();
 
     /* ---- convergence (setup.cc:49-57, convergence.cc Initialize functions) --------------------------- */
     const std::string conv = rundata.GetStringDefault("convergence", "maxits");
@@ -281,17 +310,25 @@ void Vb::DoCalculations(FabberRunData &rundata)
     prob.nx = rundata.Extent()[0];
     prob.ny = rundata.Extent()[1];
     prob.nz = rundata.Extent()[2];
-
-    const int NN = m_ar ? FABBER_CUDA_AR_NOISE_FIELDS : 2 * m_nphis;
-    m_mean.assign((size_t)P * N, 0.0);
-    m_cov.assign((size_t)NT * N, 0.0);
-    m_noise.assign((size_t)NN * N, 0.0);
-    m_F.assign(N, 9999.0);
-    m_status.assign(N, 0);
-    m_iterations.assign(N, 0);
-    m_Fhist.assign((size_t)m_fhist_len * N, 0.0);
+    m_nn = m_ar ? FABBER_CUDA_AR_NOISE_FIELDS : 2 * m_nphis;
+    const int NN = m_nn;
     if (N == 0)
         return; /* zero voxels is not an error (test/test_inference.cc:57-73) */
+
+    /* ---- device result arrays (cached blocks: no cudaMalloc on the steady-state path) ---------------- */
+    ReleaseDevice();
+    auto dev = [](DevArray &d, size_t bytes) {
+        d.bytes = bytes;
+        d.p = cached_device_alloc(bytes);
+    };
+    dev(m_d_mean, (size_t)P * N * sizeof(double));
+    dev(m_d_cov, (size_t)NT * N * sizeof(double));
+    dev(m_d_noise, (size_t)NN * N * sizeof(double));
+    dev(m_d_F, N * sizeof(double));
+    dev(m_d_its, N * sizeof(int));
+    dev(m_d_status, N * sizeof(int));
+    if (m_fhist_len > 0)
+        dev(m_d_hist, (size_t)m_fhist_len * N * sizeof(double));
 
     /* ---- restart / output-only (inference_vb.cc:181-216, 385-389) ------------------------------------ */
     std::vector<double> init_mean, init_cov, init_noise;
@@ -306,38 +343,40 @@ void Vb::DoCalculations(FabberRunData &rundata)
         init_mean.resize((size_t)P * N);
         init_cov.resize((size_t)NT * N);
         init_noise.assign((size_t)NN * N, 0.0);
-        for (size_t v = 0; v < N; v++)
-        {
-            for (int i = 0; i < P; i++)
-                init_mean[(size_t)i * N + v] = mvn.at(n_cov_all + i, v);
-            for (int r = 0; r < P; r++)
-                for (int c = 0; c <= r; c++)
-                    init_cov[(size_t)tri(r, c) * N + v] = mvn.at(tri(r, c), v);
-            if (m_ar)
+        parallel_for(N, [&](size_t vb, size_t ve) {
+            for (size_t v = vb; v < ve; v++)
             {
-                /* MVN order: alpha (2), phi (1). InputFromMVN: Gamma from mean/variance (dist_gamma.cc:29) */
-                const int ia = P, ip = P + 2;
-                const double a1 = mvn.at(n_cov_all + ia, v), a2 = mvn.at(n_cov_all + ia + 1, v);
-                const double c11 = mvn.at(tri(ia, ia), v), c21 = mvn.at(tri(ia + 1, ia), v),
-                             c22 = mvn.at(tri(ia + 1, ia + 1), v);
-                const double det = c11 * c22 - c21 * c21;
-                const double mean = mvn.at(n_cov_all + ip, v), var = mvn.at(tri(ip, ip), v);
-                init_noise[0 * N + v] = var / mean;
-                init_noise[1 * N + v] = mean * mean / var;
-                init_noise[2 * N + v] = a1;
-                init_noise[3 * N + v] = a2;
-                init_noise[4 * N + v] = c22 / det;
-                init_noise[5 * N + v] = -c21 / det;
-                init_noise[6 * N + v] = c11 / det;
-            }
-            else
-                for (int i = 0; i < m_nphis; i++)
+                for (int i = 0; i < P; i++)
+                    init_mean[(size_t)i * N + v] = mvn.at(n_cov_all + i, v);
+                for (int r = 0; r < P; r++)
+                    for (int c = 0; c <= r; c++)
+                        init_cov[(size_t)tri(r, c) * N + v] = mvn.at(tri(r, c), v);
+                if (m_ar)
                 {
-                    const double mean = mvn.at(n_cov_all + P + i, v), var = mvn.at(tri(P + i, P + i), v);
-                    init_noise[(size_t)(2 * i) * N + v] = var / mean;         /* b = variance / mean */
-                    init_noise[(size_t)(2 * i + 1) * N + v] = mean * mean / var; /* c = mean^2 / variance */
+                    /* MVN order: alpha (2), phi (1). InputFromMVN: Gamma from mean/variance (dist_gamma.cc:29) */
+                    const int ia = P, ip = P + 2;
+                    const double a1 = mvn.at(n_cov_all + ia, v), a2 = mvn.at(n_cov_all + ia + 1, v);
+                    const double c11 = mvn.at(tri(ia, ia), v), c21 = mvn.at(tri(ia + 1, ia), v),
+                                 c22 = mvn.at(tri(ia + 1, ia + 1), v);
+                    const double det = c11 * c22 - c21 * c21;
+                    const double mean = mvn.at(n_cov_all + ip, v), var = mvn.at(tri(ip, ip), v);
+                    init_noise[0 * N + v] = var / mean;
+                    init_noise[1 * N + v] = mean * mean / var;
+                    init_noise[2 * N + v] = a1;
+                    init_noise[3 * N + v] = a2;
+                    init_noise[4 * N + v] = c22 / det;
+                    init_noise[5 * N + v] = -c21 / det;
+                    init_noise[6 * N + v] = c11 / det;
                 }
-        }
+                else
+                    for (int i = 0; i < m_nphis; i++)
+                    {
+                        const double mean = mvn.at(n_cov_all + P + i, v), var = mvn.at(tri(P + i, P + i), v);
+                        init_noise[(size_t)(2 * i) * N + v] = var / mean;            /* b = variance / mean */
+                        init_noise[(size_t)(2 * i + 1) * N + v] = mean * mean / var; /* c = mean^2 / variance */
+                    }
+            }
+        });
     }
     catch (DataNotFound &)
     {
@@ -346,28 +385,48 @@ void Vb::DoCalculations(FabberRunData &rundata)
     {
         if (!continue_from_mvn)
             throw FabberRunDataError("output-only requires continue-from-mvn");
-        m_mean = init_mean;
-        m_cov = init_cov;
-        m_noise = init_noise;
+        check(fabber_cuda_memcpy_h2d(m_d_mean.p, init_mean.data(), m_d_mean.bytes, nullptr), "output-only");
+        check(fabber_cuda_memcpy_h2d(m_d_cov.p, init_cov.data(), m_d_cov.bytes, nullptr), "output-only");
+        check(fabber_cuda_memcpy_h2d(m_d_noise.p, init_noise.data(), m_d_noise.bytes, nullptr), "output-only");
+        check(fabber_cuda_memset(m_d_F.p, 0, m_d_F.bytes, nullptr), "output-only");
+        check(fabber_cuda_memset(m_d_its.p, 0, m_d_its.bytes, nullptr), "output-only");
+        check(fabber_cuda_stream_sync(nullptr), "output-only");
+        m_needF = false;
         rundata.Log() << "Vb::DoCalculations output-only set - not performing any calculations" << std::endl;
         return;
     }
 
-    /* ---- device buffers: inputs up, one launch, results down ------------------------------------------ */
+    /* ---- inputs: the series is normally already on the device (uploaded while it was being set) ------- */
     rundata.Log() << "Vb::" << (spatial ? "Spatial" : "Voxelwise") << " calculations on the GPU: " << N << " voxels x "
                   << T << " time points, " << P << " parameters" << std::endl;
     rundata.Progress(0, (int)N);
     fabber_cuda_vb_buffers buf;
     memset(&buf, 0, sizeof(buf));
-    DeviceBuf d_data((size_t)T * N * sizeof(float));
-    check(fabber_cuda_memcpy_h2d(d_data.p, data.f, (size_t)T * N * sizeof(float), nullptr), "copying data to the GPU");
-    buf.data = (const float *)d_data.p;
-    std::vector<std::unique_ptr<DeviceBuf>> keep;
-    auto upload = [&](const std::vector<double> &h) -> const double * {
-        keep.emplace_back(new DeviceBuf(h.size() * sizeof(double)));
-        check(fabber_cuda_memcpy_h2d(keep.back()->p, h.data(), h.size() * sizeof(double), nullptr), "copying to the GPU");
-        return (const double *)keep.back()->p;
+    if (!data.dev)
+    {
+        data.dev = (float *)cached_device_alloc(data.bytes());
+        check(fabber_cuda_memcpy_h2d(data.dev, data.f, data.bytes(), nullptr), "copying data to the GPU");
+    }
+    buf.data = data.dev;
+    std::vector<DevArray> scratch;
+    auto upload = [&](const void *h, size_t bytes) -> void * {
+        DevArray d;
+        d.bytes = bytes;
+        d.p = cached_device_alloc(bytes);
+        scratch.push_back(d);
+        check(fabber_cuda_memcpy_h2d(d.p, h, bytes, nullptr), "copying to the GPU");
+        return d.p;
     };
+    struct ScratchGuard
+    {
+        std::vector<DevArray> &s;
+        ~ScratchGuard()
+        {
+            fabber_cuda_stream_sync(nullptr);
+            for (size_t i = 0; i < s.size(); i++)
+                cached_device_free(s[i].p, s[i].bytes);
+        }
+    } guard = { scratch };
     std::vector<std::vector<double>> images(P);
     for (int i = 0; i < P; i++)
         if (params[i].prior_type == 'I')
@@ -377,215 +436,165 @@ void Vb::DoCalculations(FabberRunData &rundata)
             images[i].resize(N);
             for (size_t v = 0; v < N; v++)
                 images[i][v] = img.at(0, v);
-            buf.image_prior[i] = upload(images[i]);
+            buf.image_prior[i] = (const double *)upload(images[i].data(), N * sizeof(double));
         }
     if (continue_from_mvn)
     {
-        buf.init_mean = upload(init_mean);
-        buf.init_cov = upload(init_cov);
-        buf.init_noise = upload(init_noise);
+        buf.init_mean = (const double *)upload(init_mean.data(), init_mean.size() * sizeof(double));
+        buf.init_cov = (const double *)upload(init_cov.data(), init_cov.size() * sizeof(double));
+        buf.init_noise = (const double *)upload(init_noise.data(), init_noise.size() * sizeof(double));
     }
-    std::unique_ptr<DeviceBuf> d_coords;
     if (spatial)
-    {
-        d_coords.reset(new DeviceBuf(3 * N * sizeof(int)));
-        check(fabber_cuda_memcpy_h2d(d_coords->p, rundata.Coords().data(), 3 * N * sizeof(int), nullptr), "copying coordinates");
-        buf.coords = (const int *)d_coords->p;
-    }
-    DeviceBuf d_mean(m_mean.size() * sizeof(double)), d_cov(m_cov.size() * sizeof(double)),
-        d_noise(m_noise.size() * sizeof(double)), d_F(N * sizeof(double)), d_status(N * sizeof(int)),
-        d_its(N * sizeof(int)), d_hist(std::max<size_t>(1, m_Fhist.size()) * sizeof(double));
-    buf.mean = (double *)d_mean.p;
-    buf.cov = (double *)d_cov.p;
-    buf.noise = (double *)d_noise.p;
-    buf.free_energy = (double *)d_F.p;
-    buf.status = (int *)d_status.p;
-    buf.iterations = (int *)d_its.p;
-    buf.f_history = m_fhist_len > 0 ? (double *)d_hist.p : nullptr;
-    check(fabber_cuda_stream_sync(nullptr), "uploading inputs");
+        buf.coords = (const int *)upload(rundata.Coords().data(), 3 * N * sizeof(int));
+    buf.mean = (double *)m_d_mean.p;
+    buf.cov = (double *)m_d_cov.p;
+    buf.noise = (double *)m_d_noise.p;
+    buf.free_energy = (double *)m_d_F.p;
+    buf.status = (int *)m_d_status.p;
+    buf.iterations = (int *)m_d_its.p;
+    buf.f_history = m_fhist_len > 0 ? (double *)m_d_hist.p : nullptr;
+    rundata.Log() << "Vb::timing: option translation + device buffers " << sw.lap_ms() << " ms" << std::endl;
 
     int rc = spatial ? fabber_cuda_vb_spatial(&prob, &buf, nullptr) : fabber_cuda_vb_voxelwise(&prob, &buf, nullptr);
     if (rc == FABBER_CUDA_ERR_INVALID)
         throw FabberRunDataError(std::string("Vb: ") + fabber_cuda_last_error());
     check(rc, "VB kernels");
-    check(fabber_cuda_memcpy_d2h(m_mean.data(), d_mean.p, m_mean.size() * sizeof(double), nullptr), "results");
-    check(fabber_cuda_memcpy_d2h(m_cov.data(), d_cov.p, m_cov.size() * sizeof(double), nullptr), "results");
-    check(fabber_cuda_memcpy_d2h(m_noise.data(), d_noise.p, m_noise.size() * sizeof(double), nullptr), "results");
-    check(fabber_cuda_memcpy_d2h(m_F.data(), d_F.p, N * sizeof(double), nullptr), "results");
-    check(fabber_cuda_memcpy_d2h(m_status.data(), d_status.p, N * sizeof(int), nullptr), "results");
-    check(fabber_cuda_memcpy_d2h(m_iterations.data(), d_its.p, N * sizeof(int), nullptr), "results");
-    if (m_fhist_len > 0)
-        check(fabber_cuda_memcpy_d2h(m_Fhist.data(), d_hist.p, m_Fhist.size() * sizeof(double), nullptr), "results");
-    check(fabber_cuda_stream_sync(nullptr), "VB kernels");
-    rundata.Progress((int)N, (int)N);
 
-    /* ---- bad-voxel policy (inference_vb.cc:529-544; set-up failures are never caught, :235) ------------ */
+    /* ---- bad-voxel policy (inference_vb.cc:529-544; set-up failures are never caught, :235) ------------
+     * the status words are scanned on the device; only a count and the first offender come back */
     static const char *reason[] = { "", "LinearizedFwdModel::ReCentre: Non-finite values found in offset",
         "LinearizedFwdModel::ReCentre: Non-finite values found in jacobian", "Non-finite free energy!",
         "matrix is singular", "Ar1cNoiseModel::UpdateAlpha Negative variance!", "voxel ignored" };
-    size_t n_bad = 0;
-    for (size_t v = 0; v < N; v++)
+    int first = -1, code = 0;
+    const int n_bad = fabber_cuda_check_status((const int *)m_d_status.p, (int)N, &first, &code, nullptr);
+    if (n_bad < 0)
+        check(n_bad, "VB kernels");
+    rundata.Log() << "Vb::timing: kernels " << sw.lap_ms() << " ms" << std::endl;
+    rundata.Progress((int)N, (int)N);
+    if (n_bad > 0)
     {
-        const int st = m_status[v];
-        if (st == 0)
-            continue;
-        n_bad++;
-        const int code = st & 0xff;
-        const std::string why = code >= 1 && code <= 6 ? reason[code] : "numerical error";
-        if (n_bad <= 20)
-            rundata.Log() << "Vb::Internal error for voxel " << v + 1 << " : " << why << std::endl;
-        if (m_halt_bad_voxel || (st & FABBER_VOX_SETUP_FLAG))
+        const int c = code & 0xff;
+        const std::string why = c >= 1 && c <= 6 ? reason[c] : "numerical error";
+        rundata.Log() << "Vb::Internal error for voxel " << first + 1 << " : " << why << std::endl;
+        if (m_halt_bad_voxel || (code & FABBER_VOX_SETUP_FLAG))
             throw FabberInternalError(why);
-    }
-    if (n_bad)
         rundata.Log() << "Vb::" << n_bad << " voxels had numerical errors and kept their last state" << std::endl;
+    }
 }
 
 void Vb::SaveResults(FabberRunData &rundata)
 {
+    StopWatch sw;
     const size_t N = m_nvoxels;
     const int P = m_num_params, T = m_ntimes;
     const std::vector<Parameter> &params = m_model->Params();
     const int NP_all = P + m_noise_params;
-
-    /* noise block of the result MVN: means and (co)variances (OutputAsMVN) */
-    auto noise_mean = [&](int i, size_t v) -> double {
-        if (m_ar)
-            return i < 2 ? m_noise[(size_t)(2 + i) * N + v] : m_noise[0 * N + v] * m_noise[1 * N + v];
-        return m_noise[(size_t)(2 * i) * N + v] * m_noise[(size_t)(2 * i + 1) * N + v];
+    if (N == 0 || !m_d_mean.p)
+    {
+        rundata.Log() << "Vb::Done writing results." << std::endl;
+        return;
+    }
+    /* Every requested output map is produced on the device in float32 (fabber_cuda_vb_save_results) and
+     * downloaded straight into the pinned buffer fabber_get_data will read from. */
+    fabber_cuda_vb_buffers buf;
+    memset(&buf, 0, sizeof(buf));
+    buf.mean = (double *)m_d_mean.p;
+    buf.cov = (double *)m_d_cov.p;
+    buf.noise = (double *)m_d_noise.p;
+    buf.free_energy = m_needF ? (double *)m_d_F.p : nullptr;
+    buf.iterations = (int *)m_d_its.p;
+    buf.f_history = m_fhist_len > 0 ? (double *)m_d_hist.p : nullptr;
+    fabber_cuda_vb_outputs out;
+    memset(&out, 0, sizeof(out));
+    struct Pending
+    {
+        float **slot;
+        int rows;
+        std::vector<std::string> keys; /* one key per row group of `rows_per_key` rows */
+        int rows_per_key;
+        void *dev;
+        size_t bytes;
     };
-    auto noise_cov = [&](int i, int j, size_t v) -> double {
-        if (m_ar)
-        {
-            if (i < 2 && j < 2)
-            {
-                const double p11 = m_noise[4 * N + v], p21 = m_noise[5 * N + v], p22 = m_noise[6 * N + v];
-                const double det = p11 * p22 - p21 * p21;
-                return i == j ? (i == 0 ? p22 / det : p11 / det) : -p21 / det;
-            }
-            if (i == 2 && j == 2)
-                return m_noise[0 * N + v] * m_noise[0 * N + v] * m_noise[1 * N + v];
-            return 0.0;
-        }
-        if (i != j)
-            return 0.0;
-        const double b = m_noise[(size_t)(2 * i) * N + v], c = m_noise[(size_t)(2 * i + 1) * N + v];
-        return b * b * c; /* GammaDist::CalcVariance, dist_gamma.cc:25 */
+    std::vector<Pending> pending;
+    auto want = [&](float **slot, int rows, const std::vector<std::string> &keys, int rows_per_key) {
+        Pending p;
+        p.slot = slot;
+        p.rows = rows;
+        p.keys = keys;
+        p.rows_per_key = rows_per_key;
+        p.bytes = (size_t)rows * N * sizeof(float);
+        p.dev = cached_device_alloc(p.bytes);
+        *slot = (float *)p.dev;
+        pending.push_back(p);
     };
-
+    auto per_param = [&](const std::string &prefix) {
+        std::vector<std::string> k;
+        for (int i = 0; i < P; i++)
+            k.push_back(prefix + params[i].name);
+        return k;
+    };
+    if (rundata.GetBool("save-mean"))
+        want(&out.mean, P, per_param("mean_"), 1);
+    if (rundata.GetBool("save-std"))
+        want(&out.std, P, per_param("std_"), 1);
+    if (rundata.GetBool("save-zstat"))
+        want(&out.zstat, P, per_param("zstat_"), 1);
+    if (rundata.GetBool("save-var"))
+        want(&out.var, P, per_param("var_"), 1);
+    if (rundata.GetBool("save-noise-mean") && m_noise_params > 0)
+        want(&out.noise_mean, m_noise_params, std::vector<std::string>(1, "noise_means"), m_noise_params);
+    if (rundata.GetBool("save-noise-std") && m_noise_params > 0)
+        want(&out.noise_std, m_noise_params, std::vector<std::string>(1, "noise_stdevs"), m_noise_params);
     if (rundata.GetBool("save-mvn"))
     {
-        /* MVNDist::Save, dist_mvn.cc:377-433: packed lower triangle by rows, means, 1 */
-        const int n_cov = NP_all * (NP_all + 1) / 2;
-        VoxelData &out = rundata.NewVoxelData("finalMVN", n_cov + NP_all + 1);
-        for (size_t v = 0; v < N; v++)
-        {
-            int idx = 0;
-            for (int r = 0; r < NP_all; r++)
-                for (int c = 0; c <= r; c++, idx++)
-                {
-                    double val = 0.0;
-                    if (r < P)
-                        val = m_cov[(size_t)tri(r, c) * N + v];
-                    else if (c >= P)
-                        val = noise_cov(r - P, c - P, v);
-                    out.d[(size_t)idx * N + v] = val;
-                }
-            for (int i = 0; i < P; i++)
-                out.d[(size_t)(n_cov + i) * N + v] = m_mean[(size_t)i * N + v];
-            for (int i = 0; i < m_noise_params; i++)
-                out.d[(size_t)(n_cov + P + i) * N + v] = noise_mean(i, v);
-            out.d[(size_t)(n_cov + NP_all) * N + v] = 1.0;
-        }
-    }
-    const bool s_mean = rundata.GetBool("save-mean"), s_std = rundata.GetBool("save-std"),
-               s_z = rundata.GetBool("save-zstat"), s_var = rundata.GetBool("save-var");
-    if (s_mean | s_std | s_z | s_var)
-        for (int i = 0; i < P; i++)
-        {
-            /* model space: FwdModel::ToModel on mean and diagonal variance (fwdmodel.cc:326-337) */
-            VoxelData *om = s_mean ? &rundata.NewVoxelData("mean_" + params[i].name, 1) : nullptr;
-            VoxelData *oz = s_z ? &rundata.NewVoxelData("zstat_" + params[i].name, 1) : nullptr;
-            VoxelData *os = s_std ? &rundata.NewVoxelData("std_" + params[i].name, 1) : nullptr;
-            VoxelData *ov = s_var ? &rundata.NewVoxelData("var_" + params[i].name, 1) : nullptr;
-            const char tr = params[i].transform;
-            for (size_t v = 0; v < N; v++)
-            {
-                const double mean = transform_to_model(tr, m_mean[(size_t)i * N + v]);
-                const double var = transform_to_model_var(tr, m_cov[(size_t)tri(i, i) * N + v]);
-                const double sd = std::sqrt(var);
-                if (om)
-                    om->d[v] = mean;
-                if (oz)
-                    oz->d[v] = mean / sd;
-                if (os)
-                    os->d[v] = sd;
-                if (ov)
-                    ov->d[v] = var;
-            }
-        }
-    const bool s_fit = rundata.GetBool("save-model-fit"), s_res = rundata.GetBool("save-residuals");
-    if ((s_fit || s_res) && N > 0)
-    {
-        /* inference.cc:160-239: EvaluateFabber at the posterior means, as one batched device evaluation */
-        fabber_cuda_vb_problem prob;
-        memset(&prob, 0, sizeof(prob));
-        prob.n_voxels = (int)N;
-        prob.n_times = T;
-        m_model->GetDeviceModel(prob.model);
-        for (int i = 0; i < P; i++)
-            prob.params[i].transform = params[i].transform;
-        DeviceBuf d_mean(m_mean.size() * sizeof(double)), d_fit((size_t)T * N * sizeof(double));
-        check(fabber_cuda_memcpy_h2d(d_mean.p, m_mean.data(), m_mean.size() * sizeof(double), nullptr), "model fit");
-        check(fabber_cuda_model_fit(&prob, (const double *)d_mean.p, (double *)d_fit.p, nullptr), "model fit");
-        std::vector<double> fit((size_t)T * N);
-        check(fabber_cuda_memcpy_d2h(fit.data(), d_fit.p, fit.size() * sizeof(double), nullptr), "model fit");
-        check(fabber_cuda_stream_sync(nullptr), "model fit");
-        if (s_res)
-        {
-            const VoxelData &data = rundata.GetMainVoxelData();
-            VoxelData &res = rundata.NewVoxelData("residuals", T);
-            for (size_t i = 0; i < fit.size(); i++)
-                res.d[i] = (double)data.f[i] - fit[i];
-        }
-        if (s_fit)
-        {
-            VoxelData &mf = rundata.NewVoxelData("modelfit", T);
-            mf.d.swap(fit);
-        }
-    }
-    if ((rundata.GetBool("save-noise-mean") | rundata.GetBool("save-noise-std")) && m_noise_params > 0)
-    {
-        VoxelData *nm = rundata.GetBool("save-noise-mean") ? &rundata.NewVoxelData("noise_means", m_noise_params) : nullptr;
-        VoxelData *ns = rundata.GetBool("save-noise-std") ? &rundata.NewVoxelData("noise_stdevs", m_noise_params) : nullptr;
-        for (int i = 0; i < m_noise_params; i++)
-            for (size_t v = 0; v < N; v++)
-            {
-                if (nm)
-                    nm->d[(size_t)i * N + v] = noise_mean(i, v);
-                if (ns)
-                    ns->d[(size_t)i * N + v] = std::sqrt(noise_cov(i, i, v));
-            }
+        const int rows = NP_all * (NP_all + 1) / 2 + NP_all + 1; /* MVNDist::Save, dist_mvn.cc:377-433 */
+        want(&out.final_mvn, rows, std::vector<std::string>(1, "finalMVN"), rows);
     }
     if (m_saveF && m_needF)
+        want(&out.free_energy, 1, std::vector<std::string>(1, "freeEnergy"), 1);
+    if (m_saveFsHistory && m_fhist_len > 0 && m_needF)
     {
-        VoxelData &f = rundata.NewVoxelData("freeEnergy", 1);
-        for (size_t v = 0; v < N; v++)
-            f.d[v] = m_F[v];
-    }
-    if (N > 0 && m_saveFsHistory && m_fhist_len > 0)
-    {
-        /* one row per pass, plus the final value pushed after the loop (inference_vb.cc:553-554); voxels
+        /* one row per pass plus the final value pushed after the loop (inference_vb.cc:553-554); voxels
          * that stopped early repeat their last value (:1038-1045) */
         int max_its = 0;
-        for (size_t v = 0; v < N; v++)
-            max_its = std::max(max_its, m_iterations[v]);
-        const int rows = std::min(max_its + 1, m_fhist_len);
-        VoxelData &h = rundata.NewVoxelData("freeEnergyHistory", rows);
-        for (int r = 0; r < rows; r++)
-            for (size_t v = 0; v < N; v++)
-                h.d[(size_t)r * N + v] = r < m_iterations[v] ? m_Fhist[(size_t)r * N + v] : m_F[v];
+        check(fabber_cuda_max_int((const int *)m_d_its.p, (int)N, &max_its, nullptr), "free energy history");
+        out.f_history_rows = std::min(max_its + 1, m_fhist_len);
+        want(&out.f_history, out.f_history_rows, std::vector<std::string>(1, "freeEnergyHistory"), out.f_history_rows);
     }
+    if (rundata.GetBool("save-model-fit"))
+        want(&out.model_fit, T, std::vector<std::string>(1, "modelfit"), T);
+    if (rundata.GetBool("save-residuals"))
+    {
+        VoxelData &data = rundata.MutableVoxelData("data");
+        if (!data.dev)
+        {
+            data.dev = (float *)cached_device_alloc(data.bytes());
+            check(fabber_cuda_memcpy_h2d(data.dev, data.f, data.bytes(), nullptr), "copying data to the GPU");
+        }
+        out.data = data.dev;
+        want(&out.residuals, T, std::vector<std::string>(1, "residuals"), T);
+    }
+    int rc = FABBER_CUDA_OK;
+    if (!pending.empty())
+        rc = fabber_cuda_vb_save_results(&m_prob, &buf, &out, nullptr);
+    for (size_t i = 0; i < pending.size() && rc == FABBER_CUDA_OK; i++)
+    {
+        const Pending &p = pending[i];
+        for (size_t k = 0; k < p.keys.size(); k++)
+        {
+            VoxelData &vd = rundata.NewVoxelData(p.keys[k], p.rows_per_key);
+            rc = fabber_cuda_memcpy_d2h(vd.f, (const float *)p.dev + k * (size_t)p.rows_per_key * N, vd.bytes(), nullptr);
+            if (rc != FABBER_CUDA_OK)
+                break;
+        }
+    }
+    const int rc_sync = fabber_cuda_stream_sync(nullptr);
+    for (size_t i = 0; i < pending.size(); i++)
+        cached_device_free(pending[i].dev, pending[i].bytes);
+    ReleaseDevice();
+    check(rc, "saving results");
+    check(rc_sync, "saving results");
+    rundata.Log() << "Vb::timing: SaveResults " << sw.lap_ms() << " ms" << std::endl;
     rundata.Log() << "Vb::Done writing results." << std::endl;
 }
 

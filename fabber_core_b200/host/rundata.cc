@@ -10,10 +10,40 @@
 #include <cstring>
 #include <ctime>
 
+#include <map>
+#include <mutex>
+#include <thread>
+
 #include "fabber_host.h"
 
 namespace fabber_b200
 {
+void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_chunk)
+{
+    unsigned hw = std::thread::hardware_concurrency();
+    size_t threads = hw ? hw : 4;
+    if (threads > 32)
+        threads = 32;
+    if (n / min_chunk + 1 < threads)
+        threads = n / min_chunk + 1;
+    if (threads <= 1)
+    {
+        fn(0, n);
+        return;
+    }
+    std::vector<std::thread> pool;
+    const size_t per = (n + threads - 1) / threads;
+    for (size_t t = 0; t < threads; t++)
+    {
+        const size_t b = t * per, e = std::min(n, b + per);
+        if (b >= e)
+            break;
+        pool.emplace_back([&fn, b, e]() { fn(b, e); });
+    }
+    for (size_t t = 0; t < pool.size(); t++)
+        pool[t].join();
+}
+
 const char *option_type_name(OptionType t)
 {
     switch (t)
@@ -40,35 +70,95 @@ const char *option_type_name(OptionType t)
     return "UNKNOWN";
 }
 
+/* ---- memory cache (see fabber_host.h) ------------------------------------------------------------ */
+namespace
+{
+struct BlockCache
+{
+    std::mutex mu;
+    std::multimap<size_t, void *> free_blocks;
+    size_t cached_bytes = 0;
+};
+BlockCache g_pinned, g_device;
+const size_t CACHE_LIMIT = (size_t)48 << 30; /* per kind; beyond it blocks really are freed */
+
+void *cache_get(BlockCache &c, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(c.mu);
+    std::multimap<size_t, void *>::iterator it = c.free_blocks.find(bytes);
+    if (it == c.free_blocks.end())
+        return nullptr;
+    void *p = it->second;
+    c.free_blocks.erase(it);
+    c.cached_bytes -= bytes;
+    return p;
+}
+bool cache_put(BlockCache &c, void *p, size_t bytes)
+{
+    std::lock_guard<std::mutex> lock(c.mu);
+    if (c.cached_bytes + bytes > CACHE_LIMIT)
+        return false;
+    c.free_blocks.insert(std::make_pair(bytes, p));
+    c.cached_bytes += bytes;
+    return true;
+}
+} // namespace
+
+void *cached_pinned_alloc(size_t bytes)
+{
+    if (bytes == 0)
+        bytes = 1;
+    void *p = cache_get(g_pinned, bytes);
+    if (!p)
+        p = fabber_cuda_host_alloc(bytes);
+    if (!p)
+        throw FabberInternalError(std::string("Could not allocate pinned host memory: ") + fabber_cuda_last_error());
+    return p;
+}
+void cached_pinned_free(void *p, size_t bytes)
+{
+    if (p && !cache_put(g_pinned, p, bytes ? bytes : 1))
+        fabber_cuda_host_free(p);
+}
+void *cached_device_alloc(size_t bytes)
+{
+    if (bytes == 0)
+        bytes = 1;
+    void *p = cache_get(g_device, bytes);
+    if (!p)
+        p = fabber_cuda_malloc(bytes);
+    if (!p)
+        throw FabberInternalError(std::string("GPU allocation failed: ") + fabber_cuda_last_error());
+    return p;
+}
+void cached_device_free(void *p, size_t bytes)
+{
+    if (p && !cache_put(g_device, p, bytes ? bytes : 1))
+        fabber_cuda_free(p);
+}
+
 VoxelData::VoxelData()
     : rows(0)
     , cols(0)
-    , is_float(false)
     , f(nullptr)
+    , dev(nullptr)
 {
 }
 VoxelData::~VoxelData()
 {
-    if (f)
-        fabber_cuda_host_free(f);
+    /* work queued on the device may still read these blocks: drain it before they can be handed out again */
+    if (dev)
+        fabber_cuda_stream_sync(nullptr);
+    cached_pinned_free(f, bytes());
+    cached_device_free(dev, bytes());
 }
-void VoxelData::alloc_float(int r, size_t c)
+void VoxelData::alloc(int r, size_t c)
 {
+    cached_pinned_free(f, bytes());
+    f = nullptr;
     rows = r;
     cols = c;
-    is_float = true;
-    if (f)
-        fabber_cuda_host_free(f);
-    f = (float *)fabber_cuda_host_alloc((unsigned long long)r * c * sizeof(float));
-    if (!f)
-        throw FabberInternalError(std::string("Could not allocate pinned host memory: ") + fabber_cuda_last_error());
-}
-void VoxelData::alloc_double(int r, size_t c)
-{
-    rows = r;
-    cols = c;
-    is_float = false;
-    d.assign((size_t)r * c, 0.0);
+    f = (float *)cached_pinned_alloc(bytes());
 }
 
 FabberRunData::FabberRunData()
@@ -217,17 +307,35 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         throw FabberRunDataError("Extent must be set before voxel data");
     const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
     const size_t N = m_voxel_index.size();
+    m_voxel_data.erase(key); /* hand the old blocks back to the cache before asking for new ones */
     std::unique_ptr<VoxelData> vd(new VoxelData());
-    vd->alloc_float(data_size, N);
-    for (int t = 0; t < data_size; t++)
+    vd->alloc(data_size, N);
+    float *dst_all = vd->f;
+    const std::vector<int> &index = m_voxel_index;
+    /* The main series goes straight on to the GPU: rows are staged into pinned memory in ~64 MB chunks by
+     * all host cores and each chunk's host->device copy is queued as soon as it is staged, so the PCIe
+     * transfer of chunk k overlaps the staging of chunk k+1. */
+    const bool upload = (key == "data") && N > 0 && fabber_cuda_device_count() > 0;
+    if (upload)
+        vd->dev = (float *)cached_device_alloc(vd->bytes());
+    const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max<size_t>(1, N * sizeof(float)));
+    for (size_t r0 = 0; r0 < (size_t)data_size; r0 += rows_per_chunk)
     {
-        const float *src = data + (size_t)t * n_grid;
-        float *dst = vd->f + (size_t)t * N;
+        const size_t r1 = std::min<size_t>(data_size, r0 + rows_per_chunk);
+        const size_t off = r0 * N, cnt = (r1 - r0) * N;
         if (N == n_grid)
-            memcpy(dst, src, N * sizeof(float));
+            parallel_for(cnt, [&](size_t b, size_t e) { memcpy(dst_all + off + b, data + off + b, (e - b) * sizeof(float)); },
+                (size_t)1 << 20);
         else
-            for (size_t v = 0; v < N; v++)
-                dst[v] = src[m_voxel_index[v]];
+            parallel_for(cnt, [&](size_t b, size_t e) {
+                for (size_t i = off + b; i < off + e; i++)
+                {
+                    const size_t t = i / N, v = i - t * N;
+                    dst_all[i] = data[t * n_grid + index[v]];
+                }
+            });
+        if (upload && fabber_cuda_memcpy_h2d(vd->dev + off, dst_all + off, cnt * sizeof(float), nullptr) != FABBER_CUDA_OK)
+            throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
     }
     m_voxel_data[key] = std::move(vd);
 }
@@ -250,10 +358,15 @@ const VoxelData &FabberRunData::GetMainVoxelData() { return GetVoxelData("data")
 int FabberRunData::GetVoxelDataSize(const std::string &key) { return GetVoxelData(key).rows; }
 VoxelData &FabberRunData::NewVoxelData(const std::string &key, int rows)
 {
+    m_voxel_data.erase(key);
     std::unique_ptr<VoxelData> vd(new VoxelData());
-    vd->alloc_double(rows, m_voxel_index.size());
+    vd->alloc(rows, m_voxel_index.size());
     m_voxel_data[key] = std::move(vd);
     return *m_voxel_data[key];
+}
+VoxelData &FabberRunData::MutableVoxelData(const std::string &key)
+{
+    return const_cast<VoxelData &>(GetVoxelData(key));
 }
 void FabberRunData::ClearVoxelData(const std::string &key) { m_voxel_data.erase(key); }
 
@@ -263,18 +376,17 @@ void FabberRunData::GetVoxelDataArray(const std::string &key, float *data)
     const VoxelData &vd = GetVoxelData(key);
     const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
     const size_t N = m_voxel_index.size();
-    for (int t = 0; t < vd.rows; t++)
-    {
-        float *dst = data + (size_t)t * n_grid;
-        if (N != n_grid)
-            memset(dst, 0, n_grid * sizeof(float));
-        if (vd.is_float)
-            for (size_t v = 0; v < N; v++)
-                dst[m_voxel_index[v]] = vd.f[(size_t)t * N + v];
-        else
-            for (size_t v = 0; v < N; v++)
-                dst[m_voxel_index[v]] = (float)vd.d[(size_t)t * N + v];
-    }
+    const std::vector<int> &index = m_voxel_index;
+    if (N != n_grid)
+        parallel_for((size_t)vd.rows * n_grid, [&](size_t b, size_t e) { memset(data + b, 0, (e - b) * sizeof(float)); },
+            (size_t)1 << 20);
+    parallel_for((size_t)vd.rows * N, [&](size_t b, size_t e) {
+        for (size_t i = b; i < e; i++)
+        {
+            const size_t t = i / N, v = i - t * N;
+            data[t * n_grid + index[v]] = vd.f[i];
+        }
+    });
 }
 
 void FabberRunData::GetOptions(std::vector<OptionSpec> &opts)

@@ -197,6 +197,27 @@ int fabber_cuda_check_status(
 int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean /*[P][N]*/,
     double *fit /*[T][N]*/, void *stream);
 
+/* Output maps of InferenceTechnique::SaveResults / Vb::SaveResults (inference.cc:112-157,
+ * inference_vb.cc:966-1047, MVNDist::Save dist_mvn.cc:377-433) computed on the device from the result
+ * arrays of fabber_cuda_vb_*, in float32 - the precision every reference output is stored in
+ * (rundata_array.cc:68-98, NIfTI float). All pointers are DEVICE pointers; NULL = not wanted. */
+typedef struct fabber_cuda_vb_outputs
+{
+    float *mean, *std, *zstat, *var; /* [P][N], model space (FwdModel::ToModel, fwdmodel.cc:326-337) */
+    float *noise_mean, *noise_std;   /* [Nn][N]; Nn = n_phis (white) or 3 (AR1: alpha1, alpha2, phi) */
+    float *final_mvn;                /* [(P+Nn)(P+Nn+1)/2 + (P+Nn) + 1][N] packed covariance, means, 1 */
+    float *free_energy;              /* [N] */
+    float *f_history;                /* [f_history_rows][N]: rows >= iterations repeat the final F */
+    int f_history_rows;
+    const float *data;               /* [T][N] input series, needed for residuals */
+    float *model_fit, *residuals;    /* [T][N] (inference.cc:160-239) */
+} fabber_cuda_vb_outputs;
+int fabber_cuda_vb_save_results(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
+    const fabber_cuda_vb_outputs *out, void *stream);
+
+/* max over an int array on the device (synchronises the stream); used for the F-history row count */
+int fabber_cuda_max_int(const int *values, int n, int *result, void *stream);
+
 /* Measured FP64 FMA throughput of the current device in GFLOP/s (dependent-free DFMA loop on all
  * SMs; used as the roofline denominator because MEASURED_PEAKS.json carries no FP64 figure). */
 double fabber_cuda_measure_fp64_peak(int repeats);

@@ -1,0 +1,66 @@
+"""CPU, world_size 2, gloo: the N > 1 path of non-spatial VB - balanced contiguous voxel ranges, no
+data-path collective, one final gather - gives exactly the single-process result. The per-rank compute
+is the oracle here (no GPU in this container); on the B200 box the same helper wraps device.run."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import oracle
+from fabber_core_b200 import cuda_abi as abi
+from fabber_core_b200 import shard, synth
+
+
+def test_voxel_ranges_partition_exactly():
+    for n in (0, 1, 7, 8, 1000003):
+        for world in (1, 2, 3, 8):
+            ranges = [shard.voxel_range(n, r, world) for r in range(world)]
+            assert ranges[0][0] == 0 and ranges[-1][1] == n
+            for a, b in zip(ranges, ranges[1:]):
+                assert a[1] == b[0]
+            sizes = [hi - lo for lo, hi in ranges]
+            assert max(sizes) - min(sizes) <= 1
+    assert shard.z_slab_range(256, 3, 8) == (96, 128)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _worker(rank, world, port, y, img, tmp):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        mk = lambda: abi.ProblemSpec("poly", y.shape[0], degree=2, prior_types=["N", "N", "I"], need_f=True,
+                                     convergence="pointzeroone")
+        local = shard.run_sharded(oracle.run, mk, y, rank, world, image_priors={2: img})
+        lo, hi = shard.voxel_range(y.shape[1], rank, world)
+        assert local["mean"].shape == (3, hi - lo)
+        full = shard.gather_results(local, y.shape[1], rank, world, dst=0)
+        if rank == 0:
+            np.savez(tmp, **{k: v for k, v in full.items()})
+        else:
+            assert full is None
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_shards_reproduce_the_single_process_run(tmp_path):
+    y = synth.poly_volume(401, 30, 2, seed=51).numpy()  # odd count: uneven shards
+    img = np.linspace(-1e-3, 1e-3, y.shape[1])
+    tmp = str(tmp_path / "gathered.npz")
+    mp.spawn(_worker, args=(2, _free_port(), y, img, tmp), nprocs=2, join=True)
+    got = np.load(tmp)
+    ref = oracle.run(abi.ProblemSpec("poly", 30, degree=2, prior_types=["N", "N", "I"], need_f=True,
+                                     convergence="pointzeroone"), y, image_priors={2: img})
+    for k in ("mean", "cov", "noise", "free_energy", "iterations", "status"):
+        assert np.array_equal(got[k], ref[k]), k
