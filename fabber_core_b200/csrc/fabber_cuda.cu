@@ -288,6 +288,19 @@ __global__ void max_int_kernel(const int *values, int n, int *result)
         atomicMax(result, m);
 }
 
+/* accuracy probe of the table-based exponential (vb_exp.cuh) against the CUDA library exp() */
+__global__ void exp_probe_kernel(const double *x, double *fast, double *ref, int n)
+{
+    __shared__ double tab[EXP_TAB_DOUBLES];
+    exp_table_stage(tab);
+    __syncthreads();
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    fast[i] = exp_fast(x[i], tab);
+    ref[i] = exp(x[i]);
+}
+
 /* dependent-free DFMA loop: 8 independent accumulators per thread */
 __global__ void fp64_peak_kernel(double *out, int iters, double x)
 {
@@ -1072,6 +1085,16 @@ double fabber_cuda_measure_fp64_peak(int repeats)
 }
 
 unsigned long long fabber_cuda_launch_count(void) { return g_launches.load(); }
+
+int fabber_cuda_exp_probe(const double *x, double *fast, double *ref, int n, void *stream)
+{
+    if (n <= 0)
+        return FABBER_CUDA_OK;
+    exp_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, fast, ref, n);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "exp_probe");
+}
 
 /* struct sizes, so that language bindings can verify their mirror of the header */
 int fabber_cuda_sizeof_problem(void) { return (int)sizeof(fabber_cuda_vb_problem); }

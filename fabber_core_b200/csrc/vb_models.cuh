@@ -14,6 +14,9 @@
  *                          Every value is bit-identical to calling eval() on the perturbed vector;
  *                          models override it only to share sub-expressions that provably do not
  *                          depend on the perturbed element (e.g. exp(-r t) when an amplitude moves).
+ *   HAS_FAST / fast_ok()   optional: a cheaper eval_fd<true> that is valid only for a range of parameters
+ *                          (exp: the table-based exponential of vb_exp.cuh needs |r t| < 708); the pass
+ *                          checks fast_ok() once, outside the time loop, and otherwise runs eval_fd<false>
  *   init_voxel(...)        FwdModel::InitVoxelPosterior hook (model-space means)
  *
  * The arithmetic inside eval() follows the reference's EvaluateModel operation by operation, with
@@ -24,6 +27,7 @@
  */
 #pragma once
 #include "vb_device.cuh"
+#include "vb_exp.cuh"
 
 namespace fab
 {
@@ -64,6 +68,12 @@ template <int P_> struct LinearModel
             s = __dadd_rn(s, __dmul_rn(row[j], p[j]));
         return s;
     }
+    static constexpr bool HAS_FAST = false;
+    static FAB_DEV bool fast_ok(const Ctx &, int, const double (&)[P], const double (&)[P], const double (&)[P])
+    {
+        return false;
+    }
+    template <bool FAST>
     static FAB_DEV void eval_fd(const Ctx &c, int t, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
@@ -141,6 +151,12 @@ template <int P_> struct PolyModel
             s = __dadd_rn(s, __dmul_rn(p[n], pw[n]));
         return s;
     }
+    static constexpr bool HAS_FAST = false;
+    static FAB_DEV bool fast_ok(const Ctx &, int, const double (&)[P], const double (&)[P], const double (&)[P])
+    {
+        return false;
+    }
+    template <bool FAST>
     static FAB_DEV void eval_fd(const Ctx &, int t, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
@@ -189,15 +205,30 @@ template <int NE> struct ExpModel
     struct Ctx
     {
         double dt;
+        const double *tab; /* exp table in shared memory (vb_exp.cuh) */
     };
-    static __host__ __device__ size_t smem_bytes(int) { return 0; }
-    template <class Args> static FAB_DEV void stage(const Args &, double *) {}
-    template <class Args> static FAB_DEV Ctx make_ctx(const Args &a, double *)
+    static __host__ __device__ size_t smem_bytes(int) { return EXP_TAB_DOUBLES * sizeof(double); }
+    template <class Args> static FAB_DEV void stage(const Args &, double *smem) { exp_table_stage(smem); }
+    template <class Args> static FAB_DEV Ctx make_ctx(const Args &a, double *smem)
     {
         Ctx c;
         c.dt = a.exp_dt;
+        c.tab = smem;
         return c;
     }
+    static constexpr bool HAS_FAST = true;
+    /* every exponent the pass will form stays inside the table method's range */
+    static FAB_DEV bool fast_ok(const Ctx &c, int T, const double (&p0)[P], const double (&pp)[P], const double (&pn)[P])
+    {
+        const double t_max = __dmul_rn((double)(T > 0 ? T - 1 : 0), c.dt);
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+            ok = ok && exp_fast_range_ok(p0[2 * k + 1], t_max) && exp_fast_range_ok(pp[2 * k + 1], t_max)
+                && exp_fast_range_ok(pn[2 * k + 1], t_max);
+        return ok;
+    }
+    template <bool FAST> static FAB_DEV double ex(const Ctx &c, double x) { return FAST ? exp_fast(x, c.tab) : exp(x); }
     static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])
     {
         double tt = __dmul_rn((double)t, c.dt);
@@ -207,6 +238,7 @@ template <int NE> struct ExpModel
             s = __dadd_rn(s, __dmul_rn(p[2 * k], exp(__dmul_rn(-p[2 * k + 1], tt))));
         return s;
     }
+    template <bool FAST>
     static FAB_DEV void eval_fd(const Ctx &c, int t, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
@@ -215,7 +247,7 @@ template <int NE> struct ExpModel
 #pragma unroll
         for (int k = 0; k < NE; k++)
         {
-            e0[k] = exp(__dmul_rn(-p0[2 * k + 1], tt));
+            e0[k] = ex<FAST>(c, __dmul_rn(-p0[2 * k + 1], tt));
             term[k] = __dmul_rn(p0[2 * k], e0[k]);
         }
         double s = term[0];
@@ -230,8 +262,8 @@ template <int NE> struct ExpModel
             double ta[4];
             ta[0] = __dmul_rn(pp[2 * k], e0[k]);
             ta[1] = __dmul_rn(pn[2 * k], e0[k]);
-            ta[2] = __dmul_rn(p0[2 * k], exp(__dmul_rn(-pp[2 * k + 1], tt)));
-            ta[3] = __dmul_rn(p0[2 * k], exp(__dmul_rn(-pn[2 * k + 1], tt)));
+            ta[2] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pp[2 * k + 1], tt)));
+            ta[3] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pn[2 * k + 1], tt)));
             double out[4];
 #pragma unroll
             for (int q = 0; q < 4; q++)

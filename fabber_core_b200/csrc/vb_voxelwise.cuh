@@ -115,6 +115,45 @@ template <int P> struct Stats
     }
 };
 
+/* the pass over the time-series: model at the 2P+1 finite-difference points, Jacobian row, statistics */
+template <class Model, int NPHI, bool FAST>
+FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
+    const double (&p0)[Model::P], const double (&pp)[Model::P], const double (&pn)[Model::P],
+    const double (&rden)[Model::P], Stats<Model::P> (&S)[NPHI], bool &bad_g, bool &bad_j)
+{
+    constexpr int P = Model::P;
+    const float *yp = a.data + v;
+    const size_t stride = (size_t)a.N;
+    float ynext = __ldg(yp);
+#pragma unroll 1
+    for (int t = 0; t < a.T; t++)
+    {
+        const double y = (double)ynext;
+        if (t + 1 < a.T) /* software prefetch: the load of sample t+1 overlaps the arithmetic of sample t */
+            ynext = __ldg(yp + (size_t)(t + 1) * stride);
+        double g, gp[P], gn[P], J[P];
+        Model::template eval_fd<FAST>(mc, t, p0, pp, pn, g, gp, gn);
+        bad_g = bad_g || !finite_d(g);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            J[i] = (gp[i] - gn[i]) * rden[i];
+            bad_j = bad_j || !finite_d(J[i]);
+        }
+        const double r = y - g;
+        if (NPHI == 1)
+            S[0].add(r, J);
+        else
+        {
+            const int ph = pat[t];
+#pragma unroll
+            for (int i = 0; i < NPHI; i++)
+                if (ph == i)
+                    S[i].add(r, J);
+        }
+    }
+}
+
 /*
  * LinearizedFwdModel::ReCentre fused with the statistics pass. Returns 0, or FABBER_VOX_NONFINITE_*
  * exactly where the reference throws (offset checked before the Jacobian, fwdmodel_linear.cc:134,174).
@@ -145,36 +184,12 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
     for (int i = 0; i < NPHI; i++)
         S[i].zero();
     bool bad_g = false, bad_j = false;
-    const float *yp = a.data + v;
-    const size_t stride = (size_t)a.N;
-    float ynext = __ldg(yp);
-#pragma unroll 1
-    for (int t = 0; t < a.T; t++)
-    {
-        const double y = (double)ynext;
-        if (t + 1 < a.T) /* software prefetch: the load of sample t+1 overlaps the arithmetic of sample t */
-            ynext = __ldg(yp + (size_t)(t + 1) * stride);
-        double g, gp[P], gn[P], J[P];
-        Model::eval_fd(mc, t, p0, pp, pn, g, gp, gn);
-        bad_g = bad_g || !finite_d(g);
-#pragma unroll
-        for (int i = 0; i < P; i++)
-        {
-            J[i] = (gp[i] - gn[i]) * rden[i];
-            bad_j = bad_j || !finite_d(J[i]);
-        }
-        const double r = y - g;
-        if (NPHI == 1)
-            S[0].add(r, J);
-        else
-        {
-            const int ph = pat[t];
-#pragma unroll
-            for (int i = 0; i < NPHI; i++)
-                if (ph == i)
-                    S[i].add(r, J);
-        }
-    }
+    /* models with a range-limited cheaper evaluation (exp: table-based exponential) take it when every
+     * argument of this pass is inside its range - checked once here, not per sample */
+    if (Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn))
+        recentre_loop<Model, NPHI, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+    else
+        recentre_loop<Model, NPHI, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     return bad_g ? FABBER_VOX_NONFINITE_OFFSET : (bad_j ? FABBER_VOX_NONFINITE_JACOBIAN : 0);
 }
 

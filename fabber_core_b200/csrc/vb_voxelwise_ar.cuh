@@ -62,30 +62,12 @@ FAB_DEV double ar_klj(const Stats<P> &M, const double (&d)[P], const double (&Si
     return (M.rr + 2.0 * bd + quadform<P>(M.A, d)) + trace_prod<P>(Sig, M.A);
 }
 
-template <class Model>
-FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&c)[Model::P],
-    ArStats<Model::P> &S)
+template <class Model, bool FAST>
+FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&p0)[Model::P],
+    const double (&pp)[Model::P], const double (&pn)[Model::P], const double (&rden)[Model::P],
+    ArStats<Model::P> &S, bool &bad_g, bool &bad_j)
 {
     constexpr int P = Model::P;
-    double p0[P], pp[P], pn[P], rden[P];
-#pragma unroll
-    for (int i = 0; i < P; i++)
-    {
-        const char code = a.params[i].transform;
-        double delta = c[i] * 1e-5;
-        if (delta < 0)
-            delta = -delta;
-        if (delta < 1e-10)
-            delta = 1e-10;
-        const double c2 = c[i] + delta, c3 = c[i] - delta;
-        p0[i] = to_model(code, c[i]);
-        pp[i] = to_model(code, c2);
-        pn[i] = to_model(code, c3);
-        rden[i] = 1.0 / (c2 - c3);
-    }
-    S.S0.zero();
-    S.S1.zero();
-    bool bad_g = false, bad_j = false;
     const float *yp = a.data + v;
     const size_t stride = (size_t)a.N;
     float ynext = __ldg(yp);
@@ -100,7 +82,7 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
         if (t + 1 < a.T)
             ynext = __ldg(yp + (size_t)(t + 1) * stride);
         double g, gp[P], gn[P], J[P];
-        Model::eval_fd(mc, t, p0, pp, pn, g, gp, gn);
+        Model::template eval_fd<FAST>(mc, t, p0, pp, pn, g, gp, gn);
         bad_g = bad_g || !finite_d(g);
 #pragma unroll
         for (int i = 0; i < P; i++)
@@ -136,6 +118,36 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     for (int i = 0; i < P; i++)
         S.Jl[i] = Jprev[i];
     S.rl = rprev;
+}
+
+template <class Model>
+FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&c)[Model::P],
+    ArStats<Model::P> &S)
+{
+    constexpr int P = Model::P;
+    double p0[P], pp[P], pn[P], rden[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+    {
+        const char code = a.params[i].transform;
+        double delta = c[i] * 1e-5;
+        if (delta < 0)
+            delta = -delta;
+        if (delta < 1e-10)
+            delta = 1e-10;
+        const double c2 = c[i] + delta, c3 = c[i] - delta;
+        p0[i] = to_model(code, c[i]);
+        pp[i] = to_model(code, c2);
+        pn[i] = to_model(code, c3);
+        rden[i] = 1.0 / (c2 - c3);
+    }
+    S.S0.zero();
+    S.S1.zero();
+    bool bad_g = false, bad_j = false;
+    if (Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn))
+        recentre_loop_ar<Model, true>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j);
+    else
+        recentre_loop_ar<Model, false>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j);
     return bad_g ? FABBER_VOX_NONFINITE_OFFSET : (bad_j ? FABBER_VOX_NONFINITE_JACOBIAN : 0);
 }
 

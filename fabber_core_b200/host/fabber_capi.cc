@@ -4,6 +4,7 @@
  * the caller's err_buf; no exception crosses the ABI; every buffer belongs to the caller.
  */
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "../../include/fabber_capi.h"
@@ -37,6 +38,14 @@ void *fabber_new(char *err_buf)
 {
     try
     {
+        /* one process per GPU: FABBER_CUDA_DEVICE picks the device of this process (default: the
+         * calling thread's current device) */
+        if (const char *dev = getenv("FABBER_CUDA_DEVICE"))
+            if (fabber_cuda_set_device(atoi(dev)) != FABBER_CUDA_OK)
+            {
+                fabber_err(FABBER_ERR_FATAL, fabber_cuda_last_error(), err_buf);
+                return NULL;
+            }
         return new FabberRunDataArray();
     }
     catch (...)

@@ -225,6 +225,10 @@ double fabber_cuda_measure_fp64_peak(int repeats);
 /* Number of kernels this library has launched so far in this process. */
 unsigned long long fabber_cuda_launch_count(void);
 
+/* Accuracy probe: fast[i] = the kernels' table-based exp(x[i]) (csrc/vb_exp.cuh, valid for |x| < 708),
+ * ref[i] = the CUDA library's exp(x[i]). Device pointers. */
+int fabber_cuda_exp_probe(const double *x, double *fast, double *ref, int n, void *stream);
+
 /* sizeof() of the two structs above as compiled, so language bindings can verify their mirror. */
 int fabber_cuda_sizeof_problem(void);
 int fabber_cuda_sizeof_buffers(void);
