@@ -65,7 +65,7 @@ FAB_DEV double ar_klj(const Stats<P> &M, const double (&d)[P], const double (&Si
 template <class Model, bool FAST>
 FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&p0)[Model::P],
     const double (&pp)[Model::P], const double (&pn)[Model::P], const double (&rden)[Model::P],
-    ArStats<Model::P> &S, bool &bad_g, bool &bad_j)
+    ArStats<Model::P> &S, bool &bad_g, bool &bad_j, volatile double *first)
 {
     constexpr int P = Model::P;
     const float *yp = a.data + v;
@@ -104,10 +104,11 @@ FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, in
         }
         if (t == 0)
         {
+            /* the first sample is only needed after the loop: parked in shared memory, not in registers */
 #pragma unroll
             for (int i = 0; i < P; i++)
-                S.Jf[i] = J[i];
-            S.rf = r;
+                first[i * VB_BLOCK] = J[i];
+            first[P * VB_BLOCK] = r;
         }
 #pragma unroll
         for (int i = 0; i < P; i++)
@@ -116,13 +117,17 @@ FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     }
 #pragma unroll
     for (int i = 0; i < P; i++)
+    {
         S.Jl[i] = Jprev[i];
+        S.Jf[i] = first[i * VB_BLOCK];
+    }
     S.rl = rprev;
+    S.rf = first[P * VB_BLOCK];
 }
 
 template <class Model>
 FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&c)[Model::P],
-    ArStats<Model::P> &S)
+    ArStats<Model::P> &S, volatile double *first)
 {
     constexpr int P = Model::P;
     double p0[P], pp[P], pn[P], rden[P];
@@ -145,9 +150,9 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     S.S1.zero();
     bool bad_g = false, bad_j = false;
     if (Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn))
-        recentre_loop_ar<Model, true>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop_ar<Model, true>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j, first);
     else
-        recentre_loop_ar<Model, false>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop_ar<Model, false>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j, first);
     return bad_g ? FABBER_VOX_NONFINITE_OFFSET : (bad_j ? FABBER_VOX_NONFINITE_JACOBIAN : 0);
 }
 
@@ -167,7 +172,7 @@ template <class Model> struct ArVoxel
     /* alpha marginal (Ar1cMatrixCache::Update :197-222): Q = M00 + qa M10 + qcp M20 */
     double qa, qcp;
 
-    static constexpr int STASH_DOUBLES = 3 * P + 2 * NT + 1 + 2 + 2 + 3 + 2;
+    static constexpr int STASH_DOUBLES = 3 * P + 2 * NT + 1 + 2 + 2 + 3 + 2 + (P + 1); /* + first sample */
     static constexpr int SNAP_DOUBLES = 3 * P + NT + 2 + 2 + 3 + 2;
 
     template <bool WITH_SIG> FAB_DEV void put(volatile double *s) const
@@ -373,8 +378,11 @@ template <class Model> struct ArVoxel
     }
 };
 
+#ifndef FAB_AR_MIN_BLOCKS
+#define FAB_AR_MIN_BLOCKS FAB_MIN_BLOCKS
+#endif
 template <class Model>
-__global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_ar_kernel(const __grid_constant__ VbArgs a)
+__global__ void __launch_bounds__(VB_BLOCK, FAB_AR_MIN_BLOCKS) vb_voxelwise_ar_kernel(const __grid_constant__ VbArgs a)
 {
     constexpr int P = Model::P;
     constexpr int NT = NTri<P>::value;
@@ -488,7 +496,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_ar_kern
         for (int i = 0; i < P; i++)
             c[i] = X.m[i];
         X.template put<true>(park);
-        const int err = recentre_stats_ar<Model>(a, mc, v, c, S);
+        const int err = recentre_stats_ar<Model>(a, mc, v, c, S, park + (Vox::STASH_DOUBLES - (P + 1)) * VB_BLOCK);
         X.template get<true>(park);
         if (phase == PH_SETUP)
         {
