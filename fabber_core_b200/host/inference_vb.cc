@@ -541,10 +541,14 @@ void Vb::SaveResults(FabberRunData &rundata)
         want(&out.zstat, P, per_param("zstat_"), 1);
     if (rundata.GetBool("save-var"))
         want(&out.var, P, per_param("var_"), 1);
+    /* Quirk kept: Ar1cNoiseModel::NumParams() returns nPhis (noisemodel_ar.cc:362-365) although its MVN
+     * block is (alpha1, alpha2, phi), so the reference's noise_means / noise_stdevs hold ONE volume for AR
+     * noise - the first element of that block, i.e. alpha1 (inference_vb.cc:982-988). */
+    const int noise_rows = m_ar ? 1 : m_noise_params;
     if (rundata.GetBool("save-noise-mean") && m_noise_params > 0)
-        want(&out.noise_mean, m_noise_params, std::vector<std::string>(1, "noise_means"), m_noise_params);
+        want(&out.noise_mean, m_noise_params, std::vector<std::string>(1, "noise_means"), noise_rows);
     if (rundata.GetBool("save-noise-std") && m_noise_params > 0)
-        want(&out.noise_std, m_noise_params, std::vector<std::string>(1, "noise_stdevs"), m_noise_params);
+        want(&out.noise_std, m_noise_params, std::vector<std::string>(1, "noise_stdevs"), noise_rows);
     if (rundata.GetBool("save-mvn"))
     {
         const int rows = NP_all * (NP_all + 1) / 2 + NP_all + 1; /* MVNDist::Save, dist_mvn.cc:377-433 */
