@@ -377,9 +377,15 @@ void FabberRunData::GetVoxelDataArray(const std::string &key, float *data)
     const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
     const size_t N = m_voxel_index.size();
     const std::vector<int> &index = m_voxel_index;
-    if (N != n_grid)
-        parallel_for((size_t)vd.rows * n_grid, [&](size_t b, size_t e) { memset(data + b, 0, (e - b) * sizeof(float)); },
+    if (N == n_grid)
+    {
+        /* full mask: the stored layout IS the caller's layout */
+        parallel_for((size_t)vd.rows * N, [&](size_t b, size_t e) { memcpy(data + b, vd.f + b, (e - b) * sizeof(float)); },
             (size_t)1 << 20);
+        return;
+    }
+    parallel_for((size_t)vd.rows * n_grid, [&](size_t b, size_t e) { memset(data + b, 0, (e - b) * sizeof(float)); },
+        (size_t)1 << 20);
     parallel_for((size_t)vd.rows * N, [&](size_t b, size_t e) {
         for (size_t i = b; i < e; i++)
         {

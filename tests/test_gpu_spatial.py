@@ -136,3 +136,53 @@ def test_spatial_rejects_unordered_coords():
     spec.prob.nx, spec.prob.ny, spec.prob.nz = nx, ny, nz
     with pytest.raises(device.CudaError):
         device.run(spec, y, spatial=True, coords=coords)
+
+
+def test_c5_full_size_ak_reduction():
+    """BASELINE configs[4] at a single-GPU size (128^3 x 96, full mask): the aK update is a global
+    reduction over every voxel and its neighbours (priors.cc:233-343). Re-derive it in numpy from the
+    posterior left by a 1-iteration run and compare with the aK a 2-iteration run used next."""
+    import torch
+
+    side = 128
+    n = side ** 3
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=1005, device="cuda", smooth_shape=(side, side, side))
+    idx = torch.arange(n, device="cuda")
+    coords = torch.stack([idx % side, (idx // side) % side, idx // (side * side)]).to(torch.int32).contiguous()
+
+    def run(max_it):
+        kw = dict(C5)
+        kw.pop("model")
+        spec = abi.ProblemSpec("exp", 96, prior_types=list("MMMM"), max_iterations=max_it, **kw)
+        spec.prob.nx = spec.prob.ny = spec.prob.nz = side
+        r = device.VbRun(spec, n, spatial=True)
+        r.set_data_device(y.data_ptr())
+        r.buf.coords = coords.data_ptr()
+        assert r.launch(torch.cuda.current_stream().cuda_stream) == 0
+        out = r.results()
+        r.close()
+        return out
+
+    one, two = run(1), run(2)
+    assert np.all(one["status"] == 0) and np.all(two["status"] == 0)
+    q1, q2 = 10.0, 1.0
+    for k in range(4):
+        w = one["mean"][k].reshape(side, side, side)          # [z][y][x]
+        sig = one["cov"][tri(k, k)].reshape(side, side, side)
+        nn = np.zeros_like(w)
+        swk = np.zeros_like(w)
+        for axis in range(3):
+            for shift in (1, -1):
+                nb = np.roll(w, shift, axis=axis)
+                valid = np.ones_like(w, dtype=bool)
+                sl = [slice(None)] * 3
+                sl[axis] = 0 if shift == 1 else side - 1
+                valid[tuple(sl)] = False
+                nn += valid
+                swk += np.where(valid, w - nb, 0.0)
+        trace_term = np.sum(sig * (nn + 1e-8))
+        term2 = np.sum(swk * w)
+        expect = (n * 0.5 + q2) / (0.5 * trace_term + 0.5 * term2 + 1 / q1)
+        got = two["spatial_ak"][1, k]
+        assert abs(got - expect) / expect < 1e-9, (k, got, expect)
+    assert np.all(two["spatial_ak"][0] == 1e-8)   # SpatialPrior::m_aK initial value (priors.cc:185)

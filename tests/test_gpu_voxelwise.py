@@ -229,3 +229,46 @@ def test_biexp_ar1():
     y = synth.biexp_volume(600, 96, 0.02, 0.02, seed=21).numpy()
     gpu, ref, probes = both(dict(C3, noise="ar", need_f=True, convergence="pointzeroone"), y)
     compare(gpu, ref, 4, probes, label="biexp AR1")
+
+
+def _full_size_sample_check(spec_factory, y, P, label, stride):
+    """Fit of voxel i depends on voxel i only: a strided sample re-run as its own small volume must
+    reproduce the big run bit for bit, and that sample must match the oracle."""
+    n = y.shape[1]
+    run = device.VbRun(spec_factory(), n)
+    run.set_data_device(y.data_ptr())
+    assert run.launch(torch.cuda.current_stream().cuda_stream) == 0
+    torch.cuda.synchronize()
+    big = run.results()
+    run.close()
+    assert np.all(big["status"] == 0), np.unique(big["status"], return_counts=True)
+    pick = np.arange(0, n, stride)
+    ys = y[:, torch.as_tensor(pick, device="cuda")].cpu().numpy()
+    small = device.run(spec_factory(), ys)
+    for k in ("mean", "cov", "noise", "iterations", "free_energy"):
+        assert np.array_equal(small[k], big[k][..., pick]), k
+    ref = oracle.run(spec_factory(), ys)
+    probes = [oracle.run(spec_factory(), ys, variant=vr) for vr in ("fma", "ulp")]
+    compare(small, ref, P, probes, label=label)
+    return big
+
+
+def test_full_size_properties_c3():
+    """BASELINE configs[2] at full size: biexp, LM, 256^3 x 96 (6.4 GB of series resident in HBM)."""
+    n = 256 ** 3
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=1003, device="cuda")
+    mk = lambda: abi.ProblemSpec("exp", 96, num_exps=2, dt=0.02, convergence="lm", need_f=True,
+                                 param_overrides={"r2": {"mean": 6.0}})
+    big = _full_size_sample_check(mk, y, 4, "C3 full-size sample", 16411)
+    assert 1 <= big["iterations"].min() and big["iterations"].max() <= 140
+    # truth recovered on average: amp1 ~ U(0.5, 1), r1 ~ U(0.8, 1)
+    assert abs(np.mean(np.exp(big["mean"][0])) - 0.75) < 0.02 and abs(np.mean(np.exp(big["mean"][1])) - 0.9) < 0.03
+
+
+def test_full_size_properties_c4():
+    """BASELINE configs[3]: linear model, AR(1) noise, 256^3 x 200 over 8 GPUs = 2.1 M voxels per GPU."""
+    n = 256 ** 3 // 8
+    y = synth.linear_ar_volume(n, 200, 0.3, seed=1004, device="cuda")
+    mk = lambda: abi.ProblemSpec("linear", 200, design=synth.ar_design(200), noise="ar", need_f=True)
+    big = _full_size_sample_check(mk, y, 4, "C4 per-GPU-size sample", 2053)
+    assert abs(np.median(big["noise"][2]) - 0.3) < 0.02   # AR coefficient recovered
