@@ -8,6 +8,7 @@
  */
 #include <cub/cub.cuh>
 
+#include <algorithm>
 #include <atomic>
 #include <climits>
 #include <cstdio>
@@ -151,6 +152,30 @@ __global__ void rank_kernel(const int *order, int N, int *rank)
     if (i < N)
         rank[order[i]] = i;
 }
+/* z-slab mode: ghost voxels carry FABBER_VOX_GHOST so every update kernel skips them */
+__global__ void mark_ghosts_kernel(const unsigned char *ghost, const int *order, int N, int *status_p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && ghost[order[i]])
+        status_p[i] = FABBER_VOX_GHOST;
+}
+/* halo buffers: buf[k][i] <-> mean_p[k][rank[idx[i]]] */
+template <bool PACK>
+__global__ void halo_kernel(double *mean_p, const int *idx, const int *rank, int n, int P, int N, double *buf)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n)
+        return;
+    const size_t pos = (size_t)rank[idx[i]];
+    for (int k = 0; k < P; k++)
+    {
+        if (PACK)
+            buf[(size_t)k * n + i] = mean_p[(size_t)k * N + pos];
+        else
+            mean_p[(size_t)k * N + pos] = buf[(size_t)k * n + i];
+    }
+}
+
 /* neighbour table in permuted numbering: nnp[j][pos] = rank[nn[j][order[pos]]] */
 __global__ void renumber_neighbours_kernel(const int *nn, const int *order, const int *rank, int N, int *nnp)
 {
@@ -653,6 +678,12 @@ int fabber_cuda_vb_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cu
 
 int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream)
 {
+    return fabber_cuda_vb_spatial_slab(prob, buf, nullptr, stream);
+}
+
+int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
+    const fabber_cuda_slab *slab, void *stream)
+{
     cudaStream_t st = (cudaStream_t)stream;
     SpArgs sp;
     memset(&sp, 0, sizeof(sp));
@@ -713,6 +744,34 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
     sp.ak_hist = sc.get<double>((size_t)(max_it + 1) * P);
     sp.ak_partial = sc.get<double>((size_t)SP_AK_BLOCKS * 2 * P);
     sp.fprior_last = sc.get<double>(1);
+    sp.ak_sums = sc.get<double>(2 * P);
+    sp.n_global = slab ? slab->n_global_voxels : N;
+    sp.ak_phase = 0;
+    double *halo_send_lo = nullptr, *halo_send_hi = nullptr, *halo_recv_lo = nullptr, *halo_recv_hi = nullptr;
+    double *fwd_send_buf = nullptr, *fwd_recv_buf = nullptr;
+    if (slab)
+    {
+        if (!slab->ghost || !slab->allreduce_sum || !slab->exchange || !slab->forward || slab->n_global_voxels < N
+            || slab->n_blocks < 1 || slab->block_planes < 1 || slab->world < 1 || slab->rank < 0
+            || slab->rank >= slab->world || !slab->fwd_send_start || !slab->fwd_recv_start)
+            return fail(FABBER_CUDA_ERR_INVALID, "incomplete slab description");
+        halo_send_lo = sc.get<double>((size_t)P * slab->n_send_lo);
+        halo_send_hi = sc.get<double>((size_t)P * slab->n_send_hi);
+        halo_recv_lo = sc.get<double>((size_t)P * slab->n_recv_lo);
+        halo_recv_hi = sc.get<double>((size_t)P * slab->n_recv_hi);
+        if (!halo_send_lo || !halo_send_hi || !halo_recv_lo || !halo_recv_hi || !sp.ak_sums)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        size_t max_fwd = 1;
+        for (int b = 0; b < slab->n_blocks; b++)
+        {
+            max_fwd = std::max<size_t>(max_fwd, slab->fwd_send_start[b + 1] - slab->fwd_send_start[b]);
+            max_fwd = std::max<size_t>(max_fwd, slab->fwd_recv_start[b + 1] - slab->fwd_recv_start[b]);
+        }
+        fwd_send_buf = sc.get<double>((size_t)P * max_fwd);
+        fwd_recv_buf = sc.get<double>((size_t)P * max_fwd);
+        if (!fwd_send_buf || !fwd_recv_buf)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+    }
     /* the run's inputs and outputs in hyper-plane-major voxel order (see below) */
     const int H = sp.v.f_history_len;
     float *y_p = sc.get<float>((size_t)prob->n_times * N);
@@ -848,6 +907,11 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
     } while (0)
     sp.it = 0;
     FAB_SP_LAUNCH(sp_setup);
+    if (slab)
+    {
+        mark_ghosts_kernel<<<gridN, 256, 0, st>>>(slab->ghost, order, N, status_p);
+        count_launch();
+    }
     for (int it = 0; it < max_it; it++)
     {
         sp.it = it;
@@ -856,10 +920,79 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
         sp.ak_update = (any_spatial && (it > 0 || prob->update_first_iter)) ? 1 : 0;
         if (sp.ak_update)
             FAB_SP_LAUNCH(sp_ak_partial);
+        if (slab && sp.ak_update)
+        {
+            /* local sums -> all-reduce over the slabs -> aK (identical on every rank) */
+            sp.ak_phase = 1;
+            FAB_SP_LAUNCH(sp_ak_final);
+            if (slab->allreduce_sum(slab->user, sp.ak_sums, 2 * P, st) != 0)
+                return fail(FABBER_CUDA_ERR_CUDA, "slab all-reduce callback failed");
+            sp.ak_phase = 2;
+        }
         FAB_SP_LAUNCH(sp_ak_final);
+        sp.ak_phase = 0;
         FAB_SP_LAUNCH(sp_theta);
-        if (any_coupled)
+        sp.plane_first = 0;
+        sp.plane_last = sp.n_planes;
+        if (any_coupled && !slab)
             FAB_SP_LAUNCH(sp_sweep);
+        if (any_coupled && slab)
+        {
+            /* pipelined exact sweep over the slabs: block b = global planes [b B, (b+1) B) */
+            const int B = slab->block_planes;
+            for (int step = 0; step < slab->n_blocks + slab->world - 1; step++)
+            {
+                const int b = step - slab->rank;
+                int n_send = 0, n_recv = 0;
+                if (b >= 0 && b < slab->n_blocks)
+                {
+                    sp.plane_first = std::min(std::max(b * B - slab->plane_offset, 0), sp.n_planes);
+                    sp.plane_last = std::min(std::max((b + 1) * B - slab->plane_offset, 0), sp.n_planes);
+                    if (sp.plane_last > sp.plane_first)
+                        FAB_SP_LAUNCH(sp_sweep);
+                    n_send = slab->fwd_send_start[b + 1] - slab->fwd_send_start[b];
+                    if (n_send > 0)
+                    {
+                        halo_kernel<true><<<(n_send + 255) / 256, 256, 0, st>>>(
+                            mean_p, slab->fwd_send + slab->fwd_send_start[b], rank, n_send, P, N, fwd_send_buf);
+                        count_launch();
+                    }
+                }
+                const int b_in = b + 1; /* the block this rank sweeps next: its lower ghosts arrive now */
+                if (b_in >= 0 && b_in < slab->n_blocks)
+                    n_recv = slab->fwd_recv_start[b_in + 1] - slab->fwd_recv_start[b_in];
+                if (slab->forward(slab->user, step, fwd_send_buf, n_send, fwd_recv_buf, n_recv, st) != 0)
+                    return fail(FABBER_CUDA_ERR_CUDA, "slab forward callback failed");
+                if (n_recv > 0)
+                {
+                    halo_kernel<false><<<(n_recv + 255) / 256, 256, 0, st>>>(
+                        mean_p, slab->fwd_recv + slab->fwd_recv_start[b_in], rank, n_recv, P, N, fwd_recv_buf);
+                    count_launch();
+                }
+            }
+        }
+        if (slab)
+        {
+            /* halo exchange of the posterior means: own boundary planes out, ghost planes in */
+            if (slab->n_send_lo > 0)
+                halo_kernel<true><<<(slab->n_send_lo + 255) / 256, 256, 0, st>>>(
+                    mean_p, slab->send_lo, rank, slab->n_send_lo, P, N, halo_send_lo);
+            if (slab->n_send_hi > 0)
+                halo_kernel<true><<<(slab->n_send_hi + 255) / 256, 256, 0, st>>>(
+                    mean_p, slab->send_hi, rank, slab->n_send_hi, P, N, halo_send_hi);
+            count_launch();
+            if (slab->exchange(slab->user, halo_send_lo, slab->n_send_lo, halo_send_hi, slab->n_send_hi, halo_recv_lo,
+                    slab->n_recv_lo, halo_recv_hi, slab->n_recv_hi, st)
+                != 0)
+                return fail(FABBER_CUDA_ERR_CUDA, "slab halo-exchange callback failed");
+            if (slab->n_recv_lo > 0)
+                halo_kernel<false><<<(slab->n_recv_lo + 255) / 256, 256, 0, st>>>(
+                    mean_p, slab->recv_lo, rank, slab->n_recv_lo, P, N, halo_recv_lo);
+            if (slab->n_recv_hi > 0)
+                halo_kernel<false><<<(slab->n_recv_hi + 255) / 256, 256, 0, st>>>(
+                    mean_p, slab->recv_hi, rank, slab->n_recv_hi, P, N, halo_recv_hi);
+            count_launch();
+        }
         FAB_SP_LAUNCH(sp_noise);
     }
     sp.it = max_it;

@@ -53,12 +53,17 @@ struct SpArgs
     const int *order;    /* original voxel index of each (plane-major) position */
     const int *plane_starts; /* [n_planes + 1] offsets into order (device) */
     int n_planes;
+    int plane_first, plane_last; /* sp_sweep_kernel walks planes [plane_first, plane_last) */
     int ak_blocks;
     int it;
     int spatial_dims;
     int update_first_iter;
     int any_coupled; /* any 'M' / 'm' parameter */
     int ak_update;   /* sp_ak_final_kernel: recompute aK (else only record the history row) */
+    int ak_phase;    /* 0: partials -> sums and aK in one go (one GPU); 1: partials -> ak_sums only;
+                        2: aK from ak_sums (after the host all-reduced them across z-slabs) */
+    double *ak_sums; /* [2][P] */
+    int n_global;    /* voxels of the WHOLE volume (hK = N/2 + q2, priors.cc:313); == v.N on one GPU */
     double q1, q2, speed;
 };
 
@@ -224,7 +229,13 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
     const VbArgs &a = s.v;
     __shared__ double red[256];
     __shared__ double sums[2 * P];
-    if (s.ak_update)
+    if (s.ak_update && s.ak_phase == 2)
+    {
+        if (threadIdx.x < 2 * P)
+            sums[threadIdx.x] = s.ak_sums[threadIdx.x];
+        __syncthreads();
+    }
+    if (s.ak_update && s.ak_phase != 2)
         for (int q = 0; q < 2 * P; q++)
         {
             double x = 0.0;
@@ -242,6 +253,13 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
                 sums[q] = red[0];
             __syncthreads();
         }
+    if (s.ak_phase == 1)
+    {
+        /* z-slab mode: hand the local sums to the host, which all-reduces them over the slabs */
+        if (s.ak_update && threadIdx.x < 2 * P)
+            s.ak_sums[threadIdx.x] = sums[threadIdx.x];
+        return;
+    }
     const int k = threadIdx.x;
     if (k >= P)
         return;
@@ -250,7 +268,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
     {
         const double trace_term = sums[k], term2 = sums[P + k];
         const double gk = 1 / (0.5 * trace_term + 0.5 * term2 + 1 / s.q1);
-        const double hK = (a.N * 0.5 + s.q2);
+        const double hK = (s.n_global * 0.5 + s.q2);
         double aK = gk * hK;
         if (aK < 1e-50)
             aK = 1e-50;
@@ -474,15 +492,16 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
     const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
     SweepVoxel<P> cur;
     bool have = false;
+    if (s.plane_first < s.plane_last)
     {
-        const int b = s.plane_starts[0], e = s.plane_starts[1];
+        const int b = s.plane_starts[s.plane_first], e = s.plane_starts[s.plane_first + 1];
         if (b + tid < e)
         {
             cur.load_static(s, b + tid);
             have = true;
         }
     }
-    for (int h = 0; h < s.n_planes; h++)
+    for (int h = s.plane_first; h < s.plane_last; h++)
     {
         const int b = s.plane_starts[h], e = s.plane_starts[h + 1];
         if (have)
@@ -494,7 +513,7 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
             extra.finish(s);
         }
         have = false;
-        if (h + 1 < s.n_planes)
+        if (h + 1 < s.plane_last)
         {
             const int b2 = e, e2 = s.plane_starts[h + 2];
             if (b2 + tid < e2)

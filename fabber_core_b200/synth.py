@@ -34,7 +34,8 @@ def poly_volume(n_voxels, n_times=64, degree=3, seed=1002, device="cpu"):
     return y
 
 
-def biexp_volume(n_voxels, n_times=96, dt=0.02, noise=0.02, seed=1003, device="cpu", smooth_shape=None):
+def biexp_volume(n_voxels, n_times=96, dt=0.02, noise=0.02, seed=1003, device="cpu", smooth_shape=None,
+                 voxel_offset=0):
     """C3 (and C5 with smooth_shape=(nx,ny,nz)): y = amp1 exp(-r1 t) + 0.5 exp(-6 t) + N(0, noise^2).
 
     Truth as in the reference's examples/test_biexp.py:17-22: amp1~U(0.5,1), r1~U(0.8,1), amp2=0.5, r2=6.
@@ -45,8 +46,9 @@ def biexp_volume(n_voxels, n_times=96, dt=0.02, noise=0.02, seed=1003, device="c
         r1 = 0.8 + 0.2 * torch.rand(n_voxels, generator=g, device=device, dtype=torch.float64)
     else:
         nx, ny, nz = smooth_shape
-        assert nx * ny * nz == n_voxels
-        idx = torch.arange(n_voxels, device=device)
+        assert nx * ny * nz >= n_voxels + voxel_offset
+        # voxel_offset: this block starts at that voxel of the (nx, ny, nz) volume - z-slabs of a larger volume
+        idx = torch.arange(n_voxels, device=device) + voxel_offset
         x = (idx % nx).to(torch.float64)
         yy = ((idx // nx) % ny).to(torch.float64)
         z = (idx // (nx * ny)).to(torch.float64)

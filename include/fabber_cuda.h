@@ -187,6 +187,49 @@ int fabber_cuda_vb_voxelwise(
 int fabber_cuda_vb_spatial(
     const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream);
 
+/* Spatial VB on one z-slab of a volume that is partitioned over several GPUs (one process per GPU).
+ *
+ * The slab's voxel list holds its own voxels plus the GHOST planes just below and above it (their series
+ * included, so their initial posterior is computed locally exactly as their owner computes it). Ghost
+ * voxels are never updated locally; after every sweep the library packs the means of the slab's own
+ * boundary planes, calls `exchange` and unpacks what the neighbours sent into the ghosts. The two global
+ * sums of CalculateaK (priors.cc:233-343) go through `allreduce_sum`. Both callbacks receive DEVICE
+ * pointers and the stream the work is queued on; the host implements them with its communication layer
+ * (NCCL via torch.distributed in this repo) and returns 0 on success.
+ *
+ * The ordered sweep stays EXACT across slabs. The reference's sequential sweep means a voxel on the bottom
+ * plane of slab r must see THIS iteration's value of the voxel below it (top plane of slab r-1), and last
+ * iteration's value of the voxel above the slab's top plane. The hyper-planes x+y+z = H (global z) are cut
+ * into `n_blocks` blocks of `block_planes` planes; at step s rank r sweeps block s - r, then `forward`s the
+ * freshly updated means of its top plane that lie in that block to rank r+1, which sweeps the same block
+ * one step later - a software pipeline with one block of skew, n_blocks + world - 1 steps per iteration.
+ * After the sweep `exchange` refreshes all ghosts (the downward direction must wait for the sweep to end). */
+#define FABBER_VOX_GHOST 0x200 /* status of a ghost voxel in a slab run */
+typedef struct fabber_cuda_slab
+{
+    int n_global_voxels;        /* voxels of the whole volume (hK = N/2 + q2) */
+    const unsigned char *ghost; /* DEVICE [N]: 1 = ghost voxel */
+    /* DEVICE index lists (positions in this slab's voxel list): own boundary planes to send down / up,
+     * ghost planes that receive from below / above. Counts may be 0 at the ends of the volume. */
+    const int *send_lo, *send_hi, *recv_lo, *recv_hi;
+    int n_send_lo, n_send_hi, n_recv_lo, n_recv_hi;
+    /* pipelined sweep: global plane H = local plane + plane_offset (plane_offset = z of the first local
+     * plane). fwd_send / fwd_recv: positions (this slab's voxel list) of the own top plane / the lower ghost
+     * plane, grouped by block: block b is [fwd_*_start[b], fwd_*_start[b+1]). DEVICE lists, HOST starts. */
+    int rank, world, n_blocks, block_planes, plane_offset;
+    const int *fwd_send, *fwd_recv;
+    const int *fwd_send_start, *fwd_recv_start; /* HOST [n_blocks + 1] */
+    void *user;
+    int (*allreduce_sum)(void *user, double *dev_values, int n, void *stream);
+    /* buffers are [P][count] doubles */
+    int (*exchange)(void *user, const double *send_lo, int n_send_lo, const double *send_hi, int n_send_hi,
+        double *recv_lo, int n_recv_lo, double *recv_hi, int n_recv_hi, void *stream);
+    /* step s of the pipelined sweep: send n_send values up to rank+1, receive n_recv from rank-1 */
+    int (*forward)(void *user, int step, const double *send, int n_send, double *recv, int n_recv, void *stream);
+} fabber_cuda_slab;
+int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
+    const fabber_cuda_slab *slab, void *stream);
+
 /* Scan status[] on the device; returns 0 if all OK, else the number of failed voxels and the
  * index / code of the first one (synchronises the stream). */
 int fabber_cuda_check_status(
