@@ -312,13 +312,14 @@ def oracle_throughput(w, threads, budget_s):
 
 def spatial_slab_bench(args, w, rank, local_rank, world, n_vox, metric, config):
     """C5 on several GPUs: ONE volume of side x side x (side * world) voxels partitioned into z-slabs, one
-    slab (plus ghost planes) per rank; halo exchange of posterior means and all-reduce of the aK sums every
-    iteration over NCCL (fabber_core_b200/spatial_mgpu.py). Weak scaling: side^3 own voxels per GPU."""
+    slab (plus ghost planes) per rank; per iteration an all-reduce of the aK sums, the block-pipelined ordered
+    sweep (forwarding of boundary means up the ranks) and a halo exchange, all over NCCL
+    (fabber_core_b200/spatial_mgpu.py). Weak scaling: side^3 own voxels per GPU."""
     import torch
     import torch.distributed as dist
 
     from fabber_core_b200 import device, synth
-    from fabber_core_b200.spatial_mgpu import SlabPlan, TorchDistComm, run_slab
+    from fabber_core_b200.spatial_mgpu import SlabPlan, SlabRun, TorchDistComm
 
     side = round(n_vox ** (1.0 / 3))
     assert side ** 3 == n_vox
@@ -328,49 +329,80 @@ def spatial_slab_bench(args, w, rank, local_rank, world, n_vox, metric, config):
                            smooth_shape=(side, side, side * world), voxel_offset=g0)
     L = device.lib()
     comm = TorchDistComm(rank, world, w["P"])
-    its_local = None
+    sr = SlabRun(make_spec(w, 0), plan, comm)
+    sr.set_data_device(y.data_ptr())
 
     def step():
-        spec = make_spec(w, 0)
-        out = run_slab(spec, y.data_ptr(), plan, comm, data_is_device_ptr=True)
-        return out
+        sr.launch()
 
-    for _ in range(max(args.warmup, 3) - 1):
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
         step()
-    out = step()
+    out = sr.results()
     its_local = int(out["iterations"].astype(np.int64).sum())
     n_bad = int(np.count_nonzero(out["status"]))
-    dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     launches0 = L.fabber_cuda_launch_count()
+    sampler = ClockSampler(local_rank)
+    time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.time()
     ev0.record()
     for _ in range(args.steps):
         step()
     ev1.record()
-    dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
+    clocks = sampler.stop(t0, time.time())
     launches = L.fabber_cuda_launch_count() - launches0
     t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
     its = torch.tensor([its_local], dtype=torch.float64, device="cuda")
     dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
     dist.all_reduce(its, op=dist.ReduceOp.SUM)
     value = float(its.item()) * args.steps / (float(t_ms.item()) * 1e-3)
+
+    # end to end: the slab's series from pinned host memory in, the owned voxels' results out, every step
+    host_y = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
+    host_y.copy_(y)
+    host_np = host_y.numpy()
+    e2e_steps = max(1, min(args.steps, 2))
+    sr.set_data(host_np)
+    sr.launch()
+    res = sr.results()
+    barrier()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        sr.set_data(host_np)
+        sr.launch()
+        res = sr.results()
+    barrier()
+    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = float(its.item()) * e2e_steps / float(e2e_s.item())
+    d2h = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
+    sr.close()
     if rank == 0:
         cfg = dict(config)
-        cfg["sharding"] = ("z-slabs of one %dx%dx%d volume, halo exchange of means + all-reduce of aK sums per "
-                           "iteration (NCCL); block-Jacobi across slab boundaries, exact inside a slab"
-                           % (side, side, side * world))
-        # value includes each step's download of the slab results to the host (run_slab returns host arrays)
+        cfg["sharding"] = ("z-slabs of one %dx%dx%d volume; per iteration: all-reduce of aK sums, ordered sweep "
+                           "pipelined across the slabs in %d blocks of %d hyper-planes, halo exchange (NCCL); "
+                           "result equals the one-GPU run" % (side, side, side * world, plan.n_blocks,
+                                                              plan.block_planes))
+        flop = algorithmic_flops(w) * float(its.item()) * args.steps / world   # per GPU
         print(json.dumps({
             "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": float(t_ms.item()) / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "e2e": {"value": value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": 0,
-                    "d2h_bytes_per_step": int(sum(v.nbytes for v in out.values() if isinstance(v, np.ndarray))),
-                    "path": "run_slab: results downloaded to host every step; series resident in HBM"},
-            "gpu_launches": int(launches), "bad_voxels": n_bad,
-            "clocks": {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["not sampled in the slab bench"]}}))
+            "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": int(host_y.nbytes),
+                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                    "path": "SlabRun: set_data (pinned host series) -> launch -> results (host arrays) on every "
+                            "rank; wall clock, max over ranks"},
+            "gpu_launches": int(launches), "bad_voxels": n_bad, "clocks": clocks,
+            "roofline": {"bound": "fp64", "achieved": flop / (float(t_ms.item()) * 1e-3) / 1e12, "unit": "TFLOP/s",
+                         "peak": None, "frac": None, "traffic": None,
+                         "note": "per GPU; the one-GPU line of the same workload carries the measured peak"}}))
     dist.destroy_process_group()
     return 0
 

@@ -141,21 +141,29 @@ class TorchDistComm(object):
     def __init__(self, rank, world, n_params):
         self.rank, self.world, self.P = rank, world, n_params
 
-    def allreduce(self, ptr, n, stream):
+    @staticmethod
+    def _fence(stream):
+        """torch.distributed orders its NCCL work behind torch's CURRENT stream. When the library runs on that
+        very stream (the default), stream order already is the dependency and the whole iteration loop stays
+        asynchronous; on any other stream fall back to a host synchronize either side of the collective."""
         import torch
+
+        if int(stream or 0) != int(torch.cuda.current_stream().cuda_stream):
+            torch.cuda.synchronize()
+
+    def allreduce(self, ptr, n, stream):
         import torch.distributed as dist
 
-        torch.cuda.synchronize()
+        self._fence(stream)
         t = _tensor(ptr, n)
         dist.all_reduce(t)
-        torch.cuda.synchronize()
+        self._fence(stream)
         return 0
 
     def exchange(self, send_lo, n_slo, send_hi, n_shi, recv_lo, n_rlo, recv_hi, n_rhi, stream):
-        import torch
         import torch.distributed as dist
 
-        torch.cuda.synchronize()
+        self._fence(stream)
         ops, keep = [], []
         P = self.P
         if n_slo:
@@ -173,17 +181,16 @@ class TorchDistComm(object):
         if ops:
             for req in dist.batch_isend_irecv(ops):
                 req.wait()
-        torch.cuda.synchronize()
+        self._fence(stream)
         return 0
 
 
     def forward(self, step, send, n_send, recv, n_recv, stream):
-        import torch
         import torch.distributed as dist
 
         if not n_send and not n_recv:
             return 0
-        torch.cuda.synchronize()
+        self._fence(stream)
         ops, keep = [], []
         if n_send:
             keep.append(_tensor(send, self.P * n_send))
@@ -193,7 +200,7 @@ class TorchDistComm(object):
             ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank - 1))
         for req in dist.batch_isend_irecv(ops):
             req.wait()
-        torch.cuda.synchronize()
+        self._fence(stream)
         return 0
 
 
@@ -258,86 +265,102 @@ class ThreadComm(object):
         return 0
 
 
-def run_slab(spec, data_local, plan, comm, data_is_device_ptr=False):
-    """Run one rank's slab. data_local: float32 [T][plan.n_local] (host array, or a device pointer when
-    data_is_device_ptr). Returns the result dict restricted to the voxels this rank owns."""
-    L = device.lib()
-    L.fabber_cuda_vb_spatial_slab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    L.fabber_cuda_vb_spatial_slab.restype = C.c_int
-    spec.prob.nx, spec.prob.ny, spec.prob.nz = plan.nx, plan.ny, plan.nz_local
-    run = device.VbRun(spec, plan.n_local, spatial=True)
-    keep = []
-    try:
-        if data_is_device_ptr:
-            run.set_data_device(data_local)
-        else:
-            run.set_data(data_local)
-        run.set_coords(plan.coords())
-        slab = Slab()
-        slab.n_global_voxels = plan.n_global
-        ghost = device.DeviceArray.from_host(plan.ghost_mask())
-        keep.append(ghost)
-        slab.ghost = ghost.ptr
-        for name, arr in zip(("send_lo", "send_hi", "recv_lo", "recv_hi"), plan.halo_lists()):
-            d = device.DeviceArray.from_host(arr if arr.size else np.zeros(1, dtype=np.int32))
-            keep.append(d)
-            setattr(slab, name, d.ptr)
-            setattr(slab, "n_" + name, int(arr.size))
+class SlabRun(object):
+    """One rank's slab, set up once and launched any number of times (device buffers, index lists and the
+    callback trampolines persist): `launch()` enqueues one whole spatial VB run, `results()` downloads the
+    voxels this rank owns."""
 
-        def _allreduce(user, ptr, n, stream):
-            try:
-                return comm.allreduce(ptr, n, stream)
-            except Exception:   # never let an exception cross the C boundary
-                import traceback
+    def __init__(self, spec, plan, comm):
+        L = device.lib()
+        L.fabber_cuda_vb_spatial_slab.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.fabber_cuda_vb_spatial_slab.restype = C.c_int
+        self.L, self.spec, self.plan, self.comm = L, spec, plan, comm
+        spec.prob.nx, spec.prob.ny, spec.prob.nz = plan.nx, plan.ny, plan.nz_local
+        spec.prob.n_voxels = plan.n_local
+        self.run = device.VbRun(spec, plan.n_local, spatial=True)
+        self.keep = []
+        try:
+            self.run.set_coords(plan.coords())
+            self.slab = slab = Slab()
+            slab.n_global_voxels = plan.n_global
+            slab.ghost = self._dev(plan.ghost_mask())
+            for name, arr in zip(("send_lo", "send_hi", "recv_lo", "recv_hi"), plan.halo_lists()):
+                setattr(slab, name, self._dev(arr))
+                setattr(slab, "n_" + name, int(arr.size))
+            slab.rank, slab.world = plan.rank, plan.world
+            slab.n_blocks, slab.block_planes, slab.plane_offset = plan.n_blocks, plan.block_planes, plan.zlo
+            fsend, fsend_start, frecv, frecv_start = plan.forward_lists()
+            slab.fwd_send, slab.fwd_recv = self._dev(fsend), self._dev(frecv)
+            self.starts = [(C.c_int * len(a))(*a.tolist()) for a in (fsend_start, frecv_start)]
+            slab.fwd_send_start = C.cast(self.starts[0], C.POINTER(C.c_int))
+            slab.fwd_recv_start = C.cast(self.starts[1], C.POINTER(C.c_int))
 
-                traceback.print_exc()
-                return -1
+            def guarded(fn):
+                def call(user, *a):
+                    try:
+                        return fn(*a)
+                    except Exception:   # never let an exception cross the C boundary
+                        import traceback
 
-        def _exchange(user, slo, n_slo, shi, n_shi, rlo, n_rlo, rhi, n_rhi, stream):
-            try:
-                return comm.exchange(slo, n_slo, shi, n_shi, rlo, n_rlo, rhi, n_rhi, stream)
-            except Exception:
-                import traceback
+                        traceback.print_exc()
+                        return -1
+                return call
 
-                traceback.print_exc()
-                return -1
+            slab.allreduce_sum = ALLREDUCE_FN(guarded(comm.allreduce))
+            slab.exchange = EXCHANGE_FN(guarded(comm.exchange))
+            slab.forward = FORWARD_FN(guarded(comm.forward))
+        except Exception:
+            self.close()
+            raise
 
-        def _forward(user, step, send, n_send, recv, n_recv, stream):
-            try:
-                return comm.forward(step, send, n_send, recv, n_recv, stream)
-            except Exception:
-                import traceback
+    def _dev(self, arr):
+        d = device.DeviceArray.from_host(arr if arr.size else np.zeros(1, dtype=arr.dtype))
+        self.keep.append(d)
+        return d.ptr
 
-                traceback.print_exc()
-                return -1
+    def set_data(self, data_local):
+        self.run.set_data(data_local)
 
-        slab.rank, slab.world = plan.rank, plan.world
-        slab.n_blocks, slab.block_planes, slab.plane_offset = plan.n_blocks, plan.block_planes, plan.zlo
-        fsend, fsend_start, frecv, frecv_start = plan.forward_lists()
-        for name, arr in (("fwd_send", fsend), ("fwd_recv", frecv)):
-            d = device.DeviceArray.from_host(arr if arr.size else np.zeros(1, dtype=np.int32))
-            keep.append(d)
-            setattr(slab, name, d.ptr)
-        starts = [(C.c_int * len(a))(*a.tolist()) for a in (fsend_start, frecv_start)]
-        keep_host = starts   # referenced until the call returns
-        slab.fwd_send_start = C.cast(starts[0], C.POINTER(C.c_int))
-        slab.fwd_recv_start = C.cast(starts[1], C.POINTER(C.c_int))
-        slab.allreduce_sum = ALLREDUCE_FN(_allreduce)
-        slab.exchange = EXCHANGE_FN(_exchange)
-        slab.forward = FORWARD_FN(_forward)
-        prob = spec.prob
-        prob.n_voxels = plan.n_local
-        rc = L.fabber_cuda_vb_spatial_slab(C.byref(prob), C.byref(run.buf), C.byref(slab), None)
+    def set_data_device(self, ptr):
+        self.run.set_data_device(ptr)
+
+    def launch(self, stream=None):
+        """enqueue one run on `stream` (None: the default stream, which is also torch's default current stream,
+        so TorchDistComm's NCCL calls order themselves behind the kernels without a host synchronize)"""
+        rc = self.L.fabber_cuda_vb_spatial_slab(C.byref(self.spec.prob), C.byref(self.run.buf), C.byref(self.slab),
+                                                stream)
         if rc not in (abi.OK, abi.ERR_BAD_VOXEL):
             raise device.CudaError("slab VB failed (%d): %s" % (rc, device.last_error()))
-        run.sync()
-        out = run.results()
-        own = plan.own_slice()
-        res = {k: (v[..., own] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[-1] == plan.n_local else v)
-               for k, v in out.items()}
+        return rc
+
+    def results(self):
+        self.run.sync()
+        out = self.run.results()
+        own, n = self.plan.own_slice(), self.plan.n_local
+        return {k: (v[..., own] if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[-1] == n else v)
+                for k, v in out.items()}
+
+    def close(self):
+        if self.run is not None:
+            self.run.close()
+            self.run = None
+        for d in self.keep:
+            d.close()
+        self.keep = []
+
+
+def run_slab(spec, data_local, plan, comm, data_is_device_ptr=False):
+    """Run one rank's slab once. data_local: float32 [T][plan.n_local] (host array, or a device pointer when
+    data_is_device_ptr). Returns the result dict restricted to the voxels this rank owns."""
+    sr = SlabRun(spec, plan, comm)
+    try:
+        if data_is_device_ptr:
+            sr.set_data_device(data_local)
+        else:
+            sr.set_data(data_local)
+        rc = sr.launch()
+        res = sr.results()
         res["rc"] = rc
         return res
     finally:
-        run.close()
-        for d in keep:
-            d.close()
+        sr.close()
