@@ -465,6 +465,7 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
     a.init_mean = buf->init_mean;
     a.init_cov = buf->init_cov;
     a.init_noise = buf->init_noise;
+    a.lock_centre = buf->lock_centre;
     a.mean = buf->mean;
     a.cov = buf->cov;
     a.noise = buf->noise;
@@ -879,6 +880,14 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
         permute_rows<double, true>(sp.v.init_cov, ic, order, NT, N, st);
         sp.v.init_mean = im;
         sp.v.init_cov = ic;
+    }
+    if (sp.v.lock_centre)
+    {
+        double *lc = sc.get<double>((size_t)P * N);
+        if (!lc)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        permute_rows<double, true>(sp.v.lock_centre, lc, order, P, N, st);
+        sp.v.lock_centre = lc;
     }
     if (sp.v.init_noise)
     {

@@ -116,14 +116,18 @@ template <class Model> __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCK
         }
     }
     Stats<P> S[1];
-    const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, m, S);
+    double c[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        c[i] = a.lock_centre ? a.lock_centre[i * N + v] : m[i]; /* inference_vb.cc:227-236 */
+    const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, c, S);
     if (err)
         status = err | FABBER_VOX_SETUP_FLAG;
 #pragma unroll
     for (int i = 0; i < P; i++)
     {
         a.mean[i * N + v] = m[i];
-        s.centre[i * N + v] = m[i];
+        s.centre[i * N + v] = c[i];
         s.m0[i * N + v] = 0.0;
         s.L0[i * N + v] = 1.0;
         s.stats[(NT + i) * N + v] = S[0].b[i];
@@ -575,38 +579,43 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_noise_kernel(cons
         nc = ((double)a.n_per_phi[0] - 1) * 0.5 + a.noise_prior_c[0];
         if (a.locked_noise_stdev > 0)
             nb = 1 / nc / a.locked_noise_stdev / a.locked_noise_stdev;
-    }
-    /* park what F needs; the pass over the time-series only needs the new centre */
-    {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < NT; i++)
-            park[(k++) * VB_BLOCK] = Sig[i];
-    }
-    const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, m, S);
-    {
-        int k = 0;
-#pragma unroll
-        for (int i = 0; i < NT; i++)
-            Sig[i] = park[(k++) * VB_BLOCK];
+        if (a.lock_centre)
+            S[0].rr = kk; /* no re-centring below: F's k'Qk is taken about the locked centre */
     }
     a.noise[0 * N + v] = nb;
     a.noise[1 * N + v] = nc;
-    if (err)
+    if (!a.lock_centre) /* inference_vb.cc:695 */
     {
-        a.status[v] = err;
-        return;
-    }
+        /* park what F needs; the pass over the time-series only needs the new centre */
+        {
+            int k = 0;
 #pragma unroll
-    for (int i = 0; i < P; i++)
-    {
-        s.centre[i * N + v] = m[i];
-        s.stats[(NT + i) * N + v] = S[0].b[i];
-    }
+            for (int i = 0; i < NT; i++)
+                park[(k++) * VB_BLOCK] = Sig[i];
+        }
+        const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, m, S);
+        {
+            int k = 0;
 #pragma unroll
-    for (int i = 0; i < NT; i++)
-        s.stats[i * N + v] = S[0].A[i];
-    s.stats[(NT + P) * N + v] = S[0].rr;
+            for (int i = 0; i < NT; i++)
+                Sig[i] = park[(k++) * VB_BLOCK];
+        }
+        if (err)
+        {
+            a.status[v] = err;
+            return;
+        }
+#pragma unroll
+        for (int i = 0; i < P; i++)
+        {
+            s.centre[i * N + v] = m[i];
+            s.stats[(NT + i) * N + v] = S[0].b[i];
+        }
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+            s.stats[i * N + v] = S[0].A[i];
+        s.stats[(NT + P) * N + v] = S[0].rr;
+    }
     if (a.iterations)
         a.iterations[v] = s.it + 1;
     if (a.need_f)

@@ -50,6 +50,7 @@ struct VbArgs
     double fchange;
     const double *image_prior[FABBER_CUDA_MAX_PARAMS];
     const double *init_mean, *init_cov, *init_noise;
+    const double *lock_centre; /* spatial only */
     double *mean, *cov, *noise, *free_energy, *f_history;
     int *iterations, *status;
     const double *fit_mean; /* model_fit_kernel: [P][N] Fabber-space means in, */

@@ -91,6 +91,7 @@ class VbBuffers(C.Structure):
         ("init_mean", C.c_void_p),
         ("init_cov", C.c_void_p),
         ("init_noise", C.c_void_p),
+        ("lock_centre", C.c_void_p),
         ("coords", C.c_void_p),
         ("mean", C.c_void_p),
         ("cov", C.c_void_p),

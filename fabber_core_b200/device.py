@@ -151,8 +151,8 @@ class VbRun(object):
         self.inputs["image%d" % k] = d
         self.buf.image_prior[k] = d.ptr
 
-    def set_initial(self, mean=None, cov=None, noise=None):
-        for name, arr in (("init_mean", mean), ("init_cov", cov), ("init_noise", noise)):
+    def set_initial(self, mean=None, cov=None, noise=None, lock_centre=None):
+        for name, arr in (("init_mean", mean), ("init_cov", cov), ("init_noise", noise), ("lock_centre", lock_centre)):
             if arr is not None:
                 d = DeviceArray.from_host(arr, dtype=np.float64)
                 self.inputs[name] = d
@@ -184,7 +184,7 @@ class VbRun(object):
 
 
 def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=None, init_cov=None,
-        init_noise=None):
+        init_noise=None, lock_centre=None):
     """Convenience: host arrays in, host arrays out (same signature as the test oracle's run())."""
     data = np.ascontiguousarray(data, dtype=np.float32)
     r = VbRun(spec, data.shape[1], spatial=spatial)
@@ -192,7 +192,7 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
         r.set_data(data)
         for k, img in (image_priors or {}).items():
             r.set_image_prior(k, img)
-        r.set_initial(init_mean, init_cov, init_noise)
+        r.set_initial(init_mean, init_cov, init_noise, lock_centre)
         if coords is not None:
             r.set_coords(coords)
         rc = r.launch()

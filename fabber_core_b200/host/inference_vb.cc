@@ -79,6 +79,7 @@ void Vb::GetOptions(std::vector<OptionSpec> &opts)
             true, "10" },
         { "print-free-energy", OPT_BOOL, "Output the free energy", true, "" },
         { "continue-from-mvn", OPT_MVN, "Continue previous run from output MVN files", true, "" },
+        { "locked-linear-from-mvn", OPT_MVN, "MVN file containing fixed centres for linearization", true, "" },
         { "output-only", OPT_BOOL,
             "Skip model fitting, just output requested data based on supplied MVN. Can only be used with "
             "continue-from-mvn",
@@ -381,6 +382,32 @@ void Vb::DoCalculations(FabberRunData &rundata)
     catch (DataNotFound &)
     {
     }
+    /* locked-linear-from-mvn (inference_vb.cc:128-129,171-178,227-231): the first P means of each voxel's MVN
+     * are the fixed linearisation centre. Like the reference, no check that the MVN belongs to this model
+     * beyond holding at least P parameters; only the spatial method honours it (:695 vs :443). */
+    std::vector<double> lock_centre;
+    const std::string lock_name = rundata.GetStringDefault("locked-linear-from-mvn", "");
+    if (lock_name != "" && spatial)
+    {
+        const VoxelData &mvn = rundata.GetVoxelData(lock_name);
+        /* rows = n(n+1)/2 + n + 1  ->  n */
+        int n_all = 0;
+        while ((n_all + 1) * (n_all + 2) / 2 < mvn.rows)
+            n_all++;
+        if ((n_all + 1) * (n_all + 2) / 2 != mvn.rows || n_all < P || (size_t)mvn.cols != N)
+            throw FabberRunDataError("locked-linear-from-mvn: not an MVN for this mask / model");
+        const int n_cov_all = n_all * (n_all + 1) / 2;
+        for (size_t v = 0; v < N; v++)
+            if (mvn.at(mvn.rows - 1, v) != 1) /* dist_mvn.cc:365-369 */
+                throw FabberRunDataError("MVNDist::Load - Voxel data does not contain a valid MVN - last value != 1");
+        lock_centre.resize((size_t)P * N);
+        parallel_for(N, [&](size_t vb, size_t ve) {
+            for (size_t v = vb; v < ve; v++)
+                for (int i = 0; i < P; i++)
+                    lock_centre[(size_t)i * N + v] = mvn.at(n_cov_all + i, v);
+        });
+        rundata.Log() << "Vb::Loading fixed linearization centres from the MVN '" << lock_name << "'" << std::endl;
+    }
     if (rundata.GetBool("output-only"))
     {
         if (!continue_from_mvn)
@@ -444,6 +471,8 @@ void Vb::DoCalculations(FabberRunData &rundata)
         buf.init_cov = (const double *)upload(init_cov.data(), init_cov.size() * sizeof(double));
         buf.init_noise = (const double *)upload(init_noise.data(), init_noise.size() * sizeof(double));
     }
+    if (!lock_centre.empty())
+        buf.lock_centre = (const double *)upload(lock_centre.data(), lock_centre.size() * sizeof(double));
     if (spatial)
         buf.coords = (const int *)upload(rundata.Coords().data(), 3 * N * sizeof(int));
     buf.mean = (double *)m_d_mean.p;

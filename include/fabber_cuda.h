@@ -138,6 +138,10 @@ typedef struct fabber_cuda_vb_buffers
     const double *init_mean;  /* optional [P][N] Fabber-space restart means (continue-from-mvn) */
     const double *init_cov;   /* optional [P(P+1)/2][N] restart covariance, packed */
     const double *init_noise; /* optional [NN][N] restart noise posterior */
+    /* optional [P][N] fixed linearisation centres (locked-linear-from-mvn, inference_vb.cc:171-178,227-231):
+     * spatial runs linearise there once and never re-centre (:695); voxelwise runs ignore it, as the
+     * reference does (:443 re-centres on the posterior unconditionally) */
+    const double *lock_centre;
     const int *coords;        /* spatial: [3][N] integer voxel coordinates (x,y,z) */
     /* outputs */
     double *mean;        /* [P][N] */

@@ -41,7 +41,7 @@ def _ptr(a):
 
 
 def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=None, init_cov=None,
-        init_noise=None, variant=""):
+        init_noise=None, variant="", lock_centre=None):
     """Run the oracle. data: float32 [T][N]. Returns dict of numpy arrays (see fabber_cuda.h layouts)."""
     data = np.ascontiguousarray(data, dtype=np.float32)
     T, N = data.shape
@@ -65,7 +65,8 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
             arr = np.ascontiguousarray(img, dtype=np.float64)
             keep.append(arr)
             buf.image_prior[k] = arr.ctypes.data
-    for name, arr in (("init_mean", init_mean), ("init_cov", init_cov), ("init_noise", init_noise)):
+    for name, arr in (("init_mean", init_mean), ("init_cov", init_cov), ("init_noise", init_noise),
+                      ("lock_centre", lock_centre)):
         if arr is not None:
             arr = np.ascontiguousarray(arr, dtype=np.float64)
             keep.append(arr)

@@ -1794,7 +1794,15 @@ int vb_oracle_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
         {
             eng.initial_posterior(v, ys[v], ctx.fwd_post[v]);
             eng.initial_noise(v, ctx.noise_prior[v], ctx.noise_post[v]);
-            lin[v].ReCentre(eng.mc, ctx.fwd_post[v].means);
+            if (buf->lock_centre) // inference_vb.cc:227-231
+            {
+                Vec centre(P);
+                for (int i = 0; i < P; i++)
+                    centre[i] = buf->lock_centre[(size_t)i * N + v];
+                lin[v].ReCentre(eng.mc, centre);
+            }
+            else
+                lin[v].ReCentre(eng.mc, ctx.fwd_post[v].means);
         }
         catch (InternalError &e)
         {
@@ -1895,7 +1903,8 @@ int vb_oracle_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
                     resultF[v - 1] = eng.noise.free_energy(ctx.noise_post[v - 1], ctx.noise_prior[v - 1],
                                          ctx.fwd_post[v - 1], ctx.fwd_prior[v - 1], lin[v - 1], ys[v - 1])
                         + Fprior;
-                lin[v - 1].ReCentre(eng.mc, ctx.fwd_post[v - 1].means);
+                if (!buf->lock_centre) // :695
+                    lin[v - 1].ReCentre(eng.mc, ctx.fwd_post[v - 1].means);
                 double F = 1234.5678;
                 if (eng.needF)
                 {

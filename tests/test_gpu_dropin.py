@@ -98,3 +98,22 @@ def test_dropin_noise_pattern_masked_timepoints_image_prior():
                       "PSP_byname1_type": "I", "PSP_byname1_image": "img", "PSP_byname1_prec": 1e6},
                      {"data": refbuild.volume(y, (nx, ny, nz)), "img": refbuild.volume(img[None], (nx, ny, nz))[..., 0]})
     assert_same(ours, ref)
+
+
+def test_dropin_locked_linear_from_mvn():
+    """locked-linear-from-mvn through the C API of both libraries: the MVN volume is one more named data item."""
+    from test_reference_build import locked_mvn
+
+    nx, ny, nz = 5, 4, 3
+    n = nx * ny * nz
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=76, smooth_shape=(nx, ny, nz)).numpy()
+    rng = np.random.default_rng(7)
+    centres = (np.array([[1.0], [1.2], [0.8], [5.0]]) * (1 + 0.05 * rng.standard_normal((4, n)))).astype(np.float32)
+    opts = {"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "spatialvb",
+            "param-spatial-priors": "MMMM", "max-iterations": 4, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0,
+            "locked-linear-from-mvn": "lockmvn"}
+    data = {"data": refbuild.volume(y, (nx, ny, nz)), "lockmvn": refbuild.volume(locked_mvn(4, 1, centres), (nx, ny, nz))}
+    ours, ref = both(opts, data)
+    assert_same(ours, ref)
+    unlocked, _ = both({k: v for k, v in opts.items() if k != "locked-linear-from-mvn"}, {"data": data["data"]})
+    assert np.max(np.abs(unlocked.data["mean_amp1"] - ours.data["mean_amp1"])) > 1e-4   # the option is live

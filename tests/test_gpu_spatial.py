@@ -186,3 +186,24 @@ def test_c5_full_size_ak_reduction():
         got = two["spatial_ak"][1, k]
         assert abs(got - expect) / expect < 1e-9, (k, got, expect)
     assert np.all(two["spatial_ak"][0] == 1e-8)   # SpatialPrior::m_aK initial value (priors.cc:185)
+
+
+def test_locked_linearisation_centres():
+    """locked-linear-from-mvn (inference_vb.cc:171-178,227-231,695): spatial VB linearises once about given
+    centres and never re-centres; the voxelwise method ignores the option, as the reference does (:443)."""
+    nx, ny, nz = 8, 7, 5
+    n = nx * ny * nz
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=1006, smooth_shape=(nx, ny, nz)).numpy()
+    coords = grid_coords(nx, ny, nz)
+    rng = np.random.default_rng(6)
+    centres = np.array([[1.0], [1.2], [0.8], [5.0]]) * (1 + 0.05 * rng.standard_normal((4, n)))
+    kw = dict(C5, prior_types=list("MMMM"), need_f=True, max_iterations=6, allow_bad_voxels=True)
+    gpu, ref, probes = both_spatial(kw, y, coords, (nx, ny, nz), lock_centre=centres)
+    compare(gpu, ref, 4, probes, label="C5 spatial MMMM locked linearisation")
+    check_ak(gpu, ref, probes)
+    # voxelwise: same answer with and without the lock
+    kv = {k: v for k, v in kw.items() if k != "model"}
+    kv["prior_types"] = list("NNNN")
+    a = device.run(abi.ProblemSpec("exp", 96, **kv), y, lock_centre=centres)
+    b = device.run(abi.ProblemSpec("exp", 96, **kv), y)
+    assert np.array_equal(a["mean"], b["mean"]) and np.array_equal(a["free_energy"], b["free_energy"])

@@ -175,3 +175,41 @@ def test_spatial_biexp_mrf_irregular_mask():
         assert rel(mvn[15 + i], ref["mean"][i], scale=np.maximum(np.abs(ref["mean"][i]), std[i])) < TIGHT
         assert rel(mvn[tri(i, i)], ref["cov"][tri(i, i)]) < TIGHT
     assert rel(F, ref["free_energy"]) < TIGHT
+
+
+def locked_mvn(P, n_noise, centres):
+    """an MVN volume (dist_mvn.cc:377-433 layout) whose first P means are `centres` [P][N]; float32-exact"""
+    n_all = P + n_noise
+    n_cov = n_all * (n_all + 1) // 2
+    n = centres.shape[1]
+    m = np.zeros((n_cov + n_all + 1, n), dtype=np.float32)
+    for i in range(n_all):
+        m[tri(i, i)] = 1.0
+    m[n_cov:n_cov + P] = centres
+    m[n_cov + P:n_cov + n_all] = 1.0
+    m[-1] = 1.0
+    return m
+
+
+def test_locked_linearisation_centres_spatial():
+    """locked-linear-from-mvn (inference_vb.cc:171-178,227-231,695): the spatial method linearises once about
+    the centres of an MVN file and never re-centres."""
+    nx, ny, nz = 4, 4, 3
+    n = nx * ny * nz
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=66, smooth_shape=(nx, ny, nz)).numpy()
+    rng = np.random.default_rng(5)
+    centres = (np.array([[1.0], [1.2], [0.8], [5.0]]) * (1 + 0.05 * rng.standard_normal((4, n)))).astype(np.float32)
+    mvn_in = locked_mvn(4, 1, centres)
+    run = run_ref({"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "spatialvb",
+                   "param-spatial-priors": "MMMM", "max-iterations": 4, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0,
+                   "locked-linear-from-mvn": "lockmvn"}, y, (nx, ny, nz),
+                  extra={"lockmvn": refbuild.volume(mvn_in, (nx, ny, nz))})
+    idx = np.arange(n)
+    coords = np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.int32)
+    spec = abi.ProblemSpec("exp", 96, num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=4, need_f=True,
+                           param_overrides={"r2": {"mean": 6.0}})
+    spec.prob.nx, spec.prob.ny, spec.prob.nz = nx, ny, nz
+    ref = oracle.run(spec, y, spatial=True, coords=coords, lock_centre=centres.astype(np.float64))
+    check_against_oracle(run, ref, 4, 1)
+    free = oracle.run(spec, y, spatial=True, coords=coords)
+    assert rel(free["mean"], ref["mean"]) > 1e-3   # the lock changes the answer: the option is live
