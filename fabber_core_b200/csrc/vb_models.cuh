@@ -8,7 +8,7 @@
  *   stage(args, smem)      block-cooperative staging into shared memory
  *   make_ctx(args, smem)   builds Ctx
  *   eval(ctx, t, p)        one sample of EvaluateModel at model-space parameters p
- *   eval_fd(ctx, t, p0, pp, pn, g, gp, gn)
+ *   sample(ctx, t, smp); eval_fd(ctx, smp, p0, pp, pn, g, gp, gn)
  *                          the 2P+1 evaluations LinearizedFwdModel::ReCentre needs at sample t:
  *                          g = f(p0), gp[i] = f(p0 with p0[i] -> pp[i]), gn[i] likewise with pn[i].
  *                          Every value is bit-identical to calling eval() on the perturbed vector;
@@ -73,11 +73,16 @@ template <int P_> struct LinearModel
     {
         return false;
     }
+    struct Sample
+    {
+        int t;
+    };
+    static FAB_DEV void sample(const Ctx &, int t, Sample &s) { s.t = t; }
     template <bool FAST>
-    static FAB_DEV void eval_fd(const Ctx &c, int t, const double (&p0)[P], const double (&pp)[P],
+    static FAB_DEV void eval_fd(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
-        const double *row = c.design + t * P;
+        const double *row = c.design + smp.t * P;
         double d[P], prod[P];
 #pragma unroll
         for (int j = 0; j < P; j++)
@@ -156,12 +161,17 @@ template <int P_> struct PolyModel
     {
         return false;
     }
+    struct Sample
+    {
+        double pw[P]; /* (t+1)^n, n = 0..P-1 */
+    };
+    static FAB_DEV void sample(const Ctx &, int t, Sample &s) { powers(t, s.pw); }
     template <bool FAST>
-    static FAB_DEV void eval_fd(const Ctx &, int t, const double (&p0)[P], const double (&pp)[P],
+    static FAB_DEV void eval_fd(const Ctx &, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
-        double pw[P], prod[P], prefix[P + 1];
-        powers(t, pw);
+        double prod[P], prefix[P + 1];
+        const double(&pw)[P] = smp.pw;
         prefix[0] = 0.0;
 #pragma unroll
         for (int j = 0; j < P; j++)
@@ -238,11 +248,16 @@ template <int NE> struct ExpModel
             s = __dadd_rn(s, __dmul_rn(p[2 * k], exp(__dmul_rn(-p[2 * k + 1], tt))));
         return s;
     }
+    struct Sample
+    {
+        double tt; /* double(t) * dt */
+    };
+    static FAB_DEV void sample(const Ctx &c, int t, Sample &s) { s.tt = __dmul_rn((double)t, c.dt); }
     template <bool FAST>
-    static FAB_DEV void eval_fd(const Ctx &c, int t, const double (&p0)[P], const double (&pp)[P],
+    static FAB_DEV void eval_fd(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
-        double tt = __dmul_rn((double)t, c.dt);
+        const double tt = smp.tt;
         double e0[NE], term[NE];
 #pragma unroll
         for (int k = 0; k < NE; k++)

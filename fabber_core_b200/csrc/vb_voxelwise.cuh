@@ -117,7 +117,12 @@ template <int P> struct Stats
 };
 
 /* the pass over the time-series: model at the 2P+1 finite-difference points, Jacobian row, statistics */
-template <class Model, int NPHI, bool FAST>
+/* CHECK: test g and every Jacobian entry of every sample for non-finite values (ReCentre throws on them,
+ * fwdmodel_linear.cc:134,174). With a single phi and no masked samples (NPHI == 1) every sample enters
+ * rr = sum r^2 and A_ii = sum J_i^2, and a non-finite r or J_i leaves those sums non-finite for good - so the
+ * hot loop runs unchecked (11 of its 80 instructions were the tests) and recentre_stats() looks at the sums
+ * afterwards, re-walking the series with recentre_diagnose() only in the rare case they are not finite. */
+template <class Model, int NPHI, bool FAST, bool CHECK>
 FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
     const double (&p0)[Model::P], const double (&pp)[Model::P], const double (&pn)[Model::P],
     const double (&rden)[Model::P], Stats<Model::P> (&S)[NPHI], bool &bad_g, bool &bad_j)
@@ -125,21 +130,37 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
     constexpr int P = Model::P;
     const float *yp = a.data + v;
     const size_t stride = (size_t)a.N;
-    float ynext = __ldg(yp);
+    /* software prefetch, three samples deep: one sample is ~60 FP64 instructions (~120 issue cycles per
+     * warp), a miss to HBM several hundred cycles */
+    float q0 = __ldg(yp), q1 = 0.f, q2 = 0.f;
+    if (1 < a.T)
+        q1 = __ldg(yp + stride);
+    if (2 < a.T)
+        q2 = __ldg(yp + 2 * stride);
+    typename Model::Sample smp;
+    Model::sample(mc, 0, smp);
 #pragma unroll 1
     for (int t = 0; t < a.T; t++)
     {
-        const double y = (double)ynext;
-        if (t + 1 < a.T) /* software prefetch: the load of sample t+1 overlaps the arithmetic of sample t */
-            ynext = __ldg(yp + (size_t)(t + 1) * stride);
+        const double y = (double)q0;
+        q0 = q1;
+        q1 = q2;
+        if (t + 3 < a.T)
+            q2 = __ldg(yp + (size_t)(t + 3) * stride);
+        /* the next sample's model-side constants (poly: integer powers -> double, a long-latency conversion)
+         * are formed one sample ahead */
+        typename Model::Sample nxt;
+        Model::sample(mc, t + 1, nxt);
         double g, gp[P], gn[P], J[P];
-        Model::template eval_fd<FAST>(mc, t, p0, pp, pn, g, gp, gn);
-        bad_g = bad_g || !finite_d(g);
+        Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+        if (CHECK)
+            bad_g = bad_g || !finite_d(g);
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
             J[i] = (gp[i] - gn[i]) * rden[i];
-            bad_j = bad_j || !finite_d(J[i]);
+            if (CHECK)
+                bad_j = bad_j || !finite_d(J[i]);
         }
         const double r = y - g;
         if (NPHI == 1)
@@ -152,6 +173,28 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
                 if (ph == i)
                     S[i].add(r, J);
         }
+        smp = nxt;
+    }
+}
+
+/* the rare path of the unchecked loop: which of g / J was non-finite (if any: sums of finite squares can
+ * overflow too, and then the reference does not throw here either) */
+template <class Model, bool FAST>
+FAB_DEV void recentre_diagnose(const VbArgs &a, const typename Model::Ctx &mc, const double (&p0)[Model::P],
+    const double (&pp)[Model::P], const double (&pn)[Model::P], const double (&rden)[Model::P], bool &bad_g, bool &bad_j)
+{
+    constexpr int P = Model::P;
+#pragma unroll 1
+    for (int t = 0; t < a.T; t++)
+    {
+        typename Model::Sample smp;
+        Model::sample(mc, t, smp);
+        double g, gp[P], gn[P];
+        Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+        bad_g = bad_g || !finite_d(g);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            bad_j = bad_j || !finite_d((gp[i] - gn[i]) * rden[i]);
     }
 }
 
@@ -187,10 +230,26 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
     bool bad_g = false, bad_j = false;
     /* models with a range-limited cheaper evaluation (exp: table-based exponential) take it when every
      * argument of this pass is inside its range - checked once here, not per sample */
-    if (Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn))
-        recentre_loop<Model, NPHI, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+    constexpr bool CHECK = NPHI > 1; /* masked samples never reach the sums: test them one by one */
+    const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
+    if (fast)
+        recentre_loop<Model, NPHI, true, CHECK>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     else
-        recentre_loop<Model, NPHI, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop<Model, NPHI, false, CHECK>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+    if (!CHECK)
+    {
+        bool sums_finite = finite_d(S[0].rr);
+#pragma unroll
+        for (int i = 0; i < P; i++)
+            sums_finite = sums_finite && finite_d(S[0].A[tri(i, i)]);
+        if (!sums_finite)
+        {
+            if (fast)
+                recentre_diagnose<Model, true>(a, mc, p0, pp, pn, rden, bad_g, bad_j);
+            else
+                recentre_diagnose<Model, false>(a, mc, p0, pp, pn, rden, bad_g, bad_j);
+        }
+    }
     return bad_g ? FABBER_VOX_NONFINITE_OFFSET : (bad_j ? FABBER_VOX_NONFINITE_JACOBIAN : 0);
 }
 

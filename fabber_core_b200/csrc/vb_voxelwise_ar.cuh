@@ -65,31 +65,40 @@ FAB_DEV double ar_klj(const Stats<P> &M, const double (&d)[P], const double (&Si
 template <class Model, bool FAST>
 FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&p0)[Model::P],
     const double (&pp)[Model::P], const double (&pn)[Model::P], const double (&rden)[Model::P],
-    ArStats<Model::P> &S, bool &bad_g, bool &bad_j, volatile double *first)
+    ArStats<Model::P> &S, volatile double *first)
 {
     constexpr int P = Model::P;
     const float *yp = a.data + v;
     const size_t stride = (size_t)a.N;
-    float ynext = __ldg(yp);
+    /* three-deep software prefetch and unchecked arithmetic: see recentre_loop (vb_voxelwise.cuh); the lag-0
+     * sums S0.rr / S0.A_ii carry every sample, recentre_stats_ar() inspects them after the pass */
+    float q0 = __ldg(yp), q1 = 0.f, q2 = 0.f;
+    if (1 < a.T)
+        q1 = __ldg(yp + stride);
+    if (2 < a.T)
+        q2 = __ldg(yp + 2 * stride);
     double Jprev[P], rprev = 0.0;
 #pragma unroll
     for (int i = 0; i < P; i++)
         Jprev[i] = 0.0;
+    typename Model::Sample smp;
+    Model::sample(mc, 0, smp);
 #pragma unroll 1
     for (int t = 0; t < a.T; t++)
     {
-        const double y = (double)ynext;
-        if (t + 1 < a.T)
-            ynext = __ldg(yp + (size_t)(t + 1) * stride);
+        const double y = (double)q0;
+        q0 = q1;
+        q1 = q2;
+        if (t + 3 < a.T)
+            q2 = __ldg(yp + (size_t)(t + 3) * stride);
+        typename Model::Sample nxt;
+        Model::sample(mc, t + 1, nxt);
         double g, gp[P], gn[P], J[P];
-        Model::template eval_fd<FAST>(mc, t, p0, pp, pn, g, gp, gn);
-        bad_g = bad_g || !finite_d(g);
+        Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+        smp = nxt;
 #pragma unroll
         for (int i = 0; i < P; i++)
-        {
             J[i] = (gp[i] - gn[i]) * rden[i];
-            bad_j = bad_j || !finite_d(J[i]);
-        }
         const double r = y - g;
         S.S0.add(r, J);
         /* lag-1 terms: Jprev/rprev are zero at t == 0, so the first pass adds exact zeros */
@@ -149,10 +158,22 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     S.S0.zero();
     S.S1.zero();
     bool bad_g = false, bad_j = false;
-    if (Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn))
-        recentre_loop_ar<Model, true>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j, first);
+    const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
+    if (fast)
+        recentre_loop_ar<Model, true>(a, mc, v, p0, pp, pn, rden, S, first);
     else
-        recentre_loop_ar<Model, false>(a, mc, v, p0, pp, pn, rden, S, bad_g, bad_j, first);
+        recentre_loop_ar<Model, false>(a, mc, v, p0, pp, pn, rden, S, first);
+    bool sums_finite = finite_d(S.S0.rr);
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        sums_finite = sums_finite && finite_d(S.S0.A[tri(i, i)]);
+    if (!sums_finite)
+    {
+        if (fast)
+            recentre_diagnose<Model, true>(a, mc, p0, pp, pn, rden, bad_g, bad_j);
+        else
+            recentre_diagnose<Model, false>(a, mc, p0, pp, pn, rden, bad_g, bad_j);
+    }
     return bad_g ? FABBER_VOX_NONFINITE_OFFSET : (bad_j ? FABBER_VOX_NONFINITE_JACOBIAN : 0);
 }
 
