@@ -375,7 +375,7 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
 #pragma unroll
     for (int i = 0; i < P; i++)
         Lam[tri(i, i)] = L0[i] + phi * A[tri(i, i)];
-    if (!mvn_inverse<P>(Lam, Sig, ld))
+    if (!mvn_inverse<P>(Lam, Sig, ld, a.need_f != 0))
     {
         a.status[v] = FABBER_VOX_SINGULAR;
         return;
@@ -627,7 +627,9 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_noise_kernel(cons
             m0[i] = s.m0[i * N + v];
             L0[i] = s.L0[i * N + v];
         }
-        const double F = white_free_energy<P, 1>(a, S, m, Sig, s.logdet[v], m0, L0, nbv, ncv) + *s.fprior_last;
+        FCache<1> fc;
+        fc.init(a);
+        const double F = white_free_energy<P, 1>(a, S, m, Sig, s.logdet[v], m0, L0, nbv, ncv, fc) + *s.fprior_last;
         if (!finite_d(F))
         {
             a.status[v] = FABBER_VOX_NONFINITE_F;

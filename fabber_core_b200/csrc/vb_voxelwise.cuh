@@ -254,12 +254,43 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
 }
 
 /* WhiteNoiseModel::CalcFreeEnergy with c == m (always true where Vb reads F: after ReCentre). */
+/* What the free energy re-derives every iteration although it never changes: gammaln / digamma of the noise
+ * shape c (constant from the first UpdateNoise on: c = (n-1)/2 + c0) and the prior's own constant. Measured
+ * on C3 (LM, F every iteration): the two gammaln + digamma were 9 % of the kernel. Keyed on the value of c,
+ * so a changed c (first iteration, restarts) just recomputes. */
+template <int NPHI> struct FCache
+{
+    double key[NPHI], lgam[NPHI], dgam[NPHI], prior[NPHI];
+    FAB_DEV void init(const VbArgs &a)
+    {
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            key[i] = -1.0; /* a Gamma shape is positive: never matches */
+            lgam[i] = dgam[i] = prior[i] = 0.0;
+            if (a.need_f && i < a.n_phis)
+                prior[i] = -gammaln(a.noise_prior_c[i]) - a.noise_prior_c[i] * log(a.noise_prior_b[i]);
+        }
+    }
+    FAB_DEV void lookup(int i, double ci, double &lg, double &dg)
+    {
+        if (ci != key[i])
+        {
+            key[i] = ci;
+            lgam[i] = gammaln(ci);
+            dgam[i] = digamma_fsl(ci);
+        }
+        lg = lgam[i];
+        dg = dgam[i];
+    }
+};
+
 template <int P, int NPHI>
 FAB_DEV double white_free_energy(const VbArgs &a, const Stats<P> (&S)[NPHI], const double (&m)[P],
     const double (&Sig)[NTri<P>::value], double logdetLam, const double (&m0)[P], const double (&L0)[P],
-    const double (&nb)[NPHI], const double (&nc)[NPHI])
+    const double (&nb)[NPHI], const double (&nc)[NPHI], FCache<NPHI> &fc)
 {
-    const double log2pi = log(2 * 3.14159265358979323846);
+    const double log2pi = FAB_LOG_2PI;
     const double elTheta = 0.5 * logdetLam - 0.5 * P * (log2pi + 1);
     double elPhi = 0.0, p0 = 0.0, p2 = 0.0, p9 = 0.0;
 #pragma unroll
@@ -269,22 +300,27 @@ FAB_DEV double white_free_energy(const VbArgs &a, const Stats<P> (&S)[NPHI], con
         {
             const double si = nb[i], ci = nc[i];
             const double siP = a.noise_prior_b[i], ciP = a.noise_prior_c[i];
-            const double dg = digamma_fsl(ci), lsi = log(si);
-            elPhi += -gammaln(ci) - ci * lsi - ci + (ci - 1) * (dg + lsi);
+            double lg, dg;
+            fc.lookup(i, ci, lg, dg);
+            const double lsi = log(si);
+            elPhi += -lg - ci * lsi - ci + (ci - 1) * (dg + lsi);
             p0 += (dg + lsi) * ((double)a.n_per_phi[i] * 0.5 + ciP - 1);
-            p9 += -gammaln(ciP) - ciP * log(siP) - si * ci / siP;
+            p9 += fc.prior[i] - si * ci / siP;
             p2 += -0.5 * si * ci * S[i].rr - 0.5 * trace_prod<P>(S[i].A, Sig);
         }
     }
-    double ld0 = 0.0, q = 0.0, tr0 = 0.0;
+    double q = 0.0, tr0 = 0.0;
+    LogProd lp0;
+    lp0.init();
 #pragma unroll
     for (int i = 0; i < P; i++)
     {
-        ld0 += log(fabs(L0[i]));
+        lp0.mul(L0[i]);
         const double dm = m[i] - m0[i];
         q += dm * L0[i] * dm;
         tr0 += Sig[tri(i, i)] * L0[i];
     }
+    const double ld0 = lp0.value();
     const double p3 = 0.5 * ld0 - 0.5 * a.n_unmasked * log2pi - 0.5 * P * log2pi;
     const double p4 = -0.5 * q;
     const double p5 = -0.5 * tr0;
@@ -311,7 +347,8 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
      * parked in shared memory around the pass instead ([slot][thread] layout: conflict-free 64-bit
      * accesses; volatile so the compiler cannot forward the values through registers).
      * The trialmode / freduce snapshot (inference_vb.cc:432-434,451-458) lives there permanently. */
-    static constexpr int STASH_DOUBLES = 3 * P + 2 * NT + 2 * NPHI + 1;
+    FCache<NPHI> fc;
+    static constexpr int STASH_DOUBLES = 3 * P + 2 * NT + 2 * NPHI + 1 + 4 * NPHI;
     static constexpr int SNAP_DOUBLES = SNAP ? 3 * P + NT + 2 * NPHI : 0;
     FAB_DEV void stash(volatile double *s) const
     {
@@ -336,6 +373,14 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
             s[(k++) * VB_BLOCK] = nc[i];
         }
         s[(k++) * VB_BLOCK] = logdetLam;
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            s[(k++) * VB_BLOCK] = fc.key[i];
+            s[(k++) * VB_BLOCK] = fc.lgam[i];
+            s[(k++) * VB_BLOCK] = fc.dgam[i];
+            s[(k++) * VB_BLOCK] = fc.prior[i];
+        }
     }
     FAB_DEV void unstash(const volatile double *s)
     {
@@ -360,6 +405,14 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
             nc[i] = s[(k++) * VB_BLOCK];
         }
         logdetLam = s[(k++) * VB_BLOCK];
+#pragma unroll
+        for (int i = 0; i < NPHI; i++)
+        {
+            fc.key[i] = s[(k++) * VB_BLOCK];
+            fc.lgam[i] = s[(k++) * VB_BLOCK];
+            fc.dgam[i] = s[(k++) * VB_BLOCK];
+            fc.prior[i] = s[(k++) * VB_BLOCK];
+        }
     }
     FAB_DEV void save(volatile double *s) const
     {
@@ -458,7 +511,7 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
             P0m0[i] = L0[i] * m0[i];
         if (alpha <= 0.0)
         {
-            if (!mvn_inverse<P>(Lam, Sig, logdetLam))
+            if (!mvn_inverse<P>(Lam, Sig, logdetLam, a.need_f != 0))
                 return false;
             double Ac[P], rhs[P];
             symv<P>(Aw, c, Ac);
@@ -479,7 +532,7 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
                 D[tri(i, i)] = Lam[tri(i, i)] + alpha * Lam[tri(i, i)];
                 Delta[i] = bw[i] + P0m0[i] - L0[i] * c[i];
             }
-            if (ldl_inverse<P>(D, Dinv, ld))
+            if (ldl_inverse<P>(D, Dinv, ld, false))
             {
                 symv<P>(Dinv, Delta, step);
 #pragma unroll
@@ -487,7 +540,7 @@ template <class Model, int NPHI, bool SNAP> struct WhiteVoxel
                     m[i] = c[i] + step[i];
             }
             /* Sigma is first needed by UpdateNoise (theta.GetCovariance(), noisemodel_white.cc:252) */
-            if (!mvn_inverse<P>(Lam, Sig, logdetLam))
+            if (!mvn_inverse<P>(Lam, Sig, logdetLam, a.need_f != 0))
                 return false;
         }
         return true;
@@ -618,6 +671,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_white_k
         PH_ITER,
         PH_REVERT
     };
+    X.fc.init(a);
     Stats<P> S[NPHI];
     double c[P];
     Conv conv;
@@ -652,7 +706,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_white_k
             }
             if (a.need_f)
             {
-                F = white_free_energy<P, NPHI>(a, S, X.m, X.Sig, X.logdetLam, X.m0, X.L0, X.nb, X.nc) + Fprior;
+                F = white_free_energy<P, NPHI>(a, S, X.m, X.Sig, X.logdetLam, X.m0, X.L0, X.nb, X.nc, X.fc) + Fprior;
                 if (!finite_d(F))
                 {
                     status = FABBER_VOX_NONFINITE_F;
@@ -677,7 +731,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_white_k
                     if (conv.need_revert())
                     {
                         X.restore(snap);
-                        if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam))
+                        if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam, a.need_f != 0))
                         {
                             status = FABBER_VOX_SINGULAR;
                             break;

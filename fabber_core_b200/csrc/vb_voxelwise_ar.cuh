@@ -259,7 +259,7 @@ template <class Model> struct ArVoxel
     FAB_DEV bool update_marginal()
     {
         double acov[3], ld;
-        if (!mvn_inverse<2>(aprec, acov, ld))
+        if (!mvn_inverse<2>(aprec, acov, ld, false))
             return false;
         qa = am[0];
         qcp = acov[0] + am[0] * am[0];
@@ -288,7 +288,7 @@ template <class Model> struct ArVoxel
     }
 
     /* noisemodel_ar.cc:558-610 (LMalpha is ignored by the AR model) */
-    FAB_DEV bool update_theta(const ArStats<P> &S, const double (&c)[P])
+    FAB_DEV bool update_theta(const ArStats<P> &S, const double (&c)[P], bool want_logdet)
     {
         const double w = nb * nc;
         Stats<P> Q;
@@ -299,7 +299,7 @@ template <class Model> struct ArVoxel
 #pragma unroll
         for (int i = 0; i < P; i++)
             Lam[tri(i, i)] = L0[i] + Q.A[tri(i, i)];
-        if (!mvn_inverse<P>(Lam, Sig, logdetLam))
+        if (!mvn_inverse<P>(Lam, Sig, logdetLam, want_logdet))
             return false;
         double Ac[P], rhs[P];
         symv<P>(Q.A, c, Ac);
@@ -328,7 +328,7 @@ template <class Model> struct ArVoxel
         if (!finite_d(aprec[0]))
             return FABBER_VOX_NONFINITE_F; /* "Non-finite values in alpha precisions" :484 */
         double acov[3], ld;
-        if (!ldl_inverse<2>(aprec, acov, ld))
+        if (!ldl_inverse<2>(aprec, acov, ld, false))
             return FABBER_VOX_SINGULAR;
         if (fmin(acov[0], acov[2]) < 0)
             return FABBER_VOX_AR_NEG_VARIANCE;
@@ -336,7 +336,7 @@ template <class Model> struct ArVoxel
         ar_combine<P>(S, 0.0, 1.0, 0.0, M);
         const double t0 = 0.0 + -0.5 * w * ar_klj<P>(M, d, Sig);
         double acov2[3];
-        if (!mvn_inverse<2>(aprec, acov2, ld))
+        if (!mvn_inverse<2>(aprec, acov2, ld, false))
             return FABBER_VOX_SINGULAR;
         am[0] = acov2[0] * t0 + acov2[1] * 0.0;
         am[1] = acov2[1] * t0 + acov2[2] * 0.0;
@@ -353,7 +353,7 @@ template <class Model> struct ArVoxel
     /* noisemodel_ar.cc:643-747 with c == m */
     FAB_DEV double free_energy(const VbArgs &a, const ArStats<P> &S) const
     {
-        const double log2pi = log(2 * 3.14159265358979323846);
+        const double log2pi = FAB_LOG_2PI;
         const double w = nb * nc;
         Stats<P> Q;
         ar_combine<P>(S, w, w * qa, w * qcp, Q);
@@ -368,17 +368,19 @@ template <class Model> struct ArVoxel
         const double p9 = -2 * gammaln(ciP) - 2 * ciP * log(siP) - si * ci / siP;
         const double p1 = -log2pi * ((double)a.T - 1 + 0.5 * 2 + 0.5 * P);
         const double p2 = -0.5 * Q.rr - 0.5 * trace_prod<P>(Q.A, Sig);
-        double ld0 = 0.0, q = 0.0, tr0 = 0.0;
+        double q = 0.0, tr0 = 0.0;
+        LogProd lp0;
+        lp0.init();
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
-            ld0 += log(fabs(L0[i]));
+            lp0.mul(L0[i]);
             const double dm = m[i] - m0[i];
             q += dm * L0[i] * dm;
             tr0 += Sig[tri(i, i)] * L0[i];
         }
         const double pp = a.ar_alpha_prior_prec;
-        const double p3 = 0.5 * ld0;
+        const double p3 = 0.5 * lp0.value();
         const double p4 = -0.5 * q;
         const double p5 = -0.5 * tr0;
         const double p6 = 0.5 * (log(fabs(pp)) + log(fabs(pp)));
@@ -560,7 +562,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_AR_MIN_BLOCKS) vb_voxelwise_ar_k
                     if (conv.need_revert())
                     {
                         X.template get<false>(snap);
-                        if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam))
+                        if (!mvn_inverse<P>(X.Lam, X.Sig, X.logdetLam, a.need_f != 0))
                         {
                             status = FABBER_VOX_SINGULAR;
                             break;
@@ -577,7 +579,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_AR_MIN_BLOCKS) vb_voxelwise_ar_k
 #pragma unroll
         for (int k = 0; k < P; k++)
             Fprior = X.apply_prior(a, k, v, it);
-        if (!X.update_theta(S, c))
+        if (!X.update_theta(S, c, a.need_f != 0))
         {
             status = FABBER_VOX_SINGULAR;
             break;
