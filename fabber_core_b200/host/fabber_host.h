@@ -133,6 +133,12 @@ struct VoxelData
     double at(int r, size_t c) const { return (double)f[(size_t)r * cols + c]; }
 };
 
+enum VoxelDataType /* rundata.h:37-43 */
+{
+    VDT_SCALAR,
+    VDT_MVN
+};
+
 /* ---- run data (rundata.h:215-672 + rundata_array.cc) -------------------------------------------- */
 class FabberRunData
 {
@@ -155,6 +161,18 @@ public:
     std::vector<std::string> GetStringList(const std::string &key); /* key1, key2, ... (rundata.cc:557-574) */
     std::vector<int> GetIntList(const std::string &key, int min = INT32_MIN, int max = INT32_MAX);
 
+    /* command line and option files (rundata.cc:324-453): --key, --key=value, -f <file>, -@ <file>, --optfile */
+    void Parse(int argc, char **argv);
+    void ParseParamFile(const std::string &filename);
+    void ParseOldStyleParamFile(const std::string &filename);
+    void AddKeyEqualsValue(const std::string &exp, bool trim_comments = false);
+    void LogParams();                  /* rundata.cc:239-246 */
+    void CheckAllOptionsUsed();        /* "WARNING ONCE: Unused option specified: .." (rundata.cc:648-658) */
+    void WarnOnce(const std::string &text); /* easylog.cc:105-127 */
+    void ReissueWarnings();
+    /* output directory: created on first use, '+' appended until it is new unless --overwrite (rundata.cc:660-737) */
+    std::string GetOutputDir();
+
     /* extent, mask and coordinates (rundata_array.cc:23-66): voxel order x fastest, then y, then z */
     void SetExtent(int nx, int ny, int nz, const int *mask);
     const int *Extent() const { return m_extent; }
@@ -167,7 +185,11 @@ public:
     void GetVoxelDataArray(const std::string &key, float *data);
     int GetVoxelDataSize(const std::string &key);
     const VoxelData &GetVoxelData(const std::string &key);
-    const VoxelData &GetMainVoxelData();
+    const VoxelData &GetMainVoxelData(); /* "data", or data1..n combined by data-order (rundata.cc:753-905) */
+    VoxelData &MutableMainVoxelData();
+    /* called by SaveResults for every output it has stored under `key`; file-based front ends write it out
+     * (rundata.cc:932-938, rundata_newimage.cc:140-183). The array front end keeps it in memory. */
+    virtual void SaveVoxelData(const std::string &key, VoxelDataType type);
     VoxelData &NewVoxelData(const std::string &key, int rows); /* SaveVoxelData target (rundata.cc:932-938) */
     VoxelData &MutableVoxelData(const std::string &key);
     void ClearVoxelData(const std::string &key);
@@ -186,7 +208,16 @@ public:
     }
     static void GetOptions(std::vector<OptionSpec> &opts);
 
+protected:
+    /* hook: `key` is not in memory - a file-based front end loads it (rundata_newimage.cc:89-138) and returns
+     * true. The array front end has nothing to load from. */
+    virtual bool LoadVoxelData(const std::string &key);
+
 private:
+    const VoxelData &GetMainVoxelDataMultiple();
+    std::string m_outdir;
+    std::set<std::string> m_used_params;
+    std::map<std::string, int> m_warncount;
     std::map<std::string, std::string> m_params;
     std::map<std::string, std::unique_ptr<VoxelData>> m_voxel_data;
     int m_extent[3];
@@ -196,6 +227,26 @@ private:
     void (*m_progress)(int, int);
 };
 typedef FabberRunData FabberRunDataArray;
+
+/* ---- file-based run data (rundata_newimage.h): NIfTI volumes in, NIfTI volumes out ------------------
+ * Same name and behaviour as the reference's NEWIMAGE-backed class; the I/O underneath is nifti_io.cc. */
+struct NiftiHeader;
+class FabberRunDataNewimage : public FabberRunData
+{
+public:
+    explicit FabberRunDataNewimage(bool compat_options = true);
+    ~FabberRunDataNewimage();
+    /* mask (binarised: > 1e-16) or, without one, the main data file gives the extent (rundata_newimage.cc:62-87) */
+    void SetExtentFromData();
+    void SaveVoxelData(const std::string &key, VoxelDataType type) override;
+
+protected:
+    bool LoadVoxelData(const std::string &filename) override;
+
+private:
+    std::unique_ptr<NiftiHeader> m_like; /* geometry every output copies (the mask's, else the first data file's) */
+    bool m_have_mask;
+};
 
 /* ---- parameters and transforms (fwdmodel.h:24-57, transforms.h) ---------------------------------- */
 struct DistParams
@@ -310,6 +361,8 @@ private:
     double m_dt = 1.0;
     int m_num = 1;
 };
+
+const char *fabber_b200_version();
 
 /* tools.cc:27-40: VEST or plain ASCII matrix file -> row-major values */
 void read_matrix_file(const std::string &filename, std::vector<double> &values, int &rows, int &cols);

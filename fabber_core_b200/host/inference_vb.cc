@@ -160,7 +160,7 @@ void Vb::ReleaseDevice()
 void Vb::DoCalculations(FabberRunData &rundata)
 {
     StopWatch sw;
-    VoxelData &data = rundata.MutableVoxelData("data");
+    VoxelData &data = rundata.MutableMainVoxelData();
     const size_t N = data.cols;
     const int T = data.rows;
     m_nvoxels = N;
@@ -598,7 +598,7 @@ void Vb::SaveResults(FabberRunData &rundata)
         want(&out.model_fit, T, std::vector<std::string>(1, "modelfit"), T);
     if (rundata.GetBool("save-residuals"))
     {
-        VoxelData &data = rundata.MutableVoxelData("data");
+        VoxelData &data = rundata.MutableMainVoxelData();
         if (!data.dev)
         {
             data.dev = (float *)cached_device_alloc(data.bytes());
@@ -627,6 +627,10 @@ void Vb::SaveResults(FabberRunData &rundata)
     ReleaseDevice();
     check(rc, "saving results");
     check(rc_sync, "saving results");
+    /* file-based front ends write each output now (rundata_newimage.cc:140-183); a no-op for the array one */
+    for (size_t i = 0; i < pending.size(); i++)
+        for (size_t k = 0; k < pending[i].keys.size(); k++)
+            rundata.SaveVoxelData(pending[i].keys[k], pending[i].keys[k] == "finalMVN" ? VDT_MVN : VDT_SCALAR);
     rundata.Log() << "Vb::timing: SaveResults " << sw.lap_ms() << " ms" << std::endl;
     rundata.Log() << "Vb::Done writing results." << std::endl;
 }

@@ -10,14 +10,22 @@
 #include <cstring>
 #include <ctime>
 
+#include <cerrno>
+#include <fstream>
 #include <map>
 #include <mutex>
 #include <thread>
+
+#include <sys/stat.h>
+#include <sys/types.h>
+#include <unistd.h>
 
 #include "fabber_host.h"
 
 namespace fabber_b200
 {
+const char *fabber_b200_version() { return "b200-r1 (VB path of fabber_core on sm_100a)"; }
+
 void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_chunk)
 {
     unsigned hw = std::thread::hardware_concurrency();
@@ -104,13 +112,22 @@ bool cache_put(BlockCache &c, void *p, size_t bytes)
 }
 } // namespace
 
+/* Without a CUDA device there is nothing to pin for: plain memory, so that option handling, file I/O and
+ * error reporting still work (and are testable) on a machine without a GPU. The inference itself has no
+ * such fallback - Vb::DoCalculations fails with the device error. Fixed for the life of the process. */
+static bool have_device()
+{
+    static const bool yes = fabber_cuda_device_count() > 0;
+    return yes;
+}
+
 void *cached_pinned_alloc(size_t bytes)
 {
     if (bytes == 0)
         bytes = 1;
     void *p = cache_get(g_pinned, bytes);
     if (!p)
-        p = fabber_cuda_host_alloc(bytes);
+        p = have_device() ? fabber_cuda_host_alloc(bytes) : malloc(bytes);
     if (!p)
         throw FabberInternalError(std::string("Could not allocate pinned host memory: ") + fabber_cuda_last_error());
     return p;
@@ -118,7 +135,12 @@ void *cached_pinned_alloc(size_t bytes)
 void cached_pinned_free(void *p, size_t bytes)
 {
     if (p && !cache_put(g_pinned, p, bytes ? bytes : 1))
-        fabber_cuda_host_free(p);
+    {
+        if (have_device())
+            fabber_cuda_host_free(p);
+        else
+            free(p);
+    }
 }
 void *cached_device_alloc(size_t bytes)
 {
@@ -184,18 +206,21 @@ std::string FabberRunData::GetString(const std::string &key)
 {
     if (m_params.count(key) == 0)
         throw MandatoryOptionMissing(key);
+    if (m_params[key] == "")
+        throw InvalidOptionValue(key, "<no value>", "Value must be given");
+    m_used_params.insert(key);
     return m_params[key];
 }
 std::string FabberRunData::GetStringDefault(const std::string &key, const std::string &def)
 {
+    m_used_params.insert(key);
     if (m_params.count(key) == 0)
         return def;
-    if (m_params[key] == "")
-        throw InvalidOptionValue(key, "<no value>", "Value must be given");
     return m_params[key];
 }
 bool FabberRunData::GetBool(const std::string &key)
 {
+    m_used_params.insert(key);
     if (m_params.count(key) == 0)
         return false;
     if (m_params[key] == "")
@@ -308,6 +333,8 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
     const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
     const size_t N = m_voxel_index.size();
     m_voxel_data.erase(key); /* hand the old blocks back to the cache before asking for new ones */
+    if (key.compare(0, 4, "data") == 0)
+        m_voxel_data.erase("@maindata"); /* a stale combination of data1..n */
     std::unique_ptr<VoxelData> vd(new VoxelData());
     vd->alloc(data_size, N);
     float *dst_all = vd->f;
@@ -315,7 +342,9 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
     /* The main series goes straight on to the GPU: rows are staged into pinned memory in ~64 MB chunks by
      * all host cores and each chunk's host->device copy is queued as soon as it is staged, so the PCIe
      * transfer of chunk k overlaps the staging of chunk k+1. */
-    const bool upload = (key == "data") && N > 0 && fabber_cuda_device_count() > 0;
+    /* ("data" itself, or the file the data option names when a file-based front end loads it) */
+    const bool is_main = key == "data" || (m_params.count("data") && m_params["data"] == key);
+    const bool upload = is_main && N > 0 && fabber_cuda_device_count() > 0;
     if (upload)
         vd->dev = (float *)cached_device_alloc(vd->bytes());
     const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max<size_t>(1, N * sizeof(float)));
@@ -348,13 +377,103 @@ const VoxelData &FabberRunData::GetVoxelData(const std::string &key_in)
     while (m_voxel_data.count(key) == 0)
     {
         if (m_params.count(key) == 0 || m_params[key] == "" || seen.count(key))
+        {
+            /* end of the chain: the name of something a file-based front end can load */
+            if (LoadVoxelData(key) && m_voxel_data.count(key))
+                break;
             throw DataNotFound(key_in);
+        }
         seen.insert(key);
+        m_used_params.insert(key);
         key = m_params[key];
     }
     return *m_voxel_data[key];
 }
-const VoxelData &FabberRunData::GetMainVoxelData() { return GetVoxelData("data"); }
+bool FabberRunData::LoadVoxelData(const std::string &) { return false; }
+void FabberRunData::SaveVoxelData(const std::string &, VoxelDataType) {}
+
+const VoxelData &FabberRunData::GetMainVoxelData()
+{
+    if (m_voxel_data.count("@maindata"))
+        return *m_voxel_data["@maindata"];
+    try
+    {
+        return GetVoxelData("data");
+    }
+    catch (DataNotFound &e)
+    {
+        try
+        {
+            GetVoxelData("data1");
+        }
+        catch (DataNotFound &)
+        {
+            throw e;
+        }
+        return GetMainVoxelDataMultiple();
+    }
+}
+VoxelData &FabberRunData::MutableMainVoxelData() { return const_cast<VoxelData &>(GetMainVoxelData()); }
+
+/* rundata.cc:821-905 */
+const VoxelData &FabberRunData::GetMainVoxelDataMultiple()
+{
+    std::vector<const VoxelData *> sets;
+    for (int n = 1;; n++)
+    {
+        try
+        {
+            sets.push_back(&GetVoxelData("data" + stringify(n)));
+        }
+        catch (DataNotFound &)
+        {
+            break;
+        }
+    }
+    const std::string order = GetStringDefault("data-order", "interleave");
+    const int n_sets = (int)sets.size();
+    if (n_sets < 1)
+        throw DataNotFound("data");
+    if (order == "singlefile" && n_sets > 1)
+        throw InvalidOptionValue("data-order", "singlefile", "More than one file specified");
+    const size_t N = sets[0]->cols;
+    int total = 0;
+    for (int j = 0; j < n_sets; j++)
+    {
+        if (sets[j]->cols != N)
+            throw FabberRunDataError("data" + stringify(j + 1) + " has a different number of voxels");
+        total += sets[j]->rows;
+    }
+    std::unique_ptr<VoxelData> vd(new VoxelData());
+    vd->alloc(total, N);
+    if (order == "interleave")
+    {
+        m_log << "FabberRunData::Combining data into one big matrix by interleaving..." << std::endl;
+        const int n_times = sets[0]->rows;
+        for (int j = 0; j < n_sets; j++)
+            if (sets[j]->rows != n_times)
+                throw InvalidOptionValue("data-order", "interleave", "Data sets must all have the same number of time points");
+        for (int i = 0; i < n_times; i++)
+            for (int j = 0; j < n_sets; j++)
+                memcpy(vd->f + (size_t)(n_sets * i + j) * N, sets[j]->f + (size_t)i * N, N * sizeof(float));
+    }
+    else if (order == "concatenate" || order == "singlefile")
+    {
+        if (order == "concatenate")
+            m_log << "FabberRunData::Combining data into one big matrix by concatenating..." << std::endl;
+        size_t row = 0;
+        for (int j = 0; j < n_sets; j++)
+        {
+            memcpy(vd->f + row * N, sets[j]->f, sets[j]->bytes());
+            row += sets[j]->rows;
+        }
+    }
+    else
+        throw InvalidOptionValue("data-order", order, "Value not recognized");
+    m_log << "FabberRunData::Done loading data, size = " << total << " timepoints by " << N << " voxels" << std::endl;
+    m_voxel_data["@maindata"] = std::move(vd);
+    return *m_voxel_data["@maindata"];
+}
 int FabberRunData::GetVoxelDataSize(const std::string &key) { return GetVoxelData(key).rows; }
 VoxelData &FabberRunData::NewVoxelData(const std::string &key, int rows)
 {
@@ -421,6 +540,188 @@ void FabberRunData::GetOptions(std::vector<OptionSpec> &opts)
         opts.push_back(O[i]);
 }
 
+/* ---- command line and option files (rundata.cc:324-453) ------------------------------------------ */
+static std::string trim(const std::string &s)
+{
+    const char *ws = " \t\r\n";
+    const size_t b = s.find_first_not_of(ws);
+    if (b == std::string::npos)
+        return "";
+    return s.substr(b, s.find_last_not_of(ws) - b + 1);
+}
+
+void FabberRunData::AddKeyEqualsValue(const std::string &exp, bool trim_comments)
+{
+    const size_t eq = exp.find("=");
+    const std::string key = trim(exp.substr(0, eq));
+    if (eq != std::string::npos)
+    {
+        size_t end = std::string::npos;
+        if (trim_comments)
+            end = exp.find("#");
+        const std::string value = trim(exp.substr(eq + 1, end == std::string::npos ? end : end - (eq + 1)));
+        if (m_params.count(key) > 0)
+            throw InvalidOptionValue(key, value, "Already has a value: " + m_params[key]);
+        if (key == "loadmodels")
+            throw InvalidOptionValue(key, value,
+                "dynamic model libraries hold host code; models here are __device__ hooks compiled into the library");
+        m_params[key] = value;
+    }
+    else
+        m_params[exp] = "";
+}
+
+void FabberRunData::ParseParamFile(const std::string &filename)
+{
+    std::ifstream is(filename.c_str());
+    if (!is.good())
+        throw FabberRunDataError("Couldn't read input options file:" + filename);
+    std::string input;
+    while (std::getline(is, input))
+    {
+        input = trim(input);
+        if (input.size() > 0 && input[0] != '#')
+            AddKeyEqualsValue(input, true);
+    }
+}
+
+void FabberRunData::ParseOldStyleParamFile(const std::string &filename)
+{
+    std::ifstream is(filename.c_str());
+    if (!is.good())
+        throw FabberRunDataError("Couldn't read input file: -@ " + filename);
+    std::string param;
+    char c;
+    while (is.good())
+    {
+        if (!is.get(c))
+            c = '\n'; /* end of file terminates the last word */
+        if (!isspace((unsigned char)c))
+            param += c;
+        else if (param == "")
+        {
+        }
+        else if (param.compare(0, 2, "--") == 0)
+        {
+            AddKeyEqualsValue(param.substr(2));
+            param = "";
+        }
+        else if (param[0] == '#')
+        {
+            param = "";
+            while (is.good() && c != '\n')
+                is.get(c);
+        }
+        else if (param.compare(0, 2, "-@") == 0)
+            throw FabberRunDataError("Can only use -@ on the command line");
+        else
+            throw FabberRunDataError("Invalid data '" + param + "' found in file '" + filename + "'");
+    }
+}
+
+void FabberRunData::Parse(int argc, char **argv)
+{
+    m_params[""] = argv[0];
+    for (int a = 1; a < argc; a++)
+    {
+        const std::string arg = argv[a];
+        if (arg == "-f")
+        {
+            if (++a < argc)
+                ParseParamFile(argv[a]);
+            else
+                throw InvalidOptionValue("-f", "", "No filename specified");
+        }
+        else if (arg.compare(0, 2, "--") == 0)
+            AddKeyEqualsValue(arg.substr(2));
+        else if (arg == "-@")
+        {
+            if (++a < argc)
+                ParseOldStyleParamFile(argv[a]);
+            else
+                throw InvalidOptionValue("-@", "", "No filename specified");
+        }
+        else
+            throw FabberRunDataError("Option '" + arg + "' doesn't begin with --");
+    }
+    if (HaveKey("optfile"))
+        ParseOldStyleParamFile(GetString("optfile"));
+}
+
+void FabberRunData::LogParams()
+{
+    for (std::map<std::string, std::string>::const_iterator i = m_params.begin(); i != m_params.end(); ++i)
+        m_log << "FabberRunData::Parameter " << i->first << "=" << i->second << std::endl;
+}
+
+void FabberRunData::WarnOnce(const std::string &text)
+{
+    if (++m_warncount[text] == 1)
+        m_log << "WARNING ONCE: " << text << std::endl;
+}
+
+void FabberRunData::ReissueWarnings()
+{
+    if (m_warncount.empty())
+        return;
+    m_log << "\nSummary of warnings (" << m_warncount.size() << " distinct warnings)\n";
+    for (std::map<std::string, int>::const_iterator it = m_warncount.begin(); it != m_warncount.end(); ++it)
+        m_log << "Issued " << (it->second == 1 ? std::string("once: ") : stringify(it->second) + " times: ") << it->first
+              << std::endl;
+}
+
+void FabberRunData::CheckAllOptionsUsed()
+{
+    for (std::map<std::string, std::string>::const_iterator i = m_params.begin(); i != m_params.end(); ++i)
+        if (i->first != "" && m_used_params.count(i->first) == 0)
+            WarnOnce("Unused option specified: " + i->first);
+}
+
+static bool is_dir(const std::string &path)
+{
+    struct stat s;
+    return stat(path.c_str(), &s) == 0 && S_ISDIR(s.st_mode);
+}
+
+std::string FabberRunData::GetOutputDir()
+{
+    const bool link_to_latest = GetBool("link-to-latest");
+    if (m_outdir != "")
+        return m_outdir;
+    const std::string basename = GetStringDefault("output", "");
+    if (basename == "")
+    {
+        m_outdir = ".";
+        return m_outdir;
+    }
+    const bool overwrite = GetBool("overwrite");
+    m_outdir = basename;
+    for (int count = 0;; count++)
+    {
+        if (count >= 50)
+            throw FabberInternalError("Cannot create output directory (bad path, or too many + signs?): " + m_outdir);
+        errno = 0;
+        if (mkdir(m_outdir.c_str(), 0777) == 0)
+            break;
+        if (overwrite)
+        {
+            if (errno == EEXIST && is_dir(m_outdir))
+                break;
+            throw FabberInternalError("Unexpected problem creating output directory in overwrite mode: " + m_outdir);
+        }
+        m_outdir += "+";
+    }
+    if (link_to_latest)
+    {
+        /* "<output>_latest" -> the directory actually used; failure does not matter (rundata.cc:727-733) */
+        const std::string link = basename + "_latest";
+        unlink(link.c_str());
+        if (symlink(m_outdir.c_str(), link.c_str()) != 0)
+            m_log << "FabberRunData::link-to-latest failed" << std::endl;
+    }
+    return m_outdir;
+}
+
 /* rundata.cc:248-311 */
 void FabberRunData::Run(void (*progress_cb)(int, int))
 {
@@ -428,11 +729,18 @@ void FabberRunData::Run(void (*progress_cb)(int, int))
     time_t start;
     time(&start);
     m_log << "FabberRunData::Start time: " << ctime(&start);
+    LogParams();
     std::unique_ptr<FwdModel> fwd_model(FwdModel::NewFromName(GetString("model")));
     fwd_model->Initialize(*this);
     std::vector<Parameter> params;
     fwd_model->GetParameters(*this, params);
     m_log << "FabberRunData::Forward Model version " << fwd_model->ModelVersion() << std::endl;
+    if (GetBool("dump-param-names")) /* rundata.cc:277-286 */
+    {
+        std::ofstream param_file((GetStringDefault("output", ".") + "/paramnames.txt").c_str());
+        for (size_t i = 0; i < params.size(); i++)
+            param_file << params[i].name << std::endl;
+    }
 
     const std::string method = GetString("method");
     if (method != "vb" && method != "spatialvb")
@@ -445,6 +753,7 @@ void FabberRunData::Run(void (*progress_cb)(int, int))
     time_t end;
     time(&end);
     m_log << "FabberRunData::All done." << std::endl;
+    CheckAllOptionsUsed();
     m_log << "FabberRunData::End time: " << ctime(&end);
     m_log << "FabberRunData::Duration: " << (long)difftime(end, start) << " seconds." << std::endl;
     m_progress = nullptr;
