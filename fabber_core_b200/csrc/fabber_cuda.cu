@@ -60,6 +60,13 @@ static void keep_pool_memory()
 #include "vb_models.inc"
 #undef FAB_MODEL
 
+const ModelLaunchers *find_model(const fabber_cuda_model &m, int n_params)
+{
+    if (m.id == FABBER_MODEL_PLUGIN)
+        return static_cast<const ModelLaunchers *>(m.plugin_launchers); /* NULL: reported by the caller */
+    return find_model(m.id, n_params);
+}
+
 const ModelLaunchers *find_model(int model_id, int n_params)
 {
     struct Entry
@@ -408,6 +415,8 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
             return fail(FABBER_CUDA_ERR_INVALID, "image prior without image");
     }
     a.exp_dt = prob->model.exp_dt;
+    memcpy(a.model_consts, prob->model.consts, sizeof(a.model_consts));
+    a.design_len = prob->model.design_len;
     if (prob->model.id == FABBER_MODEL_POLY && prob->model.poly_degree + 1 != P)
         return fail(FABBER_CUDA_ERR_INVALID, "poly: n_params != degree + 1");
     if (prob->model.id == FABBER_MODEL_EXP && 2 * prob->model.exp_num != P)
@@ -476,11 +485,12 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
 
     /* stage the per-run constants */
     cudaError_t e;
-    if (prob->model.id == FABBER_MODEL_LINEAR)
+    const bool plugin_vec = prob->model.id == FABBER_MODEL_PLUGIN && prob->model.design && prob->model.design_len > 0;
+    if (prob->model.id == FABBER_MODEL_LINEAR || plugin_vec)
     {
         if (!prob->model.design)
             return fail(FABBER_CUDA_ERR_INVALID, "linear model without design matrix");
-        const size_t bytes = (size_t)T * P * sizeof(double);
+        const size_t bytes = (plugin_vec ? (size_t)prob->model.design_len : (size_t)T * P) * sizeof(double);
         if ((e = cudaMallocAsync((void **)&st.design, bytes, s)) != cudaSuccess)
             return cuda_fail(e, "cudaMallocAsync(design)");
         if ((e = cudaMemcpyAsync(st.design, prob->model.design, bytes, cudaMemcpyHostToDevice, s)) != cudaSuccess)
@@ -651,7 +661,7 @@ int fabber_cuda_vb_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cu
                 "prior type is spatial or unknown: use fabber_cuda_vb_spatial (inference_vb.cc:334-358)");
         }
     }
-    const ModelLaunchers *ml = find_model(prob->model.id, P);
+    const ModelLaunchers *ml = find_model(prob->model, P);
     if (!ml)
     {
         st.release(s);
@@ -716,7 +726,7 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
     }
     if (prob->spatial_dims < 0 || prob->spatial_dims > 3)
         return fail(FABBER_CUDA_ERR_INVALID, "spatial-dims must be 0, 1, 2 or 3"); /* priors.cc:191-194 */
-    const ModelLaunchers *ml = find_model(prob->model.id, P);
+    const ModelLaunchers *ml = find_model(prob->model, P);
     if (!ml)
         return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
     if (N == 0)
@@ -1152,7 +1162,7 @@ static int model_fit_impl(const fabber_cuda_vb_problem *prob, const double *mean
     const int P = prob->model.n_params, T = prob->n_times, N = prob->n_voxels;
     if (P < 1 || P > FABBER_CUDA_MAX_PARAMS || T < 1 || N < 0)
         return fail(FABBER_CUDA_ERR_INVALID, "bad sizes");
-    const ModelLaunchers *ml = find_model(prob->model.id, P);
+    const ModelLaunchers *ml = find_model(prob->model, P);
     if (!ml || !ml->model_fit)
         return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
     VbArgs a;
@@ -1162,17 +1172,20 @@ static int model_fit_impl(const fabber_cuda_vb_problem *prob, const double *mean
     for (int i = 0; i < P; i++)
         a.params[i] = prob->params[i];
     a.exp_dt = prob->model.exp_dt;
+    memcpy(a.model_consts, prob->model.consts, sizeof(a.model_consts));
+    a.design_len = prob->model.design_len;
     a.fit_mean = mean;
     a.fit_out = fit;
     a.fit_out_f32 = fit_f32;
     a.resid_out_f32 = resid_f32;
     a.data = data;
     Staged staged;
-    if (prob->model.id == FABBER_MODEL_LINEAR)
+    const bool plugin_vec = prob->model.id == FABBER_MODEL_PLUGIN && prob->model.design && prob->model.design_len > 0;
+    if (prob->model.id == FABBER_MODEL_LINEAR || plugin_vec)
     {
         if (!prob->model.design)
             return fail(FABBER_CUDA_ERR_INVALID, "linear model without design matrix");
-        const size_t bytes = (size_t)T * P * sizeof(double);
+        const size_t bytes = (plugin_vec ? (size_t)prob->model.design_len : (size_t)T * P) * sizeof(double);
         cudaError_t e = cudaMallocAsync((void **)&staged.design, bytes, st);
         if (e != cudaSuccess)
             return cuda_fail(e, "cudaMallocAsync(design)");

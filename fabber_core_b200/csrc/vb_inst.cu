@@ -1,6 +1,8 @@
 /*
  * vb_inst.cu - one translation unit per forward model: compiled repeatedly by the Makefile with
  *   -DFAB_FAMILY=<LinearModel|PolyModel|ExpModel> -DFAB_K=<template argument> -DFAB_GETTER=<symbol>
+ * A model plug-in (include/fabber_model_plugin.h) includes this file after defining its model struct, with
+ *   #define FAB_MODEL_TYPE <the struct>  and  #define FAB_GETTER <symbol>
  * Instantiates every kernel that model needs and exports its launcher table.
  */
 #include <cstdlib>
@@ -10,15 +12,19 @@
 #include "vb_voxelwise_ar.cuh"
 #include "vb_spatial.cuh"
 
-#if !defined(FAB_FAMILY) || !defined(FAB_K) || !defined(FAB_GETTER)
-#error "compile with -DFAB_FAMILY=.. -DFAB_K=.. -DFAB_GETTER=.."
+#if !defined(FAB_GETTER) || !(defined(FAB_MODEL_TYPE) || (defined(FAB_FAMILY) && defined(FAB_K)))
+#error "compile with -DFAB_FAMILY=.. -DFAB_K=.. -DFAB_GETTER=.. (or define FAB_MODEL_TYPE and FAB_GETTER)"
 #endif
 
 namespace fab
 {
 void count_launch();
 
+#ifdef FAB_MODEL_TYPE
+typedef FAB_MODEL_TYPE M;
+#else
 typedef FAB_FAMILY<FAB_K> M;
+#endif
 
 template <int NPHI, bool SNAP> static cudaError_t launch_white(const VbArgs &a, cudaStream_t s)
 {
@@ -154,6 +160,10 @@ static const ModelLaunchers g_launchers = {
     launch_sp_noise,
 };
 
+#ifdef FAB_MODEL_TYPE
+extern "C" const void *FAB_GETTER() { return &g_launchers; } /* plug-ins hand the table out through the C ABI */
+#else
 const ModelLaunchers *FAB_GETTER() { return &g_launchers; }
+#endif
 
 } // namespace fab

@@ -39,6 +39,8 @@ struct VbArgs
     const unsigned char *pattern; /* device [T]: phi index per sample, 255 = masked; NULL = all phi 0 */
     fabber_cuda_param params[FABBER_CUDA_MAX_PARAMS];
     double exp_dt;
+    double model_consts[FABBER_CUDA_MODEL_CONSTS]; /* plug-in models */
+    int design_len;                                /* plug-in models: doubles behind `design` */
     int n_phis;
     int n_per_phi[FAB_MAX_PHIS]; /* unmasked samples using each phi (Qi.Trace()) */
     int n_unmasked;              /* T - #masked */

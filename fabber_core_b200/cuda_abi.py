@@ -14,6 +14,8 @@ AR_NOISE_FIELDS = 7
 
 OK, ERR_INVALID, ERR_CUDA, ERR_BAD_VOXEL = 0, -1, -2, -3
 MODEL_LINEAR, MODEL_POLY, MODEL_EXP = 1, 2, 3
+MODEL_PLUGIN = 100
+MODEL_ORACLE_SINE = 101   # known to the test oracle only (oracle/vb_oracle.cc), never to the device library
 NOISE_WHITE, NOISE_AR1 = 0, 1
 CONV_MAXITS, CONV_FCHANGE, CONV_FREDUCE, CONV_TRIALMODE, CONV_LM = 0, 1, 2, 3, 4
 CONV_BY_NAME = {
@@ -34,6 +36,9 @@ class Model(C.Structure):
         ("poly_degree", C.c_int),
         ("exp_num", C.c_int),
         ("exp_dt", C.c_double),
+        ("plugin_launchers", C.c_void_p),
+        ("consts", C.c_double * 16),
+        ("design_len", C.c_int),
     ]
 
 
@@ -148,7 +153,7 @@ class ProblemSpec(object):
                  locked_noise_stdev=-1.0, convergence="maxits", max_iterations=10, fchange=0.01,
                  max_trials=10, need_f=None, f_history_len=0, allow_bad_voxels=False,
                  prior_types=None, spatial_dims=3, spatial_speed=-1.0, spatial_q1=10.0, spatial_q2=1.0,
-                 update_first_iter=False, param_overrides=None):
+                 update_first_iter=False, param_overrides=None, plugin_launchers=None):
         self.keep = []
         self.n_times = int(n_times)
         m = Model()
@@ -167,6 +172,16 @@ class ProblemSpec(object):
             for i in range(num_exps):
                 defaults.append(("amp%d" % (i + 1), 1.0, 1e5, 1.0, 1.5, "L"))
                 defaults.append(("r%d" % (i + 1), 1.0, 1e5, 1.0, 1.5, "L"))
+        elif model == "sine":
+            # the example plug-in model (fabber_core_b200/examples/sine_model.cu): a*sin(b*(t-c))+d.
+            # plugin_launchers=None describes it to the TEST ORACLE (which knows it as model id 101);
+            # with the table of a loaded plug-in library it is a device problem.
+            m.n_params = 4
+            m.consts[0] = dt
+            m.id = MODEL_PLUGIN if plugin_launchers else MODEL_ORACLE_SINE
+            m.plugin_launchers = plugin_launchers
+            defaults = [("a", 1.0, 1e6, 1.0, 1e6, "I"), ("b", 1.0, 1e6, 1.0, 1e6, "I"), ("c", 0.0, 1e6, 0.0, 1e6, "I"),
+                        ("d", 0.0, 1e6, 0.0, 1e6, "I")]
         else:
             raise ValueError("no device Evaluate hook for model %r" % model)
         self.param_names = [d[0] for d in defaults]

@@ -95,11 +95,18 @@ class Fabber(object):
 
     def _set_options(self, rundata):
         for key, value in rundata.items():
+            if key == "loadmodels":   # not an option of the run: load the library (py/fabber.py:507-513)
+                self.load_models(value)
+                continue
             if isinstance(value, bool):  # boolean options: key present with empty value
                 if not value:
                     continue
                 value = ""
             self._trycall(self.clib.fabber_set_opt, self.handle, str(key).encode(), str(value).encode(), self.errbuf)
+
+    def load_models(self, libpath):
+        """register the models of a plug-in library (fabber_load_models; py/fabber.py:505-513)"""
+        self._trycall(self.clib.fabber_load_models, self.handle, str(libpath).encode(), self.errbuf)
 
     # ---- self description ------------------------------------------------------------------------
     def get_methods(self):

@@ -61,10 +61,15 @@ int fabber_load_models(void *fab, const char *libpath, char *err_buf)
         return fabber_err(FABBER_ERR_FATAL, "Rundata is NULL", err_buf);
     if (!libpath)
         return fabber_err(FABBER_ERR_FATAL, "Library path is NULL", err_buf);
-    return fabber_err(FABBER_ERR_FATAL,
-        "Dynamically loaded CPU model libraries have no __device__ Evaluate hook; models available on the GPU "
-        "path: linear, poly, exp",
-        err_buf);
+    try
+    {
+        FwdModel::LoadFromDynamicLibrary(libpath);
+        return 0;
+    }
+    catch (std::exception &e)
+    {
+        return fabber_err(FABBER_ERR_FATAL, e.what(), err_buf);
+    }
 }
 
 int fabber_set_extent(void *fab, unsigned int nx, unsigned int ny, unsigned int nz, const int *mask, char *err_buf)

@@ -291,8 +291,11 @@ std::string ExpandPriorTypesString(std::string priors_str, unsigned num_params);
 class FwdModel
 {
 public:
+    typedef FwdModel *(*NewInstanceFptr)(void);
     static FwdModel *NewFromName(const std::string &name); /* registry names: setup.cc:44-47 + "exp" */
     static std::vector<std::string> GetKnown();
+    /* --loadmodels / fabber_load_models: register the models of a plug-in library (fwdmodel.cc:63-129) */
+    static void LoadFromDynamicLibrary(const std::string &filename, std::ostream *log = nullptr);
     virtual ~FwdModel() {}
     virtual std::string ModelVersion() const { return "b200"; }
     virtual std::string GetDescription() const { return ""; }
@@ -363,6 +366,8 @@ private:
 };
 
 const char *fabber_b200_version();
+/* bumped whenever FwdModel / Parameter / fabber_cuda_model / the launcher table change layout */
+#define FABBER_B200_PLUGIN_ABI 1
 
 /* tools.cc:27-40: VEST or plain ASCII matrix file -> row-major values */
 void read_matrix_file(const std::string &filename, std::vector<double> &values, int &rows, int &cols);

@@ -12,6 +12,10 @@
 #include <cmath>
 #include <fstream>
 
+#include <dlfcn.h>
+
+#include <mutex>
+
 #include "fabber_host.h"
 
 namespace fabber_b200
@@ -110,23 +114,100 @@ std::string ExpandPriorTypesString(std::string priors_str, unsigned num_params)
 }
 
 /* ---- registry (setup.cc:44-47; "exp" is the reference's example model library) ---------------------- */
+namespace
+{
+FwdModel *new_linear() { return new LinearFwdModel(); }
+FwdModel *new_poly() { return new PolynomialFwdModel(); }
+FwdModel *new_exp() { return new ExpFwdModel(); }
+std::mutex g_registry_mu;
+std::map<std::string, FwdModel::NewInstanceFptr> &registry()
+{
+    static std::map<std::string, FwdModel::NewInstanceFptr> r;
+    if (r.empty())
+    {
+        r["linear"] = new_linear;
+        r["poly"] = new_poly;
+        r["exp"] = new_exp;
+    }
+    return r;
+}
+} // namespace
+
 FwdModel *FwdModel::NewFromName(const std::string &name)
 {
-    if (name == "linear")
-        return new LinearFwdModel();
-    if (name == "poly")
-        return new PolynomialFwdModel();
-    if (name == "exp")
-        return new ExpFwdModel();
-    throw InvalidOptionValue("model", name, "Unrecognized forward model (models with a device hook: linear, poly, exp)");
+    NewInstanceFptr make = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(g_registry_mu);
+        std::map<std::string, NewInstanceFptr>::const_iterator it = registry().find(name);
+        if (it != registry().end())
+            make = it->second;
+    }
+    if (!make)
+    {
+        std::string known;
+        const std::vector<std::string> k = GetKnown();
+        for (size_t i = 0; i < k.size(); i++)
+            known += (i ? ", " : "") + k[i];
+        throw InvalidOptionValue("model", name, "Unrecognized forward model (models with a device hook: " + known + ")");
+    }
+    return make();
 }
 std::vector<std::string> FwdModel::GetKnown()
 {
+    std::lock_guard<std::mutex> lock(g_registry_mu);
     std::vector<std::string> k;
-    k.push_back("exp");
-    k.push_back("linear");
-    k.push_back("poly");
+    for (std::map<std::string, NewInstanceFptr>::const_iterator it = registry().begin(); it != registry().end(); ++it)
+        k.push_back(it->first);
     return k;
+}
+
+/* fwdmodel.cc:63-129: a plug-in library exports get_num_models / get_model_name / get_new_instance_func,
+ * exactly the reference's three symbols; what it returns are FwdModel objects of THIS library whose
+ * GetDeviceModel() names the plug-in's own kernels (include/fabber_model_plugin.h). */
+void FwdModel::LoadFromDynamicLibrary(const std::string &filename, std::ostream *log)
+{
+    typedef int (*GetNumModelsFptr)(void);
+    typedef const char *(*GetModelNameFptr)(int);
+    typedef NewInstanceFptr (*GetNewInstanceFptrFptr)(const char *);
+    if (log)
+        *log << "Loading dynamic models from " << filename << std::endl;
+    void *lib = dlopen(filename.c_str(), RTLD_NOW | RTLD_GLOBAL);
+    if (!lib)
+        throw InvalidOptionValue("loadmodels", filename, std::string("Failed to open library ") + dlerror());
+    GetNumModelsFptr get_num_models = (GetNumModelsFptr)dlsym(lib, "get_num_models");
+    if (!get_num_models)
+        throw InvalidOptionValue("loadmodels", filename, "Failed to resolve symbol 'get_num_models'");
+    GetModelNameFptr get_model_name = (GetModelNameFptr)dlsym(lib, "get_model_name");
+    if (!get_model_name)
+        throw InvalidOptionValue("loadmodels", filename, "Failed to resolve symbol 'get_model_name'");
+    GetNewInstanceFptrFptr get_new_instance = (GetNewInstanceFptrFptr)dlsym(lib, "get_new_instance_func");
+    if (!get_new_instance)
+        throw InvalidOptionValue("loadmodels", filename, "Failed to resolve symbol 'get_new_instance_func'");
+    /* a plug-in built against another layout of the host classes or of fabber_cuda.h must not be used */
+    typedef int (*AbiFptr)(void);
+    AbiFptr abi = (AbiFptr)dlsym(lib, "fabber_b200_plugin_abi");
+    if (!abi || abi() != FABBER_B200_PLUGIN_ABI)
+        throw InvalidOptionValue("loadmodels", filename,
+            "not a fabber_core_b200 model plug-in of this ABI version (the reference's CPU model libraries have no "
+            "__device__ Evaluate hook: rebuild the model with include/fabber_model_plugin.h)");
+    const int n = get_num_models();
+    if (log)
+        *log << "Loading " << n << " models" << std::endl;
+    for (int i = 0; i < n; i++)
+    {
+        const char *name = get_model_name(i);
+        if (!name)
+            throw InvalidOptionValue("loadmodels", filename,
+                "Dynamic library failed to return model name for index " + stringify(i));
+        if (log)
+            *log << "Loading model " << name << std::endl;
+        NewInstanceFptr make = get_new_instance(name);
+        if (!make)
+            throw InvalidOptionValue("loadmodels", filename,
+                std::string("Dynamic library failed to return new instance function for model") + name);
+        std::lock_guard<std::mutex> lock(g_registry_mu);
+        registry()[name] = make;
+    }
 }
 
 /* fwdmodel.cc:210-282 */

@@ -562,10 +562,10 @@ void FabberRunData::AddKeyEqualsValue(const std::string &exp, bool trim_comments
         const std::string value = trim(exp.substr(eq + 1, end == std::string::npos ? end : end - (eq + 1)));
         if (m_params.count(key) > 0)
             throw InvalidOptionValue(key, value, "Already has a value: " + m_params[key]);
-        if (key == "loadmodels")
-            throw InvalidOptionValue(key, value,
-                "dynamic model libraries hold host code; models here are __device__ hooks compiled into the library");
-        m_params[key] = value;
+        if (key == "loadmodels") /* rundata.cc:440-443: acted on at once, not stored */
+            FwdModel::LoadFromDynamicLibrary(value, &m_log);
+        else
+            m_params[key] = value;
     }
     else
         m_params[exp] = "";

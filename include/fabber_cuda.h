@@ -45,6 +45,10 @@ extern "C" {
 #define FABBER_MODEL_LINEAR 1 /* fwdmodel_linear.cc:92-96  */
 #define FABBER_MODEL_POLY 2   /* fwdmodel_poly.cc:62-80    */
 #define FABBER_MODEL_EXP 3    /* examples/fwdmodel_exp.cc:65-82 */
+/* a model from a plug-in library (the --loadmodels mechanism, fwdmodel.cc:63-129): the kernels live in the
+ * plug-in, fabber_cuda_model.plugin_launchers points at its launcher table (include/fabber_model_plugin.h) */
+#define FABBER_MODEL_PLUGIN 100
+#define FABBER_CUDA_MODEL_CONSTS 16
 
 /* noise models */
 #define FABBER_NOISE_WHITE 0 /* noisemodel_white.cc */
@@ -80,6 +84,12 @@ typedef struct fabber_cuda_model
     /* EXP */
     int exp_num;   /* number of exponentials, P = 2 * exp_num, params (amp_k, r_k) */
     double exp_dt; /* sample spacing */
+    /* PLUGIN: launcher table of the plug-in's kernels (const fab::ModelLaunchers *), scalar constants the
+     * plug-in's device hooks read, and optionally a vector of `design_len` doubles passed through `design`
+     * (HOST pointer, copied by the library; e.g. a list of inversion times) */
+    const void *plugin_launchers;
+    double consts[FABBER_CUDA_MODEL_CONSTS];
+    int design_len;
 } fabber_cuda_model;
 
 typedef struct fabber_cuda_param

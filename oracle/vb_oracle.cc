@@ -453,6 +453,8 @@ inline double model_exp(double x)
     return e;
 }
 
+static const int ORACLE_MODEL_SINE = 101; // cuda_abi.MODEL_ORACLE_SINE
+
 void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
 {
     const fabber_cuda_model &m = mc.prob->model;
@@ -497,6 +499,16 @@ void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
                 double val = amp * model_exp(-r * t);
                 result[i] += val;
             }
+        }
+    }
+    else if (m.id == ORACLE_MODEL_SINE)
+    {
+        // not a reference model: the example PLUG-IN model of fabber_core_b200/examples/sine_model.cu, restated
+        // here so that the plug-in path has an independent checker.  g = a sin(b (t - c)) + d, t = i dt
+        for (int i = 0; i < T; i++)
+        {
+            double t = double(i) * m.consts[0];
+            result[i] = p[0] * std::sin(p[1] * (t - p[2])) + p[3];
         }
     }
     else
