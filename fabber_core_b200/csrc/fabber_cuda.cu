@@ -640,7 +640,15 @@ int fabber_cuda_scatter_voxels(const double *in, int n_rows, int n_voxels, const
 
 int fabber_cuda_vb_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream)
 {
+    return fabber_cuda_vb_voxelwise_range(prob, buf, 0, prob ? prob->n_voxels : 0, stream);
+}
+
+int fabber_cuda_vb_voxelwise_range(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, int v_begin,
+    int v_end, void *stream)
+{
     cudaStream_t s = (cudaStream_t)stream;
+    if (prob && (v_begin < 0 || v_end > prob->n_voxels || v_begin > v_end))
+        return fail(FABBER_CUDA_ERR_INVALID, "voxel range outside [0, n_voxels]");
     VbArgs a;
     Staged st;
     bool general = false;
@@ -680,11 +688,57 @@ int fabber_cuda_vb_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cu
         st.release(s);
         return fail(FABBER_CUDA_ERR_INVALID, "noise model not available for this model");
     }
+    a.v_begin = v_begin;
+    a.v_end = v_end;
     cudaError_t e = fn(a, s);
     st.release(s);
     if (e != cudaSuccess)
         return cuda_fail(e, "vb_voxelwise launch");
     return FABBER_CUDA_OK;
+}
+
+/* events and a second stream: what a host needs to overlap the upload of one block of voxels with the
+ * calculation on the previous one (fabber_cuda_vb_voxelwise_range) */
+void *fabber_cuda_stream_create(void)
+{
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess)
+        return nullptr;
+    return s;
+}
+void fabber_cuda_stream_destroy(void *stream)
+{
+    if (stream)
+        cudaStreamDestroy((cudaStream_t)stream);
+}
+void *fabber_cuda_event_create(void)
+{
+    cudaEvent_t e = nullptr;
+    if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess)
+        return nullptr;
+    return e;
+}
+void fabber_cuda_event_destroy(void *event)
+{
+    if (event)
+        cudaEventDestroy((cudaEvent_t)event);
+}
+int fabber_cuda_event_record(void *event, void *stream)
+{
+    cudaError_t e = cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaEventRecord");
+}
+int fabber_cuda_stream_wait_event(void *stream, void *event)
+{
+    cudaError_t e = cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaStreamWaitEvent");
+}
+int fabber_cuda_memcpy2d_h2d(void *dst, unsigned long long dst_pitch, const void *src, unsigned long long src_pitch,
+    unsigned long long width_bytes, unsigned long long rows, void *stream)
+{
+    cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyHostToDevice,
+        (cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaMemcpy2DAsync");
 }
 
 int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream)

@@ -28,7 +28,7 @@ typedef FAB_FAMILY<FAB_K> M;
 
 template <int NPHI, bool SNAP> static cudaError_t launch_white(const VbArgs &a, cudaStream_t s)
 {
-    if (a.N <= 0)
+    if (a.v_end <= a.v_begin)
         return cudaSuccess;
     typedef WhiteVoxel<M, NPHI, SNAP> Vox;
     const size_t smem = M::smem_bytes(a.T) + (size_t)(Vox::STASH_DOUBLES + Vox::SNAP_DOUBLES) * VB_BLOCK * sizeof(double)
@@ -40,7 +40,7 @@ template <int NPHI, bool SNAP> static cudaError_t launch_white(const VbArgs &a, 
         if (e != cudaSuccess)
             return e;
     }
-    const unsigned grid = (unsigned)((a.N + VB_BLOCK - 1) / VB_BLOCK);
+    const unsigned grid = (unsigned)((a.v_end - a.v_begin + VB_BLOCK - 1) / VB_BLOCK);
     kern<<<grid, VB_BLOCK, smem, s>>>(a);
     count_launch();
     return cudaGetLastError();
@@ -48,7 +48,7 @@ template <int NPHI, bool SNAP> static cudaError_t launch_white(const VbArgs &a, 
 
 static cudaError_t launch_ar(const VbArgs &a, cudaStream_t s)
 {
-    if (a.N <= 0)
+    if (a.v_end <= a.v_begin)
         return cudaSuccess;
     typedef ArVoxel<M> Vox;
     const bool use_snap = a.conv_type == FABBER_CONV_TRIALMODE || a.conv_type == FABBER_CONV_FREDUCE;
@@ -61,7 +61,7 @@ static cudaError_t launch_ar(const VbArgs &a, cudaStream_t s)
         if (e != cudaSuccess)
             return e;
     }
-    const unsigned grid = (unsigned)((a.N + VB_BLOCK - 1) / VB_BLOCK);
+    const unsigned grid = (unsigned)((a.v_end - a.v_begin + VB_BLOCK - 1) / VB_BLOCK);
     kern<<<grid, VB_BLOCK, smem, s>>>(a);
     count_launch();
     return cudaGetLastError();

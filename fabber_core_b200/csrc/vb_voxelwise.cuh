@@ -34,6 +34,7 @@ constexpr int VB_BLOCK = 128;
 struct VbArgs
 {
     int N, T;
+    int v_begin, v_end; /* voxelwise kernels work on voxels [v_begin, v_end) of the N (N stays the array stride) */
     const float *data;          /* [T][N] */
     const double *design;       /* device [T][P], linear model */
     const unsigned char *pattern; /* device [T]: phi index per sample, 255 = masked; NULL = all phi 0 */
@@ -593,8 +594,8 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) vb_voxelwise_white_k
         for (int i = threadIdx.x; i < a.T; i += blockDim.x)
             pat[i] = a.pattern ? a.pattern[i] : 0;
     __syncthreads();
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.N)
+    const int v = a.v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.v_end)
         return;
     const typename Model::Ctx mc = Model::make_ctx(a, smem);
     const size_t N = (size_t)a.N;

@@ -415,8 +415,8 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_AR_MIN_BLOCKS) vb_voxelwise_ar_k
     volatile double *park = smem + Model::smem_bytes(a.T) / sizeof(double) + threadIdx.x;
     volatile double *snap = park + Vox::STASH_DOUBLES * VB_BLOCK;
     __syncthreads();
-    const int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= a.N)
+    const int v = a.v_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= a.v_end)
         return;
     const typename Model::Ctx mc = Model::make_ctx(a, smem);
     const size_t N = (size_t)a.N;

@@ -124,6 +124,15 @@ struct VoxelData
     size_t cols;
     float *f;   /* pinned host memory [rows][cols] */
     float *dev; /* optional device-resident copy (main data: uploaded while it is being set) */
+    /* the upload of `dev` goes block of voxels by block of voxels on a copy stream; `ready` is recorded there
+     * after columns [v0, v1) have been queued, so a consumer can start on a block while later ones travel */
+    struct Block
+    {
+        size_t v0, v1;
+        void *ready; /* fabber_cuda event */
+    };
+    std::vector<Block> blocks;
+    void wait_uploaded(); /* make the default stream wait for every block */
     VoxelData();
     ~VoxelData();
     VoxelData(const VoxelData &) = delete;

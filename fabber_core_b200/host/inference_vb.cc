@@ -484,7 +484,23 @@ void Vb::DoCalculations(FabberRunData &rundata)
     buf.f_history = m_fhist_len > 0 ? (double *)m_d_hist.p : nullptr;
     rundata.Log() << "Vb::timing: option translation + device buffers " << sw.lap_ms() << " ms" << std::endl;
 
-    int rc = spatial ? fabber_cuda_vb_spatial(&prob, &buf, nullptr) : fabber_cuda_vb_voxelwise(&prob, &buf, nullptr);
+    int rc = FABBER_CUDA_OK;
+    if (spatial || data.blocks.size() <= 1)
+    {
+        data.wait_uploaded();
+        rc = spatial ? fabber_cuda_vb_spatial(&prob, &buf, nullptr) : fabber_cuda_vb_voxelwise(&prob, &buf, nullptr);
+    }
+    else
+    {
+        /* voxels are independent (inference_vb.cc:423-571): one launch per uploaded block, each behind its
+         * block's event - block k computes while the blocks after it are still on the PCIe bus */
+        for (size_t b = 0; b < data.blocks.size() && rc == FABBER_CUDA_OK; b++)
+        {
+            rc = fabber_cuda_stream_wait_event(nullptr, data.blocks[b].ready);
+            if (rc == FABBER_CUDA_OK)
+                rc = fabber_cuda_vb_voxelwise_range(&prob, &buf, (int)data.blocks[b].v0, (int)data.blocks[b].v1, nullptr);
+        }
+    }
     if (rc == FABBER_CUDA_ERR_INVALID)
         throw FabberRunDataError(std::string("Vb: ") + fabber_cuda_last_error());
     check(rc, "VB kernels");

@@ -166,11 +166,30 @@ VoxelData::VoxelData()
     , dev(nullptr)
 {
 }
+/* one copy stream for the life of the process: uploads run beside whatever the default stream computes */
+static void *copy_stream()
+{
+    static void *s = fabber_cuda_stream_create();
+    return s;
+}
+
+void VoxelData::wait_uploaded()
+{
+    for (size_t i = 0; i < blocks.size(); i++)
+        fabber_cuda_stream_wait_event(nullptr, blocks[i].ready);
+}
+
 VoxelData::~VoxelData()
 {
     /* work queued on the device may still read these blocks: drain it before they can be handed out again */
     if (dev)
+    {
+        if (!blocks.empty())
+            fabber_cuda_stream_sync(copy_stream());
         fabber_cuda_stream_sync(nullptr);
+    }
+    for (size_t i = 0; i < blocks.size(); i++)
+        fabber_cuda_event_destroy(blocks[i].ready);
     cached_pinned_free(f, bytes());
     cached_device_free(dev, bytes());
 }
@@ -339,32 +358,55 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
     vd->alloc(data_size, N);
     float *dst_all = vd->f;
     const std::vector<int> &index = m_voxel_index;
-    /* The main series goes straight on to the GPU: rows are staged into pinned memory in ~64 MB chunks by
-     * all host cores and each chunk's host->device copy is queued as soon as it is staged, so the PCIe
-     * transfer of chunk k overlaps the staging of chunk k+1. */
+    /* The main series goes straight on to the GPU, BLOCK OF VOXELS BY BLOCK OF VOXELS: all host cores stage
+     * the columns [v0, v1) of every row into pinned memory, the block's strided host->device copy is queued
+     * on the copy stream, an event marks it - and the next block is staged while that one travels. Voxelwise
+     * VB (Vb::DoCalculations) then starts each block's kernel on its event, so the arithmetic of block k
+     * also overlaps the transfer of the blocks after it. */
     /* ("data" itself, or the file the data option names when a file-based front end loads it) */
     const bool is_main = key == "data" || (m_params.count("data") && m_params["data"] == key);
     const bool upload = is_main && N > 0 && fabber_cuda_device_count() > 0;
     if (upload)
         vd->dev = (float *)cached_device_alloc(vd->bytes());
-    const size_t rows_per_chunk = std::max<size_t>(1, ((size_t)64 << 20) / std::max<size_t>(1, N * sizeof(float)));
-    for (size_t r0 = 0; r0 < (size_t)data_size; r0 += rows_per_chunk)
+    /* ~96 MB per block, at most 64 blocks, at least 64k voxels each (a block is also one kernel launch) */
+    const size_t total = (size_t)data_size * N * sizeof(float);
+    size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, total / ((size_t)96 << 20)));
+    n_blocks = std::max<size_t>(1, std::min(n_blocks, N / 65536));
+    if (!upload)
+        n_blocks = 1;
+    const size_t per_block = ((N + n_blocks - 1) / n_blocks + 127) / 128 * 128; /* whole CTAs of 128 voxels */
+    const size_t T = (size_t)data_size;
+    for (size_t v0 = 0; v0 < N; v0 += per_block)
     {
-        const size_t r1 = std::min<size_t>(data_size, r0 + rows_per_chunk);
-        const size_t off = r0 * N, cnt = (r1 - r0) * N;
-        if (N == n_grid)
-            parallel_for(cnt, [&](size_t b, size_t e) { memcpy(dst_all + off + b, data + off + b, (e - b) * sizeof(float)); },
-                (size_t)1 << 20);
-        else
-            parallel_for(cnt, [&](size_t b, size_t e) {
-                for (size_t i = off + b; i < off + e; i++)
-                {
-                    const size_t t = i / N, v = i - t * N;
-                    dst_all[i] = data[t * n_grid + index[v]];
-                }
-            });
-        if (upload && fabber_cuda_memcpy_h2d(vd->dev + off, dst_all + off, cnt * sizeof(float), nullptr) != FABBER_CUDA_OK)
-            throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+        const size_t v1 = std::min(N, v0 + per_block), w = v1 - v0;
+        /* work item = (row, piece of the block's columns): contiguous runs in both source and destination */
+        const size_t piece = (size_t)1 << 18, pieces = (w + piece - 1) / piece;
+        parallel_for(T * pieces, [&](size_t b, size_t e) {
+            for (size_t i = b; i < e; i++)
+            {
+                const size_t t = i / pieces, c0 = v0 + (i - t * pieces) * piece, c1 = std::min(v1, c0 + piece);
+                if (N == n_grid)
+                    memcpy(dst_all + t * N + c0, data + t * N + c0, (c1 - c0) * sizeof(float));
+                else
+                    for (size_t v = c0; v < c1; v++)
+                        dst_all[t * N + v] = data[t * n_grid + index[v]];
+            }
+        }, 1);
+        if (upload)
+        {
+            VoxelData::Block blk;
+            blk.v0 = v0;
+            blk.v1 = v1;
+            blk.ready = fabber_cuda_event_create();
+            int rc = blk.ready ? fabber_cuda_memcpy2d_h2d(vd->dev + v0, N * sizeof(float), dst_all + v0, N * sizeof(float),
+                                     w * sizeof(float), T, copy_stream())
+                               : FABBER_CUDA_ERR_CUDA;
+            if (rc == FABBER_CUDA_OK)
+                rc = fabber_cuda_event_record(blk.ready, copy_stream());
+            vd->blocks.push_back(blk);
+            if (rc != FABBER_CUDA_OK)
+                throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+        }
     }
     m_voxel_data[key] = std::move(vd);
 }

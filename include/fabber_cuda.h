@@ -195,6 +195,22 @@ int fabber_cuda_scatter_voxels(const double *in, int n_rows, int n_voxels, const
 int fabber_cuda_vb_voxelwise(
     const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream);
 
+/* The same on the voxels [v_begin, v_end) only; n_voxels stays the stride of every [field][N] array. Voxels
+ * are independent in this mode (inference_vb.cc:423-571), so a host can upload the series in blocks of
+ * voxels and start each block's calculation as soon as its data has arrived - upload and arithmetic
+ * overlap. The helpers below are all that needs: a second (non-blocking) stream for the copies, events,
+ * and a strided host -> device copy of one block of columns. */
+int fabber_cuda_vb_voxelwise_range(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
+    int v_begin, int v_end, void *stream);
+void *fabber_cuda_stream_create(void);
+void fabber_cuda_stream_destroy(void *stream);
+void *fabber_cuda_event_create(void);
+void fabber_cuda_event_destroy(void *event);
+int fabber_cuda_event_record(void *event, void *stream);
+int fabber_cuda_stream_wait_event(void *stream, void *event);
+int fabber_cuda_memcpy2d_h2d(void *dst, unsigned long long dst_pitch, const void *src, unsigned long long src_pitch,
+    unsigned long long width_bytes, unsigned long long rows, void *stream);
+
 /* Spatial VB (iteration-major; replaces Vb::DoCalculationsSpatial, inference_vb.cc:578-767,
  * SpatialPrior::CalculateaK / ApplyToMVN priors.cc:221-488, Vb::CalcNeighbours :830-964).
  * Synchronous. Single-GPU entry; multi-GPU z-slab sharding is driven from the host layer. */
