@@ -240,27 +240,36 @@ def _reference_worker(job):
     return dt, its, n
 
 
-def reference_throughput(wname, procs, budget_s):
+def reference_throughput(wname, procs, budget_s, pool=None, per_voxel=None, seed=100):
     """Voxel-iterations/s of the reference's own code on `procs` processes over disjoint voxel chunks -
-    how fabber is parallelised in practice (it is single-threaded). Bounded sample sized from a probe."""
+    how fabber is parallelised in practice (it is single-threaded). Bounded sample sized from a probe.
+    `pool` / `per_voxel`: a caller timing several steps keeps one pool of warmed-up workers and one probe
+    (taken with every worker busy) instead of paying process start-up and imports per step."""
     import multiprocessing as mp
 
     w = WORKLOADS[wname]
     probe_n = 216 if w.get("spatial") else 128
-    dt, its, _ = _reference_worker((wname, probe_n, 0))
-    per_voxel = dt / probe_n
-    n = int(max(probe_n, min(100000, budget_s / per_voxel)))
-    if w.get("spatial"):
-        side = max(4, int(round(n ** (1.0 / 3))))
-        n = side ** 3
-    ctx = mp.get_context("spawn")
-    t0 = time.perf_counter()
-    with ctx.Pool(procs) as pool:
-        res = pool.map(_reference_worker, [(wname, n, 100 + i) for i in range(procs)])
-    wall = time.perf_counter() - t0
+    own_pool = pool is None
+    if own_pool:
+        pool = mp.get_context("spawn").Pool(procs)
+    try:
+        if per_voxel is None:
+            res = pool.map(_reference_worker, [(wname, probe_n, i) for i in range(procs)], chunksize=1)
+            per_voxel = max(r[0] for r in res) / probe_n
+        n = int(max(probe_n, min(100000, budget_s / per_voxel)))
+        if w.get("spatial"):
+            side = max(4, int(round(n ** (1.0 / 3))))
+            n = side ** 3
+        t0 = time.perf_counter()
+        res = pool.map(_reference_worker, [(wname, n, seed + i) for i in range(procs)], chunksize=1)
+        wall = time.perf_counter() - t0
+    finally:
+        if own_pool:
+            pool.close()
+            pool.join()
     compute = max(r[0] for r in res)
     total_its = sum(r[1] for r in res)
-    return total_its / compute, compute, n * procs, wall
+    return total_its / compute, compute, n * procs, wall, per_voxel
 
 
 def oracle_run(w, y):
@@ -438,14 +447,26 @@ def main():
         use_ref = os.path.exists(REF_LIB)
         rates = []
         t_all0 = time.perf_counter()
-        per_step = max(2.0, 90.0 / (args.warmup + args.steps))
-        for i in range(args.warmup + args.steps):
-            if use_ref:
-                rate, dt, n, _ = reference_throughput(args.workload, cores, budget_s=per_step)
-            else:
-                rate, dt, n = oracle_throughput(w, cores, budget_s=per_step)
-            if i >= args.warmup:
-                rates.append((rate, dt, n))
+        # ~75 s of reference compute over all steps (plus worker start-up), whatever K and W are
+        per_step = max(1.5, 75.0 / (args.warmup + args.steps))
+        pool, per_voxel = None, None
+        if use_ref:
+            import multiprocessing as mp
+
+            pool = mp.get_context("spawn").Pool(cores)
+        try:
+            for i in range(args.warmup + args.steps):
+                if use_ref:
+                    rate, dt, n, _, per_voxel = reference_throughput(args.workload, cores, budget_s=per_step, pool=pool,
+                                                                     per_voxel=per_voxel, seed=100 + 1000 * i)
+                else:
+                    rate, dt, n = oracle_throughput(w, cores, budget_s=per_step)
+                if i >= args.warmup:
+                    rates.append((rate, dt, n))
+        finally:
+            if pool is not None:
+                pool.close()
+                pool.join()
         value = float(np.mean([r[0] for r in rates]))
         ms = float(np.mean([r[1] for r in rates]) * 1e3)
         kind = "reference" if use_ref else "port"
@@ -618,7 +639,7 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             prate, pdt, pn = oracle_throughput(w, 1, budget_s=8.0)
             if os.path.exists(REF_LIB):
-                rate, dt, n, _ = reference_throughput(args.workload, 1, budget_s=12.0)
+                rate, dt, n, _, _ = reference_throughput(args.workload, 1, budget_s=12.0)
                 line["cpu_baseline"] = {
                     "value": rate, "unit": "voxel-iterations/s", "cores": 1, "kind": "reference",
                     "sample": "%d voxels of the same synthetic workload, %.1f s, one process: the reference's own "
