@@ -169,6 +169,14 @@ class VbRun(object):
         fn = lib().fabber_cuda_vb_spatial if self.spatial else lib().fabber_cuda_vb_voxelwise
         return fn(C.byref(prob), C.byref(self.buf), stream)
 
+    def launch_range(self, v_begin, v_end, stream=None):
+        """voxelwise VB on the voxels [v_begin, v_end) only (fabber_cuda_vb_voxelwise_range)"""
+        prob = self.spec.prob
+        prob.n_voxels = self.N
+        fn = lib().fabber_cuda_vb_voxelwise_range
+        fn.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        return fn(C.byref(prob), C.byref(self.buf), int(v_begin), int(v_end), stream)
+
     def sync(self, stream=None):
         check(lib().fabber_cuda_stream_sync(stream), "stream sync")
 

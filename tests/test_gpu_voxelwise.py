@@ -272,3 +272,27 @@ def test_full_size_properties_c4():
     mk = lambda: abi.ProblemSpec("linear", 200, design=synth.ar_design(200), noise="ar", need_f=True)
     big = _full_size_sample_check(mk, y, 4, "C4 per-GPU-size sample", 2053)
     assert abs(np.median(big["noise"][2]) - 0.3) < 0.02   # AR coefficient recovered
+
+
+@pytest.mark.parametrize("noise", ["white", "ar"])
+def test_voxel_range_launches_tile_the_volume(noise):
+    """fabber_cuda_vb_voxelwise_range: launching disjoint voxel ranges (uneven, not multiples of the CTA
+    size, one of them empty) gives bit for bit what one launch over everything gives - what the host relies
+    on when it starts each uploaded block of voxels on its own."""
+    n, T = 1000, 40
+    y = synth.poly_volume(n, T, 2, seed=77).numpy()
+    kw = dict(degree=2, noise=noise, need_f=True, max_iterations=6)
+    whole = device.run(abi.ProblemSpec("poly", T, **kw), y)
+    run = device.VbRun(abi.ProblemSpec("poly", T, **kw), n)
+    try:
+        run.set_data(y)
+        for a, b in ((300, 301), (0, 130), (130, 300), (301, 301), (301, 1000)):
+            assert run.launch_range(a, b) == abi.OK
+        run.sync()
+        parts = run.results()
+        for k in ("mean", "cov", "noise", "free_energy", "iterations", "status"):
+            assert np.array_equal(parts[k], whole[k]), k
+        assert run.launch_range(-1, 10) == abi.ERR_INVALID and run.launch_range(5, 1001) == abi.ERR_INVALID
+        assert run.launch_range(10, 5) == abi.ERR_INVALID
+    finally:
+        run.close()
