@@ -37,7 +37,8 @@ WORKLOADS = {
                spec=dict(num_exps=2, dt=0.02, convergence="lm", need_f=True,
                          param_overrides={"r2": {"mean": 6.0}}), P=4, e=46, e0=80,
                capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "vb", "convergence": "lm",
-                     "max-iterations": 10, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0}),
+                     "max-iterations": 10, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0},
+               traffic=(6.506453e9 + 2.406503e9, "profiles/r1b_ncu_full_c3_exp2.txt")),
     # BASELINE.json configs[3]: linear model (synthetic 200 x 4 design), AR(1) noise, synthetic 256^3 x 200
     # (the reference has no AR(2): Ar1cNoiseModel only, setup.cc:39)
     "c4": dict(name="C4 linear(200x4 design) VB AR(1) noise (num-echoes 1, cross-terms none), synthetic "
@@ -625,7 +626,13 @@ def main():
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf > 0 else None, "traffic": None,
+                         "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
+                         # DRAM bytes of one launch from the committed ncu --set full capture (only quoted at
+                         # the size it was captured at); algorithmic bytes are in "hbm" below
+                         "traffic": (w["traffic"][0] if "traffic" in w and n_vox == w["side"] ** 3 else None),
+                         "traffic_unit": "bytes per launch (dram read + write)",
+                         "traffic_source": (w["traffic"][1] if "traffic" in w and n_vox == w["side"] ** 3 else None),
+                         "algorithmic_bytes_per_launch": bytes_per_launch,
                          "peak_source": "measured live: dependent-free DFMA loop on all SMs "
                                         "(MEASURED_PEAKS.json has no FP64 figure)",
                          "flop_per_voxel_iteration": W, "kernel": ("sp_noise_kernel (+ sp_theta / sp_sweep / sp_ak)" if spatial else "vb_voxelwise_ar_kernel"

@@ -417,6 +417,11 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
     a.exp_dt = prob->model.exp_dt;
     memcpy(a.model_consts, prob->model.consts, sizeof(a.model_consts));
     a.design_len = prob->model.design_len;
+    {
+        /* opt-in, default off: see recentre_loop (vb_voxelwise.cuh) */
+        const char *bj = getenv("FABBER_B200_BASIS_JACOBIAN");
+        a.basis_jacobian = (bj && bj[0] == '1') ? 1 : 0;
+    }
     if (prob->model.id == FABBER_MODEL_POLY && prob->model.poly_degree + 1 != P)
         return fail(FABBER_CUDA_ERR_INVALID, "poly: n_params != degree + 1");
     if (prob->model.id == FABBER_MODEL_EXP && 2 * prob->model.exp_num != P)

@@ -14,6 +14,11 @@
  *                          Every value is bit-identical to calling eval() on the perturbed vector;
  *                          models override it only to share sub-expressions that provably do not
  *                          depend on the perturbed element (e.g. exp(-r t) when an amplitude moves).
+ *   LINEAR / basis_row()   models that are LINEAR IN THEIR MODEL-SPACE PARAMETERS (g = sum_j phi_j(t) p_j) say so
+ *                          and hand out phi: the central difference of such a model is phi_j times the
+ *                          difference quotient of the parameter transform, up to the rounding noise of the
+ *                          subtraction, so the pass needs one evaluation per sample instead of 2P+1
+ *                          (recentre_loop in vb_voxelwise.cuh; opt-in with FABBER_B200_BASIS_JACOBIAN=1)
  *   HAS_FAST / fast_ok()   optional: a cheaper eval_fd<true> that is valid only for a range of parameters
  *                          (exp: the table-based exponential of vb_exp.cuh needs |r t| < 708); the pass
  *                          checks fast_ok() once, outside the time loop, and otherwise runs eval_fd<false>
@@ -78,6 +83,21 @@ template <int P_> struct LinearModel
         int t;
     };
     static FAB_DEV void sample(const Ctx &, int t, Sample &s) { s.t = t; }
+    /* linear in its model-space parameters: g = sum_j phi_j(t) p_j. basis_row returns g (eval()'s operation
+     * order) and phi - see recentre_loop for what that buys */
+    static constexpr bool LINEAR = true;
+    static FAB_DEV void basis_row(const Ctx &c, const Sample &smp, const double (&p0)[P], double &g, double (&phi)[P])
+    {
+        const double *row = c.design + smp.t * P;
+#pragma unroll
+        for (int j = 0; j < P; j++)
+            phi[j] = row[j];
+        double s = __dmul_rn(phi[0], p0[0]);
+#pragma unroll
+        for (int j = 1; j < P; j++)
+            s = __dadd_rn(s, __dmul_rn(phi[j], p0[j]));
+        g = s;
+    }
     template <bool FAST>
     static FAB_DEV void eval_fd(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
@@ -166,6 +186,18 @@ template <int P_> struct PolyModel
         double pw[P]; /* (t+1)^n, n = 0..P-1 */
     };
     static FAB_DEV void sample(const Ctx &, int t, Sample &s) { powers(t, s.pw); }
+    static constexpr bool LINEAR = true; /* g = sum_n (t+1)^n c_n */
+    static FAB_DEV void basis_row(const Ctx &, const Sample &smp, const double (&p0)[P], double &g, double (&phi)[P])
+    {
+#pragma unroll
+        for (int n = 0; n < P; n++)
+            phi[n] = smp.pw[n];
+        double s = __dmul_rn(p0[0], phi[0]);
+#pragma unroll
+        for (int n = 1; n < P; n++)
+            s = __dadd_rn(s, __dmul_rn(p0[n], phi[n]));
+        g = s;
+    }
     template <bool FAST>
     static FAB_DEV void eval_fd(const Ctx &, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
@@ -248,6 +280,7 @@ template <int NE> struct ExpModel
             s = __dadd_rn(s, __dmul_rn(p[2 * k], exp(__dmul_rn(-p[2 * k + 1], tt))));
         return s;
     }
+    static constexpr bool LINEAR = false;
     struct Sample
     {
         double tt; /* double(t) * dt */

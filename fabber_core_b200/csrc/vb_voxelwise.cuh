@@ -34,6 +34,7 @@ constexpr int VB_BLOCK = 128;
 struct VbArgs
 {
     int N, T;
+    int basis_jacobian; /* 1: opt-in basis-row Jacobian for linear-in-parameter models (FABBER_B200_BASIS_JACOBIAN=1), see recentre_loop; 0 = the reference's 2P+1 evaluations */
     int v_begin, v_end; /* voxelwise kernels work on voxels [v_begin, v_end) of the N (N stays the array stride) */
     const float *data;          /* [T][N] */
     const double *design;       /* device [T][P], linear model */
@@ -125,12 +126,25 @@ template <int P> struct Stats
  * rr = sum r^2 and A_ii = sum J_i^2, and a non-finite r or J_i leaves those sums non-finite for good - so the
  * hot loop runs unchecked (11 of its 80 instructions were the tests) and recentre_stats() looks at the sums
  * afterwards, re-walking the series with recentre_diagnose() only in the rare case they are not finite. */
-template <class Model, int NPHI, bool FAST, bool CHECK>
+/* BASIS (models with LINEAR = true): the reference differentiates every model numerically,
+ *     J_i(t) = [g(c + d e_i) - g(c - d e_i)] / [(c_i + d) - (c_i - d)]        (fwdmodel_linear.cc:142-172).
+ * For g = sum_j phi_j(t) p_j with p = transform(c) the numerator is phi_i(t) [p_i(c_i+d) - p_i(c_i-d)] plus
+ * the rounding error of subtracting two nearly equal sums - error, not signal: ~eps |g| / d, up to 1e-8
+ * relative in the reference's own J. So J_i(t) = phi_i(t) * s_i with s_i = (pp_i - pn_i) * rden_i formed once
+ * per pass is the same Jacobian without that noise, and the pass evaluates the model ONCE per sample:
+ * 23 + P FP64 instructions per sample instead of 54 at P = 4. The results stay inside the reference's own
+ * noise floor (same parity rule, same tests). OPT-IN (FABBER_B200_BASIS_JACOBIAN=1): the default is the reference's
+ * literal 2P+1 evaluations per sample. */
+template <class Model, int NPHI, bool FAST, bool CHECK, bool BASIS>
 FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
     const double (&p0)[Model::P], const double (&pp)[Model::P], const double (&pn)[Model::P],
     const double (&rden)[Model::P], Stats<Model::P> (&S)[NPHI], bool &bad_g, bool &bad_j)
 {
     constexpr int P = Model::P;
+    double jscale[P];
+#pragma unroll
+    for (int i = 0; i < P; i++)
+        jscale[i] = (pp[i] - pn[i]) * rden[i];
     const float *yp = a.data + v;
     const size_t stride = (size_t)a.N;
     /* software prefetch, three samples deep: one sample is ~60 FP64 instructions (~120 issue cycles per
@@ -154,15 +168,27 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
          * are formed one sample ahead */
         typename Model::Sample nxt;
         Model::sample(mc, t + 1, nxt);
-        double g, gp[P], gn[P], J[P];
-        Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+        double g, J[P];
+        if constexpr (BASIS)
+        {
+            Model::basis_row(mc, smp, p0, g, J);
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                J[i] = J[i] * jscale[i];
+        }
+        else
+        {
+            double gp[P], gn[P];
+            Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                J[i] = (gp[i] - gn[i]) * rden[i];
+        }
         if (CHECK)
+        {
             bad_g = bad_g || !finite_d(g);
 #pragma unroll
-        for (int i = 0; i < P; i++)
-        {
-            J[i] = (gp[i] - gn[i]) * rden[i];
-            if (CHECK)
+            for (int i = 0; i < P; i++)
                 bad_j = bad_j || !finite_d(J[i]);
         }
         const double r = y - g;
@@ -235,10 +261,20 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
      * argument of this pass is inside its range - checked once here, not per sample */
     constexpr bool CHECK = NPHI > 1; /* masked samples never reach the sums: test them one by one */
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
-    if (fast)
-        recentre_loop<Model, NPHI, true, CHECK>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+    bool done = false;
+    if constexpr (Model::LINEAR)
+        if (a.basis_jacobian)
+        {
+            recentre_loop<Model, NPHI, false, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+            done = true;
+        }
+    if (done)
+    {
+    }
+    else if (fast)
+        recentre_loop<Model, NPHI, true, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     else
-        recentre_loop<Model, NPHI, false, CHECK>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop<Model, NPHI, false, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     if (!CHECK)
     {
         bool sums_finite = finite_d(S[0].rr);

@@ -62,7 +62,7 @@ FAB_DEV double ar_klj(const Stats<P> &M, const double (&d)[P], const double (&Si
     return (M.rr + 2.0 * bd + quadform<P>(M.A, d)) + trace_prod<P>(Sig, M.A);
 }
 
-template <class Model, bool FAST>
+template <class Model, bool FAST, bool BASIS>
 FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&p0)[Model::P],
     const double (&pp)[Model::P], const double (&pn)[Model::P], const double (&rden)[Model::P],
     ArStats<Model::P> &S, volatile double *first)
@@ -77,10 +77,13 @@ FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, in
         q1 = __ldg(yp + stride);
     if (2 < a.T)
         q2 = __ldg(yp + 2 * stride);
-    double Jprev[P], rprev = 0.0;
+    double Jprev[P], rprev = 0.0, jscale[P];
 #pragma unroll
     for (int i = 0; i < P; i++)
+    {
         Jprev[i] = 0.0;
+        jscale[i] = (pp[i] - pn[i]) * rden[i]; /* BASIS: see recentre_loop (vb_voxelwise.cuh) */
+    }
     typename Model::Sample smp;
     Model::sample(mc, 0, smp);
 #pragma unroll 1
@@ -93,12 +96,23 @@ FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, in
             q2 = __ldg(yp + (size_t)(t + 3) * stride);
         typename Model::Sample nxt;
         Model::sample(mc, t + 1, nxt);
-        double g, gp[P], gn[P], J[P];
-        Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
-        smp = nxt;
+        double g, J[P];
+        if constexpr (BASIS)
+        {
+            Model::basis_row(mc, smp, p0, g, J);
 #pragma unroll
-        for (int i = 0; i < P; i++)
-            J[i] = (gp[i] - gn[i]) * rden[i];
+            for (int i = 0; i < P; i++)
+                J[i] = J[i] * jscale[i];
+        }
+        else
+        {
+            double gp[P], gn[P];
+            Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+#pragma unroll
+            for (int i = 0; i < P; i++)
+                J[i] = (gp[i] - gn[i]) * rden[i];
+        }
+        smp = nxt;
         const double r = y - g;
         S.S0.add(r, J);
         /* lag-1 terms: Jprev/rprev are zero at t == 0, so the first pass adds exact zeros */
@@ -159,10 +173,20 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     S.S1.zero();
     bool bad_g = false, bad_j = false;
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
-    if (fast)
-        recentre_loop_ar<Model, true>(a, mc, v, p0, pp, pn, rden, S, first);
+    bool done = false;
+    if constexpr (Model::LINEAR)
+        if (a.basis_jacobian)
+        {
+            recentre_loop_ar<Model, false, true>(a, mc, v, p0, pp, pn, rden, S, first);
+            done = true;
+        }
+    if (done)
+    {
+    }
+    else if (fast)
+        recentre_loop_ar<Model, true, false>(a, mc, v, p0, pp, pn, rden, S, first);
     else
-        recentre_loop_ar<Model, false>(a, mc, v, p0, pp, pn, rden, S, first);
+        recentre_loop_ar<Model, false, false>(a, mc, v, p0, pp, pn, rden, S, first);
     bool sums_finite = finite_d(S.S0.rr);
 #pragma unroll
     for (int i = 0; i < P; i++)

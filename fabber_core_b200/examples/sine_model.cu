@@ -39,6 +39,7 @@ struct SineModel
         return one(__dmul_rn((double)t, c.dt), p[0], p[1], p[2], p[3]);
     }
     static constexpr bool HAS_FAST = false;
+    static constexpr bool LINEAR = false;
     static FAB_DEV bool fast_ok(const Ctx &, int, const double (&)[P], const double (&)[P], const double (&)[P])
     {
         return false;

@@ -296,3 +296,48 @@ def test_voxel_range_launches_tile_the_volume(noise):
         assert run.launch_range(10, 5) == abi.ERR_INVALID
     finally:
         run.close()
+
+
+# ---- opt-in basis-row Jacobian (FABBER_B200_BASIS_JACOBIAN=1, recentre_loop in vb_voxelwise.cuh) ------------
+@pytest.mark.parametrize("case", ["c2_poly", "c2_poly_lm", "c4_linear_ar1", "c1_linear", "linear_spatial"])
+def test_basis_jacobian_option_stays_inside_the_parity_rule(case, golden, monkeypatch):
+    """Models that are linear in their model-space parameters may form J as basis row x transform
+    difference quotient instead of 2P+1 evaluations. Opt-in; held to the same parity rule as the default
+    path, and it must actually be a different code path (results differ in the last bits)."""
+    if case == "c2_poly" or case == "c2_poly_lm":
+        y = synth.poly_volume(3000, 64, 3, seed=1002).numpy()
+        kw = dict(model="poly", degree=3, need_f=True, convergence="lm" if case.endswith("lm") else "maxits")
+        P, run_kw = 4, {}
+    elif case == "c4_linear_ar1":
+        y = synth.linear_ar_volume(1500, 200, 0.3, seed=1004).numpy()
+        kw = dict(model="linear", design=synth.ar_design(200), noise="ar", need_f=True)
+        P, run_kw = 4, {}
+    elif case == "c1_linear":
+        y = golden["data"]
+        kw = dict(model="linear", design=golden["design"])
+        P, run_kw = 4, {}
+    else:
+        nx, ny, nz = 10, 9, 5
+        y = synth.poly_volume(nx * ny * nz, 40, 2, seed=35).numpy()
+        idx = np.arange(nx * ny * nz)
+        coords = np.ascontiguousarray(np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.int32))
+        kw = dict(model="poly", degree=2, prior_types=list("pMm"), need_f=True, max_iterations=5)
+        P, run_kw = 3, dict(spatial=True, coords=coords)
+    spec_kw = dict(kw)
+    model = spec_kw.pop("model")
+
+    def mk():
+        sp = abi.ProblemSpec(model, y.shape[0], **spec_kw)
+        if "spatial" in run_kw:
+            sp.prob.nx, sp.prob.ny, sp.prob.nz = nx, ny, nz
+        return sp
+
+    ref = oracle.run(mk(), y, **run_kw)
+    probes = [oracle.run(mk(), y, variant="fma", **run_kw)]
+    default = device.run(mk(), y, **run_kw)
+    monkeypatch.setenv("FABBER_B200_BASIS_JACOBIAN", "1")
+    basis = device.run(mk(), y, **run_kw)
+    monkeypatch.delenv("FABBER_B200_BASIS_JACOBIAN")
+    compare(basis, ref, P, probes, check_f="need_f" in kw, label="basis jacobian %s" % case)
+    assert np.mean(basis["iterations"] != default["iterations"]) < 0.01  # a voxel may sit on a detector threshold
+    assert not np.array_equal(basis["mean"], default["mean"])
