@@ -990,23 +990,61 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
         mark_ghosts_kernel<<<gridN, 256, 0, st>>>(slab->ghost, order, N, status_p);
         count_launch();
     }
+    /* z-slab mode: the aK sums of iteration it+1 depend on the means and covariances as the sweep and the halo
+     * exchange of iteration it leave them - sp_noise does not touch either. The slabs finish their sweeps
+     * staggered (slab r starts r * nz_local hyper-planes after slab 0), so an all-reduce in front of the next
+     * iteration would make every slab wait for the LAST slab's sp_noise. Instead the local sums and the
+     * all-reduce are issued on a side stream right after the halo exchange and run under this slab's own
+     * sp_noise; the next iteration only waits for the event. (Only difference: with allow_bad_voxels a voxel
+     * that fails in sp_noise of iteration it still contributes to the aK of iteration it+1.) */
+    struct SideStream
+    {
+        cudaStream_t s = nullptr;
+        cudaEvent_t swept = nullptr, ak = nullptr;
+        ~SideStream()
+        {
+            if (swept)
+                cudaEventDestroy(swept);
+            if (ak)
+                cudaEventDestroy(ak);
+            if (s)
+                cudaStreamDestroy(s);
+        }
+    } side;
+    if (slab && any_spatial)
+    {
+        cudaError_t se = cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking);
+        if (se == cudaSuccess)
+            se = cudaEventCreateWithFlags(&side.swept, cudaEventDisableTiming);
+        if (se == cudaSuccess)
+            se = cudaEventCreateWithFlags(&side.ak, cudaEventDisableTiming);
+        if (se != cudaSuccess)
+            return cuda_fail(se, "spatial VB side stream");
+    }
+    bool ak_ahead = false; /* this iteration's all-reduced sums are in flight on (or done by) the side stream */
     for (int it = 0; it < max_it; it++)
     {
         sp.it = it;
         /* SpatialPrior::ApplyToMVN at v == 1: aK is refreshed from the current posteriors unless this is
          * the first iteration (priors.cc:350-358) */
         sp.ak_update = (any_spatial && (it > 0 || prob->update_first_iter)) ? 1 : 0;
-        if (sp.ak_update)
-            FAB_SP_LAUNCH(sp_ak_partial);
         if (slab && sp.ak_update)
         {
             /* local sums -> all-reduce over the slabs -> aK (identical on every rank) */
-            sp.ak_phase = 1;
-            FAB_SP_LAUNCH(sp_ak_final);
-            if (slab->allreduce_sum(slab->user, sp.ak_sums, 2 * P, st) != 0)
-                return fail(FABBER_CUDA_ERR_CUDA, "slab all-reduce callback failed");
+            if (ak_ahead)
+                cudaStreamWaitEvent(st, side.ak, 0);
+            else
+            {
+                FAB_SP_LAUNCH(sp_ak_partial);
+                sp.ak_phase = 1;
+                FAB_SP_LAUNCH(sp_ak_final);
+                if (slab->allreduce_sum(slab->user, sp.ak_sums, 2 * P, st) != 0)
+                    return fail(FABBER_CUDA_ERR_CUDA, "slab all-reduce callback failed");
+            }
             sp.ak_phase = 2;
         }
+        else if (sp.ak_update)
+            FAB_SP_LAUNCH(sp_ak_partial);
         FAB_SP_LAUNCH(sp_ak_final);
         sp.ak_phase = 0;
         FAB_SP_LAUNCH(sp_theta);
@@ -1070,6 +1108,25 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
                 halo_kernel<false><<<(slab->n_recv_hi + 255) / 256, 256, 0, st>>>(
                     mean_p, slab->recv_hi, rank, slab->n_recv_hi, P, N, halo_recv_hi);
             count_launch();
+        }
+        ak_ahead = false;
+        if (slab && any_spatial && it + 1 < max_it)
+        {
+            SpArgs nxt = sp;
+            nxt.it = it + 1;
+            nxt.ak_update = 1;
+            nxt.ak_phase = 1;
+            cudaEventRecord(side.swept, st);
+            cudaStreamWaitEvent(side.s, side.swept, 0);
+            cudaError_t le = ml->sp_ak_partial(nxt, side.s);
+            if (le == cudaSuccess)
+                le = ml->sp_ak_final(nxt, side.s);
+            if (le != cudaSuccess)
+                return cuda_fail(le, "spatial VB aK sums (side stream)");
+            if (slab->allreduce_sum(slab->user, sp.ak_sums, 2 * P, side.s) != 0)
+                return fail(FABBER_CUDA_ERR_CUDA, "slab all-reduce callback failed");
+            cudaEventRecord(side.ak, side.s);
+            ak_ahead = true;
         }
         FAB_SP_LAUNCH(sp_noise);
     }

@@ -53,6 +53,39 @@ void check(int rc, const char *what)
         throw FabberInternalError(std::string(what) + ": " + fabber_cuda_last_error());
 }
 int tri(int i, int j) { return i >= j ? i * (i + 1) / 2 + j : j * (j + 1) / 2 + i; }
+
+/* noise-initial-prior / noise-initial-posterior (Vb::InitializeNoiseFromParam, inference_vb.cc:132-142): an MVN
+ * matrix file [covariance means(:); means(:)' 1.0] (MVNDist::LoadFromMatrix, dist_mvn.cc:287-309); each phi's
+ * Gamma is moment-matched to its mean and variance (WhiteParams::InputFromMVN, noisemodel_white.cc:70-79;
+ * GammaDist::SetMeanVariance, dist_gamma.cc:29-33: b = v / m, c = m / b). */
+void NoiseGammasFromMvnFile(FabberRunData &rundata, const std::string &key, int nphis, double *b, double *c)
+{
+    const std::string filename = rundata.GetStringDefault(key, "modeldefault");
+    if (filename == "modeldefault")
+        return;
+    std::vector<double> m;
+    int rows = 0, cols = 0;
+    read_matrix_file(filename, m, rows, cols);
+    const int n = rows - 1;
+    bool ok = n >= 1 && rows == cols && m[(size_t)n * cols + n] == 1.0;
+    for (int i = 0; ok && i < rows; i++)
+        for (int j = 0; j < i; j++)
+            ok = ok && m[(size_t)i * cols + j] == m[(size_t)j * cols + i];
+    if (!ok)
+        throw InvalidOptionValue(filename, "",
+            "MVNs must be symmetric matrices (format = [covariance means(:); means(:) 1.0])");
+    if (n < nphis)
+        throw InvalidOptionValue(key, filename, "MVN has fewer rows than the noise model has precisions");
+    for (int i = 0; i < nphis; i++)
+    {
+        for (int j = i + 1; j < n; j++)
+            if (m[(size_t)i * cols + j] != 0.0)
+                throw FabberRunDataError("Phis should have zero covariance!");
+        const double mean = m[(size_t)i * cols + n], var = m[(size_t)i * cols + i];
+        b[i] = var / mean;
+        c[i] = mean / b[i];
+    }
+}
 } // namespace
 
 std::vector<std::string> Vb::GetKnownMethods()
@@ -84,6 +117,8 @@ void Vb::GetOptions(std::vector<OptionSpec> &opts)
             "Skip model fitting, just output requested data based on supplied MVN. Can only be used with "
             "continue-from-mvn",
             true, "" },
+        { "noise-initial-prior", OPT_MATRIX, "MVN of initial noise prior", true, "" },
+        { "noise-initial-posterior", OPT_MATRIX, "MVN of initial noise posterior", true, "" },
         { "noise-pattern", OPT_STR,
             "repeating pattern of noise variances for each point (e.g. 12 gives odd and even data points different "
             "variances)",
@@ -207,6 +242,10 @@ void Vb::DoCalculations(FabberRunData &rundata)
             throw InvalidOptionValue("num-echoes", rundata.GetString("num-echoes"), "only 1 echo has a device kernel");
         if (rundata.GetStringDefault("ar1-cross-terms", "none") != "none")
             throw InvalidOptionValue("ar1-cross-terms", rundata.GetString("ar1-cross-terms"), "only 'none' has a device kernel");
+        for (const char *key : { "noise-initial-prior", "noise-initial-posterior" })
+            if (rundata.GetStringDefault(key, "modeldefault") != "modeldefault")
+                throw InvalidOptionValue(key, rundata.GetString(key),
+                    "the AR(1) device kernel starts alpha at N(0, 1e4 I) only: not supported with noise=ar");
         prob.noise_type = FABBER_NOISE_AR1;
         prob.n_phis = 1;
         prob.noise_prior_b[0] = 1e6; /* noisemodel_ar.cc:379-403 */
@@ -261,6 +300,9 @@ void Vb::DoCalculations(FabberRunData &rundata)
             }
         }
         prob.locked_noise_stdev = rundata.GetDoubleDefault("locked-noise-stdev", -1);
+        /* after the hard-coded values, as in the reference (inference_vb.cc:204-205) */
+        NoiseGammasFromMvnFile(rundata, "noise-initial-prior", nphis, prob.noise_prior_b, prob.noise_prior_c);
+        NoiseGammasFromMvnFile(rundata, "noise-initial-posterior", nphis, prob.noise_post_b, prob.noise_post_c);
     }
     prob.phi_pattern = m_pattern.data();
     prob.time_masked = mt.empty() ? nullptr : m_masked.data();

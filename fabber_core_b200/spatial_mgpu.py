@@ -139,7 +139,14 @@ class TorchDistComm(object):
     """The real thing: one process per GPU, NCCL through torch.distributed."""
 
     def __init__(self, rank, world, n_params):
+        import torch.distributed as dist
+
         self.rank, self.world, self.P = rank, world, n_params
+        # The aK all-reduce runs on the library's side stream, under sp_noise, while the next point-to-point
+        # operations may already be queued on the main stream: it gets a communicator of its own, so the two
+        # streams never interleave operations of one NCCL communicator. (Collective call: every rank builds its
+        # TorchDistComm at the same point.)
+        self.ak_group = dist.new_group(ranks=list(range(world)))
 
     @staticmethod
     def _fence(stream):
@@ -152,12 +159,18 @@ class TorchDistComm(object):
             torch.cuda.synchronize()
 
     def allreduce(self, ptr, n, stream):
+        """ordered behind `stream` (the library's side stream, or the main one for the very first aK) without
+        a host synchronize: torch.distributed queues NCCL work behind torch's current stream, so make `stream`
+        current for the call"""
+        import torch
         import torch.distributed as dist
 
-        self._fence(stream)
         t = _tensor(ptr, n)
-        dist.all_reduce(t)
-        self._fence(stream)
+        if int(stream or 0) == int(torch.cuda.current_stream().cuda_stream):
+            dist.all_reduce(t, group=self.ak_group)
+        else:
+            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
+                dist.all_reduce(t, group=self.ak_group)
         return 0
 
     def exchange(self, send_lo, n_slo, send_hi, n_shi, recv_lo, n_rlo, recv_hi, n_rhi, stream):

@@ -117,3 +117,35 @@ def test_dropin_locked_linear_from_mvn():
     assert_same(ours, ref)
     unlocked, _ = both({k: v for k, v in opts.items() if k != "locked-linear-from-mvn"}, {"data": data["data"]})
     assert np.max(np.abs(unlocked.data["mean_amp1"] - ours.data["mean_amp1"])) > 1e-4   # the option is live
+
+
+def test_dropin_noise_initial_prior_and_posterior_files(tmp_path):
+    """noise-initial-prior / noise-initial-posterior (inference_vb.cc:132-142,204-205): MVN matrix files whose
+    means and variances set each phi's Gamma; two phis (noise-pattern=12), both libraries read the same files."""
+    def mvn_file(name, means, variances):
+        n = len(means)
+        m = np.zeros((n + 1, n + 1))
+        m[np.arange(n), np.arange(n)] = variances
+        m[:n, n] = m[n, :n] = means
+        m[n, n] = 1.0
+        path = str(tmp_path / name)
+        np.savetxt(path, m, fmt="%.17g")
+        return path
+
+    nx, ny, nz = 5, 4, 3
+    y = synth.poly_volume(nx * ny * nz, 40, 2, seed=78).numpy()
+    opts = {"model": "poly", "degree": 2, "noise": "white", "method": "vb", "noise-pattern": "12",
+            "noise-initial-prior": mvn_file("prior.mat", [2.0, 0.5], [4e6, 1e5]),
+            "noise-initial-posterior": mvn_file("post.mat", [1e-3, 5e-4], [2e-8, 5e-9])}
+    data = {"data": refbuild.volume(y, (nx, ny, nz))}
+    ours, ref = both(opts, data)
+    assert_same(ours, ref)
+    plain, _ = both({k: v for k, v in opts.items() if not k.startswith("noise-initial")}, data)
+    assert np.max(np.abs(plain.data["noise_means"] - ours.data["noise_means"])
+                  / np.abs(plain.data["noise_means"])) > 1e-4   # the options are live
+    # a malformed file is refused with the reference's message
+    bad = str(tmp_path / "bad.mat")
+    np.savetxt(bad, np.array([[1.0, 0.5, 1.0], [0.0, 1.0, 1.0], [1.0, 1.0, 1.0]]))
+    for lib in (fab.Fabber(), refbuild.ReferenceFabber()):
+        with pytest.raises(Exception, match="MVNs must be symmetric"):
+            lib.run_with_data(dict(opts, **{"noise-initial-prior": bad}), data)
