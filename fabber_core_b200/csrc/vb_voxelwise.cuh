@@ -261,15 +261,13 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
      * argument of this pass is inside its range - checked once here, not per sample */
     constexpr bool CHECK = NPHI > 1; /* masked samples never reach the sums: test them one by one */
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
-    bool done = false;
+    bool basis = false; /* opt-in, and only for models that hand out their basis row */
     if constexpr (Model::LINEAR)
-        if (a.basis_jacobian)
-        {
-            recentre_loop<Model, NPHI, false, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
-            done = true;
-        }
-    if (done)
+        basis = a.basis_jacobian != 0;
+    if (basis)
     {
+        if constexpr (Model::LINEAR)
+            recentre_loop<Model, NPHI, false, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     }
     else if (fast)
         recentre_loop<Model, NPHI, true, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);

@@ -173,15 +173,13 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     S.S1.zero();
     bool bad_g = false, bad_j = false;
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
-    bool done = false;
+    bool basis = false; /* opt-in, and only for models that hand out their basis row */
     if constexpr (Model::LINEAR)
-        if (a.basis_jacobian)
-        {
-            recentre_loop_ar<Model, false, true>(a, mc, v, p0, pp, pn, rden, S, first);
-            done = true;
-        }
-    if (done)
+        basis = a.basis_jacobian != 0;
+    if (basis)
     {
+        if constexpr (Model::LINEAR)
+            recentre_loop_ar<Model, false, true>(a, mc, v, p0, pp, pn, rden, S, first);
     }
     else if (fast)
         recentre_loop_ar<Model, true, false>(a, mc, v, p0, pp, pn, rden, S, first);
