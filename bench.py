@@ -180,9 +180,16 @@ def capi_e2e(w, host_y, extent, steps):
     bufs = {}
     noop = f.progress_cb_type(0)
 
+    phases = {"set_data": 0.0, "dorun": 0.0, "get_data": 0.0}
+
     def one():
+        t_a = time.perf_counter()
         f._trycall(f.clib.fabber_set_data, f.handle, b"data", w["T"], flat, f.errbuf)
+        t_b = time.perf_counter()
         f._trycall(f.clib.fabber_dorun, f.handle, len(f.outbuf), f.outbuf, f.errbuf, noop)
+        t_c = time.perf_counter()
+        phases["set_data"] += t_b - t_a
+        phases["dorun"] += t_c - t_b
         nbytes = 0
         for key in outputs:
             size = f._trycall(f.clib.fabber_get_data_size, f.handle, key.encode(), f.errbuf)
@@ -190,9 +197,12 @@ def capi_e2e(w, host_y, extent, steps):
                 bufs[key] = np.empty(n * size, dtype=np.float32)
             f._trycall(f.clib.fabber_get_data, f.handle, key.encode(), bufs[key], f.errbuf)
             nbytes += bufs[key].nbytes
+        phases["get_data"] += time.perf_counter() - t_c
         return nbytes
 
     one()  # warm-up
+    for k in phases:
+        phases[k] = 0.0
     t0 = time.perf_counter()
     d2h = 0
     for _ in range(steps):
@@ -200,6 +210,8 @@ def capi_e2e(w, host_y, extent, steps):
     dt = (time.perf_counter() - t0) / steps
     if tmp is not None:
         os.unlink(tmp.name)
+    capi_e2e.last_phases_ms = {k: v / steps * 1e3 for k, v in phases.items()}
+    capi_e2e.last_log = [l for l in f.outbuf.value.decode(errors="replace").splitlines() if "Vb::timing" in l]
     return dt, flat.nbytes, d2h
 
 
@@ -618,6 +630,8 @@ def main():
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
             "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": capi_h2d,
                     "d2h_bytes_per_step": capi_d2h, "steps": capi_steps,
+                    "calls_ms": getattr(capi_e2e, "last_phases_ms", None),
+                    "dorun_log": getattr(capi_e2e, "last_log", None),
                     "path": "fabber_capi (libfabbercore_b200.so): fabber_set_data -> fabber_dorun -> fabber_get_data "
                             "of mean_*, std_*, noise_means; host float32 buffers in and out; wall clock",
                     "inner_abi": {"value": e2e_inner, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,

@@ -6,6 +6,7 @@
  * as in the reference.
  */
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstring>
 #include <ctime>
@@ -17,6 +18,7 @@
 #include <thread>
 
 #include <sys/stat.h>
+#include <immintrin.h>
 #include <sys/types.h>
 #include <unistd.h>
 
@@ -26,12 +28,18 @@ namespace fabber_b200
 {
 const char *fabber_b200_version() { return "b200-r1 (VB path of fabber_core on sm_100a)"; }
 
-void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_chunk)
+size_t host_threads()
 {
     unsigned hw = std::thread::hardware_concurrency();
     size_t threads = hw ? hw : 4;
     if (threads > 32)
         threads = 32;
+    return threads;
+}
+
+void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_chunk)
+{
+    size_t threads = host_threads();
     if (n / min_chunk + 1 < threads)
         threads = n / min_chunk + 1;
     if (threads <= 1)
@@ -50,6 +58,42 @@ void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_
     }
     for (size_t t = 0; t < pool.size(); t++)
         pool[t].join();
+}
+
+/* Staging copy for SetVoxelDataArray: the destination is pinned memory that only the DMA engine reads next, so
+ * the stores go around the cache (no read-for-ownership of the destination lines: 2 bytes of DRAM traffic per
+ * byte copied instead of 3). glibc's memcpy only does this above a threshold far larger than the ~1 MB pieces
+ * staged here. Falls back to memcpy without AVX2. */
+__attribute__((target("avx2"))) static void stream_copy_avx2(float *dst, const float *src, size_t n)
+{
+    size_t i = 0;
+    while (i < n && ((uintptr_t)(dst + i) & 31))
+    {
+        dst[i] = src[i];
+        i++;
+    }
+    for (; i + 32 <= n; i += 32)
+    {
+        const __m256i a = _mm256_loadu_si256((const __m256i *)(src + i));
+        const __m256i b = _mm256_loadu_si256((const __m256i *)(src + i + 8));
+        const __m256i c = _mm256_loadu_si256((const __m256i *)(src + i + 16));
+        const __m256i d = _mm256_loadu_si256((const __m256i *)(src + i + 24));
+        _mm256_stream_si256((__m256i *)(dst + i), a);
+        _mm256_stream_si256((__m256i *)(dst + i + 8), b);
+        _mm256_stream_si256((__m256i *)(dst + i + 16), c);
+        _mm256_stream_si256((__m256i *)(dst + i + 24), d);
+    }
+    for (; i < n; i++)
+        dst[i] = src[i];
+    _mm_sfence(); /* the copy must be globally visible before the host->device copy is queued */
+}
+void stage_copy(float *dst, const float *src, size_t n)
+{
+    static const bool avx2 = __builtin_cpu_supports("avx2") && !getenv("FABBER_B200_NO_STREAM_COPY");
+    if (avx2 && n >= 4096)
+        stream_copy_avx2(dst, src, n);
+    else
+        memcpy(dst, src, n * sizeof(float));
 }
 
 const char *option_type_name(OptionType t)
@@ -370,28 +414,74 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         vd->dev = (float *)cached_device_alloc(vd->bytes());
     /* ~96 MB per block, at most 64 blocks, at least 64k voxels each (a block is also one kernel launch) */
     const size_t total = (size_t)data_size * N * sizeof(float);
-    size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, total / ((size_t)96 << 20)));
+    static const size_t block_mb = []() {
+        const char *e = getenv("FABBER_B200_UPLOAD_BLOCK_MB"); /* tuning knob; default measured on C2 / C3 */
+        const long v = e ? atol(e) : 0;
+        return (size_t)(v > 0 ? v : 96);
+    }();
+    size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, total / (block_mb << 20)));
     n_blocks = std::max<size_t>(1, std::min(n_blocks, N / 65536));
     if (!upload)
         n_blocks = 1;
     const size_t per_block = ((N + n_blocks - 1) / n_blocks + 127) / 128 * 128; /* whole CTAs of 128 voxels */
     const size_t T = (size_t)data_size;
-    for (size_t v0 = 0; v0 < N; v0 += per_block)
-    {
-        const size_t v1 = std::min(N, v0 + per_block), w = v1 - v0;
-        /* work item = (row, piece of the block's columns): contiguous runs in both source and destination */
-        const size_t piece = (size_t)1 << 18, pieces = (w + piece - 1) / piece;
-        parallel_for(T * pieces, [&](size_t b, size_t e) {
-            for (size_t i = b; i < e; i++)
+    /* One pool of workers for the whole volume, no barrier between blocks: work item = (block, row, piece of
+     * the block's columns) - contiguous runs in both source and destination - handed out block-major from one
+     * counter; a per-block count of unfinished items tells the calling thread when a block is staged, and it
+     * queues that block's copy while the workers are already on the next one. */
+    const size_t real_blocks = per_block ? (N + per_block - 1) / per_block : 0; /* empty mask: nothing to stage */
+    const size_t piece = (size_t)1 << 18, pieces = (per_block + piece - 1) / piece, per_items = T * pieces;
+    std::vector<std::atomic<size_t>> unfinished(real_blocks);
+    for (size_t b = 0; b < real_blocks; b++)
+        unfinished[b].store(per_items, std::memory_order_relaxed);
+    std::atomic<size_t> next(0);
+    const size_t total_items = real_blocks * per_items;
+    auto worker = [&]() {
+        for (;;)
+        {
+            const size_t i = next.fetch_add(1, std::memory_order_relaxed);
+            if (i >= total_items)
+                return;
+            const size_t b = i / per_items, r = i - b * per_items, t = r / pieces;
+            const size_t v0 = b * per_block, v1 = std::min(N, v0 + per_block);
+            const size_t c0 = v0 + (r - t * pieces) * piece, c1 = std::min(v1, c0 + piece);
+            if (c0 < c1)
             {
-                const size_t t = i / pieces, c0 = v0 + (i - t * pieces) * piece, c1 = std::min(v1, c0 + piece);
                 if (N == n_grid)
-                    memcpy(dst_all + t * N + c0, data + t * N + c0, (c1 - c0) * sizeof(float));
+                    stage_copy(dst_all + t * N + c0, data + t * N + c0, c1 - c0);
                 else
                     for (size_t v = c0; v < c1; v++)
                         dst_all[t * N + v] = data[t * n_grid + index[v]];
             }
-        }, 1);
+            unfinished[b].fetch_sub(1, std::memory_order_release);
+        }
+    };
+    std::vector<std::thread> pool;
+    {
+        size_t threads = host_threads();
+        if (total_items < threads)
+            threads = total_items;
+        if ((size_t)data_size * N < ((size_t)1 << 16))
+            threads = 0; /* tiny: the calling thread does it */
+        for (size_t t = 0; t < threads; t++)
+            pool.emplace_back(worker);
+        if (threads == 0)
+            worker();
+    }
+    struct Join
+    {
+        std::vector<std::thread> &p;
+        ~Join()
+        {
+            for (size_t t = 0; t < p.size(); t++)
+                p[t].join();
+        }
+    } join = { pool };
+    for (size_t b = 0; b < real_blocks; b++)
+    {
+        const size_t v0 = b * per_block, v1 = std::min(N, v0 + per_block), w = v1 - v0;
+        while (unfinished[b].load(std::memory_order_acquire) != 0)
+            std::this_thread::yield();
         if (upload)
         {
             VoxelData::Block blk;
@@ -405,7 +495,10 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
                 rc = fabber_cuda_event_record(blk.ready, copy_stream());
             vd->blocks.push_back(blk);
             if (rc != FABBER_CUDA_OK)
+            {
+                next.store(total_items, std::memory_order_relaxed); /* stop the workers before unwinding */
                 throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+            }
         }
     }
     m_voxel_data[key] = std::move(vd);
@@ -541,8 +634,8 @@ void FabberRunData::GetVoxelDataArray(const std::string &key, float *data)
     if (N == n_grid)
     {
         /* full mask: the stored layout IS the caller's layout */
-        parallel_for((size_t)vd.rows * N, [&](size_t b, size_t e) { memcpy(data + b, vd.f + b, (e - b) * sizeof(float)); },
-            (size_t)1 << 20);
+        parallel_for((size_t)vd.rows * N, [&](size_t b, size_t e) { stage_copy(data + b, vd.f + b, e - b); },
+            (size_t)1 << 17);
         return;
     }
     parallel_for((size_t)vd.rows * n_grid, [&](size_t b, size_t e) { memset(data + b, 0, (e - b) * sizeof(float)); },
