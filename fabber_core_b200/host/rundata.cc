@@ -414,11 +414,8 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         vd->dev = (float *)cached_device_alloc(vd->bytes());
     /* ~96 MB per block, at most 64 blocks, at least 64k voxels each (a block is also one kernel launch) */
     const size_t total = (size_t)data_size * N * sizeof(float);
-    static const size_t block_mb = []() {
-        const char *e = getenv("FABBER_B200_UPLOAD_BLOCK_MB"); /* tuning knob; default measured on C2 / C3 */
-        const long v = e ? atol(e) : 0;
-        return (size_t)(v > 0 ? v : 96);
-    }();
+    const char *block_env = getenv("FABBER_B200_UPLOAD_BLOCK_MB"); /* tuning / test knob; 32-128 MB measure alike */
+    const size_t block_mb = (block_env && atol(block_env) > 0) ? (size_t)atol(block_env) : 96;
     size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, total / (block_mb << 20)));
     n_blocks = std::max<size_t>(1, std::min(n_blocks, N / 65536));
     if (!upload)

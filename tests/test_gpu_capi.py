@@ -179,3 +179,34 @@ def test_bad_voxel_policy_through_capi():
     with pytest.raises(fab.FabberException) as e:
         f.run_with_data(opts, {"data": volume(y, (nx, ny, nz))})
     assert e.value.errcode == fab.FABBER_ERR_FATAL and "Non-finite" in str(e.value)
+
+
+def test_blockwise_upload_with_a_mask_equals_one_block(monkeypatch):
+    """The main series is staged and uploaded one block of voxels at a time by a pool of host threads, and
+    voxelwise VB is launched block by block (rundata.cc SetVoxelDataArray, Vb::DoCalculations). With a mask
+    (gathered, not contiguous, staging) and two blocks the outputs must be bit for bit those of one block."""
+    n = 72
+    g = np.arange(n) - (n - 1) / 2.0
+    r2 = g[:, None, None] ** 2 + g[None, :, None] ** 2 + g[None, None, :] ** 2
+    mask = (r2 < (0.45 * n) ** 2).astype(np.int32)
+    n_in = int(mask.sum())
+    assert n_in >= 2 * 65536                     # enough voxels for two blocks
+    rng = np.random.default_rng(91)
+    t = np.arange(1, 9, dtype=np.float32)
+    data = (rng.uniform(50, 150, (n, n, n, 1)) + rng.uniform(-2, 2, (n, n, n, 1)) * t
+            + rng.standard_normal((n, n, n, 8))).astype(np.float32)
+    opts = {"model": "poly", "degree": 1, "noise": "white", "method": "vb", "save-mean": True, "save-std": True,
+            "save-noise-mean": True}
+    monkeypatch.setenv("FABBER_B200_UPLOAD_BLOCK_MB", "1")      # 8 x n_in x 4 B = 4.5 MB -> two blocks
+    two = fab.Fabber().run_with_data(opts, {"data": data}, mask=mask)
+    monkeypatch.setenv("FABBER_B200_UPLOAD_BLOCK_MB", "4096")   # one block
+    one = fab.Fabber().run_with_data(opts, {"data": data}, mask=mask)
+    for k in one.data:
+        assert np.array_equal(one.data[k], two.data[k]), k
+    assert np.all(two.data["mean_c0"][mask == 0] == 0)
+    # and it is the right answer: a straight-line fit of a few voxels, done independently
+    for (x, y, z) in ((36, 36, 36), (20, 40, 50), (36, 10, 36)):
+        assert mask[x, y, z]
+        c1, c0 = np.polyfit(t.astype(np.float64), data[x, y, z].astype(np.float64), 1)
+        assert abs(two.data["mean_c1"][x, y, z] - c1) < 1e-3 * max(1.0, abs(c1))
+        assert abs(two.data["mean_c0"][x, y, z] - c0) < 1e-3 * abs(c0)
