@@ -751,6 +751,14 @@ int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda
     return fabber_cuda_vb_spatial_slab(prob, buf, nullptr, stream);
 }
 
+/* FABBER_B200_SLAB_EXCHANGE=side moves the halo exchange to the side stream (under sp_noise); the default keeps
+ * it on the main stream, in front of sp_noise, until the side-stream variant has been measured over NCCL */
+static bool slab_exchange_on_main()
+{
+    const char *e = getenv("FABBER_B200_SLAB_EXCHANGE");
+    return !(e && strcmp(e, "side") == 0);
+}
+
 int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
     const fabber_cuda_slab *slab, void *stream)
 {
@@ -1087,46 +1095,60 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
                 }
             }
         }
+        /* z-slab mode, after the sweep: halo exchange of the posterior means (own boundary planes out, ghost
+         * planes in), then - if another iteration follows - the local aK sums of that iteration and their
+         * all-reduce. Nothing in sp_noise reads a ghost or a neighbour, so when another iteration follows all of
+         * this goes on the side stream and runs under this slab's sp_noise: the main stream does not even wait
+         * for the upper neighbour's sweep to end (its bottom plane is this slab's upper ghost). */
+        ak_ahead = false;
         if (slab)
         {
-            /* halo exchange of the posterior means: own boundary planes out, ghost planes in */
+            const bool ahead = any_spatial && it + 1 < max_it && !slab_exchange_on_main();
+            cudaStream_t xs = ahead ? side.s : st;
+            if (ahead)
+            {
+                cudaEventRecord(side.swept, st);
+                cudaStreamWaitEvent(side.s, side.swept, 0);
+            }
             if (slab->n_send_lo > 0)
-                halo_kernel<true><<<(slab->n_send_lo + 255) / 256, 256, 0, st>>>(
+                halo_kernel<true><<<(slab->n_send_lo + 255) / 256, 256, 0, xs>>>(
                     mean_p, slab->send_lo, rank, slab->n_send_lo, P, N, halo_send_lo);
             if (slab->n_send_hi > 0)
-                halo_kernel<true><<<(slab->n_send_hi + 255) / 256, 256, 0, st>>>(
+                halo_kernel<true><<<(slab->n_send_hi + 255) / 256, 256, 0, xs>>>(
                     mean_p, slab->send_hi, rank, slab->n_send_hi, P, N, halo_send_hi);
             count_launch();
             if (slab->exchange(slab->user, halo_send_lo, slab->n_send_lo, halo_send_hi, slab->n_send_hi, halo_recv_lo,
-                    slab->n_recv_lo, halo_recv_hi, slab->n_recv_hi, st)
+                    slab->n_recv_lo, halo_recv_hi, slab->n_recv_hi, xs)
                 != 0)
                 return fail(FABBER_CUDA_ERR_CUDA, "slab halo-exchange callback failed");
             if (slab->n_recv_lo > 0)
-                halo_kernel<false><<<(slab->n_recv_lo + 255) / 256, 256, 0, st>>>(
+                halo_kernel<false><<<(slab->n_recv_lo + 255) / 256, 256, 0, xs>>>(
                     mean_p, slab->recv_lo, rank, slab->n_recv_lo, P, N, halo_recv_lo);
             if (slab->n_recv_hi > 0)
-                halo_kernel<false><<<(slab->n_recv_hi + 255) / 256, 256, 0, st>>>(
+                halo_kernel<false><<<(slab->n_recv_hi + 255) / 256, 256, 0, xs>>>(
                     mean_p, slab->recv_hi, rank, slab->n_recv_hi, P, N, halo_recv_hi);
             count_launch();
-        }
-        ak_ahead = false;
-        if (slab && any_spatial && it + 1 < max_it)
-        {
-            SpArgs nxt = sp;
-            nxt.it = it + 1;
-            nxt.ak_update = 1;
-            nxt.ak_phase = 1;
-            cudaEventRecord(side.swept, st);
-            cudaStreamWaitEvent(side.s, side.swept, 0);
-            cudaError_t le = ml->sp_ak_partial(nxt, side.s);
-            if (le == cudaSuccess)
-                le = ml->sp_ak_final(nxt, side.s);
-            if (le != cudaSuccess)
-                return cuda_fail(le, "spatial VB aK sums (side stream)");
-            if (slab->allreduce_sum(slab->user, sp.ak_sums, 2 * P, side.s) != 0)
-                return fail(FABBER_CUDA_ERR_CUDA, "slab all-reduce callback failed");
-            cudaEventRecord(side.ak, side.s);
-            ak_ahead = true;
+            if (any_spatial && it + 1 < max_it)
+            {
+                if (!ahead)
+                {
+                    cudaEventRecord(side.swept, st);
+                    cudaStreamWaitEvent(side.s, side.swept, 0);
+                }
+                SpArgs nxt = sp;
+                nxt.it = it + 1;
+                nxt.ak_update = 1;
+                nxt.ak_phase = 1;
+                cudaError_t le = ml->sp_ak_partial(nxt, side.s);
+                if (le == cudaSuccess)
+                    le = ml->sp_ak_final(nxt, side.s);
+                if (le != cudaSuccess)
+                    return cuda_fail(le, "spatial VB aK sums (side stream)");
+                if (slab->allreduce_sum(slab->user, sp.ak_sums, 2 * P, side.s) != 0)
+                    return fail(FABBER_CUDA_ERR_CUDA, "slab all-reduce callback failed");
+                cudaEventRecord(side.ak, side.s);
+                ak_ahead = true;
+            }
         }
         FAB_SP_LAUNCH(sp_noise);
     }

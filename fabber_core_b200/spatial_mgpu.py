@@ -149,34 +149,30 @@ class TorchDistComm(object):
         self.ak_group = dist.new_group(ranks=list(range(world)))
 
     @staticmethod
-    def _fence(stream):
-        """torch.distributed orders its NCCL work behind torch's CURRENT stream. When the library runs on that
-        very stream (the default), stream order already is the dependency and the whole iteration loop stays
-        asynchronous; on any other stream fall back to a host synchronize either side of the collective."""
+    def _on(stream):
+        """torch.distributed orders its NCCL work behind torch's CURRENT stream (and makes that stream wait for
+        the result). The library runs on torch's default stream plus one side stream of its own; making the
+        callback's stream current for the call keeps the whole iteration loop asynchronous - no host
+        synchronize per callback."""
+        import contextlib
+
         import torch
 
-        if int(stream or 0) != int(torch.cuda.current_stream().cuda_stream):
-            torch.cuda.synchronize()
+        if int(stream or 0) == int(torch.cuda.current_stream().cuda_stream):
+            return contextlib.nullcontext()
+        return torch.cuda.stream(torch.cuda.ExternalStream(int(stream)))
 
     def allreduce(self, ptr, n, stream):
-        """ordered behind `stream` (the library's side stream, or the main one for the very first aK) without
-        a host synchronize: torch.distributed queues NCCL work behind torch's current stream, so make `stream`
-        current for the call"""
-        import torch
         import torch.distributed as dist
 
         t = _tensor(ptr, n)
-        if int(stream or 0) == int(torch.cuda.current_stream().cuda_stream):
+        with self._on(stream):
             dist.all_reduce(t, group=self.ak_group)
-        else:
-            with torch.cuda.stream(torch.cuda.ExternalStream(int(stream))):
-                dist.all_reduce(t, group=self.ak_group)
         return 0
 
     def exchange(self, send_lo, n_slo, send_hi, n_shi, recv_lo, n_rlo, recv_hi, n_rhi, stream):
         import torch.distributed as dist
 
-        self._fence(stream)
         ops, keep = [], []
         P = self.P
         if n_slo:
@@ -192,18 +188,16 @@ class TorchDistComm(object):
             keep.append(_tensor(recv_hi, P * n_rhi))
             ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank + 1))
         if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
-        self._fence(stream)
+            with self._on(stream):
+                for req in dist.batch_isend_irecv(ops):
+                    req.wait()
         return 0
-
 
     def forward(self, step, send, n_send, recv, n_recv, stream):
         import torch.distributed as dist
 
         if not n_send and not n_recv:
             return 0
-        self._fence(stream)
         ops, keep = [], []
         if n_send:
             keep.append(_tensor(send, self.P * n_send))
@@ -211,9 +205,9 @@ class TorchDistComm(object):
         if n_recv:
             keep.append(_tensor(recv, self.P * n_recv))
             ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank - 1))
-        for req in dist.batch_isend_irecv(ops):
-            req.wait()
-        self._fence(stream)
+        with self._on(stream):
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
         return 0
 
 
