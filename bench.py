@@ -28,7 +28,9 @@ WORKLOADS = {
     # BASELINE.json configs[1]: poly degree 3, VB, white noise, synthetic 128^3 x 64, maxits 10
     "c2": dict(name="C2 poly(degree 3) VB white noise, synthetic 128^3 x 64, maxits 10", side=128, T=64,
                model="poly", spec=dict(degree=3), P=4, e=8, e0=0,
-               capi={"model": "poly", "degree": 3, "noise": "white", "method": "vb", "max-iterations": 10}),
+               capi={"model": "poly", "degree": 3, "noise": "white", "method": "vb", "max-iterations": 10},
+               # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size (ncu --set full)
+               traffic=(538.487808e6 + 273.267968e6, "profiles/r1b_ncu_full_c2_poly4.txt")),
     # BASELINE.json configs[2]: biexp VB, LM convergence, synthetic 256^3 x 96
     # (prior mean 6 on r2 via PSP_byname: with the default symmetric priors the reference's own fit is
     #  chaotic - see DESIGN.md "C3")
