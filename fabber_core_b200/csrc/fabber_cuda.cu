@@ -1021,7 +1021,14 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
     } side;
     if (slab && any_spatial)
     {
-        cudaError_t se = cudaStreamCreateWithFlags(&side.s, cudaStreamNonBlocking);
+        /* FABBER_B200_SLAB_PRIORITY=1: highest stream priority, so that the side stream's small kernels are
+         * dispatched between sp_noise's thread blocks instead of behind the last of them (see DESIGN.md section
+         * 7: without it the 8-GPU run measured no gain from the side stream). Opt-in until measured. */
+        const char *pe = getenv("FABBER_B200_SLAB_PRIORITY");
+        int least = 0, greatest = 0;
+        cudaError_t se = cudaDeviceGetStreamPriorityRange(&least, &greatest);
+        if (se == cudaSuccess)
+            se = cudaStreamCreateWithPriority(&side.s, cudaStreamNonBlocking, (pe && pe[0] == '1') ? greatest : least);
         if (se == cudaSuccess)
             se = cudaEventCreateWithFlags(&side.swept, cudaEventDisableTiming);
         if (se == cudaSuccess)

@@ -17,6 +17,7 @@
 #include <mutex>
 #include <thread>
 
+#include <sched.h>
 #include <sys/stat.h>
 #include <immintrin.h>
 #include <sys/types.h>
@@ -30,8 +31,18 @@ const char *fabber_b200_version() { return "b200-r1 (VB path of fabber_core on s
 
 size_t host_threads()
 {
-    unsigned hw = std::thread::hardware_concurrency();
-    size_t threads = hw ? hw : 4;
+    /* the CPUs this process may run on (what `nproc` reports), not every CPU of the machine; FABBER_B200_HOST_THREADS
+     * overrides (e.g. several ranks sharing one host) */
+    if (const char *e = getenv("FABBER_B200_HOST_THREADS"))
+        if (atol(e) > 0)
+            return (size_t)std::min<long>(atol(e), 256);
+    size_t threads = std::thread::hardware_concurrency();
+    cpu_set_t set;
+    CPU_ZERO(&set);
+    if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0)
+        threads = threads ? std::min<size_t>(threads, (size_t)CPU_COUNT(&set)) : (size_t)CPU_COUNT(&set);
+    if (threads == 0)
+        threads = 4;
     if (threads > 32)
         threads = 32;
     return threads;

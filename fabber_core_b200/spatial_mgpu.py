@@ -146,7 +146,14 @@ class TorchDistComm(object):
         # operations may already be queued on the main stream: it gets a communicator of its own, so the two
         # streams never interleave operations of one NCCL communicator. (Collective call: every rank builds its
         # TorchDistComm at the same point.)
-        self.ak_group = dist.new_group(ranks=list(range(world)))
+        # FABBER_B200_SLAB_PRIORITY=1 (opt-in, with the library's side stream at high priority): NCCL streams of
+        # high priority too, and a communicator for the halo exchange when it runs on the side stream.
+        import os
+
+        prio = os.environ.get("FABBER_B200_SLAB_PRIORITY") == "1"
+        opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True) if prio else None
+        self.ak_group = dist.new_group(ranks=list(range(world)), pg_options=opts)
+        self.side_group = dist.new_group(ranks=list(range(world)), pg_options=opts) if prio else None
 
     @staticmethod
     def _on(stream):
@@ -171,22 +178,26 @@ class TorchDistComm(object):
         return 0
 
     def exchange(self, send_lo, n_slo, send_hi, n_shi, recv_lo, n_rlo, recv_hi, n_rhi, stream):
+        import torch
         import torch.distributed as dist
 
         ops, keep = [], []
         P = self.P
+        # on the side stream (every rank takes the same branch in the same iteration): its own communicator
+        on_side = int(stream or 0) != int(torch.cuda.current_stream().cuda_stream)
+        grp = self.side_group if on_side else None
         if n_slo:
             keep.append(_tensor(send_lo, P * n_slo))
-            ops.append(dist.P2POp(dist.isend, keep[-1], self.rank - 1))
+            ops.append(dist.P2POp(dist.isend, keep[-1], self.rank - 1, group=grp))
         if n_rlo:
             keep.append(_tensor(recv_lo, P * n_rlo))
-            ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank - 1))
+            ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank - 1, group=grp))
         if n_shi:
             keep.append(_tensor(send_hi, P * n_shi))
-            ops.append(dist.P2POp(dist.isend, keep[-1], self.rank + 1))
+            ops.append(dist.P2POp(dist.isend, keep[-1], self.rank + 1, group=grp))
         if n_rhi:
             keep.append(_tensor(recv_hi, P * n_rhi))
-            ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank + 1))
+            ops.append(dist.P2POp(dist.irecv, keep[-1], self.rank + 1, group=grp))
         if ops:
             with self._on(stream):
                 for req in dist.batch_isend_irecv(ops):
