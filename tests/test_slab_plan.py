@@ -110,3 +110,21 @@ def test_gloo_halo_exchange_and_allreduce_protocol(tmp_path):
     out = str(tmp_path / "rank%d.txt")
     mp.spawn(_worker, args=(2, _free_port(), 4, 3, 7, out), nprocs=2, join=True)
     assert open(out % 0).read() == "ok" and open(out % 1).read() == "ok"
+
+
+def test_eight_slabs_schedule_is_a_wavefront():
+    """The 8-GPU configuration of bench.py (one volume in eight z-slabs), scaled down: every rank's blocks with
+    work form one contiguous run, each rank starts later than the one below it (the stagger DESIGN.md section 7
+    measures), and the pipeline needs n_blocks + world - 1 steps."""
+    nx, ny, nz, world = 6, 6, 48, 8
+    plans = [SlabPlan(nx, ny, nz, r, world) for r in range(world)]
+    nb, B = plans[0].n_blocks, plans[0].block_planes
+    first = []
+    for r, p in enumerate(plans):
+        # local hyper-planes of slab r are global planes [zlo, zlo + nx + ny + nz_local - 2]
+        lo, hi = p.zlo, p.zlo + nx + ny + p.nz_local - 3
+        busy = [b for b in range(nb) if not ((b + 1) * B - 1 < lo or b * B > hi)]
+        assert busy == list(range(busy[0], busy[-1] + 1))
+        first.append(busy[0] + r)                     # rank r sweeps block b at step b + r
+        assert busy[-1] + r <= nb + world - 2
+    assert all(b > a for a, b in zip(first, first[1:]))
