@@ -856,6 +856,12 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
     double *mean_p = sc.get<double>((size_t)P * N), *cov_p = sc.get<double>((size_t)NT * N);
     double *noise_p = sc.get<double>((size_t)2 * N), *F_p = sc.get<double>(N), *hist_p = sc.get<double>((size_t)H * N);
     int *its_p = sc.get<int>(N), *status_p = sc.get<int>(N);
+    /* allow-bad-voxels: the status words as they stood when the iteration began (Vb::IgnoreVoxel, see
+     * nbr_alive in vb_spatial.cuh); without it any failure ends the run and the live array serves */
+    int *status_prev = prob->allow_bad_voxels ? sc.get<int>(N) : status_p;
+    if (!status_prev)
+        return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+    sp.status_prev = status_prev;
     if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !rank || !bad || !iota || !plane_sorted || !nnp
         || !plane_starts || !sp.centre || !sp.stats || !sp.m0 || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK
         || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last || !y_p || !mean_p || !cov_p || !noise_p || !F_p || !hist_p
@@ -888,6 +894,20 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
     const unsigned gridN = (unsigned)((N + 255) / 256);
     sp_grid_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, bad);
     count_launch();
+    {
+        /* nothing below may index by plane or grid cell before the coordinates are known to be inside the
+         * grid: a caller's bad coords must come back as ERR_INVALID, not as an illegal address */
+        int h_bad0 = 0;
+        cudaMemcpyAsync(&h_bad0, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t be = cudaStreamSynchronize(st);
+        if (be != cudaSuccess)
+            return cuda_fail(be, "spatial coordinate check");
+        if (h_bad0 == 1)
+            return fail(FABBER_CUDA_ERR_INVALID, "voxel coordinates outside the nx, ny, nz grid");
+        if (h_bad0 == 2)
+            return fail(FABBER_CUDA_ERR_INVALID,
+                "coordinates must be in increasing order (x fastest, then y, then z), inference_vb.cc:769-793");
+    }
     sp_neighbour_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, prob->spatial_dims, nn_idx,
         plane_of, hist);
     count_launch();
@@ -1062,6 +1082,8 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
             FAB_SP_LAUNCH(sp_ak_partial);
         FAB_SP_LAUNCH(sp_ak_final);
         sp.ak_phase = 0;
+        if (status_prev != status_p)
+            cudaMemcpyAsync(status_prev, status_p, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, st);
         FAB_SP_LAUNCH(sp_theta);
         sp.plane_first = 0;
         sp.plane_last = sp.n_planes;
@@ -1110,7 +1132,7 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
         ak_ahead = false;
         if (slab)
         {
-            const bool ahead = any_spatial && it + 1 < max_it && !slab_exchange_on_main();
+            const bool ahead = any_spatial && it + 1 < max_it && !slab_exchange_on_main() && !prob->allow_bad_voxels;
             cudaStream_t xs = ahead ? side.s : st;
             if (ahead)
             {
@@ -1135,7 +1157,10 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
                 halo_kernel<false><<<(slab->n_recv_hi + 255) / 256, 256, 0, xs>>>(
                     mean_p, slab->recv_hi, rank, slab->n_recv_hi, P, N, halo_recv_hi);
             count_launch();
-            if (any_spatial && it + 1 < max_it)
+            /* with allow_bad_voxels the sums must see the failures sp_noise of THIS iteration records
+             * (CalculateaK skips ignored voxels, priors.cc:238-241): then they are formed in order, at the top of
+             * the next iteration, not under sp_noise */
+            if (any_spatial && it + 1 < max_it && !prob->allow_bad_voxels)
             {
                 if (!ahead)
                 {

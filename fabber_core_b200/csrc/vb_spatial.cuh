@@ -64,10 +64,25 @@ struct SpArgs
                         2: aK from ak_sums (after the host all-reduced them across z-slabs) */
     double *ak_sums; /* [2][P] */
     int n_global;    /* voxels of the WHOLE volume (hK = N/2 + q2, priors.cc:313); == v.N on one GPU */
+    /* [N] status words as they were when this iteration began (== v.status unless allow_bad_voxels): which
+     * neighbours Vb::IgnoreVoxel had already struck from the lists, see nbr_alive() */
+    const int *status_prev;
     double q1, q2, speed;
 };
 
 FAB_DEV bool is_spatial_type(char t) { return t == 'M' || t == 'm' || t == 'P' || t == 'p'; }
+
+/* Vb::IgnoreVoxel (inference_vb.cc:266-297): a voxel that failed under allow-bad-voxels is erased from its
+ * neighbours' lists, so it no longer counts towards nn and its stale mean no longer feeds the MRF prior mean
+ * or the aK sums. The lists here are static; a neighbour is skipped when its status word reports a failure.
+ * Ghost voxels of a z-slab are alive (their owner updates them). */
+FAB_DEV bool nbr_alive(const int *status, int n)
+{
+    if (n < 0)
+        return false;
+    const int st = status[n];
+    return st == 0 || st == FABBER_VOX_GHOST;
+}
 
 /* ---- set-up: initial posterior, noise, first ReCentre (Vb::SetupPerVoxelDists) ------------------- */
 template <class Model> __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_setup_kernel(const __grid_constant__ SpArgs s)
@@ -168,6 +183,8 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + v];
+            if (!nbr_alive(a.status, nbr[j])) /* every failure so far: CalculateaK runs at v == 1 */
+                nbr[j] = -1;
             nn += nbr[j] >= 0;
         }
 #pragma unroll
@@ -313,7 +330,7 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
     int nn = 0;
 #pragma unroll
     for (int j = 0; j < 6; j++)
-        nn += s.nn_idx[j * N + v] >= 0;
+        nn += nbr_alive(s.status_prev, s.nn_idx[j * N + v]);
     const int dims = s.spatial_dims;
     double Fprior = 0.0;
     bool coupled[P];
@@ -435,9 +452,15 @@ template <int P> struct SweepVoxel
         const size_t N = (size_t)a.N;
         v = pos;
         live = a.status[pos] == 0;
+        /* neighbours struck by IgnoreVoxel before this iteration are gone from the list (same count as
+         * sp_theta used for the prior precision) */
 #pragma unroll
         for (int j = 0; j < 6; j++)
+        {
             nbr[j] = s.nn_idx[j * N + pos];
+            if (!nbr_alive(s.status_prev, nbr[j]))
+                nbr[j] = -1;
+        }
 #pragma unroll
         for (int i = 0; i < P; i++)
         {
@@ -674,6 +697,8 @@ __global__ void sp_neighbour_kernel(const int *coords, int N, int nx, int ny, in
     if (v >= N)
         return;
     const int x = coords[v], y = coords[(size_t)N + v], z = coords[2 * (size_t)N + v];
+    if (x < 0 || y < 0 || z < 0 || x >= nx || y >= ny || z >= nz)
+        return; /* reported by sp_grid_kernel; never index plane_hist with it */
     const int dx[6] = { 1, -1, 0, 0, 0, 0 }, dy[6] = { 0, 0, 1, -1, 0, 0 }, dz[6] = { 0, 0, 0, 0, 1, -1 };
 #pragma unroll
     for (int j = 0; j < 6; j++)

@@ -273,6 +273,8 @@ void Vb::DoCalculations(FabberRunData &rundata)
             else
                 throw InvalidOptionValue("noise-pattern", pat, "Invalid character in pattern");
         }
+        if (digits.empty())
+            throw InvalidOptionValue("noise-pattern", pat, "Pattern must not be empty");
         int nphis = *std::max_element(digits.begin(), digits.end());
         if (nphis > FABBER_CUDA_MAX_PHIS)
             throw InvalidOptionValue("noise-pattern", pat, "more noise precisions than the device kernels carry");

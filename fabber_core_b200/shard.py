@@ -4,7 +4,8 @@ Non-spatial VB: voxels are independent (inference_vb.cc:423-571), so the masked 
 contiguous, balanced ranges - one per rank, one process per GPU - with NO data-path collective; the only
 communication is the final gather of the result arrays (torch.distributed, NCCL on GPUs / gloo in the
 CPU tests). Spatial VB partitions z-slabs (voxel order is z-major, so a slab is a contiguous range too);
-its halo exchange is not built yet - see DESIGN.md section 7.
+the slab run itself - all-reduced aK sums, the pipelined exact sweep and the halo exchange - lives in
+fabber_cuda_vb_spatial_slab / spatial_mgpu.py, see DESIGN.md section 7.
 """
 import numpy as np
 

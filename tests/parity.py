@@ -104,3 +104,28 @@ def compare(gpu, ref, P, probes=None, rtol=RTOL, check_f=True, label="", max_amb
     bad = {k: v for k, v in errs.items() if not (v <= tol[k])}
     assert not bad, "%s parity outside tolerance: %s (tolerance %s, floor %s, all %s)" % (label, bad, tol, floor, errs)
     return report
+
+
+def one_bad_voxel_case():
+    """A spatial run in which exactly ONE voxel fails under allow-bad-voxels, with finite numbers only (the
+    reference asserts on a NaN centre, fwdmodel_linear.cc:128): mono-exponential model, amplitude under an
+    image prior whose value for the bad voxel is 800 in Fabber (log) space -> exp overflows in the second
+    loop's ReCentre -> Vb::IgnoreVoxel (inference_vb.cc:266-297) strikes it from its neighbours' lists, so
+    their neighbour counts, MRF prior means and the aK sums change from the next iteration on. The decay rate
+    carries the 'M' prior; the amplitude is not spatial, so nothing but the neighbour lists is touched.
+    Returns (spec kwargs, data [T][N], coords, shape, image, index of the bad voxel)."""
+    nx, ny, nz, T = 6, 5, 4, 60
+    n = nx * ny * nz
+    rng = np.random.default_rng(7)
+    t = np.arange(T) * 0.05
+    amp = 1.0 + 0.2 * rng.random(n)
+    r = 1.0 + 0.3 * rng.random(n)
+    y = (amp[None, :] * np.exp(-r[None, :] * t[:, None]) + 0.01 * rng.standard_normal((T, n))).astype(np.float32)
+    bad = 2 + 2 * nx + 1 * nx * ny
+    img = np.log(amp).astype(np.float32).astype(np.float64)
+    img[bad] = 800.0
+    idx = np.arange(n)
+    coords = np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.int32)
+    kw = dict(model="exp", num_exps=1, dt=0.05, prior_types=list("IM"), max_iterations=5, allow_bad_voxels=True,
+              param_overrides={"amp1": {"prec": 100.0}})
+    return kw, y, coords, (nx, ny, nz), img, bad

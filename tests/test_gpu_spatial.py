@@ -93,6 +93,20 @@ def test_spatial_blow_up_is_reported_like_the_reference():
     assert np.array_equal(gpu["status"] != 0, ref["status"] != 0)
 
 
+def test_failed_voxel_is_struck_from_its_neighbours_lists():
+    """allow-bad-voxels: one voxel fails in the second loop (finite numbers only); Vb::IgnoreVoxel
+    (inference_vb.cc:266-297) removes it from its neighbours' lists - their neighbour counts, MRF prior means
+    and the aK sums must follow the oracle (pinned bit for bit on the reference's own code for this very case in
+    tests/test_reference_build.py)."""
+    from parity import one_bad_voxel_case
+
+    kw, y, coords, shape, img, bad = one_bad_voxel_case()
+    gpu, ref, probes = both_spatial(kw, y, coords, shape, image_priors={0: img})
+    assert list(np.nonzero(ref["status"])[0]) == [bad] and list(np.nonzero(gpu["status"])[0]) == [bad]
+    compare(gpu, ref, 2, probes, check_f=False, label="spatial IgnoreVoxel, one bad voxel")
+    check_ak(gpu, ref, probes)
+
+
 def test_spatial_irregular_mask_and_update_first_iter():
     nx, ny, nz = 11, 11, 7
     zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")

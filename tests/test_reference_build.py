@@ -177,6 +177,36 @@ def test_spatial_biexp_mrf_irregular_mask():
     assert rel(F, ref["free_energy"]) < TIGHT
 
 
+def test_ignore_voxel_strikes_the_failed_voxel_from_its_neighbours():
+    """allow-bad-voxels in spatial mode: one voxel fails in the second loop, Vb::IgnoreVoxel
+    (inference_vb.cc:266-297) removes it from its neighbours' lists; the oracle follows the reference's code
+    bit for bit through that, including the aK history."""
+    from parity import one_bad_voxel_case
+
+    kw, y, coords, shape, img, bad = one_bad_voxel_case()
+    kw = dict(kw)
+    kw.pop("model")
+    spec = abi.ProblemSpec("exp", y.shape[0], **kw)
+    spec.prob.nx, spec.prob.ny, spec.prob.nz = shape
+    ref = oracle.run(spec, y, spatial=True, coords=coords, image_priors={0: img})
+    assert list(np.nonzero(ref["status"])[0]) == [bad]
+    f = refbuild.ReferenceFabber()
+    f.run_with_data({"model": "exp", "num-exps": 1, "dt": 0.05, "noise": "white", "method": "spatialvb",
+                     "param-spatial-priors": "IM", "max-iterations": 5, "allow-bad-voxels": True, "save-mvn": True,
+                     "PSP_byname1": "amp1", "PSP_byname1_prec": 100.0, "PSP_byname1_image": "ampimg"},
+                    {"data": refbuild.volume(y, shape),
+                     "ampimg": refbuild.volume(img[None, :].astype(np.float32), shape)})
+    mvn = f.doubles("finalMVN", y.shape[1])
+    for i in range(2):
+        assert rel(mvn[6 + i], ref["mean"][i]) < TIGHT      # the frozen bad voxel included
+        assert rel(mvn[tri(i, i)], ref["cov"][tri(i, i)]) < TIGHT
+    # the strike matters: the same run with the bad voxel's image value repaired differs next to it
+    img2 = img.copy()
+    img2[bad] = np.log(1.1)
+    ok = oracle.run(spec, y, spatial=True, coords=coords, image_priors={0: img2})
+    assert rel(ok["mean"][1][bad - 1], ref["mean"][1][bad - 1]) > 1e-6
+
+
 def locked_mvn(P, n_noise, centres):
     """an MVN volume (dist_mvn.cc:377-433 layout) whose first P means are `centres` [P][N]; float32-exact"""
     n_all = P + n_noise
