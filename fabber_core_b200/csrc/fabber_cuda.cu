@@ -42,9 +42,11 @@ static int cuda_fail(cudaError_t e, const char *what)
  * (seconds, and erratic - measured). Keep it cached in the pool instead. */
 static void keep_pool_memory()
 {
-    static int done_for_device = -1;
+    static std::atomic<unsigned long long> done_mask(0); /* one bit per device: a run may span several */
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev == done_for_device)
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64)
+        return;
+    if (done_mask.load(std::memory_order_relaxed) & (1ull << dev))
         return;
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
@@ -52,7 +54,7 @@ static void keep_pool_memory()
         unsigned long long threshold = ~0ull;
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
     }
-    done_for_device = dev;
+    done_mask.fetch_or(1ull << dev, std::memory_order_relaxed);
 }
 
 /* getters exported by the per-model translation units (vb_inst.cu) */
@@ -559,6 +561,14 @@ int fabber_cuda_set_device(int dev)
     return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaSetDevice");
 }
 
+int fabber_cuda_get_device(void)
+{
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess)
+        return -1;
+    return dev;
+}
+
 const char *fabber_cuda_last_error(void) { return g_last_error.c_str(); }
 
 void *fabber_cuda_malloc(unsigned long long bytes)
@@ -744,6 +754,29 @@ int fabber_cuda_memcpy2d_h2d(void *dst, unsigned long long dst_pitch, const void
     cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyHostToDevice,
         (cudaStream_t)stream);
     return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaMemcpy2DAsync");
+}
+
+int fabber_cuda_memcpy2d_d2h(void *dst, unsigned long long dst_pitch, const void *src, unsigned long long src_pitch,
+    unsigned long long width_bytes, unsigned long long rows, void *stream)
+{
+    cudaError_t e = cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, width_bytes, rows, cudaMemcpyDeviceToHost,
+        (cudaStream_t)stream);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaMemcpy2DAsync(d2h)");
+}
+int fabber_cuda_event_sync(void *event)
+{
+    cudaError_t e = cudaEventSynchronize((cudaEvent_t)event);
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "cudaEventSynchronize");
+}
+int fabber_cuda_host_is_pinned(const void *host_ptr)
+{
+    cudaPointerAttributes at;
+    if (!host_ptr || cudaPointerGetAttributes(&at, host_ptr) != cudaSuccess)
+    {
+        cudaGetLastError(); /* older runtimes report unregistered memory as an error: clear it */
+        return 0;
+    }
+    return at.type == cudaMemoryTypeHost ? 1 : 0;
 }
 
 int fabber_cuda_vb_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf, void *stream)

@@ -112,8 +112,32 @@ template <class T> std::string stringify(const T &v)
  * blocks are parked by size and handed out again. */
 void *cached_pinned_alloc(size_t bytes);
 void cached_pinned_free(void *p, size_t bytes);
-void *cached_device_alloc(size_t bytes);
+void *cached_device_alloc(size_t bytes); /* on the calling thread's current device */
 void cached_device_free(void *p, size_t bytes);
+
+/* ---- the GPUs of a run -------------------------------------------------------------------------------
+ * One process drives every GPU of the box: voxelwise VB deals contiguous voxel ranges to the devices (voxels
+ * are independent, inference_vb.cc:423-571), each with its own copy stream, kernels and result arrays.
+ * FABBER_B200_DEVICES = "all" | comma list of ordinals picks them; unset: a process started by a one-process-
+ * per-GPU launcher (LOCAL_RANK / LOCAL_WORLD_SIZE in the environment) stays on its own GPU, any other process
+ * takes all visible ones. A device only takes part when it gets at least FABBER_B200_MIN_VOXELS_PER_DEVICE
+ * (default 65536) voxels. */
+const std::vector<int> &run_devices();
+struct DeviceScope /* make `device` current for the calling thread, restore the previous one on exit */
+{
+    int prev;
+    explicit DeviceScope(int device);
+    ~DeviceScope();
+    DeviceScope(const DeviceScope &) = delete;
+    DeviceScope &operator=(const DeviceScope &) = delete;
+};
+void *copy_stream_of(int device); /* one non-blocking copy stream per device for the life of the process */
+
+/* ---- host worker pool: threads are created once per process, not per call ---------------------------- */
+size_t host_threads();
+struct PoolJob;
+PoolJob *pool_launch(size_t n_workers, const std::function<void()> &fn); /* fn runs once on each of n workers */
+void pool_wait(PoolJob *job);                                            /* blocks, then frees the job */
 
 /* ---- voxel data: rows x nvoxels, row t = volume t (rundata.h:628) --------------------------------
  * float32 throughout: every value enters (fabber_set_data) and leaves (fabber_get_data) the reference's
@@ -123,16 +147,32 @@ struct VoxelData
     int rows;
     size_t cols;
     float *f;   /* pinned host memory [rows][cols] */
-    float *dev; /* optional device-resident copy (main data: uploaded while it is being set) */
-    /* the upload of `dev` goes block of voxels by block of voxels on a copy stream; `ready` is recorded there
-     * after columns [v0, v1) have been queued, so a consumer can start on a block while later ones travel */
+    /* optional device-resident copy (main data: uploaded while it is being set): the voxels [v0, v1) of part p
+     * live on parts[p].device as a [rows][v1 - v0] array. One part = one GPU. */
+    struct Part
+    {
+        int device;
+        size_t v0, v1;
+        float *dev;
+    };
+    std::vector<Part> parts;
+    /* the upload goes block of voxels by block of voxels on the owning device's copy stream; `ready` is
+     * recorded there after columns [v0, v1) have been queued, so a consumer can start on a block while later
+     * ones travel */
     struct Block
     {
         size_t v0, v1;
         void *ready; /* fabber_cuda event */
+        int part;
     };
     std::vector<Block> blocks;
-    void wait_uploaded(); /* make the default stream wait for every block */
+    /* false while `f` has not been filled: the caller's buffer was page-locked and went to the devices by DMA
+     * without a staging copy. ensure_host() downloads it on demand. */
+    bool host_valid;
+    void ensure_host();
+    void wait_uploaded(int part); /* make that device's default stream wait for every block of the part */
+    void release_device();        /* drain pending work, hand the device copies back to the cache */
+    void upload_whole(int device); /* (re)load everything on to ONE device from the host copy */
     VoxelData();
     ~VoxelData();
     VoxelData(const VoxelData &) = delete;
@@ -224,6 +264,7 @@ protected:
 
 private:
     const VoxelData &GetMainVoxelDataMultiple();
+    bool LooksSpatial() const;
     std::string m_outdir;
     std::set<std::string> m_used_params;
     std::map<std::string, int> m_warncount;
@@ -231,6 +272,7 @@ private:
     std::map<std::string, std::unique_ptr<VoxelData>> m_voxel_data;
     int m_extent[3];
     bool m_have_extent;
+    bool m_device_only_access;
     std::vector<int> m_mask, m_voxel_index, m_coords;
     std::ostringstream m_log;
     void (*m_progress)(int, int);
@@ -410,7 +452,16 @@ private:
         void *p = nullptr;
         size_t bytes = 0;
     };
-    DevArray m_d_mean, m_d_cov, m_d_noise, m_d_F, m_d_hist, m_d_its, m_d_status;
+    /* one context per GPU of the run: its contiguous voxel range [v0, v1), the device copy of that range's
+     * series ([T][v1 - v0]) and its result arrays (all strides v1 - v0) */
+    struct DevCtx
+    {
+        int device = 0;
+        size_t v0 = 0, v1 = 0;
+        const float *data = nullptr;
+        DevArray mean, cov, noise, F, hist, its, status;
+    };
+    std::vector<DevCtx> m_ctx;
     void ReleaseDevice();
 
 public:

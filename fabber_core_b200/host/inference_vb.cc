@@ -178,18 +178,24 @@ bool Vb::IsSpatial(FabberRunData &rundata, const std::vector<Parameter> &params)
 
 void Vb::ReleaseDevice()
 {
-    DevArray *all[] = { &m_d_mean, &m_d_cov, &m_d_noise, &m_d_F, &m_d_hist, &m_d_its, &m_d_status };
-    bool any = false;
-    for (DevArray *d : all)
-        any = any || d->p;
-    if (any)
-        fabber_cuda_stream_sync(nullptr);
-    for (DevArray *d : all)
+    for (size_t g = 0; g < m_ctx.size(); g++)
     {
-        cached_device_free(d->p, d->bytes);
-        d->p = nullptr;
-        d->bytes = 0;
+        DevCtx &c = m_ctx[g];
+        DeviceScope scope(c.device);
+        DevArray *all[] = { &c.mean, &c.cov, &c.noise, &c.F, &c.hist, &c.its, &c.status };
+        bool any = false;
+        for (DevArray *d : all)
+            any = any || d->p;
+        if (any)
+            fabber_cuda_stream_sync(nullptr);
+        for (DevArray *d : all)
+        {
+            cached_device_free(d->p, d->bytes);
+            d->p = nullptr;
+            d->bytes = 0;
+        }
     }
+    m_ctx.clear();
 }
 
 void Vb::DoCalculations(FabberRunData &rundata)
@@ -360,20 +366,44 @@ void Vb::DoCalculations(FabberRunData &rundata)
     if (N == 0)
         return; /* zero voxels is not an error (test/test_inference.cc:57-73) */
 
-    /* ---- device result arrays (cached blocks: no cudaMalloc on the steady-state path) ---------------- */
+    /* ---- the devices of this run: one contiguous voxel range per GPU (the series is normally already there,
+     * dealt out while it was being set); spatial VB couples the voxels and runs on one device ------------- */
     ReleaseDevice();
-    auto dev = [](DevArray &d, size_t bytes) {
-        d.bytes = bytes;
-        d.p = cached_device_alloc(bytes);
-    };
-    dev(m_d_mean, (size_t)P * N * sizeof(double));
-    dev(m_d_cov, (size_t)NT * N * sizeof(double));
-    dev(m_d_noise, (size_t)NN * N * sizeof(double));
-    dev(m_d_F, N * sizeof(double));
-    dev(m_d_its, N * sizeof(int));
-    dev(m_d_status, N * sizeof(int));
-    if (m_fhist_len > 0)
-        dev(m_d_hist, (size_t)m_fhist_len * N * sizeof(double));
+    if (data.parts.empty() || (spatial && data.parts.size() != 1))
+    {
+        const std::vector<int> &devs = run_devices();
+        if (devs.empty())
+            throw FabberInternalError(std::string("no CUDA device: ") + fabber_cuda_last_error());
+        data.upload_whole(devs[0]);
+    }
+    for (size_t g = 0; g < data.parts.size(); g++)
+    {
+        DevCtx c;
+        c.device = data.parts[g].device;
+        c.v0 = data.parts[g].v0;
+        c.v1 = data.parts[g].v1;
+        c.data = data.parts[g].dev;
+        m_ctx.push_back(c);
+    }
+    /* device result arrays (cached blocks: no cudaMalloc on the steady-state path) */
+    for (size_t g = 0; g < m_ctx.size(); g++)
+    {
+        DevCtx &c = m_ctx[g];
+        DeviceScope scope(c.device);
+        const size_t n = c.v1 - c.v0;
+        auto dev = [](DevArray &d, size_t bytes) {
+            d.bytes = bytes;
+            d.p = cached_device_alloc(bytes);
+        };
+        dev(c.mean, (size_t)P * n * sizeof(double));
+        dev(c.cov, (size_t)NT * n * sizeof(double));
+        dev(c.noise, (size_t)NN * n * sizeof(double));
+        dev(c.F, n * sizeof(double));
+        dev(c.its, n * sizeof(int));
+        dev(c.status, n * sizeof(int));
+        if (m_fhist_len > 0)
+            dev(c.hist, (size_t)m_fhist_len * n * sizeof(double));
+    }
 
     /* ---- restart / output-only (inference_vb.cc:181-216, 385-389) ------------------------------------ */
     std::vector<double> init_mean, init_cov, init_noise;
@@ -452,52 +482,66 @@ void Vb::DoCalculations(FabberRunData &rundata)
         });
         rundata.Log() << "Vb::Loading fixed linearization centres from the MVN '" << lock_name << "'" << std::endl;
     }
+    /* rows x N host array -> the columns [v0, v1) of every row on the current device */
+    auto copy_columns = [&](void *dst, const std::vector<double> &h, int rows, const DevCtx &c) {
+        const size_t n = c.v1 - c.v0;
+        check(fabber_cuda_memcpy2d_h2d(dst, n * sizeof(double), h.data() + c.v0, N * sizeof(double), n * sizeof(double),
+                  (size_t)rows, nullptr),
+            "copying to the GPU");
+    };
     if (rundata.GetBool("output-only"))
     {
         if (!continue_from_mvn)
             throw FabberRunDataError("output-only requires continue-from-mvn");
-        check(fabber_cuda_memcpy_h2d(m_d_mean.p, init_mean.data(), m_d_mean.bytes, nullptr), "output-only");
-        check(fabber_cuda_memcpy_h2d(m_d_cov.p, init_cov.data(), m_d_cov.bytes, nullptr), "output-only");
-        check(fabber_cuda_memcpy_h2d(m_d_noise.p, init_noise.data(), m_d_noise.bytes, nullptr), "output-only");
-        check(fabber_cuda_memset(m_d_F.p, 0, m_d_F.bytes, nullptr), "output-only");
-        check(fabber_cuda_memset(m_d_its.p, 0, m_d_its.bytes, nullptr), "output-only");
-        check(fabber_cuda_stream_sync(nullptr), "output-only");
+        for (size_t g = 0; g < m_ctx.size(); g++)
+        {
+            DevCtx &c = m_ctx[g];
+            DeviceScope scope(c.device);
+            copy_columns(c.mean.p, init_mean, P, c);
+            copy_columns(c.cov.p, init_cov, NT, c);
+            copy_columns(c.noise.p, init_noise, NN, c);
+            check(fabber_cuda_memset(c.F.p, 0, c.F.bytes, nullptr), "output-only");
+            check(fabber_cuda_memset(c.its.p, 0, c.its.bytes, nullptr), "output-only");
+            check(fabber_cuda_stream_sync(nullptr), "output-only");
+        }
         m_needF = false;
         rundata.Log() << "Vb::DoCalculations output-only set - not performing any calculations" << std::endl;
         return;
     }
 
-    /* ---- inputs: the series is normally already on the device (uploaded while it was being set) ------- */
+    /* ---- inputs --------------------------------------------------------------------------------------- */
     rundata.Log() << "Vb::" << (spatial ? "Spatial" : "Voxelwise") << " calculations on the GPU: " << N << " voxels x "
-                  << T << " time points, " << P << " parameters" << std::endl;
+                  << T << " time points, " << P << " parameters, " << m_ctx.size() << " device"
+                  << (m_ctx.size() == 1 ? "" : "s") << std::endl;
     rundata.Progress(0, (int)N);
-    fabber_cuda_vb_buffers buf;
-    memset(&buf, 0, sizeof(buf));
-    if (!data.dev)
+    struct Scratch
     {
-        data.dev = (float *)cached_device_alloc(data.bytes());
-        check(fabber_cuda_memcpy_h2d(data.dev, data.f, data.bytes(), nullptr), "copying data to the GPU");
-    }
-    buf.data = data.dev;
-    std::vector<DevArray> scratch;
-    auto upload = [&](const void *h, size_t bytes) -> void * {
+        int device;
         DevArray d;
-        d.bytes = bytes;
-        d.p = cached_device_alloc(bytes);
-        scratch.push_back(d);
-        check(fabber_cuda_memcpy_h2d(d.p, h, bytes, nullptr), "copying to the GPU");
-        return d.p;
     };
+    std::vector<Scratch> scratch;
     struct ScratchGuard
     {
-        std::vector<DevArray> &s;
+        std::vector<Scratch> &s;
         ~ScratchGuard()
         {
-            fabber_cuda_stream_sync(nullptr);
             for (size_t i = 0; i < s.size(); i++)
-                cached_device_free(s[i].p, s[i].bytes);
+            {
+                DeviceScope scope(s[i].device);
+                fabber_cuda_stream_sync(nullptr);
+                cached_device_free(s[i].d.p, s[i].d.bytes);
+            }
         }
     } guard = { scratch };
+    auto upload_columns = [&](const std::vector<double> &h, int rows, const DevCtx &c) -> void * {
+        Scratch sc;
+        sc.device = c.device;
+        sc.d.bytes = (size_t)rows * (c.v1 - c.v0) * sizeof(double);
+        sc.d.p = cached_device_alloc(sc.d.bytes);
+        scratch.push_back(sc);
+        copy_columns(sc.d.p, h, rows, c);
+        return sc.d.p;
+    };
     std::vector<std::vector<double>> images(P);
     for (int i = 0; i < P; i++)
         if (params[i].prior_type == 'I')
@@ -507,57 +551,104 @@ void Vb::DoCalculations(FabberRunData &rundata)
             images[i].resize(N);
             for (size_t v = 0; v < N; v++)
                 images[i][v] = img.at(0, v);
-            buf.image_prior[i] = (const double *)upload(images[i].data(), N * sizeof(double));
         }
-    if (continue_from_mvn)
+    std::vector<fabber_cuda_vb_buffers> bufs(m_ctx.size());
+    std::vector<fabber_cuda_vb_problem> probs(m_ctx.size(), prob);
+    for (size_t g = 0; g < m_ctx.size(); g++)
     {
-        buf.init_mean = (const double *)upload(init_mean.data(), init_mean.size() * sizeof(double));
-        buf.init_cov = (const double *)upload(init_cov.data(), init_cov.size() * sizeof(double));
-        buf.init_noise = (const double *)upload(init_noise.data(), init_noise.size() * sizeof(double));
+        DevCtx &c = m_ctx[g];
+        DeviceScope scope(c.device);
+        fabber_cuda_vb_buffers &buf = bufs[g];
+        memset(&buf, 0, sizeof(buf));
+        probs[g].n_voxels = (int)(c.v1 - c.v0);
+        buf.data = c.data;
+        for (int i = 0; i < P; i++)
+            if (!images[i].empty())
+                buf.image_prior[i] = (const double *)upload_columns(images[i], 1, c);
+        if (continue_from_mvn)
+        {
+            buf.init_mean = (const double *)upload_columns(init_mean, P, c);
+            buf.init_cov = (const double *)upload_columns(init_cov, NT, c);
+            buf.init_noise = (const double *)upload_columns(init_noise, NN, c);
+        }
+        if (!lock_centre.empty())
+            buf.lock_centre = (const double *)upload_columns(lock_centre, P, c);
+        if (spatial)
+        {
+            Scratch sc;
+            sc.device = c.device;
+            sc.d.bytes = 3 * N * sizeof(int);
+            sc.d.p = cached_device_alloc(sc.d.bytes);
+            scratch.push_back(sc);
+            check(fabber_cuda_memcpy_h2d(sc.d.p, rundata.Coords().data(), sc.d.bytes, nullptr), "copying to the GPU");
+            buf.coords = (const int *)sc.d.p;
+        }
+        buf.mean = (double *)c.mean.p;
+        buf.cov = (double *)c.cov.p;
+        buf.noise = (double *)c.noise.p;
+        buf.free_energy = (double *)c.F.p;
+        buf.status = (int *)c.status.p;
+        buf.iterations = (int *)c.its.p;
+        buf.f_history = m_fhist_len > 0 ? (double *)c.hist.p : nullptr;
     }
-    if (!lock_centre.empty())
-        buf.lock_centre = (const double *)upload(lock_centre.data(), lock_centre.size() * sizeof(double));
-    if (spatial)
-        buf.coords = (const int *)upload(rundata.Coords().data(), 3 * N * sizeof(int));
-    buf.mean = (double *)m_d_mean.p;
-    buf.cov = (double *)m_d_cov.p;
-    buf.noise = (double *)m_d_noise.p;
-    buf.free_energy = (double *)m_d_F.p;
-    buf.status = (int *)m_d_status.p;
-    buf.iterations = (int *)m_d_its.p;
-    buf.f_history = m_fhist_len > 0 ? (double *)m_d_hist.p : nullptr;
     rundata.Log() << "Vb::timing: option translation + device buffers " << sw.lap_ms() << " ms" << std::endl;
 
     int rc = FABBER_CUDA_OK;
-    if (spatial || data.blocks.size() <= 1)
+    if (spatial)
     {
-        data.wait_uploaded();
-        rc = spatial ? fabber_cuda_vb_spatial(&prob, &buf, nullptr) : fabber_cuda_vb_voxelwise(&prob, &buf, nullptr);
+        DeviceScope scope(m_ctx[0].device);
+        data.wait_uploaded(0);
+        rc = fabber_cuda_vb_spatial(&probs[0], &bufs[0], nullptr);
     }
     else
     {
-        /* voxels are independent (inference_vb.cc:423-571): one launch per uploaded block, each behind its
-         * block's event - block k computes while the blocks after it are still on the PCIe bus */
+        /* voxels are independent (inference_vb.cc:423-571): one launch per uploaded block on the block's
+         * device, each behind its block's event - block k computes while the blocks after it are still on
+         * the PCIe bus, and every device works on its own range. All calls are asynchronous. */
         for (size_t b = 0; b < data.blocks.size() && rc == FABBER_CUDA_OK; b++)
         {
-            rc = fabber_cuda_stream_wait_event(nullptr, data.blocks[b].ready);
+            const VoxelData::Block &blk = data.blocks[b];
+            const DevCtx &c = m_ctx[blk.part];
+            DeviceScope scope(c.device);
+            rc = fabber_cuda_stream_wait_event(nullptr, blk.ready);
             if (rc == FABBER_CUDA_OK)
-                rc = fabber_cuda_vb_voxelwise_range(&prob, &buf, (int)data.blocks[b].v0, (int)data.blocks[b].v1, nullptr);
+                rc = fabber_cuda_vb_voxelwise_range(&probs[blk.part], &bufs[blk.part], (int)(blk.v0 - c.v0),
+                    (int)(blk.v1 - c.v0), nullptr);
         }
+        if (data.blocks.empty()) /* uploaded in one piece */
+            for (size_t g = 0; g < m_ctx.size() && rc == FABBER_CUDA_OK; g++)
+            {
+                DeviceScope scope(m_ctx[g].device);
+                rc = fabber_cuda_vb_voxelwise(&probs[g], &bufs[g], nullptr);
+            }
     }
     if (rc == FABBER_CUDA_ERR_INVALID)
         throw FabberRunDataError(std::string("Vb: ") + fabber_cuda_last_error());
     check(rc, "VB kernels");
 
     /* ---- bad-voxel policy (inference_vb.cc:529-544; set-up failures are never caught, :235) ------------
-     * the status words are scanned on the device; only a count and the first offender come back */
+     * the status words are scanned on the devices; only a count and the first offender come back */
     static const char *reason[] = { "", "LinearizedFwdModel::ReCentre: Non-finite values found in offset",
         "LinearizedFwdModel::ReCentre: Non-finite values found in jacobian", "Non-finite free energy!",
         "matrix is singular", "Ar1cNoiseModel::UpdateAlpha Negative variance!", "voxel ignored" };
-    int first = -1, code = 0;
-    const int n_bad = fabber_cuda_check_status((const int *)m_d_status.p, (int)N, &first, &code, nullptr);
-    if (n_bad < 0)
-        check(n_bad, "VB kernels");
+    long n_bad = 0;
+    long first = -1;
+    int code = 0;
+    for (size_t g = 0; g < m_ctx.size(); g++)
+    {
+        DevCtx &c = m_ctx[g];
+        DeviceScope scope(c.device);
+        int first_g = -1, code_g = 0;
+        const int bad_g = fabber_cuda_check_status((const int *)c.status.p, (int)(c.v1 - c.v0), &first_g, &code_g, nullptr);
+        if (bad_g < 0)
+            check(bad_g, "VB kernels");
+        if (bad_g > 0 && first < 0) /* ranges are in voxel order: the first device with a failure holds the first */
+        {
+            first = (long)c.v0 + first_g;
+            code = code_g;
+        }
+        n_bad += bad_g;
+    }
     rundata.Log() << "Vb::timing: kernels " << sw.lap_ms() << " ms" << std::endl;
     rundata.Progress((int)N, (int)N);
     if (n_bad > 0)
@@ -578,43 +669,29 @@ void Vb::SaveResults(FabberRunData &rundata)
     const int P = m_num_params, T = m_ntimes;
     const std::vector<Parameter> &params = m_model->Params();
     const int NP_all = P + m_noise_params;
-    if (N == 0 || !m_d_mean.p)
+    if (N == 0 || m_ctx.empty())
     {
         rundata.Log() << "Vb::Done writing results." << std::endl;
         return;
     }
     /* Every requested output map is produced on the device in float32 (fabber_cuda_vb_save_results) and
-     * downloaded straight into the pinned buffer fabber_get_data will read from. */
-    fabber_cuda_vb_buffers buf;
-    memset(&buf, 0, sizeof(buf));
-    buf.mean = (double *)m_d_mean.p;
-    buf.cov = (double *)m_d_cov.p;
-    buf.noise = (double *)m_d_noise.p;
-    buf.free_energy = m_needF ? (double *)m_d_F.p : nullptr;
-    buf.iterations = (int *)m_d_its.p;
-    buf.f_history = m_fhist_len > 0 ? (double *)m_d_hist.p : nullptr;
-    fabber_cuda_vb_outputs out;
-    memset(&out, 0, sizeof(out));
-    struct Pending
+     * downloaded straight into the pinned buffer fabber_get_data will read from - each device writes the
+     * columns of its own voxel range. */
+    struct Wanted
     {
-        float **slot;
+        float *fabber_cuda_vb_outputs::*slot;
         int rows;
         std::vector<std::string> keys; /* one key per row group of `rows_per_key` rows */
         int rows_per_key;
-        void *dev;
-        size_t bytes;
     };
-    std::vector<Pending> pending;
-    auto want = [&](float **slot, int rows, const std::vector<std::string> &keys, int rows_per_key) {
-        Pending p;
-        p.slot = slot;
-        p.rows = rows;
-        p.keys = keys;
-        p.rows_per_key = rows_per_key;
-        p.bytes = (size_t)rows * N * sizeof(float);
-        p.dev = cached_device_alloc(p.bytes);
-        *slot = (float *)p.dev;
-        pending.push_back(p);
+    std::vector<Wanted> wanted;
+    auto want = [&](float *fabber_cuda_vb_outputs::*slot, int rows, const std::vector<std::string> &keys, int rows_per_key) {
+        Wanted w;
+        w.slot = slot;
+        w.rows = rows;
+        w.keys = keys;
+        w.rows_per_key = rows_per_key;
+        wanted.push_back(w);
     };
     auto per_param = [&](const std::string &prefix) {
         std::vector<std::string> k;
@@ -623,74 +700,122 @@ void Vb::SaveResults(FabberRunData &rundata)
         return k;
     };
     if (rundata.GetBool("save-mean"))
-        want(&out.mean, P, per_param("mean_"), 1);
+        want(&fabber_cuda_vb_outputs::mean, P, per_param("mean_"), 1);
     if (rundata.GetBool("save-std"))
-        want(&out.std, P, per_param("std_"), 1);
+        want(&fabber_cuda_vb_outputs::std, P, per_param("std_"), 1);
     if (rundata.GetBool("save-zstat"))
-        want(&out.zstat, P, per_param("zstat_"), 1);
+        want(&fabber_cuda_vb_outputs::zstat, P, per_param("zstat_"), 1);
     if (rundata.GetBool("save-var"))
-        want(&out.var, P, per_param("var_"), 1);
+        want(&fabber_cuda_vb_outputs::var, P, per_param("var_"), 1);
     /* Quirk kept: Ar1cNoiseModel::NumParams() returns nPhis (noisemodel_ar.cc:362-365) although its MVN
      * block is (alpha1, alpha2, phi), so the reference's noise_means / noise_stdevs hold ONE volume for AR
      * noise - the first element of that block, i.e. alpha1 (inference_vb.cc:982-988). */
     const int noise_rows = m_ar ? 1 : m_noise_params;
     if (rundata.GetBool("save-noise-mean") && m_noise_params > 0)
-        want(&out.noise_mean, m_noise_params, std::vector<std::string>(1, "noise_means"), noise_rows);
+        want(&fabber_cuda_vb_outputs::noise_mean, m_noise_params, std::vector<std::string>(1, "noise_means"), noise_rows);
     if (rundata.GetBool("save-noise-std") && m_noise_params > 0)
-        want(&out.noise_std, m_noise_params, std::vector<std::string>(1, "noise_stdevs"), noise_rows);
+        want(&fabber_cuda_vb_outputs::noise_std, m_noise_params, std::vector<std::string>(1, "noise_stdevs"), noise_rows);
     if (rundata.GetBool("save-mvn"))
     {
         const int rows = NP_all * (NP_all + 1) / 2 + NP_all + 1; /* MVNDist::Save, dist_mvn.cc:377-433 */
-        want(&out.final_mvn, rows, std::vector<std::string>(1, "finalMVN"), rows);
+        want(&fabber_cuda_vb_outputs::final_mvn, rows, std::vector<std::string>(1, "finalMVN"), rows);
     }
     if (m_saveF && m_needF)
-        want(&out.free_energy, 1, std::vector<std::string>(1, "freeEnergy"), 1);
+        want(&fabber_cuda_vb_outputs::free_energy, 1, std::vector<std::string>(1, "freeEnergy"), 1);
+    int f_history_rows = 0;
     if (m_saveFsHistory && m_fhist_len > 0 && m_needF)
     {
         /* one row per pass plus the final value pushed after the loop (inference_vb.cc:553-554); voxels
          * that stopped early repeat their last value (:1038-1045) */
         int max_its = 0;
-        check(fabber_cuda_max_int((const int *)m_d_its.p, (int)N, &max_its, nullptr), "free energy history");
-        out.f_history_rows = std::min(max_its + 1, m_fhist_len);
-        want(&out.f_history, out.f_history_rows, std::vector<std::string>(1, "freeEnergyHistory"), out.f_history_rows);
+        for (size_t g = 0; g < m_ctx.size(); g++)
+        {
+            DeviceScope scope(m_ctx[g].device);
+            int m = 0;
+            check(fabber_cuda_max_int((const int *)m_ctx[g].its.p, (int)(m_ctx[g].v1 - m_ctx[g].v0), &m, nullptr),
+                "free energy history");
+            max_its = std::max(max_its, m);
+        }
+        f_history_rows = std::min(max_its + 1, m_fhist_len);
+        want(&fabber_cuda_vb_outputs::f_history, f_history_rows, std::vector<std::string>(1, "freeEnergyHistory"),
+            f_history_rows);
     }
     if (rundata.GetBool("save-model-fit"))
-        want(&out.model_fit, T, std::vector<std::string>(1, "modelfit"), T);
-    if (rundata.GetBool("save-residuals"))
+        want(&fabber_cuda_vb_outputs::model_fit, T, std::vector<std::string>(1, "modelfit"), T);
+    const bool residuals = rundata.GetBool("save-residuals");
+    if (residuals)
+        want(&fabber_cuda_vb_outputs::residuals, T, std::vector<std::string>(1, "residuals"), T);
+    /* host side of every output, created before any device starts filling its columns */
+    for (size_t i = 0; i < wanted.size(); i++)
+        for (size_t k = 0; k < wanted[i].keys.size(); k++)
+            rundata.NewVoxelData(wanted[i].keys[k], wanted[i].rows_per_key);
+
+    struct Pending
     {
-        VoxelData &data = rundata.MutableMainVoxelData();
-        if (!data.dev)
-        {
-            data.dev = (float *)cached_device_alloc(data.bytes());
-            check(fabber_cuda_memcpy_h2d(data.dev, data.f, data.bytes(), nullptr), "copying data to the GPU");
-        }
-        out.data = data.dev;
-        want(&out.residuals, T, std::vector<std::string>(1, "residuals"), T);
-    }
+        int device;
+        void *dev;
+        size_t bytes;
+    };
+    std::vector<Pending> pending;
     int rc = FABBER_CUDA_OK;
-    if (!pending.empty())
-        rc = fabber_cuda_vb_save_results(&m_prob, &buf, &out, nullptr);
-    for (size_t i = 0; i < pending.size() && rc == FABBER_CUDA_OK; i++)
+    for (size_t g = 0; g < m_ctx.size() && rc == FABBER_CUDA_OK && !wanted.empty(); g++)
     {
-        const Pending &p = pending[i];
-        for (size_t k = 0; k < p.keys.size(); k++)
+        DevCtx &c = m_ctx[g];
+        DeviceScope scope(c.device);
+        const size_t n = c.v1 - c.v0;
+        fabber_cuda_vb_problem prob = m_prob;
+        prob.n_voxels = (int)n;
+        fabber_cuda_vb_buffers buf;
+        memset(&buf, 0, sizeof(buf));
+        buf.mean = (double *)c.mean.p;
+        buf.cov = (double *)c.cov.p;
+        buf.noise = (double *)c.noise.p;
+        buf.free_energy = m_needF ? (double *)c.F.p : nullptr;
+        buf.iterations = (int *)c.its.p;
+        buf.f_history = m_fhist_len > 0 ? (double *)c.hist.p : nullptr;
+        fabber_cuda_vb_outputs out;
+        memset(&out, 0, sizeof(out));
+        out.f_history_rows = f_history_rows;
+        if (residuals)
+            out.data = c.data;
+        std::vector<void *> dev_of(wanted.size());
+        for (size_t i = 0; i < wanted.size(); i++)
         {
-            VoxelData &vd = rundata.NewVoxelData(p.keys[k], p.rows_per_key);
-            rc = fabber_cuda_memcpy_d2h(vd.f, (const float *)p.dev + k * (size_t)p.rows_per_key * N, vd.bytes(), nullptr);
-            if (rc != FABBER_CUDA_OK)
-                break;
+            Pending p;
+            p.device = c.device;
+            p.bytes = (size_t)wanted[i].rows * n * sizeof(float);
+            p.dev = cached_device_alloc(p.bytes);
+            pending.push_back(p);
+            out.*(wanted[i].slot) = (float *)p.dev;
+            dev_of[i] = p.dev;
         }
+        rc = fabber_cuda_vb_save_results(&prob, &buf, &out, nullptr);
+        for (size_t i = 0; i < wanted.size() && rc == FABBER_CUDA_OK; i++)
+            for (size_t k = 0; k < wanted[i].keys.size() && rc == FABBER_CUDA_OK; k++)
+            {
+                VoxelData &vd = rundata.MutableVoxelData(wanted[i].keys[k]);
+                rc = fabber_cuda_memcpy2d_d2h(vd.f + c.v0, N * sizeof(float),
+                    (const float *)dev_of[i] + k * (size_t)wanted[i].rows_per_key * n, n * sizeof(float), n * sizeof(float),
+                    (size_t)wanted[i].rows_per_key, nullptr);
+            }
     }
-    const int rc_sync = fabber_cuda_stream_sync(nullptr);
+    int rc_sync = FABBER_CUDA_OK;
+    for (size_t g = 0; g < m_ctx.size(); g++)
+    {
+        DeviceScope scope(m_ctx[g].device);
+        const int r = fabber_cuda_stream_sync(nullptr);
+        if (r != FABBER_CUDA_OK)
+            rc_sync = r;
+    }
     for (size_t i = 0; i < pending.size(); i++)
         cached_device_free(pending[i].dev, pending[i].bytes);
     ReleaseDevice();
     check(rc, "saving results");
     check(rc_sync, "saving results");
     /* file-based front ends write each output now (rundata_newimage.cc:140-183); a no-op for the array one */
-    for (size_t i = 0; i < pending.size(); i++)
-        for (size_t k = 0; k < pending[i].keys.size(); k++)
-            rundata.SaveVoxelData(pending[i].keys[k], pending[i].keys[k] == "finalMVN" ? VDT_MVN : VDT_SCALAR);
+    for (size_t i = 0; i < wanted.size(); i++)
+        for (size_t k = 0; k < wanted[i].keys.size(); k++)
+            rundata.SaveVoxelData(wanted[i].keys[k], wanted[i].keys[k] == "finalMVN" ? VDT_MVN : VDT_SCALAR);
     rundata.Log() << "Vb::timing: SaveResults " << sw.lap_ms() << " ms" << std::endl;
     rundata.Log() << "Vb::Done writing results." << std::endl;
 }

@@ -13,9 +13,12 @@
 
 #include <cerrno>
 #include <fstream>
+#include <condition_variable>
+#include <deque>
 #include <map>
 #include <mutex>
 #include <thread>
+#include <unordered_map>
 
 #include <sched.h>
 #include <sys/stat.h>
@@ -31,8 +34,10 @@ const char *fabber_b200_version() { return "b200-r1 (VB path of fabber_core on s
 
 size_t host_threads()
 {
-    /* the CPUs this process may run on (what `nproc` reports), not every CPU of the machine; FABBER_B200_HOST_THREADS
-     * overrides (e.g. several ranks sharing one host) */
+    /* the CPUs this process may run on (what `nproc` reports), not every CPU of the machine, divided by the
+     * number of processes a one-process-per-GPU launcher started on this host (LOCAL_WORLD_SIZE: eight ranks
+     * x 32 staging threads on 32 cores was measured to triple every rank's copy times);
+     * FABBER_B200_HOST_THREADS overrides */
     if (const char *e = getenv("FABBER_B200_HOST_THREADS"))
         if (atol(e) > 0)
             return (size_t)std::min<long>(atol(e), 256);
@@ -43,9 +48,103 @@ size_t host_threads()
         threads = threads ? std::min<size_t>(threads, (size_t)CPU_COUNT(&set)) : (size_t)CPU_COUNT(&set);
     if (threads == 0)
         threads = 4;
-    if (threads > 32)
-        threads = 32;
+    if (const char *lw = getenv("LOCAL_WORLD_SIZE"))
+        if (atol(lw) > 1 && !getenv("FABBER_B200_DEVICES"))
+            threads = std::max<size_t>(2, threads / (size_t)atol(lw));
+    if (threads > 64)
+        threads = 64;
     return threads;
+}
+
+/* ---- worker pool ------------------------------------------------------------------------------------
+ * Threads are created on first use and parked on a condition variable between jobs (a std::thread per call
+ * per worker cost ~50 us each, 32 of them per set_data / get_data). */
+struct PoolJob
+{
+    std::function<void()> fn;
+    std::atomic<size_t> remaining;
+    std::mutex mu;
+    std::condition_variable done;
+};
+namespace
+{
+struct HostPool
+{
+    std::mutex mu;
+    std::condition_variable wake;
+    std::deque<PoolJob *> queue; /* one entry per worker slot still to be claimed */
+    std::vector<std::thread> threads;
+    bool stop = false;
+    void grow(size_t n)
+    {
+        while (threads.size() < n)
+            threads.emplace_back([this]() { loop(); });
+    }
+    void loop()
+    {
+        for (;;)
+        {
+            PoolJob *job = nullptr;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                wake.wait(lock, [this]() { return stop || !queue.empty(); });
+                if (stop && queue.empty())
+                    return;
+                job = queue.front();
+                queue.pop_front();
+            }
+            job->fn();
+            if (job->remaining.fetch_sub(1, std::memory_order_acq_rel) == 1)
+            {
+                std::lock_guard<std::mutex> lock(job->mu);
+                job->done.notify_all();
+            }
+        }
+    }
+    ~HostPool()
+    {
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            stop = true;
+        }
+        wake.notify_all();
+        for (size_t i = 0; i < threads.size(); i++)
+            threads[i].join();
+    }
+};
+HostPool &host_pool()
+{
+    static HostPool *pool = new HostPool(); /* leaked on purpose: workers may outlive static destruction order */
+    return *pool;
+}
+} // namespace
+
+PoolJob *pool_launch(size_t n_workers, const std::function<void()> &fn)
+{
+    PoolJob *job = new PoolJob();
+    job->fn = fn;
+    job->remaining.store(n_workers, std::memory_order_relaxed);
+    if (n_workers == 0)
+        return job;
+    HostPool &pool = host_pool();
+    {
+        std::lock_guard<std::mutex> lock(pool.mu);
+        pool.grow(std::min<size_t>(std::max(n_workers, pool.threads.size()), 256));
+        for (size_t i = 0; i < n_workers; i++)
+            pool.queue.push_back(job);
+    }
+    pool.wake.notify_all();
+    return job;
+}
+void pool_wait(PoolJob *job)
+{
+    if (!job)
+        return;
+    {
+        std::unique_lock<std::mutex> lock(job->mu);
+        job->done.wait(lock, [job]() { return job->remaining.load(std::memory_order_acquire) == 0; });
+    }
+    delete job;
 }
 
 void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_t min_chunk)
@@ -58,17 +157,14 @@ void parallel_for(size_t n, const std::function<void(size_t, size_t)> &fn, size_
         fn(0, n);
         return;
     }
-    std::vector<std::thread> pool;
     const size_t per = (n + threads - 1) / threads;
-    for (size_t t = 0; t < threads; t++)
-    {
+    std::atomic<size_t> next(0);
+    pool_wait(pool_launch(threads, [&]() {
+        const size_t t = next.fetch_add(1, std::memory_order_relaxed);
         const size_t b = t * per, e = std::min(n, b + per);
-        if (b >= e)
-            break;
-        pool.emplace_back([&fn, b, e]() { fn(b, e); });
-    }
-    for (size_t t = 0; t < pool.size(); t++)
-        pool[t].join();
+        if (b < e)
+            fn(b, e);
+    }));
 }
 
 /* Staging copy for SetVoxelDataArray: the destination is pinned memory that only the DMA engine reads next, so
@@ -142,7 +238,12 @@ struct BlockCache
     std::multimap<size_t, void *> free_blocks;
     size_t cached_bytes = 0;
 };
-BlockCache g_pinned, g_device;
+BlockCache g_pinned;
+/* device blocks are parked per device; the owner of every live block is remembered so that a block can be
+ * handed back from any thread, whatever its current device */
+std::mutex g_device_mu;
+std::map<int, BlockCache> g_device;
+std::unordered_map<void *, int> g_device_owner;
 const size_t CACHE_LIMIT = (size_t)48 << 30; /* per kind; beyond it blocks really are freed */
 
 void *cache_get(BlockCache &c, size_t bytes)
@@ -201,52 +302,171 @@ void *cached_device_alloc(size_t bytes)
 {
     if (bytes == 0)
         bytes = 1;
-    void *p = cache_get(g_device, bytes);
+    const int dev = fabber_cuda_get_device();
+    BlockCache *cache;
+    {
+        std::lock_guard<std::mutex> lock(g_device_mu);
+        cache = &g_device[dev];
+    }
+    void *p = cache_get(*cache, bytes);
     if (!p)
         p = fabber_cuda_malloc(bytes);
     if (!p)
         throw FabberInternalError(std::string("GPU allocation failed: ") + fabber_cuda_last_error());
+    std::lock_guard<std::mutex> lock(g_device_mu);
+    g_device_owner[p] = dev;
     return p;
 }
 void cached_device_free(void *p, size_t bytes)
 {
-    if (p && !cache_put(g_device, p, bytes ? bytes : 1))
+    if (!p)
+        return;
+    BlockCache *cache;
+    int dev;
+    {
+        std::lock_guard<std::mutex> lock(g_device_mu);
+        std::unordered_map<void *, int>::iterator it = g_device_owner.find(p);
+        dev = it == g_device_owner.end() ? fabber_cuda_get_device() : it->second;
+        if (it != g_device_owner.end())
+            g_device_owner.erase(it);
+        cache = &g_device[dev];
+    }
+    if (!cache_put(*cache, p, bytes ? bytes : 1))
+    {
+        DeviceScope scope(dev);
         fabber_cuda_free(p);
+    }
+}
+
+/* ---- the GPUs of a run (see fabber_host.h) ------------------------------------------------------- */
+const std::vector<int> &run_devices()
+{
+    static const std::vector<int> devices = []() {
+        std::vector<int> d;
+        const int n = fabber_cuda_device_count();
+        if (n <= 0)
+            return d;
+        const char *env = getenv("FABBER_B200_DEVICES");
+        if (env && *env && strcmp(env, "all") != 0)
+        {
+            std::istringstream in(env);
+            std::string item;
+            while (std::getline(in, item, ','))
+            {
+                const int v = atoi(item.c_str());
+                if (!item.empty() && v >= 0 && v < n) /* a repeated ordinal gives that GPU two ranges (tests on one GPU) */
+                    d.push_back(v);
+            }
+        }
+        else if (!env && getenv("LOCAL_RANK") && getenv("LOCAL_WORLD_SIZE") && atoi(getenv("LOCAL_WORLD_SIZE")) > 1)
+            d.push_back(std::max(0, fabber_cuda_get_device())); /* one process per GPU: the launcher's choice */
+        else
+            for (int i = 0; i < n; i++)
+                d.push_back(i);
+        if (d.empty())
+            d.push_back(std::max(0, fabber_cuda_get_device()));
+        return d;
+    }();
+    return devices;
+}
+DeviceScope::DeviceScope(int device)
+    : prev(fabber_cuda_get_device())
+{
+    if (device >= 0 && device != prev)
+        fabber_cuda_set_device(device);
+    else
+        prev = -1;
+}
+DeviceScope::~DeviceScope()
+{
+    if (prev >= 0)
+        fabber_cuda_set_device(prev);
+}
+void *copy_stream_of(int device)
+{
+    static std::mutex mu;
+    static std::map<int, void *> streams;
+    std::lock_guard<std::mutex> lock(mu);
+    std::map<int, void *>::iterator it = streams.find(device);
+    if (it != streams.end())
+        return it->second;
+    DeviceScope scope(device);
+    void *s = fabber_cuda_stream_create();
+    streams[device] = s;
+    return s;
 }
 
 VoxelData::VoxelData()
     : rows(0)
     , cols(0)
     , f(nullptr)
-    , dev(nullptr)
+    , host_valid(true)
 {
-}
-/* one copy stream for the life of the process: uploads run beside whatever the default stream computes */
-static void *copy_stream()
-{
-    static void *s = fabber_cuda_stream_create();
-    return s;
 }
 
-void VoxelData::wait_uploaded()
+void VoxelData::wait_uploaded(int part)
 {
     for (size_t i = 0; i < blocks.size(); i++)
-        fabber_cuda_stream_wait_event(nullptr, blocks[i].ready);
+        if (blocks[i].part == part)
+            fabber_cuda_stream_wait_event(nullptr, blocks[i].ready);
+}
+
+void VoxelData::release_device()
+{
+    /* work queued on the devices may still read these blocks: drain it before they can be handed out again */
+    for (size_t p = 0; p < parts.size(); p++)
+    {
+        DeviceScope scope(parts[p].device);
+        fabber_cuda_stream_sync(copy_stream_of(parts[p].device));
+        fabber_cuda_stream_sync(nullptr);
+        cached_device_free(parts[p].dev, (size_t)rows * (parts[p].v1 - parts[p].v0) * sizeof(float));
+    }
+    for (size_t i = 0; i < blocks.size(); i++)
+        fabber_cuda_event_destroy(blocks[i].ready);
+    parts.clear();
+    blocks.clear();
+}
+
+void VoxelData::ensure_host()
+{
+    if (host_valid)
+        return;
+    for (size_t p = 0; p < parts.size(); p++)
+    {
+        const Part &pt = parts[p];
+        DeviceScope scope(pt.device);
+        const size_t w = pt.v1 - pt.v0;
+        fabber_cuda_stream_sync(copy_stream_of(pt.device));
+        if (fabber_cuda_memcpy2d_d2h(f + pt.v0, cols * sizeof(float), pt.dev, w * sizeof(float), w * sizeof(float),
+                (size_t)rows, nullptr)
+                != FABBER_CUDA_OK
+            || fabber_cuda_stream_sync(nullptr) != FABBER_CUDA_OK)
+            throw FabberInternalError(std::string("copying data back from the GPU: ") + fabber_cuda_last_error());
+    }
+    host_valid = true;
+}
+
+void VoxelData::upload_whole(int device)
+{
+    if (parts.size() == 1 && parts[0].device == device && parts[0].v0 == 0 && parts[0].v1 == cols)
+        return;
+    ensure_host();
+    release_device();
+    DeviceScope scope(device);
+    Part pt;
+    pt.device = device;
+    pt.v0 = 0;
+    pt.v1 = cols;
+    pt.dev = (float *)cached_device_alloc(bytes());
+    parts.push_back(pt);
+    if (fabber_cuda_memcpy_h2d(pt.dev, f, bytes(), nullptr) != FABBER_CUDA_OK)
+        throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
 }
 
 VoxelData::~VoxelData()
 {
-    /* work queued on the device may still read these blocks: drain it before they can be handed out again */
-    if (dev)
-    {
-        if (!blocks.empty())
-            fabber_cuda_stream_sync(copy_stream());
-        fabber_cuda_stream_sync(nullptr);
-    }
-    for (size_t i = 0; i < blocks.size(); i++)
-        fabber_cuda_event_destroy(blocks[i].ready);
+    release_device();
     cached_pinned_free(f, bytes());
-    cached_device_free(dev, bytes());
 }
 void VoxelData::alloc(int r, size_t c)
 {
@@ -259,6 +479,7 @@ void VoxelData::alloc(int r, size_t c)
 
 FabberRunData::FabberRunData()
     : m_have_extent(false)
+    , m_device_only_access(false)
     , m_progress(nullptr)
 {
     m_extent[0] = m_extent[1] = m_extent[2] = 0;
@@ -399,6 +620,24 @@ void FabberRunData::SetExtent(int nx, int ny, int nz, const int *mask)
     m_coords.insert(m_coords.end(), cz.begin(), cz.end());
 }
 
+/* do the options set so far describe a spatial run (method=spatialvb or a spatial prior type)? Spatial VB
+ * couples the voxels, so its series is not dealt to several devices here. A wrong guess costs one re-upload
+ * in Vb::DoCalculations, never a wrong result. */
+bool FabberRunData::LooksSpatial() const
+{
+    std::map<std::string, std::string>::const_iterator it = m_params.find("method");
+    if (it != m_params.end() && it->second == "spatialvb")
+        return true;
+    it = m_params.find("param-spatial-priors");
+    if (it != m_params.end() && it->second.find_first_of("MmPp") != std::string::npos)
+        return true;
+    for (it = m_params.begin(); it != m_params.end(); ++it)
+        if (it->first.compare(0, 10, "PSP_byname") == 0 && it->first.size() > 5
+            && it->first.compare(it->first.size() - 5, 5, "_type") == 0 && it->second.find_first_of("MmPp") != std::string::npos)
+            return true;
+    return false;
+}
+
 /* rundata_array.cc:100-133: float[t][z][y][x] -> T x Nvox */
 void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, const float *data)
 {
@@ -413,36 +652,122 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
     vd->alloc(data_size, N);
     float *dst_all = vd->f;
     const std::vector<int> &index = m_voxel_index;
-    /* The main series goes straight on to the GPU, BLOCK OF VOXELS BY BLOCK OF VOXELS: all host cores stage
-     * the columns [v0, v1) of every row into pinned memory, the block's strided host->device copy is queued
-     * on the copy stream, an event marks it - and the next block is staged while that one travels. Voxelwise
-     * VB (Vb::DoCalculations) then starts each block's kernel on its event, so the arithmetic of block k
-     * also overlaps the transfer of the blocks after it. */
+    /* The main series goes straight on to the GPUs, BLOCK OF VOXELS BY BLOCK OF VOXELS: the voxel list is cut
+     * into one contiguous range per device (voxels are independent in voxelwise VB), each range into blocks;
+     * all host cores stage the columns [v0, v1) of every row of a block into pinned memory, the block's strided
+     * host->device copy is queued on its device's copy stream, an event marks it - and the next block (for the
+     * next device: the blocks are dealt round-robin so every PCIe link is busy) is staged while that one
+     * travels. Voxelwise VB (Vb::DoCalculations) then starts each block's kernel on its event, so the
+     * arithmetic of block k also overlaps the transfer of the blocks after it. */
     /* ("data" itself, or the file the data option names when a file-based front end loads it) */
     const bool is_main = key == "data" || (m_params.count("data") && m_params["data"] == key);
     const bool upload = is_main && N > 0 && fabber_cuda_device_count() > 0;
+    const size_t T = (size_t)data_size;
+    std::vector<int> devs(1, 0);
     if (upload)
-        vd->dev = (float *)cached_device_alloc(vd->bytes());
-    /* ~96 MB per block, at most 64 blocks, at least 64k voxels each (a block is also one kernel launch) */
-    const size_t total = (size_t)data_size * N * sizeof(float);
+    {
+        devs = run_devices();
+        const char *mv = getenv("FABBER_B200_MIN_VOXELS_PER_DEVICE");
+        const size_t min_per = (mv && atol(mv) > 0) ? (size_t)atol(mv) : 65536;
+        size_t g = std::min(devs.size(), std::max<size_t>(1, N / min_per));
+        if (LooksSpatial())
+            g = 1;
+        devs.resize(g);
+    }
+    const size_t G = devs.size();
+    const size_t per_part = ((N + G - 1) / G + 127) / 128 * 128; /* whole CTAs of 128 voxels */
+    /* ~96 MB per block, at most 64 blocks per device, at least 64k voxels each (a block is also one launch) */
     const char *block_env = getenv("FABBER_B200_UPLOAD_BLOCK_MB"); /* tuning / test knob; 32-128 MB measure alike */
     const size_t block_mb = (block_env && atol(block_env) > 0) ? (size_t)atol(block_env) : 96;
-    size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, total / (block_mb << 20)));
-    n_blocks = std::max<size_t>(1, std::min(n_blocks, N / 65536));
+    size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, T * per_part * sizeof(float) / (block_mb << 20)));
+    n_blocks = std::max<size_t>(1, std::min(n_blocks, per_part / 65536));
     if (!upload)
         n_blocks = 1;
-    const size_t per_block = ((N + n_blocks - 1) / n_blocks + 127) / 128 * 128; /* whole CTAs of 128 voxels */
-    const size_t T = (size_t)data_size;
+    const size_t per_block = ((per_part + n_blocks - 1) / n_blocks + 127) / 128 * 128;
+    std::vector<VoxelData::Block> blocks; /* round-robin over the devices */
+    if (upload)
+        for (size_t g = 0; g < G; g++)
+        {
+            VoxelData::Part pt;
+            pt.device = devs[g];
+            pt.v0 = std::min(N, g * per_part);
+            pt.v1 = std::min(N, pt.v0 + per_part);
+            pt.dev = nullptr;
+            if (pt.v1 > pt.v0)
+                vd->parts.push_back(pt);
+        }
+    for (size_t bi = 0; bi < n_blocks; bi++)
+        for (size_t g = 0; g < (upload ? vd->parts.size() : 1); g++)
+        {
+            const size_t p0 = upload ? vd->parts[g].v0 : 0, p1 = upload ? vd->parts[g].v1 : N;
+            VoxelData::Block blk;
+            blk.v0 = p0 + bi * per_block;
+            blk.v1 = std::min(p1, blk.v0 + per_block);
+            blk.ready = nullptr;
+            blk.part = (int)g;
+            if (blk.v0 < blk.v1)
+                blocks.push_back(blk);
+        }
+    for (size_t g = 0; g < vd->parts.size(); g++)
+    {
+        DeviceScope scope(vd->parts[g].device);
+        vd->parts[g].dev = (float *)cached_device_alloc(T * (vd->parts[g].v1 - vd->parts[g].v0) * sizeof(float));
+    }
+    auto queue_block = [&](VoxelData::Block &blk, const float *src, size_t src_pitch_elems) {
+        const VoxelData::Part &pt = vd->parts[blk.part];
+        DeviceScope scope(pt.device);
+        void *cs = copy_stream_of(pt.device);
+        const size_t w = blk.v1 - blk.v0, pw = pt.v1 - pt.v0;
+        blk.ready = fabber_cuda_event_create();
+        int rc = blk.ready ? fabber_cuda_memcpy2d_h2d(pt.dev + (blk.v0 - pt.v0), pw * sizeof(float), src + blk.v0,
+                                 src_pitch_elems * sizeof(float), w * sizeof(float), T, cs)
+                           : FABBER_CUDA_ERR_CUDA;
+        if (rc == FABBER_CUDA_OK)
+            rc = fabber_cuda_event_record(blk.ready, cs);
+        vd->blocks.push_back(blk);
+        return rc;
+    };
+
+    /* The caller's buffer is page-locked (cudaMallocHost / cudaHostRegister) and in voxel-list order (full
+     * mask): the DMA engines read it in place, no staging copy - with several GPUs their PCIe links together
+     * move data faster than the host cores can copy it. The call still returns only when every copy has
+     * landed (the caller may reuse its buffer afterwards, as with the reference), unless the caller has
+     * promised to leave it alone until fabber_dorun returns (FABBER_B200_ASYNC_SET_DATA=1). With ONE device
+     * the staged path is kept: its copy (measured 76 GB/s) outruns one PCIe link and lets set_data return
+     * while the tail of the upload is still in flight. */
+    const char *direct_env = getenv("FABBER_B200_DIRECT_UPLOAD"); /* 0 = never, 1 = whenever possible */
+    bool direct = upload && N == n_grid && fabber_cuda_host_is_pinned(data) == 1 && vd->parts.size() >= 2;
+    if (direct_env && direct_env[0] == '0')
+        direct = false;
+    if (direct_env && direct_env[0] == '1')
+        direct = upload && N == n_grid && fabber_cuda_host_is_pinned(data) == 1;
+    if (direct)
+    {
+        for (size_t b = 0; b < blocks.size(); b++)
+            if (queue_block(blocks[b], data, N) != FABBER_CUDA_OK)
+                throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+        vd->host_valid = false;
+        const char *async_env = getenv("FABBER_B200_ASYNC_SET_DATA");
+        if (!(async_env && async_env[0] == '1'))
+            for (size_t b = 0; b < vd->blocks.size(); b++)
+                if (fabber_cuda_event_sync(vd->blocks[b].ready) != FABBER_CUDA_OK)
+                    throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+        m_voxel_data[key] = std::move(vd);
+        return;
+    }
+
     /* One pool of workers for the whole volume, no barrier between blocks: work item = (block, row, piece of
      * the block's columns) - contiguous runs in both source and destination - handed out block-major from one
      * counter; a per-block count of unfinished items tells the calling thread when a block is staged, and it
      * queues that block's copy while the workers are already on the next one. */
-    const size_t real_blocks = per_block ? (N + per_block - 1) / per_block : 0; /* empty mask: nothing to stage */
     const size_t piece = (size_t)1 << 18, pieces = (per_block + piece - 1) / piece, per_items = T * pieces;
+    const size_t real_blocks = blocks.size(); /* empty mask: nothing to stage */
     std::vector<std::atomic<size_t>> unfinished(real_blocks);
     for (size_t b = 0; b < real_blocks; b++)
         unfinished[b].store(per_items, std::memory_order_relaxed);
     std::atomic<size_t> next(0);
+    std::mutex staged_mu;
+    std::condition_variable staged_cv;
     const size_t total_items = real_blocks * per_items;
     auto worker = [&]() {
         for (;;)
@@ -451,7 +776,7 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
             if (i >= total_items)
                 return;
             const size_t b = i / per_items, r = i - b * per_items, t = r / pieces;
-            const size_t v0 = b * per_block, v1 = std::min(N, v0 + per_block);
+            const size_t v0 = blocks[b].v0, v1 = blocks[b].v1;
             const size_t c0 = v0 + (r - t * pieces) * piece, c1 = std::min(v1, c0 + piece);
             if (c0 < c1)
             {
@@ -461,53 +786,40 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
                     for (size_t v = c0; v < c1; v++)
                         dst_all[t * N + v] = data[t * n_grid + index[v]];
             }
-            unfinished[b].fetch_sub(1, std::memory_order_release);
-        }
-    };
-    std::vector<std::thread> pool;
-    {
-        size_t threads = host_threads();
-        if (total_items < threads)
-            threads = total_items;
-        if ((size_t)data_size * N < ((size_t)1 << 16))
-            threads = 0; /* tiny: the calling thread does it */
-        for (size_t t = 0; t < threads; t++)
-            pool.emplace_back(worker);
-        if (threads == 0)
-            worker();
-    }
-    struct Join
-    {
-        std::vector<std::thread> &p;
-        ~Join()
-        {
-            for (size_t t = 0; t < p.size(); t++)
-                p[t].join();
-        }
-    } join = { pool };
-    for (size_t b = 0; b < real_blocks; b++)
-    {
-        const size_t v0 = b * per_block, v1 = std::min(N, v0 + per_block), w = v1 - v0;
-        while (unfinished[b].load(std::memory_order_acquire) != 0)
-            std::this_thread::yield();
-        if (upload)
-        {
-            VoxelData::Block blk;
-            blk.v0 = v0;
-            blk.v1 = v1;
-            blk.ready = fabber_cuda_event_create();
-            int rc = blk.ready ? fabber_cuda_memcpy2d_h2d(vd->dev + v0, N * sizeof(float), dst_all + v0, N * sizeof(float),
-                                     w * sizeof(float), T, copy_stream())
-                               : FABBER_CUDA_ERR_CUDA;
-            if (rc == FABBER_CUDA_OK)
-                rc = fabber_cuda_event_record(blk.ready, copy_stream());
-            vd->blocks.push_back(blk);
-            if (rc != FABBER_CUDA_OK)
+            if (unfinished[b].fetch_sub(1, std::memory_order_acq_rel) == 1)
             {
-                next.store(total_items, std::memory_order_relaxed); /* stop the workers before unwinding */
-                throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+                std::lock_guard<std::mutex> lock(staged_mu);
+                staged_cv.notify_all();
             }
         }
+    };
+    size_t threads = host_threads();
+    if (total_items < threads)
+        threads = total_items;
+    if ((size_t)data_size * N < ((size_t)1 << 16))
+        threads = 0; /* tiny: the calling thread does it */
+    PoolJob *job = pool_launch(threads, worker);
+    if (threads == 0)
+        worker();
+    struct Join
+    {
+        PoolJob *job;
+        std::atomic<size_t> &next;
+        size_t total;
+        ~Join()
+        {
+            next.store(total, std::memory_order_relaxed); /* on an exception: stop the workers before unwinding */
+            pool_wait(job);
+        }
+    } join = { job, next, total_items };
+    for (size_t b = 0; b < real_blocks; b++)
+    {
+        {
+            std::unique_lock<std::mutex> lock(staged_mu);
+            staged_cv.wait(lock, [&]() { return unfinished[b].load(std::memory_order_acquire) == 0; });
+        }
+        if (upload && queue_block(blocks[b], dst_all, N) != FABBER_CUDA_OK)
+            throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
     }
     m_voxel_data[key] = std::move(vd);
 }
@@ -530,6 +842,8 @@ const VoxelData &FabberRunData::GetVoxelData(const std::string &key_in)
         m_used_params.insert(key);
         key = m_params[key];
     }
+    if (!m_device_only_access)
+        m_voxel_data[key]->ensure_host(); /* every reader but Vb's device path wants the host copy */
     return *m_voxel_data[key];
 }
 bool FabberRunData::LoadVoxelData(const std::string &) { return false; }
@@ -556,7 +870,21 @@ const VoxelData &FabberRunData::GetMainVoxelData()
         return GetMainVoxelDataMultiple();
     }
 }
-VoxelData &FabberRunData::MutableMainVoxelData() { return const_cast<VoxelData &>(GetMainVoxelData()); }
+VoxelData &FabberRunData::MutableMainVoxelData()
+{
+    /* Vb works on the device copy: do not pull a directly-uploaded series back to the host for it */
+    struct Flag
+    {
+        bool &f;
+        explicit Flag(bool &b)
+            : f(b)
+        {
+            f = true;
+        }
+        ~Flag() { f = false; }
+    } flag(m_device_only_access);
+    return const_cast<VoxelData &>(GetMainVoxelData());
+}
 
 /* rundata.cc:821-905 */
 const VoxelData &FabberRunData::GetMainVoxelDataMultiple()

@@ -167,6 +167,7 @@ typedef struct fabber_cuda_vb_buffers
 /* --- device management helpers (so a C/C++ host needs no CUDA headers) -------------------- */
 int fabber_cuda_device_count(void);
 int fabber_cuda_set_device(int dev);
+int fabber_cuda_get_device(void); /* current device of the calling thread, < 0 on error */
 const char *fabber_cuda_last_error(void);
 void *fabber_cuda_malloc(unsigned long long bytes);
 void fabber_cuda_free(void *dptr);
@@ -210,6 +211,12 @@ int fabber_cuda_event_record(void *event, void *stream);
 int fabber_cuda_stream_wait_event(void *stream, void *event);
 int fabber_cuda_memcpy2d_h2d(void *dst, unsigned long long dst_pitch, const void *src, unsigned long long src_pitch,
     unsigned long long width_bytes, unsigned long long rows, void *stream);
+int fabber_cuda_memcpy2d_d2h(void *dst, unsigned long long dst_pitch, const void *src, unsigned long long src_pitch,
+    unsigned long long width_bytes, unsigned long long rows, void *stream);
+int fabber_cuda_event_sync(void *event);
+/* 1 if `host_ptr` is page-locked memory known to the CUDA runtime (cudaMallocHost / cudaHostRegister: a
+ * DMA engine can read it in place), 0 if it is ordinary pageable memory */
+int fabber_cuda_host_is_pinned(const void *host_ptr);
 
 /* Spatial VB (iteration-major; replaces Vb::DoCalculationsSpatial, inference_vb.cc:578-767,
  * SpatialPrior::CalculateaK / ApplyToMVN priors.cc:221-488, Vb::CalcNeighbours :830-964).
