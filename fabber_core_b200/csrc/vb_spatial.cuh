@@ -569,6 +569,10 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_noise_kernel(cons
     if (v >= a.N)
         return;
     const size_t N = (size_t)a.N;
+    /* the reference counts iterations once for the whole volume (m_ctx->it, inference_vb.cc:724): every
+     * voxel, ignored ones included, reports the global count */
+    if (a.iterations)
+        a.iterations[v] = s.it + 1;
     if (a.status[v] != 0)
         return;
     const typename Model::Ctx mc = Model::make_ctx(a, smem);
@@ -639,8 +643,6 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_noise_kernel(cons
             s.stats[i * N + v] = S[0].A[i];
         s.stats[(NT + P) * N + v] = S[0].rr;
     }
-    if (a.iterations)
-        a.iterations[v] = s.it + 1;
     if (a.need_f)
     {
         double m0[P], L0[P], nbv[1] = { nb }, ncv[1] = { nc };

@@ -213,6 +213,7 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
             if nbad:
                 rc = abi.ERR_BAD_VOXEL
         out["rc"] = rc
+        out["n_times"] = int(data.shape[0])
         return out
     finally:
         r.close()

@@ -21,9 +21,11 @@ def build():
 
 def lib(variant=""):
     """variant "" = the oracle proper; "fma" / "ulp" = noise-floor probes (same source with FMA
-    contraction / with the model's exp() perturbed by <= 1 ULP, see oracle/Makefile)."""
+    contraction / with the model's exp() perturbed by <= 1 ULP, see oracle/Makefile); "ld" = the same
+    source in 80-bit extended precision, the higher-precision "truth" of tests/parity.py."""
     if variant not in _LIBS:
-        name = {"fma": "libvb_oracle_fma.so", "ulp": "libvb_oracle_ulp.so"}.get(variant, "libvb_oracle.so")
+        name = {"fma": "libvb_oracle_fma.so", "ulp": "libvb_oracle_ulp.so",
+                "ld": "libvb_oracle_ld.so"}.get(variant, "libvb_oracle.so")
         path = os.path.join(_HERE, "_build", name)
         if not os.path.exists(path):
             build()
@@ -91,6 +93,7 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
     fn.restype = C.c_int
     rc = fn(C.byref(prob), C.byref(buf))
     out["rc"] = rc
+    out["n_times"] = T
     return out
 
 

@@ -44,7 +44,17 @@
 
 namespace
 {
-typedef std::vector<double> Vec;
+/* Every quantity of the algorithm is a `real`: double in the oracle proper (NEWMAT::Real is double in the
+ * reference). -DORACLE_LONG_DOUBLE builds the SAME source in 80-bit extended precision (64-bit mantissa: rounding
+ * noise 2048 x smaller) - the "truth" build of tests/parity.py: where the reference's own FP64 arithmetic is the
+ * limit (ill-conditioned normal equations), the CUDA path is required to be as close to that truth as the
+ * reference's arithmetic is. Inputs, outputs and the C interface stay double / float. */
+#ifdef ORACLE_LONG_DOUBLE
+typedef long double real;
+#else
+typedef double real;
+#endif
+typedef std::vector<real> Vec;
 
 struct InternalError : std::runtime_error
 {
@@ -75,14 +85,14 @@ struct Mat
         , c(0)
     {
     }
-    Mat(int r_, int c_, double v = 0.0)
+    Mat(int r_, int c_, real v = 0.0)
         : r(r_)
         , c(c_)
         , a((size_t)r_ * c_, v)
     {
     }
-    double &operator()(int i, int j) { return a[(size_t)i * c + j]; }
-    double operator()(int i, int j) const { return a[(size_t)i * c + j]; }
+    real &operator()(int i, int j) { return a[(size_t)i * c + j]; }
+    real operator()(int i, int j) const { return a[(size_t)i * c + j]; }
     static Mat identity(int n)
     {
         Mat m(n, n);
@@ -98,7 +108,7 @@ Mat mul(const Mat &A, const Mat &B)
     for (int i = 0; i < A.r; i++)
         for (int j = 0; j < B.c; j++)
         {
-            double s = 0;
+            real s = 0;
             for (int k = 0; k < A.c; k++)
                 s += A(i, k) * B(k, j);
             C(i, j) = s;
@@ -125,16 +135,16 @@ Vec mulv(const Mat &A, const Vec &x)
     Vec y(A.r);
     for (int i = 0; i < A.r; i++)
     {
-        double s = 0;
+        real s = 0;
         for (int k = 0; k < A.c; k++)
             s += A(i, k) * x[k];
         y[i] = s;
     }
     return y;
 }
-double trace(const Mat &A)
+real trace(const Mat &A)
 {
-    double s = 0;
+    real s = 0;
     for (int i = 0; i < A.r; i++)
         s += A(i, i);
     return s;
@@ -171,7 +181,7 @@ struct LU
         for (int k = 0; k < n; k++)
         {
             int p = k;
-            double best = std::fabs(lu(k, k));
+            real best = std::fabs(lu(k, k));
             for (int i = k + 1; i < n; i++)
                 if (std::fabs(lu(i, k)) > best)
                 {
@@ -193,7 +203,7 @@ struct LU
             for (int i = k + 1; i < n; i++)
             {
                 lu(i, k) /= lu(k, k);
-                double f = lu(i, k);
+                real f = lu(i, k);
                 for (int j = k + 1; j < n; j++)
                     lu(i, j) -= f * lu(k, j);
             }
@@ -219,14 +229,14 @@ Mat inverse(const Mat &A)
                 std::swap(b[k], b[f.piv[k]]);
         for (int i = 1; i < n; i++)
         {
-            double s = b[i];
+            real s = b[i];
             for (int j = 0; j < i; j++)
                 s -= f.lu(i, j) * b[j];
             b[i] = s;
         }
         for (int i = n - 1; i >= 0; i--)
         {
-            double s = b[i];
+            real s = b[i];
             for (int j = i + 1; j < n; j++)
                 s -= f.lu(i, j) * b[j];
             b[i] = s / f.lu(i, i);
@@ -243,7 +253,7 @@ Mat inverse(const Mat &A)
 
 struct LogAndSign
 {
-    double logval;
+    real logval;
     int sign;
 };
 LogAndSign log_determinant(const Mat &A)
@@ -254,7 +264,7 @@ LogAndSign log_determinant(const Mat &A)
     r.sign = f.sign;
     for (int i = 0; i < A.r; i++)
     {
-        double d = f.lu(i, i);
+        real d = f.lu(i, i);
         if (d == 0.0 || f.singular)
         {
             r.sign = 0;
@@ -272,11 +282,11 @@ LogAndSign log_determinant(const Mat &A)
 // Special functions
 // ---------------------------------------------------------------------------------------------
 // tools.cc:87-98 - 6-term Lanczos, NOT lgamma
-double gammaln(double x)
+real gammaln(real x)
 {
-    static const double series[7] = { 2.5066282746310005, 76.18009172947146, -86.50532032941677,
+    static const real series[7] = { 2.5066282746310005, 76.18009172947146, -86.50532032941677,
         24.01409824083091, -1.231739572450155, 0.1208650973866179e-2, -0.5395239384953e-5 };
-    double total = 1.000000000190015;
+    real total = 1.000000000190015;
     for (int i = 2; i <= 7; i++)
         total += series[i - 1] / (x + i - 1);
     return std::log(series[0] * total / x) + (x + 0.5) * std::log(x + 5.5) - x - 5.5;
@@ -307,7 +317,7 @@ double digamma_fsl(double xin)
 // ---------------------------------------------------------------------------------------------
 // Transforms (transforms.h:114-242, transforms.cc:17-25)
 // ---------------------------------------------------------------------------------------------
-double t_to_model(char code, double v)
+real t_to_model(char code, real v)
 {
     switch (code)
     {
@@ -323,7 +333,7 @@ double t_to_model(char code, double v)
         return v;
     }
 }
-double t_to_fabber(char code, double v)
+real t_to_fabber(char code, real v)
 {
     switch (code)
     {
@@ -337,7 +347,7 @@ double t_to_fabber(char code, double v)
         return v;
     }
 }
-double t_to_fabber_var(char code, double v)
+real t_to_fabber_var(char code, real v)
 {
     switch (code)
     {
@@ -432,11 +442,11 @@ struct ModelCtx
 
 // Noise-floor probe only (oracle/Makefile target libvb_oracle_ulp.so, -DORACLE_EXP_ULP_PROBE): model
 // the forward model being linked against a different, equally valid libm whose exp() is accurate to
-// <= 1 ULP instead of glibc's: half of the results are moved to an adjacent double, chosen by a hash of
+// <= 1 ULP instead of glibc's: half of the results are moved to an adjacent real, chosen by a hash of
 // the bits. Never defined for the oracle proper.
-inline double model_exp(double x)
+inline real model_exp(real x)
 {
-    double e = std::exp(x);
+    real e = std::exp(x);
 #ifdef ORACLE_EXP_ULP_PROBE
     unsigned long long u;
     std::memcpy(&u, &e, sizeof(u));
@@ -465,7 +475,7 @@ void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
         // fwdmodel_linear.cc:95  result = J*(params - centre) + offset, centre = offset = 0
         for (int t = 0; t < T; t++)
         {
-            double s = 0;
+            real s = 0;
             for (int j = 0; j < mc.P; j++)
                 s += m.design[(size_t)t * mc.P + j] * (p[j] - 0.0);
             result[t] = s + 0.0;
@@ -476,11 +486,11 @@ void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
         // fwdmodel_poly.cc:68-79 - note the *int* power accumulator (wraps for large i^n)
         for (int i = 1; i <= T; i++)
         {
-            double res = 0;
+            real res = 0;
             unsigned int pw = 1; // unsigned arithmetic == two's complement wrap of the reference's int
             for (int n = 0; n <= m.poly_degree; n++)
             {
-                res += p[n] * (double)(int)pw;
+                res += p[n] * (real)(int)pw;
                 pw *= (unsigned int)i;
             }
             result[i - 1] = res;
@@ -491,12 +501,12 @@ void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
         // examples/fwdmodel_exp.cc:71-81
         for (int k = 0; k < m.exp_num; k++)
         {
-            double amp = p[2 * k];
-            double r = p[2 * k + 1];
+            real amp = p[2 * k];
+            real r = p[2 * k + 1];
             for (int i = 0; i < T; i++)
             {
-                double t = double(i) * m.exp_dt;
-                double val = amp * model_exp(-r * t);
+                real t = real(i) * m.exp_dt;
+                real val = amp * model_exp(-r * t);
                 result[i] += val;
             }
         }
@@ -507,7 +517,7 @@ void evaluate_model(const ModelCtx &mc, const Vec &p, Vec &result)
         // here so that the plug-in path has an independent checker.  g = a sin(b (t - c)) + d, t = i dt
         for (int i = 0; i < T; i++)
         {
-            double t = double(i) * m.consts[0];
+            real t = real(i) * m.consts[0];
             result[i] = p[0] * std::sin(p[1] * (t - p[2])) + p[3];
         }
     }
@@ -540,7 +550,7 @@ struct LinModel
         Vec c2, c3, o2, o3;
         for (int i = 0; i < mc.P; i++)
         {
-            double delta = centre[i] * 1e-5;
+            real delta = centre[i] * 1e-5;
             if (delta < 0)
                 delta = -delta;
             if (delta < 1e-10)
@@ -551,7 +561,7 @@ struct LinModel
             c3[i] -= delta;
             evaluate_fabber(mc, c2, o2);
             evaluate_fabber(mc, c3, o3);
-            double den = c2[i] - c3[i];
+            real den = c2[i] - c3[i];
             for (int t = 0; t < mc.T; t++)
                 J(t, i) = (o2[t] - o3[t]) / den;
         }
@@ -566,7 +576,7 @@ struct LinModel
 // ---------------------------------------------------------------------------------------------
 struct Gamma
 {
-    double b, c;
+    real b, c;
 };
 
 struct NoiseParams
@@ -624,7 +634,7 @@ struct NoiseModel
 
     // ------------------------------ white ------------------------------------------------
     // (Sigma * J' * Q * J).Trace()  evaluated left to right as NEWMAT does
-    static double trace_SJtQJ(const Mat &Sigma, const Mat &J, const Vec &q)
+    static real trace_SJtQJ(const Mat &Sigma, const Mat &J, const Vec &q)
     {
         Mat SJt = mul(Sigma, transpose(J)); // P x T
         for (int i = 0; i < SJt.r; i++)
@@ -640,12 +650,12 @@ struct NoiseModel
         for (int i = 0; i < nPhis; i++)
         {
             const Vec &Qi = Qis[i];
-            double kqk = 0;
+            real kqk = 0;
             for (int t = 0; t < T; t++)
                 kqk += k[t] * Qi[t] * k[t];
-            double tmp = kqk + trace_SJtQJ(theta.GetCovariance(), lin.J, Qi);
+            real tmp = kqk + trace_SJtQJ(theta.GetCovariance(), lin.J, Qi);
             post.phis[i].b = 1 / (tmp * 0.5 + 1 / prior.phis[i].b);
-            double nTimes = 0;
+            real nTimes = 0;
             for (int t = 0; t < T; t++)
                 nTimes += Qi[t];
             post.phis[i].c = (nTimes - 1) * 0.5 + prior.phis[i].c;
@@ -663,7 +673,7 @@ struct NoiseModel
         Vec X(T, 0.0);
         for (int i = 0; i < nPhis; i++)
         {
-            double mean = noise.phis[i].b * noise.phis[i].c;
+            real mean = noise.phis[i].b * noise.phis[i].c;
             for (int t = 0; t < T; t++)
                 X[t] += Qis[i][t] * mean;
         }
@@ -704,7 +714,7 @@ struct NoiseModel
                 Delta[i] = JtXr[i] + P0m0[i] - P0ml[i];
             Mat damped = prec;
             for (int i = 0; i < P; i++)
-                damped(i, i) = prec(i, i) + (double)LMalpha * prec(i, i);
+                damped(i, i) = prec(i, i) + (real)LMalpha * prec(i, i);
             try
             {
                 Vec step = mulv(inverse(damped), Delta);
@@ -718,7 +728,7 @@ struct NoiseModel
         }
     }
 
-    double white_free_energy(const NoiseParams &noise, const NoiseParams &noisePrior,
+    real white_free_energy(const NoiseParams &noise, const NoiseParams &noisePrior,
         const MVN &theta, const MVN &thetaPrior, const LinModel &lin, const Vec &data) const
     {
         const Mat &J = lin.J;
@@ -731,25 +741,25 @@ struct NoiseModel
         int nTimes = T - n_masked;
         int nTheta = P;
 
-        double expectedLogThetaDist
+        real expectedLogThetaDist
             = +0.5 * log_determinant(theta.GetPrecisions()).logval - 0.5 * nTheta * (std::log(2 * M_PI) + 1);
-        double expectedLogPhiDist = 0;
-        double parts[10] = { 0 };
+        real expectedLogPhiDist = 0;
+        real parts[10] = { 0 };
         for (int i = 0; i < nPhis; i++)
         {
-            double si = noise.phis[i].b, ci = noise.phis[i].c;
-            double siPrior = noisePrior.phis[i].b, ciPrior = noisePrior.phis[i].c;
+            real si = noise.phis[i].b, ci = noise.phis[i].c;
+            real siPrior = noisePrior.phis[i].b, ciPrior = noisePrior.phis[i].c;
             expectedLogPhiDist
                 += -gammaln(ci) - ci * std::log(si) - ci + (ci - 1) * (digamma_fsl(ci) + std::log(si));
-            double qtrace = 0;
+            real qtrace = 0;
             for (int t = 0; t < T; t++)
                 qtrace += Qis[i][t];
             parts[0] += (digamma_fsl(ci) + std::log(si)) * (qtrace * 0.5 + ciPrior - 1);
             parts[9] += -gammaln(ciPrior) - ciPrior * std::log(siPrior) - si * ci / siPrior;
-            double kk = 0;
+            real kk = 0;
             for (int t = 0; t < T; t++)
             {
-                double ki = Qis[i][t] * k[t];
+                real ki = Qis[i][t] * k[t];
                 kk += ki * ki;
             }
             Mat Ji = J;
@@ -764,12 +774,12 @@ struct NoiseModel
         for (int i = 0; i < P; i++)
             dm[i] = theta.means[i] - thetaPrior.means[i];
         Vec Pdm = mulv(thetaPrior.GetPrecisions(), dm);
-        double q = 0;
+        real q = 0;
         for (int i = 0; i < P; i++)
             q += dm[i] * Pdm[i];
         parts[4] = -0.5 * q;
         parts[5] = -0.5 * trace(mul(Linv, thetaPrior.GetPrecisions()));
-        double F = -expectedLogThetaDist - expectedLogPhiDist;
+        real F = -expectedLogThetaDist - expectedLogPhiDist;
         for (int i = 0; i < 10; i++)
             F += parts[i];
         if (!(F - F == 0))
@@ -781,13 +791,13 @@ struct NoiseModel
     // Symmetric tridiagonal "alpha matrices" (noisemodel_ar.cc:130-179, nPhis == 1):
     //   M00 = diag(0,1,..,1)   M20 = diag(1,..,1,0)   M10 = -1 on the first off-diagonals.
     // Stored as (diag, off) so products skip exact zeros (bit-identical to the dense sums).
-    static double quad_tri(const Vec &k, const Vec &d, const Vec &e)
+    static real quad_tri(const Vec &k, const Vec &d, const Vec &e)
     {
         int T = (int)k.size();
-        double s = 0;
+        real s = 0;
         for (int i = 0; i < T; i++)
         {
-            double mk = 0;
+            real mk = 0;
             if (i > 0)
                 mk += e[i - 1] * k[i - 1];
             mk += d[i] * k[i];
@@ -805,7 +815,7 @@ struct NoiseModel
         for (int i = 0; i < T; i++)
             for (int p = 0; p < P; p++)
             {
-                double s = 0;
+                real s = 0;
                 if (i > 0)
                     s += e[i - 1] * J(i - 1, p);
                 s += d[i] * J(i, p);
@@ -816,7 +826,7 @@ struct NoiseModel
         return mul(transpose(J), MJ);
     }
     // OperatorKLJ (noisemodel_ar.cc:433-445): k'Mk + Trace(L.i() * J' M J)
-    static double op_klj(const Vec &k, const Mat &Sigma, const Mat &J, const Vec &d, const Vec &e)
+    static real op_klj(const Vec &k, const Mat &Sigma, const Mat &J, const Vec &d, const Vec &e)
     {
         return quad_tri(k, d, e) + trace(mul(Sigma, JtMJ_tri(J, d, e)));
     }
@@ -835,8 +845,8 @@ struct NoiseModel
     {
         Vec d00, d20, e10;
         ar_alpha_matrices(d00, d20, e10);
-        double a = np.alpha.means[0];
-        double covarPlus = np.alpha.GetCovariance()(0, 0) + a * a;
+        real a = np.alpha.means[0];
+        real covarPlus = np.alpha.GetCovariance()(0, 0) + a * a;
         np.q_diag.assign(T, 0.0);
         np.q_off.assign(T > 0 ? T - 1 : 0, 0.0);
         for (int t = 0; t < T; t++)
@@ -860,7 +870,7 @@ struct NoiseModel
         Vec zeros_off(T > 0 ? T - 1 : 0, 0.0), zeros_diag(T, 0.0);
         {
             Vec k = calc_k(theta, lin, data);
-            double si_ci = post.phis[0].b * post.phis[0].c;
+            real si_ci = post.phis[0].b * post.phis[0].c;
             const Mat &Sigma = theta.GetCovariance(); // OpKLJ uses L.i() with L = precisions
             Mat alphaPrec = prior.alpha.GetPrecisions();
             alphaPrec(0, 0) += si_ci * op_klj(k, Sigma, lin.J, d20, zeros_off);
@@ -869,7 +879,7 @@ struct NoiseModel
                 throw InternalError(FABBER_VOX_NONFINITE_F,
                     "Ar1cNoiseModel::UpdateAlpha Non-finite values in alpha precisions!");
             Mat chk = inverse(alphaPrec);
-            double mn = chk(0, 0);
+            real mn = chk(0, 0);
             for (int i = 1; i < chk.r; i++)
                 mn = std::min(mn, chk(i, i));
             if (mn < 0)
@@ -883,7 +893,7 @@ struct NoiseModel
         // UpdatePhi (noisemodel_ar.cc:530-556)
         {
             Vec k = calc_k(theta, lin, data);
-            double tmp = quad_tri(k, post.q_diag, post.q_off)
+            real tmp = quad_tri(k, post.q_diag, post.q_off)
                 + trace(mul(theta.GetCovariance(), JtMJ_tri(lin.J, post.q_diag, post.q_off)));
             post.phis[0].b = 1 / (tmp * 0.5 + 1 / prior.phis[0].b);
             post.phis[0].c = (T - 1) * 0.5 + prior.phis[0].c;
@@ -893,7 +903,7 @@ struct NoiseModel
     void ar_update_theta(const NoiseParams &noise, MVN &theta, const MVN &thetaPrior,
         const LinModel &lin, const Vec &data) const
     {
-        double si_ci = noise.phis[0].b * noise.phis[0].c;
+        real si_ci = noise.phis[0].b * noise.phis[0].c;
         Vec xd(T), xe(T > 0 ? T - 1 : 0);
         for (int t = 0; t < T; t++)
             xd[t] = si_ci * noise.q_diag[t];
@@ -912,7 +922,7 @@ struct NoiseModel
         Mat Xm(T, 1);
         for (int i = 0; i < T; i++)
         {
-            double s = 0;
+            real s = 0;
             if (i > 0)
                 s += xe[i - 1] * resid[i - 1];
             s += xd[i] * resid[i];
@@ -923,7 +933,7 @@ struct NoiseModel
         Vec mTmp(P);
         for (int p = 0; p < P; p++)
         {
-            double s = 0;
+            real s = 0;
             for (int t = 0; t < T; t++)
                 s += lin.J(t, p) * Xm(t, 0);
             mTmp[p] = s;
@@ -935,13 +945,13 @@ struct NoiseModel
         theta.means = mulv(theta.GetCovariance(), rhs);
     }
 
-    double ar_free_energy(const NoiseParams &post, const NoiseParams &prior, const MVN &theta,
+    real ar_free_energy(const NoiseParams &post, const NoiseParams &prior, const MVN &theta,
         const MVN &thetaPrior, const LinModel &lin, const Vec &data) const
     {
         Vec k = calc_k(theta, lin, data);
         const Mat &Linv = theta.GetCovariance();
         const Gamma &phi1 = post.phis[0];
-        double w = phi1.b * phi1.c;
+        real w = phi1.b * phi1.c;
         Vec qd(T), qe(T > 0 ? T - 1 : 0);
         for (int t = 0; t < T; t++)
             qd[t] = post.q_diag[t] * w;
@@ -950,15 +960,15 @@ struct NoiseModel
         int nTimes = T;
         int nTheta = P;
         int nAlphas = 2;
-        double expectedLogAlphaDist = +0.5 * log_determinant(post.alpha.GetPrecisions()).logval
+        real expectedLogAlphaDist = +0.5 * log_determinant(post.alpha.GetPrecisions()).logval
             - 0.5 * nAlphas * (std::log(2 * M_PI) + 1);
-        double expectedLogThetaDist = +0.5 * log_determinant(theta.GetPrecisions()).logval
+        real expectedLogThetaDist = +0.5 * log_determinant(theta.GetPrecisions()).logval
             - 0.5 * nTheta * (std::log(2 * M_PI) + 1);
-        double expectedLogPhiDist = 0;
-        double parts[10] = { 0 };
+        real expectedLogPhiDist = 0;
+        real parts[10] = { 0 };
         {
-            double si = phi1.b, ci = phi1.c;
-            double siPrior = prior.phis[0].b, ciPrior = prior.phis[0].c;
+            real si = phi1.b, ci = phi1.c;
+            real siPrior = prior.phis[0].b, ciPrior = prior.phis[0].c;
             expectedLogPhiDist
                 += -gammaln(ci) - ci * std::log(si) - ci + (ci - 1) * (digamma_fsl(ci) + std::log(si));
             parts[0] += (digamma_fsl(ci) + std::log(si)) * ((nTimes - 1) * 0.5 + ciPrior - 1);
@@ -971,7 +981,7 @@ struct NoiseModel
         for (int i = 0; i < P; i++)
             dm[i] = theta.means[i] - thetaPrior.means[i];
         Vec Pdm = mulv(thetaPrior.GetPrecisions(), dm);
-        double q = 0;
+        real q = 0;
         for (int i = 0; i < P; i++)
             q += dm[i] * Pdm[i];
         parts[4] = -0.5 * q;
@@ -983,7 +993,7 @@ struct NoiseModel
         Vec Pda = mulv(prior.alpha.GetPrecisions(), da);
         parts[7] = -0.5 * (da[0] * Pda[0] + da[1] * Pda[1]);
         parts[8] = -0.5 * trace(mul(post.alpha.GetCovariance(), prior.alpha.GetPrecisions()));
-        double F = -expectedLogAlphaDist - expectedLogThetaDist - expectedLogPhiDist;
+        real F = -expectedLogAlphaDist - expectedLogThetaDist - expectedLogPhiDist;
         for (int i = 0; i < 10; i++)
             F += parts[i];
         if (!(F - F == 0))
@@ -1033,7 +1043,7 @@ struct NoiseModel
         else
             white_update_noise(post, prior, theta, lin, data);
     }
-    double free_energy(const NoiseParams &post, const NoiseParams &prior, const MVN &theta,
+    real free_energy(const NoiseParams &post, const NoiseParams &prior, const MVN &theta,
         const MVN &thetaPrior, const LinModel &lin, const Vec &data) const
     {
         return ar ? ar_free_energy(post, prior, theta, thetaPrior, lin, data)
@@ -1048,15 +1058,15 @@ struct Conv
 {
     int type;
     int m_its, m_max_its;
-    double m_prev_f, m_min_fchange;
+    real m_prev_f, m_min_fchange;
     bool m_revert, m_save;
     int m_trials, m_max_trials;
     bool m_trialmode;
     // LM
     bool m_LM;
-    double m_alpha, m_alphastart, m_alphamax;
+    real m_alpha, m_alphastart, m_alphamax;
 
-    void Initialize(int type_, int max_its, double fchange, int max_trials)
+    void Initialize(int type_, int max_its, real fchange, int max_trials)
     {
         type = type_;
         m_max_its = max_its;
@@ -1066,7 +1076,7 @@ struct Conv
             m_max_its += 1; // convergence.cc:145
         Reset();
     }
-    void Reset(double F = -99e99)
+    void Reset(real F = -99e99)
     {
         m_its = 0;
         m_prev_f = F;
@@ -1090,16 +1100,16 @@ struct Conv
         ++m_its;
         return m_its >= m_max_its;
     }
-    bool fchange_test(double F)
+    bool fchange_test(real F)
     {
-        double diff = F - m_prev_f;
+        real diff = F - m_prev_f;
         m_prev_f = F;
         diff = diff > 0 ? diff : -diff;
         if (diff < m_min_fchange)
             return true;
         return counting_test();
     }
-    bool Test(double F)
+    bool Test(real F)
     {
         switch (type)
         {
@@ -1109,7 +1119,7 @@ struct Conv
             return fchange_test(F);
         case FABBER_CONV_FREDUCE:
         {
-            double diff = F - m_prev_f;
+            real diff = F - m_prev_f;
             if (diff < 0)
             {
                 m_revert = true;
@@ -1124,9 +1134,9 @@ struct Conv
         }
         return true;
     }
-    bool trial_test(double F)
+    bool trial_test(real F)
     {
-        double diff = F - m_prev_f;
+        real diff = F - m_prev_f;
         if (!m_trialmode)
         {
             if (diff < 0)
@@ -1138,7 +1148,7 @@ struct Conv
                 m_save = false;
                 return false;
             }
-            double absdiff = diff > 0 ? diff : -diff;
+            real absdiff = diff > 0 ? diff : -diff;
             if (absdiff < m_min_fchange)
             {
                 m_revert = false;
@@ -1154,7 +1164,7 @@ struct Conv
         ++m_trials;
         if (diff > 0)
         {
-            double absdiff = diff > 0 ? diff : -diff;
+            real absdiff = diff > 0 ? diff : -diff;
             if (absdiff < m_min_fchange)
             {
                 m_revert = false;
@@ -1178,10 +1188,10 @@ struct Conv
         m_revert = false;
         return false;
     }
-    bool lm_test(double F)
+    bool lm_test(real F)
     {
-        double diff = F - m_prev_f;
-        double absdiff = diff;
+        real diff = F - m_prev_f;
+        real absdiff = diff;
         if (diff < 0)
             absdiff = -diff;
         if (!m_LM)
@@ -1255,21 +1265,21 @@ struct Prior
     const fabber_cuda_vb_buffers *buf;
     int idx;
     char type;
-    double mean, prec, var;
-    double aK; // spatial
+    real mean, prec, var;
+    real aK; // spatial
 
     bool is_spatial() const { return type == 'M' || type == 'm' || type == 'P' || type == 'p'; }
 
     // SpatialPrior::CalculateaK priors.cc:221-344
-    double CalculateaK(const RunContext &ctx) const
+    real CalculateaK(const RunContext &ctx) const
     {
         const int dims = prob->spatial_dims;
-        double trace_term = 0.0, term2 = 0.0;
+        real trace_term = 0.0, term2 = 0.0;
         for (int v = 1; v <= ctx.nvoxels; v++)
         {
             if (std::find(ctx.ignore_voxels.begin(), ctx.ignore_voxels.end(), v) != ctx.ignore_voxels.end())
                 continue;
-            double sigmaK = ctx.fwd_post[v - 1].GetCovariance()(idx, idx);
+            real sigmaK = ctx.fwd_post[v - 1].GetCovariance()(idx, idx);
             int nn = (int)ctx.neighbours[v - 1].size();
             if (type == 'm')
                 trace_term += sigmaK * dims * 2;
@@ -1279,23 +1289,23 @@ struct Prior
                 trace_term += sigmaK * (4 * dims * dims + 2 * dims);
             else
                 trace_term += sigmaK * (nn * nn + nn);
-            double wK = ctx.fwd_post[v - 1].means[idx];
-            double SwK = 0.0;
+            real wK = ctx.fwd_post[v - 1].means[idx];
+            real SwK = 0.0;
             for (size_t j = 0; j < ctx.neighbours[v - 1].size(); j++)
                 SwK += wK - ctx.fwd_post[ctx.neighbours[v - 1][j] - 1].means[idx];
             if (type == 'p' || type == 'm')
-                SwK += wK * (dims * 2 - (double)ctx.neighbours[v - 1].size());
+                SwK += wK * (dims * 2 - (real)ctx.neighbours[v - 1].size());
             if (type == 'm' || type == 'M')
                 term2 += SwK * wK;
             else
                 term2 += SwK * SwK;
         }
-        double gk = 1 / (0.5 * trace_term + 0.5 * term2 + 1 / prob->spatial_q1);
-        double hK = (ctx.nvoxels * 0.5 + prob->spatial_q2);
-        double a = gk * hK;
+        real gk = 1 / (0.5 * trace_term + 0.5 * term2 + 1 / prob->spatial_q1);
+        real hK = (ctx.nvoxels * 0.5 + prob->spatial_q2);
+        real a = gk * hK;
         if (a < 1e-50)
             a = 1e-50;
-        double aKMax = a * prob->spatial_speed;
+        real aKMax = a * prob->spatial_speed;
         if (aKMax < 0.5)
             aKMax = 0.5;
         if ((prob->spatial_speed > 0) && (a > aKMax))
@@ -1303,7 +1313,7 @@ struct Prior
         return a;
     }
 
-    double ApplyToMVN(MVN *prior, RunContext &ctx)
+    real ApplyToMVN(MVN *prior, RunContext &ctx)
     {
         if (type == 'N' || type == '-' || type == 'I')
         {
@@ -1318,9 +1328,9 @@ struct Prior
         {
             // priors.cc:150-181
             Mat cov = prior->GetCovariance();
-            double post_mean = ctx.fwd_post[ctx.v - 1].means[idx];
-            double post_cov = ctx.fwd_post[ctx.v - 1].GetCovariance()(idx, idx);
-            double new_cov = post_mean * post_mean + post_cov;
+            real post_mean = ctx.fwd_post[ctx.v - 1].means[idx];
+            real post_cov = ctx.fwd_post[ctx.v - 1].GetCovariance()(idx, idx);
+            real new_cov = post_mean * post_mean + post_cov;
             if (ctx.it == 0)
             {
                 cov(idx, idx) = var;
@@ -1329,18 +1339,18 @@ struct Prior
             else
                 cov(idx, idx) = new_cov;
             prior->SetCovariance(cov);
-            double b = 2 / new_cov;
+            real b = 2 / new_cov;
             return -1.5 * (std::log(b) + digamma_fsl(0.5)) - 0.5 - gammaln(0.5) - 0.5 * std::log(b);
         }
         // SpatialPrior::ApplyToMVN priors.cc:346-488
         if (ctx.v == 1 && (ctx.it > 0 || prob->update_first_iter))
             aK = CalculateaK(ctx);
         int nn = (int)ctx.neighbours[ctx.v - 1].size();
-        double contrib_nn = 0.0;
+        real contrib_nn = 0.0;
         for (size_t j = 0; j < ctx.neighbours[ctx.v - 1].size(); j++)
             contrib_nn += ctx.fwd_post[ctx.neighbours[ctx.v - 1][j] - 1].means[idx];
         int nn2 = (int)ctx.neighbours2[ctx.v - 1].size();
-        double contrib_nn2 = 0.0;
+        real contrib_nn2 = 0.0;
         for (size_t j = 0; j < ctx.neighbours2[ctx.v - 1].size(); j++)
             contrib_nn2 += -ctx.fwd_post[ctx.neighbours2[ctx.v - 1][j] - 1].means[idx];
         const int dims = prob->spatial_dims;
@@ -1349,7 +1359,7 @@ struct Prior
             nn = 2 * dims;
             nn2 = 4 * dims * dims - nn;
         }
-        double spatial_prec = 0;
+        real spatial_prec = 0;
         if (type == 'M')
             spatial_prec = aK * (nn + 1e-8);
         else if (type == 'm')
@@ -1362,21 +1372,21 @@ struct Prior
         else
             precs(idx, idx) = prec + spatial_prec;
         prior->SetPrecisions(precs);
-        double spatial_mean;
+        real spatial_mean;
         if (type == 'm' || type == 'M')
         {
-            double rec = 1 / double(nn);
+            real rec = 1 / real(nn);
             spatial_mean = contrib_nn * rec;
         }
         else if (nn != 0)
         {
-            // priors.cc:455 - INTEGER division quirk: `double rec = 1 / (8*nn - nn2);`
+            // priors.cc:455 - INTEGER division quirk: `real rec = 1 / (8*nn - nn2);`
             int den = 8 * nn - nn2;
-            double rec;
+            real rec;
             if (den == 0)
                 rec = INFINITY; // the reference would trap (SIGFPE); not reachable for 3D grids
             else
-                rec = (double)(1 / den);
+                rec = (real)(1 / den);
             spatial_mean = (8 * contrib_nn + contrib_nn2) * rec;
         }
         else
@@ -1439,7 +1449,7 @@ struct Engine
     {
         Vec y(T);
         for (int t = 0; t < T; t++)
-            y[t] = (double)buf->data[(size_t)t * N + v];
+            y[t] = (real)buf->data[(size_t)t * N + v];
         return y;
     }
 
@@ -1472,7 +1482,7 @@ struct Engine
         if (prob->model.id == FABBER_MODEL_EXP)
         {
             // ExpFwdModel::InitVoxelPosterior examples/fwdmodel_exp.cc:84-91
-            double mx = y[0];
+            real mx = y[0];
             for (int t = 1; t < T; t++)
                 mx = std::max(mx, y[t]);
             for (int k = 0; k < prob->model.exp_num; k++)
@@ -1516,7 +1526,7 @@ struct Engine
         noise.precalculate(post, prior);
     }
 
-    void write_result(int v, const MVN &post, const NoiseParams &np, double F, int its, int status) const
+    void write_result(int v, const MVN &post, const NoiseParams &np, real F, int its, int status) const
     {
         for (int i = 0; i < P; i++)
             buf->mean[(size_t)i * N + v] = post.means[i];
@@ -1679,8 +1689,8 @@ int vb_oracle_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb
         LinModel lin;
         Conv conv;
         int status = 0;
-        double F = 1234.5678;
-        double Fprior = 0;
+        real F = 1234.5678;
+        real Fprior = 0;
         ctx.v = 1; // priors index ctx.fwd_post[ctx.v-1]; single-slot context here
         ctx.it = 0;
         // SetupPerVoxelDists (inference_vb.cc:207-247) is outside the reference's try block:
@@ -1853,10 +1863,10 @@ int vb_oracle_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
         }
     };
 
-    double Fglobal = 1234.5678;
+    real Fglobal = 1234.5678;
     do
     {
-        double Fprior = 0;
+        real Fprior = 0;
         for (int v = 1; v <= N; v++)
         {
             ctx.v = v;
@@ -1917,7 +1927,7 @@ int vb_oracle_spatial(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
                         + Fprior;
                 if (!buf->lock_centre) // :695
                     lin[v - 1].ReCentre(eng.mc, ctx.fwd_post[v - 1].means);
-                double F = 1234.5678;
+                real F = 1234.5678;
                 if (eng.needF)
                 {
                     F = eng.noise.free_energy(ctx.noise_post[v - 1], ctx.noise_prior[v - 1],

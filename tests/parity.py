@@ -11,11 +11,33 @@ We measure that floor directly: besides the oracle proper (-ffp-contract=off) th
 with FMA contraction allowed ("fma") and with the forward model's exp() perturbed by <= 1 ULP ("ulp",
 standing for a different, equally valid libm - CUDA's exp is one), see oracle/Makefile; all run on the
 same inputs. A field passes when
-    err(gpu, oracle) <= max(RTOL, FLOOR_FACTOR * max_probe err(probe, oracle)).
-FLOOR_FACTOR is 8: each probe perturbs one source of rounding, while the CUDA path differs in several
-at once (exp, summation order, LDL^T instead of pivoted LU, reciprocal instead of division), and the
-statistic is a maximum over thousands of voxels of a heavy-tailed quantity. Medians and 99th
-percentiles go into the report so the bulk of the distribution is visible, not only the tail.
+    err(gpu, oracle) <= max(RTOL, FLOOR_FACTOR * max_probe err(probe, oracle)),
+FLOOR_FACTOR = 8 (each probe perturbs one source of rounding, the CUDA path differs in several at once, and
+the statistic is a maximum over thousands of voxels of a heavy-tailed quantity).
+
+THE RULE IS CAPPED (round 2). A tolerance above CAP = 1e-5 proves nothing - any wrong kernel would pass it:
+    tolerance = min(max(RTOL, FLOOR_FACTOR * floor), CAP),
+and when the floor itself - the distance between two CPU builds of the SAME source - exceeds UNINFORMATIVE =
+1e-4, the multi-iteration comparison is declared UNINFORMATIVE and the test FAILS (chaotic trajectories: C5
+'MMMM' bi-exponential, default-prior biexp). Those configurations are pinned by single-iteration,
+teacher-forced comparisons instead (teacher_forced() below: the oracle's state after k iterations is fed to
+both sides and ONE iteration is compared - rounding noise cannot be amplified over iterations there). Between
+the two (floor 1.25e-6 ... 1e-4: ill-conditioned but not chaotic, e.g. C2's cubic normal equations, condition
+number 1.9e11) the CUDA path simply has to be within 1e-5 of the oracle.
+
+TRUTH. The same oracle source built in 80-bit extended precision ("ld", rounding noise 2048 x smaller) gives
+the answer of the reference algorithm in (nearly) exact arithmetic. Where a `truth` run is supplied the report
+carries err(oracle, truth) and err(gpu, truth) side by side - is the CUDA path as close to exact arithmetic as
+the reference's own FP64 arithmetic? - and the weak form err(gpu, truth) <= max(tolerance, TRUTH_FACTOR x
+err(oracle, truth)) is asserted (both are maxima over thousands of voxels of independent heavy-tailed rounding
+errors: two equally valid CPU builds measure ratios from 0.1 to 12 on the C2 family, so the strict form
+"<=" is reported, not asserted).
+
+Means are reported under two scalings: |d| / |mean| ("mean_rel", the literal relative error) and
+|d| / max(|mean|, posterior std) ("mean"). The assertion is on the second: a mean that is zero within its own
+uncertainty has no meaningful relative error (its literal relative error is reported, not asserted).
+The free energy is scaled by max(|F|, n/2 ln 2 pi), the magnitude of its own constant term (it cancels to ~0
+regularly; the detectors use absolute differences); the literal |dF| / |F| is reported as "F_rel".
 Voxels whose iteration count or status differs between the two CPU builds are inherently ambiguous
 (the F-difference sits on a detector threshold) and are excluded, and counted, not hidden.
 """
@@ -26,6 +48,9 @@ import numpy as np
 
 RTOL = 1e-6
 FLOOR_FACTOR = 8.0
+TRUTH_FACTOR = 4.0
+CAP = 1e-5
+UNINFORMATIVE = 1e-4
 REPORT = os.environ.get("FABBER_PARITY_REPORT", "")
 
 
@@ -49,9 +74,8 @@ def field_errors(x, ref, P, sel, check_f=True):
     var_r = np.stack([ref["cov"][tri(i, i)] for i in range(P)])
     var_x = np.stack([x["cov"][tri(i, i)] for i in range(P)])
     std = np.sqrt(np.abs(var_r))
-    # means: relative to max(|mean|, posterior std): a mean that is zero within its own uncertainty has no
-    # meaningful relative error
     errs["mean"] = float(np.max(rel_err(x["mean"], ref["mean"], scale=std)[:, sel], initial=0.0))
+    errs["mean_rel"] = float(np.max(rel_err(x["mean"], ref["mean"])[:, sel], initial=0.0))
     errs["var"] = float(np.max(rel_err(var_x, var_r)[:, sel], initial=0.0))
     worst = 0.0
     for i in range(P):
@@ -62,14 +86,24 @@ def field_errors(x, ref, P, sel, check_f=True):
     errs["cov_offdiag"] = worst
     errs["noise"] = float(np.max(rel_err(x["noise"], ref["noise"])[:, sel], initial=0.0))
     if check_f:
-        errs["F"] = float(np.max(rel_err(x["free_energy"], ref["free_energy"])[sel], initial=0.0))
+        # |dF| / max(|F|, n/2 ln 2 pi): F is a sum that contains the constant -n/2 ln(2 pi) (noisemodel_white.cc:
+        # 420-423; 88 at T = 96) and regularly cancels to ~0; the rounding error of a sum is relative to its
+        # largest summand, not to the cancelled total (and the detectors compare ABSOLUTE differences of F
+        # with 0.01). The literal |dF| / |F| is reported as "F_rel", not asserted.
+        f_scale = max(1.0, 0.5 * float(ref.get("n_times", 0)) * np.log(2 * np.pi))
+        errs["F"] = float(np.max(rel_err(x["free_energy"], ref["free_energy"], scale=f_scale)[sel], initial=0.0))
+        errs["F_rel"] = float(np.max(rel_err(x["free_energy"], ref["free_energy"])[sel], initial=0.0))
     return errs
 
 
-def compare(gpu, ref, P, probes=None, rtol=RTOL, check_f=True, label="", max_ambiguous=0.01):
+NOT_ASSERTED = ("mean_rel", "F_rel")
+
+
+def compare(gpu, ref, P, probes=None, rtol=RTOL, check_f=True, label="", max_ambiguous=0.01, truth=None):
     """Assert parity of `gpu` with the oracle run `ref`; `probes` (one run or a list of runs of the
-    noise-floor builds of the oracle on the same inputs) supply the reference's own noise floor.
-    Returns the report dict."""
+    noise-floor builds of the oracle on the same inputs) supply the reference's own noise floor; `truth` is the
+    extended-precision oracle run on the same inputs (needed only where the floor-based tolerance would exceed
+    CAP). Returns the report dict."""
     n = ref["status"].size
     stable = np.ones(n, dtype=bool)
     floor = None
@@ -88,22 +122,90 @@ def compare(gpu, ref, P, probes=None, rtol=RTOL, check_f=True, label="", max_amb
         label, ds, np.unique(gpu["status"], return_counts=True), np.unique(ref["status"], return_counts=True))
     di = np.count_nonzero((gpu["iterations"] != ref["iterations"]) & stable)
     assert di == 0, "%s iteration counts differ at %d stable voxels" % (label, di)
-    errs = field_errors(gpu, ref, P, stable & (ref["status"] == 0), check_f)
-    tol = {k: max(rtol, FLOOR_FACTOR * (floor[k] if floor else 0.0)) for k in errs}
     sel = stable & (ref["status"] == 0)
+    errs = field_errors(gpu, ref, P, sel, check_f)
+    tol = {k: max(rtol, FLOOR_FACTOR * (floor[k] if floor else 0.0)) for k in errs if k not in NOT_ASSERTED}
+    rule = {k: "floor" for k in tol}
+    uninformative = {k: floor[k] for k in tol if floor and floor[k] > UNINFORMATIVE}
+    for k in tol:
+        if tol[k] > CAP:
+            tol[k] = CAP
+            rule[k] = "capped"
+    truth_report = None
+    truth_bad = {}
+    if truth is not None:
+        sel_t = sel & (truth["status"] == ref["status"]) & (truth["iterations"] == ref["iterations"])
+        ref_t = field_errors(ref, truth, P, sel_t, check_f)
+        gpu_t = field_errors(gpu, truth, P, sel_t, check_f)
+        truth_report = {"oracle_vs_truth": ref_t, "gpu_vs_truth": gpu_t, "voxels": int(np.count_nonzero(sel_t)),
+                        "gpu_at_least_as_close_as_oracle": {k: bool(gpu_t[k] <= ref_t[k]) for k in tol}}
+        truth_bad = {k: gpu_t[k] for k in tol if not (gpu_t[k] <= max(tol[k], TRUTH_FACTOR * ref_t[k]))}
     var_r = np.stack([ref["cov"][tri(i, i)] for i in range(P)])
     e_mean = rel_err(gpu["mean"], ref["mean"], scale=np.sqrt(np.abs(var_r)))[:, sel].max(axis=0) if sel.any() else np.zeros(1)
     quant = {"mean_median": float(np.median(e_mean)), "mean_p99": float(np.quantile(e_mean, 0.99))}
     report = {"label": label, "voxels": int(n), "ambiguous_voxels": n_amb, "gpu_vs_oracle": errs,
-              "gpu_vs_oracle_quantiles": quant,
-              "oracle_probes_vs_oracle": floor, "tolerance": tol,
-              "iterations_total": int(ref["iterations"].sum())}
+              "gpu_vs_oracle_quantiles": quant, "oracle_probes_vs_oracle": floor, "tolerance": tol, "rule": rule,
+              "truth": truth_report, "iterations_total": int(ref["iterations"].sum())}
     if REPORT:
         with open(REPORT, "a") as f:
             f.write(json.dumps(report) + "\n")
-    bad = {k: v for k, v in errs.items() if not (v <= tol[k])}
-    assert not bad, "%s parity outside tolerance: %s (tolerance %s, floor %s, all %s)" % (label, bad, tol, floor, errs)
+    assert not uninformative, (
+        "%s: UNINFORMATIVE comparison - two CPU builds of the same source are more than %.0e apart in %s: pin this "
+        "configuration with teacher_forced() instead" % (label, UNINFORMATIVE, uninformative))
+    bad = {k: v for k, v in errs.items() if k in tol and not (v <= tol[k])}
+    assert not truth_bad, "%s further from the extended-precision truth than the rule allows: %s (%s)" % (
+        label, truth_bad, truth_report)
+    assert not bad, "%s parity outside tolerance: %s (tolerance %s, rule %s, floor %s, all %s)" % (
+        label, bad, tol, rule, floor, errs)
     return report
+
+
+def teacher_forced(make_spec, data, P, ks, label, spatial=False, variants=("fma",), check_f=True, device_run=None,
+                   trajectory_kwargs=None, **run_kwargs):
+    """Single-iteration, teacher-forced parity. For each k in `ks` the ORACLE's state after k iterations
+    (posterior means, covariance, noise posterior; for spatial runs that includes every neighbour's mean, and
+    aK is recomputed from that state because the step runs with update-spatial-prior-on-first-iteration) is
+    handed to both sides as a restart (init_mean / init_cov / init_noise, the continue-from-mvn path,
+    inference_vb.cc:181-216), both run ONE iteration, and the results are compared under the capped rule of
+    compare(). k = 0 is the plain first iteration from the model's own initial posterior. Rounding noise is not
+    fed back over iterations here, so chaotic trajectories (C5 'MMMM' bi-exponential, default-prior biexp) are
+    as informative as well-conditioned ones.
+    make_spec(max_iterations, **extra) -> ProblemSpec. Returns the list of reports."""
+    import oracle
+    from fabber_core_b200 import device
+
+    device_run = device_run or device.run
+    reports = []
+    for k in ks:
+        init = {}
+        if k > 0:
+            st = oracle.run(make_spec(k, **(trajectory_kwargs or {})), data, spatial=spatial, **run_kwargs)
+            alive = st["status"] == 0
+            assert alive.any(), "%s: no voxel survives %d iterations in the oracle" % (label, k)
+            # a voxel that failed on the way has no usable state: it restarts from a live voxel's (both sides
+            # get the same input either way)
+            donor = int(np.flatnonzero(alive)[0])
+            init = {}
+            for name, key in (("init_mean", "mean"), ("init_cov", "cov"), ("init_noise", "noise")):
+                arr = st[key].copy()
+                arr[:, ~alive] = arr[:, [donor]]
+                init[name] = arr
+        extra = dict(update_first_iter=True) if spatial else {}
+        kw = dict(run_kwargs)
+        kw.update(init)
+        ref = oracle.run(make_spec(1, **extra), data, spatial=spatial, **kw)
+        probes = [oracle.run(make_spec(1, **extra), data, spatial=spatial, variant=v, **kw) for v in variants]
+        gpu = device_run(make_spec(1, **extra), data, spatial=spatial, **kw)
+        truth = oracle.run(make_spec(1, **extra), data, spatial=spatial, variant="ld", **kw)
+        rep = compare(gpu, ref, P, probes, check_f=check_f, label="%s, teacher-forced step %d -> %d" % (label, k, k + 1),
+                      max_ambiguous=0.05, truth=truth)
+        if spatial:
+            ak_floor = max(np.max(rel_err(p["spatial_ak"], ref["spatial_ak"])) for p in probes)
+            ak_err = float(np.max(rel_err(gpu["spatial_ak"], ref["spatial_ak"])))
+            assert ak_err <= min(CAP, max(RTOL, FLOOR_FACTOR * ak_floor)), (label, k, ak_err, ak_floor)
+            rep["ak_err"] = ak_err
+        reports.append(rep)
+    return reports
 
 
 def one_bad_voxel_case():
