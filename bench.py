@@ -1,15 +1,23 @@
 #!/usr/bin/env python
 """bench.py - voxel-iterations/second of the VB update loop on B200 (see BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c2|c3] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--sub c2,c4,c5|none] [--impl reference]
 
-One "step" = one complete VB run (all iterations of every voxel, one fused kernel launch) over the
-synthetic volume that is already resident in HBM. `value` = voxel-iterations of all ranks / time.
-`e2e` = the same run driven with HOST buffers: pinned host -> device copy of the time-series, the
-launch, and the device -> host copy of every result array inside the timed region.
+The default line is BASELINE.json's north-star configuration: C3, the bi-exponential model under VB with
+Levenberg-Marquardt convergence on a synthetic 256^3 x 96 volume (the largest configuration that is quoted on
+one GPU and on 1/2/4/8). One "step" = one complete VB run (all iterations of every voxel) over the volume that
+is already resident in HBM. `value` = voxel-iterations of all ranks / time (max over ranks, CUDA events).
+`e2e` = the same run through the reference-facing C API (fabber_set_data -> fabber_dorun -> fabber_get_data)
+with HOST buffers: every host<->device copy is inside the timed region.
 
-Multi-GPU: one process per GPU (torchrun), voxels sharded, no data-path collective;
-each rank holds a full-size volume of its own (weak scaling).
+Multi-GPU is STRONG scaling: `--gpus N` cuts the SAME 16.8 M-voxel volume into N contiguous voxel ranges, one
+process per GPU, no data-path collective (voxels are independent, inference_vb.cc:423). The end-to-end leg at
+N > 1 is ONE process (rank 0) driving all N GPUs through the C API - what a fabber user's single fabber_dorun
+call gets on this box (libfabbercore_b200.so deals the voxel ranges to the devices itself).
+
+Sub-records (`sub`): the other synthetic BASELINE configurations in the same JSON line - C2 (poly, 128^3 x 64),
+C4 (linear + AR(1), 256^3 x 200), C5 (spatial VB, bi-exponential, 256^3 x 96; at N > 1 ONE volume in N
+z-slabs with the exact ordered sweep) - each measured the same way with fewer steps.
 """
 import argparse
 import json
@@ -24,48 +32,75 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# fp64_active: sm__pipe_fp64_cycles_active of the dominant kernel from the committed `ncu --set full` capture
+# of this round (profiles/), traffic: dram__bytes_read.sum + dram__bytes_write.sum of one launch there
 WORKLOADS = {
     # BASELINE.json configs[1]: poly degree 3, VB, white noise, synthetic 128^3 x 64, maxits 10
     "c2": dict(name="C2 poly(degree 3) VB white noise, synthetic 128^3 x 64, maxits 10", side=128, T=64,
-               model="poly", spec=dict(degree=3), P=4, e=8, e0=0,
+               model="poly", spec=dict(degree=3), P=4, kind="poly",
                capi={"model": "poly", "degree": 3, "noise": "white", "method": "vb", "max-iterations": 10},
-               # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size (ncu --set full)
-               traffic=(538.487808e6 + 273.267968e6, "profiles/r1b_ncu_full_c2_poly4.txt")),
+               ncu=dict(fp64_active=0.780, traffic=538.487808e6 + 273.267968e6,
+                        source="profiles/r1b_ncu_full_c2_poly4.txt")),
     # BASELINE.json configs[2]: biexp VB, LM convergence, synthetic 256^3 x 96
     # (prior mean 6 on r2 via PSP_byname: with the default symmetric priors the reference's own fit is
-    #  chaotic - see DESIGN.md "C3")
-    "c3": dict(name="C3 exp(num-exps 2, dt 0.02, PSP_byname r2 mean 6) VB white noise, convergence=lm, "
+    #  chaotic - see DESIGN.md "C3"; the default-prior run is timed too and reported as `default_priors`)
+    "c3": dict(name="C3 exp(num-exps 2, dt 0.02, PSP_byname1=r2 PSP_byname1_mean=6) VB white noise, convergence=lm, "
                     "synthetic 256^3 x 96", side=256, T=96, model="exp",
                spec=dict(num_exps=2, dt=0.02, convergence="lm", need_f=True,
-                         param_overrides={"r2": {"mean": 6.0}}), P=4, e=46, e0=80,
+                         param_overrides={"r2": {"mean": 6.0}}), P=4, kind="exp", NE=2,
                capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "vb", "convergence": "lm",
                      "max-iterations": 10, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0},
-               traffic=(6.506453e9 + 2.406503e9, "profiles/r1b_ncu_full_c3_exp2.txt")),
+               ncu=dict(fp64_active=0.729, traffic=6.506453e9 + 2.406503e9,
+                        source="profiles/r1b_ncu_full_c3_exp2.txt")),
     # BASELINE.json configs[3]: linear model (synthetic 200 x 4 design), AR(1) noise, synthetic 256^3 x 200
     # (the reference has no AR(2): Ar1cNoiseModel only, setup.cc:39)
     "c4": dict(name="C4 linear(200x4 design) VB AR(1) noise (num-echoes 1, cross-terms none), synthetic "
-                    "256^3 x 200, maxits 10", side=256, T=200, model="linear", spec=dict(noise="ar"), P=4, e=8, e0=0,
-               flops=35900,
-               capi={"model": "linear", "basis": "@design", "noise": "ar", "method": "vb", "max-iterations": 10}),
+                    "256^3 x 200, maxits 10", side=256, T=200, model="linear", spec=dict(noise="ar"), P=4, kind="ar",
+               capi={"model": "linear", "basis": "@design", "noise": "ar", "method": "vb", "max-iterations": 10},
+               ncu=dict(fp64_active=0.71, traffic=None, source="profiles/r1_ncu_full_c4_linear4_ar1.txt")),
     # BASELINE.json configs[4]: spatialvb (MRF spatial prior 'M' on every parameter), biexp, smooth synthetic
     # 256^3 x 96. NB the reference's CovarianceCache is dead code; the MRF prior is
     # SpatialPrior in priors.cc.
-    "c5": dict(name="C5 exp(num-exps 2, dt 0.02, PSP_byname r2 mean 6) spatialvb, param-spatial-priors=M+, "
-                    "smooth synthetic 256^3 x 96, maxits 10", side=256, T=96, model="exp", spatial=True,
+    "c5": dict(name="C5 exp(num-exps 2, dt 0.02, PSP_byname1=r2 PSP_byname1_mean=6) spatialvb, "
+                    "param-spatial-priors=M+, smooth synthetic 256^3 x 96, maxits 10", side=256, T=96, model="exp",
+               spatial=True,
                spec=dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), param_overrides={"r2": {"mean": 6.0}}),
-               P=4, e=46, e0=80,
+               P=4, kind="exp", NE=2,
                capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "spatialvb",
                      "param-spatial-priors": "M+", "max-iterations": 10, "PSP_byname1": "r2",
-                     "PSP_byname1_mean": 6.0}),
+                     "PSP_byname1_mean": 6.0},
+               ncu=dict(fp64_active=None, traffic=None, source=None)),
 }
 
 
 def algorithmic_flops(w):
-    """FLOP per voxel-iteration of the minimal algorithm (FMA = 2, div = sqrt = 10,
-    exp = log = 20): (2P+1)(T e + e0) + 2TP + T[P(P+1) + 2P + 3] + (2P^3 + 10P^2 + 300)."""
-    if "flops" in w:  # AR(1): statistics tripled + 2x2 alpha algebra, SURVEY.md 8(d): 35.9 kFLOP
-        return w["flops"]
-    P, T, e, e0 = w["P"], w["T"], w["e"], w["e0"]
+    """FLOP per voxel-iteration of the minimal algorithm, SURVEY.md 8(d) convention (FMA = 2, add = mul = 1,
+    div = sqrt = 10, exp = log = 20): one pass over t evaluating the model at the 2P+1 finite-difference points
+    and accumulating the sufficient statistics, plus the O(P^3) algebra:
+        W = T * e + e0 + 2TP + T [P(P+1) + 2P + 3] + (2 P^3 + 10 P^2 + 300).
+    poly(d): e = (2P+1) * 2(d+1), e0 = 0.          linear: e = (2P+1) * 2P, e0 = 0.
+    exp(NE): the perturbed points differ from the centre in ONE parameter, so a sample needs the exponential of
+      each rate at its three values only (3 NE exponentials, not (2P+1) NE as SURVEY.md's e = 23 NE assumed - the
+      round-1 judge's correction): e = 3 NE (20 + 1) + 1 + (2P+1)(2 NE - 1), and the log-transforms of the
+      3 P parameter values per pass: e0 = 3 P * 20.
+    AR(1): SURVEY.md 8(d): statistics tripled + 2x2 alpha algebra = 35.9 kFLOP at P = 4, T = 200."""
+    P, T = w["P"], w["T"]
+    common = 2 * T * P + T * (P * (P + 1) + 2 * P + 3) + (2 * P ** 3 + 10 * P ** 2 + 300)
+    if w["kind"] == "ar":
+        return 35900
+    if w["kind"] == "poly":
+        return (2 * P + 1) * T * 2 * P + common
+    NE = w["NE"]
+    e = 3 * NE * 21 + 1 + (2 * P + 1) * (2 * NE - 1)
+    return T * e + 3 * P * 20 + common
+
+
+def survey_formula_flops(w):
+    """SURVEY.md 8(d)'s own formula (counts (2P+1) full model evaluations per sample); reported beside W."""
+    P, T = w["P"], w["T"]
+    if w["kind"] == "ar":
+        return 35900
+    e, e0 = (2 * P, 0) if w["kind"] == "poly" else (23 * w["NE"], 20 * P)
     return (2 * P + 1) * (T * e + e0) + 2 * T * P + T * (P * (P + 1) + 2 * P + 3) + (2 * P ** 3 + 10 * P ** 2 + 300)
 
 
@@ -77,7 +112,9 @@ def algorithmic_bytes(w, n_iter):
     return (4 * T + 4 * ((P + 1) * (P + 2) // 2 + (P + 1) + 1) + 16) / max(n_iter, 1e-9)
 
 
-def make_volume(w, n_voxels, device, seed_offset=0):
+def make_volume(w, n_voxels, device, seed_offset=0, voxel_offset=0, n_total=None):
+    """`n_voxels` voxels of the workload's synthetic volume, starting at voxel `voxel_offset` of a volume of
+    `n_total` voxels (strong scaling: every rank generates its own contiguous range)."""
     from fabber_core_b200 import synth
 
     if w["model"] == "poly":
@@ -85,10 +122,11 @@ def make_volume(w, n_voxels, device, seed_offset=0):
     if w["model"] == "linear":
         return synth.linear_ar_volume(n_voxels, w["T"], 0.3, seed=1004 + seed_offset, device=device)
     if w.get("spatial"):
-        side = round(n_voxels ** (1.0 / 3))
-        assert side ** 3 == n_voxels, "spatial workloads need a cubic voxel count"
+        n_total = n_total or n_voxels
+        side = round(n_total ** (1.0 / 3))
+        assert side ** 3 == n_total, "spatial workloads need a cubic voxel count"
         return synth.biexp_volume(n_voxels, w["T"], 0.02, 0.02, seed=1005 + seed_offset, device=device,
-                                  smooth_shape=(side, side, side))
+                                  smooth_shape=(side, side, side), voxel_offset=voxel_offset)
     return synth.biexp_volume(n_voxels, w["T"], 0.02, 0.02, seed=1003 + seed_offset, device=device)
 
 
@@ -213,7 +251,9 @@ def capi_e2e(w, host_y, extent, steps):
     if tmp is not None:
         os.unlink(tmp.name)
     capi_e2e.last_phases_ms = {k: v / steps * 1e3 for k, v in phases.items()}
-    capi_e2e.last_log = [l for l in f.outbuf.value.decode(errors="replace").splitlines() if "Vb::timing" in l]
+    log_lines = f.outbuf.value.decode(errors="replace").splitlines()
+    capi_e2e.last_log = [l for l in log_lines if "Vb::timing" in l]
+    capi_e2e.last_devices = [l.split(",")[-1].strip() for l in log_lines if "calculations on the GPU" in l]
     return dt, flat.nbytes, d2h
 
 
@@ -334,100 +374,345 @@ def oracle_throughput(w, threads, budget_s):
     return total / dt, dt, n_per_thread * threads
 
 
-def spatial_slab_bench(args, w, rank, local_rank, world, n_vox, metric, config):
-    """C5 on several GPUs: ONE volume of side x side x (side * world) voxels partitioned into z-slabs, one
-    slab (plus ghost planes) per rank; per iteration an all-reduce of the aK sums, the block-pipelined ordered
-    sweep (forwarding of boundary means up the ranks) and a halo exchange, all over NCCL
-    (fabber_core_b200/spatial_mgpu.py). Weak scaling: side^3 own voxels per GPU."""
+def roofline_block(w, its_launch, avg_kernel_s, n_vox_launch, fp64_peak_gflops, spatial):
+    """roofline of the dominant kernel: algorithmic FLOP of one launch / its measured duration against the FP64
+    DFMA peak measured live on this GPU; HBM fraction beside it (this path is nowhere near HBM-bound)."""
+    W = algorithmic_flops(w)
+    achieved_tf = W * its_launch / avg_kernel_s / 1e12
+    peak_tf = fp64_peak_gflops / 1e3
+    n_iter = its_launch / float(max(n_vox_launch, 1))
+    bytes_per_launch = algorithmic_bytes(w, n_iter) * its_launch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    ncu = w.get("ncu", {})
+    full_size = n_vox_launch == w["side"] ** 3
+    return {
+        "bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
+        "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
+        # DRAM bytes of one launch from the committed ncu --set full capture (only quoted at the size it was
+        # captured at); algorithmic bytes are in "hbm" below
+        "traffic": ncu.get("traffic") if full_size else None,
+        "traffic_unit": "bytes per launch (dram read + write)",
+        "traffic_source": ncu.get("source") if full_size else None,
+        "fp64_pipe_active_ncu": ncu.get("fp64_active"), "fp64_pipe_active_source": ncu.get("source"),
+        "algorithmic_bytes_per_launch": bytes_per_launch,
+        "peak_source": "measured live: dependent-free DFMA loop on all SMs (MEASURED_PEAKS.json has no FP64 figure)",
+        "flop_per_voxel_iteration": W, "flop_per_voxel_iteration_survey_formula": survey_formula_flops(w),
+        "flop_note": "W counts the 3*NE exponentials per sample the algorithm needs (exp model), not (2P+1)*NE",
+        "kernel": ("sp_noise_kernel (+ sp_theta / sp_sweep / sp_ak)" if spatial else "vb_voxelwise_ar_kernel"
+                   if w["spec"].get("noise") == "ar" else "vb_voxelwise_white_kernel"),
+        "avg_launch_ms": avg_kernel_s * 1e3,
+        "hbm": {"achieved": bytes_per_launch / avg_kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": bytes_per_launch / avg_kernel_s / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}}
+
+
+class Dist(object):
+    """the bench's use of torch.distributed: a barrier and max / sum over ranks (no data-path collective)"""
+
+    def __init__(self, world):
+        self.world = world
+        if world > 1:
+            import torch.distributed as dist
+
+            self.dist = dist
+
+    def barrier(self):
+        import torch
+
+        if self.world > 1:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def reduce(self, value, op):
+        import torch
+
+        t = torch.tensor([value], dtype=torch.float64, device="cuda")
+        if self.world > 1:
+            self.dist.all_reduce(t, op=getattr(self.dist.ReduceOp, op))
+        return float(t.item())
+
+
+def host_volume_full(w, n_total, world):
+    """The whole synthetic volume in pinned host memory, [T][n_total] float32, generated on this GPU rank range
+    by rank range (the same generators and seeds the ranks use for their device-resident shards)."""
     import torch
-    import torch.distributed as dist
+
+    from fabber_core_b200 import shard
+
+    host = torch.empty((w["T"], n_total), dtype=torch.float32, pin_memory=True)
+    for r in range(world):
+        lo, hi = shard.voxel_range(n_total, r, world)
+        part = make_volume(w, hi - lo, "cuda", seed_offset=r, voxel_offset=lo, n_total=n_total)
+        host[:, lo:hi].copy_(part)
+        del part
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
+    return host
+
+
+def run_workload(wname, args, D, rank, local_rank, world, steps, warmup, main_line):
+    """Device-resident timing (all ranks), then the end-to-end leg through the C API (rank 0 drives every GPU).
+    Returns the record on rank 0, None elsewhere."""
+    import torch
+
+    from fabber_core_b200 import device, shard
+
+    w = WORKLOADS[wname]
+    L = device.lib()
+    stream = torch.cuda.current_stream().cuda_stream
+    spatial = bool(w.get("spatial"))
+    n_total = args.voxels if (args.voxels and main_line) else w["side"] ** 3
+    side = round(n_total ** (1.0 / 3))
+    lo, hi = shard.voxel_range(n_total, rank, world)
+    n_local = hi - lo
+    config = {"workload": w["name"], "voxels_total": n_total, "voxels_per_gpu": n_local, "timepoints": w["T"],
+              "params": w["P"],
+              "sharding": ("one volume, contiguous voxel ranges, no collective" if not spatial else "one GPU"),
+              "cache": "inputs larger than L2 (%.0f MB per GPU per step)" % (n_local * w["T"] * 4 / 1e6)}
+
+    if spatial and world > 1:
+        rec = spatial_slab_bench(args, w, D, rank, local_rank, world, n_total, steps, warmup, config)
+        dev = None
+    else:
+        y = make_volume(w, n_local, "cuda", seed_offset=rank, voxel_offset=lo, n_total=n_total)
+        spec = make_spec(w, n_local)
+        run = device.VbRun(spec, n_local, spatial=spatial)
+        run.set_data_device(y.data_ptr())
+        if spatial:
+            idx = torch.arange(n_local, device="cuda")
+            coords = torch.stack([idx % side, (idx // side) % side, idx // (side * side)]).to(torch.int32).contiguous()
+            run.buf.coords = coords.data_ptr()
+
+        def step():
+            rc = run.launch(stream)
+            if rc != 0:
+                raise RuntimeError("launch failed: %s" % device.last_error())
+
+        for _ in range(max(warmup, 3)):
+            step()
+        D.barrier()
+        its_local = int(run.out["iterations"].to_host().astype(np.int64).sum())
+        n_bad = int(np.count_nonzero(run.out["status"].to_host()))
+        fp64_peak = L.fabber_cuda_measure_fp64_peak(3)  # GFLOP/s, live (no FP64 figure in MEASURED_PEAKS.json)
+        if main_line:
+            torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed region is listed
+        sampler = ClockSampler(local_rank)
+        time.sleep(0.3)
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        launches0 = L.fabber_cuda_launch_count()
+        D.barrier()
+        t0 = time.time()
+        ev[0].record()
+        for i in range(steps):
+            step()
+            ev[i + 1].record()
+        D.barrier()
+        t1 = time.time()
+        if main_line:
+            torch.cuda.profiler.stop()
+        launches = L.fabber_cuda_launch_count() - launches0
+        clocks = sampler.stop(t0, t1)
+        kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+        total_ms = D.reduce(ev[0].elapsed_time(ev[-1]), "MAX")
+        its_all = D.reduce(its_local, "SUM")
+        bad_all = int(D.reduce(n_bad, "SUM"))
+        rec = {
+            "value": its_all * steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "steps": steps,
+            "warmup": max(warmup, 3), "config": config, "gpu_launches": int(launches), "clocks": clocks,
+            "iterations_per_voxel": its_all / float(n_total), "bad_voxels": bad_all,
+            "roofline": roofline_block(w, its_local, float(np.mean(kernel_ms)) * 1e-3, n_local, fp64_peak, spatial)}
+
+        # the inner ABI with pinned host buffers: copy in, run, copy every raw result array out (CUDA events)
+        host_y = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
+        host_y.copy_(y)
+        outs = run.out
+        host_out = {k: torch.empty(v.nbytes, dtype=torch.uint8, pin_memory=True) for k, v in outs.items()}
+        h2d = host_y.numel() * 4
+        d2h = sum(v.nbytes for v in outs.values())
+
+        def inner_step():
+            device.check(L.fabber_cuda_memcpy_h2d(y.data_ptr(), host_y.data_ptr(), h2d, stream), "h2d")
+            step()
+            for k, v in outs.items():
+                device.check(L.fabber_cuda_memcpy_d2h(host_out[k].data_ptr(), v.ptr, v.nbytes, stream), "d2h")
+
+        inner_step()
+        D.barrier()
+        inner_steps = max(1, min(steps, 3))
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(inner_steps):
+            inner_step()
+        e1.record()
+        D.barrier()
+        inner_ms = D.reduce(e0.elapsed_time(e1), "MAX")
+        rec["inner_abi"] = {"value": its_all * inner_steps / (inner_ms * 1e-3), "h2d_bytes_per_step": h2d,
+                            "d2h_bytes_per_step": d2h, "steps": inner_steps,
+                            "path": "fabber_cuda_vb_* per rank with pinned host buffers, raw result arrays, CUDA events"}
+
+        # C3 with the reference's DEFAULT (symmetric) priors: throughput and how many voxels diverge
+        if main_line and wname == "c3":
+            spec_d = dict(w["spec"])
+            spec_d.pop("param_overrides")
+            from fabber_core_b200 import cuda_abi as abi
+
+            sd = abi.ProblemSpec(w["model"], w["T"], allow_bad_voxels=True, **spec_d)
+            run_d = device.VbRun(sd, n_local)
+            run_d.set_data_device(y.data_ptr())
+            run_d.launch(stream)
+            D.barrier()
+            d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            d0.record()
+            for _ in range(2):
+                run_d.launch(stream)
+            d1.record()
+            D.barrier()
+            its_d = D.reduce(int(run_d.out["iterations"].to_host().astype(np.int64).sum()), "SUM")
+            bad_d = D.reduce(int(np.count_nonzero(run_d.out["status"].to_host())), "SUM")
+            ms_d = D.reduce(d0.elapsed_time(d1), "MAX")
+            rec["default_priors"] = {
+                "value": its_d * 2 / (ms_d * 1e-3), "unit": "voxel-iterations/s", "ms_per_step": ms_d / 2,
+                "iterations_per_voxel": its_d / float(n_total), "bad_voxels": int(bad_d),
+                "note": "same data and options without the PSP_byname override (allow-bad-voxels): the symmetric "
+                        "start is a saddle in the reference itself (DESIGN.md section 4)"}
+            run_d.close()
+        run.close()
+        del host_out, host_y, y
+        torch.cuda.empty_cache()
+
+    # ---- end to end through the reference's public C API with host buffers: rank 0 drives all `world` GPUs ----
+    D.barrier()
+    e2e = None
+    if rank == 0:
+        host = host_volume_full(w, n_total, world)
+        capi_steps = max(1, min(steps, 3))
+        extent = (side, side, side) if side ** 3 == n_total else (n_total, 1, 1)
+        capi_s, capi_h2d, capi_d2h = capi_e2e(w, host.numpy(), extent, capi_steps)
+        its_all = rec["iterations_per_voxel"] * n_total
+        dev_line = [l for l in capi_e2e.last_devices] or ["?"]
+        e2e = {"value": its_all / capi_s, "unit": "voxel-iterations/s", "h2d_bytes_per_step": capi_h2d,
+               "d2h_bytes_per_step": capi_d2h, "steps": capi_steps, "ms_per_step": capi_s * 1e3,
+               "calls_ms": capi_e2e.last_phases_ms, "dorun_log": capi_e2e.last_log, "devices_used": dev_line[0],
+               "path": "fabber_capi (libfabbercore_b200.so), ONE process: fabber_set_data (pinned host float32 volume "
+                       "in) -> fabber_dorun -> fabber_get_data of mean_*, std_*, noise_means (host float32 volumes "
+                       "out); the library deals the voxel ranges to the GPUs it was given (FABBER_B200_DEVICES=%s); "
+                       "wall clock" % os.environ.get("FABBER_B200_DEVICES", "")}
+        del host
+    D.barrier()
+    if rank != 0:
+        return None
+    rec["e2e"] = e2e
+    if "inner_abi" in rec:
+        rec["e2e"]["inner_abi"] = rec.pop("inner_abi")
+    return rec
+
+
+def spatial_slab_bench(args, w, D, rank, local_rank, world, n_total, steps, warmup, config):
+    """C5 on several GPUs, STRONG scaling: ONE side^3 volume partitioned into `world` z-slabs, one slab (plus
+    ghost planes) per rank; per iteration an all-reduce of the aK sums, the block-pipelined ordered sweep
+    (forwarding of boundary means up the ranks) and a halo exchange (fabber_core_b200/spatial_mgpu.py)."""
+    import torch
 
     from fabber_core_b200 import device, synth
     from fabber_core_b200.spatial_mgpu import SlabPlan, SlabRun, TorchDistComm
 
-    side = round(n_vox ** (1.0 / 3))
-    assert side ** 3 == n_vox
-    plan = SlabPlan(side, side, side * world, rank, world)
+    side = round(n_total ** (1.0 / 3))
+    assert side ** 3 == n_total
+    plan = SlabPlan(side, side, side, rank, world)
     g0, g1 = plan.global_columns()
     y = synth.biexp_volume(g1 - g0, w["T"], 0.02, 0.02, seed=1005 + rank, device="cuda",
-                           smooth_shape=(side, side, side * world), voxel_offset=g0)
+                           smooth_shape=(side, side, side), voxel_offset=g0)
     L = device.lib()
     comm = TorchDistComm(rank, world, w["P"])
     sr = SlabRun(make_spec(w, 0), plan, comm)
     sr.set_data_device(y.data_ptr())
-
-    def step():
+    for _ in range(max(warmup, 3)):
         sr.launch()
-
-    def barrier():
-        dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
     out = sr.results()
     its_local = int(out["iterations"].astype(np.int64).sum())
     n_bad = int(np.count_nonzero(out["status"]))
-    barrier()
+    fp64_peak = L.fabber_cuda_measure_fp64_peak(3)
+    D.barrier()
     launches0 = L.fabber_cuda_launch_count()
     sampler = ClockSampler(local_rank)
     time.sleep(0.3)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
+    D.barrier()
     t0 = time.time()
     ev0.record()
-    for _ in range(args.steps):
-        step()
+    for _ in range(steps):
+        sr.launch()
     ev1.record()
-    barrier()
+    D.barrier()
     clocks = sampler.stop(t0, time.time())
     launches = L.fabber_cuda_launch_count() - launches0
-    t_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device="cuda")
-    its = torch.tensor([its_local], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-    dist.all_reduce(its, op=dist.ReduceOp.SUM)
-    value = float(its.item()) * args.steps / (float(t_ms.item()) * 1e-3)
-
-    # end to end: the slab's series from pinned host memory in, the owned voxels' results out, every step
-    host_y = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
-    host_y.copy_(y)
-    host_np = host_y.numpy()
-    e2e_steps = max(1, min(args.steps, 2))
-    sr.set_data(host_np)
-    sr.launch()
-    res = sr.results()
-    barrier()
-    t0 = time.time()
-    for _ in range(e2e_steps):
-        sr.set_data(host_np)
-        sr.launch()
-        res = sr.results()
-    barrier()
-    e2e_s = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
-    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-    e2e_value = float(its.item()) * e2e_steps / float(e2e_s.item())
-    d2h = int(sum(v.nbytes for v in res.values() if isinstance(v, np.ndarray)))
+    t_ms = D.reduce(ev0.elapsed_time(ev1), "MAX")
+    its = D.reduce(its_local, "SUM")
+    bad = int(D.reduce(n_bad, "SUM"))
     sr.close()
-    if rank == 0:
-        cfg = dict(config)
-        cfg["sharding"] = ("z-slabs of one %dx%dx%d volume; per iteration: all-reduce of aK sums, ordered sweep "
-                           "pipelined across the slabs in %d blocks of %d hyper-planes, halo exchange (NCCL); "
-                           "result equals the one-GPU run" % (side, side, side * world, plan.n_blocks,
-                                                              plan.block_planes))
-        flop = algorithmic_flops(w) * float(its.item()) * args.steps / world   # per GPU
-        print(json.dumps({
-            "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": float(t_ms.item()) / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
-            "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": int(host_y.nbytes),
-                    "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                    "path": "SlabRun: set_data (pinned host series) -> launch -> results (host arrays) on every "
-                            "rank; wall clock, max over ranks"},
-            "gpu_launches": int(launches), "bad_voxels": n_bad, "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": flop / (float(t_ms.item()) * 1e-3) / 1e12, "unit": "TFLOP/s",
-                         "peak": None, "frac": None, "traffic": None,
-                         "note": "per GPU; the one-GPU line of the same workload carries the measured peak"}}))
-    dist.destroy_process_group()
+    del y
+    torch.cuda.empty_cache()
+    cfg = dict(config)
+    cfg["voxels_per_gpu"] = plan.n_own
+    cfg["sharding"] = ("z-slabs of ONE %dx%dx%d volume; per iteration: all-reduce of the aK sums, ordered sweep pipelined "
+                       "across the slabs in %d blocks of %d hyper-planes, halo exchange; result equals the one-GPU run"
+                       % (side, side, side, plan.n_blocks, plan.block_planes))
+    return {"value": its * steps / (t_ms * 1e-3), "ms_per_step": t_ms / steps, "steps": steps,
+            "warmup": max(warmup, 3), "config": cfg, "gpu_launches": int(launches), "clocks": clocks,
+            "iterations_per_voxel": its / float(n_total), "bad_voxels": bad,
+            "roofline": roofline_block(w, its_local, t_ms / steps * 1e-3, plan.n_own, fp64_peak, True)}
+
+
+def reference_arm(args, metric):
+    """--impl reference: the reference's own CPU implementation of the path on the box's host cores: oracle/_ref
+    (its unchanged sources compiled against the test-only NEWMAT stand-in, built where /root/reference exists and
+    shipped with the tree), one single-threaded process per core - how fabber is parallelised in practice. Falls
+    back to the oracle port only if that library is missing."""
+    w = WORKLOADS[args.workload]
+    cores = os.cpu_count() or 1
+    use_ref = os.path.exists(REF_LIB)
+    rates = []
+    t_all0 = time.perf_counter()
+    # ~75 s of reference compute over all steps (plus worker start-up), whatever K and W are
+    per_step = max(1.5, 75.0 / (args.warmup + args.steps))
+    pool, per_voxel = None, None
+    if use_ref:
+        import multiprocessing as mp
+
+        pool = mp.get_context("spawn").Pool(cores)
+    try:
+        for i in range(args.warmup + args.steps):
+            if use_ref:
+                rate, dt, n, _, per_voxel = reference_throughput(args.workload, cores, budget_s=per_step, pool=pool,
+                                                                 per_voxel=per_voxel, seed=100 + 1000 * i)
+            else:
+                rate, dt, n = oracle_throughput(w, cores, budget_s=per_step)
+            if i >= args.warmup:
+                rates.append((rate, dt, n))
+    finally:
+        if pool is not None:
+            pool.close()
+            pool.join()
+    value = float(np.mean([r[0] for r in rates]))
+    ms = float(np.mean([r[1] for r in rates]) * 1e3)
+    kind = "reference" if use_ref else "port"
+    sample = "%d voxels of the same synthetic workload per step, %d %s" % (
+        rates[0][2], cores, "single-threaded processes (oracle/_ref)" if use_ref else "threads (oracle port)")
+    n_total = w["side"] ** 3
+    config = {"workload": w["name"], "voxels_total": n_total, "timepoints": w["T"], "params": w["P"]}
+    print(json.dumps({
+        "impl": "reference", "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+        "cpu_baseline": {"value": value, "unit": "voxel-iterations/s", "cores": cores, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.perf_counter() - t_all0}))
     return 0
 
 
@@ -436,66 +721,27 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--sub", default="c2,c4,c5", help="comma list of workloads reported as sub-records, or 'none'")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--voxels", type=int, default=0, help="override voxels per GPU (debug)")
+    ap.add_argument("--voxels", type=int, default=0, help="override the TOTAL voxel count of the main workload (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    n_vox = args.voxels or w["side"] ** 3
     metric = "voxel-iterations/sec"
-    config = {"workload": w["name"], "voxels_per_gpu": n_vox, "timepoints": w["T"], "params": w["P"],
-              "sharding": "voxel ranges, no collective", "cache": "inputs larger than L2 (%.0f MB per step)"
-              % (n_vox * w["T"] * 4 / 1e6)}
 
     if args.impl == "reference":
-        # The reference's own CPU implementation of the path on the box's host cores: oracle/_ref (its
-        # unchanged sources compiled against the test-only NEWMAT stand-in, built where /root/reference
-        # exists and shipped with the tree), one single-threaded process per core. Falls back to the
-        # oracle port only if that library is missing.
         if rank != 0:
             return 0
-        cores = os.cpu_count() or 1
-        use_ref = os.path.exists(REF_LIB)
-        rates = []
-        t_all0 = time.perf_counter()
-        # ~75 s of reference compute over all steps (plus worker start-up), whatever K and W are
-        per_step = max(1.5, 75.0 / (args.warmup + args.steps))
-        pool, per_voxel = None, None
-        if use_ref:
-            import multiprocessing as mp
+        return reference_arm(args, metric)
 
-            pool = mp.get_context("spawn").Pool(cores)
-        try:
-            for i in range(args.warmup + args.steps):
-                if use_ref:
-                    rate, dt, n, _, per_voxel = reference_throughput(args.workload, cores, budget_s=per_step, pool=pool,
-                                                                     per_voxel=per_voxel, seed=100 + 1000 * i)
-                else:
-                    rate, dt, n = oracle_throughput(w, cores, budget_s=per_step)
-                if i >= args.warmup:
-                    rates.append((rate, dt, n))
-        finally:
-            if pool is not None:
-                pool.close()
-                pool.join()
-        value = float(np.mean([r[0] for r in rates]))
-        ms = float(np.mean([r[1] for r in rates]) * 1e3)
-        kind = "reference" if use_ref else "port"
-        sample = "%d voxels of the same synthetic workload per step, %d %s" % (
-            rates[0][2], cores, "single-threaded processes (oracle/_ref)" if use_ref else "threads (oracle port)")
-        print(json.dumps({
-            "impl": "reference", "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "cpu_baseline": {"value": value, "unit": "voxel-iterations/s", "cores": cores, "kind": kind,
-                             "sample": sample},
-            "e2e": {"value": value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "wall_s": time.perf_counter() - t_all0}))
-        return 0
+    # the end-to-end leg is ONE process (rank 0) driving every GPU of the job through the C API: tell the host
+    # library which devices that is before it is first used (it reads the variable once)
+    if "FABBER_B200_DEVICES" not in os.environ:
+        os.environ["FABBER_B200_DEVICES"] = ",".join(str(i) for i in range(world)) if rank == 0 else str(local_rank)
 
     import torch
 
@@ -510,155 +756,30 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     L = device.lib()
     device.check(L.fabber_cuda_set_device(local_rank), "set_device")
-    stream = torch.cuda.current_stream().cuda_stream
+    D = Dist(world)
 
-    spatial = bool(w.get("spatial"))
-    if spatial and world > 1:
-        return spatial_slab_bench(args, w, rank, local_rank, world, n_vox, metric, config)
-    y = make_volume(w, n_vox, "cuda", seed_offset=rank)
-    spec = make_spec(w, n_vox)
-    run = device.VbRun(spec, n_vox, spatial=spatial)
-    run.set_data_device(y.data_ptr())
-    if spatial:
-        idx = torch.arange(n_vox, device="cuda")
-        side = spec.prob.nx
-        coords = torch.stack([idx % side, (idx // side) % side, idx // (side * side)]).to(torch.int32).contiguous()
-        run.buf.coords = coords.data_ptr()
-
-    def step():
-        rc = run.launch(stream)
-        if rc != 0:
-            raise RuntimeError("launch failed: %s" % device.last_error())
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    barrier()
-    its_total = int(run.out["iterations"].to_host().astype(np.int64).sum())
-    n_bad = int(np.count_nonzero(run.out["status"].to_host()))
-    fp64_peak = L.fabber_cuda_measure_fp64_peak(3)  # GFLOP/s, measured live (no FP64 figure in MEASURED_PEAKS.json)
-
-    torch.cuda.profiler.start()  # ncu --profile-from-start off: only the timed regions are listed
-    sampler = ClockSampler(local_rank)
-    time.sleep(0.3)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    launches0 = L.fabber_cuda_launch_count()
-    barrier()
-    t0 = time.time()
-    ev[0].record()
-    for i in range(args.steps):
-        step()
-        ev[i + 1].record()
-    barrier()
-    t1 = time.time()
-    launches = L.fabber_cuda_launch_count() - launches0
-    clocks = sampler.stop(t0, t1)
-    total_ms = ev[0].elapsed_time(ev[-1])
-    kernel_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(args.steps)]
-    t_ms = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    its = torch.tensor([its_total], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
-        dist.all_reduce(its, op=dist.ReduceOp.SUM)
-    total_ms_max = float(t_ms.item())
-    its_all = float(its.item())
-    value = its_all * args.steps / (total_ms_max * 1e-3)
-
-    # ---- end-to-end: host buffers in, host buffers out, copies inside the timed region ------------
-    host_y = torch.empty(y.shape, dtype=torch.float32, pin_memory=True)
-    host_y.copy_(y)
-    outs = run.out
-    host_out = {k: torch.empty(v.nbytes, dtype=torch.uint8, pin_memory=True) for k, v in outs.items()}
-    h2d = host_y.numel() * 4
-    d2h = sum(v.nbytes for v in outs.values())
-
-    def e2e_step():
-        device.check(L.fabber_cuda_memcpy_h2d(y.data_ptr(), host_y.data_ptr(), h2d, stream), "h2d")
-        step()
-        for k, v in outs.items():
-            device.check(L.fabber_cuda_memcpy_d2h(host_out[k].data_ptr(), v.ptr, v.nbytes, stream), "d2h")
-
-    e2e_step()
-    barrier()
-    e2e_steps = max(1, min(args.steps, 5))
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
-    e1.record()
-    barrier()
-    e2e_ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
-    e2e_inner = its_all * e2e_steps / (float(e2e_ms.item()) * 1e-3)
-    torch.cuda.profiler.stop()
-
-    # ---- the headline end-to-end number: the reference's public C API with host buffers --------------
-    run.close()
-    del host_out
-    host_np = host_y.numpy()
-    del y
-    torch.cuda.empty_cache()
-    capi_steps = max(1, min(args.steps, 3))
-    side = round(n_vox ** (1.0 / 3))
-    extent = (side, side, side) if side ** 3 == n_vox else (n_vox, 1, 1)
-    capi_s, capi_h2d, capi_d2h = capi_e2e(w, host_np, extent, capi_steps)
-    t_capi = torch.tensor([capi_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t_capi, op=dist.ReduceOp.MAX)
-    e2e_value = its_all / float(t_capi.item())
+    rec = run_workload(args.workload, args, D, rank, local_rank, world, args.steps, args.warmup, True)
+    subs = {}
+    sub_names = [x for x in args.sub.split(",") if x and x != "none" and x != args.workload]
+    for name in sub_names:
+        if name not in WORKLOADS:
+            raise SystemExit("unknown sub workload %r" % name)
+        sub_steps = max(1, min(args.steps, 3))
+        r = run_workload(name, args, D, rank, local_rank, world, sub_steps, 3, False)
+        if rank == 0:
+            r.update({"metric": metric, "unit": "voxel-iterations/s", "n_gpus": world, "scaling": "strong",
+                      "dtype": "f64", "data": "synthetic"})
+            subs[name] = r
 
     if rank == 0:
-        W = algorithmic_flops(w)
-        per_launch_its = its_total  # this rank's launch
-        avg_kernel_s = float(np.mean(kernel_ms)) * 1e-3
-        achieved_tf = W * per_launch_its / avg_kernel_s / 1e12
-        peak_tf = fp64_peak / 1e3
-        n_iter = its_total / float(n_vox)
-        bytes_per_launch = algorithmic_bytes(w, n_iter) * per_launch_its
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except (OSError, ValueError):
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        line = {
-            "metric": metric, "value": value, "unit": "voxel-iterations/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e_value, "unit": "voxel-iterations/s", "h2d_bytes_per_step": capi_h2d,
-                    "d2h_bytes_per_step": capi_d2h, "steps": capi_steps,
-                    "calls_ms": getattr(capi_e2e, "last_phases_ms", None),
-                    "dorun_log": getattr(capi_e2e, "last_log", None),
-                    "path": "fabber_capi (libfabbercore_b200.so): fabber_set_data -> fabber_dorun -> fabber_get_data "
-                            "of mean_*, std_*, noise_means; host float32 buffers in and out; wall clock",
-                    "inner_abi": {"value": e2e_inner, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                                  "steps": e2e_steps,
-                                  "path": "fabber_cuda_vb_* with pinned host buffers, raw result arrays, CUDA events"}},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "fp64", "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s",
-                         "frac": achieved_tf / peak_tf if peak_tf > 0 else None,
-                         # DRAM bytes of one launch from the committed ncu --set full capture (only quoted at
-                         # the size it was captured at); algorithmic bytes are in "hbm" below
-                         "traffic": (w["traffic"][0] if "traffic" in w and n_vox == w["side"] ** 3 else None),
-                         "traffic_unit": "bytes per launch (dram read + write)",
-                         "traffic_source": (w["traffic"][1] if "traffic" in w and n_vox == w["side"] ** 3 else None),
-                         "algorithmic_bytes_per_launch": bytes_per_launch,
-                         "peak_source": "measured live: dependent-free DFMA loop on all SMs "
-                                        "(MEASURED_PEAKS.json has no FP64 figure)",
-                         "flop_per_voxel_iteration": W, "kernel": ("sp_noise_kernel (+ sp_theta / sp_sweep / sp_ak)" if spatial else "vb_voxelwise_ar_kernel"
-                                    if w["spec"].get("noise") == "ar" else "vb_voxelwise_white_kernel"),
-                         "avg_launch_ms": avg_kernel_s * 1e3,
-                         "hbm": {"achieved": bytes_per_launch / avg_kernel_s / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                                 "frac": bytes_per_launch / avg_kernel_s / 1e9 / hbm_peak,
-                                 "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"}},
-            "iterations_per_voxel": n_iter, "bad_voxels": n_bad,
-        }
+        line = {"metric": metric, "value": rec["value"], "unit": "voxel-iterations/s", "n_gpus": world,
+                "steps": rec["steps"], "warmup": rec["warmup"], "ms_per_step": rec["ms_per_step"],
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic", "config": rec["config"], "e2e": rec["e2e"], "gpu_launches": rec["gpu_launches"],
+                "clocks": rec["clocks"], "roofline": rec["roofline"],
+                "iterations_per_voxel": rec["iterations_per_voxel"], "bad_voxels": rec["bad_voxels"]}
+        if "default_priors" in rec:
+            line["default_priors"] = rec["default_priors"]
         if world == 1 and not args.no_cpu_baseline:
             prate, pdt, pn = oracle_throughput(w, 1, budget_s=8.0)
             if os.path.exists(REF_LIB):
@@ -673,8 +794,13 @@ def main():
                 line["cpu_baseline"] = {"value": prate, "unit": "voxel-iterations/s", "cores": 1, "kind": "port",
                                         "sample": "%d voxels of the same synthetic workload, %.1f s, single thread"
                                         % (pn, pdt)}
+        if subs:
+            line["sub"] = subs
         print(json.dumps(line))
     if world > 1:
+        import torch.distributed as dist
+
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
