@@ -792,251 +792,375 @@ static bool slab_exchange_on_main()
     return !(e && strcmp(e, "side") == 0);
 }
 
+} // extern "C"
+
+namespace fab
+{
+/* own voxels are the positions [own0, own1) of the caller's list: everything else is a ghost */
+__global__ void mark_ghost_range_kernel(const int *order, int N, int own0, int own1, int *status_p)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < N && (order[i] < own0 || order[i] >= own1))
+        status_p[i] = FABBER_VOX_GHOST;
+}
+/* one thread: wait until both ghost planes of this slab hold the neighbours' values of iteration it-1 (the aK
+ * sums of iteration it read them). A kernel of its own, one thread: a full-GPU kernel spinning in every CTA would
+ * keep slabs that share the GPU from ever running the sweep that raises the flag. */
+__global__ void slab_wait_kernel(const unsigned long long *flags, int wait_fwd, int wait_hi, int it, int *error)
+{
+    if (wait_fwd)
+        slab_wait(flags + SLAB_FLAG_FWD, (unsigned long long)it * SLAB_IT_STRIDE, error);
+    if (wait_hi)
+        slab_wait(flags + SLAB_FLAG_HI, (unsigned long long)it, error);
+}
+/* links between two neighbouring slabs, in plane-major positions: for every voxel of the caller's list of the
+ * LOWER slab that is also in the UPPER slab's list (global ids [g0, g1)), lower position <-> upper position */
+__global__ void slab_up_pos_kernel(const int *rank_lo, int v0_lo, const int *rank_hi, int v0_hi, int g0, int g1,
+    int own1_lo /* global */, int *up_pos)
+{
+    const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= g1 || g >= own1_lo)
+        return; /* only the lower slab's OWN voxels forward upwards */
+    up_pos[rank_lo[g - v0_lo]] = rank_hi[g - v0_hi];
+}
+__global__ void slab_dn_list_kernel(const int *rank_hi, int v0_hi, const int *rank_lo, int v0_lo, int g0, int n,
+    int *dn_src, int *dn_dst)
+{
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n)
+        return;
+    const int g = g0 + j; /* own voxels of the upper slab that the lower slab holds as its upper ghosts */
+    dn_src[j] = rank_hi[g - v0_hi];
+    dn_dst[j] = rank_lo[g - v0_lo];
+}
+
+/* One spatial VB run on one device: the state fabber_cuda_vb_spatial_slab used to keep in locals, so that
+ * several of them (one per z-slab / GPU) can be stepped in lock-step by one host thread. */
+struct SpRun
+{
+    int device = 0;
+    cudaStream_t st = nullptr;
+    const fabber_cuda_vb_problem *prob = nullptr;
+    fabber_cuda_vb_buffers buf;
+    SpArgs sp;
+    Staged staged;
+    Scratch *sc = nullptr;
+    const ModelLaunchers *ml = nullptr;
+    int P = 0, N = 0, NT = 0, H = 0, max_it = 0;
+    bool any_spatial = false, any_coupled = false;
+    int *order = nullptr, *rank = nullptr, *status_p = nullptr, *status_prev = nullptr, *its_p = nullptr;
+    float *y_p = nullptr;
+    double *mean_p = nullptr, *cov_p = nullptr, *noise_p = nullptr, *F_p = nullptr, *hist_p = nullptr;
+    unsigned gridN = 0;
+
+    ~SpRun()
+    {
+        if (sc)
+        {
+            cudaSetDevice(device);
+            staged.release(st);
+            delete sc;
+        }
+    }
+    template <class T> T *get(size_t n) { return sc->get<T>(n); }
+
+    /* validation, scratch, neighbours, hyper-plane renumbering, inputs into plane-major order, sp_setup.
+     * Returns FABBER_CUDA_OK with N == 0 handled by the caller. */
+    int prepare(const fabber_cuda_vb_problem *prob_, const fabber_cuda_vb_buffers *buf_, cudaStream_t stream,
+        int n_global)
+    {
+        prob = prob_;
+        buf = *buf_;
+        st = stream;
+        cudaGetDevice(&device);
+        memset(&sp, 0, sizeof(sp));
+        bool general = false;
+        int rc = build_args(prob, &buf, st, sp.v, staged, general);
+        sc = new Scratch(st);
+        if (rc != FABBER_CUDA_OK)
+            return rc;
+        if (prob->noise_type != FABBER_NOISE_WHITE || general)
+            return fail(FABBER_CUDA_ERR_INVALID,
+                "spatial VB kernels support white noise with one phi and no masked time points");
+        P = prob->model.n_params;
+        N = prob->n_voxels;
+        NT = P * (P + 1) / 2;
+        for (int i = 0; i < P; i++)
+        {
+            const char ty = sp.v.params[i].prior_type;
+            if (ty == 'M' || ty == 'm')
+                any_coupled = true;
+            if (ty == 'M' || ty == 'm' || ty == 'P' || ty == 'p')
+                any_spatial = true;
+            else if (ty != 'N' && ty != 'I' && ty != 'A')
+                return fail(FABBER_CUDA_ERR_INVALID, "unknown prior type");
+        }
+        if (prob->spatial_dims < 0 || prob->spatial_dims > 3)
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial-dims must be 0, 1, 2 or 3"); /* priors.cc:191-194 */
+        ml = find_model(prob->model, P);
+        if (!ml)
+            return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
+        if (N == 0)
+            return FABBER_CUDA_OK;
+        if (!buf.coords)
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial VB needs voxel coordinates");
+        const int nx = prob->nx, ny = prob->ny, nz = prob->nz;
+        if (nx <= 0 || ny <= 0 || nz <= 0)
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial VB needs the bounding grid nx, ny, nz");
+        const size_t n_grid = (size_t)nx * ny * nz;
+        const int n_planes = nx + ny + nz;
+        max_it = prob->max_iterations;
+
+        int *grid2vox = get<int>(n_grid), *nn_idx = get<int>((size_t)6 * N), *plane_of = get<int>(N);
+        int *hist = get<int>(n_planes + 1);
+        order = get<int>(N);
+        rank = get<int>(N);
+        int *bad = get<int>(1), *iota = get<int>(N), *plane_sorted = get<int>(N), *nnp = get<int>((size_t)6 * N);
+        int *plane_starts = get<int>(n_planes + 2);
+        sp.centre = get<double>((size_t)P * N);
+        sp.stats = get<double>((size_t)(NT + P + 1) * N);
+        sp.m0 = get<double>((size_t)P * N);
+        sp.L0 = get<double>((size_t)P * N);
+        sp.rhs = get<double>((size_t)P * N);
+        sp.logdet = get<double>(N);
+        sp.aK = get<double>(P);
+        sp.ak_hist = get<double>((size_t)(max_it + 1) * P);
+        sp.ak_partial = get<double>((size_t)SP_AK_BLOCKS * 2 * P);
+        sp.fprior_last = get<double>(1);
+        sp.ak_sums = get<double>(2 * P);
+        sp.n_global = n_global > 0 ? n_global : N;
+        sp.ak_phase = 0;
+        /* the run's inputs and outputs in hyper-plane-major voxel order (see below) */
+        H = sp.v.f_history_len;
+        y_p = get<float>((size_t)prob->n_times * N);
+        mean_p = get<double>((size_t)P * N);
+        cov_p = get<double>((size_t)NT * N);
+        noise_p = get<double>((size_t)2 * N);
+        F_p = get<double>(N);
+        hist_p = get<double>((size_t)H * N);
+        its_p = get<int>(N);
+        status_p = get<int>(N);
+        /* allow-bad-voxels: the status words as they stood when the iteration began (Vb::IgnoreVoxel, see
+         * nbr_alive in vb_spatial.cuh); without it any failure ends the run and the live array serves */
+        status_prev = prob->allow_bad_voxels ? get<int>(N) : status_p;
+        if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !rank || !bad || !iota || !plane_sorted || !nnp
+            || !plane_starts || !sp.centre || !sp.stats || !sp.m0 || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK
+            || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last || !sp.ak_sums || !y_p || !mean_p || !cov_p || !noise_p
+            || !F_p || !hist_p || !its_p || !status_p || !status_prev)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        sp.status_prev = status_prev;
+        sp.ak_blocks = SP_AK_BLOCKS;
+        sp.spatial_dims = prob->spatial_dims;
+        sp.update_first_iter = prob->update_first_iter;
+        sp.any_coupled = any_coupled ? 1 : 0;
+        sp.q1 = prob->spatial_q1;
+        sp.q2 = prob->spatial_q2;
+        sp.speed = prob->spatial_speed;
+
+        /* ---- neighbours (Vb::CalcNeighbours) and the hyper-plane-major renumbering ----------------------
+         * The ordered sweep walks planes x+y+z = h. In the caller's x-fastest order the voxels of a plane are
+         * strided through memory and every access of the sweep is an uncoalesced 8-byte gather (measured:
+         * 64 % of the step). So the whole spatial run works on a renumbered volume: voxels sorted by plane,
+         * original order kept inside a plane (stable radix sort), which makes every per-voxel array access of
+         * every kernel coalesced and keeps the -x/-y/-z neighbours of consecutive voxels consecutive too. The
+         * time-series is permuted once on the way in, the results once on the way out. */
+        cudaMemsetAsync(grid2vox, 0xff, n_grid * sizeof(int), st);
+        cudaMemsetAsync(hist, 0, (n_planes + 1) * sizeof(int), st);
+        cudaMemsetAsync(bad, 0, sizeof(int), st);
+        cudaMemsetAsync(sp.fprior_last, 0, sizeof(double), st);
+        {
+            std::vector<double> ak0(P, 1e-8); /* SpatialPrior::m_aK initial value, priors.cc:185 */
+            cudaMemcpyAsync(sp.aK, ak0.data(), P * sizeof(double), cudaMemcpyHostToDevice, st);
+            cudaStreamSynchronize(st);
+        }
+        gridN = (unsigned)((N + 255) / 256);
+        sp_grid_kernel<<<gridN, 256, 0, st>>>(buf.coords, N, nx, ny, nz, grid2vox, bad);
+        count_launch();
+        {
+            /* nothing below may index by plane or grid cell before the coordinates are known to be inside the
+             * grid: a caller's bad coords must come back as ERR_INVALID, not as an illegal address */
+            int h_bad0 = 0;
+            cudaMemcpyAsync(&h_bad0, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
+            cudaError_t be = cudaStreamSynchronize(st);
+            if (be != cudaSuccess)
+                return cuda_fail(be, "spatial coordinate check");
+            if (h_bad0 == 1)
+                return fail(FABBER_CUDA_ERR_INVALID, "voxel coordinates outside the nx, ny, nz grid");
+            if (h_bad0 == 2)
+                return fail(FABBER_CUDA_ERR_INVALID,
+                    "coordinates must be in increasing order (x fastest, then y, then z), inference_vb.cc:769-793");
+        }
+        sp_neighbour_kernel<<<gridN, 256, 0, st>>>(buf.coords, N, nx, ny, nz, grid2vox, prob->spatial_dims, nn_idx,
+            plane_of, hist);
+        count_launch();
+        iota_kernel<<<gridN, 256, 0, st>>>(iota, N);
+        count_launch();
+        {
+            int bits = 1;
+            while ((1 << bits) <= n_planes)
+                bits++;
+            size_t tmp_bytes = 0;
+            cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plane_of, plane_sorted, iota, order, N, 0, bits, st);
+            void *tmp = get<char>(tmp_bytes);
+            if (!tmp)
+                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+            cudaError_t se = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plane_of, plane_sorted, iota, order, N, 0,
+                bits, st);
+            if (se != cudaSuccess)
+                return cuda_fail(se, "hyper-plane sort");
+            count_launch();
+        }
+        rank_kernel<<<gridN, 256, 0, st>>>(order, N, rank);
+        count_launch();
+        renumber_neighbours_kernel<<<gridN, 256, 0, st>>>(nn_idx, order, rank, N, nnp);
+        count_launch();
+        std::vector<int> h_hist(n_planes + 1), h_begin(n_planes + 2);
+        cudaMemcpyAsync(h_hist.data(), hist, (n_planes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "spatial neighbour set-up");
+        int acc = 0;
+        for (int h = 0; h <= n_planes; h++)
+        {
+            h_begin[h] = acc;
+            acc += h_hist[h];
+        }
+        h_begin[n_planes + 1] = acc;
+        cudaMemcpyAsync(plane_starts, h_begin.data(), (n_planes + 2) * sizeof(int), cudaMemcpyHostToDevice, st);
+        sp.plane_starts = plane_starts;
+        sp.n_planes = n_planes + 1;
+        sp.nn_idx = nnp;
+        sp.order = order;
+
+        /* inputs into plane-major order */
+        permute_rows<float, true>(buf.data, y_p, order, prob->n_times, N, st);
+        sp.v.data = y_p;
+        for (int i = 0; i < P; i++)
+            if (sp.v.image_prior[i])
+            {
+                double *img = get<double>(N);
+                if (!img)
+                    return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+                permute_rows<double, true>(sp.v.image_prior[i], img, order, 1, N, st);
+                sp.v.image_prior[i] = img;
+            }
+        if (sp.v.init_mean)
+        {
+            double *im = get<double>((size_t)P * N), *ic = get<double>((size_t)NT * N);
+            if (!im || !ic)
+                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+            permute_rows<double, true>(sp.v.init_mean, im, order, P, N, st);
+            permute_rows<double, true>(sp.v.init_cov, ic, order, NT, N, st);
+            sp.v.init_mean = im;
+            sp.v.init_cov = ic;
+        }
+        if (sp.v.lock_centre)
+        {
+            double *lc = get<double>((size_t)P * N);
+            if (!lc)
+                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+            permute_rows<double, true>(sp.v.lock_centre, lc, order, P, N, st);
+            sp.v.lock_centre = lc;
+        }
+        if (sp.v.init_noise)
+        {
+            double *in = get<double>((size_t)2 * N);
+            if (!in)
+                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+            permute_rows<double, true>(sp.v.init_noise, in, order, 2, N, st);
+            sp.v.init_noise = in;
+        }
+        sp.v.mean = mean_p;
+        sp.v.cov = cov_p;
+        sp.v.noise = noise_p;
+        sp.v.free_energy = F_p;
+        sp.v.f_history = H > 0 ? hist_p : nullptr;
+        sp.v.iterations = its_p;
+        sp.v.status = status_p;
+        cudaStreamSynchronize(st); /* h_begin is pageable host memory */
+        sp.it = 0;
+        cudaError_t le = ml->sp_setup(sp, st);
+        if (le != cudaSuccess)
+            return cuda_fail(le, "spatial VB sp_setup");
+        return FABBER_CUDA_OK;
+    }
+
+    void snapshot_status()
+    {
+        if (status_prev != status_p)
+            cudaMemcpyAsync(status_prev, status_p, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, st);
+    }
+
+    /* results back into the caller's voxel order; synchronises */
+    int finish()
+    {
+        permute_rows<double, false>(mean_p, buf.mean, order, P, N, st);
+        permute_rows<double, false>(cov_p, buf.cov, order, NT, N, st);
+        permute_rows<double, false>(noise_p, buf.noise, order, 2, N, st);
+        permute_rows<int, false>(status_p, buf.status, order, 1, N, st);
+        if (buf.free_energy)
+            permute_rows<double, false>(F_p, buf.free_energy, order, 1, N, st);
+        if (buf.iterations)
+            permute_rows<int, false>(its_p, buf.iterations, order, 1, N, st);
+        if (H > 0)
+            permute_rows<double, false>(hist_p, buf.f_history, order, H, N, st);
+        if (buf.spatial_ak)
+            cudaMemcpyAsync(buf.spatial_ak, sp.ak_hist, (size_t)(max_it + 1) * P * sizeof(double),
+                cudaMemcpyDeviceToHost, st);
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "spatial VB");
+        return FABBER_CUDA_OK;
+    }
+};
+} // namespace fab
+
+extern "C" {
+
 int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
     const fabber_cuda_slab *slab, void *stream)
 {
     cudaStream_t st = (cudaStream_t)stream;
-    SpArgs sp;
-    memset(&sp, 0, sizeof(sp));
-    Staged staged;
-    bool general = false;
-    int rc = build_args(prob, buf, st, sp.v, staged, general);
-    struct ReleaseStaged
-    {
-        Staged &s;
-        cudaStream_t st;
-        ~ReleaseStaged() { s.release(st); }
-    } rel = { staged, st };
-    if (rc != FABBER_CUDA_OK)
+    if (!prob || !buf)
+        return fail(FABBER_CUDA_ERR_INVALID, "null problem or buffers");
+    if (slab
+        && (!slab->ghost || !slab->allreduce_sum || !slab->exchange || !slab->forward
+            || slab->n_global_voxels < prob->n_voxels || slab->n_blocks < 1 || slab->block_planes < 1 || slab->world < 1
+            || slab->rank < 0 || slab->rank >= slab->world || !slab->fwd_send_start || !slab->fwd_recv_start))
+        return fail(FABBER_CUDA_ERR_INVALID, "incomplete slab description");
+    SpRun R;
+    int rc = R.prepare(prob, buf, st, slab ? slab->n_global_voxels : 0);
+    if (rc != FABBER_CUDA_OK || R.N == 0)
         return rc;
-    if (prob->noise_type != FABBER_NOISE_WHITE || general)
-        return fail(FABBER_CUDA_ERR_INVALID,
-            "spatial VB kernels support white noise with one phi and no masked time points");
-    const int P = prob->model.n_params, N = prob->n_voxels, NT = P * (P + 1) / 2;
-    bool any_spatial = false, any_coupled = false;
-    for (int i = 0; i < P; i++)
-    {
-        const char ty = sp.v.params[i].prior_type;
-        if (ty == 'M' || ty == 'm')
-            any_coupled = true;
-        if (ty == 'M' || ty == 'm' || ty == 'P' || ty == 'p')
-            any_spatial = true;
-        else if (ty != 'N' && ty != 'I' && ty != 'A')
-            return fail(FABBER_CUDA_ERR_INVALID, "unknown prior type");
-    }
-    if (prob->spatial_dims < 0 || prob->spatial_dims > 3)
-        return fail(FABBER_CUDA_ERR_INVALID, "spatial-dims must be 0, 1, 2 or 3"); /* priors.cc:191-194 */
-    const ModelLaunchers *ml = find_model(prob->model, P);
-    if (!ml)
-        return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
-    if (N == 0)
-        return FABBER_CUDA_OK;
-    if (!buf->coords)
-        return fail(FABBER_CUDA_ERR_INVALID, "spatial VB needs voxel coordinates");
-    const int nx = prob->nx, ny = prob->ny, nz = prob->nz;
-    if (nx <= 0 || ny <= 0 || nz <= 0)
-        return fail(FABBER_CUDA_ERR_INVALID, "spatial VB needs the bounding grid nx, ny, nz");
-    const size_t n_grid = (size_t)nx * ny * nz;
-    const int n_planes = nx + ny + nz;
-    const int max_it = prob->max_iterations;
-
-    Scratch sc(st);
-    int *grid2vox = sc.get<int>(n_grid), *nn_idx = sc.get<int>((size_t)6 * N), *plane_of = sc.get<int>(N);
-    int *order = sc.get<int>(N), *hist = sc.get<int>(n_planes + 1), *rank = sc.get<int>(N);
-    int *bad = sc.get<int>(1), *iota = sc.get<int>(N), *plane_sorted = sc.get<int>(N), *nnp = sc.get<int>((size_t)6 * N);
-    int *plane_starts = sc.get<int>(n_planes + 2);
-    sp.centre = sc.get<double>((size_t)P * N);
-    sp.stats = sc.get<double>((size_t)(NT + P + 1) * N);
-    sp.m0 = sc.get<double>((size_t)P * N);
-    sp.L0 = sc.get<double>((size_t)P * N);
-    sp.rhs = sc.get<double>((size_t)P * N);
-    sp.logdet = sc.get<double>(N);
-    sp.aK = sc.get<double>(P);
-    sp.ak_hist = sc.get<double>((size_t)(max_it + 1) * P);
-    sp.ak_partial = sc.get<double>((size_t)SP_AK_BLOCKS * 2 * P);
-    sp.fprior_last = sc.get<double>(1);
-    sp.ak_sums = sc.get<double>(2 * P);
-    sp.n_global = slab ? slab->n_global_voxels : N;
-    sp.ak_phase = 0;
+    SpArgs &sp = R.sp;
+    const ModelLaunchers *ml = R.ml;
+    const int P = R.P, N = R.N, max_it = R.max_it;
+    const bool any_spatial = R.any_spatial, any_coupled = R.any_coupled;
+    double *mean_p = R.mean_p;
+    int *rank = R.rank;
     double *halo_send_lo = nullptr, *halo_send_hi = nullptr, *halo_recv_lo = nullptr, *halo_recv_hi = nullptr;
     double *fwd_send_buf = nullptr, *fwd_recv_buf = nullptr;
     if (slab)
     {
-        if (!slab->ghost || !slab->allreduce_sum || !slab->exchange || !slab->forward || slab->n_global_voxels < N
-            || slab->n_blocks < 1 || slab->block_planes < 1 || slab->world < 1 || slab->rank < 0
-            || slab->rank >= slab->world || !slab->fwd_send_start || !slab->fwd_recv_start)
-            return fail(FABBER_CUDA_ERR_INVALID, "incomplete slab description");
-        halo_send_lo = sc.get<double>((size_t)P * slab->n_send_lo);
-        halo_send_hi = sc.get<double>((size_t)P * slab->n_send_hi);
-        halo_recv_lo = sc.get<double>((size_t)P * slab->n_recv_lo);
-        halo_recv_hi = sc.get<double>((size_t)P * slab->n_recv_hi);
-        if (!halo_send_lo || !halo_send_hi || !halo_recv_lo || !halo_recv_hi || !sp.ak_sums)
-            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        halo_send_lo = R.get<double>((size_t)P * slab->n_send_lo);
+        halo_send_hi = R.get<double>((size_t)P * slab->n_send_hi);
+        halo_recv_lo = R.get<double>((size_t)P * slab->n_recv_lo);
+        halo_recv_hi = R.get<double>((size_t)P * slab->n_recv_hi);
         size_t max_fwd = 1;
         for (int b = 0; b < slab->n_blocks; b++)
         {
             max_fwd = std::max<size_t>(max_fwd, slab->fwd_send_start[b + 1] - slab->fwd_send_start[b]);
             max_fwd = std::max<size_t>(max_fwd, slab->fwd_recv_start[b + 1] - slab->fwd_recv_start[b]);
         }
-        fwd_send_buf = sc.get<double>((size_t)P * max_fwd);
-        fwd_recv_buf = sc.get<double>((size_t)P * max_fwd);
-        if (!fwd_send_buf || !fwd_recv_buf)
+        fwd_send_buf = R.get<double>((size_t)P * max_fwd);
+        fwd_recv_buf = R.get<double>((size_t)P * max_fwd);
+        if (!halo_send_lo || !halo_send_hi || !halo_recv_lo || !halo_recv_hi || !fwd_send_buf || !fwd_recv_buf)
             return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-    }
-    /* the run's inputs and outputs in hyper-plane-major voxel order (see below) */
-    const int H = sp.v.f_history_len;
-    float *y_p = sc.get<float>((size_t)prob->n_times * N);
-    double *mean_p = sc.get<double>((size_t)P * N), *cov_p = sc.get<double>((size_t)NT * N);
-    double *noise_p = sc.get<double>((size_t)2 * N), *F_p = sc.get<double>(N), *hist_p = sc.get<double>((size_t)H * N);
-    int *its_p = sc.get<int>(N), *status_p = sc.get<int>(N);
-    /* allow-bad-voxels: the status words as they stood when the iteration began (Vb::IgnoreVoxel, see
-     * nbr_alive in vb_spatial.cuh); without it any failure ends the run and the live array serves */
-    int *status_prev = prob->allow_bad_voxels ? sc.get<int>(N) : status_p;
-    if (!status_prev)
-        return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-    sp.status_prev = status_prev;
-    if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !rank || !bad || !iota || !plane_sorted || !nnp
-        || !plane_starts || !sp.centre || !sp.stats || !sp.m0 || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK
-        || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last || !y_p || !mean_p || !cov_p || !noise_p || !F_p || !hist_p
-        || !its_p || !status_p)
-        return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-    sp.ak_blocks = SP_AK_BLOCKS;
-    sp.spatial_dims = prob->spatial_dims;
-    sp.update_first_iter = prob->update_first_iter;
-    sp.any_coupled = any_coupled ? 1 : 0;
-    sp.q1 = prob->spatial_q1;
-    sp.q2 = prob->spatial_q2;
-    sp.speed = prob->spatial_speed;
-
-    /* ---- neighbours (Vb::CalcNeighbours) and the hyper-plane-major renumbering ----------------------
-     * The ordered sweep walks planes x+y+z = h. In the caller's x-fastest order the voxels of a plane are
-     * strided through memory and every access of the sweep is an uncoalesced 8-byte gather (measured:
-     * 64 % of the step). So the whole spatial run works on a renumbered volume: voxels sorted by plane,
-     * original order kept inside a plane (stable radix sort), which makes every per-voxel array access of
-     * every kernel coalesced and keeps the -x/-y/-z neighbours of consecutive voxels consecutive too. The
-     * time-series is permuted once on the way in, the results once on the way out. */
-    cudaMemsetAsync(grid2vox, 0xff, n_grid * sizeof(int), st);
-    cudaMemsetAsync(hist, 0, (n_planes + 1) * sizeof(int), st);
-    cudaMemsetAsync(bad, 0, sizeof(int), st);
-    cudaMemsetAsync(sp.fprior_last, 0, sizeof(double), st);
-    {
-        std::vector<double> ak0(P, 1e-8); /* SpatialPrior::m_aK initial value, priors.cc:185 */
-        cudaMemcpyAsync(sp.aK, ak0.data(), P * sizeof(double), cudaMemcpyHostToDevice, st);
-        cudaStreamSynchronize(st);
-    }
-    const unsigned gridN = (unsigned)((N + 255) / 256);
-    sp_grid_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, bad);
-    count_launch();
-    {
-        /* nothing below may index by plane or grid cell before the coordinates are known to be inside the
-         * grid: a caller's bad coords must come back as ERR_INVALID, not as an illegal address */
-        int h_bad0 = 0;
-        cudaMemcpyAsync(&h_bad0, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
-        cudaError_t be = cudaStreamSynchronize(st);
-        if (be != cudaSuccess)
-            return cuda_fail(be, "spatial coordinate check");
-        if (h_bad0 == 1)
-            return fail(FABBER_CUDA_ERR_INVALID, "voxel coordinates outside the nx, ny, nz grid");
-        if (h_bad0 == 2)
-            return fail(FABBER_CUDA_ERR_INVALID,
-                "coordinates must be in increasing order (x fastest, then y, then z), inference_vb.cc:769-793");
-    }
-    sp_neighbour_kernel<<<gridN, 256, 0, st>>>(buf->coords, N, nx, ny, nz, grid2vox, prob->spatial_dims, nn_idx,
-        plane_of, hist);
-    count_launch();
-    iota_kernel<<<gridN, 256, 0, st>>>(iota, N);
-    count_launch();
-    {
-        int bits = 1;
-        while ((1 << bits) <= n_planes)
-            bits++;
-        size_t tmp_bytes = 0;
-        cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plane_of, plane_sorted, iota, order, N, 0, bits, st);
-        void *tmp = sc.get<char>(tmp_bytes);
-        if (!tmp)
-            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-        cudaError_t se = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plane_of, plane_sorted, iota, order, N, 0, bits, st);
-        if (se != cudaSuccess)
-            return cuda_fail(se, "hyper-plane sort");
+        mark_ghosts_kernel<<<R.gridN, 256, 0, st>>>(slab->ghost, R.order, N, R.status_p);
         count_launch();
     }
-    rank_kernel<<<gridN, 256, 0, st>>>(order, N, rank);
-    count_launch();
-    renumber_neighbours_kernel<<<gridN, 256, 0, st>>>(nn_idx, order, rank, N, nnp);
-    count_launch();
-    std::vector<int> h_hist(n_planes + 1), h_begin(n_planes + 2);
-    int h_bad = 0;
-    cudaMemcpyAsync(h_hist.data(), hist, (n_planes + 1) * sizeof(int), cudaMemcpyDeviceToHost, st);
-    cudaMemcpyAsync(&h_bad, bad, sizeof(int), cudaMemcpyDeviceToHost, st);
-    cudaError_t e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess)
-        return cuda_fail(e, "spatial neighbour set-up");
-    if (h_bad == 1)
-        return fail(FABBER_CUDA_ERR_INVALID, "voxel coordinates outside the nx, ny, nz grid");
-    if (h_bad == 2)
-        return fail(FABBER_CUDA_ERR_INVALID,
-            "coordinates must be in increasing order (x fastest, then y, then z), inference_vb.cc:769-793");
-    int acc = 0;
-    for (int h = 0; h <= n_planes; h++)
-    {
-        h_begin[h] = acc;
-        acc += h_hist[h];
-    }
-    h_begin[n_planes + 1] = acc;
-    cudaMemcpyAsync(plane_starts, h_begin.data(), (n_planes + 2) * sizeof(int), cudaMemcpyHostToDevice, st);
-    sp.plane_starts = plane_starts;
-    sp.n_planes = n_planes + 1;
-    sp.nn_idx = nnp;
-    sp.order = order;
 
-    /* inputs into plane-major order */
-    permute_rows<float, true>(buf->data, y_p, order, prob->n_times, N, st);
-    sp.v.data = y_p;
-    for (int i = 0; i < P; i++)
-        if (sp.v.image_prior[i])
-        {
-            double *img = sc.get<double>(N);
-            if (!img)
-                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-            permute_rows<double, true>(sp.v.image_prior[i], img, order, 1, N, st);
-            sp.v.image_prior[i] = img;
-        }
-    if (sp.v.init_mean)
-    {
-        double *im = sc.get<double>((size_t)P * N), *ic = sc.get<double>((size_t)NT * N);
-        if (!im || !ic)
-            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-        permute_rows<double, true>(sp.v.init_mean, im, order, P, N, st);
-        permute_rows<double, true>(sp.v.init_cov, ic, order, NT, N, st);
-        sp.v.init_mean = im;
-        sp.v.init_cov = ic;
-    }
-    if (sp.v.lock_centre)
-    {
-        double *lc = sc.get<double>((size_t)P * N);
-        if (!lc)
-            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-        permute_rows<double, true>(sp.v.lock_centre, lc, order, P, N, st);
-        sp.v.lock_centre = lc;
-    }
-    if (sp.v.init_noise)
-    {
-        double *in = sc.get<double>((size_t)2 * N);
-        if (!in)
-            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
-        permute_rows<double, true>(sp.v.init_noise, in, order, 2, N, st);
-        sp.v.init_noise = in;
-    }
-    sp.v.mean = mean_p;
-    sp.v.cov = cov_p;
-    sp.v.noise = noise_p;
-    sp.v.free_energy = F_p;
-    sp.v.f_history = H > 0 ? hist_p : nullptr;
-    sp.v.iterations = its_p;
-    sp.v.status = status_p;
-    cudaStreamSynchronize(st); /* h_begin is pageable host memory */
-
-    /* ---- set-up, then the iteration-major loop ------------------------------------------------- */
+    /* ---- the iteration-major loop --------------------------------------------------------------- */
 #define FAB_SP_LAUNCH(fn)                                \
     do                                                   \
     {                                                    \
@@ -1044,13 +1168,6 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
         if (le != cudaSuccess)                           \
             return cuda_fail(le, "spatial VB " #fn);     \
     } while (0)
-    sp.it = 0;
-    FAB_SP_LAUNCH(sp_setup);
-    if (slab)
-    {
-        mark_ghosts_kernel<<<gridN, 256, 0, st>>>(slab->ghost, order, N, status_p);
-        count_launch();
-    }
     /* z-slab mode: the aK sums of iteration it+1 depend on the means and covariances as the sweep and the halo
      * exchange of iteration it leave them - sp_noise does not touch either. The slabs finish their sweeps
      * staggered (slab r starts r * nz_local hyper-planes after slab 0), so an all-reduce in front of the next
@@ -1115,8 +1232,7 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
             FAB_SP_LAUNCH(sp_ak_partial);
         FAB_SP_LAUNCH(sp_ak_final);
         sp.ak_phase = 0;
-        if (status_prev != status_p)
-            cudaMemcpyAsync(status_prev, status_p, (size_t)N * sizeof(int), cudaMemcpyDeviceToDevice, st);
+        R.snapshot_status();
         FAB_SP_LAUNCH(sp_theta);
         sp.plane_first = 0;
         sp.plane_last = sp.n_planes;
@@ -1221,24 +1337,248 @@ int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber
     sp.ak_update = 0;
     FAB_SP_LAUNCH(sp_ak_final);
 #undef FAB_SP_LAUNCH
-    /* results back into the caller's voxel order */
-    permute_rows<double, false>(mean_p, buf->mean, order, P, N, st);
-    permute_rows<double, false>(cov_p, buf->cov, order, NT, N, st);
-    permute_rows<double, false>(noise_p, buf->noise, order, 2, N, st);
-    permute_rows<int, false>(status_p, buf->status, order, 1, N, st);
-    if (buf->free_energy)
-        permute_rows<double, false>(F_p, buf->free_energy, order, 1, N, st);
-    if (buf->iterations)
-        permute_rows<int, false>(its_p, buf->iterations, order, 1, N, st);
-    if (H > 0)
-        permute_rows<double, false>(hist_p, buf->f_history, order, H, N, st);
-    if (buf->spatial_ak)
-        cudaMemcpyAsync(buf->spatial_ak, sp.ak_hist, (size_t)(max_it + 1) * P * sizeof(double),
-            cudaMemcpyDeviceToHost, st);
-    e = cudaStreamSynchronize(st);
-    if (e != cudaSuccess)
-        return cuda_fail(e, "spatial VB");
-    return FABBER_CUDA_OK;
+    return R.finish();
+}
+
+/* ---- device-driven z-slabs: ONE process, one slab per part, kernels coupled through peer memory ---------- */
+int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts, const fabber_cuda_slab_part *parts)
+{
+    if (!prob || !parts || n_parts < 1 || n_parts > SLAB_MAX_WORLD)
+        return fail(FABBER_CUDA_ERR_INVALID, "spatial multi: 1..16 parts");
+    int prev_dev = 0;
+    cudaGetDevice(&prev_dev);
+    struct Restore
+    {
+        int dev;
+        ~Restore() { cudaSetDevice(dev); }
+    } restore = { prev_dev };
+    if (n_parts == 1)
+    {
+        cudaSetDevice(parts[0].device);
+        fabber_cuda_vb_problem p1 = *prob;
+        p1.n_voxels = parts[0].v1 - parts[0].v0;
+        return fabber_cuda_vb_spatial(&p1, &parts[0].buf, nullptr);
+    }
+    const int W = n_parts;
+    const int n_global = prob->n_voxels;
+    for (int r = 0; r < W; r++)
+    {
+        const fabber_cuda_slab_part &pt = parts[r];
+        if (pt.v0 < 0 || pt.v1 > n_global || pt.own0 < pt.v0 || pt.own1 > pt.v1 || pt.own0 >= pt.own1
+            || pt.own_z0 >= pt.own_z1)
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial multi: bad part ranges");
+        if (r > 0 && (pt.own0 != parts[r - 1].own1 || pt.v0 > parts[r - 1].own1 || pt.own_z0 != parts[r - 1].own_z1))
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial multi: parts must tile the voxel list in order");
+        if (r + 1 < W && pt.v1 < pt.own1)
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial multi: bad part ranges");
+    }
+    if (parts[0].own0 != 0 || parts[W - 1].own1 != n_global)
+        return fail(FABBER_CUDA_ERR_INVALID, "spatial multi: parts must cover the whole voxel list");
+    /* peer access between neighbouring devices (and all-to-all for the aK mailboxes) */
+    int ranks_on_device[64] = { 0 };
+    for (int r = 0; r < W; r++)
+    {
+        if (parts[r].device < 0 || parts[r].device >= 64)
+            return fail(FABBER_CUDA_ERR_INVALID, "spatial multi: bad device ordinal");
+        ranks_on_device[parts[r].device]++;
+    }
+    for (int r = 0; r < W; r++)
+        for (int q = 0; q < W; q++)
+            if (parts[r].device != parts[q].device)
+            {
+                int can = 0;
+                cudaDeviceCanAccessPeer(&can, parts[r].device, parts[q].device);
+                if (!can)
+                    return fail(FABBER_CUDA_ERR_CUDA, "spatial multi: the devices cannot access each other's memory");
+                cudaSetDevice(parts[r].device);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(parts[q].device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                    return cuda_fail(pe, "cudaDeviceEnablePeerAccess");
+                cudaGetLastError();
+            }
+    std::vector<SpRun> runs(W);
+    std::vector<fabber_cuda_vb_problem> probs(W, *prob);
+    std::vector<cudaStream_t> streams(W, nullptr);
+    struct Streams
+    {
+        std::vector<cudaStream_t> &s;
+        const fabber_cuda_slab_part *parts;
+        ~Streams()
+        {
+            for (size_t i = 0; i < s.size(); i++)
+                if (s[i])
+                {
+                    cudaSetDevice(parts[i].device);
+                    cudaStreamDestroy(s[i]);
+                }
+        }
+    } stream_guard = { streams, parts };
+    for (int r = 0; r < W; r++)
+    {
+        cudaSetDevice(parts[r].device);
+        cudaError_t se = cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking);
+        if (se != cudaSuccess)
+            return cuda_fail(se, "spatial multi: stream");
+        probs[r].n_voxels = parts[r].v1 - parts[r].v0;
+        int rc = runs[r].prepare(&probs[r], &parts[r].buf, streams[r], n_global);
+        if (rc != FABBER_CUDA_OK)
+            return rc;
+    }
+    const int P = runs[0].P, max_it = runs[0].max_it;
+    const bool any_spatial = runs[0].any_spatial, any_coupled = runs[0].any_coupled;
+    /* flags, mailboxes, error word, neighbour links */
+    std::vector<unsigned long long *> flags(W);
+    std::vector<double *> mail(W);
+    std::vector<int *> err(W);
+    for (int r = 0; r < W; r++)
+    {
+        SpRun &R = runs[r];
+        cudaSetDevice(parts[r].device);
+        flags[r] = R.get<unsigned long long>(SLAB_FLAG_MAIL + SLAB_MAX_WORLD);
+        mail[r] = R.get<double>((size_t)2 * W * 2 * P);
+        err[r] = R.get<int>(1);
+        int *up_pos = R.get<int>(R.N);
+        if (!flags[r] || !mail[r] || !err[r] || !up_pos)
+            return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+        cudaMemsetAsync(flags[r], 0, (SLAB_FLAG_MAIL + SLAB_MAX_WORLD) * sizeof(unsigned long long), R.st);
+        cudaMemsetAsync(mail[r], 0, (size_t)2 * W * 2 * P * sizeof(double), R.st);
+        cudaMemsetAsync(err[r], 0, sizeof(int), R.st);
+        cudaMemsetAsync(up_pos, 0xff, (size_t)R.N * sizeof(int), R.st);
+        mark_ghost_range_kernel<<<R.gridN, 256, 0, R.st>>>(R.order, R.N, parts[r].own0 - parts[r].v0,
+            parts[r].own1 - parts[r].v0, R.status_p);
+        count_launch();
+        SlabLinks &lk = R.sp.link;
+        lk.world = W;
+        lk.rank = r;
+        lk.own_z0 = parts[r].own_z0;
+        lk.own_z1 = parts[r].own_z1;
+        lk.inplane_span = (prob->spatial_dims >= 3 || prob->spatial_dims == 0) ? prob->nx + prob->ny - 2
+                                                                              : prob->nx + prob->ny - 2;
+        lk.flags = flags[r];
+        lk.error = err[r];
+        lk.up_pos = (r + 1 < W) ? up_pos : nullptr;
+        /* small slabs: planes hold few voxels, and the grid-wide barrier gets cheaper with every CTA less; ranks
+         * that share a device (tests on one GPU) must all be co-resident, they spin on each other's flags */
+        R.sp.sweep_share = ranks_on_device[parts[r].device];
+        /* a slab's hyper-planes hold at most nx * ny voxels... and far fewer CTAs make the barrier cheaper */
+        {
+            const long long widest = (long long)prob->nx * prob->ny;
+            R.sp.sweep_max_ctas = (int)std::max<long long>(8, std::min<long long>(1 << 20, (widest + SP_SWEEP_BLOCK - 1) / SP_SWEEP_BLOCK));
+        }
+    }
+    for (int r = 0; r < W; r++)
+        cudaStreamSynchronize(streams[r]); /* rank[] tables are read across devices below */
+    for (int r = 0; r < W; r++)
+    {
+        SpRun &R = runs[r];
+        SlabLinks &lk = R.sp.link;
+        cudaSetDevice(parts[r].device);
+        for (int q = 0; q < W; q++)
+        {
+            lk.mail[q] = mail[q];
+            lk.mail_flags[q] = flags[q];
+        }
+        if (r + 1 < W)
+        {
+            /* our own voxels that the slab above also holds (its lower ghosts): global ids [v0_up, own0_up) */
+            const fabber_cuda_slab_part &up = parts[r + 1];
+            lk.up_flags = flags[r + 1];
+            lk.up_mean = runs[r + 1].mean_p;
+            lk.up_N = runs[r + 1].N;
+            const int g0 = std::max(up.v0, parts[r].own0), g1 = up.own0;
+            if (g1 > g0)
+            {
+                slab_up_pos_kernel<<<(g1 - g0 + 255) / 256, 256, 0, R.st>>>(R.rank, parts[r].v0, runs[r + 1].rank, up.v0,
+                    g0, g1, parts[r].own1, const_cast<int *>(lk.up_pos));
+                count_launch();
+            }
+        }
+        if (r > 0)
+        {
+            /* our own voxels that the slab below also holds (its upper ghosts): global ids [own0, v1_dn) */
+            const fabber_cuda_slab_part &dn = parts[r - 1];
+            lk.dn_flags = flags[r - 1];
+            lk.dn_mean = runs[r - 1].mean_p;
+            lk.dn_N = runs[r - 1].N;
+            const int g0 = parts[r].own0, n_dn = std::max(0, std::min(dn.v1, parts[r].own1) - g0);
+            int *dn_src = R.get<int>(n_dn), *dn_dst = R.get<int>(n_dn);
+            if (!dn_src || !dn_dst)
+                return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
+            if (n_dn > 0)
+            {
+                slab_dn_list_kernel<<<(n_dn + 255) / 256, 256, 0, R.st>>>(R.rank, parts[r].v0, runs[r - 1].rank, dn.v0, g0,
+                    n_dn, dn_src, dn_dst);
+                count_launch();
+            }
+            lk.dn_src = dn_src;
+            lk.dn_dst = dn_dst;
+            lk.n_dn = n_dn;
+        }
+    }
+    for (int r = 0; r < W; r++)
+        cudaStreamSynchronize(streams[r]);
+
+    /* ---- the iteration-major loop: every launch is asynchronous; the slabs order themselves through the flags
+     * in each other's memory, the host only queues work ---------------------------------------------------- */
+    for (int it = 0; it < max_it; it++)
+        for (int r = 0; r < W; r++)
+        {
+            SpRun &R = runs[r];
+            SpArgs &sp = R.sp;
+            cudaSetDevice(parts[r].device);
+            cudaError_t le = cudaSuccess;
+            sp.it = it;
+            sp.ak_update = (any_spatial && (it > 0 || prob->update_first_iter)) ? 1 : 0;
+            sp.ak_phase = 3;
+            if (sp.ak_update)
+            {
+                if (it > 0)
+                {
+                    slab_wait_kernel<<<1, 1, 0, R.st>>>(flags[r], r > 0, r + 1 < W, it, err[r]);
+                    count_launch();
+                }
+                le = R.ml->sp_ak_partial(sp, R.st);
+            }
+            if (le == cudaSuccess)
+                le = R.ml->sp_ak_final(sp, R.st);
+            R.snapshot_status();
+            if (le == cudaSuccess)
+                le = R.ml->sp_theta(sp, R.st);
+            /* the sweep kernel also carries the slab coupling (forwarding, halo, flags): it runs even when no
+             * parameter needs the ordered sweep, then with an empty plane range */
+            sp.plane_first = 0;
+            sp.plane_last = any_coupled ? sp.n_planes : 0;
+            if (le == cudaSuccess)
+                le = R.ml->sp_sweep(sp, R.st);
+            if (le == cudaSuccess)
+                le = R.ml->sp_noise(sp, R.st);
+            if (le != cudaSuccess)
+                return cuda_fail(le, "spatial VB (multi-device) launch");
+        }
+    int rc = FABBER_CUDA_OK;
+    for (int r = 0; r < W; r++)
+    {
+        SpRun &R = runs[r];
+        cudaSetDevice(parts[r].device);
+        R.sp.it = max_it;
+        R.sp.ak_update = 0;
+        R.sp.ak_phase = 0;
+        cudaError_t le = R.ml->sp_ak_final(R.sp, R.st);
+        if (le != cudaSuccess)
+            return cuda_fail(le, "spatial VB (multi-device) launch");
+    }
+    for (int r = 0; r < W; r++)
+    {
+        cudaSetDevice(parts[r].device);
+        const int frc = runs[r].finish();
+        if (frc != FABBER_CUDA_OK && rc == FABBER_CUDA_OK)
+            rc = frc;
+        int h_err = 0;
+        cudaMemcpy(&h_err, err[r], sizeof(int), cudaMemcpyDeviceToHost);
+        if (h_err && rc == FABBER_CUDA_OK)
+            rc = fail(FABBER_CUDA_ERR_CUDA, "spatial multi: a slab timed out waiting for its neighbour");
+    }
+    return rc;
 }
 
 int fabber_cuda_check_status(const int *status, int n_voxels, int *first_bad_voxel, int *first_bad_code, void *stream)

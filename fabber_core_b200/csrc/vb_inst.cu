@@ -121,7 +121,7 @@ static cudaError_t launch_sp_theta(const SpArgs &s, cudaStream_t st)
 static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
 {
     /* persistent cooperative kernel: as many CTAs as can be co-resident (grid-wide barrier inside) */
-    static int grid = 0;
+    static int grid = 0, max_grid = 0;
     auto kern = sp_sweep_kernel<M::P>;
     if (grid == 0)
     {
@@ -138,10 +138,16 @@ static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
             want = atoi(env);
         if (want < 1)
             want = 1;
+        max_grid = sms * per_sm;
         grid = sms * (per_sm > want ? want : per_sm);
     }
+    int launch_grid = grid;
+    if (s.sweep_share > 1 && max_grid / s.sweep_share < launch_grid)
+        launch_grid = max_grid / s.sweep_share > 0 ? max_grid / s.sweep_share : 1;
+    if (s.sweep_max_ctas > 0 && s.sweep_max_ctas < launch_grid)
+        launch_grid = s.sweep_max_ctas;
     void *args[] = { (void *)&s };
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3(grid), dim3(SP_SWEEP_BLOCK), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3(launch_grid), dim3(SP_SWEEP_BLOCK), args, 0, st);
     count_launch();
     return e;
 }

@@ -37,6 +37,75 @@
 
 namespace fab
 {
+/* ---- device-driven z-slab coupling (fabber_cuda_vb_spatial_multi) ----------------------------------------
+ * One volume, cut into z-slabs over several GPUs. Each slab's kernels talk to the neighbouring slabs' memory
+ * DIRECTLY (peer access over NVLink): no host callback, no separate pack / send / receive / unpack step.
+ *   forward   the ordered sweep of slab r stores the fresh mean of every voxel of its TOP own plane straight
+ *             into slab r+1's lower ghost voxel, and after the grid-wide barrier of hyper-plane H publishes
+ *             "planes <= H done" in r+1's FWD flag (st.release.sys); slab r+1 spins on that flag
+ *             (ld.acquire.sys) before it finishes hyper-plane H+1 - the exact Gauss-Seidel order across slabs
+ *             with ONE hyper-plane of skew.
+ *   halo      at the end of its sweep slab r stores its BOTTOM own plane into slab r-1's upper ghost voxels
+ *             and bumps r-1's HI flag (the upper ghost must stay one iteration old during the sweep).
+ *   aK sums   every slab writes its partial sums of CalculateaK into EVERY slab's mailbox, raises that slab's
+ *             mail flag, waits for all its own flags and adds the world's partials in rank order: an
+ *             all-gather fused into sp_ak_final, bit-identical on every slab.
+ * Flags only ever grow (iteration number folded in), mailboxes are double-buffered by iteration parity; every
+ * spin has a cycle budget and reports through `error` instead of hanging the GPU. */
+constexpr int SLAB_MAX_WORLD = 16;
+constexpr unsigned long long SLAB_IT_STRIDE = 1ull << 20; /* FWD flag = it * stride + hyper-planes done */
+enum
+{
+    SLAB_FLAG_FWD = 0, /* written by the slab below */
+    SLAB_FLAG_HI = 1,  /* written by the slab above: iterations whose bottom plane has been published */
+    SLAB_FLAG_MAIL = 2 /* [SLAB_FLAG_MAIL + q]: written by slab q: aK iterations mailed */
+};
+struct SlabLinks
+{
+    int world, rank; /* world == 0: not a slab run */
+    int own_z0, own_z1, inplane_span; /* own z-planes [own_z0, own_z1); nx + ny - 2 restricted by spatial_dims */
+    unsigned long long *flags;        /* this slab's flag block */
+    unsigned long long *up_flags, *dn_flags; /* the neighbours' (peer memory), NULL at the ends */
+    double *up_mean; /* slab r+1's mean array [P][up_N] (peer memory) */
+    int up_N;
+    const int *up_pos; /* [N]: position in slab r+1 of the same voxel (its lower ghost), -1 = none */
+    double *dn_mean;   /* slab r-1's mean array [P][dn_N] (peer memory) */
+    int dn_N;
+    const int *dn_src, *dn_dst; /* [n_dn]: own bottom-plane position -> position in slab r-1 (its upper ghost) */
+    int n_dn;
+    double *mail[SLAB_MAX_WORLD]; /* every slab's mailbox [2][world][2P] (peer memory; own included) */
+    unsigned long long *mail_flags[SLAB_MAX_WORLD]; /* every slab's flag block */
+    int *error; /* set to 1 when a spin ran out of budget */
+};
+
+FAB_DEV unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+FAB_DEV void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+/* spin until *flag >= want; ~2 s budget (a dead peer must not hang the GPU: gpurun counts that as a strike) */
+FAB_DEV void slab_wait(const unsigned long long *flag, unsigned long long want, int *error)
+{
+    const long long t0 = clock64();
+    while (ld_acquire_sys(flag) < want)
+    {
+        /* once any wait of this slab has given up, none waits again: the run is lost, end it quickly */
+        if (*(volatile int *)error != 0)
+            break;
+        if (clock64() - t0 > 4000000000ll)
+        {
+            atomicExch(error, 1);
+            break;
+        }
+        __nanosleep(64);
+    }
+}
+
 struct SpArgs
 {
     VbArgs v;
@@ -67,6 +136,10 @@ struct SpArgs
     /* [N] status words as they were when this iteration began (== v.status unless allow_bad_voxels): which
      * neighbours Vb::IgnoreVoxel had already struck from the lists, see nbr_alive() */
     const int *status_prev;
+    SlabLinks link;     /* link.world == 0 on one GPU and in the host-callback slab mode */
+    int sweep_max_ctas; /* > 0: cap on the cooperative sweep grid (small slabs: the barrier gets cheaper) */
+    int sweep_share;    /* > 1: that many slabs share this GPU and spin on each other's flags - each sweep grid is
+                           held to 1/share of what the GPU can keep resident, so that all of them fit */
     double q1, q2, speed;
 };
 
@@ -169,6 +242,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
 {
     const VbArgs &a = s.v;
     const size_t N = (size_t)a.N;
+    /* (slab mode: the host queues slab_wait_kernel in front of this kernel - the sums read the ghost planes) */
     double tr[P], t2[P];
 #pragma unroll
     for (int k = 0; k < P; k++)
@@ -207,7 +281,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
 #pragma unroll
             for (int j = 0; j < 6; j++)
                 if (nbr[j] >= 0)
-                    SwK += wK - a.mean[k * N + nbr[j]];
+                    SwK += wK - __ldcg(a.mean + k * N + nbr[j]); /* ghosts are written by a peer GPU */
             if (ty == 'p' || ty == 'm')
                 SwK += wK * (dims * 2 - (double)nn);
             if (ty == 'm' || ty == 'M')
@@ -280,6 +354,32 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
         if (s.ak_update && threadIdx.x < 2 * P)
             s.ak_sums[threadIdx.x] = sums[threadIdx.x];
         return;
+    }
+    if (s.ak_update && s.ak_phase == 3)
+    {
+        /* device-driven slab mode: all-gather of the partial sums through the slabs' mailboxes, then the
+         * same fixed-order sum on every slab (priors.cc:233-343: two global sums per spatial parameter) */
+        const int W = s.link.world, me = s.link.rank, slot = s.it & 1;
+        if (threadIdx.x < 2 * P * W)
+        {
+            const int q = threadIdx.x / (2 * P), j = threadIdx.x - q * 2 * P;
+            s.link.mail[q][((size_t)slot * W + me) * 2 * P + j] = sums[j];
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < W)
+            st_release_sys(s.link.mail_flags[threadIdx.x] + SLAB_FLAG_MAIL + me, (unsigned long long)s.it + 1);
+        if (threadIdx.x < W)
+            slab_wait(s.link.flags + SLAB_FLAG_MAIL + threadIdx.x, (unsigned long long)s.it + 1, s.link.error);
+        __syncthreads();
+        if (threadIdx.x < 2 * P)
+        {
+            double x = 0.0;
+            for (int q = 0; q < W; q++)
+                x += __ldcg(s.link.mail[me] + ((size_t)slot * W + q) * 2 * P + threadIdx.x);
+            sums[threadIdx.x] = x;
+        }
+        __syncthreads();
     }
     const int k = threadIdx.x;
     if (k >= P)
@@ -509,6 +609,19 @@ template <int P> struct SweepVoxel
 #pragma unroll
         for (int i = 0; i < P; i++)
             __stcg(a.mean + i * N + v, mn[i]);
+        if (s.link.up_pos)
+        {
+            /* top own plane of a z-slab: the slab above sweeps this voxel's +z neighbour one hyper-plane later
+             * and must see THIS sweep's value - store it straight into that slab's lower ghost voxel */
+            const int up = s.link.up_pos[v];
+            if (up >= 0)
+            {
+#pragma unroll
+                for (int i = 0; i < P; i++)
+                    s.link.up_mean[(size_t)i * s.link.up_N + up] = mn[i];
+                __threadfence_system(); /* ordered before this plane's barrier and the flag behind it */
+            }
+        }
     }
 };
 
@@ -517,6 +630,17 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const SlabLinks &lk = s.link;
+    const bool slab = lk.world > 1;
+    const bool has_dn = slab && lk.rank > 0, has_up = slab && lk.rank + 1 < lk.world;
+    const unsigned long long fwd_base = (unsigned long long)s.it * SLAB_IT_STRIDE;
+    if (has_up)
+    {
+        /* the upper ghost plane must hold the slab above's values of the PREVIOUS iteration */
+        if (threadIdx.x == 0)
+            slab_wait(lk.flags + SLAB_FLAG_HI, (unsigned long long)s.it, lk.error);
+        __syncthreads();
+    }
     SweepVoxel<P> cur;
     bool have = false;
     if (s.plane_first < s.plane_last)
@@ -531,6 +655,15 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
     for (int h = s.plane_first; h < s.plane_last; h++)
     {
         const int b = s.plane_starts[h], e = s.plane_starts[h + 1];
+        /* slab mode works on GLOBAL coordinates: local plane h IS hyper-plane x+y+z = h of the whole volume.
+         * Its voxels on the bottom own plane (z = own_z0) have their -z neighbour in the slab below, on
+         * hyper-plane h-1: wait until that slab has published it. */
+        if (has_dn && e > b && h >= lk.own_z0 && h <= lk.own_z0 + lk.inplane_span)
+        {
+            if (threadIdx.x == 0)
+                slab_wait(lk.flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h, lk.error);
+            __syncthreads();
+        }
         if (have)
             cur.finish(s);
         for (int i = b + tid + stride; i < e; i += stride) /* planes wider than the grid */
@@ -551,6 +684,52 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
         }
         if (e > b) /* uniform across the grid: every thread skips the same empty planes */
             grid.sync();
+        /* hyper-plane h is done everywhere on this GPU: tell the slab above (only the planes that hold voxels of
+         * the top own plane z = own_z1 - 1 matter to it) */
+        if (has_up && tid == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span)
+        {
+            __threadfence_system();
+            st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h + 1);
+        }
+    }
+    if (!slab)
+        return;
+    /* ---- end of the sweep ------------------------------------------------------------------------------
+     * (a) no ordered sweep in this run (no 'M' / 'm' parameter): the means were written by sp_theta; the slab
+     *     above still needs this iteration's values of our top plane for its aK sums */
+    if (has_up && s.plane_first >= s.plane_last)
+    {
+        const size_t N = (size_t)s.v.N;
+        for (int v = tid; v < s.v.N; v += stride)
+        {
+            const int up = lk.up_pos[v];
+            if (up >= 0)
+                for (int i = 0; i < P; i++)
+                    lk.up_mean[(size_t)i * lk.up_N + up] = __ldcg(s.v.mean + i * N + v);
+        }
+    }
+    /* (b) our bottom own plane becomes the slab below's upper ghost - only now: during its own sweep that slab
+     *     had to see last iteration's values, and it finished the planes that read them before we could finish
+     *     ours (we waited for its flag plane by plane) */
+    if (has_dn)
+    {
+        const size_t N = (size_t)s.v.N;
+        for (int j = tid; j < lk.n_dn; j += stride)
+        {
+            const int src = lk.dn_src[j], dst = lk.dn_dst[j];
+            for (int i = 0; i < P; i++)
+                lk.dn_mean[(size_t)i * lk.dn_N + dst] = __ldcg(s.v.mean + i * N + src);
+        }
+    }
+    __threadfence_system();
+    grid.sync();
+    if (tid == 0)
+    {
+        __threadfence_system();
+        if (has_up) /* everything up to the last hyper-plane is forwarded: releases the next iteration's waits */
+            st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + SLAB_IT_STRIDE);
+        if (has_dn)
+            st_release_sys(lk.dn_flags + SLAB_FLAG_HI, (unsigned long long)s.it + 1);
     }
 }
 

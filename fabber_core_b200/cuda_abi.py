@@ -109,6 +109,16 @@ class VbBuffers(C.Structure):
     ]
 
 
+class SlabPart(C.Structure):
+    """mirror of fabber_cuda_slab_part (fabber_cuda_vb_spatial_multi)"""
+    _fields_ = [
+        ("device", C.c_int),
+        ("v0", C.c_int), ("v1", C.c_int), ("own0", C.c_int), ("own1", C.c_int),
+        ("own_z0", C.c_int), ("own_z1", C.c_int),
+        ("buf", VbBuffers),
+    ]
+
+
 # ------------------------------------------------------------------------------------------------
 # Parameter transforms, host side (transforms.h:114-242, transforms.cc:17-25) - used to build the
 # Fabber-space prior exactly as FwdModel::GetParameters does (fwdmodel.cc:268-277).

@@ -217,3 +217,104 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
         return out
     finally:
         r.close()
+
+
+def z_slab_parts(coords, nz, n_parts):
+    """Cut a z-major voxel list (coords int [3][N], global coordinates) into `n_parts` z-slabs:
+    -> list of (v0, v1, own0, own1, z0, z1): part r owns the voxels with z in [z0, z1) = list positions
+    [own0, own1) and also holds the ghost planes z0-1 and z1 = positions [v0, v1)."""
+    from . import shard
+
+    z = np.asarray(coords[2])
+    assert np.all(np.diff(z) >= 0), "voxel list must be z-major (x fastest, then y, then z)"
+    first = np.searchsorted(z, np.arange(nz + 2))  # first list position with z >= k
+    parts = []
+    for r in range(n_parts):
+        z0, z1 = shard.z_slab_range(nz, r, n_parts)
+        if z1 <= z0:
+            raise ValueError("more parts than z-planes")
+        own0, own1 = int(first[z0]), int(first[z1])
+        v0 = int(first[max(z0 - 1, 0)])
+        v1 = int(first[min(z1 + 1, nz)])
+        if own1 <= own0:
+            raise ValueError("a z-slab holds no voxel of the mask")
+        parts.append((v0, v1, own0, own1, z0, z1))
+    return parts
+
+
+def run_spatial_multi(spec, data, coords, n_parts, devices=None, image_priors=None, init_mean=None, init_cov=None,
+                      init_noise=None, lock_centre=None):
+    """Spatial VB of one volume over `n_parts` z-slabs in ONE process (fabber_cuda_vb_spatial_multi): host arrays in,
+    host arrays out in the caller's voxel order - same signature and result layout as run(spatial=True). `devices`:
+    one ordinal per part (default: round-robin over the visible GPUs; repeats put several slabs on one GPU)."""
+    L = lib()
+    data = np.ascontiguousarray(data, dtype=np.float32)
+    coords = np.ascontiguousarray(coords, dtype=np.int32)
+    T, N = data.shape
+    P, NN = spec.P, spec.NN
+    prob = spec.prob
+    prob.n_voxels = N
+    n_dev = L.fabber_cuda_device_count()
+    devices = list(devices) if devices is not None else [r % n_dev for r in range(n_parts)]
+    cuts = z_slab_parts(coords, prob.nz, n_parts)
+    Parts = abi.SlabPart * n_parts
+    parts = Parts()
+    keep = []
+    prev = L.fabber_cuda_get_device()
+    ak = np.zeros((prob.max_iterations + 1, P))
+    outs = []
+    try:
+        for r, (v0, v1, own0, own1, z0, z1) in enumerate(cuts):
+            check(L.fabber_cuda_set_device(devices[r]), "set_device")
+            pt = parts[r]
+            pt.device, pt.v0, pt.v1, pt.own0, pt.own1, pt.own_z0, pt.own_z1 = devices[r], v0, v1, own0, own1, z0, z1
+            n = v1 - v0
+
+            def dev(arr, dtype):
+                d = DeviceArray.from_host(np.ascontiguousarray(arr, dtype=dtype))
+                keep.append(d)
+                return d.ptr
+
+            pt.buf.data = dev(data[:, v0:v1], np.float32)
+            pt.buf.coords = dev(coords[:, v0:v1], np.int32)
+            for k, img in (image_priors or {}).items():
+                pt.buf.image_prior[k] = dev(np.asarray(img)[v0:v1], np.float64)
+            for name, arr in (("init_mean", init_mean), ("init_cov", init_cov), ("init_noise", init_noise),
+                              ("lock_centre", lock_centre)):
+                if arr is not None:
+                    setattr(pt.buf, name, dev(np.asarray(arr)[:, v0:v1], np.float64))
+            o = {"mean": DeviceArray((P, n), np.float64), "cov": DeviceArray((spec.ncov, n), np.float64),
+                 "noise": DeviceArray((NN, n), np.float64), "free_energy": DeviceArray((n,), np.float64),
+                 "iterations": DeviceArray((n,), np.int32), "status": DeviceArray((n,), np.int32)}
+            for k2, v in o.items():
+                setattr(pt.buf, k2, v.ptr)
+            if r == 0:
+                pt.buf.spatial_ak = ak.ctypes.data
+            outs.append(o)
+        fn = L.fabber_cuda_vb_spatial_multi
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        fn.restype = C.c_int
+        rc = fn(C.byref(prob), n_parts, C.byref(parts))
+        if rc not in (abi.OK, abi.ERR_BAD_VOXEL):
+            raise CudaError("spatial multi-device run failed (%d): %s" % (rc, last_error()))
+        full = {"mean": np.zeros((P, N)), "cov": np.zeros((spec.ncov, N)), "noise": np.zeros((NN, N)),
+                "free_energy": np.zeros(N), "iterations": np.zeros(N, dtype=np.int32), "status": np.zeros(N, dtype=np.int32)}
+        for r, (v0, v1, own0, own1, z0, z1) in enumerate(cuts):
+            check(L.fabber_cuda_set_device(devices[r]), "set_device")
+            for k2, v in outs[r].items():
+                h = v.to_host()
+                full[k2][..., own0:own1] = h[..., own0 - v0:own1 - v0]
+        if rc == abi.OK and not prob.allow_bad_voxels and np.count_nonzero(full["status"]):
+            rc = abi.ERR_BAD_VOXEL
+        full["spatial_ak"] = ak.copy()
+        full["rc"] = rc
+        full["n_times"] = T
+        return full
+    finally:
+        for r in range(len(outs)):
+            L.fabber_cuda_set_device(devices[r])
+            for v in outs[r].values():
+                v.close()
+        for d in keep:
+            d.close()
+        L.fabber_cuda_set_device(max(prev, 0))

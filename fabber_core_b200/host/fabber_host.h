@@ -154,6 +154,11 @@ struct VoxelData
         int device;
         size_t v0, v1;
         float *dev;
+        /* [own0, own1) is the sub-range this part is responsible for. Voxelwise VB: all of it. Spatial VB cuts
+         * the volume into z-slabs: the part also holds the ghost planes just below and above its own planes
+         * [z0, z1) (the same voxels are some other part's own), see fabber_cuda_vb_spatial_multi. */
+        size_t own0, own1;
+        int z0, z1; /* z0 == z1: not a z-slab */
     };
     std::vector<Part> parts;
     /* the upload goes block of voxels by block of voxels on the owning device's copy stream; `ready` is
@@ -458,6 +463,7 @@ private:
     {
         int device = 0;
         size_t v0 = 0, v1 = 0;
+        size_t own0 = 0, own1 = 0; /* the columns this device publishes (== [v0, v1) unless it is a z-slab) */
         const float *data = nullptr;
         DevArray mean, cov, noise, F, hist, its, status;
     };

@@ -369,7 +369,10 @@ void Vb::DoCalculations(FabberRunData &rundata)
     /* ---- the devices of this run: one contiguous voxel range per GPU (the series is normally already there,
      * dealt out while it was being set); spatial VB couples the voxels and runs on one device ------------- */
     ReleaseDevice();
-    if (data.parts.empty() || (spatial && data.parts.size() != 1))
+    bool slabs = spatial && data.parts.size() > 1; /* z-slabs dealt out at set_data: the multi-device engine */
+    for (size_t g = 0; g < data.parts.size(); g++)
+        slabs = slabs && data.parts[g].z1 > data.parts[g].z0;
+    if (data.parts.empty() || (spatial && data.parts.size() != 1 && !slabs))
     {
         const std::vector<int> &devs = run_devices();
         if (devs.empty())
@@ -382,6 +385,8 @@ void Vb::DoCalculations(FabberRunData &rundata)
         c.device = data.parts[g].device;
         c.v0 = data.parts[g].v0;
         c.v1 = data.parts[g].v1;
+        c.own0 = data.parts[g].own0;
+        c.own1 = data.parts[g].own1;
         c.data = data.parts[g].dev;
         m_ctx.push_back(c);
     }
@@ -575,12 +580,16 @@ void Vb::DoCalculations(FabberRunData &rundata)
             buf.lock_centre = (const double *)upload_columns(lock_centre, P, c);
         if (spatial)
         {
+            /* [3][n] coordinates of this device's voxels (global coordinates) */
+            const size_t n = c.v1 - c.v0;
             Scratch sc;
             sc.device = c.device;
-            sc.d.bytes = 3 * N * sizeof(int);
+            sc.d.bytes = 3 * n * sizeof(int);
             sc.d.p = cached_device_alloc(sc.d.bytes);
             scratch.push_back(sc);
-            check(fabber_cuda_memcpy_h2d(sc.d.p, rundata.Coords().data(), sc.d.bytes, nullptr), "copying to the GPU");
+            check(fabber_cuda_memcpy2d_h2d(sc.d.p, n * sizeof(int), rundata.Coords().data() + c.v0, N * sizeof(int),
+                      n * sizeof(int), 3, nullptr),
+                "copying to the GPU");
             buf.coords = (const int *)sc.d.p;
         }
         buf.mean = (double *)c.mean.p;
@@ -594,7 +603,27 @@ void Vb::DoCalculations(FabberRunData &rundata)
     rundata.Log() << "Vb::timing: option translation + device buffers " << sw.lap_ms() << " ms" << std::endl;
 
     int rc = FABBER_CUDA_OK;
-    if (spatial)
+    if (spatial && slabs)
+    {
+        /* ONE volume over all the devices: z-slabs whose kernels talk through each other's memory */
+        std::vector<fabber_cuda_slab_part> sp(m_ctx.size());
+        for (size_t g = 0; g < m_ctx.size(); g++)
+        {
+            DeviceScope scope(m_ctx[g].device);
+            data.wait_uploaded((int)g);
+            check(fabber_cuda_stream_sync(nullptr), "copying data to the GPU"); /* the engine runs on streams of its own */
+            sp[g].device = m_ctx[g].device;
+            sp[g].v0 = (int)m_ctx[g].v0;
+            sp[g].v1 = (int)m_ctx[g].v1;
+            sp[g].own0 = (int)m_ctx[g].own0;
+            sp[g].own1 = (int)m_ctx[g].own1;
+            sp[g].own_z0 = data.parts[g].z0;
+            sp[g].own_z1 = data.parts[g].z1;
+            sp[g].buf = bufs[g];
+        }
+        rc = fabber_cuda_vb_spatial_multi(&prob, (int)sp.size(), sp.data());
+    }
+    else if (spatial)
     {
         DeviceScope scope(m_ctx[0].device);
         data.wait_uploaded(0);
@@ -639,12 +668,14 @@ void Vb::DoCalculations(FabberRunData &rundata)
         DevCtx &c = m_ctx[g];
         DeviceScope scope(c.device);
         int first_g = -1, code_g = 0;
-        const int bad_g = fabber_cuda_check_status((const int *)c.status.p, (int)(c.v1 - c.v0), &first_g, &code_g, nullptr);
+        /* only the columns this device publishes (a z-slab's ghost voxels carry FABBER_VOX_GHOST) */
+        const int bad_g = fabber_cuda_check_status((const int *)c.status.p + (c.own0 - c.v0), (int)(c.own1 - c.own0),
+            &first_g, &code_g, nullptr);
         if (bad_g < 0)
             check(bad_g, "VB kernels");
         if (bad_g > 0 && first < 0) /* ranges are in voxel order: the first device with a failure holds the first */
         {
-            first = (long)c.v0 + first_g;
+            first = (long)c.own0 + first_g;
             code = code_g;
         }
         n_bad += bad_g;
@@ -794,9 +825,9 @@ void Vb::SaveResults(FabberRunData &rundata)
             for (size_t k = 0; k < wanted[i].keys.size() && rc == FABBER_CUDA_OK; k++)
             {
                 VoxelData &vd = rundata.MutableVoxelData(wanted[i].keys[k]);
-                rc = fabber_cuda_memcpy2d_d2h(vd.f + c.v0, N * sizeof(float),
-                    (const float *)dev_of[i] + k * (size_t)wanted[i].rows_per_key * n, n * sizeof(float), n * sizeof(float),
-                    (size_t)wanted[i].rows_per_key, nullptr);
+                rc = fabber_cuda_memcpy2d_d2h(vd.f + c.own0, N * sizeof(float),
+                    (const float *)dev_of[i] + k * (size_t)wanted[i].rows_per_key * n + (c.own0 - c.v0), n * sizeof(float),
+                    (c.own1 - c.own0) * sizeof(float), (size_t)wanted[i].rows_per_key, nullptr);
             }
     }
     int rc_sync = FABBER_CUDA_OK;

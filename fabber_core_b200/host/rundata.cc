@@ -455,8 +455,9 @@ void VoxelData::upload_whole(int device)
     DeviceScope scope(device);
     Part pt;
     pt.device = device;
-    pt.v0 = 0;
-    pt.v1 = cols;
+    pt.v0 = pt.own0 = 0;
+    pt.v1 = pt.own1 = cols;
+    pt.z0 = pt.z1 = 0;
     pt.dev = (float *)cached_device_alloc(bytes());
     parts.push_back(pt);
     if (fabber_cuda_memcpy_h2d(pt.dev, f, bytes(), nullptr) != FABBER_CUDA_OK)
@@ -670,44 +671,108 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         const char *mv = getenv("FABBER_B200_MIN_VOXELS_PER_DEVICE");
         const size_t min_per = (mv && atol(mv) > 0) ? (size_t)atol(mv) : 65536;
         size_t g = std::min(devs.size(), std::max<size_t>(1, N / min_per));
-        if (LooksSpatial())
-            g = 1;
         devs.resize(g);
     }
-    const size_t G = devs.size();
-    const size_t per_part = ((N + G - 1) / G + 127) / 128 * 128; /* whole CTAs of 128 voxels */
+    const bool spatial_like = LooksSpatial();
+    size_t G = devs.size();
     /* ~96 MB per block, at most 64 blocks per device, at least 64k voxels each (a block is also one launch) */
     const char *block_env = getenv("FABBER_B200_UPLOAD_BLOCK_MB"); /* tuning / test knob; 32-128 MB measure alike */
     const size_t block_mb = (block_env && atol(block_env) > 0) ? (size_t)atol(block_env) : 96;
-    size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, T * per_part * sizeof(float) / (block_mb << 20)));
-    n_blocks = std::max<size_t>(1, std::min(n_blocks, per_part / 65536));
-    if (!upload)
-        n_blocks = 1;
-    const size_t per_block = ((per_part + n_blocks - 1) / n_blocks + 127) / 128 * 128;
-    std::vector<VoxelData::Block> blocks; /* round-robin over the devices */
     if (upload)
-        for (size_t g = 0; g < G; g++)
+    {
+        bool slabs = false;
+        if (spatial_like && G > 1)
         {
-            VoxelData::Part pt;
-            pt.device = devs[g];
-            pt.v0 = std::min(N, g * per_part);
-            pt.v1 = std::min(N, pt.v0 + per_part);
-            pt.dev = nullptr;
-            if (pt.v1 > pt.v0)
-                vd->parts.push_back(pt);
+            /* spatial VB couples neighbouring voxels: the volume is cut into z-slabs (the voxel list is z-major,
+             * so a slab is a contiguous range), each device also gets the planes just below and above its own */
+            const int nz = m_extent[2];
+            G = std::min<size_t>(G, (size_t)nz);
+            std::vector<size_t> first(nz + 2, N); /* first list position with z >= k */
+            {
+                size_t v = 0;
+                for (int k = 0; k <= nz + 1; k++)
+                {
+                    while (v < N && m_coords[2 * N + v] < k)
+                        v++;
+                    first[k] = v;
+                }
+            }
+            std::vector<VoxelData::Part> cut;
+            for (size_t g = 0; g < G; g++)
+            {
+                const int base = nz / (int)G, extra = nz % (int)G;
+                const int z0 = (int)g * base + std::min((int)g, extra), z1 = z0 + base + ((int)g < extra ? 1 : 0);
+                VoxelData::Part pt;
+                pt.device = devs[g];
+                pt.z0 = z0;
+                pt.z1 = z1;
+                pt.own0 = first[z0];
+                pt.own1 = first[z1];
+                pt.v0 = first[std::max(z0 - 1, 0)];
+                pt.v1 = first[std::min(z1 + 1, nz)];
+                pt.dev = nullptr;
+                cut.push_back(pt);
+            }
+            slabs = true;
+            for (size_t g = 0; g < cut.size(); g++)
+                if (cut[g].own1 <= cut[g].own0)
+                    slabs = false; /* a slab without a voxel of the mask: one device runs it all */
+            if (slabs)
+                vd->parts = cut;
+            else
+                G = 1;
         }
-    for (size_t bi = 0; bi < n_blocks; bi++)
-        for (size_t g = 0; g < (upload ? vd->parts.size() : 1); g++)
+        if (!slabs)
         {
-            const size_t p0 = upload ? vd->parts[g].v0 : 0, p1 = upload ? vd->parts[g].v1 : N;
-            VoxelData::Block blk;
-            blk.v0 = p0 + bi * per_block;
-            blk.v1 = std::min(p1, blk.v0 + per_block);
-            blk.ready = nullptr;
-            blk.part = (int)g;
-            if (blk.v0 < blk.v1)
-                blocks.push_back(blk);
+            const size_t per_part = ((N + G - 1) / G + 127) / 128 * 128; /* whole CTAs of 128 voxels */
+            for (size_t g = 0; g < G; g++)
+            {
+                VoxelData::Part pt;
+                pt.device = devs[g];
+                pt.v0 = std::min(N, g * per_part);
+                pt.v1 = std::min(N, pt.v0 + per_part);
+                pt.own0 = pt.v0;
+                pt.own1 = pt.v1;
+                pt.z0 = pt.z1 = 0;
+                pt.dev = nullptr;
+                if (pt.v1 > pt.v0)
+                    vd->parts.push_back(pt);
+            }
         }
+    }
+    std::vector<VoxelData::Block> blocks; /* round-robin over the devices */
+    size_t max_block = 0;
+    {
+        std::vector<std::vector<VoxelData::Block>> per_part_blocks(upload ? vd->parts.size() : 1);
+        size_t most = 0;
+        for (size_t g = 0; g < per_part_blocks.size(); g++)
+        {
+            const size_t p0 = upload ? vd->parts[g].v0 : 0, p1 = upload ? vd->parts[g].v1 : N, pn = p1 - p0;
+            size_t n_blocks = std::min<size_t>(64, std::max<size_t>(1, T * pn * sizeof(float) / (block_mb << 20)));
+            n_blocks = std::max<size_t>(1, std::min(n_blocks, pn / 65536));
+            if (!upload)
+                n_blocks = 1;
+            const size_t per_block = ((pn + n_blocks - 1) / n_blocks + 127) / 128 * 128;
+            for (size_t bi = 0; bi < n_blocks; bi++)
+            {
+                VoxelData::Block blk;
+                blk.v0 = p0 + bi * per_block;
+                blk.v1 = std::min(p1, blk.v0 + per_block);
+                blk.ready = nullptr;
+                blk.part = (int)g;
+                if (blk.v0 < blk.v1)
+                {
+                    per_part_blocks[g].push_back(blk);
+                    max_block = std::max(max_block, blk.v1 - blk.v0);
+                }
+            }
+            most = std::max(most, per_part_blocks[g].size());
+        }
+        for (size_t bi = 0; bi < most; bi++)
+            for (size_t g = 0; g < per_part_blocks.size(); g++)
+                if (bi < per_part_blocks[g].size())
+                    blocks.push_back(per_part_blocks[g][bi]);
+    }
     for (size_t g = 0; g < vd->parts.size(); g++)
     {
         DeviceScope scope(vd->parts[g].device);
@@ -760,7 +825,7 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
      * the block's columns) - contiguous runs in both source and destination - handed out block-major from one
      * counter; a per-block count of unfinished items tells the calling thread when a block is staged, and it
      * queues that block's copy while the workers are already on the next one. */
-    const size_t piece = (size_t)1 << 18, pieces = (per_block + piece - 1) / piece, per_items = T * pieces;
+    const size_t piece = (size_t)1 << 18, pieces = std::max<size_t>(1, (max_block + piece - 1) / piece), per_items = T * pieces;
     const size_t real_blocks = blocks.size(); /* empty mask: nothing to stage */
     std::vector<std::atomic<size_t>> unfinished(real_blocks);
     for (size_t b = 0; b < real_blocks; b++)

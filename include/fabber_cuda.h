@@ -267,6 +267,30 @@ typedef struct fabber_cuda_slab
 int fabber_cuda_vb_spatial_slab(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf,
     const fabber_cuda_slab *slab, void *stream);
 
+/* Spatial VB of ONE volume over several GPUs driven by ONE process: the voxel list is cut into z-slabs, part r
+ * holds its own voxels [own0, own1) of the list plus the ghost planes just below and above (the whole range
+ * [v0, v1), series included), on device `device`. The slabs' kernels are coupled through each other's memory
+ * (peer access over NVLink): the ordered sweep forwards its top plane into the next slab's ghosts hyper-plane by
+ * hyper-plane behind release/acquire flags, the bottom plane goes down after the sweep, and the two aK sums
+ * (priors.cc:233-343) are all-gathered through mailboxes inside the aK kernel - no host callback, one
+ * cooperative sweep launch per iteration per GPU, and the same result as the one-GPU run (the aK sums differ
+ * in summation order only). Replaces Vb::DoCalculationsSpatial (inference_vb.cc:578-767) for the whole box.
+ *   prob      n_voxels = voxels of the WHOLE volume; nx, ny, nz the whole grid
+ *   parts[r]  buf: DEVICE pointers on parts[r].device, every per-voxel array of v1 - v0 voxels (data
+ *             [T][v1-v0], coords [3][v1-v0] with GLOBAL coordinates, outputs, optional image priors / restart
+ *             arrays); own_z0 / own_z1: the z-planes this part owns. Parts tile the list in order; part r's
+ *             ghosts are part r-1's last and part r+1's first plane. Outputs of ghost voxels are not
+ *             meaningful (status FABBER_VOX_GHOST).
+ * Synchronous. Several parts may name the same device (tests on one GPU). */
+typedef struct fabber_cuda_slab_part
+{
+    int device;
+    int v0, v1, own0, own1;
+    int own_z0, own_z1;
+    fabber_cuda_vb_buffers buf;
+} fabber_cuda_slab_part;
+int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts, const fabber_cuda_slab_part *parts);
+
 /* Scan status[] on the device; returns 0 if all OK, else the number of failed voxels and the
  * index / code of the first one (synchronises the stream). */
 int fabber_cuda_check_status(

@@ -1,0 +1,133 @@
+"""GPU: spatial VB of ONE volume over several z-slabs driven by ONE process (fabber_cuda_vb_spatial_multi): the
+slabs' kernels are coupled through each other's memory - the ordered sweep forwards its top plane into the next
+slab's ghost voxels hyper-plane by hyper-plane behind release/acquire flags, the bottom plane goes down after the
+sweep, the aK sums are all-gathered through mailboxes inside the aK kernel. The result must be the one-GPU
+result (inference_vb.cc:605-725 sequential sweep; priors.cc:221-344 aK sums): only the summation order of the aK
+partials differs. With one GPU the slabs share it (every slab's sweep grid is capped so that all are
+co-resident - they spin on each other's flags); with more GPUs present they are dealt round-robin."""
+import numpy as np
+import pytest
+
+import oracle
+from fabber_core_b200 import cuda_abi as abi
+from fabber_core_b200 import device, synth
+from parity import compare, tri
+
+pytestmark = pytest.mark.gpu
+
+
+def grid_coords(nx, ny, nz, mask=None):
+    idx = np.arange(nx * ny * nz)
+    coords = np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.int32)
+    if mask is not None:
+        coords = coords[:, mask.reshape(-1)]
+    return np.ascontiguousarray(coords)
+
+
+def maxrel(a, b, scale=None):
+    den = np.maximum(np.abs(b), 1e-300 if scale is None else scale)
+    return float(np.max(np.abs(a - b) / den))
+
+
+def spec_for(shape, model, T, **kw):
+    sp = abi.ProblemSpec(model, T, **kw)
+    sp.prob.nx, sp.prob.ny, sp.prob.nz = shape
+    return sp
+
+
+def check_equal(multi, one, P, tol):
+    assert np.array_equal(multi["status"], one["status"])
+    assert np.array_equal(multi["iterations"], one["iterations"])
+    std = np.sqrt(np.abs(np.stack([one["cov"][tri(i, i)] for i in range(P)])))
+    assert float(np.max(np.abs(multi["mean"] - one["mean"]) / std)) < tol
+    for i in range(P):
+        assert maxrel(multi["cov"][tri(i, i)], one["cov"][tri(i, i)]) < tol
+    assert maxrel(multi["noise"], one["noise"]) < tol
+    assert maxrel(multi["spatial_ak"], one["spatial_ak"]) < tol
+    assert maxrel(multi["free_energy"], one["free_energy"], scale=1.0) < tol
+
+
+def test_one_part_is_the_one_gpu_run():
+    shape = (6, 5, 4)
+    y = synth.poly_volume(6 * 5 * 4, 30, 1, seed=82).numpy()
+    coords = grid_coords(*shape)
+    kw = dict(degree=1, prior_types=list("MM"), need_f=True, max_iterations=4)
+    one = device.run(spec_for(shape, "poly", 30, **kw), y, spatial=True, coords=coords)
+    multi = device.run_spatial_multi(spec_for(shape, "poly", 30, **kw), y, coords, 1)
+    for k in ("mean", "cov", "noise", "free_energy", "spatial_ak", "status"):
+        assert np.array_equal(multi[k], one[k]), k
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 4])
+def test_mrf_slabs_equal_the_sequential_sweep(n_parts):
+    """'MMMM' on the bi-exponential model (BASELINE config 5's prior set), 10 iterations: same bound as the
+    host-callback slab path (1e-6 posterior std; a stale boundary plane gives tens of std here)."""
+    shape = (8, 8, 8)
+    y = synth.biexp_volume(8 * 8 * 8, 96, 0.02, 0.02, seed=83, smooth_shape=shape).numpy()
+    coords = grid_coords(*shape)
+    kw = dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=10, need_f=True,
+              param_overrides={"r2": {"mean": 6.0}})
+    one = device.run(spec_for(shape, "exp", 96, **kw), y, spatial=True, coords=coords)
+    multi = device.run_spatial_multi(spec_for(shape, "exp", 96, **kw), y, coords, n_parts)
+    assert np.all(one["status"] == 0)
+    check_equal(multi, one, 4, 1e-6)
+
+
+def test_three_iterations_agree_to_rounding():
+    """3 iterations: the only difference, the summation order of the aK partials, has not been amplified yet"""
+    shape = (12, 10, 16)
+    n = 12 * 10 * 16
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=85, smooth_shape=shape).numpy()
+    coords = grid_coords(*shape)
+    kw = dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=3, need_f=True,
+              param_overrides={"r2": {"mean": 6.0}})
+    one = device.run(spec_for(shape, "exp", 96, **kw), y, spatial=True, coords=coords)
+    multi = device.run_spatial_multi(spec_for(shape, "exp", 96, **kw), y, coords, 4)
+    check_equal(multi, one, 4, 1e-9)
+
+
+def test_mixed_prior_types_uneven_slabs_and_no_ordered_sweep():
+    shape = (5, 7, 7)
+    y = synth.poly_volume(5 * 7 * 7, 40, 2, seed=84).numpy()
+    coords = grid_coords(*shape)
+    for types in ("mPN", "PpA"):   # the second has no 'M' / 'm': no ordered sweep, the halo still moves
+        kw = dict(degree=2, prior_types=list(types), need_f=True, max_iterations=6)
+        one = device.run(spec_for(shape, "poly", 40, **kw), y, spatial=True, coords=coords)
+        multi = device.run_spatial_multi(spec_for(shape, "poly", 40, **kw), y, coords, 3)
+        check_equal(multi, one, 3, 1e-6)
+
+
+def test_irregular_mask_over_slabs_against_the_oracle():
+    nx, ny, nz = 11, 11, 9
+    zz, yy, xx = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    mask = ((xx - 5) ** 2 + (yy - 5) ** 2 + (1.3 * (zz - 4)) ** 2) < 0.45 * 11 * 0.45 * 11
+    full = synth.poly_volume(nx * ny * nz, 40, 2, seed=31).numpy()
+    y = np.ascontiguousarray(full[:, mask.reshape(-1)])
+    coords = grid_coords(nx, ny, nz, mask)
+    kw = dict(degree=2, prior_types=list("MMM"), need_f=True, update_first_iter=True, max_iterations=5,
+              allow_bad_voxels=True)
+    mk = lambda: spec_for((nx, ny, nz), "poly", 40, **kw)
+    ref = oracle.run(mk(), y, spatial=True, coords=coords)
+    fma = oracle.run(mk(), y, spatial=True, coords=coords, variant="fma")
+    multi = device.run_spatial_multi(mk(), y, coords, 3)
+    compare(multi, ref, 3, [fma], label="spatial multi-device, irregular mask, 3 slabs")
+    assert maxrel(multi["spatial_ak"], ref["spatial_ak"]) < 1e-6
+
+
+def test_restart_and_image_prior_over_slabs():
+    """teacher-forced step of C5 'MMMM' over 3 slabs + an image prior column: per-part slicing of every input"""
+    shape = (8, 6, 6)
+    n = 8 * 6 * 6
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=1005, smooth_shape=shape).numpy()
+    coords = grid_coords(*shape)
+    base = dict(num_exps=2, dt=0.02, need_f=True, allow_bad_voxels=True, param_overrides={"r2": {"mean": 6.0}})
+    st = oracle.run(spec_for(shape, "exp", 96, prior_types=list("MMMM"), max_iterations=4, **base), y, spatial=True,
+                    coords=coords)
+    img = np.log(0.5 + 0.01 * np.arange(n) / n)
+    kw = dict(prior_types=list("MMIM"), max_iterations=1, update_first_iter=True, **base)
+    ins = dict(image_priors={2: img}, init_mean=st["mean"], init_cov=st["cov"], init_noise=st["noise"])
+    ref = oracle.run(spec_for(shape, "exp", 96, **kw), y, spatial=True, coords=coords, **ins)
+    probes = [oracle.run(spec_for(shape, "exp", 96, **kw), y, spatial=True, coords=coords, variant=v, **ins)
+              for v in ("fma", "ulp")]
+    multi = device.run_spatial_multi(spec_for(shape, "exp", 96, **kw), y, coords, 3, **ins)
+    compare(multi, ref, 4, probes, label="spatial multi-device, restart + image prior, 3 slabs")
