@@ -477,7 +477,8 @@ def run_workload(wname, args, D, rank, local_rank, world, steps, warmup, main_li
 
     if spatial and world > 1:
         rec = spatial_slab_bench(args, w, D, rank, local_rank, world, n_total, steps, warmup, config)
-        dev = None
+        if rank != 0:
+            rec = {"iterations_per_voxel": 0.0}
     else:
         y = make_volume(w, n_local, "cuda", seed_offset=rank, voxel_offset=lo, n_total=n_total)
         spec = make_spec(w, n_local)
@@ -613,59 +614,75 @@ def run_workload(wname, args, D, rank, local_rank, world, steps, warmup, main_li
 
 
 def spatial_slab_bench(args, w, D, rank, local_rank, world, n_total, steps, warmup, config):
-    """C5 on several GPUs, STRONG scaling: ONE side^3 volume partitioned into `world` z-slabs, one slab (plus
-    ghost planes) per rank; per iteration an all-reduce of the aK sums, the block-pipelined ordered sweep
-    (forwarding of boundary means up the ranks) and a halo exchange (fabber_core_b200/spatial_mgpu.py)."""
+    """C5 on several GPUs, STRONG scaling: ONE side^3 volume cut into `world` z-slabs. The slabs are coupled
+    DEVICE to DEVICE (fabber_cuda_vb_spatial_multi: the ordered sweep forwards its top plane into the next slab's
+    ghost voxels behind release/acquire flags in peer memory, the aK sums are all-gathered through mailboxes), so
+    one process drives the whole job: rank 0 queues the launches for all `world` GPUs, the other ranks' processes
+    stand by at the barrier. Timed on the devices (CUDA events on every slab's stream, max over the slabs)."""
     import torch
 
     from fabber_core_b200 import device, synth
-    from fabber_core_b200.spatial_mgpu import SlabPlan, SlabRun, TorchDistComm
 
     side = round(n_total ** (1.0 / 3))
     assert side ** 3 == n_total
-    plan = SlabPlan(side, side, side, rank, world)
-    g0, g1 = plan.global_columns()
-    y = synth.biexp_volume(g1 - g0, w["T"], 0.02, 0.02, seed=1005 + rank, device="cuda",
-                           smooth_shape=(side, side, side), voxel_offset=g0)
-    L = device.lib()
-    comm = TorchDistComm(rank, world, w["P"])
-    sr = SlabRun(make_spec(w, 0), plan, comm)
-    sr.set_data_device(y.data_ptr())
-    for _ in range(max(warmup, 3)):
-        sr.launch()
-    out = sr.results()
-    its_local = int(out["iterations"].astype(np.int64).sum())
-    n_bad = int(np.count_nonzero(out["status"]))
-    fp64_peak = L.fabber_cuda_measure_fp64_peak(3)
+    rec = None
     D.barrier()
-    launches0 = L.fabber_cuda_launch_count()
-    sampler = ClockSampler(local_rank)
-    time.sleep(0.3)
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if rank == 0:
+        L = device.lib()
+        idx = np.arange(n_total)
+        coords = np.stack([idx % side, (idx // side) % side, idx // (side * side)]).astype(np.int32)
+        del idx
+        run = device.SpatialMultiRun(make_spec(w, n_total), coords, world, devices=list(range(world)))
+        ys = []
+        for r in range(world):
+            g0, g1 = run.part_range(r)
+            with torch.cuda.device(r):
+                y = synth.biexp_volume(g1 - g0, w["T"], 0.02, 0.02, seed=1005 + r, device="cuda:%d" % r,
+                                       smooth_shape=(side, side, side), voxel_offset=g0)
+                torch.cuda.synchronize()
+            ys.append(y)
+            run.set_data_device(r, y.data_ptr())
+
+        def step():
+            rc = run.launch()
+            if rc != 0:
+                raise RuntimeError("spatial multi-device launch failed: %s" % device.last_error())
+            return run.last_ms
+
+        for _ in range(max(warmup, 3)):
+            step()
+        out = run.results()
+        its = int(out["iterations"].astype(np.int64).sum())
+        n_bad = int(np.count_nonzero(out["status"]))
+        fp64_peak = L.fabber_cuda_measure_fp64_peak(3)
+        launches0 = L.fabber_cuda_launch_count()
+        sampler = ClockSampler(local_rank)
+        time.sleep(0.3)
+        t0 = time.time()
+        ms = [step() for _ in range(steps)]
+        wall_ms = (time.time() - t0) * 1e3 / steps
+        clocks = sampler.stop(t0, time.time())
+        launches = L.fabber_cuda_launch_count() - launches0
+        t_ms = float(np.sum(ms))
+        run.close()
+        del ys
+        for r in range(world):
+            with torch.cuda.device(r):
+                torch.cuda.empty_cache()
+        cfg = dict(config)
+        cfg["voxels_per_gpu"] = n_total // world
+        cfg["sharding"] = ("z-slabs of ONE %dx%dx%d volume, one per GPU, driven by one process; slabs coupled device to "
+                           "device through peer memory: the exact ordered sweep forwards hyper-plane by hyper-plane behind "
+                           "release/acquire flags, halo after the sweep, aK sums all-gathered through mailboxes in the aK "
+                           "kernel; result equals the one-GPU run" % (side, side, side))
+        rec = {"value": its * steps / (t_ms * 1e-3), "ms_per_step": t_ms / steps, "wall_ms_per_step": wall_ms,
+               "steps": steps, "warmup": max(warmup, 3), "config": cfg, "gpu_launches": int(launches), "clocks": clocks,
+               "iterations_per_voxel": its / float(n_total), "bad_voxels": n_bad,
+               "timing": "CUDA events on every slab's stream around set-up + iterations + result permutation, max over "
+                         "the slabs, summed over the steps (the call is synchronous)",
+               "roofline": roofline_block(w, its // world, t_ms / steps * 1e-3, n_total // world, fp64_peak, True)}
     D.barrier()
-    t0 = time.time()
-    ev0.record()
-    for _ in range(steps):
-        sr.launch()
-    ev1.record()
-    D.barrier()
-    clocks = sampler.stop(t0, time.time())
-    launches = L.fabber_cuda_launch_count() - launches0
-    t_ms = D.reduce(ev0.elapsed_time(ev1), "MAX")
-    its = D.reduce(its_local, "SUM")
-    bad = int(D.reduce(n_bad, "SUM"))
-    sr.close()
-    del y
-    torch.cuda.empty_cache()
-    cfg = dict(config)
-    cfg["voxels_per_gpu"] = plan.n_own
-    cfg["sharding"] = ("z-slabs of ONE %dx%dx%d volume; per iteration: all-reduce of the aK sums, ordered sweep pipelined "
-                       "across the slabs in %d blocks of %d hyper-planes, halo exchange; result equals the one-GPU run"
-                       % (side, side, side, plan.n_blocks, plan.block_planes))
-    return {"value": its * steps / (t_ms * 1e-3), "ms_per_step": t_ms / steps, "steps": steps,
-            "warmup": max(warmup, 3), "config": cfg, "gpu_launches": int(launches), "clocks": clocks,
-            "iterations_per_voxel": its / float(n_total), "bad_voxels": bad,
-            "roofline": roofline_block(w, its_local, t_ms / steps * 1e-3, plan.n_own, fp64_peak, True)}
+    return rec
 
 
 def reference_arm(args, metric):

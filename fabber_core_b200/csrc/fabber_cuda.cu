@@ -14,6 +14,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "vb_launch.h"
@@ -24,6 +25,7 @@
 namespace fab
 {
 static std::atomic<unsigned long long> g_launches(0);
+static std::atomic<double> g_last_multi_ms(0.0);
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 static thread_local std::string g_last_error;
@@ -949,6 +951,7 @@ struct SpRun
             || !F_p || !hist_p || !its_p || !status_p || !status_prev)
             return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
         sp.status_prev = status_prev;
+        sp.ignore_bad = prob->allow_bad_voxels ? 1 : 0;
         sp.ak_blocks = SP_AK_BLOCKS;
         sp.spatial_dims = prob->spatial_dims;
         sp.update_first_iter = prob->update_first_iter;
@@ -1092,8 +1095,19 @@ struct SpRun
     }
 
     /* results back into the caller's voxel order; synchronises */
+    bool finish_queued = false;
     int finish()
     {
+        if (!finish_queued)
+            finish_async();
+        cudaError_t e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess)
+            return cuda_fail(e, "spatial VB");
+        return FABBER_CUDA_OK;
+    }
+    void finish_async()
+    {
+        finish_queued = true;
         permute_rows<double, false>(mean_p, buf.mean, order, P, N, st);
         permute_rows<double, false>(cov_p, buf.cov, order, NT, N, st);
         permute_rows<double, false>(noise_p, buf.noise, order, 2, N, st);
@@ -1107,10 +1121,6 @@ struct SpRun
         if (buf.spatial_ak)
             cudaMemcpyAsync(buf.spatial_ak, sp.ak_hist, (size_t)(max_it + 1) * P * sizeof(double),
                 cudaMemcpyDeviceToHost, st);
-        cudaError_t e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess)
-            return cuda_fail(e, "spatial VB");
-        return FABBER_CUDA_OK;
     }
 };
 } // namespace fab
@@ -1396,7 +1406,6 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
                     return cuda_fail(pe, "cudaDeviceEnablePeerAccess");
                 cudaGetLastError();
             }
-    std::vector<SpRun> runs(W);
     std::vector<fabber_cuda_vb_problem> probs(W, *prob);
     std::vector<cudaStream_t> streams(W, nullptr);
     struct Streams
@@ -1413,16 +1422,58 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
                 }
         }
     } stream_guard = { streams, parts };
+    /* per-device start / end events on the engine's streams: the device-side duration of the call (max over
+     * the devices) for fabber_cuda_last_multi_ms() */
+    std::vector<cudaEvent_t> ev0(W, nullptr), ev1(W, nullptr);
+    struct Events
+    {
+        std::vector<cudaEvent_t> &a, &b;
+        ~Events()
+        {
+            for (size_t i = 0; i < a.size(); i++)
+            {
+                if (a[i])
+                    cudaEventDestroy(a[i]);
+                if (b[i])
+                    cudaEventDestroy(b[i]);
+            }
+        }
+    } event_guard = { ev0, ev1 };
+    /* declared after the streams: the runs hand their scratch back to the stream-ordered allocator ON their
+     * stream when they go out of scope, so the streams must outlive them */
+    std::vector<SpRun> runs(W);
     for (int r = 0; r < W; r++)
     {
         cudaSetDevice(parts[r].device);
         cudaError_t se = cudaStreamCreateWithFlags(&streams[r], cudaStreamNonBlocking);
+        if (se == cudaSuccess)
+            se = cudaEventCreate(&ev0[r]);
+        if (se == cudaSuccess)
+            se = cudaEventCreate(&ev1[r]);
+        if (se == cudaSuccess)
+            se = cudaEventRecord(ev0[r], streams[r]);
         if (se != cudaSuccess)
             return cuda_fail(se, "spatial multi: stream");
         probs[r].n_voxels = parts[r].v1 - parts[r].v0;
-        int rc = runs[r].prepare(&probs[r], &parts[r].buf, streams[r], n_global);
-        if (rc != FABBER_CUDA_OK)
-            return rc;
+    }
+    {
+        /* set-up (neighbours, hyper-plane sort, permutation of the series) has host synchronisations inside:
+         * one host thread per slab so that the devices prepare side by side */
+        std::vector<int> rcs(W, FABBER_CUDA_OK);
+        std::vector<std::string> msgs(W);
+        std::vector<std::thread> workers;
+        for (int r = 0; r < W; r++)
+            workers.emplace_back([&, r]() {
+                cudaSetDevice(parts[r].device);
+                rcs[r] = runs[r].prepare(&probs[r], &parts[r].buf, streams[r], n_global);
+                if (rcs[r] != FABBER_CUDA_OK)
+                    msgs[r] = g_last_error;
+            });
+        for (size_t i = 0; i < workers.size(); i++)
+            workers[i].join();
+        for (int r = 0; r < W; r++)
+            if (rcs[r] != FABBER_CUDA_OK)
+                return fail(rcs[r], msgs[r]);
     }
     const int P = runs[0].P, max_it = runs[0].max_it;
     const bool any_spatial = runs[0].any_spatial, any_coupled = runs[0].any_coupled;
@@ -1569,17 +1620,31 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
     }
     for (int r = 0; r < W; r++)
     {
+        /* queue every slab's result permutation before waiting for any of them */
+        cudaSetDevice(parts[r].device);
+        runs[r].finish_async();
+        cudaEventRecord(ev1[r], streams[r]);
+    }
+    double worst_ms = 0.0;
+    for (int r = 0; r < W; r++)
+    {
         cudaSetDevice(parts[r].device);
         const int frc = runs[r].finish();
         if (frc != FABBER_CUDA_OK && rc == FABBER_CUDA_OK)
             rc = frc;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ev0[r], ev1[r]) == cudaSuccess)
+            worst_ms = std::max(worst_ms, (double)ms);
         int h_err = 0;
         cudaMemcpy(&h_err, err[r], sizeof(int), cudaMemcpyDeviceToHost);
         if (h_err && rc == FABBER_CUDA_OK)
             rc = fail(FABBER_CUDA_ERR_CUDA, "spatial multi: a slab timed out waiting for its neighbour");
     }
+    g_last_multi_ms.store(worst_ms);
     return rc;
 }
+
+double fabber_cuda_last_multi_ms(void) { return g_last_multi_ms.load(); }
 
 int fabber_cuda_check_status(const int *status, int n_voxels, int *first_bad_voxel, int *first_bad_code, void *stream)
 {

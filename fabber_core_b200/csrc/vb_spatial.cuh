@@ -136,6 +136,7 @@ struct SpArgs
     /* [N] status words as they were when this iteration began (== v.status unless allow_bad_voxels): which
      * neighbours Vb::IgnoreVoxel had already struck from the lists, see nbr_alive() */
     const int *status_prev;
+    int ignore_bad;     /* allow_bad_voxels: failed voxels are struck from their neighbours' lists (nbr_alive) */
     SlabLinks link;     /* link.world == 0 on one GPU and in the host-callback slab mode */
     int sweep_max_ctas; /* > 0: cap on the cooperative sweep grid (small slabs: the barrier gets cheaper) */
     int sweep_share;    /* > 1: that many slabs share this GPU and spin on each other's flags - each sweep grid is
@@ -149,10 +150,12 @@ FAB_DEV bool is_spatial_type(char t) { return t == 'M' || t == 'm' || t == 'P' |
  * neighbours' lists, so it no longer counts towards nn and its stale mean no longer feeds the MRF prior mean
  * or the aK sums. The lists here are static; a neighbour is skipped when its status word reports a failure.
  * Ghost voxels of a z-slab are alive (their owner updates them). */
-FAB_DEV bool nbr_alive(const int *status, int n)
+FAB_DEV bool nbr_alive(bool ignore_bad, const int *status, int n)
 {
     if (n < 0)
         return false;
+    if (!ignore_bad) /* without allow-bad-voxels the first failure ends the run: no status look-ups */
+        return true;
     const int st = status[n];
     return st == 0 || st == FABBER_VOX_GHOST;
 }
@@ -257,7 +260,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + v];
-            if (!nbr_alive(a.status, nbr[j])) /* every failure so far: CalculateaK runs at v == 1 */
+            if (!nbr_alive(s.ignore_bad != 0, a.status, nbr[j])) /* every failure so far: CalculateaK runs at v == 1 */
                 nbr[j] = -1;
             nn += nbr[j] >= 0;
         }
@@ -280,8 +283,8 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
             double SwK = 0.0;
 #pragma unroll
             for (int j = 0; j < 6; j++)
-                if (nbr[j] >= 0)
-                    SwK += wK - __ldcg(a.mean + k * N + nbr[j]); /* ghosts are written by a peer GPU */
+                if (nbr[j] >= 0) /* slab mode: ghosts are written by a peer GPU, never serve them from L1 */
+                    SwK += wK - (s.link.world > 1 ? __ldcg(a.mean + k * N + nbr[j]) : a.mean[k * N + nbr[j]]);
             if (ty == 'p' || ty == 'm')
                 SwK += wK * (dims * 2 - (double)nn);
             if (ty == 'm' || ty == 'M')
@@ -430,7 +433,7 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
     int nn = 0;
 #pragma unroll
     for (int j = 0; j < 6; j++)
-        nn += nbr_alive(s.status_prev, s.nn_idx[j * N + v]);
+        nn += nbr_alive(s.ignore_bad != 0, s.status_prev, s.nn_idx[j * N + v]);
     const int dims = s.spatial_dims;
     double Fprior = 0.0;
     bool coupled[P];
@@ -558,7 +561,7 @@ template <int P> struct SweepVoxel
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + pos];
-            if (!nbr_alive(s.status_prev, nbr[j]))
+            if (!nbr_alive(s.ignore_bad != 0, s.status_prev, nbr[j]))
                 nbr[j] = -1;
         }
 #pragma unroll

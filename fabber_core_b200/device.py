@@ -242,79 +242,125 @@ def z_slab_parts(coords, nz, n_parts):
     return parts
 
 
-def run_spatial_multi(spec, data, coords, n_parts, devices=None, image_priors=None, init_mean=None, init_cov=None,
-                      init_noise=None, lock_centre=None):
-    """Spatial VB of one volume over `n_parts` z-slabs in ONE process (fabber_cuda_vb_spatial_multi): host arrays in,
-    host arrays out in the caller's voxel order - same signature and result layout as run(spatial=True). `devices`:
-    one ordinal per part (default: round-robin over the visible GPUs; repeats put several slabs on one GPU)."""
-    L = lib()
-    data = np.ascontiguousarray(data, dtype=np.float32)
-    coords = np.ascontiguousarray(coords, dtype=np.int32)
-    T, N = data.shape
-    P, NN = spec.P, spec.NN
-    prob = spec.prob
-    prob.n_voxels = N
-    n_dev = L.fabber_cuda_device_count()
-    devices = list(devices) if devices is not None else [r % n_dev for r in range(n_parts)]
-    cuts = z_slab_parts(coords, prob.nz, n_parts)
-    Parts = abi.SlabPart * n_parts
-    parts = Parts()
-    keep = []
-    prev = L.fabber_cuda_get_device()
-    ak = np.zeros((prob.max_iterations + 1, P))
-    outs = []
-    try:
-        for r, (v0, v1, own0, own1, z0, z1) in enumerate(cuts):
-            check(L.fabber_cuda_set_device(devices[r]), "set_device")
-            pt = parts[r]
-            pt.device, pt.v0, pt.v1, pt.own0, pt.own1, pt.own_z0, pt.own_z1 = devices[r], v0, v1, own0, own1, z0, z1
+class SpatialMultiRun(object):
+    """Device-resident buffers of one spatial VB run cut into z-slabs over several GPUs, driven by THIS process
+    (fabber_cuda_vb_spatial_multi). `devices`: one ordinal per part (default: round-robin over the visible GPUs;
+    repeats put several slabs on one GPU)."""
+
+    def __init__(self, spec, coords, n_parts, devices=None):
+        L = lib()
+        self.spec = spec
+        self.coords = np.ascontiguousarray(coords, dtype=np.int32)
+        self.N = self.coords.shape[1]
+        spec.prob.n_voxels = self.N
+        n_dev = L.fabber_cuda_device_count()
+        self.devices = list(devices) if devices is not None else [r % n_dev for r in range(n_parts)]
+        self.cuts = z_slab_parts(self.coords, spec.prob.nz, n_parts)
+        self.parts = (abi.SlabPart * n_parts)()
+        self.keep, self.outs = [], []
+        self.ak = np.zeros((spec.prob.max_iterations + 1, spec.P))
+        self.prev = L.fabber_cuda_get_device()
+        P, NN = spec.P, spec.NN
+        for r, (v0, v1, own0, own1, z0, z1) in enumerate(self.cuts):
+            check(L.fabber_cuda_set_device(self.devices[r]), "set_device")
+            pt = self.parts[r]
+            pt.device, pt.v0, pt.v1, pt.own0, pt.own1, pt.own_z0, pt.own_z1 = self.devices[r], v0, v1, own0, own1, z0, z1
             n = v1 - v0
-
-            def dev(arr, dtype):
-                d = DeviceArray.from_host(np.ascontiguousarray(arr, dtype=dtype))
-                keep.append(d)
-                return d.ptr
-
-            pt.buf.data = dev(data[:, v0:v1], np.float32)
-            pt.buf.coords = dev(coords[:, v0:v1], np.int32)
-            for k, img in (image_priors or {}).items():
-                pt.buf.image_prior[k] = dev(np.asarray(img)[v0:v1], np.float64)
-            for name, arr in (("init_mean", init_mean), ("init_cov", init_cov), ("init_noise", init_noise),
-                              ("lock_centre", lock_centre)):
-                if arr is not None:
-                    setattr(pt.buf, name, dev(np.asarray(arr)[:, v0:v1], np.float64))
+            pt.buf.coords = self._dev(self.coords[:, v0:v1], np.int32)
             o = {"mean": DeviceArray((P, n), np.float64), "cov": DeviceArray((spec.ncov, n), np.float64),
                  "noise": DeviceArray((NN, n), np.float64), "free_energy": DeviceArray((n,), np.float64),
                  "iterations": DeviceArray((n,), np.int32), "status": DeviceArray((n,), np.int32)}
             for k2, v in o.items():
                 setattr(pt.buf, k2, v.ptr)
             if r == 0:
-                pt.buf.spatial_ak = ak.ctypes.data
-            outs.append(o)
+                pt.buf.spatial_ak = self.ak.ctypes.data
+            self.outs.append(o)
+        L.fabber_cuda_set_device(max(self.prev, 0))
+
+    def _dev(self, arr, dtype):
+        d = DeviceArray.from_host(np.ascontiguousarray(arr, dtype=dtype))
+        self.keep.append(d)
+        return d.ptr
+
+    def part_range(self, r):
+        """(v0, v1): the columns of the whole voxel list part r holds (own + ghost planes)"""
+        return self.cuts[r][0], self.cuts[r][1]
+
+    def set_data(self, data):
+        data = np.ascontiguousarray(data, dtype=np.float32)
+        for r, cut in enumerate(self.cuts):
+            check(lib().fabber_cuda_set_device(self.devices[r]), "set_device")
+            self.parts[r].buf.data = self._dev(data[:, cut[0]:cut[1]], np.float32)
+        lib().fabber_cuda_set_device(max(self.prev, 0))
+
+    def set_data_device(self, r, ptr):
+        """device pointer ON part r's device to its [T][v1 - v0] series"""
+        self.parts[r].buf.data = ptr
+
+    def set_inputs(self, image_priors=None, init_mean=None, init_cov=None, init_noise=None, lock_centre=None):
+        for r, cut in enumerate(self.cuts):
+            v0, v1 = cut[0], cut[1]
+            check(lib().fabber_cuda_set_device(self.devices[r]), "set_device")
+            buf = self.parts[r].buf
+            for k, img in (image_priors or {}).items():
+                buf.image_prior[k] = self._dev(np.asarray(img)[v0:v1], np.float64)
+            for name, arr in (("init_mean", init_mean), ("init_cov", init_cov), ("init_noise", init_noise),
+                              ("lock_centre", lock_centre)):
+                if arr is not None:
+                    setattr(buf, name, self._dev(np.asarray(arr)[:, v0:v1], np.float64))
+        lib().fabber_cuda_set_device(max(self.prev, 0))
+
+    def launch(self):
+        """synchronous; returns the library's return code. self.last_ms: device-side duration (max over devices)"""
+        L = lib()
         fn = L.fabber_cuda_vb_spatial_multi
         fn.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         fn.restype = C.c_int
-        rc = fn(C.byref(prob), n_parts, C.byref(parts))
+        rc = fn(C.byref(self.spec.prob), len(self.cuts), C.byref(self.parts))
+        L.fabber_cuda_last_multi_ms.restype = C.c_double
+        self.last_ms = float(L.fabber_cuda_last_multi_ms())
+        return rc
+
+    def results(self):
+        spec, N = self.spec, self.N
+        full = {"mean": np.zeros((spec.P, N)), "cov": np.zeros((spec.ncov, N)), "noise": np.zeros((spec.NN, N)),
+                "free_energy": np.zeros(N), "iterations": np.zeros(N, dtype=np.int32),
+                "status": np.zeros(N, dtype=np.int32)}
+        for r, (v0, v1, own0, own1, z0, z1) in enumerate(self.cuts):
+            check(lib().fabber_cuda_set_device(self.devices[r]), "set_device")
+            for k2, v in self.outs[r].items():
+                full[k2][..., own0:own1] = v.to_host()[..., own0 - v0:own1 - v0]
+        lib().fabber_cuda_set_device(max(self.prev, 0))
+        full["spatial_ak"] = self.ak.copy()
+        return full
+
+    def close(self):
+        for r in range(len(self.outs)):
+            lib().fabber_cuda_set_device(self.devices[r])
+            for v in self.outs[r].values():
+                v.close()
+        for d in self.keep:
+            d.close()
+        self.outs, self.keep = [], []
+        lib().fabber_cuda_set_device(max(self.prev, 0))
+
+
+def run_spatial_multi(spec, data, coords, n_parts, devices=None, image_priors=None, init_mean=None, init_cov=None,
+                      init_noise=None, lock_centre=None):
+    """Spatial VB of one volume over `n_parts` z-slabs in ONE process (fabber_cuda_vb_spatial_multi): host arrays in,
+    host arrays out in the caller's voxel order - same signature and result layout as run(spatial=True)."""
+    r = SpatialMultiRun(spec, coords, n_parts, devices)
+    try:
+        r.set_data(data)
+        r.set_inputs(image_priors, init_mean, init_cov, init_noise, lock_centre)
+        rc = r.launch()
         if rc not in (abi.OK, abi.ERR_BAD_VOXEL):
             raise CudaError("spatial multi-device run failed (%d): %s" % (rc, last_error()))
-        full = {"mean": np.zeros((P, N)), "cov": np.zeros((spec.ncov, N)), "noise": np.zeros((NN, N)),
-                "free_energy": np.zeros(N), "iterations": np.zeros(N, dtype=np.int32), "status": np.zeros(N, dtype=np.int32)}
-        for r, (v0, v1, own0, own1, z0, z1) in enumerate(cuts):
-            check(L.fabber_cuda_set_device(devices[r]), "set_device")
-            for k2, v in outs[r].items():
-                h = v.to_host()
-                full[k2][..., own0:own1] = h[..., own0 - v0:own1 - v0]
-        if rc == abi.OK and not prob.allow_bad_voxels and np.count_nonzero(full["status"]):
+        out = r.results()
+        if rc == abi.OK and not spec.prob.allow_bad_voxels and np.count_nonzero(out["status"]):
             rc = abi.ERR_BAD_VOXEL
-        full["spatial_ak"] = ak.copy()
-        full["rc"] = rc
-        full["n_times"] = T
-        return full
+        out["rc"] = rc
+        out["n_times"] = int(np.asarray(data).shape[0])
+        return out
     finally:
-        for r in range(len(outs)):
-            L.fabber_cuda_set_device(devices[r])
-            for v in outs[r].values():
-                v.close()
-        for d in keep:
-            d.close()
-        L.fabber_cuda_set_device(max(prev, 0))
+        r.close()

@@ -290,6 +290,9 @@ typedef struct fabber_cuda_slab_part
     fabber_cuda_vb_buffers buf;
 } fabber_cuda_slab_part;
 int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts, const fabber_cuda_slab_part *parts);
+/* device-side duration of the last fabber_cuda_vb_spatial_multi call with more than one part: CUDA events on every
+ * slab's stream around set-up, iterations and result permutation, maximum over the devices, in ms */
+double fabber_cuda_last_multi_ms(void);
 
 /* Scan status[] on the device; returns 0 if all OK, else the number of failed voxels and the
  * index / code of the first one (synchronises the stream). */

@@ -17,7 +17,17 @@ from fabber_core_b200 import fabber as fab  # noqa: E402
 def main():
     out, case, pinned = sys.argv[1], sys.argv[2], sys.argv[3] == "pinned"
     n, T = 6000, 40
-    if case == "poly_image_lm":
+    shape = None
+    if case == "spatial":
+        # spatial VB through the C API: the library cuts the volume into z-slabs, one per device
+        shape = (16, 15, 12)
+        n = shape[0] * shape[1] * shape[2]
+        y = synth.poly_volume(n, T, 2, seed=79).numpy()
+        opts = {"model": "poly", "degree": 2, "noise": "white", "method": "spatialvb", "param-spatial-priors": "MMM",
+                "max-iterations": 5, "save-mean": True, "save-std": True, "save-mvn": True, "save-noise-mean": True,
+                "save-free-energy": True}
+        extra = {}
+    elif case == "poly_image_lm":
         y = synth.poly_volume(n, T, 2, seed=77).numpy()
         opts = {"model": "poly", "degree": 2, "noise": "white", "method": "vb", "convergence": "lm",
                 "PSP_byname1": "c2", "PSP_byname1_type": "I", "PSP_byname1_image": "c2img", "PSP_byname1_prec": 1e4,
@@ -37,7 +47,8 @@ def main():
     f = fab.Fabber()
     f._set_options(opts)
     mask = np.ones(n, dtype=np.int32)
-    f._trycall(f.clib.fabber_set_extent, f.handle, n, 1, 1, mask, f.errbuf)
+    ext = shape or (n, 1, 1)
+    f._trycall(f.clib.fabber_set_extent, f.handle, ext[0], ext[1], ext[2], mask, f.errbuf)
     for k, v in extra.items():
         f._trycall(f.clib.fabber_set_data, f.handle, k.encode(), 1, np.ascontiguousarray(v), f.errbuf)
     flat = np.ascontiguousarray(y.reshape(-1))
@@ -58,6 +69,8 @@ def main():
     f._trycall(f.clib.fabber_get_model_params, f.handle, len(f.outbuf), f.outbuf, f.errbuf)
     params = f.outbuf.value.decode().splitlines()
     keys = ["mean_" + p for p in params] + ["finalMVN", "noise_means"]
+    if case == "spatial":
+        keys += ["std_" + p for p in params] + ["freeEnergy"]
     if case == "poly_image_lm":
         keys += ["std_" + p for p in params] + ["freeEnergy", "modelfit", "residuals", "freeEnergyHistory", "data"]
     for key in keys:

@@ -53,3 +53,19 @@ def test_pinned_caller_buffer_is_uploaded_in_place(tmp_path):
         for k in one.files:
             if k != "n_devices":
                 assert np.array_equal(one[k], got[k], equal_nan=True), k   # incl. "data": read back from the device
+
+
+def test_spatial_vb_through_the_capi_is_cut_into_z_slabs(tmp_path):
+    """method=spatialvb with several devices: the host library deals z-slabs (own planes + ghost planes) to the
+    devices and runs fabber_cuda_vb_spatial_multi; the outputs equal the one-device run (float32 outputs; the
+    aK sums differ in summation order only)."""
+    env = {"FABBER_B200_MIN_VOXELS_PER_DEVICE": "500"}
+    one = run_worker(tmp_path, "one", "spatial", "0", extra_env=env)
+    three = run_worker(tmp_path, "three", "spatial", device_list(3), extra_env=env)
+    assert int(one["n_devices"][0]) == 1 and int(three["n_devices"][0]) == 3
+    for k in one.files:
+        if k == "n_devices":
+            continue
+        a, b = one[k].astype(np.float64), three[k].astype(np.float64)
+        scale = np.maximum(np.abs(a), np.abs(a).max(axis=-1, keepdims=True) * 1e-6)
+        assert np.max(np.abs(a - b) / np.maximum(scale, 1e-30)) < 2e-6, k
