@@ -259,7 +259,13 @@ template <int NE> struct ExpModel
         return c;
     }
     static constexpr bool HAS_FAST = true;
-    /* every exponent the pass will form stays inside the table method's range */
+    /* The fast pass: table-based exp for the centre rates, and for the two perturbed values of each rate
+     *     exp(-(r + dr) t) = exp(-r t) * exp(-dr t),  exp(z) = 1 + z (1 + z/2 + z^2/6 + z^3/24),  z = -dr t.
+     * dr = r(c +- delta) - r(c) is five orders of magnitude below r (the finite-difference step is 1e-5 |c|,
+     * fwdmodel_linear.cc:157-161), so the series is exact to < 1e-17 once |z| < 1e-3 (z^5/120): the same <= 1 ULP
+     * result a library exp gives, for 6 FP64 instructions instead of 11 - and both perturbed values now share the
+     * rounding error of exp(-r t), which cancels in the difference the Jacobian is made of. Valid when every
+     * exponent stays inside the table method's range and every |dr| t_max < 1e-3; checked once per pass. */
     static FAB_DEV bool fast_ok(const Ctx &c, int T, const double (&p0)[P], const double (&pp)[P], const double (&pn)[P])
     {
         const double t_max = __dmul_rn((double)(T > 0 ? T - 1 : 0), c.dt);
@@ -267,8 +273,17 @@ template <int NE> struct ExpModel
 #pragma unroll
         for (int k = 0; k < NE; k++)
             ok = ok && exp_fast_range_ok(p0[2 * k + 1], t_max) && exp_fast_range_ok(pp[2 * k + 1], t_max)
-                && exp_fast_range_ok(pn[2 * k + 1], t_max);
+                && exp_fast_range_ok(pn[2 * k + 1], t_max) && fabs(pp[2 * k + 1] - p0[2 * k + 1]) * t_max < 1e-3
+                && fabs(pn[2 * k + 1] - p0[2 * k + 1]) * t_max < 1e-3; /* false for NaN */
         return ok;
+    }
+    /* e0 * exp(z) for |z| < 1e-3 */
+    static FAB_DEV double scaled_exp_small(double e0, double z)
+    {
+        double q = fma(z, 1.0 / 24.0, 1.0 / 6.0);
+        q = fma(z, q, 0.5);
+        q = fma(z, q, 1.0);
+        return fma(e0, z * q, e0);
     }
     template <bool FAST> static FAB_DEV double ex(const Ctx &c, double x) { return FAST ? exp_fast(x, c.tab) : exp(x); }
     static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])
@@ -310,8 +325,16 @@ template <int NE> struct ExpModel
             double ta[4];
             ta[0] = __dmul_rn(pp[2 * k], e0[k]);
             ta[1] = __dmul_rn(pn[2 * k], e0[k]);
-            ta[2] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pp[2 * k + 1], tt)));
-            ta[3] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pn[2 * k + 1], tt)));
+            if (FAST)
+            {
+                ta[2] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], (p0[2 * k + 1] - pp[2 * k + 1]) * tt));
+                ta[3] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], (p0[2 * k + 1] - pn[2 * k + 1]) * tt));
+            }
+            else
+            {
+                ta[2] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pp[2 * k + 1], tt)));
+                ta[3] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pn[2 * k + 1], tt)));
+            }
             double out[4];
 #pragma unroll
             for (int q = 0; q < 4; q++)
