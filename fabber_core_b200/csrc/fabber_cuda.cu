@@ -930,6 +930,7 @@ struct SpRun
         sp.ak_partial = get<double>((size_t)SP_AK_BLOCKS * 2 * P);
         sp.fprior_last = get<double>(1);
         sp.ak_sums = get<double>(2 * P);
+        sp.sweep_barrier = get<unsigned>(1);
         sp.n_global = n_global > 0 ? n_global : N;
         sp.ak_phase = 0;
         /* the run's inputs and outputs in hyper-plane-major voxel order (see below) */
@@ -947,7 +948,7 @@ struct SpRun
         status_prev = prob->allow_bad_voxels ? get<int>(N) : status_p;
         if (!grid2vox || !nn_idx || !plane_of || !order || !hist || !rank || !bad || !iota || !plane_sorted || !nnp
             || !plane_starts || !sp.centre || !sp.stats || !sp.m0 || !sp.L0 || !sp.rhs || !sp.logdet || !sp.aK
-            || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last || !sp.ak_sums || !y_p || !mean_p || !cov_p || !noise_p
+            || !sp.ak_hist || !sp.ak_partial || !sp.fprior_last || !sp.ak_sums || !sp.sweep_barrier || !y_p || !mean_p || !cov_p || !noise_p
             || !F_p || !hist_p || !its_p || !status_p || !status_prev)
             return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
         sp.status_prev = status_prev;
@@ -1514,7 +1515,7 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
         /* a slab's hyper-planes hold at most nx * ny voxels... and far fewer CTAs make the barrier cheaper */
         {
             const long long widest = (long long)prob->nx * prob->ny;
-            R.sp.sweep_max_ctas = (int)std::max<long long>(8, std::min<long long>(1 << 20, (widest + SP_SWEEP_BLOCK - 1) / SP_SWEEP_BLOCK));
+            R.sp.sweep_max_ctas = (int)std::max<long long>(8, std::min<long long>(1 << 20, (widest + SP_SWEEP_WORKERS - 1) / SP_SWEEP_WORKERS));
         }
     }
     for (int r = 0; r < W; r++)

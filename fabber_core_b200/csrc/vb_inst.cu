@@ -133,11 +133,7 @@ static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
             return e;
         if (per_sm < 1)
             return cudaErrorLaunchOutOfResources;
-        int want = 2; /* CTAs per SM: the grid-wide barrier gets dearer with every CTA (measured, profiles/) */
-        if (const char *env = getenv("FABBER_SWEEP_CTAS_PER_SM"))
-            want = atoi(env);
-        if (want < 1)
-            want = 1;
+        const int want = 1; /* one CTA of 480 voxel threads + the barrier warp per SM */
         max_grid = sms * per_sm;
         grid = sms * (per_sm > want ? want : per_sm);
     }
@@ -146,6 +142,7 @@ static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
         launch_grid = max_grid / s.sweep_share > 0 ? max_grid / s.sweep_share : 1;
     if (s.sweep_max_ctas > 0 && s.sweep_max_ctas < launch_grid)
         launch_grid = s.sweep_max_ctas;
+    cudaMemsetAsync(s.sweep_barrier, 0, sizeof(unsigned), st); /* the barrier's arrival counter only grows */
     void *args[] = { (void *)&s };
     cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3(launch_grid), dim3(SP_SWEEP_BLOCK), args, 0, st);
     count_launch();

@@ -139,6 +139,7 @@ struct SpArgs
     int ignore_bad;     /* allow_bad_voxels: failed voxels are struck from their neighbours' lists (nbr_alive) */
     SlabLinks link;     /* link.world == 0 on one GPU and in the host-callback slab mode */
     int sweep_max_ctas; /* > 0: cap on the cooperative sweep grid (small slabs: the barrier gets cheaper) */
+    unsigned *sweep_barrier; /* [1] arrival counter of the sweep's grid-wide barrier, zeroed before every launch */
     int sweep_share;    /* > 1: that many slabs share this GPU and spin on each other's flags - each sweep grid is
                            held to 1/share of what the GPU can keep resident, so that all of them fit */
     double q1, q2, speed;
@@ -536,11 +537,39 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
 }
 
 /* ---- ordered sweep: MRF prior means + posterior means, in place, plane by plane ------------------------
- * One persistent cooperative kernel walks the hyper-planes with a grid-wide barrier between them (a
- * launch per plane costs ~13 us each, 64 % of the spatial step in the round-1 launch list). Neighbour
- * means are read with ld.global.cg: they were written by other SMs one barrier ago and must not be
- * served from a stale L1 line. */
-constexpr int SP_SWEEP_BLOCK = 256;
+ * One persistent kernel walks the hyper-planes with a grid-wide barrier between them (a launch per plane
+ * costs ~13 us each, 64 % of the spatial step in the round-1 launch list). Neighbour means are read with
+ * ld.global.cg: they were written by other SMs one barrier ago and must not be served from a stale L1 line.
+ *
+ * The step from one plane to the next is pure latency (766 planes at 256^3, a few thousand voxels each), so the
+ * barrier is hand-made and SPLIT: a CTA is 480 voxel threads plus ONE EXTRA WARP that does nothing but the
+ * barrier. After the voxel threads have stored a plane (bar.sync), that warp's leader fences and ARRIVES
+ * (one atomic on a counter that only grows), the voxel threads meanwhile issue the next plane's
+ * neighbour-independent loads (DRAM latency), and only then everyone WAITS for the leader to see all CTAs
+ * arrived. With cooperative-groups' grid.sync() the fence sat in a warp that had those loads in flight and so
+ * put a DRAM round trip on the critical path of every plane. The launch stays cooperative: every CTA must be
+ * resident (one per SM). */
+constexpr int SP_SWEEP_WORKERS = 480; /* 15 warps + the barrier warp = 16: four per SM sub-partition, 128 registers each */
+constexpr int SP_SWEEP_BLOCK = SP_SWEEP_WORKERS + 32;
+
+struct SweepBarrier
+{
+    unsigned *counter; /* zeroed by the host before the launch */
+    unsigned target;
+    FAB_DEV void arrive(unsigned n_ctas)
+    {
+        target += n_ctas;
+        __threadfence(); /* release: this CTA's stores (ordered before us by bar.sync) before the arrival */
+        atomicAdd(counter, 1u);
+    }
+    FAB_DEV void wait()
+    {
+        while (*(volatile unsigned *)counter < target)
+        {
+        }
+        __threadfence(); /* acquire */
+    }
+};
 
 template <int P> struct SweepVoxel
 {
@@ -628,11 +657,12 @@ template <int P> struct SweepVoxel
     }
 };
 
-template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kernel(const __grid_constant__ SpArgs s)
+template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __grid_constant__ SpArgs s)
 {
-    namespace cg = cooperative_groups;
-    cg::grid_group grid = cg::this_grid();
-    const int stride = gridDim.x * blockDim.x, tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool worker = threadIdx.x < SP_SWEEP_WORKERS;
+    const bool leader = threadIdx.x == SP_SWEEP_WORKERS; /* lane 0 of the barrier warp */
+    const int stride = gridDim.x * SP_SWEEP_WORKERS, tid = blockIdx.x * SP_SWEEP_WORKERS + threadIdx.x;
+    SweepBarrier bar = { s.sweep_barrier, 0u };
     const SlabLinks &lk = s.link;
     const bool slab = lk.world > 1;
     const bool has_dn = slab && lk.rank > 0, has_up = slab && lk.rank + 1 < lk.world;
@@ -640,13 +670,13 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
     if (has_up)
     {
         /* the upper ghost plane must hold the slab above's values of the PREVIOUS iteration */
-        if (threadIdx.x == 0)
+        if (leader)
             slab_wait(lk.flags + SLAB_FLAG_HI, (unsigned long long)s.it, lk.error);
         __syncthreads();
     }
     SweepVoxel<P> cur;
     bool have = false;
-    if (s.plane_first < s.plane_last)
+    if (worker && s.plane_first < s.plane_last)
     {
         const int b = s.plane_starts[s.plane_first], e = s.plane_starts[s.plane_first + 1];
         if (b + tid < e)
@@ -663,33 +693,47 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
          * hyper-plane h-1: wait until that slab has published it. */
         if (has_dn && e > b && h >= lk.own_z0 && h <= lk.own_z0 + lk.inplane_span)
         {
-            if (threadIdx.x == 0)
+            if (leader)
                 slab_wait(lk.flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h, lk.error);
             __syncthreads();
         }
-        if (have)
-            cur.finish(s);
-        for (int i = b + tid + stride; i < e; i += stride) /* planes wider than the grid */
+        if (worker)
         {
-            SweepVoxel<P> extra;
-            extra.load_static(s, i);
-            extra.finish(s);
+            if (have)
+                cur.finish(s);
+            for (int i = b + tid + stride; i < e; i += stride) /* planes wider than the grid */
+            {
+                SweepVoxel<P> extra;
+                extra.load_static(s, i);
+                extra.finish(s);
+            }
         }
         have = false;
-        if (h + 1 < s.plane_last)
+        const bool sync = e > b; /* uniform across the grid: every thread skips the same empty planes */
+        if (sync)
+        {
+            __syncthreads(); /* this CTA's stores of plane h are issued */
+            if (leader)
+                bar.arrive(gridDim.x);
+        }
+        if (worker && h + 1 < s.plane_last)
         {
             const int b2 = e, e2 = s.plane_starts[h + 2];
             if (b2 + tid < e2)
             {
-                cur.load_static(s, b2 + tid); /* prefetch: overlaps the barrier */
+                cur.load_static(s, b2 + tid); /* prefetch: in flight while the barrier completes */
                 have = true;
             }
         }
-        if (e > b) /* uniform across the grid: every thread skips the same empty planes */
-            grid.sync();
+        if (sync)
+        {
+            if (leader)
+                bar.wait();
+            __syncthreads();
+        }
         /* hyper-plane h is done everywhere on this GPU: tell the slab above (only the planes that hold voxels of
          * the top own plane z = own_z1 - 1 matter to it) */
-        if (has_up && tid == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span)
+        if (has_up && leader && blockIdx.x == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span)
         {
             __threadfence_system();
             st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h + 1);
@@ -700,7 +744,7 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
     /* ---- end of the sweep ------------------------------------------------------------------------------
      * (a) no ordered sweep in this run (no 'M' / 'm' parameter): the means were written by sp_theta; the slab
      *     above still needs this iteration's values of our top plane for its aK sums */
-    if (has_up && s.plane_first >= s.plane_last)
+    if (worker && has_up && s.plane_first >= s.plane_last)
     {
         const size_t N = (size_t)s.v.N;
         for (int v = tid; v < s.v.N; v += stride)
@@ -714,7 +758,7 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
     /* (b) our bottom own plane becomes the slab below's upper ghost - only now: during its own sweep that slab
      *     had to see last iteration's values, and it finished the planes that read them before we could finish
      *     ours (we waited for its flag plane by plane) */
-    if (has_dn)
+    if (worker && has_dn)
     {
         const size_t N = (size_t)s.v.N;
         for (int j = tid; j < lk.n_dn; j += stride)
@@ -725,14 +769,19 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK) sp_sweep_kern
         }
     }
     __threadfence_system();
-    grid.sync();
-    if (tid == 0)
+    __syncthreads();
+    if (leader)
     {
-        __threadfence_system();
-        if (has_up) /* everything up to the last hyper-plane is forwarded: releases the next iteration's waits */
-            st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + SLAB_IT_STRIDE);
-        if (has_dn)
-            st_release_sys(lk.dn_flags + SLAB_FLAG_HI, (unsigned long long)s.it + 1);
+        bar.arrive(gridDim.x);
+        bar.wait();
+        if (blockIdx.x == 0)
+        {
+            __threadfence_system();
+            if (has_up) /* everything up to the last hyper-plane is forwarded: releases the next iteration's waits */
+                st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + SLAB_IT_STRIDE);
+            if (has_dn)
+                st_release_sys(lk.dn_flags + SLAB_FLAG_HI, (unsigned long long)s.it + 1);
+        }
     }
 }
 

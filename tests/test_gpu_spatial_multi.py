@@ -35,7 +35,7 @@ def spec_for(shape, model, T, **kw):
     return sp
 
 
-def check_equal(multi, one, P, tol):
+def check_equal(multi, one, P, tol, ak_tol=None):
     assert np.array_equal(multi["status"], one["status"])
     assert np.array_equal(multi["iterations"], one["iterations"])
     std = np.sqrt(np.abs(np.stack([one["cov"][tri(i, i)] for i in range(P)])))
@@ -43,7 +43,7 @@ def check_equal(multi, one, P, tol):
     for i in range(P):
         assert maxrel(multi["cov"][tri(i, i)], one["cov"][tri(i, i)]) < tol
     assert maxrel(multi["noise"], one["noise"]) < tol
-    assert maxrel(multi["spatial_ak"], one["spatial_ak"]) < tol
+    assert maxrel(multi["spatial_ak"], one["spatial_ak"]) < (ak_tol or tol)
     assert maxrel(multi["free_energy"], one["free_energy"], scale=1.0) < tol
 
 
@@ -60,17 +60,21 @@ def test_one_part_is_the_one_gpu_run():
 
 @pytest.mark.parametrize("n_parts", [2, 3, 4])
 def test_mrf_slabs_equal_the_sequential_sweep(n_parts):
-    """'MMMM' on the bi-exponential model (BASELINE config 5's prior set), 10 iterations: same bound as the
-    host-callback slab path (1e-6 posterior std; a stale boundary plane gives tens of std here)."""
+    """'MMMM' on the bi-exponential model (BASELINE config 5's prior set). The slab run differs from the one-GPU
+    run ONLY in the summation order of the aK partial sums (1 ULP): after 3 iterations the results agree to 1e-8;
+    over 10 iterations this chaotic trajectory amplifies that ULP (two CPU builds of the reference drift apart by
+    O(1) here, tests/test_teacher_forced_harness.py), so the means are held to 1e-3 posterior std there - a stale
+    boundary plane gives tens of std - and aK to 1e-6."""
     shape = (8, 8, 8)
     y = synth.biexp_volume(8 * 8 * 8, 96, 0.02, 0.02, seed=83, smooth_shape=shape).numpy()
     coords = grid_coords(*shape)
-    kw = dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=10, need_f=True,
-              param_overrides={"r2": {"mean": 6.0}})
-    one = device.run(spec_for(shape, "exp", 96, **kw), y, spatial=True, coords=coords)
-    multi = device.run_spatial_multi(spec_for(shape, "exp", 96, **kw), y, coords, n_parts)
-    assert np.all(one["status"] == 0)
-    check_equal(multi, one, 4, 1e-6)
+    for its, tol in ((3, 1e-8), (10, 1e-3)):
+        kw = dict(num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=its, need_f=True,
+                  param_overrides={"r2": {"mean": 6.0}})
+        one = device.run(spec_for(shape, "exp", 96, **kw), y, spatial=True, coords=coords)
+        multi = device.run_spatial_multi(spec_for(shape, "exp", 96, **kw), y, coords, n_parts)
+        assert np.all(one["status"] == 0)
+        check_equal(multi, one, 4, tol, ak_tol=min(tol, 1e-6))
 
 
 def test_three_iterations_agree_to_rounding():

@@ -95,16 +95,19 @@ def test_mrf_slab_run_equals_the_sequential_sweep(world, block_planes):
     shape = (8, 8, 8)
     n = 8 * 8 * 8
     y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=83, smooth_shape=shape).numpy()
-    mk = lambda: abi.ProblemSpec("exp", 96, num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=10,
-                                 need_f=True, param_overrides={"r2": {"mean": 6.0}})
-    one = single(mk, y, shape)
-    slab = run_emulated(mk, y, shape, world, block_planes)
-    assert np.all(slab["status"] == 0) and np.all(one["status"] == 0)
-    std = np.sqrt(np.stack([one["cov"][tri(i, i)] for i in range(4)]))
-    assert float(np.max(np.abs(slab["mean"] - one["mean"]) / std)) < 1e-6
-    assert maxrel(slab["spatial_ak"], one["spatial_ak"]) < 1e-6
-    assert maxrel(slab["noise"], one["noise"]) < 1e-6
-    assert maxrel(slab["free_energy"], one["free_energy"]) < 1e-6
+    # 3 iterations: the 1-ULP summation-order difference of the aK sums has not been amplified yet; 10: this
+    # chaotic trajectory amplifies it (a stale boundary plane would still show as tens of std)
+    for its, tol in ((3, 1e-8), (10, 1e-3)):
+        mk = lambda: abi.ProblemSpec("exp", 96, num_exps=2, dt=0.02, prior_types=list("MMMM"), max_iterations=its,
+                                     need_f=True, param_overrides={"r2": {"mean": 6.0}})
+        one = single(mk, y, shape)
+        slab = run_emulated(mk, y, shape, world, block_planes)
+        assert np.all(slab["status"] == 0) and np.all(one["status"] == 0)
+        std = np.sqrt(np.stack([one["cov"][tri(i, i)] for i in range(4)]))
+        assert float(np.max(np.abs(slab["mean"] - one["mean"]) / std)) < tol
+        assert maxrel(slab["spatial_ak"], one["spatial_ak"]) < min(tol, 1e-6)
+        assert maxrel(slab["noise"], one["noise"]) < tol
+        assert maxrel(slab["free_energy"], one["free_energy"], scale=1.0) < tol
 
 
 def test_mrf_m_and_p_mix_on_uneven_slabs():
