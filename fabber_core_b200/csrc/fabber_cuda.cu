@@ -1035,6 +1035,7 @@ struct SpRun
         sp.n_planes = n_planes + 1;
         sp.nn_idx = nnp;
         sp.order = order;
+        sp.last_pos = rank + (N - 1);
 
         /* inputs into plane-major order */
         permute_rows<float, true>(buf.data, y_p, order, prob->n_times, N, st);
@@ -1487,13 +1488,13 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
         SpRun &R = runs[r];
         cudaSetDevice(parts[r].device);
         flags[r] = R.get<unsigned long long>(SLAB_FLAG_MAIL + SLAB_MAX_WORLD);
-        mail[r] = R.get<double>((size_t)2 * W * 2 * P);
+        mail[r] = R.get<double>((size_t)2 * W * (2 * P + 1));
         err[r] = R.get<int>(1);
         int *up_pos = R.get<int>(R.N);
         if (!flags[r] || !mail[r] || !err[r] || !up_pos)
             return fail(FABBER_CUDA_ERR_CUDA, "out of device memory for the spatial VB state");
         cudaMemsetAsync(flags[r], 0, (SLAB_FLAG_MAIL + SLAB_MAX_WORLD) * sizeof(unsigned long long), R.st);
-        cudaMemsetAsync(mail[r], 0, (size_t)2 * W * 2 * P * sizeof(double), R.st);
+        cudaMemsetAsync(mail[r], 0, (size_t)2 * W * (2 * P + 1) * sizeof(double), R.st);
         cudaMemsetAsync(err[r], 0, sizeof(int), R.st);
         cudaMemsetAsync(up_pos, 0xff, (size_t)R.N * sizeof(int), R.st);
         mark_ghost_range_kernel<<<R.gridN, 256, 0, R.st>>>(R.order, R.N, parts[r].own0 - parts[r].v0,

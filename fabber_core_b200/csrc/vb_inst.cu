@@ -102,7 +102,18 @@ static cudaError_t launch_sp_noise(const SpArgs &s, cudaStream_t st)
 }
 static cudaError_t launch_sp_ak_partial(const SpArgs &s, cudaStream_t st)
 {
-    sp_ak_partial_kernel<M::P><<<SP_AK_BLOCKS, 256, 0, st>>>(s);
+    const bool slab = s.link.world > 1;
+    if (s.ignore_bad)
+    {
+        if (slab)
+            sp_ak_partial_kernel<M::P, true, true><<<SP_AK_BLOCKS, 256, 0, st>>>(s);
+        else
+            sp_ak_partial_kernel<M::P, true, false><<<SP_AK_BLOCKS, 256, 0, st>>>(s);
+    }
+    else if (slab)
+        sp_ak_partial_kernel<M::P, false, true><<<SP_AK_BLOCKS, 256, 0, st>>>(s);
+    else
+        sp_ak_partial_kernel<M::P, false, false><<<SP_AK_BLOCKS, 256, 0, st>>>(s);
     count_launch();
     return cudaGetLastError();
 }
@@ -122,7 +133,14 @@ static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
 {
     /* persistent cooperative kernel: as many CTAs as can be co-resident (grid-wide barrier inside) */
     static int grid = 0, max_grid = 0;
-    auto kern = sp_sweep_kernel<M::P>;
+    /* one instantiation per (failed voxels struck from neighbour lists?, z-slab coupling?): both are uniform for
+     * a launch, and the plain one-GPU sweep must not carry the others' look-ups */
+    const bool slab = s.link.world > 1;
+    const void *kern_any = s.ignore_bad ? (slab ? (const void *)sp_sweep_kernel<M::P, true, true>
+                                                : (const void *)sp_sweep_kernel<M::P, true, false>)
+                                        : (slab ? (const void *)sp_sweep_kernel<M::P, false, true>
+                                                : (const void *)sp_sweep_kernel<M::P, false, false>);
+    auto kern = sp_sweep_kernel<M::P, true, true>; /* the largest: sizes the grid for all four */
     if (grid == 0)
     {
         int dev = 0, sms = 0, per_sm = 0;
@@ -144,7 +162,7 @@ static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
         launch_grid = s.sweep_max_ctas;
     cudaMemsetAsync(s.sweep_barrier, 0, sizeof(unsigned), st); /* the barrier's arrival counter only grows */
     void *args[] = { (void *)&s };
-    cudaError_t e = cudaLaunchCooperativeKernel((const void *)kern, dim3(launch_grid), dim3(SP_SWEEP_BLOCK), args, 0, st);
+    cudaError_t e = cudaLaunchCooperativeKernel(kern_any, dim3(launch_grid), dim3(SP_SWEEP_BLOCK), args, 0, st);
     count_launch();
     return e;
 }

@@ -19,6 +19,7 @@
  *                          difference quotient of the parameter transform, up to the rounding noise of the
  *                          subtraction, so the pass needs one evaluation per sample instead of 2P+1
  *                          (recentre_loop in vb_voxelwise.cuh; opt-in with FABBER_B200_BASIS_JACOBIAN=1)
+ *   HAS_SERIES / series_ok() / eval_fd_series()   optional third level, cheaper still (exp model)
  *   HAS_FAST / fast_ok()   optional: a cheaper eval_fd<true> that is valid only for a range of parameters
  *                          (exp: the table-based exponential of vb_exp.cuh needs |r t| < 708); the pass
  *                          checks fast_ok() once, outside the time loop, and otherwise runs eval_fd<false>
@@ -36,6 +37,16 @@
 
 namespace fab
 {
+/* does the model offer the optional eval_fd_series level? (plug-in models need not mention it) */
+template <class M, class = void> struct ModelHasSeries
+{
+    static constexpr bool value = false;
+};
+template <class M> struct ModelHasSeries<M, decltype((void)M::HAS_SERIES)>
+{
+    static constexpr bool value = M::HAS_SERIES;
+};
+
 struct VbArgs;
 
 /* ---------------------------------------------------------------------------------------------
@@ -259,13 +270,7 @@ template <int NE> struct ExpModel
         return c;
     }
     static constexpr bool HAS_FAST = true;
-    /* The fast pass: table-based exp for the centre rates, and for the two perturbed values of each rate
-     *     exp(-(r + dr) t) = exp(-r t) * exp(-dr t),  exp(z) = 1 + z (1 + z/2 + z^2/6 + z^3/24),  z = -dr t.
-     * dr = r(c +- delta) - r(c) is five orders of magnitude below r (the finite-difference step is 1e-5 |c|,
-     * fwdmodel_linear.cc:157-161), so the series is exact to < 1e-17 once |z| < 1e-3 (z^5/120): the same <= 1 ULP
-     * result a library exp gives, for 6 FP64 instructions instead of 11 - and both perturbed values now share the
-     * rounding error of exp(-r t), which cancels in the difference the Jacobian is made of. Valid when every
-     * exponent stays inside the table method's range and every |dr| t_max < 1e-3; checked once per pass. */
+    /* every exponent the pass will form stays inside the table method's range */
     static FAB_DEV bool fast_ok(const Ctx &c, int T, const double (&p0)[P], const double (&pp)[P], const double (&pn)[P])
     {
         const double t_max = __dmul_rn((double)(T > 0 ? T - 1 : 0), c.dt);
@@ -273,14 +278,33 @@ template <int NE> struct ExpModel
 #pragma unroll
         for (int k = 0; k < NE; k++)
             ok = ok && exp_fast_range_ok(p0[2 * k + 1], t_max) && exp_fast_range_ok(pp[2 * k + 1], t_max)
-                && exp_fast_range_ok(pn[2 * k + 1], t_max) && fabs(pp[2 * k + 1] - p0[2 * k + 1]) * t_max < 1e-3
-                && fabs(pn[2 * k + 1] - p0[2 * k + 1]) * t_max < 1e-3; /* false for NaN */
+                && exp_fast_range_ok(pn[2 * k + 1], t_max);
         return ok;
     }
-    /* e0 * exp(z) for |z| < 1e-3 */
+    /* A third, still cheaper pass (optional model hook, see recentre_stats): the two perturbed values of each
+     * rate by SERIES from the centre exponential,
+     *     exp(-(r + dr) t) = exp(-r t) * exp(z),  exp(z) = 1 + z (1 + z/2 + z^2/6 + z^3/24 + z^4/120),  z = -dr t.
+     * dr = r(c +- delta) - r(c) is five orders of magnitude below r (the finite-difference step is 1e-5 |c|,
+     * fwdmodel_linear.cc:157-161), so the series is exact to < 1e-17 once |z| < 4e-3 (z^6/720): the same <= 1 ULP
+     * result a library exp gives, for 7 FP64 instructions instead of 11 - and both perturbed values now share the
+     * rounding error of exp(-r t), which cancels in the difference the Jacobian is made of. Valid when the table
+     * pass is valid and every |dr| t_max < 4e-3; checked once per pass, per voxel. */
+    static constexpr bool HAS_SERIES = true;
+    static FAB_DEV bool series_ok(const Ctx &c, int T, const double (&p0)[P], const double (&pp)[P], const double (&pn)[P])
+    {
+        const double t_max = __dmul_rn((double)(T > 0 ? T - 1 : 0), c.dt);
+        bool ok = true;
+#pragma unroll
+        for (int k = 0; k < NE; k++)
+            ok = ok && fabs(pp[2 * k + 1] - p0[2 * k + 1]) * t_max < 4e-3
+                && fabs(pn[2 * k + 1] - p0[2 * k + 1]) * t_max < 4e-3; /* false for NaN */
+        return ok;
+    }
+    /* e0 * exp(z) for |z| < 4e-3 */
     static FAB_DEV double scaled_exp_small(double e0, double z)
     {
-        double q = fma(z, 1.0 / 24.0, 1.0 / 6.0);
+        double q = fma(z, 1.0 / 120.0, 1.0 / 24.0);
+        q = fma(z, q, 1.0 / 6.0);
         q = fma(z, q, 0.5);
         q = fma(z, q, 1.0);
         return fma(e0, z * q, e0);
@@ -305,6 +329,17 @@ template <int NE> struct ExpModel
     static FAB_DEV void eval_fd(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
+        eval_fd_impl<FAST, false>(c, smp, p0, pp, pn, g, gp, gn);
+    }
+    static FAB_DEV void eval_fd_series(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
+        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
+    {
+        eval_fd_impl<true, true>(c, smp, p0, pp, pn, g, gp, gn);
+    }
+    template <bool FAST, bool SERIES>
+    static FAB_DEV void eval_fd_impl(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
+        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
+    {
         const double tt = smp.tt;
         double e0[NE], term[NE];
 #pragma unroll
@@ -325,7 +360,7 @@ template <int NE> struct ExpModel
             double ta[4];
             ta[0] = __dmul_rn(pp[2 * k], e0[k]);
             ta[1] = __dmul_rn(pn[2 * k], e0[k]);
-            if (FAST)
+            if (SERIES)
             {
                 ta[2] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], (p0[2 * k + 1] - pp[2 * k + 1]) * tt));
                 ta[3] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], (p0[2 * k + 1] - pn[2 * k + 1]) * tt));

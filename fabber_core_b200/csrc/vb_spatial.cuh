@@ -119,6 +119,7 @@ struct SpArgs
     double *ak_hist;     /* [max_it + 1][P] (device) */
     double *ak_partial;  /* [ak_blocks][2][P] */
     double *fprior_last; /* [1] stale Fprior of the last voxel (inference_vb.cc:700) */
+    const int *last_pos; /* [1] plane-major position of the caller's last voxel */
     const int *order;    /* original voxel index of each (plane-major) position */
     const int *plane_starts; /* [n_planes + 1] offsets into order (device) */
     int n_planes;
@@ -151,11 +152,12 @@ FAB_DEV bool is_spatial_type(char t) { return t == 'M' || t == 'm' || t == 'P' |
  * neighbours' lists, so it no longer counts towards nn and its stale mean no longer feeds the MRF prior mean
  * or the aK sums. The lists here are static; a neighbour is skipped when its status word reports a failure.
  * Ghost voxels of a z-slab are alive (their owner updates them). */
-FAB_DEV bool nbr_alive(bool ignore_bad, const int *status, int n)
+template <bool IGNORE> FAB_DEV bool nbr_alive(const int *status, int n)
 {
     if (n < 0)
         return false;
-    if (!ignore_bad) /* without allow-bad-voxels the first failure ends the run: no status look-ups */
+    if (!IGNORE) /* without allow-bad-voxels the first failure ends the run: no status look-ups (compile time: a
+                    run-time test here cost the latency-bound kernels 15-25 %, measured) */
         return true;
     const int st = status[n];
     return st == 0 || st == FABBER_VOX_GHOST;
@@ -242,7 +244,8 @@ template <class Model> __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCK
 }
 
 /* ---- aK: per-block partial sums of trace_term and term2 (priors.cc:233-294) ------------------------ */
-template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(const __grid_constant__ SpArgs s)
+template <int P, bool IGNORE, bool SLAB>
+__global__ void __launch_bounds__(256) sp_ak_partial_kernel(const __grid_constant__ SpArgs s)
 {
     const VbArgs &a = s.v;
     const size_t N = (size_t)a.N;
@@ -261,7 +264,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + v];
-            if (!nbr_alive(s.ignore_bad != 0, a.status, nbr[j])) /* every failure so far: CalculateaK runs at v == 1 */
+            if (!nbr_alive<IGNORE>(a.status, nbr[j])) /* every failure so far: CalculateaK runs at v == 1 */
                 nbr[j] = -1;
             nn += nbr[j] >= 0;
         }
@@ -285,7 +288,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_partial_kernel(con
 #pragma unroll
             for (int j = 0; j < 6; j++)
                 if (nbr[j] >= 0) /* slab mode: ghosts are written by a peer GPU, never serve them from L1 */
-                    SwK += wK - (s.link.world > 1 ? __ldcg(a.mean + k * N + nbr[j]) : a.mean[k * N + nbr[j]]);
+                    SwK += wK - (SLAB ? __ldcg(a.mean + k * N + nbr[j]) : a.mean[k * N + nbr[j]]);
             if (ty == 'p' || ty == 'm')
                 SwK += wK * (dims * 2 - (double)nn);
             if (ty == 'm' || ty == 'M')
@@ -359,15 +362,37 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
             s.ak_sums[threadIdx.x] = sums[threadIdx.x];
         return;
     }
-    if (s.ak_update && s.ak_phase == 3)
+    if (s.ak_phase == 3)
     {
-        /* device-driven slab mode: all-gather of the partial sums through the slabs' mailboxes, then the
-         * same fixed-order sum on every slab (priors.cc:233-343: two global sums per spatial parameter) */
+        /* device-driven slab mode: all-gather through the slabs' mailboxes, then the same fixed-order sum on
+         * every slab (priors.cc:233-343: two global sums per spatial parameter). The mail also carries the ARD
+         * free-energy term of the volume's LAST voxel (inference_vb.cc:700 adds that voxel's stale Fprior to every
+         * voxel's F): only the top slab owns it, every slab needs it. Runs every iteration. */
+        constexpr int MP = 2 * P + 1;
         const int W = s.link.world, me = s.link.rank, slot = s.it & 1;
-        if (threadIdx.x < 2 * P * W)
+        __shared__ double fprior_mail;
+        if (threadIdx.x == 0)
         {
-            const int q = threadIdx.x / (2 * P), j = threadIdx.x - q * 2 * P;
-            s.link.mail[q][((size_t)slot * W + me) * 2 * P + j] = sums[j];
+            double fp = 0.0;
+            if (me == W - 1)
+            {
+                const size_t N = (size_t)a.N;
+                const int pos = *s.last_pos;
+                for (int k = 0; k < P; k++)
+                    if (a.params[k].prior_type == 'A')
+                    {
+                        const double mk = a.mean[k * N + pos];
+                        const double bb = 2 / (mk * mk + a.cov[tri(k, k) * N + pos]);
+                        fp += -1.5 * (log(bb) + digamma_fsl(0.5)) - 0.5 - gammaln(0.5) - 0.5 * log(bb);
+                    }
+            }
+            fprior_mail = fp;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < MP * W; i += blockDim.x)
+        {
+            const int q = i / MP, j = i - q * MP;
+            s.link.mail[q][((size_t)slot * W + me) * MP + j] = j < 2 * P ? (s.ak_update ? sums[j] : 0.0) : fprior_mail;
         }
         __threadfence_system();
         __syncthreads();
@@ -380,9 +405,11 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
         {
             double x = 0.0;
             for (int q = 0; q < W; q++)
-                x += __ldcg(s.link.mail[me] + ((size_t)slot * W + q) * 2 * P + threadIdx.x);
+                x += __ldcg(s.link.mail[me] + ((size_t)slot * W + q) * MP + threadIdx.x);
             sums[threadIdx.x] = x;
         }
+        if (threadIdx.x == 0)
+            *s.fprior_last = __ldcg(s.link.mail[me] + ((size_t)slot * W + (W - 1)) * MP + 2 * P);
         __syncthreads();
     }
     const int k = threadIdx.x;
@@ -434,7 +461,7 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
     int nn = 0;
 #pragma unroll
     for (int j = 0; j < 6; j++)
-        nn += nbr_alive(s.ignore_bad != 0, s.status_prev, s.nn_idx[j * N + v]);
+        nn += s.ignore_bad ? nbr_alive<true>(s.status_prev, s.nn_idx[j * N + v]) : (s.nn_idx[j * N + v] >= 0);
     const int dims = s.spatial_dims;
     double Fprior = 0.0;
     bool coupled[P];
@@ -486,7 +513,9 @@ template <int P> __global__ void __launch_bounds__(VB_BLOCK) sp_theta_kernel(con
             L0[k] = p.prior_prec;
         }
     }
-    if (s.order[v] == a.N - 1) /* the reference's last voxel: its Fprior goes stale into the second loop */
+    /* the reference's last voxel: its Fprior goes stale into the second loop (z-slabs: the top slab owns it, the
+     * others got its value by mail in sp_ak_final) */
+    if (s.order[v] == a.N - 1 && (s.link.world <= 1 || s.link.rank == s.link.world - 1))
         *s.fprior_last = Fprior;
     const double phi = a.noise[0 * N + v] * a.noise[1 * N + v];
     double Lam[NT], Sig[NT], ld;
@@ -571,7 +600,7 @@ struct SweepBarrier
     }
 };
 
-template <int P> struct SweepVoxel
+template <int P, bool IGNORE, bool SLAB> struct SweepVoxel
 {
     static constexpr int NT = NTri<P>::value;
     int v, nbr[6];
@@ -590,7 +619,7 @@ template <int P> struct SweepVoxel
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + pos];
-            if (!nbr_alive(s.ignore_bad != 0, s.status_prev, nbr[j]))
+            if (!nbr_alive<IGNORE>(s.status_prev, nbr[j]))
                 nbr[j] = -1;
         }
 #pragma unroll
@@ -641,7 +670,7 @@ template <int P> struct SweepVoxel
 #pragma unroll
         for (int i = 0; i < P; i++)
             __stcg(a.mean + i * N + v, mn[i]);
-        if (s.link.up_pos)
+        if (SLAB && s.link.up_pos)
         {
             /* top own plane of a z-slab: the slab above sweeps this voxel's +z neighbour one hyper-plane later
              * and must see THIS sweep's value - store it straight into that slab's lower ghost voxel */
@@ -657,14 +686,15 @@ template <int P> struct SweepVoxel
     }
 };
 
-template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __grid_constant__ SpArgs s)
+template <int P, bool IGNORE, bool SLAB>
+__global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __grid_constant__ SpArgs s)
 {
     const bool worker = threadIdx.x < SP_SWEEP_WORKERS;
     const bool leader = threadIdx.x == SP_SWEEP_WORKERS; /* lane 0 of the barrier warp */
     const int stride = gridDim.x * SP_SWEEP_WORKERS, tid = blockIdx.x * SP_SWEEP_WORKERS + threadIdx.x;
     SweepBarrier bar = { s.sweep_barrier, 0u };
     const SlabLinks &lk = s.link;
-    const bool slab = lk.world > 1;
+    const bool slab = SLAB && lk.world > 1;
     const bool has_dn = slab && lk.rank > 0, has_up = slab && lk.rank + 1 < lk.world;
     const unsigned long long fwd_base = (unsigned long long)s.it * SLAB_IT_STRIDE;
     if (has_up)
@@ -674,7 +704,7 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_k
             slab_wait(lk.flags + SLAB_FLAG_HI, (unsigned long long)s.it, lk.error);
         __syncthreads();
     }
-    SweepVoxel<P> cur;
+    SweepVoxel<P, IGNORE, SLAB> cur;
     bool have = false;
     if (worker && s.plane_first < s.plane_last)
     {
@@ -703,7 +733,7 @@ template <int P> __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_k
                 cur.finish(s);
             for (int i = b + tid + stride; i < e; i += stride) /* planes wider than the grid */
             {
-                SweepVoxel<P> extra;
+                SweepVoxel<P, IGNORE, SLAB> extra;
                 extra.load_static(s, i);
                 extra.finish(s);
             }

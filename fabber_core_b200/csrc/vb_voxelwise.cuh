@@ -135,7 +135,7 @@ template <int P> struct Stats
  * 23 + P FP64 instructions per sample instead of 54 at P = 4. The results stay inside the reference's own
  * noise floor (same parity rule, same tests). OPT-IN (FABBER_B200_BASIS_JACOBIAN=1): the default is the reference's
  * literal 2P+1 evaluations per sample. */
-template <class Model, int NPHI, bool FAST, bool CHECK, bool BASIS>
+template <class Model, int NPHI, int FAST, bool CHECK, bool BASIS>
 FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
     const double (&p0)[Model::P], const double (&pp)[Model::P], const double (&pn)[Model::P],
     const double (&rden)[Model::P], Stats<Model::P> (&S)[NPHI], bool &bad_g, bool &bad_j)
@@ -179,7 +179,10 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
         else
         {
             double gp[P], gn[P];
-            Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+            if constexpr (FAST == 2)
+                Model::eval_fd_series(mc, smp, p0, pp, pn, g, gp, gn);
+            else
+                Model::template eval_fd<(FAST != 0)>(mc, smp, p0, pp, pn, g, gp, gn);
 #pragma unroll
             for (int i = 0; i < P; i++)
                 J[i] = (gp[i] - gn[i]) * rden[i];
@@ -261,18 +264,26 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
      * argument of this pass is inside its range - checked once here, not per sample */
     constexpr bool CHECK = NPHI > 1; /* masked samples never reach the sums: test them one by one */
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
+    bool series = false; /* optional third level (exp: perturbed-rate exponentials by series) */
+    if constexpr (ModelHasSeries<Model>::value)
+        series = fast && Model::series_ok(mc, a.T, p0, pp, pn);
     bool basis = false; /* opt-in, and only for models that hand out their basis row */
     if constexpr (Model::LINEAR)
         basis = a.basis_jacobian != 0;
     if (basis)
     {
         if constexpr (Model::LINEAR)
-            recentre_loop<Model, NPHI, false, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+            recentre_loop<Model, NPHI, 0, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+    }
+    else if (series)
+    {
+        if constexpr (ModelHasSeries<Model>::value)
+            recentre_loop<Model, NPHI, 2, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     }
     else if (fast)
-        recentre_loop<Model, NPHI, true, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop<Model, NPHI, 1, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     else
-        recentre_loop<Model, NPHI, false, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop<Model, NPHI, 0, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     if (!CHECK)
     {
         bool sums_finite = finite_d(S[0].rr);

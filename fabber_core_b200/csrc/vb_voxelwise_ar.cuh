@@ -62,7 +62,7 @@ FAB_DEV double ar_klj(const Stats<P> &M, const double (&d)[P], const double (&Si
     return (M.rr + 2.0 * bd + quadform<P>(M.A, d)) + trace_prod<P>(Sig, M.A);
 }
 
-template <class Model, bool FAST, bool BASIS>
+template <class Model, int FAST, bool BASIS>
 FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&p0)[Model::P],
     const double (&pp)[Model::P], const double (&pn)[Model::P], const double (&rden)[Model::P],
     ArStats<Model::P> &S, volatile double *first)
@@ -107,7 +107,10 @@ FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, in
         else
         {
             double gp[P], gn[P];
-            Model::template eval_fd<FAST>(mc, smp, p0, pp, pn, g, gp, gn);
+            if constexpr (FAST == 2)
+                Model::eval_fd_series(mc, smp, p0, pp, pn, g, gp, gn);
+            else
+                Model::template eval_fd<(FAST != 0)>(mc, smp, p0, pp, pn, g, gp, gn);
 #pragma unroll
             for (int i = 0; i < P; i++)
                 J[i] = (gp[i] - gn[i]) * rden[i];
@@ -173,18 +176,26 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     S.S1.zero();
     bool bad_g = false, bad_j = false;
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
+    bool series = false;
+    if constexpr (ModelHasSeries<Model>::value)
+        series = fast && Model::series_ok(mc, a.T, p0, pp, pn);
     bool basis = false; /* opt-in, and only for models that hand out their basis row */
     if constexpr (Model::LINEAR)
         basis = a.basis_jacobian != 0;
     if (basis)
     {
         if constexpr (Model::LINEAR)
-            recentre_loop_ar<Model, false, true>(a, mc, v, p0, pp, pn, rden, S, first);
+            recentre_loop_ar<Model, 0, true>(a, mc, v, p0, pp, pn, rden, S, first);
+    }
+    else if (series)
+    {
+        if constexpr (ModelHasSeries<Model>::value)
+            recentre_loop_ar<Model, 2, false>(a, mc, v, p0, pp, pn, rden, S, first);
     }
     else if (fast)
-        recentre_loop_ar<Model, true, false>(a, mc, v, p0, pp, pn, rden, S, first);
+        recentre_loop_ar<Model, 1, false>(a, mc, v, p0, pp, pn, rden, S, first);
     else
-        recentre_loop_ar<Model, false, false>(a, mc, v, p0, pp, pn, rden, S, first);
+        recentre_loop_ar<Model, 0, false>(a, mc, v, p0, pp, pn, rden, S, first);
     bool sums_finite = finite_d(S.S0.rr);
 #pragma unroll
     for (int i = 0; i < P; i++)
