@@ -1569,7 +1569,17 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
         }
     }
     for (int r = 0; r < W; r++)
+    {
+        /* every kernel of the loop must be loaded on its device before any slab starts to spin on another */
+        cudaSetDevice(parts[r].device);
+        cudaFuncAttributes at;
+        cudaError_t pe = cudaFuncGetAttributes(&at, (const void *)slab_wait_kernel);
+        if (pe == cudaSuccess && runs[r].ml->sp_preload)
+            pe = runs[r].ml->sp_preload();
+        if (pe != cudaSuccess)
+            return cuda_fail(pe, "spatial multi: loading the kernels");
         cudaStreamSynchronize(streams[r]);
+    }
 
     /* ---- the iteration-major loop: every launch is asynchronous; the slabs order themselves through the flags
      * in each other's memory, the host only queues work ---------------------------------------------------- */

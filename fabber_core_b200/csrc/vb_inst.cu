@@ -167,6 +167,24 @@ static cudaError_t launch_sp_sweep(const SpArgs &s, cudaStream_t st)
     return e;
 }
 
+static cudaError_t preload_spatial()
+{
+    const void *kernels[] = { (const void *)sp_setup_kernel<M>, (const void *)sp_noise_kernel<M>,
+        (const void *)sp_theta_kernel<M::P>, (const void *)sp_ak_final_kernel<M::P>,
+        (const void *)sp_ak_partial_kernel<M::P, false, false>, (const void *)sp_ak_partial_kernel<M::P, false, true>,
+        (const void *)sp_ak_partial_kernel<M::P, true, false>, (const void *)sp_ak_partial_kernel<M::P, true, true>,
+        (const void *)sp_sweep_kernel<M::P, false, false>, (const void *)sp_sweep_kernel<M::P, false, true>,
+        (const void *)sp_sweep_kernel<M::P, true, false>, (const void *)sp_sweep_kernel<M::P, true, true> };
+    for (size_t i = 0; i < sizeof(kernels) / sizeof(kernels[0]); i++)
+    {
+        cudaFuncAttributes at;
+        cudaError_t e = cudaFuncGetAttributes(&at, kernels[i]);
+        if (e != cudaSuccess)
+            return e;
+    }
+    return cudaSuccess;
+}
+
 static const ModelLaunchers g_launchers = {
     launch_white<1, false>,
     launch_white<1, true>,
@@ -179,6 +197,7 @@ static const ModelLaunchers g_launchers = {
     launch_sp_theta,
     launch_sp_sweep,
     launch_sp_noise,
+    preload_spatial,
 };
 
 #ifdef FAB_MODEL_TYPE

@@ -25,6 +25,10 @@ struct ModelLaunchers
     VbLaunchFn model_fit;       /* batched model evaluation */
     /* spatial mode (vb_spatial.cuh) */
     SpLaunchFn sp_setup, sp_ak_partial, sp_ak_final, sp_theta, sp_sweep, sp_noise;
+    /* load every spatial kernel variant on the current device NOW. CUDA loads kernels lazily, and loading one may
+     * have to wait for kernels that are running - with slabs that spin on each other's flags a first launch in
+     * the middle of an iteration would deadlock until the spin gives up. Appended: older plug-ins leave it NULL. */
+    cudaError_t (*sp_preload)(void);
 };
 
 /* number of blocks the aK partial reduction is launched with (size of SpArgs::ak_partial) */

@@ -19,7 +19,6 @@
  *                          difference quotient of the parameter transform, up to the rounding noise of the
  *                          subtraction, so the pass needs one evaluation per sample instead of 2P+1
  *                          (recentre_loop in vb_voxelwise.cuh; opt-in with FABBER_B200_BASIS_JACOBIAN=1)
- *   HAS_SERIES / series_ok() / eval_fd_series()   optional third level, cheaper still (exp model)
  *   HAS_FAST / fast_ok()   optional: a cheaper eval_fd<true> that is valid only for a range of parameters
  *                          (exp: the table-based exponential of vb_exp.cuh needs |r t| < 708); the pass
  *                          checks fast_ok() once, outside the time loop, and otherwise runs eval_fd<false>
@@ -37,15 +36,6 @@
 
 namespace fab
 {
-/* does the model offer the optional eval_fd_series level? (plug-in models need not mention it) */
-template <class M, class = void> struct ModelHasSeries
-{
-    static constexpr bool value = false;
-};
-template <class M> struct ModelHasSeries<M, decltype((void)M::HAS_SERIES)>
-{
-    static constexpr bool value = M::HAS_SERIES;
-};
 
 struct VbArgs;
 
@@ -281,26 +271,21 @@ template <int NE> struct ExpModel
                 && exp_fast_range_ok(pn[2 * k + 1], t_max);
         return ok;
     }
-    /* A third, still cheaper pass (optional model hook, see recentre_stats): the two perturbed values of each
-     * rate by SERIES from the centre exponential,
+    /* Inside the table pass the two PERTURBED values of each rate come by series from the centre exponential
+     * wherever that is exact:
      *     exp(-(r + dr) t) = exp(-r t) * exp(z),  exp(z) = 1 + z (1 + z/2 + z^2/6 + z^3/24 + z^4/120),  z = -dr t.
      * dr = r(c +- delta) - r(c) is five orders of magnitude below r (the finite-difference step is 1e-5 |c|,
-     * fwdmodel_linear.cc:157-161), so the series is exact to < 1e-17 once |z| < 4e-3 (z^6/720): the same <= 1 ULP
-     * result a library exp gives, for 7 FP64 instructions instead of 11 - and both perturbed values now share the
-     * rounding error of exp(-r t), which cancels in the difference the Jacobian is made of. Valid when the table
-     * pass is valid and every |dr| t_max < 4e-3; checked once per pass, per voxel. */
-    static constexpr bool HAS_SERIES = true;
-    static FAB_DEV bool series_ok(const Ctx &c, int T, const double (&p0)[P], const double (&pp)[P], const double (&pn)[P])
+     * fwdmodel_linear.cc:157-161), so |z| < 2^-8 nearly always and the series is then exact to < 1e-17
+     * (z^6/720): the same <= 1 ULP result a library exp gives, for 7 FP64 instructions instead of 11 - and both
+     * perturbed values share the rounding error of exp(-r t), which cancels in the difference the Jacobian is
+     * made of. Decided PER SAMPLE AND PER VALUE on the exponent bits of z (integer pipe); a larger z takes the
+     * table exponential. (A per-pass choice made whole warps run both passes once a few voxels' rates had grown:
+     * the C5 noise kernel went from 14.5 to 36 ms over ten iterations - measured, profiles/.) */
+    static FAB_DEV bool small_z(double z)
     {
-        const double t_max = __dmul_rn((double)(T > 0 ? T - 1 : 0), c.dt);
-        bool ok = true;
-#pragma unroll
-        for (int k = 0; k < NE; k++)
-            ok = ok && fabs(pp[2 * k + 1] - p0[2 * k + 1]) * t_max < 4e-3
-                && fabs(pn[2 * k + 1] - p0[2 * k + 1]) * t_max < 4e-3; /* false for NaN */
-        return ok;
+        return ((unsigned)__double2hiint(z) & 0x7ff00000u) < 0x3f700000u; /* |z| < 2^-8, false for inf / nan */
     }
-    /* e0 * exp(z) for |z| < 4e-3 */
+    /* e0 * exp(z) for |z| < 2^-8 */
     static FAB_DEV double scaled_exp_small(double e0, double z)
     {
         double q = fma(z, 1.0 / 120.0, 1.0 / 24.0);
@@ -329,17 +314,6 @@ template <int NE> struct ExpModel
     static FAB_DEV void eval_fd(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
         const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
     {
-        eval_fd_impl<FAST, false>(c, smp, p0, pp, pn, g, gp, gn);
-    }
-    static FAB_DEV void eval_fd_series(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
-        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
-    {
-        eval_fd_impl<true, true>(c, smp, p0, pp, pn, g, gp, gn);
-    }
-    template <bool FAST, bool SERIES>
-    static FAB_DEV void eval_fd_impl(const Ctx &c, const Sample &smp, const double (&p0)[P], const double (&pp)[P],
-        const double (&pn)[P], double &g, double (&gp)[P], double (&gn)[P])
-    {
         const double tt = smp.tt;
         double e0[NE], term[NE];
 #pragma unroll
@@ -360,15 +334,18 @@ template <int NE> struct ExpModel
             double ta[4];
             ta[0] = __dmul_rn(pp[2 * k], e0[k]);
             ta[1] = __dmul_rn(pn[2 * k], e0[k]);
-            if (SERIES)
+            if (FAST)
             {
-                ta[2] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], (p0[2 * k + 1] - pp[2 * k + 1]) * tt));
-                ta[3] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], (p0[2 * k + 1] - pn[2 * k + 1]) * tt));
+                const double zp = (p0[2 * k + 1] - pp[2 * k + 1]) * tt, zn = (p0[2 * k + 1] - pn[2 * k + 1]) * tt;
+                const double ep = small_z(zp) ? scaled_exp_small(e0[k], zp) : exp_fast(__dmul_rn(-pp[2 * k + 1], tt), c.tab);
+                const double en = small_z(zn) ? scaled_exp_small(e0[k], zn) : exp_fast(__dmul_rn(-pn[2 * k + 1], tt), c.tab);
+                ta[2] = __dmul_rn(p0[2 * k], ep);
+                ta[3] = __dmul_rn(p0[2 * k], en);
             }
             else
             {
-                ta[2] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pp[2 * k + 1], tt)));
-                ta[3] = __dmul_rn(p0[2 * k], ex<FAST>(c, __dmul_rn(-pn[2 * k + 1], tt)));
+                ta[2] = __dmul_rn(p0[2 * k], exp(__dmul_rn(-pp[2 * k + 1], tt)));
+                ta[3] = __dmul_rn(p0[2 * k], exp(__dmul_rn(-pn[2 * k + 1], tt)));
             }
             double out[4];
 #pragma unroll

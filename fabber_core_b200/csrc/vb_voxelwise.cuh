@@ -179,10 +179,7 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
         else
         {
             double gp[P], gn[P];
-            if constexpr (FAST == 2)
-                Model::eval_fd_series(mc, smp, p0, pp, pn, g, gp, gn);
-            else
-                Model::template eval_fd<(FAST != 0)>(mc, smp, p0, pp, pn, g, gp, gn);
+            Model::template eval_fd<(FAST != 0)>(mc, smp, p0, pp, pn, g, gp, gn);
 #pragma unroll
             for (int i = 0; i < P; i++)
                 J[i] = (gp[i] - gn[i]) * rden[i];
@@ -264,9 +261,6 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
      * argument of this pass is inside its range - checked once here, not per sample */
     constexpr bool CHECK = NPHI > 1; /* masked samples never reach the sums: test them one by one */
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
-    bool series = false; /* optional third level (exp: perturbed-rate exponentials by series) */
-    if constexpr (ModelHasSeries<Model>::value)
-        series = fast && Model::series_ok(mc, a.T, p0, pp, pn);
     bool basis = false; /* opt-in, and only for models that hand out their basis row */
     if constexpr (Model::LINEAR)
         basis = a.basis_jacobian != 0;
@@ -274,11 +268,6 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
     {
         if constexpr (Model::LINEAR)
             recentre_loop<Model, NPHI, 0, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
-    }
-    else if (series)
-    {
-        if constexpr (ModelHasSeries<Model>::value)
-            recentre_loop<Model, NPHI, 2, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     }
     else if (fast)
         recentre_loop<Model, NPHI, 1, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);

@@ -107,10 +107,7 @@ FAB_DEV void recentre_loop_ar(const VbArgs &a, const typename Model::Ctx &mc, in
         else
         {
             double gp[P], gn[P];
-            if constexpr (FAST == 2)
-                Model::eval_fd_series(mc, smp, p0, pp, pn, g, gp, gn);
-            else
-                Model::template eval_fd<(FAST != 0)>(mc, smp, p0, pp, pn, g, gp, gn);
+            Model::template eval_fd<(FAST != 0)>(mc, smp, p0, pp, pn, g, gp, gn);
 #pragma unroll
             for (int i = 0; i < P; i++)
                 J[i] = (gp[i] - gn[i]) * rden[i];
@@ -176,9 +173,6 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     S.S1.zero();
     bool bad_g = false, bad_j = false;
     const bool fast = Model::HAS_FAST && Model::fast_ok(mc, a.T, p0, pp, pn);
-    bool series = false;
-    if constexpr (ModelHasSeries<Model>::value)
-        series = fast && Model::series_ok(mc, a.T, p0, pp, pn);
     bool basis = false; /* opt-in, and only for models that hand out their basis row */
     if constexpr (Model::LINEAR)
         basis = a.basis_jacobian != 0;
@@ -186,11 +180,6 @@ FAB_DEV int recentre_stats_ar(const VbArgs &a, const typename Model::Ctx &mc, in
     {
         if constexpr (Model::LINEAR)
             recentre_loop_ar<Model, 0, true>(a, mc, v, p0, pp, pn, rden, S, first);
-    }
-    else if (series)
-    {
-        if constexpr (ModelHasSeries<Model>::value)
-            recentre_loop_ar<Model, 2, false>(a, mc, v, p0, pp, pn, rden, S, first);
     }
     else if (fast)
         recentre_loop_ar<Model, 1, false>(a, mc, v, p0, pp, pn, rden, S, first);

@@ -270,6 +270,16 @@ protected:
 private:
     const VoxelData &GetMainVoxelDataMultiple();
     bool LooksSpatial() const;
+    /* Speculative start. fabber_set_data("data") is normally the last call before fabber_dorun, and the options
+     * are complete by then: the run is prepared right there and every block of voxels starts computing the
+     * moment its upload is queued, while the host is still staging the blocks behind it. fabber_dorun adopts
+     * that run if NOTHING was set or changed since (m_version), else it is thrown away and the run starts from
+     * scratch - the result is the same either way. FABBER_B200_SPECULATE=0 turns it off. */
+    struct SpeculativeRun;
+    std::unique_ptr<SpeculativeRun> m_spec;
+    unsigned long long m_version;
+    bool m_in_run;
+    void DiscardSpeculative();
     std::string m_outdir;
     std::set<std::string> m_used_params;
     std::map<std::string, int> m_warncount;
@@ -437,6 +447,13 @@ public:
     static std::string GetDescription();
     void Initialize(FwdModel *model, FabberRunData &rundata); /* inference_vb.cc:100, inference.cc:62 */
     void DoCalculations(FabberRunData &rundata);              /* inference_vb.cc:360 - runs on the GPU */
+    /* DoCalculations in three steps (it is Prepare + LaunchAll + Finish): the host library starts a run
+     * speculatively while the series is still being uploaded, block by block */
+    void Prepare(FabberRunData &rundata, VoxelData &data);
+    void LaunchBlock(VoxelData &data, size_t block);
+    void LaunchAll(VoxelData &data);
+    void Finish(FabberRunData &rundata);
+    bool LaunchesByBlock() const { return m_nvoxels > 0 && !m_spatial && !m_output_only; }
     void SaveResults(FabberRunData &rundata);                 /* inference_vb.cc:966, inference.cc:112 */
 
 private:
@@ -468,10 +485,26 @@ private:
         DevArray mean, cov, noise, F, hist, its, status;
     };
     std::vector<DevCtx> m_ctx;
+    struct Scratch
+    {
+        int device;
+        DevArray d;
+    };
+    std::vector<Scratch> m_scratch; /* per-voxel inputs on the devices (image priors, restart state, coordinates) */
+    std::vector<fabber_cuda_vb_buffers> m_bufs;
+    std::vector<fabber_cuda_vb_problem> m_probs;
+    bool m_spatial = false, m_slabs = false, m_output_only = false;
+    int m_launch_rc = 0;
+    std::string m_launch_error;
+    void FreeScratch();
     void ReleaseDevice();
 
 public:
-    ~Vb() { ReleaseDevice(); }
+    ~Vb()
+    {
+        FreeScratch();
+        ReleaseDevice();
+    }
 };
 
 } // namespace fabber_b200

@@ -200,8 +200,23 @@ void Vb::ReleaseDevice()
 
 void Vb::DoCalculations(FabberRunData &rundata)
 {
-    StopWatch sw;
     VoxelData &data = rundata.MutableMainVoxelData();
+    Prepare(rundata, data);
+    if (m_nvoxels == 0 || m_output_only)
+        return;
+    LaunchAll(data);
+    Finish(rundata);
+}
+
+/* Everything of DoCalculations up to the first kernel launch: options -> plain-C problem description, the
+ * devices of the run, result arrays, per-voxel inputs on the devices. Split off so that the host library can
+ * run it while the series is still being staged (FabberRunData::SetVoxelDataArray starts each block's kernel
+ * the moment that block is on its way - see "speculative start" there). */
+void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
+{
+    StopWatch sw;
+    m_output_only = false;
+    m_launch_rc = FABBER_CUDA_OK;
     const size_t N = data.cols;
     const int T = data.rows;
     m_nvoxels = N;
@@ -363,6 +378,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
     prob.nz = rundata.Extent()[2];
     m_nn = m_ar ? FABBER_CUDA_AR_NOISE_FIELDS : 2 * m_nphis;
     const int NN = m_nn;
+    m_spatial = spatial;
     if (N == 0)
         return; /* zero voxels is not an error (test/test_inference.cc:57-73) */
 
@@ -370,6 +386,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
      * dealt out while it was being set); spatial VB couples the voxels and runs on one device ------------- */
     ReleaseDevice();
     bool slabs = spatial && data.parts.size() > 1; /* z-slabs dealt out at set_data: the multi-device engine */
+    FreeScratch();
     for (size_t g = 0; g < data.parts.size(); g++)
         slabs = slabs && data.parts[g].z1 > data.parts[g].z0;
     if (data.parts.empty() || (spatial && data.parts.size() != 1 && !slabs))
@@ -510,6 +527,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
             check(fabber_cuda_stream_sync(nullptr), "output-only");
         }
         m_needF = false;
+        m_output_only = true;
         rundata.Log() << "Vb::DoCalculations output-only set - not performing any calculations" << std::endl;
         return;
     }
@@ -519,25 +537,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
                   << T << " time points, " << P << " parameters, " << m_ctx.size() << " device"
                   << (m_ctx.size() == 1 ? "" : "s") << std::endl;
     rundata.Progress(0, (int)N);
-    struct Scratch
-    {
-        int device;
-        DevArray d;
-    };
-    std::vector<Scratch> scratch;
-    struct ScratchGuard
-    {
-        std::vector<Scratch> &s;
-        ~ScratchGuard()
-        {
-            for (size_t i = 0; i < s.size(); i++)
-            {
-                DeviceScope scope(s[i].device);
-                fabber_cuda_stream_sync(nullptr);
-                cached_device_free(s[i].d.p, s[i].d.bytes);
-            }
-        }
-    } guard = { scratch };
+    std::vector<Scratch> &scratch = m_scratch;
     auto upload_columns = [&](const std::vector<double> &h, int rows, const DevCtx &c) -> void * {
         Scratch sc;
         sc.device = c.device;
@@ -557,8 +557,10 @@ void Vb::DoCalculations(FabberRunData &rundata)
             for (size_t v = 0; v < N; v++)
                 images[i][v] = img.at(0, v);
         }
-    std::vector<fabber_cuda_vb_buffers> bufs(m_ctx.size());
-    std::vector<fabber_cuda_vb_problem> probs(m_ctx.size(), prob);
+    m_bufs.assign(m_ctx.size(), fabber_cuda_vb_buffers());
+    m_probs.assign(m_ctx.size(), prob);
+    std::vector<fabber_cuda_vb_buffers> &bufs = m_bufs;
+    std::vector<fabber_cuda_vb_problem> &probs = m_probs;
     for (size_t g = 0; g < m_ctx.size(); g++)
     {
         DevCtx &c = m_ctx[g];
@@ -600,8 +602,43 @@ void Vb::DoCalculations(FabberRunData &rundata)
         buf.iterations = (int *)c.its.p;
         buf.f_history = m_fhist_len > 0 ? (double *)c.hist.p : nullptr;
     }
+    m_slabs = slabs;
     rundata.Log() << "Vb::timing: option translation + device buffers " << sw.lap_ms() << " ms" << std::endl;
+}
 
+void Vb::FreeScratch()
+{
+    for (size_t i = 0; i < m_scratch.size(); i++)
+    {
+        DeviceScope scope(m_scratch[i].device);
+        fabber_cuda_stream_sync(nullptr);
+        cached_device_free(m_scratch[i].d.p, m_scratch[i].d.bytes);
+    }
+    m_scratch.clear();
+}
+
+/* voxelwise VB on one uploaded block of voxels, on the block's device, behind the block's upload event */
+void Vb::LaunchBlock(VoxelData &data, size_t b)
+{
+    if (m_launch_rc != FABBER_CUDA_OK)
+        return;
+    const VoxelData::Block &blk = data.blocks[b];
+    const DevCtx &c = m_ctx[blk.part];
+    DeviceScope scope(c.device);
+    m_launch_rc = fabber_cuda_stream_wait_event(nullptr, blk.ready);
+    if (m_launch_rc == FABBER_CUDA_OK)
+        m_launch_rc = fabber_cuda_vb_voxelwise_range(&m_probs[blk.part], &m_bufs[blk.part], (int)(blk.v0 - c.v0),
+            (int)(blk.v1 - c.v0), nullptr);
+    if (m_launch_rc != FABBER_CUDA_OK)
+        m_launch_error = fabber_cuda_last_error();
+}
+
+void Vb::LaunchAll(VoxelData &data)
+{
+    const bool spatial = m_spatial, slabs = m_slabs;
+    fabber_cuda_vb_problem &prob = m_prob;
+    std::vector<fabber_cuda_vb_buffers> &bufs = m_bufs;
+    std::vector<fabber_cuda_vb_problem> &probs = m_probs;
     int rc = FABBER_CUDA_OK;
     if (spatial && slabs)
     {
@@ -634,16 +671,9 @@ void Vb::DoCalculations(FabberRunData &rundata)
         /* voxels are independent (inference_vb.cc:423-571): one launch per uploaded block on the block's
          * device, each behind its block's event - block k computes while the blocks after it are still on
          * the PCIe bus, and every device works on its own range. All calls are asynchronous. */
-        for (size_t b = 0; b < data.blocks.size() && rc == FABBER_CUDA_OK; b++)
-        {
-            const VoxelData::Block &blk = data.blocks[b];
-            const DevCtx &c = m_ctx[blk.part];
-            DeviceScope scope(c.device);
-            rc = fabber_cuda_stream_wait_event(nullptr, blk.ready);
-            if (rc == FABBER_CUDA_OK)
-                rc = fabber_cuda_vb_voxelwise_range(&probs[blk.part], &bufs[blk.part], (int)(blk.v0 - c.v0),
-                    (int)(blk.v1 - c.v0), nullptr);
-        }
+        for (size_t b = 0; b < data.blocks.size(); b++)
+            LaunchBlock(data, b);
+        rc = m_launch_rc;
         if (data.blocks.empty()) /* uploaded in one piece */
             for (size_t g = 0; g < m_ctx.size() && rc == FABBER_CUDA_OK; g++)
             {
@@ -651,9 +681,27 @@ void Vb::DoCalculations(FabberRunData &rundata)
                 rc = fabber_cuda_vb_voxelwise(&probs[g], &bufs[g], nullptr);
             }
     }
-    if (rc == FABBER_CUDA_ERR_INVALID)
-        throw FabberRunDataError(std::string("Vb: ") + fabber_cuda_last_error());
-    check(rc, "VB kernels");
+    if (rc != FABBER_CUDA_OK && m_launch_rc == FABBER_CUDA_OK)
+    {
+        m_launch_rc = rc;
+        m_launch_error = fabber_cuda_last_error();
+    }
+}
+
+/* after the last launch: errors, the bad-voxel policy, scratch */
+void Vb::Finish(FabberRunData &rundata)
+{
+    StopWatch sw;
+    const size_t N = m_nvoxels;
+    struct ScratchGuard
+    {
+        Vb &vb;
+        ~ScratchGuard() { vb.FreeScratch(); }
+    } guard = { *this };
+    if (m_launch_rc == FABBER_CUDA_ERR_INVALID)
+        throw FabberRunDataError(std::string("Vb: ") + m_launch_error);
+    if (m_launch_rc != FABBER_CUDA_OK)
+        throw FabberInternalError(std::string("VB kernels: ") + m_launch_error);
 
     /* ---- bad-voxel policy (inference_vb.cc:529-544; set-up failures are never caught, :235) ------------
      * the status words are scanned on the devices; only a count and the first offender come back */
@@ -680,7 +728,7 @@ void Vb::DoCalculations(FabberRunData &rundata)
         }
         n_bad += bad_g;
     }
-    rundata.Log() << "Vb::timing: kernels " << sw.lap_ms() << " ms" << std::endl;
+    rundata.Log() << "Vb::timing: waiting for the kernels " << sw.lap_ms() << " ms" << std::endl;
     rundata.Progress((int)N, (int)N);
     if (n_bad > 0)
     {

@@ -478,24 +478,48 @@ void VoxelData::alloc(int r, size_t c)
     f = (float *)cached_pinned_alloc(bytes());
 }
 
+struct FabberRunData::SpeculativeRun
+{
+    std::unique_ptr<FwdModel> model;
+    std::unique_ptr<Vb> vb;
+    unsigned long long version = 0;
+    const VoxelData *data = nullptr;
+    bool by_block = false;
+};
+
 FabberRunData::FabberRunData()
-    : m_have_extent(false)
+    : m_version(0)
+    , m_in_run(false)
+    , m_have_extent(false)
     , m_device_only_access(false)
     , m_progress(nullptr)
 {
     m_extent[0] = m_extent[1] = m_extent[2] = 0;
 }
-FabberRunData::~FabberRunData() {}
+FabberRunData::~FabberRunData() { DiscardSpeculative(); }
+void FabberRunData::DiscardSpeculative()
+{
+    m_spec.reset(); /* ~Vb drains its devices and hands the buffers back */
+}
 
-void FabberRunData::Set(const std::string &key, const std::string &value) { m_params[key] = value; }
+void FabberRunData::Set(const std::string &key, const std::string &value)
+{
+    m_version++;
+    m_params[key] = value;
+}
 void FabberRunData::SetBool(const std::string &key, bool value)
 {
+    m_version++;
     if (value)
         m_params[key] = "";
     else
         m_params.erase(key);
 }
-void FabberRunData::Unset(const std::string &key) { m_params.erase(key); }
+void FabberRunData::Unset(const std::string &key)
+{
+    m_version++;
+    m_params.erase(key);
+}
 bool FabberRunData::HaveKey(const std::string &key) const { return m_params.count(key) > 0; }
 
 std::string FabberRunData::GetString(const std::string &key)
@@ -593,6 +617,8 @@ void FabberRunData::SetExtent(int nx, int ny, int nz, const int *mask)
 {
     if (nx <= 0 || ny <= 0 || nz <= 0)
         throw FabberRunDataError("Dimensions must be >0");
+    m_version++;
+    DiscardSpeculative();
     m_extent[0] = nx;
     m_extent[1] = ny;
     m_extent[2] = nz;
@@ -646,6 +672,8 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         throw FabberRunDataError("Extent must be set before voxel data");
     const size_t n_grid = (size_t)m_extent[0] * m_extent[1] * m_extent[2];
     const size_t N = m_voxel_index.size();
+    m_version++;
+    DiscardSpeculative(); /* before its series can go away */
     m_voxel_data.erase(key); /* hand the old blocks back to the cache before asking for new ones */
     if (key.compare(0, 4, "data") == 0)
         m_voxel_data.erase("@maindata"); /* a stale combination of data1..n */
@@ -778,6 +806,34 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         DeviceScope scope(vd->parts[g].device);
         vd->parts[g].dev = (float *)cached_device_alloc(T * (vd->parts[g].v1 - vd->parts[g].v0) * sizeof(float));
     }
+    /* speculative start (see fabber_host.h): prepare the run now; every block's kernel is queued right behind
+     * its upload. Any failure here just means no speculation - fabber_dorun then reports it properly. */
+    std::unique_ptr<SpeculativeRun> spec;
+    {
+        const char *se = getenv("FABBER_B200_SPECULATE");
+        if (upload && !m_in_run && !(se && se[0] == '0') && m_params.count("model") && m_params.count("method")
+            && m_params["method"] == "vb" && m_params.count("noise") && !spatial_like)
+        {
+            try
+            {
+                spec.reset(new SpeculativeRun());
+                spec->model.reset(FwdModel::NewFromName(m_params["model"]));
+                spec->model->Initialize(*this);
+                std::vector<Parameter> params;
+                spec->model->GetParameters(*this, params);
+                spec->vb.reset(new Vb());
+                spec->vb->Initialize(spec->model.get(), *this);
+                spec->vb->Prepare(*this, *vd);
+                spec->by_block = spec->vb->LaunchesByBlock();
+                if (!spec->by_block)
+                    spec.reset();
+            }
+            catch (...)
+            {
+                spec.reset();
+            }
+        }
+    }
     auto queue_block = [&](VoxelData::Block &blk, const float *src, size_t src_pitch_elems) {
         const VoxelData::Part &pt = vd->parts[blk.part];
         DeviceScope scope(pt.device);
@@ -790,7 +846,17 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         if (rc == FABBER_CUDA_OK)
             rc = fabber_cuda_event_record(blk.ready, cs);
         vd->blocks.push_back(blk);
+        if (rc == FABBER_CUDA_OK && spec)
+            spec->vb->LaunchBlock(*vd, vd->blocks.size() - 1);
         return rc;
+    };
+    auto keep_spec = [&]() {
+        if (spec)
+        {
+            spec->version = m_version;
+            spec->data = vd.get();
+            m_spec = std::move(spec);
+        }
     };
 
     /* The caller's buffer is page-locked (cudaMallocHost / cudaHostRegister) and in voxel-list order (full
@@ -817,6 +883,7 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
             for (size_t b = 0; b < vd->blocks.size(); b++)
                 if (fabber_cuda_event_sync(vd->blocks[b].ready) != FABBER_CUDA_OK)
                     throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
+        keep_spec();
         m_voxel_data[key] = std::move(vd);
         return;
     }
@@ -886,6 +953,7 @@ void FabberRunData::SetVoxelDataArray(const std::string &key, int data_size, con
         if (upload && queue_block(blocks[b], dst_all, N) != FABBER_CUDA_OK)
             throw FabberInternalError(std::string("copying data to the GPU: ") + fabber_cuda_last_error());
     }
+    keep_spec();
     m_voxel_data[key] = std::move(vd);
 }
 
@@ -1023,7 +1091,12 @@ VoxelData &FabberRunData::MutableVoxelData(const std::string &key)
 {
     return const_cast<VoxelData &>(GetVoxelData(key));
 }
-void FabberRunData::ClearVoxelData(const std::string &key) { m_voxel_data.erase(key); }
+void FabberRunData::ClearVoxelData(const std::string &key)
+{
+    if (m_spec && m_voxel_data.count(key) && m_voxel_data[key].get() == m_spec->data)
+        DiscardSpeculative();
+    m_voxel_data.erase(key);
+}
 
 /* rundata_array.cc:68-98: T x Nvox -> float[t][z][y][x], zeros outside the mask */
 void FabberRunData::GetVoxelDataArray(const std::string &key, float *data)
@@ -1105,6 +1178,7 @@ void FabberRunData::AddKeyEqualsValue(const std::string &exp, bool trim_comments
     }
     else
         m_params[exp] = "";
+    m_version++;
 }
 
 void FabberRunData::ParseParamFile(const std::string &filename)
@@ -1261,6 +1335,16 @@ std::string FabberRunData::GetOutputDir()
 /* rundata.cc:248-311 */
 void FabberRunData::Run(void (*progress_cb)(int, int))
 {
+    struct InRun
+    {
+        bool &f;
+        explicit InRun(bool &b)
+            : f(b)
+        {
+            f = true;
+        }
+        ~InRun() { f = false; }
+    } in_run(m_in_run);
     m_progress = progress_cb;
     time_t start;
     time(&start);
@@ -1282,10 +1366,23 @@ void FabberRunData::Run(void (*progress_cb)(int, int))
     if (method != "vb" && method != "spatialvb")
         throw InvalidOptionValue("method", method,
             "only vb and spatialvb run on the GPU path (nlls and other methods are outside this library)");
-    Vb vb;
-    vb.Initialize(fwd_model.get(), *this);
-    vb.DoCalculations(*this);
-    vb.SaveResults(*this);
+    /* a run that fabber_set_data started speculatively is adopted if nothing was set since */
+    std::unique_ptr<SpeculativeRun> spec = std::move(m_spec);
+    if (spec && (spec->version != m_version || m_voxel_data.count("data") == 0 || m_voxel_data["data"].get() != spec->data))
+        spec.reset();
+    if (spec)
+    {
+        m_log << "FabberRunData::Adopting the run started while the data was being set" << std::endl;
+        spec->vb->Finish(*this);
+        spec->vb->SaveResults(*this);
+    }
+    else
+    {
+        Vb vb;
+        vb.Initialize(fwd_model.get(), *this);
+        vb.DoCalculations(*this);
+        vb.SaveResults(*this);
+    }
     time_t end;
     time(&end);
     m_log << "FabberRunData::All done." << std::endl;
