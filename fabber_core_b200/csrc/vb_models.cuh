@@ -268,24 +268,23 @@ template <int NE> struct ExpModel
 #pragma unroll
         for (int k = 0; k < NE; k++)
             ok = ok && exp_fast_range_ok(p0[2 * k + 1], t_max) && exp_fast_range_ok(pp[2 * k + 1], t_max)
-                && exp_fast_range_ok(pn[2 * k + 1], t_max);
+                && exp_fast_range_ok(pn[2 * k + 1], t_max) && fabs(pp[2 * k + 1] - p0[2 * k + 1]) * t_max < 0.05
+                && fabs(pn[2 * k + 1] - p0[2 * k + 1]) * t_max < 0.05; /* false for NaN */
         return ok;
     }
-    /* Inside the table pass the two PERTURBED values of each rate come by series from the centre exponential
-     * wherever that is exact:
+    /* Inside the table pass the two PERTURBED values of each rate come by series from the centre exponential:
      *     exp(-(r + dr) t) = exp(-r t) * exp(z),  exp(z) = 1 + z (1 + z/2 + z^2/6 + z^3/24 + z^4/120),  z = -dr t.
      * dr = r(c +- delta) - r(c) is five orders of magnitude below r (the finite-difference step is 1e-5 |c|,
-     * fwdmodel_linear.cc:157-161), so |z| < 2^-8 nearly always and the series is then exact to < 1e-17
-     * (z^6/720): the same <= 1 ULP result a library exp gives, for 7 FP64 instructions instead of 11 - and both
-     * perturbed values share the rounding error of exp(-r t), which cancels in the difference the Jacobian is
-     * made of. Decided PER SAMPLE AND PER VALUE on the exponent bits of z (integer pipe); a larger z takes the
-     * table exponential. (A per-pass choice made whole warps run both passes once a few voxels' rates had grown:
-     * the C5 noise kernel went from 14.5 to 36 ms over ten iterations - measured, profiles/.) */
-    static FAB_DEV bool small_z(double z)
-    {
-        return ((unsigned)__double2hiint(z) & 0x7ff00000u) < 0x3f700000u; /* |z| < 2^-8, false for inf / nan */
-    }
-    /* e0 * exp(z) for |z| < 2^-8 */
+     * fwdmodel_linear.cc:157-161): z ~ 1e-5 |c| r t. For |z| < 2^-8 the series is exact to < 1e-17 (z^6/720) - the
+     * same <= 1 ULP result a library exp gives, for 7 FP64 instructions instead of 11, and both perturbed values
+     * share the rounding error of exp(-r t), which cancels in the difference the Jacobian is made of. A larger z
+     * needs r t > 390 / |c|, where exp(-r t) itself has all but vanished: the truncation error of the VALUE is
+     * exp(-x) (1e-5 |c| x)^6 / 720 <= 1.6e-31 |c|^6 (x = r t; x^6 e^-x peaks at 116) relative to the amplitude, and
+     * of the Jacobian entry 5e-20 of it - both far below the rounding of the sum they enter. So the series is used
+     * for every sample of the table pass, without a test (a per-pass choice between passes made whole warps run
+     * both once a few voxels' rates had grown: the C5 noise kernel went from 14.5 to 36 ms over ten iterations; a
+     * per-sample branch cost C3 15 % - both measured). fast_ok() keeps |z| < 0.05 as a backstop. */
+    /* e0 * exp(z), |z| small (see above) */
     static FAB_DEV double scaled_exp_small(double e0, double z)
     {
         double q = fma(z, 1.0 / 120.0, 1.0 / 24.0);
@@ -337,10 +336,8 @@ template <int NE> struct ExpModel
             if (FAST)
             {
                 const double zp = (p0[2 * k + 1] - pp[2 * k + 1]) * tt, zn = (p0[2 * k + 1] - pn[2 * k + 1]) * tt;
-                const double ep = small_z(zp) ? scaled_exp_small(e0[k], zp) : exp_fast(__dmul_rn(-pp[2 * k + 1], tt), c.tab);
-                const double en = small_z(zn) ? scaled_exp_small(e0[k], zn) : exp_fast(__dmul_rn(-pn[2 * k + 1], tt), c.tab);
-                ta[2] = __dmul_rn(p0[2 * k], ep);
-                ta[3] = __dmul_rn(p0[2 * k], en);
+                ta[2] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], zp));
+                ta[3] = __dmul_rn(p0[2 * k], scaled_exp_small(e0[k], zn));
             }
             else
             {

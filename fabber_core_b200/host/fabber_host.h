@@ -454,6 +454,7 @@ public:
     void LaunchAll(VoxelData &data);
     void Finish(FabberRunData &rundata);
     bool LaunchesByBlock() const { return m_nvoxels > 0 && !m_spatial && !m_output_only; }
+    const std::string &Description() const { return m_description; }
     void SaveResults(FabberRunData &rundata);                 /* inference_vb.cc:966, inference.cc:112 */
 
 private:
@@ -495,7 +496,7 @@ private:
     std::vector<fabber_cuda_vb_problem> m_probs;
     bool m_spatial = false, m_slabs = false, m_output_only = false;
     int m_launch_rc = 0;
-    std::string m_launch_error;
+    std::string m_launch_error, m_description;
     void FreeScratch();
     void ReleaseDevice();
 

@@ -533,9 +533,10 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
     }
 
     /* ---- inputs --------------------------------------------------------------------------------------- */
-    rundata.Log() << "Vb::" << (spatial ? "Spatial" : "Voxelwise") << " calculations on the GPU: " << N << " voxels x "
-                  << T << " time points, " << P << " parameters, " << m_ctx.size() << " device"
-                  << (m_ctx.size() == 1 ? "" : "s") << std::endl;
+    m_description = std::string("Vb::") + (spatial ? "Spatial" : "Voxelwise") + " calculations on the GPU: " + stringify(N)
+        + " voxels x " + stringify(T) + " time points, " + stringify(P) + " parameters, " + stringify(m_ctx.size())
+        + " device" + (m_ctx.size() == 1 ? "" : "s");
+    rundata.Log() << m_description << std::endl;
     rundata.Progress(0, (int)N);
     std::vector<Scratch> &scratch = m_scratch;
     auto upload_columns = [&](const std::vector<double> &h, int rows, const DevCtx &c) -> void * {

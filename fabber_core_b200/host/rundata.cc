@@ -1373,6 +1373,7 @@ void FabberRunData::Run(void (*progress_cb)(int, int))
     if (spec)
     {
         m_log << "FabberRunData::Adopting the run started while the data was being set" << std::endl;
+        m_log << spec->vb->Description() << std::endl;
         spec->vb->Finish(*this);
         spec->vb->SaveResults(*this);
     }

@@ -210,3 +210,71 @@ def test_blockwise_upload_with_a_mask_equals_one_block(monkeypatch):
         c1, c0 = np.polyfit(t.astype(np.float64), data[x, y, z].astype(np.float64), 1)
         assert abs(two.data["mean_c1"][x, y, z] - c1) < 1e-3 * max(1.0, abs(c1))
         assert abs(two.data["mean_c0"][x, y, z] - c0) < 1e-3 * abs(c0)
+
+
+def _run_ordered(opts, items, late_opts=None):
+    """options -> extent -> data items IN THE GIVEN ORDER -> (optional late options) -> dorun -> mean / std / F"""
+    f = fab.Fabber()
+    f._set_options(opts)
+    shape = items[0][1].shape
+    n = shape[0] * shape[1] * shape[2]
+    f._trycall(f.clib.fabber_set_extent, f.handle, shape[0], shape[1], shape[2], np.ones(n, dtype=np.int32), f.errbuf)
+    for key, item in items:
+        size = 1 if item.ndim == 3 else item.shape[3]
+        flat = np.ascontiguousarray(np.asarray(item).flatten(order="F"), dtype=np.float32)
+        f._trycall(f.clib.fabber_set_data, f.handle, key.encode(), size, flat, f.errbuf)
+    if late_opts:
+        f._set_options(late_opts)
+    f._trycall(f.clib.fabber_dorun, f.handle, len(f.outbuf), f.outbuf, f.errbuf, f.progress_cb_type(0))
+    log = f.outbuf.value.decode(errors="replace")
+    f._trycall(f.clib.fabber_get_model_params, f.handle, len(f.outbuf), f.outbuf, f.errbuf)
+    out = {}
+    for key in ["mean_" + p for p in f.outbuf.value.decode().splitlines()] + ["freeEnergy", "finalMVN"]:
+        size = f._trycall(f.clib.fabber_get_data_size, f.handle, key.encode(), f.errbuf)
+        arr = np.empty(n * size, dtype=np.float32)
+        f._trycall(f.clib.fabber_get_data, f.handle, key.encode(), arr, f.errbuf)
+        out[key] = arr
+    return out, log
+
+
+def test_speculative_start_is_adopted_only_when_nothing_changed(monkeypatch):
+    """fabber_set_data("data") starts voxelwise VB while the series is still being uploaded; fabber_dorun adopts
+    that run only if no option or data item was set since - and the outputs are bit-identical to a run started
+    from scratch in every case."""
+    n, T = 70000, 40   # more than one upload block's worth of CTAs, a few blocks with the knob below
+    monkeypatch.setenv("FABBER_B200_UPLOAD_BLOCK_MB", "2")
+    y = synth.poly_volume(n, T, 2, seed=90).numpy()
+    vol = volume(y, (n, 1, 1))
+    img = np.linspace(-0.05, 0.05, n).astype(np.float32).reshape(n, 1, 1)
+    base = {"model": "poly", "degree": 2, "noise": "white", "method": "vb", "convergence": "lm", "save-mean": True,
+            "save-free-energy": True, "save-mvn": True}
+    ADOPT = "Adopting the run started while the data was being set"
+
+    monkeypatch.setenv("FABBER_B200_SPECULATE", "0")
+    ref, log = _run_ordered(base, [("data", vol)])
+    assert ADOPT not in log
+    ref_it, _ = _run_ordered(dict(base, **{"max-iterations": 3}), [("data", vol)])
+    img_opts = dict(base, PSP_byname1="c2", PSP_byname1_type="I", PSP_byname1_image="c2img", PSP_byname1_prec=1e4)
+    ref_img, _ = _run_ordered(img_opts, [("c2img", img), ("data", vol)])
+    monkeypatch.delenv("FABBER_B200_SPECULATE")
+
+    got, log = _run_ordered(base, [("data", vol)])
+    assert ADOPT in log
+    for k in ref:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
+    # an option set after the data: the speculative run is thrown away, the new option holds
+    got, log = _run_ordered(base, [("data", vol)], late_opts={"max-iterations": 3})
+    assert ADOPT not in log
+    for k in ref_it:
+        assert np.array_equal(got[k], ref_it[k], equal_nan=True), k
+    assert not np.array_equal(ref_it["mean_c1"], ref["mean_c1"])
+    # the image prior arrives AFTER the main data: no speculation possible (or it is discarded), same result;
+    # and when it arrives first the speculative run uses it
+    got, log = _run_ordered(img_opts, [("data", vol), ("c2img", img)])
+    assert ADOPT not in log
+    for k in ref_img:
+        assert np.array_equal(got[k], ref_img[k], equal_nan=True), k
+    got, log = _run_ordered(img_opts, [("c2img", img), ("data", vol)])
+    assert ADOPT in log
+    for k in ref_img:
+        assert np.array_equal(got[k], ref_img[k], equal_nan=True), k
