@@ -9,8 +9,9 @@
  * shared memory): 11 FP64 instructions, no branch. Accuracy: max 0.79 ULP over 3e5 random arguments
  * against 60-digit references, 96.7 % correctly rounded (CUDA's own exp is documented at 1 ULP); checked
  * on the device against exp() in tests/test_gpu_exp.py.
- * Valid for |x| < 708 (no overflow / denormal results); the caller checks the argument range once per
- * pass, outside the time loop, and falls back to exp() otherwise (vb_models.cuh).
+ * Valid for finite x < 708 (no overflow); x < -708 returns 0 where exp() returns a denormal or 0 (< 3e-308 of
+ * the amplitude it multiplies - a decayed exponential; one integer compare). The caller checks the argument
+ * range once per pass, outside the time loop, and falls back to exp() otherwise (vb_models.cuh).
  */
 #pragma once
 #include "vb_device.cuh"
@@ -86,14 +87,16 @@ FAB_DEV double exp_fast(double x, const double *tab)
     const double p = r * q;
     const double v = fma(T, p, Tlo) + T;
     /* scale by 2^m on the integer pipe: v is in [1, 2), m in [-1022, 1021] for |x| < 708 */
-    return __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));
+    const double e = __hiloint2double(__double2hiint(v) + (m << 20), __double2loint(v));
+    /* x < -708 (a rate that has run away: the term has decayed to nothing): 0. Sign bit set and magnitude bits
+     * above those of 708.0, tested on the high word */
+    return ((unsigned)__double2hiint(x) > 0xc0862000u) ? 0.0 : e;
 }
 
-/* |x| < 708 for every argument the pass will form: |rate| * t_max < 708 */
+/* every argument -rate * t the pass will form is finite and < 708 (no overflow); large positive rates are fine */
 FAB_DEV bool exp_fast_range_ok(double rate, double t_max)
 {
-    const double a = fabs(rate) * t_max;
-    return a < 708.0; /* false for NaN */
+    return rate * t_max > -708.0 && rate < 1e300; /* false for NaN */
 }
 
 } // namespace fab

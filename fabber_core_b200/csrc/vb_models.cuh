@@ -268,8 +268,7 @@ template <int NE> struct ExpModel
 #pragma unroll
         for (int k = 0; k < NE; k++)
             ok = ok && exp_fast_range_ok(p0[2 * k + 1], t_max) && exp_fast_range_ok(pp[2 * k + 1], t_max)
-                && exp_fast_range_ok(pn[2 * k + 1], t_max) && fabs(pp[2 * k + 1] - p0[2 * k + 1]) * t_max < 0.05
-                && fabs(pn[2 * k + 1] - p0[2 * k + 1]) * t_max < 0.05; /* false for NaN */
+                && exp_fast_range_ok(pn[2 * k + 1], t_max);
         return ok;
     }
     /* Inside the table pass the two PERTURBED values of each rate come by series from the centre exponential:
@@ -283,7 +282,8 @@ template <int NE> struct ExpModel
      * of the Jacobian entry 5e-20 of it - both far below the rounding of the sum they enter. So the series is used
      * for every sample of the table pass, without a test (a per-pass choice between passes made whole warps run
      * both once a few voxels' rates had grown: the C5 noise kernel went from 14.5 to 36 ms over ten iterations; a
-     * per-sample branch cost C3 15 % - both measured). fast_ok() keeps |z| < 0.05 as a backstop. */
+     * per-sample branch cost C3 15 % - both measured). The bound holds for any |c| a double can reach before
+     * r = exp(c) overflows the table pass's own range test. */
     /* e0 * exp(z), |z| small (see above) */
     static FAB_DEV double scaled_exp_small(double e0, double z)
     {

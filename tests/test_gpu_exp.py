@@ -35,3 +35,17 @@ def test_exp_fast_within_one_ulp():
         err = abs(Decimal(float(fast[i])) - exact) / Decimal(float(np.spacing(float(exact))))
         worst = max(worst, float(err))
     assert worst <= 1.0, worst
+
+
+def test_exp_fast_returns_zero_for_decayed_arguments():
+    """x < -708 (a decay rate that has run away): 0 where exp() gives a denormal or 0 - less than 3e-308 of the
+    amplitude it multiplies - so such voxels stay on the table pass instead of dragging their warp on to libm"""
+    x = np.concatenate([np.linspace(-708.5, -2000.0, 500), np.array([-1e6, -1e300, -np.inf])])
+    L = device.lib()
+    L.fabber_cuda_exp_probe.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    dx = device.DeviceArray.from_host(x)
+    df, dr = device.DeviceArray(x.shape, np.float64), device.DeviceArray(x.shape, np.float64)
+    device.check(L.fabber_cuda_exp_probe(dx.ptr, df.ptr, dr.ptr, x.size, None), "exp probe")
+    fast, ref = df.to_host(), dr.to_host()
+    assert np.all(fast == 0.0)
+    assert np.all(ref < 3e-308)
