@@ -1407,6 +1407,21 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
                 if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
                     return cuda_fail(pe, "cudaDeviceEnablePeerAccess");
                 cudaGetLastError();
+                /* the slabs' state lives in the stream-ordered allocator's pool, which peer access does not cover:
+                 * the pool of device q must grant device r access explicitly */
+                cudaMemPool_t pool;
+                pe = cudaDeviceGetDefaultMemPool(&pool, parts[q].device);
+                if (pe == cudaSuccess)
+                {
+                    cudaMemAccessDesc desc;
+                    memset(&desc, 0, sizeof(desc));
+                    desc.location.type = cudaMemLocationTypeDevice;
+                    desc.location.id = parts[r].device;
+                    desc.flags = cudaMemAccessFlagsProtReadWrite;
+                    pe = cudaMemPoolSetAccess(pool, &desc, 1);
+                }
+                if (pe != cudaSuccess)
+                    return cuda_fail(pe, "cudaMemPoolSetAccess (peer access to the slabs' scratch)");
             }
     std::vector<fabber_cuda_vb_problem> probs(W, *prob);
     std::vector<cudaStream_t> streams(W, nullptr);
