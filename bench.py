@@ -420,6 +420,14 @@ class Dist(object):
             import torch.distributed as dist
 
             self.dist = dist
+            # a CPU-side group for the phases in which rank 0 alone drives every GPU: an NCCL barrier would leave a
+            # kernel spinning on the other ranks' GPUs, and two processes on one GPU are time-sliced - rank 0's
+            # kernels there ran at half speed (measured at N = 2)
+            self.cpu = dist.new_group(backend="gloo")
+
+    def cpu_barrier(self):
+        if self.world > 1:
+            self.dist.barrier(group=self.cpu)
 
     def barrier(self):
         import torch
@@ -588,6 +596,9 @@ def run_workload(wname, args, D, rank, local_rank, world, steps, warmup, main_li
 
     # ---- end to end through the reference's public C API with host buffers: rank 0 drives all `world` GPUs ----
     D.barrier()
+    import torch
+
+    torch.cuda.synchronize()
     e2e = None
     if rank == 0:
         host = host_volume_full(w, n_total, world)
@@ -604,6 +615,7 @@ def run_workload(wname, args, D, rank, local_rank, world, steps, warmup, main_li
                        "out); the library deals the voxel ranges to the GPUs it was given (FABBER_B200_DEVICES=%s); "
                        "wall clock" % os.environ.get("FABBER_B200_DEVICES", "")}
         del host
+    D.cpu_barrier()  # the other ranks wait on the CPU, their GPUs idle
     D.barrier()
     if rank != 0:
         return None
@@ -681,6 +693,7 @@ def spatial_slab_bench(args, w, D, rank, local_rank, world, n_total, steps, warm
                "timing": "CUDA events on every slab's stream around set-up + iterations + result permutation, max over "
                          "the slabs, summed over the steps (the call is synchronous)",
                "roofline": roofline_block(w, its // world, t_ms / steps * 1e-3, n_total // world, fp64_peak, True)}
+    D.cpu_barrier()  # the other ranks wait on the CPU: rank 0's kernels have their GPUs to themselves
     D.barrier()
     return rec
 

@@ -354,6 +354,7 @@ struct Parameter
 std::string ExpandPriorTypesString(std::string priors_str, unsigned num_params); /* priors.cc:35-106 */
 
 /* ---- forward models ----------------------------------------------------------------------------- */
+class MVNDist; /* host/operators.h */
 class FwdModel
 {
 public:
@@ -367,10 +368,27 @@ public:
     virtual std::string GetDescription() const { return ""; }
     virtual void GetOptions(std::vector<OptionSpec> &) const {}
     virtual void Initialize(FabberRunData &rundata) = 0;
-    virtual void GetParameterDefaults(std::vector<Parameter> &params) const = 0;
-    /* one voxel's model prediction from model-space parameters (fwdmodel.h:149) */
+    /* default: built from the deprecated NameParams + HardcodedInitialDists + ardindices (fwdmodel.cc:339-363) */
+    virtual void GetParameterDefaults(std::vector<Parameter> &params) const;
+    /* one voxel's model prediction from model-space parameters (fwdmodel.h:149); default: forwards to the
+     * deprecated Evaluate (fwdmodel.h:152) */
     virtual void EvaluateModel(const std::vector<double> &params, std::vector<double> &result, int n_times,
-        const std::string &key = "") const = 0;
+        const std::string &key = "") const;
+    /* ---- deprecated API (fwdmodel.h:256-348; rundata.h:27 keeps it compiled in the reference): a model may
+     * implement these instead of GetParameterDefaults / EvaluateModel ---- */
+    virtual void Evaluate(const std::vector<double> &params, std::vector<double> &result) const
+    {
+        (void)params;
+        (void)result;
+    }
+    virtual int NumParams() const { return (int)m_params.size(); }
+    virtual void NameParams(std::vector<std::string> &names) const { (void)names; }
+    virtual void HardcodedInitialDists(MVNDist &prior, MVNDist &posterior) const
+    {
+        (void)prior;
+        (void)posterior;
+    }
+    std::vector<int> ardindices; /* 1-based indices of parameters under an ARD prior */
     virtual void GetOutputs(std::vector<std::string> &) const {}
     /* B200 addition: describe the compiled __device__ Evaluate hook for this model instance */
     virtual void GetDeviceModel(fabber_cuda_model &m) const = 0;
@@ -433,7 +451,7 @@ private:
 
 const char *fabber_b200_version();
 /* bumped whenever FwdModel / Parameter / fabber_cuda_model / the launcher table change layout */
-#define FABBER_B200_PLUGIN_ABI 1
+#define FABBER_B200_PLUGIN_ABI 2 /* 2: FwdModel gained the deprecated-API virtuals, ModelLaunchers gained sp_preload */
 
 /* tools.cc:27-40: VEST or plain ASCII matrix file -> row-major values */
 void read_matrix_file(const std::string &filename, std::vector<double> &values, int &rows, int &cols);

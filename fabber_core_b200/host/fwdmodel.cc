@@ -18,6 +18,8 @@
 
 #include "fabber_host.h"
 
+#include "operators.h"
+
 namespace fabber_b200
 {
 double transform_to_model(char code, double v)
@@ -464,6 +466,33 @@ void ExpFwdModel::GetDeviceModel(fabber_cuda_model &m) const
     m.n_params = 2 * m_num;
     m.exp_num = m_num;
     m.exp_dt = m_dt;
+}
+
+/* fwdmodel.cc:339-363: a model written against the deprecated API names its parameters and fills two MVNs */
+void FwdModel::GetParameterDefaults(std::vector<Parameter> &params) const
+{
+    params.clear();
+    std::vector<std::string> names;
+    NameParams(names);
+    MVNDist priors((int)names.size()), posts((int)names.size());
+    HardcodedInitialDists(priors, posts);
+    for (size_t i = 0; i < names.size(); i++)
+    {
+        Parameter p((unsigned)i, names[i], DistParams(priors.means[i], priors.GetCovariance((int)i, (int)i)),
+            DistParams(posts.means[i], posts.GetCovariance((int)i, (int)i)), 'N', 'I');
+        if (std::find(ardindices.begin(), ardindices.end(), (int)i + 1) != ardindices.end())
+            p.prior_type = 'A';
+        params.push_back(p);
+    }
+}
+/* fwdmodel.h:149-153 */
+void FwdModel::EvaluateModel(const std::vector<double> &params, std::vector<double> &result, int n_times,
+    const std::string &key) const
+{
+    if (key != "")
+        throw FabberInternalError("This model does not provide the output '" + key + "'");
+    result.assign(n_times, 0.0);
+    Evaluate(params, result);
 }
 
 } // namespace fabber_b200

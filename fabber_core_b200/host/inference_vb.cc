@@ -17,6 +17,7 @@
 #include <chrono>
 
 #include "fabber_host.h"
+#include "operators.h"
 
 namespace fabber_b200
 {
@@ -244,8 +245,8 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
         q.post_var = params[i].post.var();
     }
 
-    /* ---- noise model options ---------------------------------------------------------------------- */
-    m_pattern.assign(T, 0);
+    /* ---- noise model, convergence detector, priors: the reference's operator classes (host/operators.h) know
+     * their options, their hard-coded initial distributions and their device codes ----------------------- */
     m_masked.assign(T, 0);
     const std::vector<int> mt = rundata.GetIntList("mt", 1); /* inference.cc:96-103 */
     for (size_t i = 0; i < mt.size(); i++)
@@ -254,106 +255,46 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
             throw InvalidOptionValue("mt", stringify(mt[i]), "Masked time point beyond the end of the data");
         m_masked[mt[i] - 1] = 1;
     }
+    if (m_ar && !mt.empty())
+        throw InvalidOptionValue("noise", "ar", "AR noise model does not support masked time points");
+    std::unique_ptr<NoiseModel> noise(NoiseModel::NewFromName(rundata.GetString("noise")));
+    noise->Initialize(rundata);
+    noise->Describe(prob, T, m_pattern);
     if (m_ar)
     {
         /* noisemodel_ar.cc:305-349: one echo, no cross terms is what the device kernels implement */
-        if (!mt.empty())
-            throw InvalidOptionValue("noise", "ar", "AR noise model does not support masked time points");
-        if (rundata.GetIntDefault("num-echoes", 1) != 1)
-            throw InvalidOptionValue("num-echoes", rundata.GetString("num-echoes"), "only 1 echo has a device kernel");
-        if (rundata.GetStringDefault("ar1-cross-terms", "none") != "none")
-            throw InvalidOptionValue("ar1-cross-terms", rundata.GetString("ar1-cross-terms"), "only 'none' has a device kernel");
         for (const char *key : { "noise-initial-prior", "noise-initial-posterior" })
             if (rundata.GetStringDefault(key, "modeldefault") != "modeldefault")
                 throw InvalidOptionValue(key, rundata.GetString(key),
                     "the AR(1) device kernel starts alpha at N(0, 1e4 I) only: not supported with noise=ar");
-        prob.noise_type = FABBER_NOISE_AR1;
-        prob.n_phis = 1;
-        prob.noise_prior_b[0] = 1e6; /* noisemodel_ar.cc:379-403 */
-        prob.noise_prior_c[0] = 1e-6;
-        prob.noise_post_b[0] = 1e-8;
-        prob.noise_post_c[0] = 1e-6;
-        prob.ar_alpha_prior_prec = 1e-4;
         m_noise_params = 3; /* alpha (2) + phi (1): Ar1cParams::OutputAsMVN, noisemodel_ar.cc:287-300 */
         m_nphis = 1;
     }
     else
     {
-        prob.noise_type = FABBER_NOISE_WHITE;
-        const std::string pat = rundata.GetStringDefault("noise-pattern", "1");
-        std::vector<int> digits; /* noisemodel_white.cc:166-215 */
-        for (size_t i = 0; i < pat.size(); i++)
-        {
-            const char ch = pat[i];
-            if (ch >= '1' && ch <= '9')
-                digits.push_back(ch - '0');
-            else if (ch >= 'A' && ch <= 'Z')
-                digits.push_back(ch - 'A' + 10);
-            else if (ch >= 'a' && ch <= 'z')
-                digits.push_back(ch - 'a' + 10);
-            else
-                throw InvalidOptionValue("noise-pattern", pat, "Invalid character in pattern");
-        }
-        if (digits.empty())
-            throw InvalidOptionValue("noise-pattern", pat, "Pattern must not be empty");
-        int nphis = *std::max_element(digits.begin(), digits.end());
-        if (nphis > FABBER_CUDA_MAX_PHIS)
-            throw InvalidOptionValue("noise-pattern", pat, "more noise precisions than the device kernels carry");
-        for (int t = 0; t < T; t++)
-            m_pattern[t] = (unsigned char)(digits[t % digits.size()] - 1);
-        prob.n_phis = nphis;
-        m_nphis = nphis;
-        m_noise_params = nphis;
-        const double phiprior = rundata.GetDoubleDefault("prior-noise-stddev", -1);
-        if (phiprior < 0 && phiprior != -1)
-            throw InvalidOptionValue("prior-noise-stddev", stringify(phiprior), "Must be > 0");
-        for (int i = 0; i < nphis; i++)
-        {
-            if (phiprior == -1)
-            {
-                prob.noise_prior_b[i] = 1e6; /* noisemodel_white.cc:142-149 */
-                prob.noise_prior_c[i] = 1e-6;
-                prob.noise_post_b[i] = 1e-8;
-                prob.noise_post_c[i] = 50;
-            }
-            else
-            {
-                prob.noise_prior_c[i] = prob.noise_post_c[i] = 0.5; /* :156-161 */
-                prob.noise_prior_b[i] = prob.noise_post_b[i] = 1 / (phiprior * phiprior * 0.5);
-            }
-        }
-        prob.locked_noise_stdev = rundata.GetDoubleDefault("locked-noise-stdev", -1);
+        m_nphis = prob.n_phis;
+        m_noise_params = m_nphis;
         /* after the hard-coded values, as in the reference (inference_vb.cc:204-205) */
-        NoiseGammasFromMvnFile(rundata, "noise-initial-prior", nphis, prob.noise_prior_b, prob.noise_prior_c);
-        NoiseGammasFromMvnFile(rundata, "noise-initial-posterior", nphis, prob.noise_post_b, prob.noise_post_c);
+        NoiseGammasFromMvnFile(rundata, "noise-initial-prior", m_nphis, prob.noise_prior_b, prob.noise_prior_c);
+        NoiseGammasFromMvnFile(rundata, "noise-initial-posterior", m_nphis, prob.noise_post_b, prob.noise_post_c);
     }
     prob.phi_pattern = m_pattern.data();
     prob.time_masked = mt.empty() ? nullptr : m_masked.data();
 
-    /* ---- convergence (setup.cc:49-57, convergence.cc Initialize functions) --------------------------- */
-    const std::string conv = rundata.GetStringDefault("convergence", "maxits");
-    if (conv == "maxits")
-        prob.conv_type = FABBER_CONV_MAXITS;
-    else if (conv == "pointzeroone")
-        prob.conv_type = FABBER_CONV_FCHANGE;
-    else if (conv == "freduce")
-        prob.conv_type = FABBER_CONV_FREDUCE;
-    else if (conv == "trialmode")
-        prob.conv_type = FABBER_CONV_TRIALMODE;
-    else if (conv == "lm")
-        prob.conv_type = FABBER_CONV_LM;
-    else
-        throw InvalidOptionValue("convergence", conv, "Unrecognized convergence detector");
-    prob.max_iterations = rundata.GetIntDefault("max-iterations", 10);
-    if (prob.max_iterations <= 0)
-        throw InvalidOptionValue("max-iterations", stringify(prob.max_iterations), "Must be positive");
-    prob.fchange = (conv == "lm") ? rundata.GetDoubleDefault("max-fchange", 0.01)
-                                  : rundata.GetDoubleDefault("min-fchange", 0.01);
-    if (!(prob.fchange > 0))
-        throw InvalidOptionValue(conv == "lm" ? "max-fchange" : "min-fchange", stringify(prob.fchange), "Must be positive");
-    prob.max_trials = rundata.GetIntDefault("max-trials", 10);
-    if (prob.max_trials <= 0)
-        throw InvalidOptionValue("max-trials", stringify(prob.max_trials), "Must be positive");
+    /* convergence (setup.cc:49-57, convergence.cc Initialize functions) */
+    std::unique_ptr<ConvergenceDetector> detector(
+        ConvergenceDetector::NewFromName(rundata.GetStringDefault("convergence", "maxits")));
+    detector->Initialize(rundata);
+    detector->Describe(prob);
+    if (rundata.GetIntDefault("max-trials", 10) <= 0)
+        throw InvalidOptionValue("max-trials", rundata.GetString("max-trials"), "Must be positive");
+    /* priors (priors.cc:490-528): the factory validates every parameter's prior type and options (image data
+     * present, spatial-dims / speed in range); the types themselves travel in prob.params[] */
+    {
+        std::vector<Prior *> priors = PriorFactory(rundata).CreatePriors(params);
+        for (size_t i = 0; i < priors.size(); i++)
+            delete priors[i];
+    }
     const bool spatial = IsSpatial(rundata, params);
     const bool useF = !spatial && prob.conv_type != FABBER_CONV_MAXITS;
     m_needF = useF || m_printF || m_saveF || m_saveFsHistory; /* inference_vb.cc:242 */

@@ -588,9 +588,7 @@ SpatialPrior::SpatialPrior(const Parameter &p, FabberRunData &rundata)
     m_spatial_dims = rundata.GetIntDefault("spatial-dims", 3);
     if (m_spatial_dims < 0 || m_spatial_dims > 3)
         throw InvalidOptionValue("spatial-dims", stringify(m_spatial_dims), "Must be 0, 1, 2 or 3");
-    m_spatial_speed = rundata.GetDoubleDefault("spatial-speed", -1);
-    if (m_spatial_speed <= 1 && m_spatial_speed != -1)
-        throw InvalidOptionValue("spatial-speed", stringify(m_spatial_speed), "Must be > 1 or -1 (no limit)");
+    m_spatial_speed = rundata.GetDoubleDefault("spatial-speed", -1); /* range unchecked, as in the reference */
     m_q1 = rundata.GetDoubleDefault("spatial-q1", 10.0);
     m_q2 = rundata.GetDoubleDefault("spatial-q2", 1.0);
     m_update_first_iter = rundata.GetBool("update-spatial-prior-on-first-iteration");

@@ -151,4 +151,4 @@ def test_nccl_slab_run_equals_one_gpu_run(its, tol):
     rep = json.loads(line[len("SLAB_NCCL_REPORT "):])
     assert rep["bad"] == 0 and rep["ak_same_on_all_ranks"]
     assert rep["mean_err_in_std"] < tol, rep
-    assert rep["noise_rel"] < tol and rep["f_rel"] < tol and rep["ak_rel"] < min(tol, 1e-6), rep
+    assert rep["noise_rel"] < tol and rep["f_rel"] < tol and rep["ak_rel"] < min(tol, 1e-6 if its <= 3 else 1e-5), rep

@@ -23,14 +23,14 @@ def run(extra):
     ({"mt1": "13"}, ("mt", "beyond the end of the data")),                      # 12 time points
     ({"noise": "ar", "mt1": "2"}, ("AR noise model does not support masked time points",)),
     ({"noise": "ar", "num-echoes": "2"}, ("num-echoes", "only 1 echo")),
-    ({"noise": "ar", "ar1-cross-terms": "dual"}, ("ar1-cross-terms", "only 'none'")),
+    ({"noise": "ar", "ar1-cross-terms": "dual"}, ("ar1-cross-terms", "ar1-cross-terms=none with num-echoes=1")),
     ({"noise": "pink"}, ("noise", "Unrecognized noise model")),
     ({"prior-noise-stddev": "-2"}, ("prior-noise-stddev", "Must be > 0")),
     ({"model": "nosuch"}, ("model", "Unrecognized forward model")),
     ({"method": "nlls"}, ("method", "nlls")),
     ({"degree": "-1"}, ("degree", "Minimum 0")),
     ({"max-iterations": "0"}, ("max-iterations", "Must be positive")),
-    ({"method": "spatialvb", "param-spatial-priors": "M+", "spatial-dims": "4"}, ("spatial-dims", "Maximum 3")),
+    ({"method": "spatialvb", "param-spatial-priors": "M+", "spatial-dims": "4"}, ("spatial-dims", "Must be 0, 1, 2 or 3")),
 ])
 def test_invalid_options_are_refused_before_any_device_work(extra, fragments):
     with pytest.raises(fab.FabberException) as e:
