@@ -26,7 +26,7 @@ def test_plugin_exports_the_reference_symbols():
     C.CDLL(HOSTLIB, mode=C.RTLD_GLOBAL)
     lib = C.CDLL(PLUGIN)
     lib.get_model_name.restype = C.c_char_p
-    assert lib.fabber_b200_plugin_abi() == 1
+    assert lib.fabber_b200_plugin_abi() == 2
     assert lib.get_num_models() == 2
     assert [lib.get_model_name(i) for i in range(2)] == [b"sine", b"exp"]
     assert lib.get_model_name(2) is None
