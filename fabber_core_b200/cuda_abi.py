@@ -11,6 +11,13 @@ import numpy as np
 MAX_PARAMS = 8
 MAX_PHIS = 4
 AR_NOISE_FIELDS = 7
+AR_CROSS_BY_NAME = {"none": 0, "same": 1, "dual": 2}
+
+
+def ar2_noise_fields(n_alphas):
+    """FABBER_CUDA_AR2_NOISE_FIELDS: b1 c1 b2 c2, alpha means, packed alpha precisions"""
+    return 4 + n_alphas + n_alphas * (n_alphas + 1) // 2
+
 
 OK, ERR_INVALID, ERR_CUDA, ERR_BAD_VOXEL = 0, -1, -2, -3
 MODEL_LINEAR, MODEL_POLY, MODEL_EXP = 1, 2, 3
@@ -71,6 +78,7 @@ class VbProblem(C.Structure):
         ("noise_post_c", C.c_double * MAX_PHIS),
         ("locked_noise_stdev", C.c_double),
         ("ar_alpha_prior_prec", C.c_double),
+        ("ar_cross_terms", C.c_int),
         ("conv_type", C.c_int),
         ("max_iterations", C.c_int),
         ("fchange", C.c_double),
@@ -163,7 +171,8 @@ class ProblemSpec(object):
                  locked_noise_stdev=-1.0, convergence="maxits", max_iterations=10, fchange=0.01,
                  max_trials=10, need_f=None, f_history_len=0, allow_bad_voxels=False,
                  prior_types=None, spatial_dims=3, spatial_speed=-1.0, spatial_q1=10.0, spatial_q2=1.0,
-                 update_first_iter=False, param_overrides=None, plugin_launchers=None):
+                 update_first_iter=False, param_overrides=None, plugin_launchers=None, num_echoes=1,
+                 ar_cross_terms="none"):
         self.keep = []
         self.n_times = int(n_times)
         m = Model()
@@ -248,9 +257,13 @@ class ProblemSpec(object):
                     prob.noise_prior_c[i] = prob.noise_post_c[i] = c
         elif noise == "ar":
             prob.noise_type = NOISE_AR1
-            prob.n_phis = 1
-            prob.noise_prior_b[0], prob.noise_prior_c[0] = 1e6, 1e-6
-            prob.noise_post_b[0], prob.noise_post_c[0] = 1e-8, 1e-6
+            if num_echoes not in (1, 2) or (num_echoes == 1 and ar_cross_terms != "none"):
+                raise ValueError("num_echoes 1 or 2; cross terms need two echoes")
+            prob.n_phis = num_echoes
+            prob.ar_cross_terms = AR_CROSS_BY_NAME[ar_cross_terms]
+            for i in range(num_echoes):
+                prob.noise_prior_b[i], prob.noise_prior_c[i] = 1e6, 1e-6
+                prob.noise_post_b[i], prob.noise_post_c[i] = 1e-8, 1e-6
             prob.ar_alpha_prior_prec = 1e-4
         else:
             raise ValueError(noise)
@@ -275,7 +288,11 @@ class ProblemSpec(object):
         prob.update_first_iter = int(update_first_iter)
         self.prob = prob
         self.P = P
-        self.NN = AR_NOISE_FIELDS if noise == "ar" else 2 * prob.n_phis
+        self.n_alphas = 2 + prob.ar_cross_terms if noise == "ar" else 0
+        if noise == "ar":
+            self.NN = AR_NOISE_FIELDS if num_echoes == 1 else ar2_noise_fields(self.n_alphas)
+        else:
+            self.NN = 2 * prob.n_phis
         self.ncov = P * (P + 1) // 2
 
 

@@ -69,6 +69,35 @@ def ar_design(n_times=200):
     return np.stack([np.ones(n_times), t / n_times, np.sin(2 * np.pi * t / 50), np.cos(2 * np.pi * t / 50)], axis=1)
 
 
+def dual_echo_design(n_pairs=100):
+    """Two-echo design, samples interleaved TE1 TE2 TE1 .. (2 n_pairs rows): a baseline, a slow BOLD-like
+    regressor that doubles at the second echo, and a tag/control alternation that is weaker there."""
+    t = np.arange(n_pairs, dtype=np.float64)
+    slow = np.sin(2 * np.pi * t / 20)
+    tag = np.where(t % 2 == 0, 1.0, -1.0)
+    d = np.zeros((2 * n_pairs, 3))
+    d[0::2] = np.stack([np.ones(n_pairs), slow, tag], axis=1)
+    d[1::2] = np.stack([0.7 * np.ones(n_pairs), 2 * slow, 0.3 * tag], axis=1)
+    return d
+
+
+def dual_echo_volume(n_voxels, n_pairs=100, rho1=0.3, rho2=0.2, cross=0.4, seed=1006, device="cpu"):
+    """y = design beta + noise; each echo has AR(1) noise of its own and the second echo also carries `cross`
+    times the first echo's noise of the same time point (what ar1-cross-terms models)."""
+    g = _gen(device, seed)
+    design = torch.as_tensor(dual_echo_design(n_pairs), device=device)
+    beta = 50.0 * torch.randn((3, n_voxels), generator=g, device=device, dtype=torch.float64)
+    y = torch.empty((2 * n_pairs, n_voxels), dtype=torch.float32, device=device)
+    e1 = torch.zeros(n_voxels, dtype=torch.float64, device=device)
+    e2 = torch.zeros(n_voxels, dtype=torch.float64, device=device)
+    for t in range(n_pairs):
+        e1 = rho1 * e1 + torch.randn(n_voxels, generator=g, device=device, dtype=torch.float64)
+        e2 = rho2 * e2 + cross * e1 + 2.0 * torch.randn(n_voxels, generator=g, device=device, dtype=torch.float64)
+        y[2 * t] = (design[2 * t] @ beta + e1).to(torch.float32)
+        y[2 * t + 1] = (design[2 * t + 1] @ beta + e2).to(torch.float32)
+    return y
+
+
 def linear_ar_volume(n_voxels, n_times=200, rho=0.3, seed=1004, device="cpu"):
     """C4: y = design beta + AR(1) noise (rho, unit innovations); beta ~ N(0, 100^2)^4."""
     g = _gen(device, seed)

@@ -32,7 +32,12 @@ extern "C" {
 
 #define FABBER_CUDA_MAX_PARAMS 8
 #define FABBER_CUDA_MAX_PHIS 4
-#define FABBER_CUDA_AR_NOISE_FIELDS 7
+#define FABBER_CUDA_AR_NOISE_FIELDS 7 /* AR(1), one echo: b c alpha1 alpha2 prec11 prec21 prec22 */
+/* AR(1), two echoes (num-echoes=2): b1 c1 b2 c2, the nA alpha means, the alpha precisions as a packed lower
+ * triangle (row-major: 11 21 22 31 ..). nA = 2 / 3 / 4 for ar1-cross-terms = none / same / dual
+ * (Ar1cNoiseModel::NumAlphas, noisemodel_ar.cc:367-377) */
+#define FABBER_CUDA_AR2_NOISE_FIELDS(nA) (4 + (nA) + (nA) * ((nA) + 1) / 2)
+#define FABBER_CUDA_AR_MAX_NOISE_FIELDS 18
 
 /* return codes */
 #define FABBER_CUDA_OK 0
@@ -52,7 +57,11 @@ extern "C" {
 
 /* noise models */
 #define FABBER_NOISE_WHITE 0 /* noisemodel_white.cc */
-#define FABBER_NOISE_AR1 1   /* noisemodel_ar.cc, num-echoes=1, ar1-cross-terms=none */
+#define FABBER_NOISE_AR1 1   /* noisemodel_ar.cc: n_phis = num-echoes (1 or 2), ar_cross_terms */
+/* ar1-cross-terms (noisemodel_ar.cc:332,367-377); anything but NONE needs two echoes (:336-340) */
+#define FABBER_AR_CROSS_NONE 0
+#define FABBER_AR_CROSS_SAME 1
+#define FABBER_AR_CROSS_DUAL 2
 
 /* convergence detectors (registry names in setup.cc:49-57) */
 #define FABBER_CONV_MAXITS 0    /* "maxits"        convergence.cc:43  */
@@ -113,7 +122,9 @@ typedef struct fabber_cuda_vb_problem
 
     /* noise */
     int noise_type; /* FABBER_NOISE_* */
-    int n_phis;     /* white: number of distinct phis in noise-pattern (<= FABBER_CUDA_MAX_PHIS) */
+    int n_phis;     /* white: number of distinct phis in noise-pattern (<= FABBER_CUDA_MAX_PHIS);
+                       AR1: num-echoes, 1 or 2 (0 is read as 1). Two echoes: the series interleaves them,
+                       TE1 TE2 TE1 TE2 .., n_times must be even (noisemodel_ar.cc:126-129) */
     const unsigned char *phi_pattern; /* HOST [T]: 0-based phi index per time point, NULL = all 0 */
     const unsigned char *time_masked; /* HOST [T]: 1 = masked time point (mt<n>), NULL = none */
     double noise_prior_b[FABBER_CUDA_MAX_PHIS]; /* Gamma scale of prior      (noisemodel_white.cc:144) */
@@ -122,6 +133,7 @@ typedef struct fabber_cuda_vb_problem
     double noise_post_c[FABBER_CUDA_MAX_PHIS];
     double locked_noise_stdev; /* <= 0: off (noisemodel_white.cc:265) */
     double ar_alpha_prior_prec; /* AR1: prior/initial precision of alpha (1e-4, noisemodel_ar.cc:393) */
+    int ar_cross_terms;         /* AR1: FABBER_AR_CROSS_* */
 
     /* convergence */
     int conv_type; /* FABBER_CONV_* */

@@ -17,7 +17,7 @@
  *   fwdmodel.cc:284-324 (GetInitialPosterior/ToFabber), :365-382 (EvaluateFabber)
  *   fwdmodel_poly.cc:62-80, examples/fwdmodel_exp.cc:65-91
  *   transforms.h:114-242, transforms.cc:17-25
- *   noisemodel_white.cc:127-454, noisemodel_ar.cc:83-223,379-769 (num-echoes=1 only)
+ *   noisemodel_white.cc:127-454, noisemodel_ar.cc:83-223,379-769 (num-echoes=1 and 2, all ar1-cross-terms)
  *   priors.cc:108-181 (Default/Image/ARD), :221-488 (SpatialPrior)
  *   convergence.cc:34-378, convergence.h
  *   dist_mvn.cc:57-100,197-265, dist_gamma.cc:21-33, tools.cc:87-98 (gammaln)
@@ -38,6 +38,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -585,6 +586,10 @@ struct NoiseParams
     // AR(1): alpha MVN (size 2) and the marginal tridiagonal Q = M00 + M10 E[a] + M20 E[a^2]
     MVN alpha;
     Vec q_diag, q_off;
+    // AR(1), two echoes: alpha MVN of size 2 / 3 / 4 and one marginal per echo, sparse symmetric
+    // ((row, col) with row >= col stands for both triangles)
+    typedef std::map<std::pair<int, int>, real> SymSparse;
+    std::vector<SymSparse> Qm;
     NoiseParams()
         : alpha(2)
     {
@@ -595,8 +600,8 @@ struct NoiseModel
 {
     const fabber_cuda_vb_problem *prob;
     int T, P;
-    bool ar;
-    int nPhis;
+    bool ar, ar2;
+    int nPhis, nAlphas;
     std::vector<Vec> Qis; // white: 0/1 diagonal masks per phi (noisemodel_white.cc:166-226)
 
     void init(const fabber_cuda_vb_problem *p)
@@ -605,7 +610,9 @@ struct NoiseModel
         T = p->n_times;
         P = p->model.n_params;
         ar = p->noise_type == FABBER_NOISE_AR1;
-        nPhis = ar ? 1 : p->n_phis;
+        nPhis = ar ? (p->n_phis == 2 ? 2 : 1) : p->n_phis;
+        ar2 = ar && nPhis == 2;
+        nAlphas = 2 + (ar2 ? p->ar_cross_terms : 0); // Ar1cNoiseModel::NumAlphas, noisemodel_ar.cc:367-377
         if (!ar)
         {
             Qis.assign(nPhis, Vec(T, 0.0));
@@ -1002,6 +1009,284 @@ struct NoiseModel
         return F;
     }
 
+    // ------------------------------ AR(1), num-echoes=2 -----------------------------------
+    // The series interleaves the echoes, TE1 TE2 TE1 TE2 .. (noisemodel_ar.cc:126-129), nTimes = T / 2
+    // samples each. Every alpha matrix is ONE diagonal line of nTimes-1 entries of +-1, reflected to keep the
+    // matrix symmetric (:108-179). n = 1, 2 is the echo; (a12pow, a34pow) the powers of the echo's own alpha
+    // and of its cross-term alpha the matrix multiplies in the marginal.
+    typedef NoiseParams::SymSparse SymSparse;
+    SymSparse ar2_matrix(int n, int a12pow, int a34pow) const
+    {
+        const int nTimes = T / nPhis;
+        int row, col; // 1-based, as in the reference
+        switch (a12pow * 10 + a34pow)
+        {
+        case 0:
+            row = col = 1 + nPhis;
+            break;
+        case 10:
+            row = 1;
+            col = 1 + nPhis;
+            break;
+        case 20:
+            row = col = 1;
+            break;
+        case 1:
+            row = 4;
+            col = 3;
+            break;
+        case 11:
+            row = 4;
+            col = 1;
+            break;
+        case 2:
+            row = col = 4;
+            break;
+        default:
+            throw InternalError(FABBER_VOX_SINGULAR, "Ar1cMatrixCache::Update Invalid row/col");
+        }
+        const real value = (a12pow + a34pow == 1) ? -1 : 1;
+        if (n == 2)
+        {
+            row = row - 1 + 2 * (row % 2); // 2n->2n-1, 2n-1->2n: the other echo
+            col = col - 1 + 2 * (col % 2);
+        }
+        SymSparse m;
+        for (int count = 0; count < nTimes - 1; count++, row += nPhis, col += nPhis)
+            m[std::make_pair(std::max(row, col) - 1, std::min(row, col) - 1)] = value;
+        return m;
+    }
+    static void sym_axpy(SymSparse &dst, real w, const SymSparse &src)
+    {
+        for (SymSparse::const_iterator e = src.begin(); e != src.end(); ++e)
+            dst[e->first] += w * e->second;
+    }
+    static Vec sym_apply(const SymSparse &M, const Vec &x)
+    {
+        Vec y(x.size(), 0.0);
+        for (SymSparse::const_iterator e = M.begin(); e != M.end(); ++e)
+        {
+            const int r = e->first.first, c = e->first.second;
+            y[r] += e->second * x[c];
+            if (r != c)
+                y[c] += e->second * x[r];
+        }
+        return y;
+    }
+    static real sym_quad(const SymSparse &M, const Vec &k)
+    {
+        Vec y = sym_apply(M, k);
+        real s = 0;
+        for (size_t i = 0; i < k.size(); i++)
+            s += k[i] * y[i];
+        return s;
+    }
+    static Mat sym_JtMJ(const Mat &J, const SymSparse &M)
+    {
+        Mat MJ(J.r, J.c);
+        Vec col(J.r);
+        for (int p = 0; p < J.c; p++)
+        {
+            for (int t = 0; t < J.r; t++)
+                col[t] = J(t, p);
+            Vec y = sym_apply(M, col);
+            for (int t = 0; t < J.r; t++)
+                MJ(t, p) = y[t];
+        }
+        return mul(transpose(J), MJ);
+    }
+    static real op_klj2(const Vec &k, const Mat &Sigma, const Mat &J, const SymSparse &M)
+    {
+        return sym_quad(M, k) + trace(mul(Sigma, sym_JtMJ(J, M)));
+    }
+
+    // Ar1cMatrixCache::Update (noisemodel_ar.cc:197-222)
+    void ar2_update_marginal(NoiseParams &np) const
+    {
+        const Mat &cov = np.alpha.GetCovariance();
+        Mat covarPlus(nAlphas, nAlphas);
+        for (int i = 0; i < nAlphas; i++)
+            for (int j = 0; j < nAlphas; j++)
+                covarPlus(i, j) = cov(i, j) + np.alpha.means[i] * np.alpha.means[j];
+        np.Qm.assign(nPhis, SymSparse());
+        for (int n = 1; n <= nPhis; n++)
+        {
+            SymSparse &Q = np.Qm[n - 1];
+            sym_axpy(Q, 1.0, ar2_matrix(n, 0, 0));
+            sym_axpy(Q, np.alpha.means[n - 1], ar2_matrix(n, 1, 0));
+            sym_axpy(Q, covarPlus(n - 1, n - 1), ar2_matrix(n, 2, 0));
+            if (nAlphas >= 3)
+            {
+                const int Tn = (nAlphas == 4) ? 2 + n : 3; // 1-based index of this echo's cross-term alpha
+                sym_axpy(Q, np.alpha.means[Tn - 1], ar2_matrix(n, 0, 1));
+                sym_axpy(Q, covarPlus(n - 1, Tn - 1), ar2_matrix(n, 1, 1));
+                sym_axpy(Q, covarPlus(Tn - 1, Tn - 1), ar2_matrix(n, 0, 2));
+            }
+        }
+    }
+
+    void ar2_precalculate(NoiseParams &post, const NoiseParams &prior) const
+    {
+        const int nTimes = T / nPhis;
+        ar2_update_marginal(post);
+        for (int i = 0; i < nPhis; i++)
+            post.phis[i].c = prior.phis[i].c + (nTimes - 1) * 0.5; // noisemodel_ar.cc:765-768
+    }
+
+    void ar2_update_noise(NoiseParams &post, const NoiseParams &prior, const MVN &theta,
+        const LinModel &lin, const Vec &data) const
+    {
+        const int nTimes = T / nPhis;
+        // UpdateAlpha (noisemodel_ar.cc:447-528)
+        {
+            Vec k = calc_k(theta, lin, data);
+            Vec si_ci(nPhis);
+            for (int i = 0; i < nPhis; i++)
+                si_ci[i] = post.phis[i].b * post.phis[i].c;
+            const Mat &Sigma = theta.GetCovariance(); // OpKLJ uses L.i() with L = precisions
+            const Mat &J = lin.J;
+            Mat alphaPrec = prior.alpha.GetPrecisions();
+            const int Tx = nAlphas; // "use same code for nAlphas == 3 or 4" (:470)
+            for (int i = 1; i <= nPhis; i++)
+                alphaPrec(i - 1, i - 1) += si_ci[i - 1] * op_klj2(k, Sigma, J, ar2_matrix(i, 2, 0));
+            if (Tx > 2)
+            {
+                real x = 0.5 * si_ci[0] * op_klj2(k, Sigma, J, ar2_matrix(1, 1, 1));
+                alphaPrec(2, 0) += x;
+                alphaPrec(0, 2) = alphaPrec(2, 0);
+                x = 0.5 * si_ci[1] * op_klj2(k, Sigma, J, ar2_matrix(2, 1, 1));
+                alphaPrec(Tx - 1, 1) += x;
+                alphaPrec(1, Tx - 1) = alphaPrec(Tx - 1, 1);
+                alphaPrec(2, 2) += si_ci[0] * op_klj2(k, Sigma, J, ar2_matrix(1, 0, 2));
+                alphaPrec(Tx - 1, Tx - 1) += si_ci[1] * op_klj2(k, Sigma, J, ar2_matrix(2, 0, 2));
+            }
+            post.alpha.SetPrecisions(alphaPrec);
+            if (!all_finite(alphaPrec))
+                throw InternalError(FABBER_VOX_NONFINITE_F,
+                    "Ar1cNoiseModel::UpdateAlpha Non-finite values in alpha precisions!");
+            Mat chk = inverse(alphaPrec);
+            real mn = chk(0, 0);
+            for (int i = 1; i < chk.r; i++)
+                mn = std::min(mn, chk(i, i));
+            if (mn < 0)
+                throw InternalError(
+                    FABBER_VOX_AR_NEG_VARIANCE, "Ar1cNoiseModel::UpdateAlpha Negative variance!");
+            Vec tmp = mulv(prior.alpha.GetPrecisions(), prior.alpha.means);
+            for (int i = 1; i <= nPhis; i++)
+                tmp[i - 1] += -0.5 * si_ci[i - 1] * op_klj2(k, Sigma, J, ar2_matrix(i, 1, 0));
+            if (Tx > 2)
+            {
+                tmp[2] += -0.5 * si_ci[0] * op_klj2(k, Sigma, J, ar2_matrix(1, 0, 1));
+                tmp[Tx - 1] += -0.5 * si_ci[1] * op_klj2(k, Sigma, J, ar2_matrix(2, 0, 1));
+            }
+            post.alpha.means = mulv(post.alpha.GetCovariance(), tmp);
+            ar2_update_marginal(post);
+        }
+        // UpdatePhi (noisemodel_ar.cc:530-556)
+        {
+            Vec k = calc_k(theta, lin, data);
+            for (int i = 0; i < nPhis; i++)
+            {
+                real tmp = sym_quad(post.Qm[i], k) + trace(mul(theta.GetCovariance(), sym_JtMJ(lin.J, post.Qm[i])));
+                post.phis[i].b = 1 / (tmp * 0.5 + 1 / prior.phis[i].b);
+                post.phis[i].c = (nTimes - 1) * 0.5 + prior.phis[i].c;
+            }
+        }
+    }
+
+    SymSparse ar2_weighted_marginals(const NoiseParams &noise) const
+    {
+        SymSparse X;
+        for (int i = 0; i < nPhis; i++)
+            sym_axpy(X, noise.phis[i].b * noise.phis[i].c, noise.Qm[i]);
+        return X;
+    }
+
+    void ar2_update_theta(const NoiseParams &noise, MVN &theta, const MVN &thetaPrior,
+        const LinModel &lin, const Vec &data) const
+    {
+        // noisemodel_ar.cc:558-610 (LMalpha is ignored by the AR model)
+        SymSparse X = ar2_weighted_marginals(noise);
+        Mat Ltmp = sym_JtMJ(lin.J, X);
+        for (int i = 0; i < P; i++)
+            for (int j = i + 1; j < P; j++)
+                Ltmp(i, j) = Ltmp(j, i);
+        theta.SetPrecisions(add(thetaPrior.GetPrecisions(), Ltmp));
+        Vec Jml = mulv(lin.J, lin.centre);
+        Vec resid(T);
+        for (int t = 0; t < T; t++)
+            resid[t] = data[t] - lin.offset[t] + Jml[t];
+        Vec Xr = sym_apply(X, resid);
+        Vec mTmp(P);
+        for (int p = 0; p < P; p++)
+        {
+            real s = 0;
+            for (int t = 0; t < T; t++)
+                s += lin.J(t, p) * Xr[t];
+            mTmp[p] = s;
+        }
+        Vec P0m0 = mulv(thetaPrior.GetPrecisions(), thetaPrior.means);
+        Vec rhs(P);
+        for (int i = 0; i < P; i++)
+            rhs[i] = mTmp[i] + P0m0[i];
+        theta.means = mulv(theta.GetCovariance(), rhs);
+    }
+
+    real ar2_free_energy(const NoiseParams &post, const NoiseParams &prior, const MVN &theta,
+        const MVN &thetaPrior, const LinModel &lin, const Vec &data) const
+    {
+        // noisemodel_ar.cc:643-747
+        Vec k = calc_k(theta, lin, data);
+        const Mat &Linv = theta.GetCovariance();
+        SymSparse Qsum = ar2_weighted_marginals(post);
+        const int nTimes = T / nPhis;
+        const int nTheta = P;
+        real expectedLogAlphaDist = +0.5 * log_determinant(post.alpha.GetPrecisions()).logval
+            - 0.5 * nAlphas * (std::log(2 * M_PI) + 1);
+        real expectedLogThetaDist = +0.5 * log_determinant(theta.GetPrecisions()).logval
+            - 0.5 * nTheta * (std::log(2 * M_PI) + 1);
+        real expectedLogPhiDist = 0;
+        real parts[10] = { 0 };
+        for (int i = 0; i < nPhis; i++)
+        {
+            real si = post.phis[i].b, ci = post.phis[i].c;
+            real siPrior = prior.phis[i].b, ciPrior = prior.phis[i].c;
+            expectedLogPhiDist
+                += -gammaln(ci) - ci * std::log(si) - ci + (ci - 1) * (digamma_fsl(ci) + std::log(si));
+            parts[0] += (digamma_fsl(ci) + std::log(si)) * ((nTimes - 1) * 0.5 + ciPrior - 1);
+            parts[9] += -2 * gammaln(ciPrior) - 2 * ciPrior * std::log(siPrior) - si * ci / siPrior;
+        }
+        parts[1] = -std::log(2 * M_PI) * (nTimes - 1 + 0.5 * nAlphas + 0.5 * nTheta);
+        parts[2] = -0.5 * sym_quad(Qsum, k) - 0.5 * trace(mul(sym_JtMJ(lin.J, Qsum), Linv));
+        parts[3] = +0.5 * log_determinant(thetaPrior.GetPrecisions()).logval;
+        Vec dm(P);
+        for (int i = 0; i < P; i++)
+            dm[i] = theta.means[i] - thetaPrior.means[i];
+        Vec Pdm = mulv(thetaPrior.GetPrecisions(), dm);
+        real q = 0;
+        for (int i = 0; i < P; i++)
+            q += dm[i] * Pdm[i];
+        parts[4] = -0.5 * q;
+        parts[5] = -0.5 * trace(mul(Linv, thetaPrior.GetPrecisions()));
+        parts[6] = +0.5 * log_determinant(prior.alpha.GetPrecisions()).logval;
+        Vec da(nAlphas);
+        for (int i = 0; i < nAlphas; i++)
+            da[i] = post.alpha.means[i] - prior.alpha.means[i];
+        Vec Pda = mulv(prior.alpha.GetPrecisions(), da);
+        real qa = 0;
+        for (int i = 0; i < nAlphas; i++)
+            qa += da[i] * Pda[i];
+        parts[7] = -0.5 * qa;
+        parts[8] = -0.5 * trace(mul(post.alpha.GetCovariance(), prior.alpha.GetPrecisions()));
+        real F = -expectedLogAlphaDist - expectedLogThetaDist - expectedLogPhiDist;
+        for (int i = 0; i < 10; i++)
+            F += parts[i];
+        if (!(F - F == 0))
+            throw InternalError(
+                FABBER_VOX_NONFINITE_F, "Ar1cNoiseModel::CalcFreeEnergy Non-finite free energy!");
+        return F;
+    }
+
     // ------------------------------ dispatch ---------------------------------------------
     void hardcoded_initial(NoiseParams &prior, NoiseParams &post) const
     {
@@ -1016,21 +1301,28 @@ struct NoiseModel
         }
         if (ar)
         {
-            Mat p = Mat::identity(2);
-            p(0, 0) = p(1, 1) = prob->ar_alpha_prior_prec;
+            prior.alpha = MVN(nAlphas);
+            post.alpha = MVN(nAlphas);
+            Mat p = Mat::identity(nAlphas);
+            for (int i = 0; i < nAlphas; i++)
+                p(i, i) = prob->ar_alpha_prior_prec;
             prior.alpha.SetPrecisions(p);
             post.alpha.SetPrecisions(p);
         }
     }
     void precalculate(NoiseParams &post, const NoiseParams &prior) const
     {
-        if (ar)
+        if (ar2)
+            ar2_precalculate(post, prior);
+        else if (ar)
             ar_precalculate(post, prior);
     }
     void update_theta(const NoiseParams &noise, MVN &theta, const MVN &thetaPrior,
         const LinModel &lin, const Vec &data, float LMalpha) const
     {
-        if (ar)
+        if (ar2)
+            ar2_update_theta(noise, theta, thetaPrior, lin, data);
+        else if (ar)
             ar_update_theta(noise, theta, thetaPrior, lin, data);
         else
             white_update_theta(noise, theta, thetaPrior, lin, data, LMalpha);
@@ -1038,7 +1330,9 @@ struct NoiseModel
     void update_noise(NoiseParams &post, const NoiseParams &prior, const MVN &theta,
         const LinModel &lin, const Vec &data) const
     {
-        if (ar)
+        if (ar2)
+            ar2_update_noise(post, prior, theta, lin, data);
+        else if (ar)
             ar_update_noise(post, prior, theta, lin, data);
         else
             white_update_noise(post, prior, theta, lin, data);
@@ -1046,6 +1340,8 @@ struct NoiseModel
     real free_energy(const NoiseParams &post, const NoiseParams &prior, const MVN &theta,
         const MVN &thetaPrior, const LinModel &lin, const Vec &data) const
     {
+        if (ar2)
+            return ar2_free_energy(post, prior, theta, thetaPrior, lin, data);
         return ar ? ar_free_energy(post, prior, theta, thetaPrior, lin, data)
                   : white_free_energy(post, prior, theta, thetaPrior, lin, data);
     }
@@ -1441,7 +1737,10 @@ struct Engine
         mc.T = T;
         mc.P = P;
         noise.init(p);
-        NN = noise.ar ? FABBER_CUDA_AR_NOISE_FIELDS : 2 * noise.nPhis;
+        NN = noise.ar2 ? FABBER_CUDA_AR2_NOISE_FIELDS(noise.nAlphas)
+                       : noise.ar ? FABBER_CUDA_AR_NOISE_FIELDS : 2 * noise.nPhis;
+        if (noise.ar2 && (T % 2 != 0 || T < 4))
+            throw std::runtime_error("num-echoes=2 needs an even number of time points");
         needF = p->need_f != 0;
     }
 
@@ -1504,7 +1803,24 @@ struct Engine
         if (buf->init_noise)
         {
             // InputFromMVN is done by the caller of the ABI; here the raw fields are given
-            if (noise.ar)
+            if (noise.ar2)
+            {
+                const int nA = noise.nAlphas;
+                for (int i = 0; i < 2; i++)
+                {
+                    post.phis[i].b = buf->init_noise[(size_t)(2 * i) * N + v];
+                    post.phis[i].c = buf->init_noise[(size_t)(2 * i + 1) * N + v];
+                }
+                Mat pr(nA, nA);
+                int f = 4;
+                for (int i = 0; i < nA; i++)
+                    post.alpha.means[i] = buf->init_noise[(size_t)(f++) * N + v];
+                for (int r = 0; r < nA; r++)
+                    for (int c = 0; c <= r; c++)
+                        pr(r, c) = pr(c, r) = buf->init_noise[(size_t)(f++) * N + v];
+                post.alpha.SetPrecisions(pr);
+            }
+            else if (noise.ar)
             {
                 post.phis[0].b = buf->init_noise[(size_t)0 * N + v];
                 post.phis[0].c = buf->init_noise[(size_t)1 * N + v];
@@ -1543,7 +1859,23 @@ struct Engine
         for (int r = 0; r < P; r++)
             for (int c = 0; c <= r; c++, idx++)
                 buf->cov[(size_t)idx * N + v] = cov(r, c);
-        if (noise.ar)
+        if (noise.ar2)
+        {
+            const int nA = noise.nAlphas;
+            for (int i = 0; i < 2; i++)
+            {
+                buf->noise[(size_t)(2 * i) * N + v] = np.phis[i].b;
+                buf->noise[(size_t)(2 * i + 1) * N + v] = np.phis[i].c;
+            }
+            int f = 4;
+            for (int i = 0; i < nA; i++)
+                buf->noise[(size_t)(f++) * N + v] = np.alpha.means[i];
+            const Mat &pr = np.alpha.GetPrecisions();
+            for (int r = 0; r < nA; r++)
+                for (int c = 0; c <= r; c++)
+                    buf->noise[(size_t)(f++) * N + v] = pr(r, c);
+        }
+        else if (noise.ar)
         {
             buf->noise[(size_t)0 * N + v] = np.phis[0].b;
             buf->noise[(size_t)1 * N + v] = np.phis[0].c;
