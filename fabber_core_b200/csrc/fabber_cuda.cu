@@ -205,7 +205,7 @@ __global__ void renumber_neighbours_kernel(const int *nn, const int *order, cons
  * standard deviations, the packed finalMVN rows, F and its history - all float32 (memory-bound map). */
 struct SaveArgs
 {
-    int N, P, n_noise, ar, n_phis, f_len;
+    int N, P, n_noise, ar, n_phis, n_alphas, f_len;
     char transform[FABBER_CUDA_MAX_PARAMS];
     const double *mean, *cov, *noise, *free_energy, *f_history;
     const int *iterations;
@@ -250,14 +250,61 @@ __global__ void __launch_bounds__(256) save_results_kernel(const __grid_constant
             a.out.var[i * N + v] = (float)var;
     }
     /* noise block of the result MVN (WhiteParams / Ar1cParams::OutputAsMVN) */
-    double nmean[4], ncov[4][4];
-    for (int i = 0; i < 4; i++)
+    double nmean[6], ncov[6][6];
+    for (int i = 0; i < 6; i++)
     {
         nmean[i] = 0.0;
-        for (int j = 0; j < 4; j++)
+        for (int j = 0; j < 6; j++)
             ncov[i][j] = 0.0;
     }
-    if (a.ar)
+    if (a.ar && a.n_phis == 2)
+    {
+        /* two echoes: the alphas (means, covariance = inverse of the packed precisions), then the two phis */
+        const int nA = a.n_alphas;
+        double w[4][8];
+        for (int r = 0; r < nA; r++)
+        {
+            nmean[r] = a.noise[(size_t)(4 + r) * N + v];
+            for (int c = 0; c < nA; c++)
+            {
+                w[r][c] = a.noise[(size_t)(4 + nA + save_tri(r, c)) * N + v];
+                w[r][nA + c] = r == c ? 1.0 : 0.0;
+            }
+        }
+        for (int k = 0; k < nA; k++) /* Gauss-Jordan with partial pivoting on [prec | I] */
+        {
+            int piv = k;
+            for (int r = k + 1; r < nA; r++)
+                if (fabs(w[r][k]) > fabs(w[piv][k]))
+                    piv = r;
+            for (int c = 0; c < 2 * nA; c++)
+            {
+                const double t = w[k][c];
+                w[k][c] = w[piv][c];
+                w[piv][c] = t;
+            }
+            const double inv = 1.0 / w[k][k];
+            for (int c = 0; c < 2 * nA; c++)
+                w[k][c] *= inv;
+            for (int r = 0; r < nA; r++)
+                if (r != k)
+                {
+                    const double f = w[r][k];
+                    for (int c = 0; c < 2 * nA; c++)
+                        w[r][c] -= f * w[k][c];
+                }
+        }
+        for (int r = 0; r < nA; r++)
+            for (int c = 0; c < nA; c++)
+                ncov[r][c] = w[r][nA + c];
+        for (int i = 0; i < 2; i++)
+        {
+            const double b = a.noise[(size_t)(2 * i) * N + v], c = a.noise[(size_t)(2 * i + 1) * N + v];
+            nmean[nA + i] = b * c;
+            ncov[nA + i][nA + i] = b * b * c;
+        }
+    }
+    else if (a.ar)
     {
         const double b = a.noise[0 * N + v], c = a.noise[1 * N + v];
         const double p11 = a.noise[4 * N + v], p21 = a.noise[5 * N + v], p22 = a.noise[6 * N + v];
@@ -433,9 +480,25 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
 
     /* noise */
     const bool ar = prob->noise_type == FABBER_NOISE_AR1;
-    a.n_phis = ar ? 1 : prob->n_phis;
+    a.n_phis = ar ? (prob->n_phis == 0 ? 1 : prob->n_phis) : prob->n_phis;
     if (a.n_phis < 1 || a.n_phis > FABBER_CUDA_MAX_PHIS)
         return fail(FABBER_CUDA_ERR_INVALID, "n_phis out of range");
+    a.ar_n_alphas = 2;
+    if (ar)
+    {
+        /* noisemodel_ar.cc:318-349 */
+        if (a.n_phis > 2)
+            return fail(FABBER_CUDA_ERR_INVALID, "AR noise model: num-echoes must be 1 or 2");
+        if (prob->ar_cross_terms < FABBER_AR_CROSS_NONE || prob->ar_cross_terms > FABBER_AR_CROSS_DUAL)
+            return fail(FABBER_CUDA_ERR_INVALID, "AR noise model: unknown ar1-cross-terms");
+        if (a.n_phis == 1 && prob->ar_cross_terms != FABBER_AR_CROSS_NONE)
+            return fail(FABBER_CUDA_ERR_INVALID, "AR noise model: ar1-cross-terms needs num-echoes=2");
+        /* two echoes interleave TE1 TE2 ..; an odd series gives the reference alpha matrices of the wrong size
+         * (a NEWMAT dimension exception), and a single pair has no lag at all */
+        if (a.n_phis == 2 && (T % 2 != 0 || T < 4))
+            return fail(FABBER_CUDA_ERR_INVALID, "AR noise model: num-echoes=2 needs an even number (>= 4) of time points");
+        a.ar_n_alphas = 2 + prob->ar_cross_terms;
+    }
     if (ar && prob->time_masked)
         for (int t = 0; t < T; t++)
             if (prob->time_masked[t]) /* noisemodel_ar.cc: masked time points not supported */
@@ -448,7 +511,7 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
     for (int t = 0; t < T; t++)
     {
         int ph = (!ar && prob->phi_pattern) ? prob->phi_pattern[t] : 0;
-        if (ph >= a.n_phis)
+        if (!ar && ph >= a.n_phis)
             return fail(FABBER_CUDA_ERR_INVALID, "phi_pattern entry >= n_phis");
         if (prob->time_masked && prob->time_masked[t])
         {
@@ -462,7 +525,7 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
             a.n_per_phi[ph]++;
         }
     }
-    if (a.n_phis > 1)
+    if (!ar && a.n_phis > 1)
         general = true;
     a.n_unmasked = T - n_masked;
     for (int i = 0; i < FABBER_CUDA_MAX_PHIS; i++)
@@ -694,7 +757,7 @@ int fabber_cuda_vb_voxelwise_range(const fabber_cuda_vb_problem *prob, const fab
     }
     VbLaunchFn fn = nullptr;
     if (prob->noise_type == FABBER_NOISE_AR1)
-        fn = ml->ar1;
+        fn = a.n_phis == 2 ? ml->ar2 : ml->ar1;
     else if (prob->noise_type == FABBER_NOISE_WHITE)
     {
         const bool snap = prob->conv_type == FABBER_CONV_TRIALMODE || prob->conv_type == FABBER_CONV_FREDUCE;
@@ -1750,9 +1813,13 @@ int fabber_cuda_vb_save_results(const fabber_cuda_vb_problem *prob, const fabber
     a.N = N;
     a.P = P;
     a.ar = prob->noise_type == FABBER_NOISE_AR1;
-    a.n_phis = a.ar ? 1 : prob->n_phis;
-    a.n_noise = a.ar ? 3 : prob->n_phis;
-    if (a.n_noise < 1 || a.n_noise > 4)
+    a.n_phis = a.ar ? (prob->n_phis == 2 ? 2 : 1) : prob->n_phis;
+    a.n_alphas = 2 + (a.ar && a.n_phis == 2 ? prob->ar_cross_terms : 0);
+    if (a.n_alphas < 2 || a.n_alphas > 4)
+        return fail(FABBER_CUDA_ERR_INVALID, "ar_cross_terms out of range");
+    /* size of the noise block of the result MVN: the phis, or (alphas, phis) - Ar1cParams::OutputAsMVN */
+    a.n_noise = a.ar ? a.n_alphas + a.n_phis : prob->n_phis;
+    if (a.n_noise < 1 || a.n_noise > 6 || (!a.ar && a.n_noise > FABBER_CUDA_MAX_PHIS))
         return fail(FABBER_CUDA_ERR_INVALID, "n_phis out of range");
     a.f_len = buf->f_history ? prob->f_history_len : 0;
     for (int i = 0; i < P; i++)

@@ -29,6 +29,7 @@ struct ModelLaunchers
      * have to wait for kernels that are running - with slabs that spin on each other's flags a first launch in
      * the middle of an iteration would deadlock until the spin gives up. Appended: older plug-ins leave it NULL. */
     cudaError_t (*sp_preload)(void);
+    VbLaunchFn ar2; /* AR(1) noise on two interleaved echoes, with or without cross terms (appended, may be NULL) */
 };
 
 /* number of blocks the aK partial reduction is launched with (size of SpArgs::ak_partial) */

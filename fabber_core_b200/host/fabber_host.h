@@ -481,7 +481,7 @@ private:
     int m_num_params = 0, m_noise_params = 0;
     bool m_ar = false, m_saveF = false, m_saveFsHistory = false, m_printF = false, m_needF = false;
     bool m_halt_bad_voxel = true;
-    int m_nphis = 1;
+    int m_nphis = 1, m_nalphas = 2;
     /* results stay on the device, structure of arrays over voxels (the layout of include/fabber_cuda.h);
      * SaveResults turns them into float32 output maps there and downloads only what was asked for */
     size_t m_nvoxels = 0;

@@ -262,13 +262,14 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
     noise->Describe(prob, T, m_pattern);
     if (m_ar)
     {
-        /* noisemodel_ar.cc:305-349: one echo, no cross terms is what the device kernels implement */
+        /* noisemodel_ar.cc:305-349 */
         for (const char *key : { "noise-initial-prior", "noise-initial-posterior" })
             if (rundata.GetStringDefault(key, "modeldefault") != "modeldefault")
                 throw InvalidOptionValue(key, rundata.GetString(key),
                     "the AR(1) device kernel starts alpha at N(0, 1e4 I) only: not supported with noise=ar");
-        m_noise_params = 3; /* alpha (2) + phi (1): Ar1cParams::OutputAsMVN, noisemodel_ar.cc:287-300 */
-        m_nphis = 1;
+        m_nphis = prob.n_phis; /* num-echoes */
+        m_nalphas = 2 + prob.ar_cross_terms;
+        m_noise_params = m_nalphas + m_nphis; /* the alphas, then the phis: Ar1cParams::OutputAsMVN, noisemodel_ar.cc:287-300 */
     }
     else
     {
@@ -317,7 +318,7 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
     prob.nx = rundata.Extent()[0];
     prob.ny = rundata.Extent()[1];
     prob.nz = rundata.Extent()[2];
-    m_nn = m_ar ? FABBER_CUDA_AR_NOISE_FIELDS : 2 * m_nphis;
+    m_nn = !m_ar ? 2 * m_nphis : m_nphis == 2 ? FABBER_CUDA_AR2_NOISE_FIELDS(m_nalphas) : FABBER_CUDA_AR_NOISE_FIELDS;
     const int NN = m_nn;
     m_spatial = spatial;
     if (N == 0)
@@ -389,7 +390,50 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
                 for (int r = 0; r < P; r++)
                     for (int c = 0; c <= r; c++)
                         init_cov[(size_t)tri(r, c) * N + v] = mvn.at(tri(r, c), v);
-                if (m_ar)
+                if (m_ar && m_nphis == 2)
+                {
+                    /* MVN order: the alphas, the two phis. Fields: b1 c1 b2 c2, alpha means, packed alpha precisions
+                     * (= inverse of the MVN's alpha covariance block) */
+                    const int nA = m_nalphas, ia = P, ip = P + nA;
+                    double w[4][8];
+                    for (int r = 0; r < nA; r++)
+                        for (int c = 0; c < nA; c++)
+                        {
+                            w[r][c] = mvn.at(tri(ia + r, ia + c), v);
+                            w[r][nA + c] = r == c ? 1.0 : 0.0;
+                        }
+                    for (int k = 0; k < nA; k++) /* Gauss-Jordan, partial pivoting */
+                    {
+                        int piv = k;
+                        for (int r = k + 1; r < nA; r++)
+                            if (std::fabs(w[r][k]) > std::fabs(w[piv][k]))
+                                piv = r;
+                        for (int c = 0; c < 2 * nA; c++)
+                            std::swap(w[k][c], w[piv][c]);
+                        const double inv = 1.0 / w[k][k];
+                        for (int c = 0; c < 2 * nA; c++)
+                            w[k][c] *= inv;
+                        for (int r = 0; r < nA; r++)
+                            if (r != k)
+                            {
+                                const double f = w[r][k];
+                                for (int c = 0; c < 2 * nA; c++)
+                                    w[r][c] -= f * w[k][c];
+                            }
+                    }
+                    for (int i = 0; i < 2; i++)
+                    {
+                        const double mean = mvn.at(n_cov_all + ip + i, v), var = mvn.at(tri(ip + i, ip + i), v);
+                        init_noise[(size_t)(2 * i) * N + v] = var / mean;
+                        init_noise[(size_t)(2 * i + 1) * N + v] = mean * mean / var;
+                    }
+                    for (int i = 0; i < nA; i++)
+                        init_noise[(size_t)(4 + i) * N + v] = mvn.at(n_cov_all + ia + i, v);
+                    for (int r = 0; r < nA; r++)
+                        for (int c = 0; c <= r; c++)
+                            init_noise[(size_t)(4 + nA + tri(r, c)) * N + v] = w[r][nA + c];
+                }
+                else if (m_ar)
                 {
                     /* MVN order: alpha (2), phi (1). InputFromMVN: Gamma from mean/variance (dist_gamma.cc:29) */
                     const int ia = P, ip = P + 2;
@@ -729,9 +773,10 @@ void Vb::SaveResults(FabberRunData &rundata)
     if (rundata.GetBool("save-var"))
         want(&fabber_cuda_vb_outputs::var, P, per_param("var_"), 1);
     /* Quirk kept: Ar1cNoiseModel::NumParams() returns nPhis (noisemodel_ar.cc:362-365) although its MVN
-     * block is (alpha1, alpha2, phi), so the reference's noise_means / noise_stdevs hold ONE volume for AR
-     * noise - the first element of that block, i.e. alpha1 (inference_vb.cc:982-988). */
-    const int noise_rows = m_ar ? 1 : m_noise_params;
+     * block is (the alphas, the phis), so the reference's noise_means / noise_stdevs hold num-echoes volumes for
+     * AR noise - the first elements of that block, i.e. alpha1 (and alpha2 with two echoes)
+     * (inference_vb.cc:982-988). */
+    const int noise_rows = m_ar ? m_nphis : m_noise_params;
     if (rundata.GetBool("save-noise-mean") && m_noise_params > 0)
         want(&fabber_cuda_vb_outputs::noise_mean, m_noise_params, std::vector<std::string>(1, "noise_means"), noise_rows);
     if (rundata.GetBool("save-noise-std") && m_noise_params > 0)

@@ -483,8 +483,6 @@ void Ar1cNoiseModel::Initialize(FabberRunData &args)
         throw InvalidOptionValue("num-echoes", stringify(m_nphis), "Must be 1 or 2");
     if (!m_masked_tpoints.empty())
         throw InvalidOptionValue("mt1", "", "Masked time points are not supported for the AR noise model");
-    if (m_nphis != 1) /* dual echo: refused until its kernel exists, see DESIGN.md section 9 */
-        throw InvalidOptionValue("num-echoes", stringify(m_nphis), "only 1 echo has a device kernel");
 }
 int Ar1cNoiseModel::NumAlphas() const
 {
@@ -526,14 +524,23 @@ void Ar1cNoiseModel::HardcodedInitialDists(NoiseParams &prior, NoiseParams &post
 void Ar1cNoiseModel::Describe(fabber_cuda_vb_problem &prob, int n_times, std::vector<unsigned char> &pattern) const
 {
     prob.noise_type = FABBER_NOISE_AR1;
-    prob.n_phis = 1;
+    prob.n_phis = m_nphis;
+    prob.ar_cross_terms = NumAlphas() - 2; /* FABBER_AR_CROSS_NONE / SAME / DUAL */
+    /* two echoes interleave (noisemodel_ar.cc:126-129): with an odd series the reference's alpha matrices and its
+     * data vector disagree in size and NEWMAT throws on the first product */
+    if (m_nphis == 2 && (n_times % 2 != 0 || n_times < 4))
+        throw InvalidOptionValue("num-echoes", stringify(m_nphis),
+            "the data must hold an even number (at least 4) of time points, the two echoes interleaved");
     pattern.assign(n_times, 0);
     NoiseParams prior, post;
     HardcodedInitialDists(prior, post);
-    prob.noise_prior_b[0] = prior.phis[0].b;
-    prob.noise_prior_c[0] = prior.phis[0].c;
-    prob.noise_post_b[0] = post.phis[0].b;
-    prob.noise_post_c[0] = post.phis[0].c;
+    for (int i = 0; i < m_nphis; i++)
+    {
+        prob.noise_prior_b[i] = prior.phis[i].b;
+        prob.noise_prior_c[i] = prior.phis[i].c;
+        prob.noise_post_b[i] = post.phis[i].b;
+        prob.noise_post_c[i] = post.phis[i].c;
+    }
     prob.ar_alpha_prior_prec = prior.alpha.GetPrecisions(0, 0);
 }
 

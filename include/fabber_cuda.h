@@ -323,7 +323,7 @@ int fabber_cuda_model_fit(const fabber_cuda_vb_problem *prob, const double *mean
 typedef struct fabber_cuda_vb_outputs
 {
     float *mean, *std, *zstat, *var; /* [P][N], model space (FwdModel::ToModel, fwdmodel.cc:326-337) */
-    float *noise_mean, *noise_std;   /* [Nn][N]; Nn = n_phis (white) or 3 (AR1: alpha1, alpha2, phi) */
+    float *noise_mean, *noise_std;   /* [Nn][N]; Nn = n_phis (white) or n_alphas + num-echoes (AR1: the alphas, then the phis) */
     float *final_mvn;                /* [(P+Nn)(P+Nn+1)/2 + (P+Nn) + 1][N] packed covariance, means, 1 */
     float *free_energy;              /* [N] */
     float *f_history;                /* [f_history_rows][N]: rows >= iterations repeat the final F */

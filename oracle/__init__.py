@@ -42,6 +42,32 @@ def _ptr(a):
     return a.ctypes.data if a is not None else None
 
 
+def ar2_noise_scale(noise, n_alphas):
+    """Per-field scale for comparing the two-echo AR noise block (b1 c1 b2 c2, alpha means, packed alpha
+    precisions): an alpha that is truly ~0 (no cross coupling in the data) or an off-diagonal precision that
+    cancels has no meaningful RELATIVE error; the posterior std of that alpha, and sqrt(P_rr P_cc), are the
+    natural units. Zero rows mean plain relative error (the Gammas)."""
+    nA = n_alphas
+    scale = np.zeros_like(noise)
+    tri = lambda i, j: i * (i + 1) // 2 + j
+    n = noise.shape[1]
+    prec = np.zeros((n, nA, nA))
+    for r in range(nA):
+        for c in range(r + 1):
+            prec[:, r, c] = prec[:, c, r] = noise[4 + nA + tri(r, c)]
+    with np.errstate(all="ignore"):
+        try:
+            cov = np.linalg.inv(prec)
+        except np.linalg.LinAlgError:
+            cov = np.full_like(prec, np.nan)
+    for i in range(nA):
+        scale[4 + i] = np.sqrt(np.abs(cov[:, i, i]))
+    for r in range(nA):
+        for c in range(r + 1):
+            scale[4 + nA + tri(r, c)] = np.sqrt(np.abs(prec[:, r, r] * prec[:, c, c]))
+    return np.nan_to_num(scale, nan=0.0, posinf=0.0)
+
+
 def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=None, init_cov=None,
         init_noise=None, variant="", lock_centre=None):
     """Run the oracle. data: float32 [T][N]. Returns dict of numpy arrays (see fabber_cuda.h layouts)."""
@@ -94,6 +120,8 @@ def run(spec, data, spatial=False, image_priors=None, coords=None, init_mean=Non
     rc = fn(C.byref(prob), C.byref(buf))
     out["rc"] = rc
     out["n_times"] = T
+    if spec.prob.noise_type == abi.NOISE_AR1 and spec.prob.n_phis == 2:
+        out["noise_scale"] = ar2_noise_scale(out["noise"], spec.n_alphas)
     return out
 
 

@@ -84,7 +84,8 @@ def field_errors(x, ref, P, sel, check_f=True):
             worst = max(worst, float(np.max(rel_err(x["cov"][tri(i, j)], ref["cov"][tri(i, j)], scale=sc)[sel],
                                             initial=0.0)))
     errs["cov_offdiag"] = worst
-    errs["noise"] = float(np.max(rel_err(x["noise"], ref["noise"])[:, sel], initial=0.0))
+    # two-echo AR: the alphas and their precisions are compared in their natural units (oracle.ar2_noise_scale)
+    errs["noise"] = float(np.max(rel_err(x["noise"], ref["noise"], scale=ref.get("noise_scale"))[:, sel], initial=0.0))
     if check_f:
         # |dF| / max(|F|, n/2 ln 2 pi): F is a sum that contains the constant -n/2 ln(2 pi) (noisemodel_white.cc:
         # 420-423; 88 at T = 96) and regularly cancels to ~0; the rounding error of a sum is relative to its

@@ -169,6 +169,31 @@ def test_ar_noise_and_error_paths():
         assert "noise" in str(e.value)
 
 
+def test_two_echo_ar_noise_restart_and_odd_series(tmp_path):
+    """num-echoes=2 through the C API: a run continued from its own finalMVN (Ar1cParams::InputFromMVN order: the
+    alphas, then the phis) with zero further iterations reproduces that MVN, and an odd series is refused."""
+    nx, ny, nz = 5, 4, 2
+    y = synth.dual_echo_volume(nx * ny * nz, 50, seed=45).numpy()
+    basis = str(tmp_path / "de.mat")
+    np.savetxt(basis, synth.dual_echo_design(50), fmt="%.17g")
+    opts = {"model": "linear", "basis": basis, "noise": "ar", "num-echoes": 2, "ar1-cross-terms": "dual", "method": "vb",
+            "save-mvn": True, "save-noise-mean": True, "save-noise-std": True, "save-mean": True}
+    f = fab.Fabber()
+    first = f.run_with_data(opts, {"data": volume(y, (nx, ny, nz))})
+    mvn = first.data["finalMVN"]
+    assert mvn.shape[-1] == 9 * 10 // 2 + 9 + 1 and flat(first.data["noise_means"]).shape[0] == 2
+    again = dict(opts)
+    again.update({"continue-from-mvn": "mvn", "max-iterations": 1})
+    second = f.run_with_data(again, {"data": volume(y, (nx, ny, nz)), "mvn": mvn})
+    # one more iteration from a converged state moves nothing visibly (float32 MVN in between)
+    a, b = flat(second.data["finalMVN"]), flat(mvn)
+    scale = np.maximum(np.abs(b), np.max(np.abs(b), axis=1, keepdims=True) * 1e-3)
+    assert np.max(np.abs(a - b) / np.maximum(scale, 1e-30)) < 5e-3
+    with pytest.raises(fab.FabberException) as e:
+        f.run_with_data(opts, {"data": volume(y[:-1], (nx, ny, nz))})
+    assert "num-echoes" in str(e.value)
+
+
 def test_bad_voxel_policy_through_capi():
     nx, ny, nz = 4, 4, 2
     y = synth.biexp_volume(nx * ny * nz, 96, 0.02, 0.02, seed=44).numpy()

@@ -78,6 +78,23 @@ def test_dropin_linear_ar1(tmp_path):
     assert_same(ours, ref)
 
 
+@pytest.mark.parametrize("cross", ["none", "same", "dual"])
+def test_dropin_linear_ar1_two_echoes(cross, tmp_path):
+    """num-echoes=2: every output volume, including noise_means / noise_stdevs (TWO volumes: alpha1 and alpha2,
+    because Ar1cNoiseModel::NumParams() returns nPhis) and the finalMVN with its (alphas, phi1, phi2) noise block"""
+    nx, ny, nz = 5, 4, 3
+    y = synth.dual_echo_volume(nx * ny * nz, 60, seed=76).numpy()
+    basis = str(tmp_path / "de.mat")
+    np.savetxt(basis, synth.dual_echo_design(60), fmt="%.17g")
+    ours, ref = both({"model": "linear", "basis": basis, "noise": "ar", "num-echoes": 2, "ar1-cross-terms": cross,
+                      "method": "vb", "convergence": "pointzeroone"}, {"data": refbuild.volume(y, (nx, ny, nz))})
+    assert_same(ours, ref)
+    nA = {"none": 2, "same": 3, "dual": 4}[cross]
+    n_all = 3 + nA + 2
+    assert ours.data["noise_means"].shape[-1] == 2
+    assert ours.data["finalMVN"].shape[-1] == n_all * (n_all + 1) // 2 + n_all + 1
+
+
 @pytest.mark.parametrize("types", ["M+", "P+", "MA"])
 def test_dropin_spatialvb(types):
     nx, ny, nz = 6, 5, 4

@@ -22,7 +22,8 @@ def run(extra):
     ({"noise-pattern": "1?2"}, ("noise-pattern", "Invalid character in pattern")),
     ({"mt1": "13"}, ("mt", "beyond the end of the data")),                      # 12 time points
     ({"noise": "ar", "mt1": "2"}, ("AR noise model does not support masked time points",)),
-    ({"noise": "ar", "num-echoes": "2"}, ("num-echoes", "only 1 echo")),
+    ({"noise": "ar", "num-echoes": "3"}, ("num-echoes", "Must be 1 or 2")),
+    ({"noise": "ar", "num-echoes": "2", "ar1-cross-terms": "both"}, ("ar1-cross-terms", "Must be dual, same or none")),
     ({"noise": "ar", "ar1-cross-terms": "dual"}, ("ar1-cross-terms", "ar1-cross-terms=none with num-echoes=1")),
     ({"noise": "pink"}, ("noise", "Unrecognized noise model")),
     ({"prior-noise-stddev": "-2"}, ("prior-noise-stddev", "Must be > 0")),
