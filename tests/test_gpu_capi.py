@@ -171,7 +171,8 @@ def test_ar_noise_and_error_paths():
 
 def test_two_echo_ar_noise_restart_and_odd_series(tmp_path):
     """num-echoes=2 through the C API: a run continued from its own finalMVN (Ar1cParams::InputFromMVN order: the
-    alphas, then the phis) with zero further iterations reproduces that MVN, and an odd series is refused."""
+    alphas, then the phis) for one more iteration lands where a straight run of one more iteration lands (up to
+    the float32 MVN in between), and an odd series is refused."""
     nx, ny, nz = 5, 4, 2
     y = synth.dual_echo_volume(nx * ny * nz, 50, seed=45).numpy()
     basis = str(tmp_path / "de.mat")
@@ -185,8 +186,11 @@ def test_two_echo_ar_noise_restart_and_odd_series(tmp_path):
     again = dict(opts)
     again.update({"continue-from-mvn": "mvn", "max-iterations": 1})
     second = f.run_with_data(again, {"data": volume(y, (nx, ny, nz)), "mvn": mvn})
-    # one more iteration from a converged state moves nothing visibly (float32 MVN in between)
-    a, b = flat(second.data["finalMVN"]), flat(mvn)
+    straight = dict(opts)
+    straight["max-iterations"] = 11
+    third = f.run_with_data(straight, {"data": volume(y, (nx, ny, nz))})
+    a, b = flat(second.data["finalMVN"]), flat(third.data["finalMVN"])
+    assert np.max(np.abs(flat(mvn) - b)) > 0   # the extra iteration did move something
     scale = np.maximum(np.abs(b), np.max(np.abs(b), axis=1, keepdims=True) * 1e-3)
     assert np.max(np.abs(a - b) / np.maximum(scale, 1e-30)) < 5e-3
     with pytest.raises(fab.FabberException) as e:
