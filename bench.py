@@ -50,8 +50,8 @@ WORKLOADS = {
                          param_overrides={"r2": {"mean": 6.0}}), P=4, kind="exp", NE=2,
                capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "vb", "convergence": "lm",
                      "max-iterations": 10, "PSP_byname1": "r2", "PSP_byname1_mean": 6.0},
-               ncu=dict(fp64_active=0.729, traffic=6.506453e9 + 2.406503e9,
-                        source="profiles/r1b_ncu_full_c3_exp2.txt")),
+               ncu=dict(fp64_active=0.750, traffic=6.487053e9 + 2.401360e9,
+                        source="profiles/r2i_ncu_full_c3_exp2.txt")),
     # BASELINE.json configs[3]: linear model (synthetic 200 x 4 design), AR(1) noise, synthetic 256^3 x 200
     # (the reference has no AR(2): Ar1cNoiseModel only, setup.cc:39)
     "c4": dict(name="C4 linear(200x4 design) VB AR(1) noise (num-echoes 1, cross-terms none), synthetic "

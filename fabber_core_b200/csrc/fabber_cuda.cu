@@ -89,6 +89,27 @@ const ModelLaunchers *find_model(int model_id, int n_params)
     return nullptr;
 }
 
+/* the debug build's index-check counters (vb_device.cuh FAB_CHECK): [0] failures, [1] largest site code. The helper
+ * kernels of this file count into them directly, the model kernels through VbArgs::check. */
+__device__ unsigned long long g_fab_check[2];
+#ifdef FAB_BOUNDS_CHECK
+#define FAB_CHECK_G(cond, code)                                                                                      \
+    do                                                                                                               \
+    {                                                                                                                \
+        if (!(cond))                                                                                                 \
+        {                                                                                                            \
+            atomicAdd(&g_fab_check[0], 1ull);                                                                        \
+            atomicMax(&g_fab_check[1], (unsigned long long)(code));                                                  \
+        }                                                                                                            \
+    } while (0)
+#else
+#define FAB_CHECK_G(cond, code)                                                                                      \
+    do                                                                                                               \
+    {                                                                                                                \
+    } while (0)
+#endif
+
+
 /* ------------------------------------------------------------------------------------------------
  * small utility kernels
  * ---------------------------------------------------------------------------------------------- */
@@ -137,6 +158,7 @@ __global__ void permute_rows_kernel(const T *__restrict__ in, T *__restrict__ ou
     if (idx >= (size_t)rows * N)
         return;
     const size_t r = idx / N, i = idx - r * N;
+    FAB_CHECK_G(perm[i] >= 0 && perm[i] < N, 201);
     if (GATHER)
         out[idx] = in[r * N + (size_t)perm[i]];
     else
@@ -161,7 +183,10 @@ __global__ void rank_kernel(const int *order, int N, int *rank)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < N)
+    {
+        FAB_CHECK_G(order[i] >= 0 && order[i] < N, 202);
         rank[order[i]] = i;
+    }
 }
 /* z-slab mode: ghost voxels carry FABBER_VOX_GHOST so every update kernel skips them */
 __global__ void mark_ghosts_kernel(const unsigned char *ghost, const int *order, int N, int *status_p)
@@ -177,6 +202,7 @@ __global__ void halo_kernel(double *mean_p, const int *idx, const int *rank, int
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n)
         return;
+    FAB_CHECK_G(idx[i] >= 0 && idx[i] < N && rank[idx[i]] >= 0 && rank[idx[i]] < N, 203);
     const size_t pos = (size_t)rank[idx[i]];
     for (int k = 0; k < P; k++)
     {
@@ -197,6 +223,7 @@ __global__ void renumber_neighbours_kernel(const int *nn, const int *order, cons
     for (int j = 0; j < 6; j++)
     {
         const int n = nn[(size_t)j * N + v];
+        FAB_CHECK_G(v >= 0 && v < N && n >= -1 && n < N && n != v, 204);
         nnp[(size_t)j * N + i] = n >= 0 ? rank[n] : -1;
     }
 }
@@ -537,6 +564,14 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
     }
     a.locked_noise_stdev = prob->locked_noise_stdev;
     a.ar_alpha_prior_prec = prob->ar_alpha_prior_prec;
+    a.check = nullptr;
+#ifdef FAB_BOUNDS_CHECK
+    {
+        void *sym = nullptr;
+        if (cudaGetSymbolAddress(&sym, g_fab_check) == cudaSuccess)
+            a.check = (unsigned long long *)sym;
+    }
+#endif
     a.conv_type = prob->conv_type;
     a.max_iterations = prob->max_iterations;
     a.max_trials = prob->max_trials;
@@ -611,6 +646,52 @@ struct Scratch
 using namespace fab;
 
 extern "C" {
+
+/* debug build (make checked): failures counted by the kernels' index checks since the last call, summed over
+ * the devices, and the largest failing site code; the counters are reset. Returns 1 when the checks are compiled
+ * in, 0 when they are not (out is zeroed), < 0 on a CUDA error. */
+int fabber_cuda_check_report(unsigned long long *out)
+{
+    if (!out)
+        return fail(FABBER_CUDA_ERR_INVALID, "null argument");
+    out[0] = out[1] = 0;
+#ifdef FAB_BOUNDS_CHECK
+    int n = 0, cur = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || cudaGetDevice(&cur) != cudaSuccess)
+        return fail(FABBER_CUDA_ERR_CUDA, "no device");
+    for (int d = 0; d < n; d++)
+    {
+        unsigned long long w[2] = { 0, 0 }, zero[2] = { 0, 0 };
+        cudaError_t e = cudaSetDevice(d);
+        if (e == cudaSuccess)
+            e = cudaDeviceSynchronize();
+        if (e == cudaSuccess)
+            e = cudaMemcpyFromSymbol(w, g_fab_check, sizeof(w));
+        if (e == cudaSuccess)
+            e = cudaMemcpyToSymbol(g_fab_check, zero, sizeof(zero));
+        if (e != cudaSuccess)
+        {
+            cudaSetDevice(cur);
+            return cuda_fail(e, "check_report");
+        }
+        out[0] += w[0];
+        out[1] = w[1] > out[1] ? w[1] : out[1];
+    }
+    cudaSetDevice(cur);
+    return 1;
+#else
+    return 0;
+#endif
+}
+
+/* proves the check machinery is live: one deliberate failure with site code 999 (debug build; else a no-op) */
+__global__ void check_selftest_kernel() { FAB_CHECK_G(threadIdx.x != 0, 999); }
+int fabber_cuda_check_selftest(void)
+{
+    check_selftest_kernel<<<1, 32>>>();
+    cudaError_t e = cudaDeviceSynchronize();
+    return e == cudaSuccess ? FABBER_CUDA_OK : cuda_fail(e, "check_selftest");
+}
 
 int fabber_cuda_device_count(void)
 {
@@ -881,20 +962,23 @@ __global__ void slab_wait_kernel(const unsigned long long *flags, int wait_fwd, 
 /* links between two neighbouring slabs, in plane-major positions: for every voxel of the caller's list of the
  * LOWER slab that is also in the UPPER slab's list (global ids [g0, g1)), lower position <-> upper position */
 __global__ void slab_up_pos_kernel(const int *rank_lo, int v0_lo, const int *rank_hi, int v0_hi, int g0, int g1,
-    int own1_lo /* global */, int *up_pos)
+    int own1_lo /* global */, int *up_pos, int n_lo, int n_hi)
 {
     const int g = g0 + blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= g1 || g >= own1_lo)
         return; /* only the lower slab's OWN voxels forward upwards */
+    FAB_CHECK_G(g - v0_lo >= 0 && g - v0_lo < n_lo && g - v0_hi >= 0 && g - v0_hi < n_hi, 205);
+    FAB_CHECK_G(rank_lo[g - v0_lo] >= 0 && rank_lo[g - v0_lo] < n_lo && rank_hi[g - v0_hi] >= 0 && rank_hi[g - v0_hi] < n_hi, 206);
     up_pos[rank_lo[g - v0_lo]] = rank_hi[g - v0_hi];
 }
 __global__ void slab_dn_list_kernel(const int *rank_hi, int v0_hi, const int *rank_lo, int v0_lo, int g0, int n,
-    int *dn_src, int *dn_dst)
+    int *dn_src, int *dn_dst, int n_hi, int n_lo)
 {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n)
         return;
     const int g = g0 + j; /* own voxels of the upper slab that the lower slab holds as its upper ghosts */
+    FAB_CHECK_G(g - v0_hi >= 0 && g - v0_hi < n_hi && g - v0_lo >= 0 && g - v0_lo < n_lo, 207);
     dn_src[j] = rank_hi[g - v0_hi];
     dn_dst[j] = rank_lo[g - v0_lo];
 }
@@ -1620,7 +1704,7 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
             if (g1 > g0)
             {
                 slab_up_pos_kernel<<<(g1 - g0 + 255) / 256, 256, 0, R.st>>>(R.rank, parts[r].v0, runs[r + 1].rank, up.v0,
-                    g0, g1, parts[r].own1, const_cast<int *>(lk.up_pos));
+                    g0, g1, parts[r].own1, const_cast<int *>(lk.up_pos), R.N, runs[r + 1].N);
                 count_launch();
             }
         }
@@ -1638,7 +1722,7 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
             if (n_dn > 0)
             {
                 slab_dn_list_kernel<<<(n_dn + 255) / 256, 256, 0, R.st>>>(R.rank, parts[r].v0, runs[r - 1].rank, dn.v0, g0,
-                    n_dn, dn_src, dn_dst);
+                    n_dn, dn_src, dn_dst, R.N, runs[r - 1].N);
                 count_launch();
             }
             lk.dn_src = dn_src;

@@ -22,6 +22,30 @@ namespace fab
 {
 #define FAB_DEV __device__ __forceinline__
 
+/* Index checks for the DEBUG build (make checked: -DFAB_BOUNDS_CHECK): every look-up through an index that came
+ * out of a table (neighbour lists, plane order, slab ghost maps, mailbox slots) is tested against the size of
+ * what it indexes; a failure is COUNTED in args.check[0] and its site code kept in args.check[1] (largest seen) -
+ * the kernel carries on, the host reads the two words with fabber_cuda_check_report(). compute-sanitizer is not
+ * available on the GPU pool this was developed on; the checked build is run over the spatial / slab / two-echo
+ * tests instead (tests/test_gpu_checked_build.py). The production build compiles the checks away. */
+#ifdef FAB_BOUNDS_CHECK
+#define FAB_CHECK(args, cond, code)                                                                                  \
+    do                                                                                                               \
+    {                                                                                                                \
+        if ((args).check && !(cond))                                                                                 \
+        {                                                                                                            \
+            atomicAdd((args).check, 1ull);                                                                           \
+            atomicMax((args).check + 1, (unsigned long long)(code));                                                 \
+        }                                                                                                            \
+    } while (0)
+#else
+#define FAB_CHECK(args, cond, code)                                                                                  \
+    do                                                                                                               \
+    {                                                                                                                \
+    } while (0)
+#endif
+#define FAB_CHECK_INDEX(args, idx, n, code) FAB_CHECK(args, (long long)(idx) >= 0 && (long long)(idx) < (long long)(n), code)
+
 /* packed lower triangle by rows: (0,0),(1,0),(1,1),(2,0).. - the order of MVNDist::Save */
 __host__ __device__ constexpr int tri(int i, int j)
 {

@@ -264,6 +264,7 @@ __global__ void __launch_bounds__(256) sp_ak_partial_kernel(const __grid_constan
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + v];
+            FAB_CHECK(a, nbr[j] >= -1 && nbr[j] < a.N && nbr[j] != v, 111);
             if (!nbr_alive<IGNORE>(a.status, nbr[j])) /* every failure so far: CalculateaK runs at v == 1 */
                 nbr[j] = -1;
             nn += nbr[j] >= 0;
@@ -392,6 +393,7 @@ template <int P> __global__ void __launch_bounds__(256) sp_ak_final_kernel(const
         for (int i = threadIdx.x; i < MP * W; i += blockDim.x)
         {
             const int q = i / MP, j = i - q * MP;
+            FAB_CHECK(a, q >= 0 && q < W && W <= SLAB_MAX_WORLD && me >= 0 && me < W && (slot == 0 || slot == 1) && s.link.mail[q] != nullptr, 112);
             s.link.mail[q][((size_t)slot * W + me) * MP + j] = j < 2 * P ? (s.ak_update ? sums[j] : 0.0) : fprior_mail;
         }
         __threadfence_system();
@@ -612,6 +614,7 @@ template <int P, bool IGNORE, bool SLAB> struct SweepVoxel
         const VbArgs &a = s.v;
         const size_t N = (size_t)a.N;
         v = pos;
+        FAB_CHECK_INDEX(a, pos, a.N, 101);
         live = a.status[pos] == 0;
         /* neighbours struck by IgnoreVoxel before this iteration are gone from the list (same count as
          * sp_theta used for the prior precision) */
@@ -619,6 +622,7 @@ template <int P, bool IGNORE, bool SLAB> struct SweepVoxel
         for (int j = 0; j < 6; j++)
         {
             nbr[j] = s.nn_idx[j * N + pos];
+            FAB_CHECK(a, nbr[j] >= -1 && nbr[j] < a.N && nbr[j] != pos, 102);
             if (!nbr_alive<IGNORE>(s.status_prev, nbr[j]))
                 nbr[j] = -1;
         }
@@ -675,6 +679,7 @@ template <int P, bool IGNORE, bool SLAB> struct SweepVoxel
             /* top own plane of a z-slab: the slab above sweeps this voxel's +z neighbour one hyper-plane later
              * and must see THIS sweep's value - store it straight into that slab's lower ghost voxel */
             const int up = s.link.up_pos[v];
+            FAB_CHECK(a, up >= -1 && up < s.link.up_N, 103);
             if (up >= 0)
             {
 #pragma unroll
@@ -718,6 +723,7 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
     for (int h = s.plane_first; h < s.plane_last; h++)
     {
         const int b = s.plane_starts[h], e = s.plane_starts[h + 1];
+        FAB_CHECK(s.v, h >= 0 && h < s.n_planes && b >= 0 && b <= e && e <= s.v.N, 104);
         /* slab mode works on GLOBAL coordinates: local plane h IS hyper-plane x+y+z = h of the whole volume.
          * Its voxels on the bottom own plane (z = own_z0) have their -z neighbour in the slab below, on
          * hyper-plane h-1: wait until that slab has published it. */
@@ -780,6 +786,7 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
         for (int v = tid; v < s.v.N; v += stride)
         {
             const int up = lk.up_pos[v];
+            FAB_CHECK(s.v, up >= -1 && up < lk.up_N, 105);
             if (up >= 0)
                 for (int i = 0; i < P; i++)
                     lk.up_mean[(size_t)i * lk.up_N + up] = __ldcg(s.v.mean + i * N + v);
@@ -794,6 +801,7 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
         for (int j = tid; j < lk.n_dn; j += stride)
         {
             const int src = lk.dn_src[j], dst = lk.dn_dst[j];
+            FAB_CHECK(s.v, src >= 0 && src < s.v.N && dst >= 0 && dst < lk.dn_N, 106);
             for (int i = 0; i < P; i++)
                 lk.dn_mean[(size_t)i * lk.dn_N + dst] = __ldcg(s.v.mean + i * N + src);
         }

@@ -62,6 +62,7 @@ struct VbArgs
     double *fit_out;        /*                   [T][N] model prediction out (double), or */
     float *fit_out_f32;     /*                   [T][N] model prediction, float32, and/or */
     float *resid_out_f32;   /*                   [T][N] data - prediction, float32 */
+    unsigned long long *check; /* [2] failure count, site code: the debug build's index checks (FAB_CHECK); else NULL */
 };
 
 /* fit[t][v] = g(ToModel(mean[:, v])): the modelfit / residuals output (inference.cc:190-191) */

@@ -178,6 +178,11 @@ typedef struct fabber_cuda_vb_buffers
 
 /* --- device management helpers (so a C/C++ host needs no CUDA headers) -------------------- */
 int fabber_cuda_device_count(void);
+/* debug build only (csrc: make checked, -DFAB_BOUNDS_CHECK): out[0] = index-check failures counted by the kernels
+ * since the last call (all devices), out[1] = largest failing site code; resets the counters. Returns 1 when the
+ * checks are compiled in, 0 when not (production build; out zeroed), < 0 on error. */
+int fabber_cuda_check_report(unsigned long long *out);
+int fabber_cuda_check_selftest(void); /* debug build: one deliberate failure, site code 999 */
 int fabber_cuda_set_device(int dev);
 int fabber_cuda_get_device(void); /* current device of the calling thread, < 0 on error */
 const char *fabber_cuda_last_error(void);
