@@ -151,21 +151,15 @@ template <int P_> struct PolyModel
 {
     static constexpr int P = P_; /* degree + 1 */
     static constexpr int ID = FABBER_MODEL_POLY;
-    /* the powers (t+1)^n are the same for every voxel: formed once per CTA into a [T][P] table in shared memory
-     * (every thread of a warp reads the same row: a broadcast), with the same integer arithmetic - the time loop
-     * then carries no integer multiplies and no I2F conversions (3.4 % of the C2 kernel's issue slots and its
-     * whole XU load in round 1). Series too long for the table (> 32 KB) fall back to forming them in the loop. */
-    static constexpr int TABLE_MAX_BYTES = 32 * 1024;
     struct Ctx
     {
-        const double *tab; /* NULL: no table */
     };
-    static __host__ __device__ size_t smem_bytes(int T)
-    {
-        /* one row more than the series: the time loops fetch sample t + 1 ahead, also at the last t */
-        const size_t b = (size_t)(T + 1) * P * sizeof(double);
-        return b <= (size_t)TABLE_MAX_BYTES ? b : 0;
-    }
+    static __host__ __device__ size_t smem_bytes(int) { return 0; }
+    template <class Args> static FAB_DEV void stage(const Args &, double *) {}
+    template <class Args> static FAB_DEV Ctx make_ctx(const Args &, double *) { return Ctx(); }
+    /* measured and NOT kept (round 2): staging the powers as a [T][P] table in shared memory (no IMAD / I2F in the
+     * time loop) made C2 slower, 6.15 -> 6.56 ms - the loop is FP64-pipe bound and the integer / conversion
+     * instructions ride in its shadow, while four more LDS per sample sit on the dependency chain */
     static FAB_DEV void powers(int t, double (&pw)[P])
     {
         unsigned int x = 1u, i = (unsigned int)(t + 1);
@@ -175,25 +169,6 @@ template <int P_> struct PolyModel
             pw[n] = (double)(int)x;
             x *= i;
         }
-    }
-    template <class Args> static FAB_DEV void stage(const Args &a, double *smem)
-    {
-        if (smem_bytes(a.T) == 0)
-            return;
-        for (int t = threadIdx.x; t <= a.T; t += blockDim.x)
-        {
-            double pw[P];
-            powers(t, pw);
-#pragma unroll
-            for (int n = 0; n < P; n++)
-                smem[t * P + n] = pw[n];
-        }
-    }
-    template <class Args> static FAB_DEV Ctx make_ctx(const Args &a, double *smem)
-    {
-        Ctx c;
-        c.tab = smem_bytes(a.T) ? smem : nullptr;
-        return c;
     }
     static FAB_DEV double eval(const Ctx &, int t, const double (&p)[P])
     {
@@ -214,17 +189,7 @@ template <int P_> struct PolyModel
     {
         double pw[P]; /* (t+1)^n, n = 0..P-1 */
     };
-    static FAB_DEV void sample(const Ctx &c, int t, Sample &s)
-    {
-        if (c.tab)
-        {
-#pragma unroll
-            for (int n = 0; n < P; n++)
-                s.pw[n] = c.tab[t * P + n];
-        }
-        else
-            powers(t, s.pw);
-    }
+    static FAB_DEV void sample(const Ctx &, int t, Sample &s) { powers(t, s.pw); }
     static constexpr bool LINEAR = true; /* g = sum_n (t+1)^n c_n */
     static FAB_DEV void basis_row(const Ctx &, const Sample &smp, const double (&p0)[P], double &g, double (&phi)[P])
     {
