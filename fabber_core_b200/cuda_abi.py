@@ -24,6 +24,7 @@ MODEL_LINEAR, MODEL_POLY, MODEL_EXP = 1, 2, 3
 MODEL_PLUGIN = 100
 MODEL_ORACLE_SINE = 101   # known to the test oracle only (oracle/vb_oracle.cc), never to the device library
 NOISE_WHITE, NOISE_AR1 = 0, 1
+METHOD_VB, METHOD_NLLS = 0, 1
 CONV_MAXITS, CONV_FCHANGE, CONV_FREDUCE, CONV_TRIALMODE, CONV_LM = 0, 1, 2, 3, 4
 CONV_BY_NAME = {
     "maxits": CONV_MAXITS,
@@ -94,6 +95,10 @@ class VbProblem(C.Structure):
         ("nx", C.c_int),
         ("ny", C.c_int),
         ("nz", C.c_int),
+        ("method", C.c_int),
+        ("nlls_lm", C.c_int),
+        ("nlls_have_start", C.c_int),
+        ("nlls_start", C.c_double * MAX_PARAMS),
     ]
 
 
@@ -172,7 +177,7 @@ class ProblemSpec(object):
                  max_trials=10, need_f=None, f_history_len=0, allow_bad_voxels=False,
                  prior_types=None, spatial_dims=3, spatial_speed=-1.0, spatial_q1=10.0, spatial_q2=1.0,
                  update_first_iter=False, param_overrides=None, plugin_launchers=None, num_echoes=1,
-                 ar_cross_terms="none"):
+                 ar_cross_terms="none", method="vb", nlls_lm=False, nlls_start=None):
         self.keep = []
         self.n_times = int(n_times)
         m = Model()
@@ -286,6 +291,12 @@ class ProblemSpec(object):
         prob.spatial_speed = spatial_speed
         prob.spatial_q1, prob.spatial_q2 = spatial_q1, spatial_q2
         prob.update_first_iter = int(update_first_iter)
+        prob.method = {"vb": METHOD_VB, "nlls": METHOD_NLLS}[method]
+        prob.nlls_lm = int(nlls_lm)
+        if nlls_start is not None:
+            prob.nlls_have_start = 1
+            for i, x in enumerate(nlls_start):
+                prob.nlls_start[i] = x
         self.prob = prob
         self.P = P
         self.n_alphas = 2 + prob.ar_cross_terms if noise == "ar" else 0

@@ -55,6 +55,10 @@ extern "C" {
 #define FABBER_MODEL_PLUGIN 100
 #define FABBER_CUDA_MODEL_CONSTS 16
 
+/* inference techniques */
+#define FABBER_METHOD_VB 0   /* "vb" / "spatialvb" (inference_vb.cc) */
+#define FABBER_METHOD_NLLS 1 /* "nlls" (inference_nlls.cc) */
+
 /* noise models */
 #define FABBER_NOISE_WHITE 0 /* noisemodel_white.cc */
 #define FABBER_NOISE_AR1 1   /* noisemodel_ar.cc: n_phis = num-echoes (1 or 2), ar_cross_terms */
@@ -150,6 +154,14 @@ typedef struct fabber_cuda_vb_problem
     double spatial_q1, spatial_q2;
     int update_first_iter;
     int nx, ny, nz; /* bounding grid of the coords, used for neighbour search */
+
+    /* inference technique (setup.cc:28-33). FABBER_METHOD_NLLS (inference_nlls.cc): non-linear least squares per
+     * voxel through the same entry points; noise / priors / convergence fields are ignored, the noise, free_energy
+     * and f_history result arrays are not written, `iterations` holds the optimiser's successful steps. */
+    int method;          /* FABBER_METHOD_* */
+    int nlls_lm;         /* --lm: Levenberg-Marquardt damping, else Levenberg (inference_nlls.cc:86,135-139) */
+    int nlls_have_start; /* fwd-inital-posterior given: start from nlls_start (Fabber space) */
+    double nlls_start[FABBER_CUDA_MAX_PARAMS];
 } fabber_cuda_vb_problem;
 
 typedef struct fabber_cuda_vb_buffers

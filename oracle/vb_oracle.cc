@@ -38,6 +38,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -1992,6 +1993,218 @@ int calc_neighbours(const int *coords, int nVoxels, int spatial_dims,
     return 0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// NLLS (inference_nlls.cc:90-293). The optimiser is MISCMATHS::nonlin - FSL's miscmaths/nonlin.{h,cpp}, an FSL
+// dependency that is NOT in the reference tree (CMakeLists.txt links libmiscmaths; FSL 5.0 / 6.0). Its
+// Levenberg(-Marquardt) driver `levmar` is restated here from FSL's published source as the builder knows it:
+//   cf0 = cf(p); success = true; olambda = 0; lambda = 0.1 (NonlinParam default)
+//   while NextIter(success):                 // counts SUCCESSFUL steps only, at most 200
+//     if success: g = grad(p), H = hess(p)
+//     H_ii <- H_ii (1+lambda)/(1+olambda)    (LM)      or   H_ii + lambda - olambda    (Levenberg, fabber's default)
+//     step = -H^-1 g; ncf = cf(p + step)     // a failing solve counts as an unsuccessful step
+//     if ncf < cf: p += step; lambda /= 10; olambda = 0; stop if 2|cf-ncf| <= 1e-8 (|cf|+|ncf|+2e-16); cf = ncf
+//     else:        olambda = lambda; lambda *= 10; stop if lambda > 1e20
+// PARITY OF THIS PART IS PINNED ONLY THROUGH THE REFERENCE'S GOLDEN test/outdata_linear_nlls (means, z-stats and
+// finalMVN of the shipped regression case, tests/test_oracle_golden.py): oracle/_ref is built with NO_NLLS
+// (inference_nlls.cc:1) because nonlin is not there. Everything around the optimiser (cost function, Jacobian,
+// precision = J'J / mse with the 1e-6 floor, exception path) is the reference's own code restated.
+// ---------------------------------------------------------------------------------------------
+struct NllsCost // NLLSCF, inference_nlls.cc:232-293
+{
+    const ModelCtx &mc;
+    std::vector<int> keep; // unmasked samples (MaskRows)
+    Vec data;
+    NllsCost(const ModelCtx &m, const Vec &y, const fabber_cuda_vb_problem *prob)
+        : mc(m)
+        , data(y)
+    {
+        for (int t = 0; t < mc.T; t++)
+            if (!(prob->time_masked && prob->time_masked[t]))
+                keep.push_back(t);
+    }
+    real cf(const Vec &p) const
+    {
+        Vec pred;
+        evaluate_fabber(mc, p, pred);
+        real s = 0;
+        for (size_t k = 0; k < keep.size(); k++)
+        {
+            real d = data[keep[k]] - pred[keep[k]];
+            s += d * d;
+        }
+        return s;
+    }
+    // gradient -2 J'(data - pred) and Gauss-Newton Hessian 2 J'J about p
+    void grad_hess(const Vec &p, Vec &g, Mat &H) const
+    {
+        LinModel lin;
+        lin.ReCentre(mc, p);
+        Vec pred;
+        evaluate_fabber(mc, p, pred);
+        g.assign(mc.P, 0.0);
+        H = Mat(mc.P, mc.P);
+        for (int i = 0; i < mc.P; i++)
+        {
+            real s = 0;
+            for (size_t k = 0; k < keep.size(); k++)
+                s += lin.J(keep[k], i) * (data[keep[k]] - pred[keep[k]]);
+            g[i] = -2 * s;
+            for (int j = 0; j < mc.P; j++)
+            {
+                real h = 0;
+                for (size_t k = 0; k < keep.size(); k++)
+                    h += lin.J(keep[k], i) * lin.J(keep[k], j);
+                H(i, j) = 2 * h;
+            }
+        }
+    }
+};
+
+// MISCMATHS::nonlin with NL_LM (see the header of this section). Returns the number of successful steps.
+int nlls_levmar(const NllsCost &cost, Vec &p, bool lm)
+{
+    const int P = (int)p.size();
+    const int maxiter = 200;
+    const real cftol = 1e-8, ltol = 1e20;
+    real lambda = 0.1, olambda = 0.0;
+    real cf = cost.cf(p);
+    bool success = true;
+    int niter = 0;
+    Vec g;
+    Mat H;
+    for (;;)
+    {
+        if (success && niter++ >= maxiter)
+            break;
+        if (success)
+            cost.grad_hess(p, g, H);
+        for (int i = 0; i < P; i++)
+        {
+            if (lm)
+                H(i, i) = ((1.0 + lambda) / (1.0 + olambda)) * H(i, i);
+            else
+                H(i, i) = H(i, i) + lambda - olambda;
+        }
+        Vec trial(P);
+        real ncf = 0;
+        bool inv_fail = false;
+        try
+        {
+            Vec step = mulv(inverse(H), g);
+            for (int i = 0; i < P; i++)
+                trial[i] = p[i] + -step[i];
+            ncf = cost.cf(trial);
+        }
+        catch (SingularError &)
+        {
+            inv_fail = true;
+        }
+        if (!inv_fail && (success = (ncf < cf)))
+        {
+            olambda = 0.0;
+            p = trial;
+            lambda = lambda / 10.0;
+            const bool conv = 2.0 * std::fabs(cf - ncf) <= cftol * (std::fabs(cf) + std::fabs(ncf) + 2.0e-16);
+            cf = ncf;
+            if (conv)
+                break;
+        }
+        else
+        {
+            success = false;
+            olambda = lambda;
+            lambda = 10.0 * lambda;
+            if (lambda > ltol)
+                break;
+        }
+    }
+    return niter > maxiter ? maxiter : niter;
+}
+
+int nlls_run(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf)
+{
+    Engine eng(prob, buf);
+    const int N = eng.N, P = eng.P, T = eng.T;
+    int n_masked = 0;
+    if (prob->time_masked)
+        for (int t = 0; t < T; t++)
+            n_masked += prob->time_masked[t] ? 1 : 0;
+    const int Nsamples = T - n_masked;
+    // initialFwdPosterior: the model's hard-coded posterior (Fabber space) or the fwd-inital-posterior file;
+    // NOT the per-voxel InitVoxelPosterior (inference_nlls.cc:66-83,141-143)
+    Vec start(P);
+    for (int i = 0; i < P; i++)
+        start[i] = prob->nlls_have_start ? (real)prob->nlls_start[i]
+                                         : t_to_fabber(prob->params[i].transform, prob->params[i].post_mean);
+    for (int v = 0; v < N; v++)
+    {
+        Vec y = eng.voxel_data(v);
+        NllsCost cost(eng.mc, y, prob);
+        Vec p = start;
+        int status = 0, its = 0;
+        Mat cov(P, P);
+        try
+        {
+            its = nlls_levmar(cost, p, prob->nlls_lm != 0);
+            LinModel lin;
+            lin.ReCentre(eng.mc, p);
+            const real sqerr = cost.cf(p);
+            const real mse = sqerr / (Nsamples - P);
+            Mat prec(P, P);
+            for (int i = 0; i < P; i++)
+                for (int j = 0; j < P; j++)
+                {
+                    real h = 0;
+                    for (size_t k = 0; k < cost.keep.size(); k++)
+                        h += lin.J(cost.keep[k], i) * lin.J(cost.keep[k], j);
+                    prec(i, j) = h / mse;
+                }
+            for (int i = 0; i < P; i++)
+                if (prec(i, i) < 1e-6)
+                    prec(i, i) = 1e-6;
+            if (!all_finite(prec))
+            {
+                // mse = 0/0 (as many samples as parameters, test/test_inference.cc:79-105) or a perfect fit: NEWMAT's
+                // inverse does not throw on NaN, the covariance is NaN and the voxel is NOT an error
+                for (int i = 0; i < P; i++)
+                    for (int j = 0; j < P; j++)
+                        cov(i, j) = std::numeric_limits<real>::quiet_NaN();
+            }
+            else
+            {
+                MVN post(P);
+                post.SetPrecisions(prec);
+                cov = post.GetCovariance();
+            }
+        }
+        catch (SingularError &)
+        {
+            // "precision matrix is probably singular so set manually" (:212-221): means kept, precisions 1e-12 I
+            status = FABBER_VOX_SINGULAR;
+            cov = Mat(P, P);
+            for (int i = 0; i < P; i++)
+                cov(i, i) = 1 / (real)1e-12;
+        }
+        catch (InternalError &e)
+        {
+            status = e.code; // a non-finite offset / Jacobian ends the reference's run whatever allow-bad-voxels says
+            cov = Mat(P, P);
+        }
+        for (int i = 0; i < P; i++)
+            buf->mean[(size_t)i * N + v] = p[i];
+        int idx = 0;
+        for (int r = 0; r < P; r++)
+            for (int c = 0; c <= r; c++, idx++)
+                buf->cov[(size_t)idx * N + v] = cov(r, c);
+        if (buf->iterations)
+            buf->iterations[v] = its;
+        buf->status[v] = status;
+        if (status != 0 && !prob->allow_bad_voxels)
+            return FABBER_CUDA_ERR_BAD_VOXEL;
+    }
+    return FABBER_CUDA_OK;
+}
+
 } // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -2002,6 +2215,8 @@ extern "C" {
 /* Vb::DoCalculationsVoxelwise, inference_vb.cc:415-576 */
 int vb_oracle_voxelwise(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *buf)
 {
+    if (prob->method == FABBER_METHOD_NLLS)
+        return nlls_run(prob, buf);
     Engine eng(prob, buf);
     const int N = eng.N, P = eng.P;
     std::vector<Prior> priors = make_priors(prob, buf);

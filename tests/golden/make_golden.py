@@ -10,6 +10,7 @@ Inputs (reference repo, read-only):
   test/test_linear_design.mat            VEST design matrix 106x4
   test/outdata_linear_vb/*.nii.gz        golden outputs of `--model=linear --noise=white --method=vb`
   test/outdata_linear_spatialvb/*.nii.gz same with --method=spatialvb (only 'N' priors)
+  test/outdata_linear_nlls/*.nii.gz      same model with --method=nlls
   test/outdata_poly/*.nii.gz             golden outputs of `--model=poly --degree=2`
 The goldens live on the 64x64x42 grid of the (missing) test_data.nii.gz; test_data_small is the
 crop [30:33, 30:33, 20:22] (0-based x,y,z) of it, so the 18 golden voxels
@@ -96,6 +97,7 @@ def main():
     lin_names += ["std_Parameter_%d" % i for i in range(1, 5)] + ["finalMVN", "noise_means", "noise_stdevs", "freeEnergy"]
     grab("outdata_linear_vb", lin_names, "linear_vb/")
     grab("outdata_linear_spatialvb", lin_names, "linear_spatialvb/")
+    grab("outdata_linear_nlls", lin_names, "linear_nlls/")  # --method=nlls (Levenberg, the default)
     poly_names = []
     for c in range(3):
         poly_names += ["mean_c%d" % c, "std_c%d" % c, "zstat_c%d" % c]

@@ -80,3 +80,31 @@ def test_golden_free_energy_is_placeholder(golden):
     """The goldens hold the 9999 garbage default (inference_vb.cc:165): F is pinned by no golden."""
     assert np.all(golden["linear_vb/freeEnergy"] == 9999.0)
     assert np.all(golden["poly/freeEnergy"] == 9999.0)
+
+
+def test_linear_nlls_golden(golden):
+    """--method=nlls: the reference's optimiser is MISCMATHS::nonlin, an FSL library that is NOT in the reference
+    tree (oracle/_ref is built with NO_NLLS); the oracle restates its Levenberg driver, and this golden is what pins
+    that restatement. It is a sharp pin: the reference stops 1.1e-4 (relative) short of the exact least-squares
+    solution - its own convergence error - and the oracle lands on the SAME point to 6e-6; the Levenberg-Marquardt
+    variant of the same code (--lm) ends 5 % away for some parameters, so the damping rule is pinned too. The
+    covariance pins the post-processing: J'J / mse, the 1e-6 floor on the diagonal (every diagonal element here),
+    the inverse."""
+    data, design = golden["data"], golden["design"]
+    out = oracle.run(abi.ProblemSpec("linear", 106, design=design, method="nlls"), data)
+    assert out["rc"] == 0 and np.all(out["status"] == 0) and np.all(out["iterations"] == 3)
+    gm = np.stack([golden["linear_nlls/mean_Parameter_%d" % (i + 1)][0] for i in range(4)]).astype(np.float64)
+    gz = np.stack([golden["linear_nlls/zstat_Parameter_%d" % (i + 1)][0] for i in range(4)]).astype(np.float64)
+    assert _rel(out["mean"], gm) < 1e-5
+    var = np.stack([out["cov"][abi_tri(i, i)] for i in range(4)])
+    assert _rel(out["mean"] / np.sqrt(var), gz) < 1e-5
+    cov, means = _unpack_mvn(golden["linear_nlls/finalMVN"].astype(np.float64), 4)   # no noise block
+    assert golden["linear_nlls/finalMVN"].shape[0] == 4 * 5 // 2 + 4 + 1
+    assert _rel(out["mean"], means) < 1e-5
+    scale = np.maximum(np.abs(cov), 1e-3)
+    assert np.max(np.abs(out["cov"] - cov) / scale) < 3e-5
+    # the reference's own distance from the exact least-squares solution, reproduced
+    ols = np.linalg.lstsq(design, data.astype(np.float64), rcond=None)[0]
+    assert 5e-5 < _rel(gm, ols) < 2e-4 and 5e-5 < _rel(out["mean"], ols) < 2e-4
+    lm = oracle.run(abi.ProblemSpec("linear", 106, design=design, method="nlls", nlls_lm=True), data)
+    assert _rel(lm["mean"], gm) > 1e-2
