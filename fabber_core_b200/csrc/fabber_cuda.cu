@@ -564,6 +564,10 @@ static int build_args(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_b
     }
     a.locked_noise_stdev = prob->locked_noise_stdev;
     a.ar_alpha_prior_prec = prob->ar_alpha_prior_prec;
+    a.nlls_lm = prob->nlls_lm;
+    a.nlls_have_start = prob->nlls_have_start;
+    for (int i = 0; i < FABBER_CUDA_MAX_PARAMS; i++)
+        a.nlls_start[i] = prob->nlls_start[i];
     a.check = nullptr;
 #ifdef FAB_BOUNDS_CHECK
     {
@@ -837,7 +841,9 @@ int fabber_cuda_vb_voxelwise_range(const fabber_cuda_vb_problem *prob, const fab
         return fail(FABBER_CUDA_ERR_INVALID, "no device Evaluate hook compiled for this model / parameter count");
     }
     VbLaunchFn fn = nullptr;
-    if (prob->noise_type == FABBER_NOISE_AR1)
+    if (prob->method == FABBER_METHOD_NLLS)
+        fn = ml->nlls;
+    else if (prob->noise_type == FABBER_NOISE_AR1)
         fn = a.n_phis == 2 ? ml->ar2 : ml->ar1;
     else if (prob->noise_type == FABBER_NOISE_WHITE)
     {
@@ -847,7 +853,7 @@ int fabber_cuda_vb_voxelwise_range(const fabber_cuda_vb_problem *prob, const fab
     if (!fn)
     {
         st.release(s);
-        return fail(FABBER_CUDA_ERR_INVALID, "noise model not available for this model");
+        return fail(FABBER_CUDA_ERR_INVALID, "noise model / inference technique not available for this model");
     }
     a.v_begin = v_begin;
     a.v_end = v_end;
@@ -1890,7 +1896,8 @@ int fabber_cuda_vb_save_results(const fabber_cuda_vb_problem *prob, const fabber
         return fail(FABBER_CUDA_ERR_INVALID, "bad sizes");
     if (N == 0)
         return FABBER_CUDA_OK;
-    if (!buf->mean || !buf->cov || !buf->noise)
+    const bool nlls = prob->method == FABBER_METHOD_NLLS; /* no noise block: the result MVN is the model's alone */
+    if (!buf->mean || !buf->cov || (!buf->noise && !nlls))
         return fail(FABBER_CUDA_ERR_INVALID, "missing mean / cov / noise result arrays");
     SaveArgs a;
     memset(&a, 0, sizeof(a));
@@ -1905,6 +1912,8 @@ int fabber_cuda_vb_save_results(const fabber_cuda_vb_problem *prob, const fabber
     a.n_noise = a.ar ? a.n_alphas + a.n_phis : prob->n_phis;
     if (a.n_noise < 1 || a.n_noise > 6 || (!a.ar && a.n_noise > FABBER_CUDA_MAX_PHIS))
         return fail(FABBER_CUDA_ERR_INVALID, "n_phis out of range");
+    if (nlls)
+        a.ar = a.n_phis = a.n_noise = 0;
     a.f_len = buf->f_history ? prob->f_history_len : 0;
     for (int i = 0; i < P; i++)
         a.transform[i] = prob->params[i].transform;

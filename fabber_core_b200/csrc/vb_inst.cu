@@ -11,6 +11,7 @@
 #include "vb_voxelwise.cuh"
 #include "vb_voxelwise_ar.cuh"
 #include "vb_voxelwise_ar2.cuh"
+#include "vb_nlls.cuh"
 #include "vb_spatial.cuh"
 
 #if !defined(FAB_GETTER) || !(defined(FAB_MODEL_TYPE) || (defined(FAB_FAMILY) && defined(FAB_K)))
@@ -77,6 +78,24 @@ static cudaError_t launch_ar2(const VbArgs &a, cudaStream_t s)
     const size_t smem = M::smem_bytes(a.T)
         + (size_t)(Vox::STASH_DOUBLES + (use_snap ? Vox::SNAP_DOUBLES : 0)) * VB_BLOCK * sizeof(double);
     auto kern = vb_voxelwise_ar2_kernel<M>;
+    if (smem > 48 * 1024)
+    {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess)
+            return e;
+    }
+    const unsigned grid = (unsigned)((a.v_end - a.v_begin + VB_BLOCK - 1) / VB_BLOCK);
+    kern<<<grid, VB_BLOCK, smem, s>>>(a);
+    count_launch();
+    return cudaGetLastError();
+}
+
+static cudaError_t launch_nlls(const VbArgs &a, cudaStream_t s)
+{
+    if (a.v_end <= a.v_begin)
+        return cudaSuccess;
+    const size_t smem = M::smem_bytes(a.T);
+    auto kern = nlls_kernel<M>;
     if (smem > 48 * 1024)
     {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -221,6 +240,7 @@ static const ModelLaunchers g_launchers = {
     launch_sp_noise,
     preload_spatial,
     launch_ar2,
+    launch_nlls,
 };
 
 #ifdef FAB_MODEL_TYPE

@@ -30,6 +30,7 @@ struct ModelLaunchers
      * the middle of an iteration would deadlock until the spin gives up. Appended: older plug-ins leave it NULL. */
     cudaError_t (*sp_preload)(void);
     VbLaunchFn ar2; /* AR(1) noise on two interleaved echoes, with or without cross terms (appended, may be NULL) */
+    VbLaunchFn nlls; /* --method=nlls: non-linear least squares per voxel (appended, may be NULL) */
 };
 
 /* number of blocks the aK partial reduction is launched with (size of SpArgs::ak_partial) */

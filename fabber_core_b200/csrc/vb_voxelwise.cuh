@@ -50,6 +50,8 @@ struct VbArgs
     double noise_post_b[FAB_MAX_PHIS], noise_post_c[FAB_MAX_PHIS];
     double locked_noise_stdev;
     double ar_alpha_prior_prec;
+    int nlls_lm, nlls_have_start; /* --method=nlls (vb_nlls.cuh) */
+    double nlls_start[FABBER_CUDA_MAX_PARAMS];
     int ar_n_alphas; /* AR(1) on two echoes: 2 / 3 / 4 alphas for ar1-cross-terms none / same / dual */
     int conv_type, max_iterations, max_trials, need_f, f_history_len;
     double fchange;

@@ -233,8 +233,8 @@ int fabber_get_options(
             const std::vector<std::string> methods = Vb::GetKnownMethods();
             if (std::find(methods.begin(), methods.end(), value) == methods.end())
                 throw InvalidOptionValue("method", value, "Unrecognized inference method");
-            desc = Vb::GetDescription();
-            Vb::GetOptions(options);
+            desc = Vb::GetDescription(value);
+            Vb::GetOptions(options, value);
         }
         desc.erase(std::remove(desc.begin(), desc.end(), '\n'), desc.end());
         std::ostringstream out;

@@ -460,9 +460,11 @@ void read_matrix_file(const std::string &filename, std::vector<double> &values, 
 class Vb
 {
 public:
-    static std::vector<std::string> GetKnownMethods(); /* vb, spatialvb (setup.cc:29-30) */
+    static std::vector<std::string> GetKnownMethods(); /* nlls, spatialvb, vb (setup.cc:28-33) */
     static void GetOptions(std::vector<OptionSpec> &opts);
     static std::string GetDescription();
+    static void GetOptions(std::vector<OptionSpec> &opts, const std::string &method); /* "nlls": inference_nlls.cc:31-45 */
+    static std::string GetDescription(const std::string &method);
     void Initialize(FwdModel *model, FabberRunData &rundata); /* inference_vb.cc:100, inference.cc:62 */
     void DoCalculations(FabberRunData &rundata);              /* inference_vb.cc:360 - runs on the GPU */
     /* DoCalculations in three steps (it is Prepare + LaunchAll + Finish): the host library starts a run
@@ -482,6 +484,8 @@ private:
     bool m_ar = false, m_saveF = false, m_saveFsHistory = false, m_printF = false, m_needF = false;
     bool m_halt_bad_voxel = true;
     int m_nphis = 1, m_nalphas = 2;
+    bool m_nlls = false, m_nlls_lm = false; /* --method=nlls through the same plumbing (inference_nlls.cc) */
+    std::vector<double> m_nlls_start;
     /* results stay on the device, structure of arrays over voxels (the layout of include/fabber_cuda.h);
      * SaveResults turns them into float32 output maps there and downloads only what was asked for */
     size_t m_nvoxels = 0;

@@ -5,8 +5,8 @@
  *   fabber_b200 --output=out --method=vb --model=poly --degree=2 --noise=white --data=data.nii.gz --mask=mask.nii.gz
  *   fabber_b200 -f options.txt          fabber_b200 --listmodels | --listmethods | --help [--model=..|--method=..]
  *
- * Differences, stated: --method=nlls and --loadmodels are refused (the VB path is what runs on the GPU and
- * models are compiled __device__ hooks); the logfile is written when the run ends rather than line by line.
+ * Differences, stated: --loadmodels of the reference's CPU model libraries is refused (models are compiled
+ * __device__ hooks); the logfile is written when the run ends rather than line by line.
  */
 #include <cstdio>
 #include <cstdlib>
@@ -69,9 +69,9 @@ static void MethodUsage(const std::string &name)
     if (std::find(known.begin(), known.end(), name) == known.end())
         throw InvalidOptionValue("method", name, "Unrecognized inference method");
     std::cout << "Usage information for method: " << name << std::endl << std::endl;
-    std::cout << Vb::GetDescription() << std::endl << std::endl << "Options: " << std::endl << std::endl;
+    std::cout << Vb::GetDescription(name) << std::endl << std::endl << "Options: " << std::endl << std::endl;
     std::vector<OptionSpec> options;
-    Vb::GetOptions(options);
+    Vb::GetOptions(options, name);
     for (size_t i = 0; i < options.size(); i++)
         std::cout << options[i] << std::endl;
 }

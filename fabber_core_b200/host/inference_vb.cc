@@ -92,11 +92,30 @@ void NoiseGammasFromMvnFile(FabberRunData &rundata, const std::string &key, int 
 std::vector<std::string> Vb::GetKnownMethods()
 {
     std::vector<std::string> k;
+    k.push_back("nlls");
     k.push_back("spatialvb");
     k.push_back("vb");
     return k;
 }
 std::string Vb::GetDescription() { return "Variational Bayes inference technique (B200 GPU implementation)"; }
+std::string Vb::GetDescription(const std::string &method)
+{
+    if (method == "nlls") /* inference_nlls.cc:48-51 */
+        return "Non-linear least squares inference technique (B200 GPU implementation).";
+    return GetDescription();
+}
+void Vb::GetOptions(std::vector<OptionSpec> &opts, const std::string &method)
+{
+    if (method != "nlls")
+        return GetOptions(opts);
+    /* inference_nlls.cc:31-36 (the reference lists only the first: NUM_OPTIONS = 1) */
+    static const OptionSpec O[] = {
+        { "vb-init", OPT_BOOL, "Whether NLLS is being run in isolation or as a pre-step for VB", true, "" },
+        { "lm", OPT_BOOL, "Whether to use LM convergence (default is L)", true, "" },
+    };
+    for (size_t i = 0; i < sizeof(O) / sizeof(O[0]); i++)
+        opts.push_back(O[i]);
+}
 void Vb::GetOptions(std::vector<OptionSpec> &opts)
 {
     /* inference_vb.cc:31-76 */
@@ -155,6 +174,31 @@ void Vb::Initialize(FwdModel *model, FabberRunData &rundata)
             "number of parameters outside the compiled device hooks (1.." + stringify(FABBER_CUDA_MAX_PARAMS) + ")");
     m_halt_bad_voxel = !rundata.GetBool("allow-bad-voxels"); /* inference.cc:93 */
 
+    /* --method=nlls (NLLSInferenceTechnique::Initialize, inference_nlls.cc:57-88): no noise model, no priors, no
+     * free energy; the same device plumbing (block-wise upload, one voxel range per GPU, SaveResults) */
+    m_nlls = rundata.GetString("method") == "nlls";
+    if (m_nlls)
+    {
+        m_ar = false;
+        m_saveF = m_saveFsHistory = m_printF = false;
+        rundata.GetBool("vb-init"); /* only changes what the reference logs for an ill-conditioned voxel */
+        m_nlls_lm = rundata.GetBool("lm");
+        m_nlls_start.clear();
+        const std::string file = rundata.GetStringDefault("fwd-inital-posterior", "modeldefault"); /* sic */
+        if (file != "modeldefault")
+        {
+            /* MVNDist::LoadFromMatrix: [covariance means(:); means(:) 1.0] (dist_mvn.cc:287-309) */
+            std::vector<double> m;
+            int rows = 0, cols = 0;
+            read_matrix_file(file, m, rows, cols);
+            if (rows != cols || rows != m_num_params + 1 || m[(size_t)(rows - 1) * cols + rows - 1] != 1.0)
+                throw InvalidOptionValue("fwd-inital-posterior", file,
+                    "MVNs must be symmetric matrices (format = [covariance means(:); means(:) 1.0]) of the model's size");
+            for (int i = 0; i < m_num_params; i++)
+                m_nlls_start.push_back(m[(size_t)i * cols + rows - 1]);
+        }
+        return;
+    }
     const std::string noise = rundata.GetString("noise");
     if (noise == "white")
         m_ar = false;
@@ -255,50 +299,74 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
             throw InvalidOptionValue("mt", stringify(mt[i]), "Masked time point beyond the end of the data");
         m_masked[mt[i] - 1] = 1;
     }
-    if (m_ar && !mt.empty())
-        throw InvalidOptionValue("noise", "ar", "AR noise model does not support masked time points");
-    std::unique_ptr<NoiseModel> noise(NoiseModel::NewFromName(rundata.GetString("noise")));
-    noise->Initialize(rundata);
-    noise->Describe(prob, T, m_pattern);
-    if (m_ar)
+    if (m_nlls)
     {
-        /* noisemodel_ar.cc:305-349 */
-        for (const char *key : { "noise-initial-prior", "noise-initial-posterior" })
-            if (rundata.GetStringDefault(key, "modeldefault") != "modeldefault")
-                throw InvalidOptionValue(key, rundata.GetString(key),
-                    "the AR(1) device kernel starts alpha at N(0, 1e4 I) only: not supported with noise=ar");
-        m_nphis = prob.n_phis; /* num-echoes */
-        m_nalphas = 2 + prob.ar_cross_terms;
-        m_noise_params = m_nalphas + m_nphis; /* the alphas, then the phis: Ar1cParams::OutputAsMVN, noisemodel_ar.cc:287-300 */
+        prob.method = FABBER_METHOD_NLLS;
+        prob.nlls_lm = m_nlls_lm ? 1 : 0;
+        prob.nlls_have_start = m_nlls_start.empty() ? 0 : 1;
+        for (size_t i = 0; i < m_nlls_start.size(); i++)
+            prob.nlls_start[i] = m_nlls_start[i];
+        prob.noise_type = FABBER_NOISE_WHITE; /* unused by the NLLS kernel; keeps the shared checks quiet */
+        prob.n_phis = 1;
+        m_pattern.assign(T, 0);
+        prob.noise_prior_b[0] = prob.noise_post_b[0] = 1;
+        prob.noise_prior_c[0] = prob.noise_post_c[0] = 1;
+        prob.locked_noise_stdev = -1;
+        prob.conv_type = FABBER_CONV_MAXITS;
+        prob.max_iterations = 1;
+        prob.max_trials = 1;
+        m_nphis = 1;
+        m_noise_params = 0; /* InferenceTechnique::m_noise_params stays 0: the result MVN is the model's alone */
+        prob.phi_pattern = m_pattern.data();
+        prob.time_masked = mt.empty() ? nullptr : m_masked.data();
     }
     else
     {
-        m_nphis = prob.n_phis;
-        m_noise_params = m_nphis;
-        /* after the hard-coded values, as in the reference (inference_vb.cc:204-205) */
-        NoiseGammasFromMvnFile(rundata, "noise-initial-prior", m_nphis, prob.noise_prior_b, prob.noise_prior_c);
-        NoiseGammasFromMvnFile(rundata, "noise-initial-posterior", m_nphis, prob.noise_post_b, prob.noise_post_c);
-    }
-    prob.phi_pattern = m_pattern.data();
-    prob.time_masked = mt.empty() ? nullptr : m_masked.data();
+        if (m_ar && !mt.empty())
+            throw InvalidOptionValue("noise", "ar", "AR noise model does not support masked time points");
+        std::unique_ptr<NoiseModel> noise(NoiseModel::NewFromName(rundata.GetString("noise")));
+        noise->Initialize(rundata);
+        noise->Describe(prob, T, m_pattern);
+        if (m_ar)
+        {
+            /* noisemodel_ar.cc:305-349 */
+            for (const char *key : { "noise-initial-prior", "noise-initial-posterior" })
+                if (rundata.GetStringDefault(key, "modeldefault") != "modeldefault")
+                    throw InvalidOptionValue(key, rundata.GetString(key),
+                        "the AR(1) device kernel starts alpha at N(0, 1e4 I) only: not supported with noise=ar");
+            m_nphis = prob.n_phis; /* num-echoes */
+            m_nalphas = 2 + prob.ar_cross_terms;
+            m_noise_params = m_nalphas + m_nphis; /* the alphas, then the phis: Ar1cParams::OutputAsMVN, noisemodel_ar.cc:287-300 */
+        }
+        else
+        {
+            m_nphis = prob.n_phis;
+            m_noise_params = m_nphis;
+            /* after the hard-coded values, as in the reference (inference_vb.cc:204-205) */
+            NoiseGammasFromMvnFile(rundata, "noise-initial-prior", m_nphis, prob.noise_prior_b, prob.noise_prior_c);
+            NoiseGammasFromMvnFile(rundata, "noise-initial-posterior", m_nphis, prob.noise_post_b, prob.noise_post_c);
+        }
+        prob.phi_pattern = m_pattern.data();
+        prob.time_masked = mt.empty() ? nullptr : m_masked.data();
 
-    /* convergence (setup.cc:49-57, convergence.cc Initialize functions) */
-    std::unique_ptr<ConvergenceDetector> detector(
-        ConvergenceDetector::NewFromName(rundata.GetStringDefault("convergence", "maxits")));
-    detector->Initialize(rundata);
-    detector->Describe(prob);
-    if (rundata.GetIntDefault("max-trials", 10) <= 0)
-        throw InvalidOptionValue("max-trials", rundata.GetString("max-trials"), "Must be positive");
-    /* priors (priors.cc:490-528): the factory validates every parameter's prior type and options (image data
-     * present, spatial-dims / speed in range); the types themselves travel in prob.params[] */
-    {
-        std::vector<Prior *> priors = PriorFactory(rundata).CreatePriors(params);
-        for (size_t i = 0; i < priors.size(); i++)
-            delete priors[i];
+        /* convergence (setup.cc:49-57, convergence.cc Initialize functions) */
+        std::unique_ptr<ConvergenceDetector> detector(
+            ConvergenceDetector::NewFromName(rundata.GetStringDefault("convergence", "maxits")));
+        detector->Initialize(rundata);
+        detector->Describe(prob);
+        if (rundata.GetIntDefault("max-trials", 10) <= 0)
+            throw InvalidOptionValue("max-trials", rundata.GetString("max-trials"), "Must be positive");
+        /* priors (priors.cc:490-528): the factory validates every parameter's prior type and options (image data
+         * present, spatial-dims / speed in range); the types themselves travel in prob.params[] */
+        {
+            std::vector<Prior *> priors = PriorFactory(rundata).CreatePriors(params);
+            for (size_t i = 0; i < priors.size(); i++)
+                delete priors[i];
+        }
     }
-    const bool spatial = IsSpatial(rundata, params);
+    const bool spatial = !m_nlls && IsSpatial(rundata, params);
     const bool useF = !spatial && prob.conv_type != FABBER_CONV_MAXITS;
-    m_needF = useF || m_printF || m_saveF || m_saveFsHistory; /* inference_vb.cc:242 */
+    m_needF = !m_nlls && (useF || m_printF || m_saveF || m_saveFsHistory); /* inference_vb.cc:242 */
     prob.need_f = m_needF ? 1 : 0;
     prob.allow_bad_voxels = m_halt_bad_voxel ? 0 : 1;
     /* F history: worst case per detector - lm never runs more than (max_its + 1) * 14 passes */
@@ -374,6 +442,8 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
     bool continue_from_mvn = false;
     try
     {
+        if (m_nlls) /* continue-from-mvn / output-only are Vb options (inference_vb.cc:181): NLLS never reads them */
+            throw DataNotFound("continue-from-mvn");
         const VoxelData &mvn = rundata.GetVoxelData("continue-from-mvn");
         continue_from_mvn = true;
         const int n_all = P + m_noise_params, n_cov_all = n_all * (n_all + 1) / 2;
@@ -496,7 +566,7 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
                   (size_t)rows, nullptr),
             "copying to the GPU");
     };
-    if (rundata.GetBool("output-only"))
+    if (!m_nlls && rundata.GetBool("output-only"))
     {
         if (!continue_from_mvn)
             throw FabberRunDataError("output-only requires continue-from-mvn");
@@ -518,7 +588,8 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
     }
 
     /* ---- inputs --------------------------------------------------------------------------------------- */
-    m_description = std::string("Vb::") + (spatial ? "Spatial" : "Voxelwise") + " calculations on the GPU: " + stringify(N)
+    m_description = std::string(m_nlls ? "NLLSInferenceTechnique::" : "Vb::") + (spatial ? "Spatial" : "Voxelwise")
+        + " calculations on the GPU: " + stringify(N)
         + " voxels x " + stringify(T) + " time points, " + stringify(P) + " parameters, " + stringify(m_ctx.size())
         + " device" + (m_ctx.size() == 1 ? "" : "s");
     rundata.Log() << m_description << std::endl;
@@ -720,7 +791,8 @@ void Vb::Finish(FabberRunData &rundata)
     {
         const int c = code & 0xff;
         const std::string why = c >= 1 && c <= 6 ? reason[c] : "numerical error";
-        rundata.Log() << "Vb::Internal error for voxel " << first + 1 << " : " << why << std::endl;
+        rundata.Log() << (m_nlls ? "NLLSInferenceTechnique::" : "Vb::") << "Internal error for voxel " << first + 1 << " : "
+                      << why << std::endl;
         if (m_halt_bad_voxel || (code & FABBER_VOX_SETUP_FLAG))
             throw FabberInternalError(why);
         rundata.Log() << "Vb::" << n_bad << " voxels had numerical errors and kept their last state" << std::endl;

@@ -1363,9 +1363,8 @@ void FabberRunData::Run(void (*progress_cb)(int, int))
     }
 
     const std::string method = GetString("method");
-    if (method != "vb" && method != "spatialvb")
-        throw InvalidOptionValue("method", method,
-            "only vb and spatialvb run on the GPU path (nlls and other methods are outside this library)");
+    if (method != "vb" && method != "spatialvb" && method != "nlls") /* setup.cc:28-33 */
+        throw InvalidOptionValue("method", method, "Unrecognized inference method (vb, spatialvb, nlls)");
     /* a run that fabber_set_data started speculatively is adopted if nothing was set since */
     std::unique_ptr<SpeculativeRun> spec = std::move(m_spec);
     if (spec && (spec->version != m_version || m_voxel_data.count("data") == 0 || m_voxel_data["data"].get() != spec->data))

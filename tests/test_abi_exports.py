@@ -46,7 +46,7 @@ def test_struct_mirrors_match():
 def test_registry_names_and_options():
     f = fab.Fabber()
     assert f.get_models() == ["exp", "linear", "poly"]       # setup.cc:44-47 + examples/exp_models.cc
-    assert f.get_methods() == ["spatialvb", "vb"]            # setup.cc:29-30 (nlls is out of scope)
+    assert f.get_methods() == ["nlls", "spatialvb", "vb"]    # setup.cc:28-33
     opts, desc = f.get_options(model="poly")
     assert [o["name"] for o in opts] == ["degree"] and "polynomial" in desc
     opts, _ = f.get_options(method="vb")

@@ -162,7 +162,7 @@ def test_ar_noise_and_error_paths():
                             {"data": volume(y, (nx, ny, nz))})
         # unknown method / missing noise option
         with pytest.raises(fab.FabberException):
-            f.run_with_data({"model": "linear", "basis": basis, "noise": "white", "method": "nlls"},
+            f.run_with_data({"model": "linear", "basis": basis, "noise": "white", "method": "mcmc"},
                             {"data": volume(y, (nx, ny, nz))})
         with pytest.raises(fab.FabberException) as e:
             f.run_with_data({"model": "linear", "basis": basis, "method": "vb"}, {"data": volume(y, (nx, ny, nz))})

@@ -1,0 +1,118 @@
+"""GPU: --method=nlls (inference_nlls.cc) - the CUDA kernel of csrc/vb_nlls.cuh through the C ABI and through the
+reference's C API, against the reference's own golden (test/outdata_linear_nlls) and against the CPU oracle, whose
+restatement of the optimiser (MISCMATHS::nonlin, an FSL library outside the reference tree) is pinned on that golden
+in tests/test_oracle_golden.py."""
+import numpy as np
+import pytest
+
+import oracle
+from fabber_core_b200 import cuda_abi as abi
+from fabber_core_b200 import device, synth
+from fabber_core_b200 import fabber as fab
+from parity import compare, tri
+
+pytestmark = pytest.mark.gpu
+
+
+def both(model, data, variants=("fma",), **kw):
+    T = data.shape[0]
+    kw = dict(kw, method="nlls")
+    ref = oracle.run(abi.ProblemSpec(model, T, **kw), data)
+    probes = [oracle.run(abi.ProblemSpec(model, T, **kw), data, variant=v) for v in variants]
+    truth = oracle.run(abi.ProblemSpec(model, T, **kw), data, variant="ld")
+    gpu = device.run(abi.ProblemSpec(model, T, **kw), data)
+    return gpu, ref, probes, truth
+
+
+def _rel(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def test_linear_nlls_golden(golden):
+    """the reference's shipped regression case: means, z-statistics and the finalMVN (model block only: NLLS has no
+    noise parameters) of test/outdata_linear_nlls"""
+    data, design = golden["data"], golden["design"]
+    out = device.run(abi.ProblemSpec("linear", 106, design=design, method="nlls"), data)
+    assert out["rc"] == 0 and np.all(out["status"] == 0) and np.all(out["iterations"] == 3)
+    gm = np.stack([golden["linear_nlls/mean_Parameter_%d" % (i + 1)][0] for i in range(4)]).astype(np.float64)
+    gz = np.stack([golden["linear_nlls/zstat_Parameter_%d" % (i + 1)][0] for i in range(4)]).astype(np.float64)
+    assert _rel(out["mean"], gm) < 1e-5
+    var = np.stack([out["cov"][tri(i, i)] for i in range(4)])
+    assert _rel(out["mean"] / np.sqrt(var), gz) < 1e-5
+    cov = golden["linear_nlls/finalMVN"].astype(np.float64)[:10]
+    assert np.max(np.abs(out["cov"] - cov) / np.maximum(np.abs(cov), 1e-3)) < 3e-5
+    ref = oracle.run(abi.ProblemSpec("linear", 106, design=design, method="nlls"), data)
+    assert _rel(out["mean"], ref["mean"]) < 1e-9 and np.max(np.abs(out["cov"] - ref["cov"]) / np.maximum(np.abs(ref["cov"]), 1e-3)) < 1e-9
+
+
+@pytest.mark.parametrize("lm", [False, True])
+def test_poly_nlls(lm):
+    y = synth.poly_volume(800, 40, 2, seed=3001).numpy()
+    gpu, ref, probes, truth = both("poly", y, degree=2, nlls_lm=lm)
+    compare(gpu, ref, 3, probes, truth=truth, check_f=False, label="poly NLLS lm=%s" % lm)
+    assert ref["iterations"].min() >= 1
+
+
+@pytest.mark.parametrize("lm", [False, True])
+def test_biexp_nlls(lm):
+    """a genuinely non-linear fit (log-transformed amplitudes and rates): several accepted and refused steps per voxel"""
+    y = synth.biexp_volume(600, 96, 0.02, 0.02, seed=3002).numpy()
+    gpu, ref, probes, truth = both("exp", y, variants=("fma", "ulp"), num_exps=2, dt=0.02, nlls_lm=lm,
+                                   param_overrides={"r2": {"mean": 6.0}}, allow_bad_voxels=True)
+    compare(gpu, ref, 4, probes, truth=truth, check_f=False, label="biexp NLLS lm=%s" % lm, max_ambiguous=0.05)
+    assert ref["iterations"].max() > 3
+
+
+def test_nlls_masked_timepoints_and_start_file():
+    """test/test_inference.cc:485-562 runs masked time points under every method: masked samples count neither in the
+    cost function nor in J'J nor in the degrees of freedom of the mse; fwd-inital-posterior moves the start"""
+    rng = np.random.default_rng(3003)
+    T, N = 30, 200
+    i = np.arange(1, T + 1, dtype=np.float64)[:, None]
+    y = (2.0 + 0.5 * i + 0.01 * i * i + 0.3 * rng.standard_normal((T, N))).astype(np.float32)
+    y[4] += 1000.0
+    y[17] -= 1000.0
+    gpu, ref, probes, truth = both("poly", y, degree=2, masked_timepoints=(5, 18))
+    compare(gpu, ref, 3, probes, truth=truth, check_f=False, label="poly NLLS masked")
+    assert np.all(np.abs(gpu["mean"][1] - 0.5) < 0.1)     # the outliers were ignored
+    unmasked = device.run(abi.ProblemSpec("poly", T, degree=2, method="nlls"), y)
+    assert np.all(np.abs(unmasked["mean"][1] - 0.5) > 0.1)
+    gpu2, ref2, probes2, truth2 = both("poly", y, degree=2, masked_timepoints=(5, 18), nlls_start=[1.0, 1.0, 0.1])
+    compare(gpu2, ref2, 3, probes2, truth=truth2, check_f=False, label="poly NLLS masked, start file")
+
+
+def volume(series, shape):
+    nx, ny, nz = shape
+    return np.ascontiguousarray(series.T.reshape(nz, ny, nx, series.shape[0]).transpose(2, 1, 0, 3))
+
+
+def flat(vol):
+    return vol.reshape(-1, vol.shape[-1], order="F").T if vol.ndim == 4 else vol.reshape(-1, order="F")[None]
+
+
+def test_nlls_through_the_c_api(tmp_path):
+    """method=nlls behind fabber_dorun: no --noise needed, outputs of InferenceTechnique::SaveResults only (no noise
+    maps, no free energy), finalMVN = the model's P(P+1)/2 + P + 1 rows; the reference's own smallest cases
+    (test/test_inference.cc:79-105 one voxel, one sample, one parameter; :353-430 polynomial fit)"""
+    f = fab.Fabber()
+    assert "nlls" in f.get_methods()
+    one = f.run_with_data({"model": "poly", "degree": 0, "method": "nlls", "noise": "white", "print-free-energy": True,
+                           "save-mean": True}, {"data": np.full((1, 1, 1, 1), 7.32, dtype=np.float32)})
+    assert one.data["mean_c0"].shape == (1, 1, 1) and abs(float(one.data["mean_c0"][0, 0, 0]) - 7.32) < 1e-6
+    nx, ny, nz, T = 5, 4, 3, 10
+    n = nx * ny * nz
+    rng = np.random.default_rng(3004)
+    i = np.arange(1, T + 1, dtype=np.float64)[:, None]
+    y = (7.32 + 0.5 * i - 0.1 * i * i + 0.0 * rng.standard_normal((T, n))).astype(np.float32)
+    run = f.run_with_data({"model": "poly", "degree": 2, "method": "nlls", "save-mean": True, "save-std": True,
+                           "save-zstat": True, "save-mvn": True, "save-model-fit": True, "save-residuals": True,
+                           "save-noise-mean": True, "save-free-energy": True}, {"data": volume(y, (nx, ny, nz))})
+    assert sorted(run.data.keys()) == sorted(["mean_c0", "mean_c1", "mean_c2", "std_c0", "std_c1", "std_c2", "zstat_c0",
+                                              "zstat_c1", "zstat_c2", "finalMVN", "modelfit", "residuals"])
+    assert run.data["finalMVN"].shape[-1] == 3 * 4 // 2 + 3 + 1
+    assert np.allclose(run.data["mean_c0"], 7.32, atol=1e-3) and np.allclose(run.data["mean_c1"], 0.5, atol=1e-3)
+    assert np.allclose(run.data["mean_c2"], -0.1, atol=1e-4)
+    assert np.max(np.abs(flat(run.data["modelfit"]) - y)) < 1e-3
+    ref = oracle.run(abi.ProblemSpec("poly", T, degree=2, method="nlls"), y)
+    assert np.max(np.abs(flat(run.data["mean_c1"])[0] - ref["mean"][1])) < 1e-5
+    assert "NLLSInferenceTechnique::" in run.log

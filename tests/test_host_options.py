@@ -28,7 +28,8 @@ def run(extra):
     ({"noise": "pink"}, ("noise", "Unrecognized noise model")),
     ({"prior-noise-stddev": "-2"}, ("prior-noise-stddev", "Must be > 0")),
     ({"model": "nosuch"}, ("model", "Unrecognized forward model")),
-    ({"method": "nlls"}, ("method", "nlls")),
+    ({"method": "mcmc"}, ("method", "Unrecognized inference method")),
+    ({"method": "nlls", "fwd-inital-posterior": "/nonexistent/file.mat"}, ("Could not read matrix file",)),
     ({"degree": "-1"}, ("degree", "Minimum 0")),
     ({"max-iterations": "0"}, ("max-iterations", "Must be positive")),
     ({"method": "spatialvb", "param-spatial-priors": "M+", "spatial-dims": "4"}, ("spatial-dims", "Must be 0, 1, 2 or 3")),
