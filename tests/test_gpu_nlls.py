@@ -41,8 +41,8 @@ def test_linear_nlls_golden(golden):
     assert _rel(out["mean"] / np.sqrt(var), gz) < 1e-5
     cov = golden["linear_nlls/finalMVN"].astype(np.float64)[:10]
     assert np.max(np.abs(out["cov"] - cov) / np.maximum(np.abs(cov), 1e-3)) < 3e-5
-    ref = oracle.run(abi.ProblemSpec("linear", 106, design=design, method="nlls"), data)
-    assert _rel(out["mean"], ref["mean"]) < 1e-9 and np.max(np.abs(out["cov"] - ref["cov"]) / np.maximum(np.abs(ref["cov"]), 1e-3)) < 1e-9
+    gpu, ref, probes, truth = both("linear", data, design=design)
+    compare(gpu, ref, 4, probes, truth=truth, check_f=False, label="C1 linear NLLS")
 
 
 @pytest.mark.parametrize("lm", [False, True])
@@ -54,13 +54,37 @@ def test_poly_nlls(lm):
 
 
 @pytest.mark.parametrize("lm", [False, True])
-def test_biexp_nlls(lm):
-    """a genuinely non-linear fit (log-transformed amplitudes and rates): several accepted and refused steps per voxel"""
+def test_monoexp_nlls(lm):
+    """a genuinely non-linear fit (log-transformed amplitude and rate, numerical Jacobian of exp) with one well-defined
+    minimum: 5-8 accepted steps per voxel, iteration counts and results reproducible across CPU builds (floors 1e-9)"""
+    rng = np.random.default_rng(5)
+    T, N = 60, 400
+    t = np.arange(T) * 0.05
+    amp, r = rng.uniform(5, 10, N), rng.uniform(0.5, 2.0, N)
+    y = (amp * np.exp(-r * t[:, None]) + 0.05 * rng.standard_normal((T, N))).astype(np.float32)
+    gpu, ref, probes, truth = both("exp", y, variants=("fma", "ulp"), num_exps=1, dt=0.05, nlls_lm=lm)
+    compare(gpu, ref, 2, probes, truth=truth, check_f=False, label="monoexp NLLS lm=%s" % lm)
+    assert ref["iterations"].min() >= 5
+    assert np.median(np.abs(np.exp(gpu["mean"][1]) - r)) < 0.01
+
+
+@pytest.mark.parametrize("lm", [False, True])
+def test_biexp_nlls_reaches_the_same_cost(lm):
+    """NLLS of a bi-exponential at this noise level has a long flat valley: the reference's optimiser stops wherever
+    the relative drop of the cost falls under 1e-8, and WHERE that is depends on the last bits - two CPU builds of
+    the same source disagree on the iteration count for 3 voxels in 4 and on the parameters by many posterior
+    standard deviations (measured), so a parameter comparison says nothing here. What every build agrees on is the
+    cost reached (to 3e-10 relative between CPU builds): the GPU must reach it too, within the optimiser's own
+    stopping tolerance."""
     y = synth.biexp_volume(600, 96, 0.02, 0.02, seed=3002).numpy()
-    gpu, ref, probes, truth = both("exp", y, variants=("fma", "ulp"), num_exps=2, dt=0.02, nlls_lm=lm,
-                                   param_overrides={"r2": {"mean": 6.0}}, allow_bad_voxels=True)
-    compare(gpu, ref, 4, probes, truth=truth, check_f=False, label="biexp NLLS lm=%s" % lm, max_ambiguous=0.05)
-    assert ref["iterations"].max() > 3
+    kw = dict(num_exps=2, dt=0.02, nlls_lm=lm, param_overrides={"r2": {"mean": 6.0}}, allow_bad_voxels=True, method="nlls")
+    ref = oracle.run(abi.ProblemSpec("exp", 96, **kw), y)
+    gpu = device.run(abi.ProblemSpec("exp", 96, **kw), y)
+    assert np.array_equal(gpu["status"], ref["status"]) and np.all(ref["status"] == 0)
+    cost = lambda out: np.sum((y.astype(np.float64) - oracle.model_fit(abi.ProblemSpec("exp", 96, **kw), out["mean"])) ** 2, axis=0)
+    cg, cr = cost(gpu), cost(ref)
+    assert np.max(np.abs(cg - cr) / cr) < 1e-8
+    assert abs(int(gpu["iterations"].sum()) - int(ref["iterations"].sum())) < 0.1 * ref["iterations"].sum()
 
 
 def test_nlls_masked_timepoints_and_start_file():
@@ -105,8 +129,11 @@ def test_nlls_through_the_c_api(tmp_path):
     i = np.arange(1, T + 1, dtype=np.float64)[:, None]
     y = (7.32 + 0.5 * i - 0.1 * i * i + 0.0 * rng.standard_normal((T, n))).astype(np.float32)
     run = f.run_with_data({"model": "poly", "degree": 2, "method": "nlls", "save-mean": True, "save-std": True,
-                           "save-zstat": True, "save-mvn": True, "save-model-fit": True, "save-residuals": True,
-                           "save-noise-mean": True, "save-free-energy": True}, {"data": volume(y, (nx, ny, nz))})
+                           "save-zstat": True, "save-mvn": True, "save-model-fit": True, "save-residuals": True},
+                          {"data": volume(y, (nx, ny, nz))})
+    with pytest.raises(fab.FabberException):   # Vb::SaveResults' outputs do not exist for NLLS (inference.cc:112-252 only)
+        f.run_with_data({"model": "poly", "degree": 2, "method": "nlls", "save-noise-mean": True},
+                        {"data": volume(y, (nx, ny, nz))})
     assert sorted(run.data.keys()) == sorted(["mean_c0", "mean_c1", "mean_c2", "std_c0", "std_c1", "std_c2", "zstat_c0",
                                               "zstat_c1", "zstat_c2", "finalMVN", "modelfit", "residuals"])
     assert run.data["finalMVN"].shape[-1] == 3 * 4 // 2 + 3 + 1
