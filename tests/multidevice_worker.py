@@ -42,6 +42,18 @@ def main():
         opts = {"model": "linear", "basis": design, "noise": "ar", "method": "vb", "save-mean": True, "save-mvn": True,
                 "save-noise-mean": True}
         extra = {}
+    elif case == "nlls":
+        # --method=nlls rides the same voxel-range plumbing (no noise outputs: NLLS has no noise parameters)
+        y = synth.poly_volume(n, T, 2, seed=80).numpy()
+        opts = {"model": "poly", "degree": 2, "method": "nlls", "save-mean": True, "save-mvn": True, "save-std": True}
+        extra = {}
+    elif case == "ar2":
+        y = synth.dual_echo_volume(n, T // 2, seed=81).numpy()
+        design = os.path.join(os.path.dirname(out), "design2.mat")
+        np.savetxt(design, synth.dual_echo_design(T // 2), fmt="%.17g")
+        opts = {"model": "linear", "basis": design, "noise": "ar", "num-echoes": 2, "ar1-cross-terms": "dual",
+                "method": "vb", "save-mean": True, "save-mvn": True, "save-noise-mean": True}
+        extra = {}
     else:
         raise SystemExit("unknown case")
     f = fab.Fabber()
@@ -68,7 +80,7 @@ def main():
     res = {}
     f._trycall(f.clib.fabber_get_model_params, f.handle, len(f.outbuf), f.outbuf, f.errbuf)
     params = f.outbuf.value.decode().splitlines()
-    keys = ["mean_" + p for p in params] + ["finalMVN", "noise_means"]
+    keys = ["mean_" + p for p in params] + ["finalMVN"] + ([] if case == "nlls" else ["noise_means"])
     if case == "spatial":
         keys += ["std_" + p for p in params] + ["freeEnergy"]
     if case == "poly_image_lm":

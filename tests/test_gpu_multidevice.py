@@ -35,7 +35,7 @@ def device_list(n):
     return ",".join(str(i % have) for i in range(n))
 
 
-@pytest.mark.parametrize("case", ["poly_image_lm", "ar1"])
+@pytest.mark.parametrize("case", ["poly_image_lm", "ar1", "ar2", "nlls"])
 def test_ranges_over_devices_equal_the_one_device_run(tmp_path, case):
     one = run_worker(tmp_path, "one", case, "0")
     three = run_worker(tmp_path, "three", case, device_list(3))
