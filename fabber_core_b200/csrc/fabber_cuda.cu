@@ -857,6 +857,18 @@ int fabber_cuda_vb_voxelwise_range(const fabber_cuda_vb_problem *prob, const fab
     }
     a.v_begin = v_begin;
     a.v_end = v_end;
+    if (prob->method == FABBER_METHOD_NLLS && buf->noise && v_end > v_begin)
+    {
+        /* NLLS has no noise parameters: the two rows a white-noise caller allocates read as zeros, not as whatever
+         * the allocation held */
+        cudaError_t ez = cudaMemset2DAsync(buf->noise + v_begin, (size_t)prob->n_voxels * sizeof(double), 0,
+            (size_t)(v_end - v_begin) * sizeof(double), 2, s);
+        if (ez != cudaSuccess)
+        {
+            st.release(s);
+            return cuda_fail(ez, "cudaMemset2DAsync(noise)");
+        }
+    }
     cudaError_t e = fn(a, s);
     st.release(s);
     if (e != cudaSuccess)

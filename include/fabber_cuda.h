@@ -156,8 +156,9 @@ typedef struct fabber_cuda_vb_problem
     int nx, ny, nz; /* bounding grid of the coords, used for neighbour search */
 
     /* inference technique (setup.cc:28-33). FABBER_METHOD_NLLS (inference_nlls.cc): non-linear least squares per
-     * voxel through the same entry points; noise / priors / convergence fields are ignored, the noise, free_energy
-     * and f_history result arrays are not written, `iterations` holds the optimiser's successful steps. */
+     * voxel through the same entry points; noise / priors / convergence fields are ignored, the noise result array
+     * (2 rows) is zeroed, free_energy and f_history are not written, `iterations` holds the optimiser's accepted
+     * steps. */
     int method;          /* FABBER_METHOD_* */
     int nlls_lm;         /* --lm: Levenberg-Marquardt damping, else Levenberg (inference_nlls.cc:86,135-139) */
     int nlls_have_start; /* fwd-inital-posterior given: start from nlls_start (Fabber space) */
