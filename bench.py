@@ -746,6 +746,48 @@ def reference_arm(args, metric):
     return 0
 
 
+def extra_kernels(torch):
+    """Device-resident rates of the kernels outside BASELINE.json's five configurations (two-echo AR(1), NLLS), on
+    2^20 voxels each: reported beside the sub-records, not part of the headline."""
+    from fabber_core_b200 import cuda_abi as abi
+    from fabber_core_b200 import device, synth
+
+    def timed(spec, y, reps=3):
+        run = device.VbRun(spec, y.shape[1])
+        run.set_data_device(y.data_ptr())
+        st = torch.cuda.current_stream().cuda_stream
+        device.check(run.launch(st), "extra kernel")
+        torch.cuda.synchronize()
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+        ev[0].record()
+        for _ in range(reps):
+            device.check(run.launch(st), "extra kernel")
+        ev[1].record()
+        torch.cuda.synchronize()
+        res = run.results()
+        run.close()
+        ms = ev[0].elapsed_time(ev[1]) / reps
+        return {"value": float(res["iterations"].sum()) / ms * 1e3, "unit": "voxel-iterations/s", "ms_per_step": ms,
+                "voxels": int(y.shape[1]), "bad_voxels": int((res["status"] != 0).sum())}
+
+    n = 1 << 20
+    out = {}
+    y = synth.dual_echo_volume(n, 100, seed=5, device="cuda")
+    design = synth.dual_echo_design(100)
+    for cross in ("none", "dual"):
+        r = timed(abi.ProblemSpec("linear", 200, design=design, noise="ar", num_echoes=2, ar_cross_terms=cross,
+                                  need_f=True), y)
+        r["workload"] = "linear(200x3) VB AR(1) num-echoes=2 ar1-cross-terms=%s, maxits 10" % cross
+        out["ar1_two_echoes_" + cross] = r
+    del y
+    y = synth.biexp_volume(n, 96, 0.02, 0.02, seed=1003, device="cuda")
+    r = timed(abi.ProblemSpec("exp", 96, num_exps=2, dt=0.02, method="nlls", allow_bad_voxels=True,
+                              param_overrides={"r2": {"mean": 6.0}}), y)
+    r["workload"] = "exp(num-exps 2) method=nlls (Levenberg); iterations = accepted steps"
+    out["nlls_biexp"] = r
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -826,6 +868,8 @@ def main():
                                         % (pn, pdt)}
         if subs:
             line["sub"] = subs
+            if world == 1:
+                line["extra_kernels"] = extra_kernels(torch)
         print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist

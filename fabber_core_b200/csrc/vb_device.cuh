@@ -46,6 +46,17 @@ namespace fab
 #endif
 #define FAB_CHECK_INDEX(args, idx, n, code) FAB_CHECK(args, (long long)(idx) >= 0 && (long long)(idx) < (long long)(n), code)
 
+/* Pull one line of the voxel series into L2 well ahead of its use. The time loops prefetch three samples into
+ * registers, which covers an L2 hit but not a DRAM miss: with one pass per launch (sp_setup, sp_noise) the series
+ * streams from HBM, and ncu showed 54 % of sp_noise's stall samples on the
+ * consumer of that load (long scoreboard, FP64 pipe 59 % active; profiles/r2n_ncu_full_c5_noise.txt). No register
+ * cost, one instruction per sample. */
+#ifndef FAB_L2_AHEAD
+#define FAB_L2_AHEAD 8
+#endif
+constexpr int FAB_L2_PREFETCH_AHEAD = FAB_L2_AHEAD;
+FAB_DEV void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
 /* packed lower triangle by rows: (0,0),(1,0),(1,1),(2,0).. - the order of MVNDist::Save */
 __host__ __device__ constexpr int tri(int i, int j)
 {

@@ -214,7 +214,7 @@ template <class Model> __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCK
 #pragma unroll
     for (int i = 0; i < P; i++)
         c[i] = a.lock_centre ? a.lock_centre[i * N + v] : m[i]; /* inference_vb.cc:227-236 */
-    const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, c, S);
+    const int err = recentre_stats<Model, 1, true>(a, mc, nullptr, v, c, S);
     if (err)
         status = err | FABBER_VOX_SETUP_FLAG;
 #pragma unroll
@@ -889,7 +889,7 @@ __global__ void __launch_bounds__(VB_BLOCK, FAB_MIN_BLOCKS) sp_noise_kernel(cons
             for (int i = 0; i < NT; i++)
                 park[(k++) * VB_BLOCK] = Sig[i];
         }
-        const int err = recentre_stats<Model, 1>(a, mc, nullptr, v, m, S);
+        const int err = recentre_stats<Model, 1, true>(a, mc, nullptr, v, m, S);
         {
             int k = 0;
 #pragma unroll

@@ -139,7 +139,7 @@ template <int P> struct Stats
  * 23 + P FP64 instructions per sample instead of 54 at P = 4. The results stay inside the reference's own
  * noise floor (same parity rule, same tests). OPT-IN (FABBER_B200_BASIS_JACOBIAN=1): the default is the reference's
  * literal 2P+1 evaluations per sample. */
-template <class Model, int NPHI, int FAST, bool CHECK, bool BASIS>
+template <class Model, int NPHI, int FAST, bool CHECK, bool BASIS, bool COLD>
 FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
     const double (&p0)[Model::P], const double (&pp)[Model::P], const double (&pn)[Model::P],
     const double (&rden)[Model::P], Stats<Model::P> (&S)[NPHI], bool &bad_g, bool &bad_j)
@@ -160,6 +160,16 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
         q2 = __ldg(yp + 2 * stride);
     typename Model::Sample smp;
     Model::sample(mc, 0, smp);
+    /* COLD: a pass whose series comes from HBM (one pass per launch: the spatial kernels) also pulls it into L2
+     * well ahead. The voxelwise kernels run ~10 passes per launch over a series that stays in L2 after the first:
+     * there the extra instruction per sample cost 1-4 % (measured), so they do not. */
+    if (COLD)
+    {
+#pragma unroll
+        for (int k = 3; k < FAB_L2_PREFETCH_AHEAD; k++)
+            if (k < a.T)
+                prefetch_l2(yp + (size_t)k * stride);
+    }
 #pragma unroll 1
     for (int t = 0; t < a.T; t++)
     {
@@ -168,6 +178,8 @@ FAB_DEV void recentre_loop(const VbArgs &a, const typename Model::Ctx &mc, const
         q1 = q2;
         if (t + 3 < a.T)
             q2 = __ldg(yp + (size_t)(t + 3) * stride);
+        if (COLD && t + FAB_L2_PREFETCH_AHEAD < a.T)
+            prefetch_l2(yp + (size_t)(t + FAB_L2_PREFETCH_AHEAD) * stride);
         /* the next sample's model-side constants (poly: integer powers -> double, a long-latency conversion)
          * are formed one sample ahead */
         typename Model::Sample nxt;
@@ -236,7 +248,7 @@ FAB_DEV void recentre_diagnose(const VbArgs &a, const typename Model::Ctx &mc, c
  * exactly where the reference throws (offset checked before the Jacobian, fwdmodel_linear.cc:134,174).
  * NPHI == 1: single phi, no masked samples (fast path). NPHI > 1: `pat` gives the phi per sample.
  */
-template <class Model, int NPHI>
+template <class Model, int NPHI, bool COLD = false>
 FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const unsigned char *pat, int v,
     const double (&c)[Model::P], Stats<Model::P> (&S)[NPHI])
 {
@@ -271,12 +283,12 @@ FAB_DEV int recentre_stats(const VbArgs &a, const typename Model::Ctx &mc, const
     if (basis)
     {
         if constexpr (Model::LINEAR)
-            recentre_loop<Model, NPHI, 0, CHECK, true>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+            recentre_loop<Model, NPHI, 0, CHECK, true, COLD>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     }
     else if (fast)
-        recentre_loop<Model, NPHI, 1, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop<Model, NPHI, 1, CHECK, false, COLD>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     else
-        recentre_loop<Model, NPHI, 0, CHECK, false>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
+        recentre_loop<Model, NPHI, 0, CHECK, false, COLD>(a, mc, pat, v, p0, pp, pn, rden, S, bad_g, bad_j);
     if (!CHECK)
     {
         bool sums_finite = finite_d(S[0].rr);

@@ -307,3 +307,14 @@ def test_speculative_start_is_adopted_only_when_nothing_changed(monkeypatch):
     assert ADOPT in log
     for k in ref_img:
         assert np.array_equal(got[k], ref_img[k], equal_nan=True), k
+
+
+@pytest.mark.parametrize("method", ["vb", "nlls", "spatialvb"])
+def test_no_voxels_is_not_an_error(method):
+    """test/test_inference.cc:57-73 (NoVoxels, run for every method): an empty mask runs through and yields empty maps"""
+    nx, ny, nz, T = 3, 2, 2, 10
+    f = fab.Fabber()
+    data = np.ones((nx, ny, nz, T), dtype=np.float32)
+    run = f.run_with_data({"model": "poly", "degree": 1, "noise": "white", "method": method, "save-mean": True},
+                          {"data": data}, mask=np.zeros((nx, ny, nz), dtype=np.int32))
+    assert run.data["mean_c0"].shape == (nx, ny, nz) and not np.any(run.data["mean_c0"])
