@@ -39,8 +39,8 @@ WORKLOADS = {
     "c2": dict(name="C2 poly(degree 3) VB white noise, synthetic 128^3 x 64, maxits 10", side=128, T=64,
                model="poly", spec=dict(degree=3), P=4, kind="poly",
                capi={"model": "poly", "degree": 3, "noise": "white", "method": "vb", "max-iterations": 10},
-               ncu=dict(fp64_active=0.780, traffic=538.487808e6 + 273.267968e6,
-                        source="profiles/r1b_ncu_full_c2_poly4.txt")),
+               ncu=dict(fp64_active=0.758, traffic=537.313536e6 + 272.282112e6,
+                        source="profiles/r2n_ncu_full_c2.txt")),
     # BASELINE.json configs[2]: biexp VB, LM convergence, synthetic 256^3 x 96
     # (prior mean 6 on r2 via PSP_byname: with the default symmetric priors the reference's own fit is
     #  chaotic - see DESIGN.md "C3"; the default-prior run is timed too and reported as `default_priors`)
@@ -57,7 +57,7 @@ WORKLOADS = {
     "c4": dict(name="C4 linear(200x4 design) VB AR(1) noise (num-echoes 1, cross-terms none), synthetic "
                     "256^3 x 200, maxits 10", side=256, T=200, model="linear", spec=dict(noise="ar"), P=4, kind="ar",
                capi={"model": "linear", "basis": "@design", "noise": "ar", "method": "vb", "max-iterations": 10},
-               ncu=dict(fp64_active=0.71, traffic=None, source="profiles/r1_ncu_full_c4_linear4_ar1.txt")),
+               ncu=dict(fp64_active=0.744, traffic=16.546807e9 + 6.548900e9, source="profiles/r2n_ncu_full_c4.txt")),
     # BASELINE.json configs[4]: spatialvb (MRF spatial prior 'M' on every parameter), biexp, smooth synthetic
     # 256^3 x 96. NB the reference's CovarianceCache is dead code; the MRF prior is
     # SpatialPrior in priors.cc.
@@ -69,7 +69,10 @@ WORKLOADS = {
                capi={"model": "exp", "num-exps": 2, "dt": 0.02, "noise": "white", "method": "spatialvb",
                      "param-spatial-priors": "M+", "max-iterations": 10, "PSP_byname1": "r2",
                      "PSP_byname1_mean": 6.0},
-               ncu=dict(fp64_active=None, traffic=None, source=None)),
+               # the dominant kernel of a spatial run is sp_noise (58 % of the step): its capture, per launch (= one of the
+               # ten iterations); the step as a whole also runs sp_sweep / sp_theta / sp_ak_*
+               ncu=dict(fp64_active=0.743, traffic=None, source="profiles/r2o_ncu_full_c5_noise.txt",
+                        sp_noise_traffic_per_launch=10.939664e9 + 2.865362e9)),
 }
 
 
