@@ -52,16 +52,25 @@ template <int P_> struct LinearModel
     {
         const double *design;
     };
-    static __host__ __device__ size_t smem_bytes(int T) { return (size_t)T * P * sizeof(double); }
+    /* a design too long for shared memory next to the kernels' parked state (> 64 KB: T P > 8192) is read from
+     * global memory instead - every thread of a warp reads the same row, so it is one broadcast load from L1 / L2 */
+    static constexpr size_t STAGE_MAX_BYTES = 64 * 1024;
+    static __host__ __device__ size_t smem_bytes(int T)
+    {
+        const size_t b = (size_t)T * P * sizeof(double);
+        return b <= STAGE_MAX_BYTES ? b : 0;
+    }
     template <class Args> static FAB_DEV void stage(const Args &a, double *smem)
     {
+        if (smem_bytes(a.T) == 0)
+            return;
         for (int i = threadIdx.x; i < a.T * P; i += blockDim.x)
             smem[i] = a.design[i];
     }
-    template <class Args> static FAB_DEV Ctx make_ctx(const Args &, double *smem)
+    template <class Args> static FAB_DEV Ctx make_ctx(const Args &a, double *smem)
     {
         Ctx c;
-        c.design = smem;
+        c.design = smem_bytes(a.T) ? smem : a.design;
         return c;
     }
     static FAB_DEV double eval(const Ctx &c, int t, const double (&p)[P])

@@ -350,3 +350,28 @@ def test_basis_jacobian_option_stays_inside_the_parity_rule(case, golden, monkey
     compare(basis, ref, P, probes, check_f="need_f" in kw, label="basis jacobian %s" % case)
     assert np.mean(basis["iterations"] != default["iterations"]) < 0.01  # a voxel may sit on a detector threshold
     assert not np.array_equal(basis["mean"], default["mean"])
+
+
+@pytest.mark.parametrize("noise", ["white", "ar"])
+def test_linear_design_too_long_for_shared_memory(noise):
+    """3000 samples x 4 columns = 96 KB of design: more than the kernels stage in shared memory next to their parked
+    state, so the rows are read from global memory (one broadcast load per warp) - same arithmetic, same result"""
+    rng = np.random.default_rng(31)
+    T, N = 3000, 96
+    t = np.arange(T, dtype=np.float64)
+    design = np.stack([np.ones(T), t / T, np.sin(2 * np.pi * t / 50), np.cos(2 * np.pi * t / 300)], axis=1)
+    beta = rng.standard_normal((4, N)) * 50
+    y = (design @ beta + rng.standard_normal((T, N))).astype(np.float32)
+    gpu, ref, probes = both(dict(model="linear", design=design, noise=noise, need_f=True, max_iterations=4), y)
+    compare(gpu, ref, 4, probes, truth=probes.truth, label="linear, 3000-sample design, %s" % noise)
+
+
+def test_six_parameter_models():
+    """the widest hooks compiled (P = 6): 21-element packed covariance, 168-register kernels with the state parked"""
+    rng = np.random.default_rng(32)
+    T, N = 120, 256
+    design = rng.standard_normal((T, 6))
+    y = (design @ (rng.standard_normal((6, N)) * 10) + rng.standard_normal((T, N))).astype(np.float32)
+    for noise in ("white", "ar"):
+        gpu, ref, probes = both(dict(model="linear", design=design, noise=noise, need_f=True, convergence="pointzeroone"), y)
+        compare(gpu, ref, 6, probes, truth=probes.truth, label="linear P6 %s" % noise)
