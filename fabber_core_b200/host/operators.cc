@@ -8,6 +8,8 @@
 
 #include "operators.h"
 
+#include <memory>
+
 namespace fabber_b200
 {
 /* ---- MVNDist ----------------------------------------------------------------------------------------- */
@@ -542,6 +544,39 @@ void Ar1cNoiseModel::Describe(fabber_cuda_vb_problem &prob, int n_times, std::ve
         prob.noise_post_c[i] = post.phis[i].c;
     }
     prob.ar_alpha_prior_prec = prior.alpha.GetPrecisions(0, 0);
+}
+
+/* ---- inference techniques ---------------------------------------------------------------------------------------- */
+std::vector<std::string> InferenceTechnique::GetKnown() { return Vb::GetKnownMethods(); }
+InferenceTechnique *InferenceTechnique::NewFromName(const std::string &name)
+{
+    if (name == "vb" || name == "spatialvb")
+        return new VariationalBayesInferenceTechnique();
+    if (name == "nlls")
+        return new NLLSInferenceTechnique();
+    throw InvalidOptionValue("method", name, "Unrecognized inference method (vb, spatialvb, nlls)");
+}
+void InferenceTechnique::UsageFromName(const std::string &name, std::ostream &stream)
+{
+    std::unique_ptr<InferenceTechnique> t(NewFromName(name));
+    stream << "Usage information for method: " << name << std::endl << std::endl;
+    stream << t->GetDescription() << std::endl << std::endl << "Options: " << std::endl << std::endl;
+    std::vector<OptionSpec> options;
+    t->GetOptions(options);
+    for (size_t i = 0; i < options.size(); i++)
+        stream << "  --" << options[i].name << (options[i].optional ? " [optional]" : "") << ": " << options[i].description
+               << std::endl;
+}
+std::string InferenceTechnique::GetVersion() const { return "fabber_core_b200"; }
+void InferenceTechnique::Initialize(FwdModel *fwd_model, FabberRunData &args) { m_engine.Initialize(fwd_model, args); }
+void InferenceTechnique::DoCalculations(FabberRunData &rundata) { m_engine.DoCalculations(rundata); }
+void InferenceTechnique::SaveResults(FabberRunData &rundata) { m_engine.SaveResults(rundata); }
+void NLLSInferenceTechnique::Initialize(FwdModel *fwd_model, FabberRunData &args)
+{
+    if (args.GetStringDefault("method", "nlls") != "nlls")
+        throw InvalidOptionValue("method", args.GetString("method"), "NLLSInferenceTechnique runs method=nlls");
+    args.Set("method", "nlls");
+    InferenceTechnique::Initialize(fwd_model, args);
 }
 
 /* ---- priors --------------------------------------------------------------------------------------------------- */

@@ -19,6 +19,7 @@
  * - there is no CPU inference path in this library - and say so if called.
  */
 #pragma once
+#include <ostream>
 #include <string>
 #include <vector>
 
@@ -145,6 +146,41 @@ public:
 protected:
     double m_alpha = 0, m_alphastart = 1e-6, m_alphamax = 1e6;
     bool m_LM = false;
+};
+
+/* ---- inference techniques (inference.h:22-166, registry names of setup.cc:28-33) --------------------------------
+ * Same factory and virtuals as the reference. All three names run on the device behind one engine (class Vb of
+ * fabber_host.h: block-wise upload, one voxel range or z-slab per GPU, device-side SaveResults); "vb" / "spatialvb"
+ * are the reference's Vb, "nlls" its NLLSInferenceTechnique (csrc/vb_nlls.cuh). */
+class InferenceTechnique
+{
+public:
+    static std::vector<std::string> GetKnown();                      /* nlls, spatialvb, vb */
+    static InferenceTechnique *NewFromName(const std::string &name); /* throws InvalidOptionValue("method", ..) */
+    static void UsageFromName(const std::string &name, std::ostream &stream);
+    virtual ~InferenceTechnique() {}
+    virtual void GetOptions(std::vector<OptionSpec> &opts) const = 0;
+    virtual std::string GetDescription() const = 0;
+    virtual std::string GetVersion() const;
+    virtual void Initialize(FwdModel *fwd_model, FabberRunData &args);
+    virtual void DoCalculations(FabberRunData &rundata);
+    virtual void SaveResults(FabberRunData &rundata);
+
+protected:
+    Vb m_engine;
+};
+class VariationalBayesInferenceTechnique : public InferenceTechnique /* "vb", "spatialvb": inference_vb.h */
+{
+public:
+    void GetOptions(std::vector<OptionSpec> &opts) const override { Vb::GetOptions(opts, "vb"); }
+    std::string GetDescription() const override { return Vb::GetDescription("vb"); }
+};
+class NLLSInferenceTechnique : public InferenceTechnique /* "nlls": inference_nlls.h */
+{
+public:
+    void GetOptions(std::vector<OptionSpec> &opts) const override { Vb::GetOptions(opts, "nlls"); }
+    std::string GetDescription() const override { return Vb::GetDescription("nlls"); }
+    void Initialize(FwdModel *fwd_model, FabberRunData &args) override; /* insists on method=nlls in args */
 };
 
 /* ---- noise models (noisemodel.h) ------------------------------------------------------------------------- */

@@ -27,6 +27,7 @@
 #include <unistd.h>
 
 #include "fabber_host.h"
+#include "operators.h"
 
 namespace fabber_b200
 {
@@ -1378,10 +1379,10 @@ void FabberRunData::Run(void (*progress_cb)(int, int))
     }
     else
     {
-        Vb vb;
-        vb.Initialize(fwd_model.get(), *this);
-        vb.DoCalculations(*this);
-        vb.SaveResults(*this);
+        std::unique_ptr<InferenceTechnique> infer(InferenceTechnique::NewFromName(method)); /* fabber_core.cc:258 */
+        infer->Initialize(fwd_model.get(), *this);
+        infer->DoCalculations(*this);
+        infer->SaveResults(*this);
     }
     time_t end;
     time(&end);

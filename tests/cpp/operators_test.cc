@@ -315,8 +315,41 @@ static void test_deprecated_fwdmodel_api()
     CHECK(out.size() == 4 && out[0] == 1.0 && out[3] == 7.0);
 }
 
+/* inference.h:22-166, setup.cc:28-33, test/test_inference.cc:50-55 (CanCreate for every method) */
+static void test_inference_techniques()
+{
+    std::vector<std::string> known = InferenceTechnique::GetKnown();
+    CHECK(known.size() == 3 && known[0] == "nlls" && known[1] == "spatialvb" && known[2] == "vb");
+    for (size_t i = 0; i < known.size(); i++)
+    {
+        std::unique_ptr<InferenceTechnique> t(InferenceTechnique::NewFromName(known[i]));
+        CHECK(t.get() != nullptr && !t->GetDescription().empty());
+        std::vector<OptionSpec> opts;
+        t->GetOptions(opts);
+        bool has_noise = false, has_lm = false;
+        for (size_t k = 0; k < opts.size(); k++)
+        {
+            has_noise = has_noise || opts[k].name == "noise";
+            has_lm = has_lm || opts[k].name == "lm";
+        }
+        CHECK(has_noise == (known[i] != "nlls") && has_lm == (known[i] == "nlls"));
+    }
+    CHECK(dynamic_cast<NLLSInferenceTechnique *>(std::unique_ptr<InferenceTechnique>(InferenceTechnique::NewFromName("nlls")).get()));
+    bool threw = false;
+    try
+    {
+        InferenceTechnique::NewFromName("mcmc");
+    }
+    catch (InvalidOptionValue &)
+    {
+        threw = true;
+    }
+    CHECK(threw);
+}
+
 int main()
 {
+    test_inference_techniques();
     test_deprecated_fwdmodel_api();
     test_maxits();
     test_fchange();
