@@ -54,6 +54,7 @@ namespace fab
  * spin has a cycle budget and reports through `error` instead of hanging the GPU. */
 constexpr int SLAB_MAX_WORLD = 16;
 constexpr unsigned long long SLAB_IT_STRIDE = 1ull << 20; /* FWD flag = it * stride + hyper-planes done */
+constexpr int SLAB_PUBLISH_EVERY = 4; /* the sweep publishes "planes done" to the slab above every so many planes */
 enum
 {
     SLAB_FLAG_FWD = 0, /* written by the slab below */
@@ -89,10 +90,11 @@ FAB_DEV void st_release_sys(unsigned long long *p, unsigned long long v)
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 /* spin until *flag >= want; ~2 s budget (a dead peer must not hang the GPU: gpurun counts that as a strike) */
-FAB_DEV void slab_wait(const unsigned long long *flag, unsigned long long want, int *error)
+FAB_DEV unsigned long long slab_wait(const unsigned long long *flag, unsigned long long want, int *error)
 {
     const long long t0 = clock64();
-    while (ld_acquire_sys(flag) < want)
+    unsigned long long seen;
+    while ((seen = ld_acquire_sys(flag)) < want)
     {
         /* once any wait of this slab has given up, none waits again: the run is lost, end it quickly */
         if (*(volatile int *)error != 0)
@@ -104,6 +106,7 @@ FAB_DEV void slab_wait(const unsigned long long *flag, unsigned long long want, 
         }
         __nanosleep(64);
     }
+    return seen; /* >= want unless the wait gave up */
 }
 
 struct SpArgs
@@ -685,7 +688,11 @@ template <int P, bool IGNORE, bool SLAB> struct SweepVoxel
 #pragma unroll
                 for (int i = 0; i < P; i++)
                     s.link.up_mean[(size_t)i * s.link.up_N + up] = mn[i];
-                __threadfence_system(); /* ordered before this plane's barrier and the flag behind it */
+                /* no fence here: these stores are ordered before the flag the way NCCL orders its data before a
+                 * step flag - the CTA barrier, the barrier warp's gpu-scope fence + arrival, and then ONE system
+                 * fence and a st.release.sys by the thread that publishes the plane (release is cumulative). A
+                 * __threadfence_system() in every forwarding thread put a system round trip on the critical path of
+                 * every hyper-plane that touches the top plane: 13.2 -> see profiles/ ms per iteration on two GPUs */
             }
         }
     }
@@ -720,6 +727,12 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
             have = true;
         }
     }
+    /* how far the slab below is known to have got (its FWD flag as last read; uniform across the CTA). The flag is
+     * read with a system-scope acquire - about a microsecond - so it is read only when the next hyper-plane is not
+     * yet covered by what is known: the slab below starts own_z0 planes earlier and publishes in steps of
+     * SLAB_PUBLISH_EVERY planes, so one read usually covers many planes. */
+    __shared__ unsigned long long s_fwd_seen;
+    unsigned long long fwd_known = 0;
     for (int h = s.plane_first; h < s.plane_last; h++)
     {
         const int b = s.plane_starts[h], e = s.plane_starts[h + 1];
@@ -727,11 +740,13 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
         /* slab mode works on GLOBAL coordinates: local plane h IS hyper-plane x+y+z = h of the whole volume.
          * Its voxels on the bottom own plane (z = own_z0) have their -z neighbour in the slab below, on
          * hyper-plane h-1: wait until that slab has published it. */
-        if (has_dn && e > b && h >= lk.own_z0 && h <= lk.own_z0 + lk.inplane_span)
+        if (has_dn && e > b && h >= lk.own_z0 && h <= lk.own_z0 + lk.inplane_span
+            && fwd_known < fwd_base + (unsigned long long)h)
         {
             if (leader)
-                slab_wait(lk.flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h, lk.error);
+                s_fwd_seen = slab_wait(lk.flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h, lk.error);
             __syncthreads();
+            fwd_known = s_fwd_seen; /* rewritten at the earliest after this plane's own CTA barrier */
         }
         if (worker)
         {
@@ -769,9 +784,12 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
         }
         /* hyper-plane h is done everywhere on this GPU: tell the slab above (only the planes that hold voxels of
          * the top own plane z = own_z1 - 1 matter to it) */
-        if (has_up && leader && blockIdx.x == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span)
+        if (has_up && leader && blockIdx.x == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span
+            && ((h - (lk.own_z1 - 1)) % SLAB_PUBLISH_EVERY == SLAB_PUBLISH_EVERY - 1 || h == lk.own_z1 - 1 + lk.inplane_span))
         {
-            __threadfence_system();
+            /* one release per SLAB_PUBLISH_EVERY hyper-planes: the slab above runs that many planes later (a constant
+             * lag, tens of microseconds per sweep) and this warp pays the system-scope release a quarter as often.
+             * st.release.sys is the fence (cumulative over everything ordered before it by the barriers above). */
             st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h + 1);
         }
     }
