@@ -1689,6 +1689,11 @@ int fabber_cuda_vb_spatial_multi(const fabber_cuda_vb_problem *prob, int n_parts
                                                                               : prob->nx + prob->ny - 2;
         lk.flags = flags[r];
         lk.error = err[r];
+        {
+            /* developer knob: FABBER_B200_SLAB_FORWARD=direct restores forwarding by the voxel threads */
+            const char *fw = getenv("FABBER_B200_SLAB_FORWARD");
+            lk.forward_late = (fw && std::string(fw) == "direct") ? 0 : 1;
+        }
         lk.up_pos = (r + 1 < W) ? up_pos : nullptr;
         /* small slabs: planes hold few voxels, and the grid-wide barrier gets cheaper with every CTA less; ranks
          * that share a device (tests on one GPU) must all be co-resident, they spin on each other's flags */

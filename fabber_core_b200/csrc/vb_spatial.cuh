@@ -77,6 +77,10 @@ struct SlabLinks
     double *mail[SLAB_MAX_WORLD]; /* every slab's mailbox [2][world][2P] (peer memory; own included) */
     unsigned long long *mail_flags[SLAB_MAX_WORLD]; /* every slab's flag block */
     int *error; /* set to 1 when a spin ran out of budget */
+    /* 1: the sweep's top plane is forwarded by the idle lanes of the barrier warp one hyper-plane LATER, from the
+     * means the voxel threads stored locally (default); 0: by the voxel threads themselves as they finish a voxel.
+     * See sp_sweep_kernel. */
+    int forward_late;
 };
 
 FAB_DEV unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -677,7 +681,7 @@ template <int P, bool IGNORE, bool SLAB> struct SweepVoxel
 #pragma unroll
         for (int i = 0; i < P; i++)
             __stcg(a.mean + i * N + v, mn[i]);
-        if (SLAB && s.link.up_pos)
+        if (SLAB && s.link.up_pos && !s.link.forward_late)
         {
             /* top own plane of a z-slab: the slab above sweeps this voxel's +z neighbour one hyper-plane later
              * and must see THIS sweep's value - store it straight into that slab's lower ghost voxel */
@@ -733,6 +737,30 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
      * SLAB_PUBLISH_EVERY planes, so one read usually covers many planes. */
     __shared__ unsigned long long s_fwd_seen;
     unsigned long long fwd_known = 0;
+    /* Late forwarding (lk.forward_late). A voxel thread that stores its fresh mean straight into the slab above puts
+     * an NVLink round trip into this plane's barrier: the barrier warp's fence cannot complete before those remote
+     * stores are acknowledged (about 2 us on each of the ~510 hyper-planes that touch the top plane - measured as
+     * 6.1 -> 7.4 us per plane on two / eight GPUs against 4.9 us on one). Instead the 31 idle lanes of the barrier warp
+     * copy the top-plane voxels of the PREVIOUS hyper-plane (already stored locally, visible after its barrier) into
+     * the slab above WHILE the voxel threads work on the current one; the current plane's barrier then orders those
+     * stores before the flag. The slab above runs one more hyper-plane behind - a constant lag. */
+    const bool late = has_up && lk.forward_late != 0 && lk.up_pos != nullptr;
+    const bool helper = threadIdx.x > SP_SWEEP_WORKERS;
+    int pending = -1; /* hyper-plane finished on this GPU whose top-plane voxels are not forwarded yet (uniform) */
+    auto forward_plane = [&](int q) {
+        const size_t N = (size_t)s.v.N;
+        const int pb = s.plane_starts[q], pe = s.plane_starts[q + 1];
+        const int lanes = SP_SWEEP_BLOCK - SP_SWEEP_WORKERS - 1;
+        for (int i = pb + blockIdx.x * lanes + (threadIdx.x - SP_SWEEP_WORKERS - 1); i < pe; i += gridDim.x * lanes)
+        {
+            const int up = lk.up_pos[i];
+            FAB_CHECK(s.v, up >= -1 && up < lk.up_N, 107);
+            if (up >= 0)
+#pragma unroll
+                for (int k = 0; k < P; k++)
+                    lk.up_mean[(size_t)k * lk.up_N + up] = __ldcg(s.v.mean + k * N + i);
+        }
+    };
     for (int h = s.plane_first; h < s.plane_last; h++)
     {
         const int b = s.plane_starts[h], e = s.plane_starts[h + 1];
@@ -748,6 +776,8 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
             __syncthreads();
             fwd_known = s_fwd_seen; /* rewritten at the earliest after this plane's own CTA barrier */
         }
+        if (late && pending >= 0 && helper && e > b)
+            forward_plane(pending);
         if (worker)
         {
             if (have)
@@ -784,7 +814,7 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
         }
         /* hyper-plane h is done everywhere on this GPU: tell the slab above (only the planes that hold voxels of
          * the top own plane z = own_z1 - 1 matter to it) */
-        if (has_up && leader && blockIdx.x == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span
+        if (has_up && !late && leader && blockIdx.x == 0 && h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span
             && ((h - (lk.own_z1 - 1)) % SLAB_PUBLISH_EVERY == SLAB_PUBLISH_EVERY - 1 || h == lk.own_z1 - 1 + lk.inplane_span))
         {
             /* one release per SLAB_PUBLISH_EVERY hyper-planes: the slab above runs that many planes later (a constant
@@ -792,7 +822,19 @@ __global__ void __launch_bounds__(SP_SWEEP_BLOCK, 1) sp_sweep_kernel(const __gri
              * st.release.sys is the fence (cumulative over everything ordered before it by the barriers above). */
             st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)h + 1);
         }
+        if (late && sync)
+        {
+            /* this barrier also completed the helpers' forwarding of `pending` (their stores precede this plane's
+             * CTA barrier, the barrier warp's fence and arrival): publish it, then this plane becomes pending */
+            if (pending >= 0 && leader && blockIdx.x == 0
+                && ((pending - (lk.own_z1 - 1)) % SLAB_PUBLISH_EVERY == SLAB_PUBLISH_EVERY - 1
+                       || pending == lk.own_z1 - 1 + lk.inplane_span))
+                st_release_sys(lk.up_flags + SLAB_FLAG_FWD, fwd_base + (unsigned long long)pending + 1);
+            pending = (h >= lk.own_z1 - 1 && h <= lk.own_z1 - 1 + lk.inplane_span) ? h : -1;
+        }
     }
+    if (late && pending >= 0 && helper)
+        forward_plane(pending); /* the last one: ordered before the final flag by the end-of-sweep barrier below */
     if (!slab)
         return;
     /* ---- end of the sweep ------------------------------------------------------------------------------
