@@ -46,14 +46,25 @@ def _runner():
     return oracle.run
 
 
-def _worker(rank, world, port, y, img, tmp):
+def _spec(case, T):
+    """the problems whose voxels are independent: VB (white noise, image prior), NLLS, two-echo AR(1)"""
+    if case == "vb":
+        return abi.ProblemSpec("poly", T, degree=2, prior_types=["N", "N", "I"], need_f=True, convergence="pointzeroone")
+    if case == "nlls":
+        return abi.ProblemSpec("poly", T, degree=2, method="nlls")
+    if case == "ar2":
+        return abi.ProblemSpec("poly", T, degree=2, noise="ar", num_echoes=2, ar_cross_terms="dual", need_f=True,
+                               max_iterations=4)
+    raise ValueError(case)
+
+
+def _worker(rank, world, port, y, img, tmp, case="vb"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        mk = lambda: abi.ProblemSpec("poly", y.shape[0], degree=2, prior_types=["N", "N", "I"], need_f=True,
-                                     convergence="pointzeroone")
-        local = shard.run_sharded(_runner(), mk, y, rank, world, image_priors={2: img})
+        mk = lambda: _spec(case, y.shape[0])
+        local = shard.run_sharded(_runner(), mk, y, rank, world, image_priors={2: img} if case == "vb" else None)
         lo, hi = shard.voxel_range(y.shape[1], rank, world)
         assert local["mean"].shape == (3, hi - lo)
         full = shard.gather_results(local, y.shape[1], rank, world, dst=0)
@@ -66,13 +77,14 @@ def _worker(rank, world, port, y, img, tmp):
         dist.destroy_process_group()
 
 
-def test_two_rank_shards_reproduce_the_single_process_run(tmp_path):
-    y = synth.poly_volume(401, 30, 2, seed=51).numpy()  # odd count: uneven shards
+@pytest.mark.parametrize("case", ["vb", "nlls", "ar2"])
+def test_two_rank_shards_reproduce_the_single_process_run(tmp_path, case):
+    y = synth.poly_volume(401 if case == "vb" else 91, 30, 2, seed=51).numpy()  # odd counts: uneven shards
     img = np.linspace(-1e-3, 1e-3, y.shape[1])
     tmp = str(tmp_path / "gathered.npz")
-    mp.spawn(_worker, args=(2, _free_port(), y, img, tmp), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), y, img, tmp, case), nprocs=2, join=True)
     got = np.load(tmp)
-    ref = _runner()(abi.ProblemSpec("poly", 30, degree=2, prior_types=["N", "N", "I"], need_f=True,
-                                    convergence="pointzeroone"), y, image_priors={2: img})
-    for k in ("mean", "cov", "noise", "free_energy", "iterations", "status"):
-        assert np.array_equal(got[k], ref[k]), k
+    ref = _runner()(_spec(case, 30), y, image_priors={2: img} if case == "vb" else None)
+    keys = ("mean", "cov", "iterations", "status") + (() if case == "nlls" else ("noise", "free_energy"))
+    for k in keys:
+        assert np.array_equal(got[k], ref[k], equal_nan=True), k
