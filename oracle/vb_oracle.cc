@@ -21,14 +21,19 @@
  *   priors.cc:108-181 (Default/Image/ARD), :221-488 (SpatialPrior)
  *   convergence.cc:34-378, convergence.h
  *   dist_mvn.cc:57-100,197-265, dist_gamma.cc:21-33, tools.cc:87-98 (gammaln)
+ *   inference_nlls.cc:57-293 (NLLSInferenceTechnique, NLLSCF) - see the NLLS section for its optimiser
  *
  * Third-party arithmetic that is NOT in the reference tree (FSL armawrap/NEWMAT and
  * MISCMATHS::digamma, un-pinned - see DESIGN.md "oracle"): matrix inverse and log-determinant are
  * restated as LU with partial pivoting; digamma is restated as Bernardo's AS 103 evaluated in
  * single precision (the FSL signature is `float digamma(const float)`). Free energy therefore has
  * "parity unpinned" status with respect to the original binary: no golden in the reference pins it.
+ * The NLLS optimiser is a third FSL dependency outside the tree (MISCMATHS::nonlin): restated from its published
+ * algorithm and pinned by the reference's golden test/outdata_linear_nlls (means, z-statistics, finalMVN; the golden
+ * tells Levenberg from Levenberg-Marquardt and reproduces the reference's own 1e-4 convergence error to 6e-6);
+ * "parity unpinned" beyond that linear case - oracle/_ref cannot run NLLS (built with NO_NLLS).
  *
- * Pinned against: test/outdata_linear_vb and test/outdata_poly goldens on the 18 voxels of
+ * Pinned against: test/outdata_linear_vb, test/outdata_linear_nlls and test/outdata_poly goldens on the 18 voxels of
  * test/test_data_small.nii.gz (tests/test_oracle_golden.py), test/test_convergence.cc sequences
  * (tests/test_convergence.py), test/test_priors.cc and test/test_spatialvb.cc expectations.
  */
