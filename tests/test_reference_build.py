@@ -277,3 +277,20 @@ def test_ar1_noise_two_echoes(cross, tmp_path):
     ref1 = oracle.run(abi.ProblemSpec("linear", 120, design=design, noise="ar", num_echoes=2, ar_cross_terms=cross,
                                       max_iterations=1, need_f=True), y)
     check_against_oracle(one, ref1, 3, nA + 2, tol=1e-10)
+
+
+def test_ar1_noise_two_echoes_nonlinear_model_and_ard():
+    """two echoes under a NON-linear model (the Jacobian changes every iteration, so the alpha matrices meet a new J
+    each time) with an ARD prior on one parameter: the oracle against the reference's own code"""
+    rng = np.random.default_rng(65)
+    T, N = 80, 20
+    t = np.arange(T) * 0.05
+    amp, r = rng.uniform(5, 10, N), rng.uniform(0.5, 2.0, N)
+    y = (amp * np.exp(-r * t[:, None]) + 0.05 * rng.standard_normal((T, N))).astype(np.float32)
+    run = run_ref({"model": "exp", "num-exps": 1, "dt": 0.05, "noise": "ar", "num-echoes": 2, "ar1-cross-terms": "same",
+                   "method": "vb", "max-iterations": 6, "param-spatial-priors": "NA"}, y, (5, 2, 2))
+    ref = oracle.run(abi.ProblemSpec("exp", T, num_exps=1, dt=0.05, noise="ar", num_echoes=2, ar_cross_terms="same",
+                                     max_iterations=6, prior_types=["N", "A"], need_f=True), y)
+    mvn, n_cov = check_against_oracle(run, ref, 2, 3 + 2, tol=1e-7)
+    for i in range(3):
+        assert rel(mvn[n_cov + 2 + i], ref["noise"][4 + i], scale=1e-2) < 1e-7, "alpha %d" % i
