@@ -46,8 +46,9 @@ FAB_DEV double nlls_cf(const VbArgs &a, const typename Model::Ctx &mc, int v, co
 }
 
 /* ReCentre about c fused with the Gauss-Newton sums over the unmasked samples: S.A = J'J, S.b = J'(y - g).
+ * (ALL_SAMPLES: masked ones too - the final precision, see the kernel.)
  * Returns 0 or FABBER_VOX_NONFINITE_* (every sample is looked at, masked or not: ReCentre comes before MaskRows) */
-template <class Model>
+template <class Model, bool ALL_SAMPLES = false>
 FAB_DEV int nlls_jacobian(const VbArgs &a, const typename Model::Ctx &mc, int v, const double (&c)[Model::P],
     Stats<Model::P> &S)
 {
@@ -88,7 +89,7 @@ FAB_DEV int nlls_jacobian(const VbArgs &a, const typename Model::Ctx &mc, int v,
             J[i] = (gp[i] - gn[i]) * rden[i];
             bad_j = bad_j || !finite_d(J[i]);
         }
-        if (a.pattern && a.pattern[t] == FAB_PAT_MASKED)
+        if (!ALL_SAMPLES && a.pattern && a.pattern[t] == FAB_PAT_MASKED)
             continue;
         S.add((double)__ldg(yp + (size_t)t * stride) - g, J);
     }
@@ -192,7 +193,9 @@ __global__ void __launch_bounds__(VB_BLOCK) nlls_kernel(const __grid_constant__ 
         cov[i] = 0.0;
     if (status == 0)
     {
-        const int err = nlls_jacobian<Model>(a, mc, v, p, S);
+        /* QUIRK KEPT: inference_nlls.cc:172 calls MaskRows(J, ..) and drops its result, so this J'J is over ALL
+         * samples, masked ones included, while sqerr and the degrees of freedom leave them out */
+        const int err = nlls_jacobian<Model, true>(a, mc, v, p, S);
         if (err)
             status = err;
         else

@@ -2156,12 +2156,16 @@ int nlls_run(const fabber_cuda_vb_problem *prob, const fabber_cuda_vb_buffers *b
             const real sqerr = cost.cf(p);
             const real mse = sqerr / (Nsamples - P);
             Mat prec(P, P);
+            // QUIRK KEPT: `MaskRows(J, m_masked_tpoints);` at inference_nlls.cc:172 takes J by value and its result is
+            // discarded, so the precision is built from the Jacobian of ALL samples - masked ones included - while
+            // sqerr and the degrees of freedom leave them out (found by running the reference's own code,
+            // tests/test_reference_build.py::test_nlls_poly_masked_timepoints)
             for (int i = 0; i < P; i++)
                 for (int j = 0; j < P; j++)
                 {
                     real h = 0;
-                    for (size_t k = 0; k < cost.keep.size(); k++)
-                        h += lin.J(cost.keep[k], i) * lin.J(cost.keep[k], j);
+                    for (int t = 0; t < T; t++)
+                        h += lin.J(t, i) * lin.J(t, j);
                     prec(i, j) = h / mse;
                 }
             for (int i = 0; i < P; i++)

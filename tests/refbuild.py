@@ -9,15 +9,21 @@ from fabber_core_b200 import fabber as fab
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libfabbercore_ref.so")
+# the same sources plus inference_nlls.cc, built against the stand-in for FSL's MISCMATHS::nonlin (oracle/_shim)
+REF_NLLS_LIB = os.path.join(ROOT, "oracle", "_ref", "libfabbercore_ref_nlls.so")
 
 
 def available():
     return os.path.exists(REF_LIB)
 
 
+def nlls_available():
+    return os.path.exists(REF_NLLS_LIB)
+
+
 class ReferenceFabber(fab.Fabber):
-    def __init__(self):
-        fab.Fabber.__init__(self, lib=REF_LIB)
+    def __init__(self, lib=None):
+        fab.Fabber.__init__(self, lib=lib or REF_LIB)
 
     def _new_handle(self):
         fab.Fabber._new_handle(self)
