@@ -85,3 +85,53 @@ def test_nlls_random_configurations(seed):
         gpu, ref, probes, truth = both(name, T, spec, y)
         label = "fuzz nlls %d: %s P%d T%d lm=%s" % (seed, name, P, T, spec["nlls_lm"])
         compare(gpu, ref, P, probes, truth=truth, check_f=False, label=label, max_ambiguous=0.25)
+
+
+@pytest.mark.parametrize("seed", range(4))
+def test_spatial_random_configurations(seed):
+    """method=spatialvb on odd little volumes: random prior-type strings over M / m / P / p / N / A, holes in the
+    mask, one to three spatial dimensions, update-on-first-iteration, a speed limit (the draw of
+    tests/test_reference_fuzz.py, where the oracle side is pinned on the reference's own code)"""
+    rng = np.random.default_rng(6000 + seed)
+    for _ in range(6):
+        nx, ny, nz = int(rng.integers(2, 9)), int(rng.integers(2, 7)), int(rng.integers(1, 6))
+        n = nx * ny * nz
+        T = int(rng.integers(12, 30))
+        if rng.random() < 0.5:
+            deg = int(rng.integers(0, 3))
+            P = deg + 1
+            i = np.arange(1, T + 1)[:, None]
+            y = sum(rng.normal(0, 1, n) * (i / T) ** k * 5 for k in range(P)) + 10 + rng.normal(0, 1, (T, n))
+            name, spec = "poly", dict(degree=deg)
+        else:
+            P = int(rng.integers(1, 4))
+            design = rng.normal(0, 1, (T, P))
+            y = design @ rng.normal(0, 5, (P, n)) + rng.normal(0, 1, (T, n))
+            name, spec = "linear", dict(design=design)
+        y = y.astype(np.float32)
+        mask = rng.random((nx, ny, nz)) > 0.15
+        if mask.sum() < 2:
+            mask[:] = True
+        sel = mask.reshape(-1, order="F")
+        idx = np.arange(n)[sel]
+        coords = np.ascontiguousarray(np.stack([idx % nx, (idx // nx) % ny, idx // (nx * ny)]).astype(np.int32))
+        ys = np.ascontiguousarray(y[:, sel])
+        types = [str(rng.choice(list("MmPpNA"))) for _ in range(P)]
+        spec.update(prior_types=types, spatial_dims=int(rng.integers(1, 4)), max_iterations=int(rng.integers(2, 7)),
+                    need_f=True, update_first_iter=bool(rng.random() < 0.5),
+                    spatial_speed=float(rng.choice([-1.0, -1.0, 2.0, 10.0])))
+
+        def mk():
+            sp = abi.ProblemSpec(name, T, **spec)
+            sp.prob.nx, sp.prob.ny, sp.prob.nz = nx, ny, nz
+            return sp
+
+        ref = oracle.run(mk(), ys, spatial=True, coords=coords)
+        if ref["rc"] != 0:
+            continue   # a draw the reference itself cannot run (tests/test_reference_fuzz.py checks that agreement)
+        probes = [oracle.run(mk(), ys, spatial=True, coords=coords, variant="fma")]
+        truth = oracle.run(mk(), ys, spatial=True, coords=coords, variant="ld")
+        gpu = device.run(mk(), ys, spatial=True, coords=coords)
+        label = "fuzz spatial %d: %s P%d %dx%dx%d %s dims %d" % (seed, name, P, nx, ny, nz, "".join(types), spec["spatial_dims"])
+        compare(gpu, ref, P, probes, truth=truth, label=label, max_ambiguous=0.25)
+        assert np.max(np.abs(gpu["spatial_ak"] - ref["spatial_ak"]) / np.maximum(np.abs(ref["spatial_ak"]), 1e-300)) < 1e-5, label
