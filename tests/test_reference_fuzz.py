@@ -4,7 +4,7 @@ damping rules - through the reference's OWN code (oracle/_ref, compiled from its
 restated oracle, compared voxel by voxel in double. The hand-picked cases of tests/test_reference_build.py pin what
 was thought of; this looks for what was not (it is how the masked-Jacobian quirk of inference_nlls.cc:172 would have
 been found, had it not been found by hand first). Seeds are fixed: the
-120 VB + 40 NLLS + 40 spatial configurations are the same every run."""
+300 VB + 80 NLLS + 120 spatial configurations are the same every run."""
 import numpy as np
 import pytest
 
@@ -42,7 +42,7 @@ def draw_model(rng, tmp_path, T):
     return "linear", P, y, {"model": "linear", "basis": path}, dict(design=design)
 
 
-@pytest.mark.parametrize("seed", range(10))
+@pytest.mark.parametrize("seed", range(25))
 def test_vb_random_configurations(seed, tmp_path):
     rng = np.random.default_rng(1000 + seed)
     for _ in range(12):
@@ -78,6 +78,7 @@ def test_vb_random_configurations(seed, tmp_path):
         f = refbuild.ReferenceFabber()
         f.run_with_data(opts, {"data": refbuild.volume(y, SHAPE)})
         mvn, F = f.doubles("finalMVN", N), f.doubles("freeEnergy", N)[0]
+        f._destroy_handle()   # NOW: fabber_destroy tears the reference's factories down, a late __del__ would do that under the next run
         ref = oracle.run(abi.ProblemSpec(name, T, **spec), y)
         n_all = P + n_noise
         n_cov = n_all * (n_all + 1) // 2
@@ -89,12 +90,12 @@ def test_vb_random_configurations(seed, tmp_path):
             assert rel(mvn[n_cov + i][ok], ref["mean"][i][ok], std[i][ok]) < 1e-7, ("mean", i, opts)
             assert rel(mvn[tri(i, i)][ok], ref["cov"][tri(i, i)][ok], 1e-300) < 1e-7, ("var", i, opts)
         assert rel(F[ok], ref["free_energy"][ok], 1.0) < 1e-7, ("F", opts)
-        if noise == "white":   # white noise: bit-identical or last-bit differences
+        if noise == "white" and name != "exp":   # white noise, linear-in-parameter models: last-bit differences at most
             assert all(rel(mvn[n_cov + i][ok], ref["mean"][i][ok], std[i][ok]) < 1e-11 for i in range(P)), opts
 
 
 @pytest.mark.skipif(not refbuild.nlls_available(), reason="oracle/_ref/libfabbercore_ref_nlls.so not built")
-@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("seed", range(10))
 def test_nlls_random_configurations(seed, tmp_path):
     rng = np.random.default_rng(2000 + seed)
     for _ in range(8):
@@ -114,6 +115,7 @@ def test_nlls_random_configurations(seed, tmp_path):
         f = refbuild.ReferenceFabber(lib=refbuild.REF_NLLS_LIB)
         f.run_with_data(opts, {"data": refbuild.volume(y, SHAPE)})
         mvn = f.doubles("finalMVN", N)
+        f._destroy_handle()
         ref = oracle.run(abi.ProblemSpec(name, T, **spec), y)
         n_cov = P * (P + 1) // 2
         assert mvn.shape[0] == n_cov + P + 1 and np.all(ref["status"] == 0), opts
@@ -123,7 +125,7 @@ def test_nlls_random_configurations(seed, tmp_path):
             assert rel(mvn[tri(i, i)], ref["cov"][tri(i, i)], 1e-300) < 1e-6, ("var", i, opts)
 
 
-@pytest.mark.parametrize("seed", range(5))
+@pytest.mark.parametrize("seed", range(15))
 def test_spatial_random_configurations(seed, tmp_path):
     """method=spatialvb: random prior-type strings over M / m / P / p / N / A, holes in the mask, spatial-dims,
     update-spatial-prior-on-first-iteration, a speed limit - the ordered sweep and the aK updates of the reference's
@@ -176,10 +178,12 @@ def test_spatial_random_configurations(seed, tmp_path):
             # a configuration the reference itself cannot run (e.g. a blown-up aK makes F non-finite): the oracle
             # must stop with a numerical failure too, not sail through
             n_failed += 1
+            f._destroy_handle()
             assert ref["rc"] != 0, (str(e), opts)
             continue
         nv = int(sel.sum())
         mvn, F = f.doubles("finalMVN", nv), f.doubles("freeEnergy", nv)[0]
+        f._destroy_handle()
         n_all = P + 1
         n_cov = n_all * (n_all + 1) // 2
         assert np.all(ref["status"] == 0), opts
