@@ -53,7 +53,7 @@ struct FabberRunDataError : FabberError
 struct InvalidOptionValue : FabberRunDataError
 {
     InvalidOptionValue(const std::string &key, const std::string &value, const std::string &reason)
-        : FabberRunDataError("Invalid value for option " + key + ": " + value + " (" + reason + ")")
+        : FabberRunDataError("Invalid value given for option: " + key + "=" + value + " (" + reason + ")") /* rundata.h:730 */
     {
     }
 };
@@ -67,7 +67,7 @@ struct MandatoryOptionMissing : FabberRunDataError
 struct DataNotFound : FabberRunDataError
 {
     explicit DataNotFound(const std::string &key)
-        : FabberRunDataError("Data not found: " + key)
+        : FabberRunDataError("Voxel data not found: " + key + " ()") /* rundata.h:756 */
     {
     }
 };

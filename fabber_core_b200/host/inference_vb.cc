@@ -205,7 +205,7 @@ void Vb::Initialize(FwdModel *model, FabberRunData &rundata)
     else if (noise == "ar")
         m_ar = true;
     else
-        throw InvalidOptionValue("noise", noise, "Unrecognized noise model (white, ar)");
+        throw InvalidOptionValue("noise", noise, "Unrecognized noise type");
     m_saveF = rundata.GetBool("save-free-energy");
     m_saveFsHistory = rundata.GetBool("save-free-energy-history");
     m_printF = rundata.GetBool("print-free-energy");
@@ -354,8 +354,8 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
             ConvergenceDetector::NewFromName(rundata.GetStringDefault("convergence", "maxits")));
         detector->Initialize(rundata);
         detector->Describe(prob);
-        if (rundata.GetIntDefault("max-trials", 10) <= 0)
-            throw InvalidOptionValue("max-trials", rundata.GetString("max-trials"), "Must be positive");
+        /* (max-trials is validated by the trial-mode detector only, convergence.cc:147-149) */
+        rundata.GetIntDefault("spatial-dims", 3, 0, 3); /* range-checked here first, as Vb::Initialize does (inference_vb.cc:119) */
         /* priors (priors.cc:490-528): the factory validates every parameter's prior type and options (image data
          * present, spatial-dims / speed in range); the types themselves travel in prob.params[] */
         {
@@ -364,6 +364,10 @@ void Vb::Prepare(FabberRunData &rundata, VoxelData &data)
                 delete priors[i];
         }
     }
+    /* locked-linear-from-mvn is loaded by every Vb run, spatial or not (inference_vb.cc:171-178) - a missing data set
+     * is an error even where the centres are then not used (only the spatial method honours them, :695 vs :443) */
+    if (!m_nlls && rundata.GetStringDefault("locked-linear-from-mvn", "") != "")
+        rundata.GetVoxelData(rundata.GetString("locked-linear-from-mvn"));
     const bool spatial = !m_nlls && IsSpatial(rundata, params);
     const bool useF = !spatial && prob.conv_type != FABBER_CONV_MAXITS;
     m_needF = !m_nlls && (useF || m_printF || m_saveF || m_saveFsHistory); /* inference_vb.cc:242 */

@@ -163,7 +163,7 @@ void CountingConvergenceDetector::Initialize(FabberRunData &params)
 {
     m_max_its = params.GetIntDefault("max-iterations", 10);
     if (m_max_its <= 0)
-        throw InvalidOptionValue("max-iterations", stringify(m_max_its), "Must be positive");
+        throw InvalidOptionValue("max_iterations", stringify(m_max_its), "Must be positive"); /* sic, convergence.cc:39 */
     Reset();
 }
 void CountingConvergenceDetector::Reset(double)
@@ -384,7 +384,7 @@ NoiseModel *NoiseModel::NewFromName(const std::string &name)
         return new WhiteNoiseModel();
     if (name == "ar")
         return new Ar1cNoiseModel();
-    throw InvalidOptionValue("noise", name, "Unrecognized noise model (white, ar)");
+    throw InvalidOptionValue("noise", name, "Unrecognized noise type"); /* noisemodel.cc:29 */
 }
 void NoiseModel::Initialize(FabberRunData &args) { m_masked_tpoints = args.GetIntList("mt", 1); }
 static void device_only(const char *what)
@@ -415,7 +415,7 @@ void WhiteNoiseModel::Initialize(FabberRunData &args)
         else if (ch >= 'a' && ch <= 'z')
             m_digits.push_back(ch - 'a' + 10);
         else
-            throw InvalidOptionValue("noise-pattern", m_pattern, "Invalid character in pattern");
+            throw InvalidOptionValue("noise-pattern", std::string(1, ch), "Invalid character"); /* noisemodel_white.cc:191 */
     }
     if (m_digits.empty())
         throw InvalidOptionValue("noise-pattern", m_pattern, "Pattern must not be empty");

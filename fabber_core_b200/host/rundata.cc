@@ -569,7 +569,7 @@ int FabberRunData::GetInt(const std::string &key, int min, int max)
     std::string val = GetString(key);
     int i;
     if (!parse_int(val, i))
-        throw InvalidOptionValue(key, val, "Must be an integer");
+        throw InvalidOptionValue(key, val, "Failed to convert to required type"); /* rundata.h:768 */
     if (i < min)
         throw InvalidOptionValue(key, val, "Minimum " + stringify(min));
     if (i > max)
@@ -585,7 +585,7 @@ double FabberRunData::GetDouble(const std::string &key)
     std::string val = GetString(key);
     double d;
     if (!parse_double(val, d))
-        throw InvalidOptionValue(key, val, "Must be an number");
+        throw InvalidOptionValue(key, val, "Failed to convert to required type"); /* rundata.h:768 */
     return d;
 }
 double FabberRunData::GetDoubleDefault(const std::string &key, double def)

@@ -19,20 +19,24 @@ def run(extra):
 
 @pytest.mark.parametrize("extra, fragments", [
     ({"convergence": "nosuch"}, ("convergence", "Unrecognized convergence detector")),
-    ({"noise-pattern": "1?2"}, ("noise-pattern", "Invalid character in pattern")),
+    ({"noise-pattern": "1?2"}, ("noise-pattern=?", "Invalid character")),
     ({"mt1": "13"}, ("mt", "beyond the end of the data")),                      # 12 time points
     ({"noise": "ar", "mt1": "2"}, ("AR noise model does not support masked time points",)),
     ({"noise": "ar", "num-echoes": "3"}, ("num-echoes", "Must be 1 or 2")),
     ({"noise": "ar", "num-echoes": "2", "ar1-cross-terms": "both"}, ("ar1-cross-terms", "Must be dual, same or none")),
     ({"noise": "ar", "ar1-cross-terms": "dual"}, ("ar1-cross-terms", "ar1-cross-terms=none with num-echoes=1")),
-    ({"noise": "pink"}, ("noise", "Unrecognized noise model")),
+    ({"noise": "pink"}, ("noise=pink", "Unrecognized noise type")),
     ({"prior-noise-stddev": "-2"}, ("prior-noise-stddev", "Must be > 0")),
     ({"model": "nosuch"}, ("model", "Unrecognized forward model")),
     ({"method": "mcmc"}, ("method", "Unrecognized inference method")),
     ({"method": "nlls", "fwd-inital-posterior": "/nonexistent/file.mat"}, ("Could not read matrix file",)),
     ({"degree": "-1"}, ("degree", "Minimum 0")),
-    ({"max-iterations": "0"}, ("max-iterations", "Must be positive")),
-    ({"method": "spatialvb", "param-spatial-priors": "M+", "spatial-dims": "4"}, ("spatial-dims", "Must be 0, 1, 2 or 3")),
+    ({"max-iterations": "0"}, ("max_iterations=0", "Must be positive")),          # sic: convergence.cc:39
+    ({"convergence": "lm", "max-iterations": "0"}, ("max-iterations=0", "Must be positive")),
+    ({"convergence": "trialmode", "max-trials": "0"}, ("max-trials=0", "Must be positive")),
+    ({"degree": "abc"}, ("degree=abc", "Failed to convert to required type")),
+    ({"locked-linear-from-mvn": "nosuch"}, ("Voxel data not found: nosuch",)),
+    ({"method": "spatialvb", "param-spatial-priors": "M+", "spatial-dims": "4"}, ("spatial-dims=4", "Maximum 3")),
 ])
 def test_invalid_options_are_refused_before_any_device_work(extra, fragments):
     with pytest.raises(fab.FabberException) as e:
