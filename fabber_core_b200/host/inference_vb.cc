@@ -113,7 +113,8 @@ void Vb::GetOptions(std::vector<OptionSpec> &opts, const std::string &method)
         { "vb-init", OPT_BOOL, "Whether NLLS is being run in isolation or as a pre-step for VB", true, "" },
         { "lm", OPT_BOOL, "Whether to use LM convergence (default is L)", true, "" },
     };
-    for (size_t i = 0; i < sizeof(O) / sizeof(O[0]); i++)
+    const size_t listed = 1; /* the reference's table has both, its NUM_OPTIONS lists the first (--lm works all the same) */
+    for (size_t i = 0; i < listed; i++)
         opts.push_back(O[i]);
 }
 void Vb::GetOptions(std::vector<OptionSpec> &opts)
@@ -150,6 +151,9 @@ void Vb::GetOptions(std::vector<OptionSpec> &opts)
         { "PSP_byname<n>_transform", OPT_STR, "Transform to apply to parameter <n>", true, "" },
         { "allow-bad-voxels", OPT_BOOL, "Continue if numerical error found in a voxel, rather than stopping", true,
             "" },
+        { "mcsteps", OPT_INT, "Number of motion correction steps (motion correction is compiled out of the reference too)",
+            true, "0" },
+        { "distance-measure", OPT_STR, "", true, "dist1" },
         { "ar1-cross-terms", OPT_STR, "For AR1 noise, type of cross-linking (dual, same or none)", true, "dual" },
         { "spatial-dims", OPT_INT, "Number of spatial dimensions", true, "3" },
         { "spatial-speed", OPT_STR, "Restrict speed of spatial smoothing", true, "-1" },

@@ -1126,25 +1126,45 @@ void FabberRunData::GetVoxelDataArray(const std::string &key, float *data)
 
 void FabberRunData::GetOptions(std::vector<OptionSpec> &opts)
 {
-    /* the VB-relevant subset of rundata.cc:139-201 */
+    /* the general options, same names / types / order / defaults as rundata.cc:139-201 (what fabber_get_options
+     * and --help list; the descriptions are this library's own wording) */
     static const OptionSpec O[] = {
+        { "help", OPT_BOOL, "Print usage; with --method or --model, the usage of that method / model", true, "" },
+        { "listmethods", OPT_BOOL, "List the known inference methods", true, "" },
+        { "listmodels", OPT_BOOL, "List the known forward models", true, "" },
+        { "listparams", OPT_BOOL, "List the model's parameters (needs the model's configuration options)", true, "" },
+        { "descparams", OPT_BOOL, "Describe the model's parameters: name, description, units (needs the model's options)", true, "" },
+        { "listoutputs", OPT_BOOL, "List the model's additional outputs (needs the model's configuration options)", true, "" },
+        { "evaluate", OPT_STR, "Evaluate the model: name of the output wanted, or blank for the prediction; needs the model's options, --evaluate-params and --evaluate-nt", true, "" },
+        { "evaluate-params", OPT_MATRIX, "Parameter values for the evaluation", true, "" },
+        { "evaluate-nt", OPT_INT, "Number of time points for the evaluation", true, "" },
+        { "simple-output", OPT_BOOL, "Print only progress lines (percentages) on standard output", true, "" },
+        { "output", OPT_STR, "Directory for the output files (including the logfile)", false, "" },
+        { "overwrite", OPT_BOOL, "Overwrite an existing output directory instead of appending '+' to its name", true, "" },
+        { "link-to-latest", OPT_BOOL, "Try to create a link <output>_latest to the most recent output directory", true, "" },
         { "method", OPT_STR, "Use this inference method", false, "" },
         { "model", OPT_STR, "Use this forward model", false, "" },
-        { "data", OPT_TIMESERIES, "Main voxel data", false, "" },
+        { "loadmodels", OPT_FILE, "Load forward models from this shared library (device model plug-ins, include/fabber_model_plugin.h)", true, "" },
+        { "data", OPT_TIMESERIES, "The single input data file", false, "" },
+        { "data<n>", OPT_TIMESERIES, "Several input data files, n = 1, 2, 3...", true, "" },
+        { "data-order", OPT_STR, "How several data files are combined: concatenate (one after the other) or interleave (first sample of each, then the second, ...)", true, "interleave" },
         { "mask", OPT_IMAGE, "Mask: inference will only be performed where mask value > 0", true, "" },
-        { "mt<n>", OPT_INT, "List of masked time points, indexed from 1", true, "" },
+        { "mt<n>", OPT_INT, "List of masked time points, indexed from 1: ignored in the parameter updates", true, "" },
         { "suppdata", OPT_TIMESERIES, "'Supplemental' timeseries data, required for some models", true, "" },
+        { "dump-param-names", OPT_BOOL, "Write paramnames.txt with the names of the model's parameters", true, "" },
+        { "save-model-fit", OPT_BOOL, "Output the model prediction as a 4d volume", true, "" },
+        { "save-residuals", OPT_BOOL, "Output the difference between the data and the model prediction", true, "" },
+        { "save-model-extras", OPT_BOOL, "Output the model's additional timeseries outputs", true, "" },
+        { "save-mvn", OPT_BOOL, "Output the final MVN distributions", true, "" },
         { "save-mean", OPT_BOOL, "Output the parameter means", true, "" },
         { "save-std", OPT_BOOL, "Output the parameter standard deviations", true, "" },
         { "save-var", OPT_BOOL, "Output the parameter variances", true, "" },
         { "save-zstat", OPT_BOOL, "Output the parameter Zstats", true, "" },
-        { "save-noise-mean", OPT_BOOL, "Output the noise means", true, "" },
+        { "save-noise-mean", OPT_BOOL, "Output the noise means (the inferred distribution is the precision of a Gaussian noise source)", true, "" },
         { "save-noise-std", OPT_BOOL, "Output the noise standard deviations", true, "" },
         { "save-free-energy", OPT_BOOL, "Output the free energy, if calculated", true, "" },
-        { "save-model-fit", OPT_BOOL, "Output the model prediction as a 4d volume", true, "" },
-        { "save-residuals", OPT_BOOL, "Output the difference between the data and the model prediction", true, "" },
-        { "save-mvn", OPT_BOOL, "Output the final MVN distributions", true, "" },
-        { "allow-bad-voxels", OPT_BOOL, "Continue if numerical error found in a voxel, rather than stopping", true, "" },
+        { "optfile", OPT_BOOL, "File with further options, one per line, written as on the command line", true, "" },
+        { "debug", OPT_BOOL, "Very verbose logging (the reference's debug output is per voxel; nothing extra is logged here)", true, "" },
     };
     for (size_t i = 0; i < sizeof(O) / sizeof(O[0]); i++)
         opts.push_back(O[i]);

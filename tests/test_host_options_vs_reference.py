@@ -71,3 +71,32 @@ def test_same_verdict_as_the_reference(extra):
         if "mt1=" in head and "noise" in mine:
             return   # AR + masked time points: refused by both, the reference names mt1, this library the noise model
         assert head in mine, (mine, ref)
+
+
+@pytest.mark.parametrize("what", [{}, {"method": "vb"}, {"method": "spatialvb"}, {"method": "nlls"}, {"model": "poly"},
+                                  {"model": "linear"}, {"model": "exp"}], ids=lambda w: ",".join("%s=%s" % kv for kv in w.items()) or "general")
+def test_option_listings_match(what):
+    """fabber_get_options: the same option names with the same type, optional flag and default as the reference lists
+    (the descriptions are this library's own wording and are not compared)"""
+    mine, ref = fab.Fabber(), refbuild.ReferenceFabber(lib=refbuild.REF_NLLS_LIB)
+    try:
+        mo, _ = mine.get_options(**what)
+        ro, _ = ref.get_options(**what)
+    finally:
+        mine._destroy_handle()
+        ref._destroy_handle()
+    key = lambda o: (o["name"], o["type"], o["optional"], o["default"])
+    assert sorted(key(o) for o in mo) == sorted(key(o) for o in ro)
+
+
+def test_method_and_model_listings_match():
+    mine, ref = fab.Fabber(), refbuild.ReferenceFabber(lib=refbuild.REF_NLLS_LIB)
+    try:
+        assert mine.get_methods() == ref.get_methods()
+        assert mine.get_models() == ref.get_models()
+        assert mine.get_model_params({"model": "poly", "degree": 2}) == ref.get_model_params({"model": "poly", "degree": 2})
+        assert mine.get_model_params({"model": "exp", "num-exps": 2, "dt": 0.1}) == ref.get_model_params(
+            {"model": "exp", "num-exps": 2, "dt": 0.1})
+    finally:
+        mine._destroy_handle()
+        ref._destroy_handle()
