@@ -330,7 +330,7 @@ static void test_inference_techniques()
         for (size_t k = 0; k < opts.size(); k++)
         {
             has_noise = has_noise || opts[k].name == "noise";
-            has_lm = has_lm || opts[k].name == "lm";
+            has_lm = has_lm || opts[k].name == "vb-init"; /* the one NLLS option the reference lists (NUM_OPTIONS = 1) */
         }
         CHECK(has_noise == (known[i] != "nlls") && has_lm == (known[i] == "nlls"));
     }
