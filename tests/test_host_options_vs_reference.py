@@ -100,3 +100,22 @@ def test_method_and_model_listings_match():
     finally:
         mine._destroy_handle()
         ref._destroy_handle()
+
+
+def test_model_evaluate_matches(tmp_path):
+    """fabber_model_evaluate (fabber_capi.cc:300-351): the host-side Evaluate of the three models against the
+    reference's own, on random parameters - float32 outputs, identical"""
+    rng = np.random.default_rng(3)
+    basis = str(tmp_path / "ev.mat")
+    np.savetxt(basis, rng.normal(0, 1, (15, 3)), fmt="%.17g")
+    for opts, P, nt in (({"model": "poly", "degree": 3}, 4, 20), ({"model": "exp", "num-exps": 2, "dt": 0.1}, 4, 30),
+                        ({"model": "linear", "basis": basis}, 3, 15)):
+        for _ in range(4):
+            p = rng.uniform(0.1, 3, P).tolist()
+            mine, ref = fab.Fabber(), refbuild.ReferenceFabber(lib=refbuild.REF_NLLS_LIB)
+            try:
+                a, b = np.array(mine.model_evaluate(opts, p, nt)), np.array(ref.model_evaluate(opts, p, nt))
+            finally:
+                mine._destroy_handle()
+                ref._destroy_handle()
+            assert a.shape == b.shape == (nt,) and np.array_equal(a, b), opts
